@@ -1,0 +1,125 @@
+/* zkp_b200.h -- C ABI of the B200-native ristretto255 multi-scalar-multiplication engine.
+ *
+ * The reference (dalek-cryptography/zkp) has no FFI: its hot path is a Rust trait call on a foreign type,
+ *     RistrettoPoint::multiscalar_mul / vartime_multiscalar_mul / optional_multiscalar_mul,
+ *     CompressedRistretto::decompress, RistrettoPoint::compress, IsIdentity::is_identity
+ * (curve25519-dalek ^2, /root/reference/Cargo.toml:27).  Each entry point below names the reference call
+ * site(s) whose work it replaces; INTEGRATION.md shows the Rust `extern "C"` block and the nine-line patch of
+ * zkp's `toolbox` that binds them.
+ *
+ * Conventions
+ *   - scalars: 32 bytes little-endian, canonical (< l = 2^252 + 27742317777372353535851937790883648493),
+ *     i.e. curve25519_dalek::scalar::Scalar::as_bytes().
+ *   - compressed points: 32-byte ristretto255 encodings (CompressedRistretto::as_bytes()).
+ *   - limb-form points: 4 x 5 x uint64, the in-memory layout of dalek's u64-backend
+ *     RistrettoPoint(EdwardsPoint{X,Y,Z,T: FieldElement51}), radix 2^51, limbs < 2^54.
+ *   - all buffers are caller-owned; nothing is retained after a call returns.  Host entry points take host
+ *     pointers (pinned memory recommended) and are synchronous.  `_dev` entry points take device pointers that
+ *     are 16-byte aligned, enqueue on the context's stream and do NOT synchronise.
+ *   - a context is bound to one device and one stream; calls on one context must be serialised by the caller
+ *     (the reference's Prover/Verifier are !Sync as well, /root/reference/src/toolbox/prover.rs:23-31).
+ *   - no entry point aborts or throws across the boundary; every failure is a status code.
+ */
+#ifndef ZKP_B200_H
+#define ZKP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct zkp_ctx zkp_ctx;
+
+/* status codes */
+#define ZKP_OK 0                 /* success                                                                  */
+#define ZKP_ERR_POINT 1          /* some encoding failed to decompress  == `None` of optional_multiscalar_mul,
+                                    mapped to ProofError::VerificationFailure at verifier.rs:166,
+                                    batch_verifier.rs:228                                                    */
+#define ZKP_ERR_SIZE 2           /* inconsistent sizes / null or misaligned pointers == ProofError::BatchSizeMismatch
+                                    (batch_verifier.rs:72-74,120-122,138-140)                                */
+#define ZKP_ERR_SCALAR 3         /* a scalar is not canonical (>= l)                                         */
+#define ZKP_ERR_NOGPU (-1)       /* no CUDA device / CUDA runtime failure while creating the context         */
+#define ZKP_ERR_CUDA (-2)        /* CUDA failure during a call; zkp_last_error() has the text                */
+#define ZKP_ERR_NOMEM (-3)       /* workspace allocation failed                                              */
+
+/* flags for point inputs of zkp_msm_ct_batched */
+#define ZKP_POINTS_COMPRESSED 0  /* 32-byte encodings  */
+#define ZKP_POINTS_LIMBS51 1     /* 4x5xuint64 limb form */
+
+int32_t zkp_device_count(void);
+/* Create a context on CUDA device `device` with its own non-blocking stream. */
+int32_t zkp_ctx_create(zkp_ctx** out, int32_t device);
+void zkp_ctx_destroy(zkp_ctx* ctx);
+/* Enqueue on the caller's stream (a cudaStream_t) from now on; NULL restores the context's own stream. */
+int32_t zkp_ctx_set_stream(zkp_ctx* ctx, void* cuda_stream);
+/* Tunables: "window" (Pippenger window width c, 0 = choose from n), "lanes" (lanes per bucket, 0 = auto). */
+int32_t zkp_ctx_set_option(zkp_ctx* ctx, const char* key, int64_t value);
+int32_t zkp_ctx_synchronize(zkp_ctx* ctx);
+const char* zkp_last_error(zkp_ctx* ctx);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+uint64_t zkp_ctx_launch_count(zkp_ctx* ctx);
+
+/* CompressedRistretto::decompress over a batch.
+ * Replaces the per-point loop at /root/reference/src/toolbox/verifier.rs:87-92 (and the lazy
+ * `.map(|pt| pt.decompress())` at verifier.rs:164, batch_verifier.rs:226 when used stand-alone).
+ * limbs_out[n][4][5] receives (X,Y,Z=1,T) in FieldElement51 form; valid_out[n] is 1 where decoding succeeded
+ * (limbs are the identity where it failed).  Returns ZKP_OK even if some points are invalid.              */
+int32_t zkp_decompress_batch(zkp_ctx* ctx, const uint8_t* enc, size_t n, uint64_t* limbs_out, uint8_t* valid_out);
+
+/* RistrettoPoint::compress over a batch.
+ * Replaces /root/reference/src/toolbox/mod.rs:180 (append_point_var) and :204 (append_blinding_commitment). */
+int32_t zkp_compress_batch(zkp_ctx* ctx, const uint64_t* limbs_in, size_t n, uint8_t* enc_out);
+
+/* One variable-time MSM over compressed points: out32 = compress( sum_i scalars[i] * decompress(points[i]) ).
+ * Replaces RistrettoPoint::optional_multiscalar_mul(...) with `.map(|pt| pt.decompress())` at
+ * /root/reference/src/toolbox/batch_verifier.rs:219-228 and verifier.rs:162-166, and
+ * vartime_multiscalar_mul at verifier.rs:97-106.  The identity test of batch_verifier.rs:230 /
+ * verifier.rs:168 is `out32 == 32 zero bytes` (also returned in *is_identity when non-NULL).
+ * Returns ZKP_ERR_POINT (and the first failing index in *first_bad when non-NULL) where the reference
+ * returns None.  n == 0 yields the identity.                                                              */
+int32_t zkp_msm_vartime(zkp_ctx* ctx, const uint8_t* scalars, const uint8_t* points, size_t n, uint8_t* out32,
+                        int32_t* is_identity, int64_t* first_bad);
+
+/* Same, device-resident and asynchronous.  d_result (device, 48 bytes, 16-aligned) receives
+ *   bytes 0..31 the encoding, int32 @32 status (ZKP_OK / ZKP_ERR_POINT / ZKP_ERR_SCALAR),
+ *   int32 @36 is_identity, int64 @40 first_bad (-1 if none).                                              */
+int32_t zkp_msm_vartime_dev(zkp_ctx* ctx, const void* d_scalars, const void* d_points, size_t n, void* d_result);
+
+/* M independent variable-time MSMs described CSR-style: MSM j uses terms offsets[j] .. offsets[j+1]-1.
+ * Replaces the per-proof loops around vartime_multiscalar_mul (/root/reference/src/toolbox/verifier.rs:96-110)
+ * and optional_multiscalar_mul (verifier.rs:162) when many proofs are verified individually.
+ * out[M][32]; valid[M] = 0 where a point of that MSM failed to decode (== None).                          */
+int32_t zkp_msm_vartime_batched(zkp_ctx* ctx, const uint8_t* scalars, const uint8_t* points,
+                                const uint64_t* offsets, size_t M, uint8_t* out, uint8_t* valid);
+
+/* M independent CONSTANT-TIME MSMs followed by compression: out[j] = compress( sum scalars * points ).
+ * Replaces RistrettoPoint::multiscalar_mul + append_blinding_commitment's compress at
+ * /root/reference/src/toolbox/prover.rs:93-103.  No branch or memory address depends on the scalars.
+ * `point_format` selects ZKP_POINTS_LIMBS51 (the prover holds RistrettoPoints, prover.rs:27) or
+ * ZKP_POINTS_COMPRESSED.  Compressed inputs that fail to decode give ZKP_ERR_POINT.                        */
+int32_t zkp_msm_ct_batched(zkp_ctx* ctx, const uint8_t* scalars, const void* points, int32_t point_format,
+                           const uint64_t* offsets, size_t M, uint8_t* out);
+
+/* BatchVerifier::verify_batchable from the MSM on (/root/reference/src/toolbox/batch_verifier.rs:208-234):
+ * given the coefficient vector and the point rows exactly as the reference builds them,
+ *   static_coeffs[num_s], static_points[num_s],
+ *   instance_coeffs = row-major Matrix[(rows) x batch]  (util.rs:35-37, batch_verifier.rs:174,222),
+ *   instance_points[rows][batch]                        (batch_verifier.rs:208-217; rows = num_i + num_c),
+ * compute the combined MSM and the identity test.  *accept = 1 iff the sum is the ristretto identity.
+ * Returns ZKP_ERR_POINT when a point fails to decode (the reference returns VerificationFailure, :228).     */
+int32_t zkp_batch_verify(zkp_ctx* ctx, const uint8_t* static_coeffs, const uint8_t* static_points, size_t num_s,
+                         const uint8_t* instance_coeffs, const uint8_t* instance_points, size_t rows, size_t batch,
+                         int32_t* accept, int64_t* first_bad);
+
+/* Device-side micro-benchmark of the field multiplier variants (roofline calibration):
+ * runs `iters` dependent multiplies (or squarings) per thread over a full grid and returns the measured
+ * rate in operations per second in *ops_per_sec.  kind: 0 = fe_mul (8x32 saturated), 1 = fe_sq,
+ * 2 = 5x51-limb multiply (u64 products), 3 = 10x25.5-limb multiply.                                        */
+int32_t zkp_bench_field(zkp_ctx* ctx, int32_t kind, int32_t iters, double* ops_per_sec);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZKP_B200_H */

@@ -1,0 +1,55 @@
+// Host build of the device arithmetic headers (-DZKP_HOST_EMUL): the asm carry chains are replaced by 64-bit C
+// so the kernel *logic* can be checked against the big-int oracle without a GPU.  TEST INFRASTRUCTURE ONLY:
+// nothing in zkp_b200/ loads this library.
+#include <cstring>
+#include "../../zkp_b200/csrc/fe.cuh"
+#include "../../zkp_b200/csrc/ge.cuh"
+#include "../../zkp_b200/csrc/sc.cuh"
+using namespace zkp;
+
+static fe ld(const uint8_t* p) { fe r; memcpy(r.v, p, 32); return r; }
+static void st(uint8_t* p, const fe& a) { memcpy(p, a.v, 32); }
+
+extern "C" {
+// raw (non-canonical) 256-bit in/out so the weak-reduction invariants themselves are testable
+void emul_fe_mul(uint8_t* r, const uint8_t* a, const uint8_t* b) { fe x; fe_mul(x, ld(a), ld(b)); st(r, x); }
+void emul_fe_sq(uint8_t* r, const uint8_t* a) { fe x; fe_sq(x, ld(a)); st(r, x); }
+void emul_fe_add(uint8_t* r, const uint8_t* a, const uint8_t* b) { fe x; fe_add(x, ld(a), ld(b)); st(r, x); }
+void emul_fe_sub(uint8_t* r, const uint8_t* a, const uint8_t* b) { fe x; fe_sub(x, ld(a), ld(b)); st(r, x); }
+void emul_fe_canon(uint8_t* r, const uint8_t* a) { fe x; fe_canon(x, ld(a)); st(r, x); }
+void emul_fe_invert(uint8_t* r, const uint8_t* a) { fe x; fe_invert(x, ld(a)); st(r, x); }
+void emul_fe_pow22523(uint8_t* r, const uint8_t* a) { fe x; fe_pow22523(x, ld(a)); st(r, x); }
+void emul_fe_from_limbs51(uint8_t* r, const uint64_t* l) { fe x; fe_from_limbs51(x, l); st(r, x); }
+void emul_fe_to_limbs51(uint64_t* l, const uint8_t* a) { fe_to_limbs51(l, ld(a)); }
+
+// ---- group / ristretto ----
+static ge_ext ldp(const uint8_t* p) { ge_ext r; memcpy(&r, p, 128); return r; }
+// decode: out = x|y|t (96 B raw limbs), returns validity
+int emul_decode(uint8_t* out, const uint8_t* enc) {
+  uint32_t w[8]; memcpy(w, enc, 32);
+  fe x, y, t; uint32_t ok = ristretto_decode(x, y, t, w);
+  memcpy(out, x.v, 32); memcpy(out + 32, y.v, 32); memcpy(out + 64, t.v, 32);
+  return (int)ok;
+}
+void emul_encode(uint8_t* enc, const uint8_t* pt128) {
+  uint32_t w[8]; ristretto_encode(w, ldp(pt128)); memcpy(enc, w, 32);
+}
+// p (128 B ext) + [neg] q (x|y|t affine 96 B) via the Niels path
+void emul_madd(uint8_t* out, const uint8_t* pt128, const uint8_t* aff96, int neg) {
+  fe x, y, t; memcpy(x.v, aff96, 32); memcpy(y.v, aff96 + 32, 32); memcpy(t.v, aff96 + 64, 32);
+  ge_aniels q; ge_aniels_from_affine(q, x, y, t); ge_aniels_cneg(q, (uint32_t)neg);
+  ge_ext r; ge_madd(r, ldp(pt128), q); memcpy(out, &r, 128);
+}
+void emul_add(uint8_t* out, const uint8_t* p, const uint8_t* q) { ge_ext r; ge_add(r, ldp(p), ldp(q)); memcpy(out, &r, 128); }
+void emul_double(uint8_t* out, const uint8_t* p) { ge_ext r; ge_double(r, ldp(p)); memcpy(out, &r, 128); }
+int emul_is_identity(const uint8_t* p) { return (int)ge_is_identity_coset(ldp(p)); }
+// scalar: returns canonical; k32 = folded magnitude; *neg; digits[W] signed
+int emul_recode(int32_t* digits, uint8_t* k32, int* neg, const uint8_t* s32, int c, int W) {
+  uint32_t s[8], k[8]; memcpy(s, s32, 32);
+  uint32_t ng; uint32_t can = sc_fold_sign(k, ng, s);
+  memcpy(k32, k, 32); *neg = (int)ng;
+  uint32_t carry = 0;
+  for (int w = 0; w < W; w++) { uint32_t mag, dn; sc_digit(mag, dn, carry, k, w, c); digits[w] = dn ? -(int32_t)mag : (int32_t)mag; }
+  return (int)can | ((int)carry << 1);
+}
+}

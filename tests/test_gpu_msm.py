@@ -1,0 +1,151 @@
+"""GPU parity tests: the CUDA path through the C ABI against the oracle / golden fixtures (bit exact)."""
+import numpy as np
+import pytest
+
+from oracle import msm as M, ristretto as R
+from tests import util_data as U
+
+pytestmark = pytest.mark.gpu
+
+
+def _h(xs):
+    return np.frombuffer(b"".join(bytes.fromhex(x) for x in xs), dtype=np.uint8).reshape(-1, 32)
+
+
+def test_rfc9496_multiples_via_msm(engine):
+    g = U.golden("rfc9496.json")
+    B = bytes.fromhex(g["multiples_of_generator"][1])
+    for k, exp in enumerate(g["multiples_of_generator"]):
+        enc, ident, _ = engine.msm_vartime(k.to_bytes(32, "little"), B)
+        assert enc.hex() == exp
+        assert ident == (k == 0)
+
+
+def test_decompress_compress_roundtrip_and_bad_encodings(engine):
+    g = U.golden("rfc9496.json")
+    good = [bytes.fromhex(x) for x in g["multiples_of_generator"]] + U.base_points(40)
+    bad = [bytes.fromhex(x) for x in g["bad_encodings"]]
+    limbs, valid = engine.decompress_batch(good + bad)
+    assert valid[:len(good)].all() and not valid[len(good):].any()
+    back = engine.compress_batch(limbs[:len(good)])
+    assert [bytes(b) for b in back] == good
+    # limbs agree with the oracle's affine coordinates
+    for i, e in enumerate(good[:20]):
+        x, y, z, t = R.decompress(e)
+        got = [sum(int(limbs[i, c, j]) << (51 * j) for j in range(5)) for c in range(4)]
+        assert got == [x, y, 1, t]
+
+
+def test_msm_kats(engine):
+    for kat in U.golden("msm_kat.json")["kats"]:
+        enc, ident, _ = engine.msm_vartime(_h(kat["scalars"]), _h(kat["points"]))
+        assert enc.hex() == kat["expected"], kat["n"]
+        assert ident == (kat["expected"] == "00" * 32)
+
+
+@pytest.mark.parametrize("window", [4, 5, 7, 8, 11, 13, 16])
+def test_msm_all_windows(engine, window):
+    kat = [k for k in U.golden("msm_kat.json")["kats"] if k["n"] == 300][0]
+    engine.set_option("window", window)
+    try:
+        for lanes in (1, 4, 32):
+            engine.set_option("lanes", lanes)
+            enc, _, _ = engine.msm_vartime(_h(kat["scalars"]), _h(kat["points"]))
+            assert enc.hex() == kat["expected"], (window, lanes)
+    finally:
+        engine.set_option("window", 0)
+        engine.set_option("lanes", 0)
+
+
+def test_msm_seeded_large(engine):
+    for case in U.golden("msm_seeded.json")["cases"]:
+        base = U.base_points(case["K"])
+        sc = U.random_scalars(case["n"], seed=case["seed"])
+        pts = np.frombuffer(b"".join(base[i % case["K"]] for i in range(case["n"])), dtype=np.uint8).reshape(-1, 32)
+        enc, _, _ = engine.msm_vartime(sc, pts)
+        assert enc.hex() == case["expected"]
+
+
+def test_msm_edge_cases(engine):
+    pts = U.base_points(8)
+    # empty
+    enc, ident, _ = engine.msm_vartime(b"", b"")
+    assert enc == bytes(32) and ident
+    # invalid point -> None with index
+    g = U.golden("rfc9496.json")
+    bad = bytes.fromhex(g["bad_encodings"][5])
+    sc = U.random_scalars(8, seed=3)
+    p = list(pts)
+    p[5] = bad
+    enc, ident, first_bad = engine.msm_vartime(sc, p)
+    assert enc is None and first_bad == 5
+    # all scalars equal (one bucket per window takes everything), and all-zero scalars
+    n = 777
+    one = np.tile(np.frombuffer((R.L - 5).to_bytes(32, "little"), dtype=np.uint8), (n, 1))
+    P = [pts[i % 8] for i in range(n)]
+    exp = R.compress(M.naive_msm([(R.L - 5) * (n // 8 + (1 if i < n % 8 else 0)) for i in range(8)],
+                                 [R.decompress(e) for e in pts]))
+    enc, _, _ = engine.msm_vartime(one, P)
+    assert enc == exp
+    enc, ident, _ = engine.msm_vartime(np.zeros((n, 32), dtype=np.uint8), P)
+    assert enc == bytes(32) and ident
+    # non-canonical scalar is rejected
+    from zkp_b200 import EngineError
+    s2 = sc.copy()
+    s2[2] = np.frombuffer(R.L.to_bytes(32, "little"), dtype=np.uint8)
+    with pytest.raises(EngineError) as ei:
+        engine.msm_vartime(s2, pts)
+    assert ei.value.code == 3
+
+
+def test_msm_linearity_full_size(engine):
+    """size-independent property at a BASELINE-sized input: MSM(a*s, P) == a * MSM(s, P) via tiling."""
+    n, K = 1 << 18, 256
+    base = U.base_points(K)
+    sc = U.random_scalars(n, seed=99)
+    pts = np.frombuffer(b"".join(base[i % K] for i in range(n)), dtype=np.uint8).reshape(-1, 32)
+    enc, _, _ = engine.msm_vartime(sc, pts)
+    assert enc == U.tiled_expected(sc, base)
+
+
+def test_small_batched_vartime(engine):
+    kats = [k for k in U.golden("msm_kat.json")["kats"] if k["n"] <= 36]
+    scal = np.concatenate([_h(k["scalars"]) for k in kats])
+    pts = np.concatenate([_h(k["points"]) for k in kats])
+    off = np.cumsum([0] + [k["n"] for k in kats]).astype(np.uint64)
+    out, valid = engine.msm_vartime_batched(scal, pts, off)
+    assert valid.all()
+    assert [bytes(o).hex() for o in out] == [k["expected"] for k in kats]
+    # one bad point invalidates only its MSM
+    g = U.golden("rfc9496.json")
+    pts2 = pts.copy()
+    pts2[int(off[3])] = np.frombuffer(bytes.fromhex(g["bad_encodings"][0]), dtype=np.uint8)
+    out2, valid2 = engine.msm_vartime_batched(scal, pts2, off)
+    assert not valid2[3] and valid2.sum() == len(kats) - 1
+    assert bytes(out2[2]).hex() == kats[2]["expected"]
+
+
+def test_small_batched_ct(engine):
+    kats = [k for k in U.golden("msm_kat.json")["kats"] if k["n"] <= 36]
+    scal = np.concatenate([_h(k["scalars"]) for k in kats])
+    pts = np.concatenate([_h(k["points"]) for k in kats])
+    off = np.cumsum([0] + [k["n"] for k in kats]).astype(np.uint64)
+    out = engine.msm_ct_batched(scal, pts, off)
+    assert [bytes(o).hex() for o in out] == [k["expected"] for k in kats]
+    limbs, valid = engine.decompress_batch(pts)
+    assert valid.all()
+    out = engine.msm_ct_batched(scal, limbs, off, limbs=True)
+    assert [bytes(o).hex() for o in out] == [k["expected"] for k in kats]
+
+
+def test_batch_verify_dleq_golden(engine):
+    kb = U.golden("toolbox_kat.json")["dleq_batch"]
+    scal, pts = _h(kb["msm_scalars"]), _h(kb["msm_points"])
+    num_s, batch = 1, 4
+    rows = (scal.shape[0] - num_s) // batch
+    ok, rc = engine.batch_verify(scal[:num_s], pts[:num_s], scal[num_s:], pts[num_s:], rows, batch)
+    assert ok and rc == 0
+    bad = scal.copy()
+    bad[3, 0] ^= 1
+    ok, rc = engine.batch_verify(bad[:num_s], pts[:num_s], bad[num_s:], pts[num_s:], rows, batch)
+    assert not ok and rc == 0

@@ -1,0 +1,564 @@
+// C ABI of the engine (include/zkp_b200.h): context, workspace, launch sequencing.
+// Everything that computes is in kernels.cuh / small_msm.cuh; this file only allocates, copies and launches.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <new>
+#include <string>
+
+#include "../../include/zkp_b200.h"
+#include "kernels.cuh"
+#include "small_msm.cuh"
+#include "bench_fe.cuh"
+
+using namespace zkp;
+
+struct devbuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+struct zkp_ctx {
+  int device = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  int window = 0;      // 0 = auto
+  int lanes = 0;       // 0 = auto
+  int window_cap = 16; // upper bound for the automatic choice
+  uint64_t launches = 0;
+  std::string err;
+  // workspace (grown on demand, reused across calls)
+  devbuf in_scalars, in_points, niels, hist, offs, cursor, sorted, buckets, lvlT[2], lvlU, usum, flags, result,
+      aux0, aux1, aux2, sk0, sk1, tables;
+  void* h_result = nullptr;  // pinned, 64 bytes
+};
+
+#define CUDA_TRY(ctx, call)                                                            \
+  do {                                                                                 \
+    cudaError_t e_ = (call);                                                           \
+    if (e_ != cudaSuccess) {                                                           \
+      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                 \
+      return (e_ == cudaErrorMemoryAllocation) ? ZKP_ERR_NOMEM : ZKP_ERR_CUDA;         \
+    }                                                                                  \
+  } while (0)
+
+static int32_t ensure(zkp_ctx* ctx, devbuf& b, size_t bytes) {
+  if (bytes <= b.cap) return ZKP_OK;
+  if (b.p) {
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+  }
+  size_t want = bytes + bytes / 8 + 256;
+  cudaError_t e = cudaMalloc(&b.p, want);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    want = bytes;
+    e = cudaMalloc(&b.p, want);
+  }
+  if (e != cudaSuccess) {
+    b.p = nullptr;
+    ctx->err = std::string("cudaMalloc: ") + cudaGetErrorString(e);
+    cudaGetLastError();
+    return ZKP_ERR_NOMEM;
+  }
+  b.cap = want;
+  return ZKP_OK;
+}
+#define ENSURE(ctx, buf, bytes)                       \
+  do {                                                \
+    int32_t r_ = ensure((ctx), (buf), (bytes));       \
+    if (r_ != ZKP_OK) return r_;                      \
+  } while (0)
+
+#define LAUNCH_CHECK(ctx)                                                  \
+  do {                                                                     \
+    (ctx)->launches++;                                                     \
+    cudaError_t e_ = cudaGetLastError();                                   \
+    if (e_ != cudaSuccess) {                                               \
+      (ctx)->err = std::string("kernel launch: ") + cudaGetErrorString(e_); \
+      return ZKP_ERR_CUDA;                                                 \
+    }                                                                      \
+  } while (0)
+
+static inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
+
+extern "C" int32_t zkp_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+extern "C" int32_t zkp_ctx_create(zkp_ctx** out, int32_t device) {
+  if (!out) return ZKP_ERR_SIZE;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0 || device < 0 || device >= n) {
+    cudaGetLastError();
+    return ZKP_ERR_NOGPU;
+  }
+  zkp_ctx* ctx = new (std::nothrow) zkp_ctx();
+  if (!ctx) return ZKP_ERR_NOMEM;
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaMallocHost(&ctx->h_result, 64) != cudaSuccess) {
+    cudaGetLastError();
+    delete ctx;
+    return ZKP_ERR_NOGPU;
+  }
+  ctx->stream = ctx->own_stream;
+  *out = ctx;
+  return ZKP_OK;
+}
+
+extern "C" void zkp_ctx_destroy(zkp_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  devbuf* bufs[] = {&ctx->in_scalars, &ctx->in_points, &ctx->niels, &ctx->hist, &ctx->offs, &ctx->cursor,
+                    &ctx->sorted, &ctx->buckets, &ctx->lvlT[0], &ctx->lvlT[1], &ctx->lvlU, &ctx->usum,
+                    &ctx->flags, &ctx->result, &ctx->aux0, &ctx->aux1, &ctx->aux2, &ctx->sk0, &ctx->sk1,
+                    &ctx->tables};
+  for (devbuf* b : bufs)
+    if (b->p) cudaFree(b->p);
+  if (ctx->h_result) cudaFreeHost(ctx->h_result);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+extern "C" int32_t zkp_ctx_set_stream(zkp_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return ZKP_ERR_SIZE;
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return ZKP_OK;
+}
+
+extern "C" int32_t zkp_ctx_set_option(zkp_ctx* ctx, const char* key, int64_t value) {
+  if (!ctx || !key) return ZKP_ERR_SIZE;
+  if (!strcmp(key, "window")) {
+    if (value != 0 && (value < 4 || value > 24)) return ZKP_ERR_SIZE;
+    ctx->window = (int)value;
+  } else if (!strcmp(key, "window_cap")) {
+    if (value < 4 || value > 24) return ZKP_ERR_SIZE;
+    ctx->window_cap = (int)value;
+  } else if (!strcmp(key, "lanes")) {
+    if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8 && value != 16 && value != 32)
+      return ZKP_ERR_SIZE;
+    ctx->lanes = (int)value;
+  } else {
+    return ZKP_ERR_SIZE;
+  }
+  return ZKP_OK;
+}
+
+extern "C" int32_t zkp_ctx_synchronize(zkp_ctx* ctx) {
+  if (!ctx) return ZKP_ERR_SIZE;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return ZKP_OK;
+}
+
+extern "C" const char* zkp_last_error(zkp_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+extern "C" uint64_t zkp_ctx_launch_count(zkp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---------------------------------------------------------------------------------------------------------
+// window / lane heuristics
+// ---------------------------------------------------------------------------------------------------------
+static int choose_window(const zkp_ctx* ctx, size_t n) {
+  if (ctx->window) return ctx->window;
+  int best = 4;
+  double best_cost = 1e300;
+  for (int c = 4; c <= ctx->window_cap; c++) {
+    double W = (253 + c - 1) / c;
+    double B = (double)(1ull << (c - 1));
+    double cost = W * ((double)n + 3.0 * B);  // bucket adds + ~2 full adds per bucket in the reduction
+    if (cost < best_cost) {
+      best_cost = cost;
+      best = c;
+    }
+  }
+  return best;
+}
+
+static int choose_lanes(const zkp_ctx* ctx, size_t n, uint32_t B) {
+  if (ctx->lanes) return ctx->lanes;
+  double mean = (double)n / (double)B;
+  int g = 1;
+  while (g < 32 && mean / (g * 2) >= 96.0) g *= 2;
+  return g;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// the variable-time MSM, device-resident and asynchronous
+// ---------------------------------------------------------------------------------------------------------
+static int32_t msm_vartime_launch(zkp_ctx* ctx, const void* d_scalars, const void* d_points, size_t n,
+                                  msm_result* d_result) {
+  cudaStream_t st = ctx->stream;
+  if (n == 0) {
+    k_empty_result<<<1, 1, 0, st>>>(d_result);
+    LAUNCH_CHECK(ctx);
+    return ZKP_OK;
+  }
+  if (n >= 0x7fffffffull) {
+    ctx->err = "n too large (>= 2^31 terms per call)";
+    return ZKP_ERR_SIZE;
+  }
+  const int c = choose_window(ctx, n);
+  const int W = (253 + c - 1) / c;
+  const uint32_t B = 1u << (c - 1);
+  const int G = choose_lanes(ctx, n, B);
+  const uint32_t total_buckets = (uint32_t)W * B;
+
+  ENSURE(ctx, ctx->niels, n * 96);
+  ENSURE(ctx, ctx->hist, (size_t)W * B * 4);
+  ENSURE(ctx, ctx->offs, (size_t)W * (B + 1) * 4);
+  ENSURE(ctx, ctx->cursor, (size_t)W * B * 4);
+  ENSURE(ctx, ctx->sorted, (size_t)W * n * 4);
+  ENSURE(ctx, ctx->buckets, (size_t)total_buckets * 128);
+  ENSURE(ctx, ctx->flags, 16);
+  const uint32_t chunks0 = B / ZKP_CHUNK_L;
+  if (chunks0 > 0) {
+    ENSURE(ctx, ctx->lvlT[0], (size_t)W * chunks0 * 128);
+    ENSURE(ctx, ctx->lvlT[1], (size_t)W * (chunks0 / ZKP_CHUNK_L + 1) * 128);
+    ENSURE(ctx, ctx->lvlU, (size_t)W * chunks0 * 128);
+  }
+  ENSURE(ctx, ctx->usum, (size_t)8 * W * 128);
+
+  int* flags = (int*)ctx->flags.p;
+  k_init_flags<<<1, 1, 0, st>>>(flags);
+  LAUNCH_CHECK(ctx);
+  CUDA_TRY(ctx, cudaMemsetAsync(ctx->hist.p, 0, (size_t)W * B * 4, st));
+
+  const unsigned nb = (unsigned)((n + 255) / 256);
+  k_decompress<<<nb, 256, 0, st>>>((const uint4*)d_points, n, (uint4*)ctx->niels.p, flags);
+  LAUNCH_CHECK(ctx);
+  k_recode<false><<<nb, 256, 0, st>>>((const uint4*)d_scalars, n, c, W, B, (uint32_t*)ctx->hist.p, nullptr, flags);
+  LAUNCH_CHECK(ctx);
+  k_scan<<<W, 1024, 0, st>>>((const uint32_t*)ctx->hist.p, B, (uint32_t*)ctx->offs.p, (uint32_t*)ctx->cursor.p);
+  LAUNCH_CHECK(ctx);
+  k_recode<true><<<nb, 256, 0, st>>>((const uint4*)d_scalars, n, c, W, B, (uint32_t*)ctx->cursor.p,
+                                     (uint32_t*)ctx->sorted.p, flags);
+  LAUNCH_CHECK(ctx);
+
+  {
+    const size_t threads = (size_t)total_buckets * G;
+    const unsigned blocks = (unsigned)((threads + 127) / 128);
+    const uint4* ni = (const uint4*)ctx->niels.p;
+    const uint32_t* so = (const uint32_t*)ctx->sorted.p;
+    const uint32_t* of = (const uint32_t*)ctx->offs.p;
+    uint4* bk = (uint4*)ctx->buckets.p;
+    switch (G) {
+      case 1: k_accumulate<1><<<blocks, 128, 0, st>>>(ni, so, of, n, B, total_buckets, bk); break;
+      case 2: k_accumulate<2><<<blocks, 128, 0, st>>>(ni, so, of, n, B, total_buckets, bk); break;
+      case 4: k_accumulate<4><<<blocks, 128, 0, st>>>(ni, so, of, n, B, total_buckets, bk); break;
+      case 8: k_accumulate<8><<<blocks, 128, 0, st>>>(ni, so, of, n, B, total_buckets, bk); break;
+      case 16: k_accumulate<16><<<blocks, 128, 0, st>>>(ni, so, of, n, B, total_buckets, bk); break;
+      default: k_accumulate<32><<<blocks, 128, 0, st>>>(ni, so, of, n, B, total_buckets, bk); break;
+    }
+    LAUNCH_CHECK(ctx);
+  }
+
+  // bucket reduction levels
+  const uint4* cur = (const uint4*)ctx->buckets.p;
+  uint32_t m = B;
+  int nl = 0;
+  while (m > ZKP_CHUNK_L) {
+    const uint32_t chunks = m / ZKP_CHUNK_L;
+    uint4* T = (uint4*)ctx->lvlT[nl & 1].p;
+    uint4* U = (uint4*)ctx->lvlU.p;
+    const unsigned threads = chunks * (unsigned)W;
+    k_chunk_reduce<<<(threads + 127) / 128, 128, 0, st>>>(cur, m, W, T, U);
+    LAUNCH_CHECK(ctx);
+    k_tree_sum<<<W, 256, 0, st>>>(U, chunks, (uint4*)ctx->usum.p + (size_t)nl * W * 8);
+    LAUNCH_CHECK(ctx);
+    cur = T;
+    m = chunks;
+    nl++;
+  }
+  k_finish<<<1, 64, 0, st>>>((const uint4*)ctx->usum.p, nl, cur, m, W, c, n, flags, d_result, nullptr);
+  LAUNCH_CHECK(ctx);
+  return ZKP_OK;
+}
+
+extern "C" int32_t zkp_msm_vartime_dev(zkp_ctx* ctx, const void* d_scalars, const void* d_points, size_t n,
+                                       void* d_result) {
+  if (!ctx || !d_result || (n && (!d_scalars || !d_points))) return ZKP_ERR_SIZE;
+  if (!aligned16(d_scalars) || !aligned16(d_points) || !aligned16(d_result)) {
+    ctx->err = "device pointers must be 16-byte aligned";
+    return ZKP_ERR_SIZE;
+  }
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  return msm_vartime_launch(ctx, d_scalars, d_points, n, (msm_result*)d_result);
+}
+
+static int32_t fetch_result(zkp_ctx* ctx, uint8_t* out32, int32_t* is_identity, int64_t* first_bad) {
+  msm_result* h = (msm_result*)ctx->h_result;
+  CUDA_TRY(ctx, cudaMemcpyAsync(h, ctx->result.p, sizeof(msm_result), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (first_bad) *first_bad = h->first_bad;
+  if (h->status != ZKP_OK) {
+    if (is_identity) *is_identity = 0;
+    return h->status;
+  }
+  if (out32) memcpy(out32, h->enc, 32);
+  if (is_identity) *is_identity = h->is_identity;
+  return ZKP_OK;
+}
+
+extern "C" int32_t zkp_msm_vartime(zkp_ctx* ctx, const uint8_t* scalars, const uint8_t* points, size_t n,
+                                   uint8_t* out32, int32_t* is_identity, int64_t* first_bad) {
+  if (!ctx || (n && (!scalars || !points))) return ZKP_ERR_SIZE;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  ENSURE(ctx, ctx->result, 64);
+  if (n) {
+    ENSURE(ctx, ctx->in_scalars, n * 32);
+    ENSURE(ctx, ctx->in_points, n * 32);
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->in_points.p, points, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->in_scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  int32_t r = msm_vartime_launch(ctx, ctx->in_scalars.p, ctx->in_points.p, n, (msm_result*)ctx->result.p);
+  if (r != ZKP_OK) return r;
+  return fetch_result(ctx, out32, is_identity, first_bad);
+}
+
+extern "C" int32_t zkp_batch_verify(zkp_ctx* ctx, const uint8_t* static_coeffs, const uint8_t* static_points,
+                                    size_t num_s, const uint8_t* instance_coeffs, const uint8_t* instance_points,
+                                    size_t rows, size_t batch, int32_t* accept, int64_t* first_bad) {
+  if (!ctx || !accept) return ZKP_ERR_SIZE;
+  *accept = 0;
+  if ((num_s && (!static_coeffs || !static_points)) || (rows * batch && (!instance_coeffs || !instance_points)))
+    return ZKP_ERR_SIZE;
+  if (batch && rows > ((size_t)1 << 40) / batch) return ZKP_ERR_SIZE;
+  const size_t n_inst = rows * batch, n = num_s + n_inst;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  ENSURE(ctx, ctx->result, 64);
+  if (n) {
+    ENSURE(ctx, ctx->in_scalars, n * 32);
+    ENSURE(ctx, ctx->in_points, n * 32);
+    // scalar order: static ++ row-major instance matrix; point order: static ++ rows   (batch_verifier.rs:219-226)
+    uint8_t* ds = (uint8_t*)ctx->in_scalars.p;
+    uint8_t* dp = (uint8_t*)ctx->in_points.p;
+    if (n_inst) {
+      CUDA_TRY(ctx, cudaMemcpyAsync(dp + num_s * 32, instance_points, n_inst * 32, cudaMemcpyHostToDevice, ctx->stream));
+      CUDA_TRY(ctx, cudaMemcpyAsync(ds + num_s * 32, instance_coeffs, n_inst * 32, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (num_s) {
+      CUDA_TRY(ctx, cudaMemcpyAsync(dp, static_points, num_s * 32, cudaMemcpyHostToDevice, ctx->stream));
+      CUDA_TRY(ctx, cudaMemcpyAsync(ds, static_coeffs, num_s * 32, cudaMemcpyHostToDevice, ctx->stream));
+    }
+  }
+  int32_t r = msm_vartime_launch(ctx, ctx->in_scalars.p, ctx->in_points.p, n, (msm_result*)ctx->result.p);
+  if (r != ZKP_OK) return r;
+  int32_t ident = 0;
+  r = fetch_result(ctx, nullptr, &ident, first_bad);
+  if (r != ZKP_OK) return r;
+  *accept = ident;
+  return ZKP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// batched decompress / compress
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int32_t zkp_decompress_batch(zkp_ctx* ctx, const uint8_t* enc, size_t n, uint64_t* limbs_out,
+                                        uint8_t* valid_out) {
+  if (!ctx || (n && (!enc || !limbs_out || !valid_out))) return ZKP_ERR_SIZE;
+  if (!n) return ZKP_OK;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  ENSURE(ctx, ctx->in_points, n * 32);
+  ENSURE(ctx, ctx->aux0, n * 160);
+  ENSURE(ctx, ctx->aux1, n);
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->in_points.p, enc, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  k_decompress_limbs<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
+      (const uint4*)ctx->in_points.p, n, (unsigned long long*)ctx->aux0.p, (uint8_t*)ctx->aux1.p);
+  LAUNCH_CHECK(ctx);
+  CUDA_TRY(ctx, cudaMemcpyAsync(limbs_out, ctx->aux0.p, n * 160, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(valid_out, ctx->aux1.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return ZKP_OK;
+}
+
+extern "C" int32_t zkp_compress_batch(zkp_ctx* ctx, const uint64_t* limbs_in, size_t n, uint8_t* enc_out) {
+  if (!ctx || (n && (!limbs_in || !enc_out))) return ZKP_ERR_SIZE;
+  if (!n) return ZKP_OK;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  ENSURE(ctx, ctx->aux0, n * 160);
+  ENSURE(ctx, ctx->in_points, n * 32);
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->aux0.p, limbs_in, n * 160, cudaMemcpyHostToDevice, ctx->stream));
+  k_compress_limbs<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const unsigned long long*)ctx->aux0.p, n,
+                                                                         (uint4*)ctx->in_points.p);
+  LAUNCH_CHECK(ctx);
+  CUDA_TRY(ctx, cudaMemcpyAsync(enc_out, ctx->in_points.p, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return ZKP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// batched small MSMs (CSR)
+// ---------------------------------------------------------------------------------------------------------
+static int32_t check_offsets(zkp_ctx* ctx, const uint64_t* offsets, size_t M, size_t* total) {
+  if (!offsets) return ZKP_ERR_SIZE;
+  if (offsets[0] != 0) {
+    ctx->err = "offsets[0] must be 0";
+    return ZKP_ERR_SIZE;
+  }
+  for (size_t j = 0; j < M; j++)
+    if (offsets[j + 1] < offsets[j]) {
+      ctx->err = "offsets must be non-decreasing";
+      return ZKP_ERR_SIZE;
+    }
+  *total = (size_t)offsets[M];
+  return ZKP_OK;
+}
+
+extern "C" int32_t zkp_msm_vartime_batched(zkp_ctx* ctx, const uint8_t* scalars, const uint8_t* points,
+                                           const uint64_t* offsets, size_t M, uint8_t* out, uint8_t* valid) {
+  if (!ctx || (M && (!out || !valid))) return ZKP_ERR_SIZE;
+  if (!M) return ZKP_OK;
+  size_t total = 0;
+  int32_t r = check_offsets(ctx, offsets, M, &total);
+  if (r != ZKP_OK) return r;
+  if (total && (!scalars || !points)) return ZKP_ERR_SIZE;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  ENSURE(ctx, ctx->in_scalars, total * 32 + 32);
+  ENSURE(ctx, ctx->in_points, total * 32 + 32);
+  ENSURE(ctx, ctx->aux0, (M + 1) * 8);
+  ENSURE(ctx, ctx->aux1, M * 32);
+  ENSURE(ctx, ctx->aux2, M * 4);
+  ENSURE(ctx, ctx->niels, total * 96 + 96);
+  ENSURE(ctx, ctx->sk0, total * 32 + 32);
+  ENSURE(ctx, ctx->sk1, total * 32 + 32);
+  cudaStream_t st = ctx->stream;
+  if (total) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->in_scalars.p, scalars, total * 32, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->in_points.p, points, total * 32, cudaMemcpyHostToDevice, st));
+  }
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->aux0.p, offsets, (M + 1) * 8, cudaMemcpyHostToDevice, st));
+  if (total) {
+    const unsigned nb = (unsigned)((total + 255) / 256);
+    k_decompress_valid<<<nb, 256, 0, st>>>((const uint4*)ctx->in_points.p, total, (uint4*)ctx->niels.p);
+    LAUNCH_CHECK(ctx);
+    k_prep_scalars_vt<<<nb, 256, 0, st>>>((const uint4*)ctx->in_scalars.p, total, (uint4*)ctx->sk0.p,
+                                          (uint4*)ctx->sk1.p);
+    LAUNCH_CHECK(ctx);
+  }
+  k_small_msm_vt<<<(unsigned)((M + 63) / 64), 64, 0, st>>>(
+      (const uint32_t*)ctx->sk0.p, (const uint32_t*)ctx->sk1.p, (const uint4*)ctx->niels.p,
+      (const unsigned long long*)ctx->aux0.p, M, (uint4*)ctx->aux1.p, (int*)ctx->aux2.p);
+  LAUNCH_CHECK(ctx);
+  // status words -> valid bytes on the host
+  int* hstat = (int*)malloc(M * 4);
+  if (!hstat) return ZKP_ERR_NOMEM;
+  cudaError_t e1 = cudaMemcpyAsync(out, ctx->aux1.p, M * 32, cudaMemcpyDeviceToHost, st);
+  cudaError_t e2 = cudaMemcpyAsync(hstat, ctx->aux2.p, M * 4, cudaMemcpyDeviceToHost, st);
+  cudaError_t e3 = cudaStreamSynchronize(st);
+  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+    free(hstat);
+    ctx->err = "copy back failed";
+    cudaGetLastError();
+    return ZKP_ERR_CUDA;
+  }
+  int32_t ret = ZKP_OK;
+  for (size_t j = 0; j < M; j++) {
+    valid[j] = hstat[j] == 0 ? 1 : 0;
+    if (hstat[j] == 3) ret = ZKP_ERR_SCALAR;
+  }
+  free(hstat);
+  return ret;
+}
+
+extern "C" int32_t zkp_msm_ct_batched(zkp_ctx* ctx, const uint8_t* scalars, const void* points, int32_t point_format,
+                                      const uint64_t* offsets, size_t M, uint8_t* out) {
+  if (!ctx || (M && !out)) return ZKP_ERR_SIZE;
+  if (point_format != ZKP_POINTS_COMPRESSED && point_format != ZKP_POINTS_LIMBS51) return ZKP_ERR_SIZE;
+  if (!M) return ZKP_OK;
+  size_t total = 0;
+  int32_t r = check_offsets(ctx, offsets, M, &total);
+  if (r != ZKP_OK) return r;
+  if (total && (!scalars || !points)) return ZKP_ERR_SIZE;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const size_t psz = point_format == ZKP_POINTS_LIMBS51 ? 160 : 32;
+  ENSURE(ctx, ctx->in_scalars, total * 32 + 32);
+  ENSURE(ctx, ctx->in_points, total * psz + 160);
+  ENSURE(ctx, ctx->aux0, (M + 1) * 8);
+  ENSURE(ctx, ctx->aux1, M * 32);
+  ENSURE(ctx, ctx->aux2, M * 4);
+  ENSURE(ctx, ctx->niels, total * 128 + 128);
+  ENSURE(ctx, ctx->flags, 16);
+  cudaStream_t st = ctx->stream;
+  if (total) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->in_scalars.p, scalars, total * 32, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->in_points.p, points, total * psz, cudaMemcpyHostToDevice, st));
+  }
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->aux0.p, offsets, (M + 1) * 8, cudaMemcpyHostToDevice, st));
+  k_init_flags<<<1, 1, 0, st>>>((int*)ctx->flags.p);
+  LAUNCH_CHECK(ctx);
+  if (total) {
+    const unsigned nb = (unsigned)((total + 255) / 256);
+    if (point_format == ZKP_POINTS_LIMBS51)
+      k_limbs_to_ext<<<nb, 256, 0, st>>>((const unsigned long long*)ctx->in_points.p, total, (uint4*)ctx->niels.p);
+    else
+      k_decompress_ext<<<nb, 256, 0, st>>>((const uint4*)ctx->in_points.p, total, (uint4*)ctx->niels.p,
+                                           (int*)ctx->flags.p);
+    LAUNCH_CHECK(ctx);
+  }
+  if (total) {
+    ENSURE(ctx, ctx->tables, total * 1024);
+    ENSURE(ctx, ctx->sk0, total * 32 + 32);
+    k_build_tables<<<(unsigned)((total + 127) / 128), 128, 0, st>>>((const uint4*)ctx->niels.p,
+                                                                    (const uint4*)ctx->in_scalars.p, total,
+                                                                    (uint4*)ctx->tables.p, (uint4*)ctx->sk0.p,
+                                                                    (int*)ctx->flags.p);
+    LAUNCH_CHECK(ctx);
+  }
+  k_small_msm_ct<<<(unsigned)((M + 63) / 64), 64, 0, st>>>((const uint32_t*)ctx->sk0.p, (const uint4*)ctx->tables.p,
+                                                           (const unsigned long long*)ctx->aux0.p, M,
+                                                           (uint4*)ctx->aux1.p);
+  LAUNCH_CHECK(ctx);
+  int hflags[4];
+  CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->aux1.p, M * 32, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(hflags, ctx->flags.p, 16, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  if (hflags[0] != 0x7fffffff) return ZKP_ERR_POINT;
+  if (hflags[1] != 0x7fffffff) return ZKP_ERR_SCALAR;
+  return ZKP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// field-multiplier micro-benchmark
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int32_t zkp_bench_field(zkp_ctx* ctx, int32_t kind, int32_t iters, double* ops_per_sec) {
+  if (!ctx || !ops_per_sec || iters <= 0 || kind < 0 || kind > 3) return ZKP_ERR_SIZE;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  int sms = 0;
+  CUDA_TRY(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+  const int threads = 256, blocks = sms * 8;
+  ENSURE(ctx, ctx->aux0, (size_t)threads * blocks * 64);
+  cudaEvent_t e0, e1;
+  CUDA_TRY(ctx, cudaEventCreate(&e0));
+  CUDA_TRY(ctx, cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; rep++) {
+    CUDA_TRY(ctx, cudaEventRecord(e0, ctx->stream));
+    switch (kind) {
+      case 0: k_bench_mul32<<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, iters); break;
+      case 1: k_bench_sq32<<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, iters); break;
+      case 2: k_bench_mul51<<<blocks, threads, 0, ctx->stream>>>((unsigned long long*)ctx->aux0.p, iters); break;
+      default: k_bench_mul25<<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, iters); break;
+    }
+    LAUNCH_CHECK(ctx);
+    CUDA_TRY(ctx, cudaEventRecord(e1, ctx->stream));
+    CUDA_TRY(ctx, cudaEventSynchronize(e1));
+    float ms = 0;
+    CUDA_TRY(ctx, cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ops_per_sec = (double)threads * blocks * (double)iters / (best * 1e-3);
+  return ZKP_OK;
+}

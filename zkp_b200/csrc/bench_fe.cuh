@@ -1,0 +1,143 @@
+// Field-multiplier micro-benchmarks (zkp_bench_field): the integer-pipe roofline calibration and the
+// "51-bit radix vs saturated 32-bit" ablation that DESIGN.md reports.  Each thread runs a dependent chain of
+// `iters` operations on register-resident operands; with 8 resident warps per scheduler the chain latency is
+// hidden and the measured rate is the pipe's throughput for that instruction mix.
+#pragma once
+#include "fe.cuh"
+
+namespace zkp {
+
+__global__ void __launch_bounds__(256) k_bench_mul32(uint32_t* out, int iters) {
+  uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+  fe a, b;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    a.v[i] = gid * 2654435761u + i * 40503u + 1;
+    b.v[i] = gid * 2246822519u + i * 3266489917u + 7;
+  }
+#pragma unroll 1
+  for (int k = 0; k < iters; k += 2) {
+    fe_mul(a, a, b);
+    fe_mul(b, b, a);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; i++) out[(size_t)gid * 16 + i] = a.v[i] ^ b.v[i];
+}
+
+__global__ void __launch_bounds__(256) k_bench_sq32(uint32_t* out, int iters) {
+  uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+  fe a;
+#pragma unroll
+  for (int i = 0; i < 8; i++) a.v[i] = gid * 2654435761u + i * 40503u + 1;
+#pragma unroll 1
+  for (int k = 0; k < iters; k += 2) {
+    fe_sq(a, a);
+    fe_sq(a, a);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; i++) out[(size_t)gid * 16 + i] = a.v[i];
+}
+
+// ---- 5 x 51-bit limbs, 64x64->128 products (the layout of dalek's u64 backend, FieldElement51::mul [ext]) --
+struct fe51 { unsigned long long v[5]; };
+__device__ __forceinline__ void fe51_mul(fe51& r, const fe51& a, const fe51& b) {
+  typedef unsigned __int128 u128;
+  const unsigned long long M = 0x7ffffffffffffULL;
+  unsigned long long b1_19 = b.v[1] * 19, b2_19 = b.v[2] * 19, b3_19 = b.v[3] * 19, b4_19 = b.v[4] * 19;
+  u128 c0 = (u128)a.v[0] * b.v[0] + (u128)a.v[4] * b1_19 + (u128)a.v[3] * b2_19 + (u128)a.v[2] * b3_19 + (u128)a.v[1] * b4_19;
+  u128 c1 = (u128)a.v[1] * b.v[0] + (u128)a.v[0] * b.v[1] + (u128)a.v[4] * b2_19 + (u128)a.v[3] * b3_19 + (u128)a.v[2] * b4_19;
+  u128 c2 = (u128)a.v[2] * b.v[0] + (u128)a.v[1] * b.v[1] + (u128)a.v[0] * b.v[2] + (u128)a.v[4] * b3_19 + (u128)a.v[3] * b4_19;
+  u128 c3 = (u128)a.v[3] * b.v[0] + (u128)a.v[2] * b.v[1] + (u128)a.v[1] * b.v[2] + (u128)a.v[0] * b.v[3] + (u128)a.v[4] * b4_19;
+  u128 c4 = (u128)a.v[4] * b.v[0] + (u128)a.v[3] * b.v[1] + (u128)a.v[2] * b.v[2] + (u128)a.v[1] * b.v[3] + (u128)a.v[0] * b.v[4];
+  c1 += (unsigned long long)(c0 >> 51);
+  unsigned long long o0 = (unsigned long long)c0 & M;
+  c2 += (unsigned long long)(c1 >> 51);
+  unsigned long long o1 = (unsigned long long)c1 & M;
+  c3 += (unsigned long long)(c2 >> 51);
+  unsigned long long o2 = (unsigned long long)c2 & M;
+  c4 += (unsigned long long)(c3 >> 51);
+  unsigned long long o3 = (unsigned long long)c3 & M;
+  unsigned long long carry = (unsigned long long)(c4 >> 51);
+  unsigned long long o4 = (unsigned long long)c4 & M;
+  o0 += carry * 19;
+  o1 += o0 >> 51;
+  o0 &= M;
+  r.v[0] = o0; r.v[1] = o1; r.v[2] = o2; r.v[3] = o3; r.v[4] = o4;
+}
+
+__global__ void __launch_bounds__(256) k_bench_mul51(unsigned long long* out, int iters) {
+  uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+  fe51 a, b;
+#pragma unroll
+  for (int i = 0; i < 5; i++) {
+    a.v[i] = ((unsigned long long)gid * 0x9E3779B97F4A7C15ULL + i * 0xD1B54A32D192ED03ULL) & 0x7ffffffffffffULL;
+    b.v[i] = ((unsigned long long)gid * 0xC2B2AE3D27D4EB4FULL + i * 0x165667B19E3779F9ULL) & 0x7ffffffffffffULL;
+  }
+#pragma unroll 1
+  for (int k = 0; k < iters; k += 2) {
+    fe51_mul(a, a, b);
+    fe51_mul(b, b, a);
+  }
+#pragma unroll
+  for (int i = 0; i < 5; i++) out[(size_t)gid * 8 + i] = a.v[i] ^ b.v[i];
+}
+
+// ---- 10 x 25.5-bit limbs, 32x32->64 products accumulated lazily (dalek's u32 backend / ref10 layout) ------
+struct fe25 { uint32_t v[10]; };
+__device__ __forceinline__ void fe25_mul(fe25& r, const fe25& f, const fe25& g) {
+  uint32_t g19[10], f2[10];
+#pragma unroll
+  for (int i = 0; i < 10; i++) { g19[i] = 19u * g.v[i]; f2[i] = (i & 1) ? 2u * f.v[i] : f.v[i]; }
+  unsigned long long h[10];
+#pragma unroll
+  for (int k = 0; k < 10; k++) {
+    unsigned long long s = 0;
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+      int j = k - i;
+      bool wrap = j < 0;
+      if (wrap) j += 10;
+      // odd*odd products carry a factor 2 (26/25-bit alternating radix)
+      uint32_t fi = ((i & 1) && (j & 1)) ? f2[i] : f.v[i];
+      uint32_t gj = wrap ? g19[j] : g.v[j];
+      s += (unsigned long long)fi * gj;
+    }
+    h[k] = s;
+  }
+  // carry chain: limbs alternate 26 / 25 bits
+  unsigned long long c;
+#pragma unroll
+  for (int i = 0; i < 9; i++) {
+    int bits = (i & 1) ? 25 : 26;
+    c = h[i] >> bits;
+    h[i] &= (1ull << bits) - 1;
+    h[i + 1] += c;
+  }
+  c = h[9] >> 25;
+  h[9] &= (1ull << 25) - 1;
+  h[0] += 19 * c;
+  c = h[0] >> 26;
+  h[0] &= (1ull << 26) - 1;
+  h[1] += c;
+#pragma unroll
+  for (int i = 0; i < 10; i++) r.v[i] = (uint32_t)h[i];
+}
+
+__global__ void __launch_bounds__(256) k_bench_mul25(uint32_t* out, int iters) {
+  uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+  fe25 a, b;
+#pragma unroll
+  for (int i = 0; i < 10; i++) {
+    a.v[i] = (gid * 2654435761u + i * 40503u + 1) & 0x1ffffffu;
+    b.v[i] = (gid * 2246822519u + i * 3266489917u + 7) & 0x1ffffffu;
+  }
+#pragma unroll 1
+  for (int k = 0; k < iters; k += 2) {
+    fe25_mul(a, a, b);
+    fe25_mul(b, b, a);
+  }
+#pragma unroll
+  for (int i = 0; i < 10; i++) out[(size_t)gid * 16 + i] = a.v[i] ^ b.v[i];
+}
+
+}  // namespace zkp

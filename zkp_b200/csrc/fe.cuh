@@ -1,0 +1,635 @@
+// GF(2^255-19) arithmetic for sm_100a, entirely in registers.
+//
+// Replaces curve25519-dalek 2.x `backend/serial/u64/field.rs` (FieldElement51) [ext] -- SURVEY.md section 2.2
+// row E6 -- underneath every hot-path call of the reference (decompress: toolbox/verifier.rs:90,164,
+// toolbox/batch_verifier.rs:226; compress: toolbox/mod.rs:180,204; MSM: prover.rs:94, verifier.rs:97,162,
+// batch_verifier.rs:219).
+//
+// Representation.  The radix-2^51 five-limb form (dalek's, and the one north_star names) stays the
+// *interface* layout for limb-form points (include/zkp_b200.h).  Inside the kernels an element is eight
+// saturated 32-bit limbs, any value in [0, 2^256) standing for its residue mod p: Blackwell's integer
+// multiplier is a 32x32->64 IMAD.WIDE on the FMA pipe, and ptxas fuses each `mad.lo.cc / madc.hi.cc` pair
+// below into ONE `IMAD.WIDE.U32.X` with predicate carry-in/out, so a multiply costs 64+8 wide IMADs versus
+// ~100 for 5x51 (each 64x64->128 product = 4 IMAD.WIDE) or 10x25.5 limbs.  `bench_fe` measures all of them
+// on the device ("field multiplier ablation").  Results are bit-exact whatever the internal radix
+// because every output is canonicalised in fe_tobytes.
+//
+// Every carry chain is one self-contained asm block (no condition-code state crosses statements).
+// With -DZKP_HOST_EMUL the same source compiles for the host with the asm blocks replaced by 64-bit C
+// (tests/host_emul): the kernel *logic* is checked against the oracle on CPU; that build is test
+// infrastructure, never a fallback.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__) && !defined(ZKP_HOST_EMUL)
+#define ZKP_DEV __device__ __forceinline__
+#define ZKP_DEVICE_ASM 1
+#else
+#define ZKP_DEV static inline
+#define ZKP_DEVICE_ASM 0
+#endif
+
+namespace zkp {
+
+struct fe { uint32_t v[8]; };
+
+// ------------------------------------------------------------------------------------------------------
+// carry-chain primitives
+// ------------------------------------------------------------------------------------------------------
+
+// acc[0..2n-1] += (a0,a1,..)*b laid out as non-overlapping 64-bit pairs; returns the carry out (0/1).
+ZKP_DEV uint32_t mad4(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b) {
+#if ZKP_DEVICE_ASM
+  uint32_t c;
+  asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+      "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+      "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+      "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+      "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+      "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+      "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+      "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+      "addc.u32 %8, 0, 0;"
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]),
+        "+r"(acc[7]), "=r"(c)
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
+  return c;
+#else
+  const uint32_t a[4] = {a0, a1, a2, a3};
+  uint64_t c = 0;
+  for (int k = 0; k < 4; k++) {
+    uint64_t p = (uint64_t)a[k] * b;
+    uint64_t lo = (uint64_t)acc[2 * k] + (uint32_t)p + c;
+    acc[2 * k] = (uint32_t)lo;
+    uint64_t hi = (uint64_t)acc[2 * k + 1] + (uint32_t)(p >> 32) + (lo >> 32);
+    acc[2 * k + 1] = (uint32_t)hi;
+    c = hi >> 32;
+  }
+  return (uint32_t)c;
+#endif
+}
+
+ZKP_DEV uint32_t mad3(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t b) {
+#if ZKP_DEVICE_ASM
+  uint32_t c;
+  asm("mad.lo.cc.u32 %0, %7, %10, %0;\n\t"
+      "madc.hi.cc.u32 %1, %7, %10, %1;\n\t"
+      "madc.lo.cc.u32 %2, %8, %10, %2;\n\t"
+      "madc.hi.cc.u32 %3, %8, %10, %3;\n\t"
+      "madc.lo.cc.u32 %4, %9, %10, %4;\n\t"
+      "madc.hi.cc.u32 %5, %9, %10, %5;\n\t"
+      "addc.u32 %6, 0, 0;"
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "=r"(c)
+      : "r"(a0), "r"(a1), "r"(a2), "r"(b));
+  return c;
+#else
+  const uint32_t a[3] = {a0, a1, a2};
+  uint64_t c = 0;
+  for (int k = 0; k < 3; k++) {
+    uint64_t p = (uint64_t)a[k] * b;
+    uint64_t lo = (uint64_t)acc[2 * k] + (uint32_t)p + c;
+    acc[2 * k] = (uint32_t)lo;
+    uint64_t hi = (uint64_t)acc[2 * k + 1] + (uint32_t)(p >> 32) + (lo >> 32);
+    acc[2 * k + 1] = (uint32_t)hi;
+    c = hi >> 32;
+  }
+  return (uint32_t)c;
+#endif
+}
+
+ZKP_DEV uint32_t mad2(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t b) {
+#if ZKP_DEVICE_ASM
+  uint32_t c;
+  asm("mad.lo.cc.u32 %0, %5, %7, %0;\n\t"
+      "madc.hi.cc.u32 %1, %5, %7, %1;\n\t"
+      "madc.lo.cc.u32 %2, %6, %7, %2;\n\t"
+      "madc.hi.cc.u32 %3, %6, %7, %3;\n\t"
+      "addc.u32 %4, 0, 0;"
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "=r"(c)
+      : "r"(a0), "r"(a1), "r"(b));
+  return c;
+#else
+  const uint32_t a[2] = {a0, a1};
+  uint64_t c = 0;
+  for (int k = 0; k < 2; k++) {
+    uint64_t p = (uint64_t)a[k] * b;
+    uint64_t lo = (uint64_t)acc[2 * k] + (uint32_t)p + c;
+    acc[2 * k] = (uint32_t)lo;
+    uint64_t hi = (uint64_t)acc[2 * k + 1] + (uint32_t)(p >> 32) + (lo >> 32);
+    acc[2 * k + 1] = (uint32_t)hi;
+    c = hi >> 32;
+  }
+  return (uint32_t)c;
+#endif
+}
+
+ZKP_DEV uint32_t mad1(uint32_t* acc, uint32_t a0, uint32_t b) {
+#if ZKP_DEVICE_ASM
+  uint32_t c;
+  asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
+      "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+      "addc.u32 %2, 0, 0;"
+      : "+r"(acc[0]), "+r"(acc[1]), "=r"(c)
+      : "r"(a0), "r"(b));
+  return c;
+#else
+  uint64_t p = (uint64_t)a0 * b;
+  uint64_t lo = (uint64_t)acc[0] + (uint32_t)p;
+  acc[0] = (uint32_t)lo;
+  uint64_t hi = (uint64_t)acc[1] + (uint32_t)(p >> 32) + (lo >> 32);
+  acc[1] = (uint32_t)hi;
+  return (uint32_t)(hi >> 32);
+#endif
+}
+
+// (lo,hi) = a*b  -- a single IMAD.WIDE.U32
+ZKP_DEV void mulw(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+  uint64_t p = (uint64_t)a * b;
+  lo = (uint32_t)p;
+  hi = (uint32_t)(p >> 32);
+}
+
+// acc[0..7] += (a0^2, a1^2, a2^2, a3^2) as pairs, + cin; returns carry out
+ZKP_DEV uint32_t sqr4c(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t cin) {
+#if ZKP_DEVICE_ASM
+  uint32_t c;
+  asm("{\n\t.reg .u32 t;\n\t"
+      "add.cc.u32 t, %13, 0xffffffff;\n\t"
+      "madc.lo.cc.u32 %0, %9, %9, %0;\n\t"
+      "madc.hi.cc.u32 %1, %9, %9, %1;\n\t"
+      "madc.lo.cc.u32 %2, %10, %10, %2;\n\t"
+      "madc.hi.cc.u32 %3, %10, %10, %3;\n\t"
+      "madc.lo.cc.u32 %4, %11, %11, %4;\n\t"
+      "madc.hi.cc.u32 %5, %11, %11, %5;\n\t"
+      "madc.lo.cc.u32 %6, %12, %12, %6;\n\t"
+      "madc.hi.cc.u32 %7, %12, %12, %7;\n\t"
+      "addc.u32 %8, 0, 0;\n\t}"
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]),
+        "+r"(acc[7]), "=r"(c)
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(cin));
+  return c;
+#else
+  const uint32_t a[4] = {a0, a1, a2, a3};
+  uint64_t c = cin;
+  for (int k = 0; k < 4; k++) {
+    uint64_t p = (uint64_t)a[k] * a[k];
+    uint64_t lo = (uint64_t)acc[2 * k] + (uint32_t)p + c;
+    acc[2 * k] = (uint32_t)lo;
+    uint64_t hi = (uint64_t)acc[2 * k + 1] + (uint32_t)(p >> 32) + (lo >> 32);
+    acc[2 * k + 1] = (uint32_t)hi;
+    c = hi >> 32;
+  }
+  return (uint32_t)c;
+#endif
+}
+
+// r[0..7] = a[0..7] + b[0..7]; returns carry out
+ZKP_DEV uint32_t add8(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+#if ZKP_DEVICE_ASM
+  uint32_t c;
+  asm("add.cc.u32 %0, %9, %17;\n\t"
+      "addc.cc.u32 %1, %10, %18;\n\t"
+      "addc.cc.u32 %2, %11, %19;\n\t"
+      "addc.cc.u32 %3, %12, %20;\n\t"
+      "addc.cc.u32 %4, %13, %21;\n\t"
+      "addc.cc.u32 %5, %14, %22;\n\t"
+      "addc.cc.u32 %6, %15, %23;\n\t"
+      "addc.cc.u32 %7, %16, %24;\n\t"
+      "addc.u32 %8, 0, 0;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(c)
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+        "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+  return c;
+#else
+  uint64_t c = 0;
+  uint32_t t[8];
+  for (int i = 0; i < 8; i++) {
+    uint64_t s = (uint64_t)a[i] + b[i] + c;
+    t[i] = (uint32_t)s;
+    c = s >> 32;
+  }
+  for (int i = 0; i < 8; i++) r[i] = t[i];
+  return (uint32_t)c;
+#endif
+}
+
+// r[0..7] = a[0..7] + b[0..7] + cin; returns carry out
+ZKP_DEV uint32_t add8c(uint32_t* r, const uint32_t* a, const uint32_t* b, uint32_t cin) {
+#if ZKP_DEVICE_ASM
+  uint32_t c;
+  asm("{\n\t.reg .u32 t;\n\t"
+      "add.cc.u32 t, %25, 0xffffffff;\n\t"
+      "addc.cc.u32 %0, %9, %17;\n\t"
+      "addc.cc.u32 %1, %10, %18;\n\t"
+      "addc.cc.u32 %2, %11, %19;\n\t"
+      "addc.cc.u32 %3, %12, %20;\n\t"
+      "addc.cc.u32 %4, %13, %21;\n\t"
+      "addc.cc.u32 %5, %14, %22;\n\t"
+      "addc.cc.u32 %6, %15, %23;\n\t"
+      "addc.cc.u32 %7, %16, %24;\n\t"
+      "addc.u32 %8, 0, 0;\n\t}"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(c)
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+        "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]), "r"(cin));
+  return c;
+#else
+  uint64_t c = cin;
+  uint32_t t[8];
+  for (int i = 0; i < 8; i++) {
+    uint64_t s = (uint64_t)a[i] + b[i] + c;
+    t[i] = (uint32_t)s;
+    c = s >> 32;
+  }
+  for (int i = 0; i < 8; i++) r[i] = t[i];
+  return (uint32_t)c;
+#endif
+}
+
+// r[0..7] = a[0..7] - b[0..7]; returns borrow out (0/1)
+ZKP_DEV uint32_t sub8(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+#if ZKP_DEVICE_ASM
+  uint32_t c;
+  asm("sub.cc.u32 %0, %9, %17;\n\t"
+      "subc.cc.u32 %1, %10, %18;\n\t"
+      "subc.cc.u32 %2, %11, %19;\n\t"
+      "subc.cc.u32 %3, %12, %20;\n\t"
+      "subc.cc.u32 %4, %13, %21;\n\t"
+      "subc.cc.u32 %5, %14, %22;\n\t"
+      "subc.cc.u32 %6, %15, %23;\n\t"
+      "subc.cc.u32 %7, %16, %24;\n\t"
+      "subc.u32 %8, 0, 0;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(c)
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+        "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+  return c & 1u;
+#else
+  uint64_t br = 0;
+  uint32_t t[8];
+  for (int i = 0; i < 8; i++) {
+    uint64_t s = (uint64_t)a[i] - b[i] - br;
+    t[i] = (uint32_t)s;
+    br = (s >> 32) & 1;
+  }
+  for (int i = 0; i < 8; i++) r[i] = t[i];
+  return (uint32_t)br;
+#endif
+}
+
+// r[0..7] += k (a small word), returns carry out.
+ZKP_DEV uint32_t add_word8(uint32_t* r, uint32_t k) {
+#if ZKP_DEVICE_ASM
+  uint32_t c;
+  asm("add.cc.u32 %0, %0, %9;\n\t"
+      "addc.cc.u32 %1, %1, 0;\n\t"
+      "addc.cc.u32 %2, %2, 0;\n\t"
+      "addc.cc.u32 %3, %3, 0;\n\t"
+      "addc.cc.u32 %4, %4, 0;\n\t"
+      "addc.cc.u32 %5, %5, 0;\n\t"
+      "addc.cc.u32 %6, %6, 0;\n\t"
+      "addc.cc.u32 %7, %7, 0;\n\t"
+      "addc.u32 %8, 0, 0;"
+      : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "=r"(c)
+      : "r"(k));
+  return c;
+#else
+  uint64_t c = k;
+  for (int i = 0; i < 8; i++) {
+    uint64_t s = (uint64_t)r[i] + c;
+    r[i] = (uint32_t)s;
+    c = s >> 32;
+  }
+  return (uint32_t)c;
+#endif
+}
+
+// r[0..7] -= k, returns borrow out.
+ZKP_DEV uint32_t sub_word8(uint32_t* r, uint32_t k) {
+#if ZKP_DEVICE_ASM
+  uint32_t c;
+  asm("sub.cc.u32 %0, %0, %9;\n\t"
+      "subc.cc.u32 %1, %1, 0;\n\t"
+      "subc.cc.u32 %2, %2, 0;\n\t"
+      "subc.cc.u32 %3, %3, 0;\n\t"
+      "subc.cc.u32 %4, %4, 0;\n\t"
+      "subc.cc.u32 %5, %5, 0;\n\t"
+      "subc.cc.u32 %6, %6, 0;\n\t"
+      "subc.cc.u32 %7, %7, 0;\n\t"
+      "subc.u32 %8, 0, 0;"
+      : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "=r"(c)
+      : "r"(k));
+  return c & 1u;
+#else
+  uint64_t br = k;
+  for (int i = 0; i < 8; i++) {
+    uint64_t s = (uint64_t)r[i] - br;
+    r[i] = (uint32_t)s;
+    br = (s >> 32) & 1;
+  }
+  return (uint32_t)br;
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------------
+// reduction of a 16-limb product t (value < 2^512) to 8 limbs (< 2^256): 2^256 = 38 (mod p)
+// ------------------------------------------------------------------------------------------------------
+ZKP_DEV void fe_reduce512(fe& r, const uint32_t* t) {
+  uint32_t lo[9], od[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) lo[i] = t[i];
+  // even high limbs: 38*t[8,10,12,14] lands on pairs (0,1)(2,3)(4,5)(6,7); carry has weight 2^256
+  lo[8] = mad4(lo, t[8], t[10], t[12], t[14], 38u);
+  // odd high limbs: 38*t[9,11,13,15] lands on limbs 1..8
+  mulw(od[0], od[1], t[9], 38u);
+  mulw(od[2], od[3], t[11], 38u);
+  mulw(od[4], od[5], t[13], 38u);
+  mulw(od[6], od[7], t[15], 38u);
+  add8(lo + 1, lo + 1, od);        // lo[8] <= 1 + 37 + 1: no carry out
+  uint32_t c3 = add_word8(lo, lo[8] * 38u);
+  lo[0] += 38u * c3;  // if c3, lo is tiny: cannot carry again
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = lo[i];
+}
+
+// r = a*b mod p (weak: r < 2^256)
+ZKP_DEV void fe_mul(fe& r, const fe& a, const fe& b) {
+  const uint32_t* A = a.v;
+  const uint32_t* B = b.v;
+  uint32_t E[17], O[17];
+#pragma unroll
+  for (int i = 0; i < 17; i++) { E[i] = 0; O[i] = 0; }
+  // row 0 (fresh accumulators: plain wide multiplies)
+  mulw(E[0], E[1], A[0], B[0]); mulw(E[2], E[3], A[2], B[0]);
+  mulw(E[4], E[5], A[4], B[0]); mulw(E[6], E[7], A[6], B[0]);
+  mulw(O[0], O[1], A[1], B[0]); mulw(O[2], O[3], A[3], B[0]);
+  mulw(O[4], O[5], A[5], B[0]); mulw(O[6], O[7], A[7], B[0]);
+#pragma unroll
+  for (int i = 1; i < 8; i += 2) {
+    // odd row i: even a -> O[i-1 ..], carry into the fresh limb above; odd a -> E[i+1 ..]
+    O[i + 7] = mad4(O + i - 1, A[0], A[2], A[4], A[6], B[i]);
+    mad4(E + i + 1, A[1], A[3], A[5], A[7], B[i]);
+    if (i + 1 < 8) {
+      // even row i+1: even a -> E[i+1 ..], carry into fresh limb; odd a -> O[i+1 ..]
+      E[i + 9] = mad4(E + i + 1, A[0], A[2], A[4], A[6], B[i + 1]);
+      mad4(O + i + 1, A[1], A[3], A[5], A[7], B[i + 1]);
+    }
+  }
+  // t = E + (O << 32)
+  uint32_t t[17];
+  t[0] = E[0];
+  uint32_t c = add8(t + 1, E + 1, O);
+  add8c(t + 9, E + 9, O + 8, c);   // t[16] = 0
+  fe_reduce512(r, t);
+}
+
+// r = a^2 mod p
+ZKP_DEV void fe_sq(fe& r, const fe& a) {
+  const uint32_t* A = a.v;
+  uint32_t E[17], O[17];
+#pragma unroll
+  for (int i = 0; i < 17; i++) { E[i] = 0; O[i] = 0; }
+  // cross products a_i*a_j, i<j; (i+j) even -> E[i+j], odd -> O[i+j-1]
+  // row 0
+  mulw(E[2], E[3], A[2], A[0]); mulw(E[4], E[5], A[4], A[0]); mulw(E[6], E[7], A[6], A[0]);
+  mulw(O[0], O[1], A[1], A[0]); mulw(O[2], O[3], A[3], A[0]);
+  mulw(O[4], O[5], A[5], A[0]); mulw(O[6], O[7], A[7], A[0]);
+  // row 1: j=3,5,7 -> E[4..9]; j=2,4,6 -> O[2..7]
+  mad3(E + 4, A[3], A[5], A[7], A[1]);
+  O[8] = mad3(O + 2, A[2], A[4], A[6], A[1]);
+  // row 2: j=4,6 -> E[6..9]; j=3,5,7 -> O[4..9]
+  E[10] = mad2(E + 6, A[4], A[6], A[2]);
+  mad3(O + 4, A[3], A[5], A[7], A[2]);
+  // row 3: j=5,7 -> E[8..11]; j=4,6 -> O[6..9]
+  mad2(E + 8, A[5], A[7], A[3]);
+  O[10] = mad2(O + 6, A[4], A[6], A[3]);
+  // row 4: j=6 -> E[10,11]; j=5,7 -> O[8..11]
+  E[12] = mad1(E + 10, A[6], A[4]);
+  mad2(O + 8, A[5], A[7], A[4]);
+  // row 5: j=7 -> E[12,13]; j=6 -> O[10,11]
+  mad1(E + 12, A[7], A[5]);
+  O[12] = mad1(O + 10, A[6], A[5]);
+  // row 6: j=7 -> O[12,13]
+  mad1(O + 12, A[7], A[6]);
+  // cross = E + (O << 32): limbs 1..15
+  uint32_t x[17];
+  x[0] = 0;
+  uint32_t c = add8(x + 1, E + 1, O);
+  add8c(x + 9, E + 9, O + 8, c);   // x[15] picks up the last carry, x[16] = 0
+  // double it (funnel shifts: independent, no carry chain)
+  uint32_t t[16];
+  t[0] = 0;
+#pragma unroll
+  for (int i = 1; i < 16; i++) t[i] = (x[i] << 1) | (x[i - 1] >> 31);
+  // add the squares a_i^2 at limb 2i
+  uint32_t c2 = sqr4c(t, A[0], A[1], A[2], A[3], 0u);
+  sqr4c(t + 8, A[4], A[5], A[6], A[7], c2);
+  fe_reduce512(r, t);
+}
+
+// r = a + b
+ZKP_DEV void fe_add(fe& r, const fe& a, const fe& b) {
+  uint32_t t[8];
+  uint32_t c = add8(t, a.v, b.v);
+  uint32_t c2 = add_word8(t, 38u * c);
+  t[0] += 38u * c2;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = t[i];
+}
+
+// r = a - b
+ZKP_DEV void fe_sub(fe& r, const fe& a, const fe& b) {
+  uint32_t t[8];
+  uint32_t br = sub8(t, a.v, b.v);
+  uint32_t b2 = sub_word8(t, 38u * br);
+  t[0] -= 38u * b2;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = t[i];
+}
+
+ZKP_DEV void fe_zero(fe& r) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = 0;
+}
+ZKP_DEV void fe_one(fe& r) {
+  fe_zero(r);
+  r.v[0] = 1;
+}
+ZKP_DEV void fe_neg(fe& r, const fe& a) {
+  fe z;
+  fe_zero(z);
+  fe_sub(r, z, a);
+}
+// r = 2a
+ZKP_DEV void fe_dbl(fe& r, const fe& a) { fe_add(r, a, a); }
+
+// r = flag ? b : a   (flag is 0/1; branch-free)
+ZKP_DEV void fe_select(fe& r, const fe& a, const fe& b, uint32_t flag) {
+  uint32_t m = 0u - flag;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = a.v[i] ^ (m & (a.v[i] ^ b.v[i]));
+}
+ZKP_DEV void fe_cswap(fe& a, fe& b, uint32_t flag) {
+  uint32_t m = 0u - flag;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    uint32_t x = m & (a.v[i] ^ b.v[i]);
+    a.v[i] ^= x;
+    b.v[i] ^= x;
+  }
+}
+
+// canonical representative in [0, p)
+ZKP_DEV void fe_canon(fe& r, const fe& a) {
+  uint32_t t[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) t[i] = a.v[i];
+  // fold bit 255 twice: afterwards t < 2^255 + 19 - ... then a conditional subtract of p
+  uint32_t top = t[7] >> 31;
+  t[7] &= 0x7fffffffu;
+  add_word8(t, 19u * top);  // t < 2^255 + 19
+  top = t[7] >> 31;
+  t[7] &= 0x7fffffffu;
+  add_word8(t, 19u * top);  // t < 2^255 now (if the first fold overflowed bit 255 the rest is tiny)
+  // t >= p  <=>  t + 19 >= 2^255
+  uint32_t u[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) u[i] = t[i];
+  add_word8(u, 19u);
+  uint32_t ge = u[7] >> 31;
+  u[7] &= 0x7fffffffu;
+  uint32_t m = 0u - ge;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = t[i] ^ (m & (t[i] ^ u[i]));
+}
+
+ZKP_DEV uint32_t fe_is_zero(const fe& a) {
+  fe c;
+  fe_canon(c, a);
+  uint32_t o = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) o |= c.v[i];
+  return o == 0 ? 1u : 0u;
+}
+ZKP_DEV uint32_t fe_is_negative(const fe& a) {
+  fe c;
+  fe_canon(c, a);
+  return c.v[0] & 1u;
+}
+ZKP_DEV uint32_t fe_eq(const fe& a, const fe& b) {
+  fe d;
+  fe_sub(d, a, b);
+  return fe_is_zero(d);
+}
+// r = neg ? -a : a
+ZKP_DEV void fe_cneg(fe& r, const fe& a, uint32_t neg) {
+  fe n;
+  fe_neg(n, a);
+  fe_select(r, a, n, neg);
+}
+ZKP_DEV void fe_abs(fe& r, const fe& a) { fe_cneg(r, a, fe_is_negative(a)); }
+
+// r = a^(2^k)
+ZKP_DEV void fe_sqn(fe& r, const fe& a, int k) {
+  fe t = a;
+#if ZKP_DEVICE_ASM
+#pragma unroll 1
+#endif
+  for (int i = 0; i < k; i++) fe_sq(t, t);
+  r = t;
+}
+
+// a^(2^250 - 1) and a^11 (the shared head of invert and pow22523; dalek field.rs pow22501 [ext])
+ZKP_DEV void fe_pow22501(fe& t19, fe& t3, const fe& a) {
+  fe t0, t1, t2, t4, t5, t6, t7, t8, t9, t10, t11, t12, t13, t14, t15, t16, t17, t18;
+  fe_sq(t0, a);          // 2
+  fe_sqn(t1, t0, 2);     // 8
+  fe_mul(t2, a, t1);     // 9
+  fe_mul(t3, t0, t2);    // 11
+  fe_sq(t4, t3);         // 22
+  fe_mul(t5, t2, t4);    // 31 = 2^5-1
+  fe_sqn(t6, t5, 5);
+  fe_mul(t7, t6, t5);    // 2^10-1
+  fe_sqn(t8, t7, 10);
+  fe_mul(t9, t8, t7);    // 2^20-1
+  fe_sqn(t10, t9, 20);
+  fe_mul(t11, t10, t9);  // 2^40-1
+  fe_sqn(t12, t11, 10);
+  fe_mul(t13, t12, t7);  // 2^50-1
+  fe_sqn(t14, t13, 50);
+  fe_mul(t15, t14, t13); // 2^100-1
+  fe_sqn(t16, t15, 100);
+  fe_mul(t17, t16, t15); // 2^200-1
+  fe_sqn(t18, t17, 50);
+  fe_mul(t19, t18, t13); // 2^250-1
+}
+// a^(p-2)
+ZKP_DEV void fe_invert(fe& r, const fe& a) {
+  fe t19, t3, t20;
+  fe_pow22501(t19, t3, a);
+  fe_sqn(t20, t19, 5);
+  fe_mul(r, t20, t3);
+}
+// a^((p-5)/8) = a^(2^252 - 3)
+ZKP_DEV void fe_pow22523(fe& r, const fe& a) {
+  fe t19, t3, t20;
+  fe_pow22501(t19, t3, a);
+  fe_sqn(t20, t19, 2);
+  fe_mul(r, a, t20);
+}
+
+// 32 little-endian bytes (as 8 words) -> element; bit 255 is ignored like dalek's from_bytes.
+ZKP_DEV void fe_from_words(fe& r, const uint32_t* w) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = w[i];
+  r.v[7] &= 0x7fffffffu;
+}
+ZKP_DEV void fe_to_words(uint32_t* w, const fe& a) {
+  fe c;
+  fe_canon(c, a);
+#pragma unroll
+  for (int i = 0; i < 8; i++) w[i] = c.v[i];
+}
+
+// dalek FieldElement51 limb form (5 x u64, 51 bits each, possibly unreduced up to 2^54) <-> fe
+ZKP_DEV void fe_from_limbs51(fe& r, const uint64_t* l) {
+  // value = sum l[i] 2^(51 i); limbs may exceed 51 bits slightly: accumulate with carries, fold 2^255 -> 19
+  unsigned long long acc[5];
+#pragma unroll
+  for (int i = 0; i < 5; i++) acc[i] = l[i];
+  // carry-propagate to 51 bits
+#pragma unroll
+  for (int rep = 0; rep < 2; rep++) {
+    unsigned long long c = 0;
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+      acc[i] += c;
+      c = acc[i] >> 51;
+      acc[i] &= 0x7ffffffffffffULL;
+    }
+    acc[0] += 19ULL * c;
+  }
+  // after two passes every limb is < 2^51: pack 5x51 -> 256 bits
+  unsigned long long w0 = acc[0] | (acc[1] << 51);
+  unsigned long long w1 = (acc[1] >> 13) | (acc[2] << 38);
+  unsigned long long w2 = (acc[2] >> 26) | (acc[3] << 25);
+  unsigned long long w3 = (acc[3] >> 39) | (acc[4] << 12);
+  r.v[0] = (uint32_t)w0; r.v[1] = (uint32_t)(w0 >> 32);
+  r.v[2] = (uint32_t)w1; r.v[3] = (uint32_t)(w1 >> 32);
+  r.v[4] = (uint32_t)w2; r.v[5] = (uint32_t)(w2 >> 32);
+  r.v[6] = (uint32_t)w3; r.v[7] = (uint32_t)(w3 >> 32);
+}
+ZKP_DEV void fe_to_limbs51(uint64_t* l, const fe& a) {
+  fe c;
+  fe_canon(c, a);
+  unsigned long long w0 = c.v[0] | ((unsigned long long)c.v[1] << 32);
+  unsigned long long w1 = c.v[2] | ((unsigned long long)c.v[3] << 32);
+  unsigned long long w2 = c.v[4] | ((unsigned long long)c.v[5] << 32);
+  unsigned long long w3 = c.v[6] | ((unsigned long long)c.v[7] << 32);
+  const unsigned long long M = 0x7ffffffffffffULL;
+  l[0] = w0 & M;
+  l[1] = ((w0 >> 51) | (w1 << 13)) & M;
+  l[2] = ((w1 >> 38) | (w2 << 26)) & M;
+  l[3] = ((w2 >> 25) | (w3 << 39)) & M;
+  l[4] = (w3 >> 12) & M;
+}
+
+}  // namespace zkp

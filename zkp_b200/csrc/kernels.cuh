@@ -1,0 +1,399 @@
+// CUDA kernels of the ristretto255 MSM engine (sm_100a).
+//
+// The variable-time path replaces curve25519-dalek 2.x `backend/serial/scalar_mul/pippenger.rs` +
+// `ristretto.rs` decompress/compress [ext] as reached from
+//   /root/reference/src/toolbox/batch_verifier.rs:219-230 (the north-star call), verifier.rs:97-106, :162-168.
+// Pipeline for one MSM of n terms, window width c, W = ceil(253/c) windows, B = 2^(c-1) buckets per window:
+//   k_decompress      32 B encoding -> 96 B affine-Niels point (y+x, y-x, 2dxy) in HBM, validity via atomicMin
+//   k_recode_hist     scalar -> sign fold -> signed digits; histogram of bucket loads  (hist[W][B])
+//   k_scan            exclusive scan per window                                         (offs[W][B+1], cursor)
+//   k_scatter         counting-sort scatter of (sign | term index) by bucket            (sorted[W][n])
+//   k_accumulate<G>   G lanes per bucket: gather Niels points, mixed additions, warp-shuffle tree reduce
+//   k_chunk_reduce    running-sum reduction of bucket rows in chunks of L (recursive levels)
+//   k_tree_sum        per-window sums of the chunk partials
+//   k_finish          per-window Horner over levels, Horner over windows, ristretto encode, identity/status
+// All group arithmetic is in registers (fe.cuh / ge.cuh); HBM traffic is 64 B in per term plus the
+// workspace streams listed in DESIGN.md.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "fe.cuh"
+#include "ge.cuh"
+#include "sc.cuh"
+
+namespace zkp {
+
+#define ZKP_CHUNK_L 32      // chunk length of the bucket running-sum reduction
+#define ZKP_CHUNK_LOG 5
+
+struct msm_result {          // layout documented in include/zkp_b200.h (zkp_msm_vartime_dev)
+  uint32_t enc[8];
+  int32_t status;
+  int32_t is_identity;
+  long long first_bad;
+};
+
+// flags[0] = first invalid point index (atomicMin, init 0x7fffffff), flags[1] = first bad scalar index
+__device__ __forceinline__ void load_words8(uint32_t* w, const uint4* p) {
+  uint4 a = __ldg(p), b = __ldg(p + 1);
+  w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+  w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+}
+__device__ __forceinline__ void store_fe(uint4* p, const fe& a) {
+  p[0] = make_uint4(a.v[0], a.v[1], a.v[2], a.v[3]);
+  p[1] = make_uint4(a.v[4], a.v[5], a.v[6], a.v[7]);
+}
+__device__ __forceinline__ void load_fe(fe& a, const uint4* p) {
+  uint4 x = p[0], y = p[1];
+  a.v[0] = x.x; a.v[1] = x.y; a.v[2] = x.z; a.v[3] = x.w;
+  a.v[4] = y.x; a.v[5] = y.y; a.v[6] = y.z; a.v[7] = y.w;
+}
+__device__ __forceinline__ void load_fe_ldg(fe& a, const uint4* p) {
+  uint4 x = __ldg(p), y = __ldg(p + 1);
+  a.v[0] = x.x; a.v[1] = x.y; a.v[2] = x.z; a.v[3] = x.w;
+  a.v[4] = y.x; a.v[5] = y.y; a.v[6] = y.z; a.v[7] = y.w;
+}
+__device__ __forceinline__ void store_ext(uint4* p, const ge_ext& q) {
+  store_fe(p, q.X); store_fe(p + 2, q.Y); store_fe(p + 4, q.Z); store_fe(p + 6, q.T);
+}
+__device__ __forceinline__ void load_ext(ge_ext& q, const uint4* p) {
+  load_fe(q.X, p); load_fe(q.Y, p + 2); load_fe(q.Z, p + 4); load_fe(q.T, p + 6);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K1: decompression.  One thread per point; ~254 squarings + ~25 multiplications, all in registers.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_decompress(const uint4* __restrict__ enc, size_t n, uint4* __restrict__ niels,
+                                                    int* __restrict__ flags) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t w[8];
+  load_words8(w, enc + 2 * i);
+  fe x, y, t;
+  uint32_t ok = ristretto_decode(x, y, t, w);
+  ge_aniels q;
+  if (ok) {
+    ge_aniels_from_affine(q, x, y, t);
+  } else {
+    ge_aniels_identity(q);
+    atomicMin(&flags[0], (int)i);
+  }
+  uint4* o = niels + 6 * i;
+  store_fe(o, q.yplusx);
+  store_fe(o + 2, q.yminusx);
+  store_fe(o + 4, q.xy2d);
+}
+
+// decompress to FieldElement51 limb form (zkp_decompress_batch)
+__global__ void __launch_bounds__(256) k_decompress_limbs(const uint4* __restrict__ enc, size_t n,
+                                                          unsigned long long* __restrict__ limbs,
+                                                          uint8_t* __restrict__ valid) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t w[8];
+  load_words8(w, enc + 2 * i);
+  fe x, y, t, z;
+  uint32_t ok = ristretto_decode(x, y, t, w);
+  if (!ok) { fe_zero(x); fe_one(y); fe_zero(t); }
+  fe_one(z);
+  unsigned long long* o = limbs + 20 * i;
+  fe_to_limbs51((uint64_t*)o, x);
+  fe_to_limbs51((uint64_t*)o + 5, y);
+  fe_to_limbs51((uint64_t*)o + 10, z);
+  fe_to_limbs51((uint64_t*)o + 15, t);
+  valid[i] = (uint8_t)ok;
+}
+
+__device__ __forceinline__ void load_ext_limbs51(ge_ext& p, const unsigned long long* l) {
+  fe_from_limbs51(p.X, (const uint64_t*)l);
+  fe_from_limbs51(p.Y, (const uint64_t*)l + 5);
+  fe_from_limbs51(p.Z, (const uint64_t*)l + 10);
+  fe_from_limbs51(p.T, (const uint64_t*)l + 15);
+}
+
+// compress from limb form (zkp_compress_batch)
+__global__ void __launch_bounds__(256) k_compress_limbs(const unsigned long long* __restrict__ limbs, size_t n,
+                                                        uint4* __restrict__ enc) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  ge_ext p;
+  load_ext_limbs51(p, limbs + 20 * i);
+  uint32_t w[8];
+  ristretto_encode(w, p);
+  enc[2 * i] = make_uint4(w[0], w[1], w[2], w[3]);
+  enc[2 * i + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K2/K4: scalar recode + histogram / scatter (counting sort by bucket, per window)
+// ---------------------------------------------------------------------------------------------------------
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) k_recode(const uint4* __restrict__ scalars, size_t n, int c, int W, uint32_t B,
+                                                uint32_t* __restrict__ counters,  // hist[W][B] or cursor[W][B]
+                                                uint32_t* __restrict__ sorted,    // [W][n] (SCATTER only)
+                                                int* __restrict__ flags) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t s[8], k[8];
+  load_words8(s, scalars + 2 * i);
+  uint32_t neg;
+  uint32_t canonical = sc_fold_sign(k, neg, s);
+  if (!canonical) {
+    if (!SCATTER) atomicMin(&flags[1], (int)i);
+    return;  // contributes nothing; the call fails with ZKP_ERR_SCALAR
+  }
+  uint32_t carry = 0;
+  for (int w = 0; w < W; w++) {
+    uint32_t mag, dneg;
+    sc_digit(mag, dneg, carry, k, w, c);
+    if (mag != 0) {
+      uint32_t* ctr = counters + (size_t)w * B + (mag - 1);
+      if (SCATTER) {
+        uint32_t pos = atomicAdd(ctr, 1u);
+        sorted[(size_t)w * n + pos] = (uint32_t)i | ((neg ^ dneg) << 31);
+      } else {
+        atomicAdd(ctr, 1u);
+      }
+    }
+  }
+}
+
+// K3: per-window exclusive scan.  One block (1024 threads) per window.
+__global__ void __launch_bounds__(1024) k_scan(const uint32_t* __restrict__ hist, uint32_t B,
+                                               uint32_t* __restrict__ offs,    // [W][B+1]
+                                               uint32_t* __restrict__ cursor)  // [W][B]
+{
+  __shared__ uint32_t warp_tot[32];
+  __shared__ uint32_t base_s;
+  const int w = blockIdx.x;
+  const uint32_t* h = hist + (size_t)w * B;
+  uint32_t* o = offs + (size_t)w * (B + 1);
+  uint32_t* cu = cursor + (size_t)w * B;
+  if (threadIdx.x == 0) base_s = 0;
+  __syncthreads();
+  for (uint32_t start = 0; start < B; start += 1024) {
+    uint32_t idx = start + threadIdx.x;
+    uint32_t v = idx < B ? h[idx] : 0u;
+    // inclusive warp scan
+    uint32_t x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+      if ((threadIdx.x & 31) >= d) x += y;
+    }
+    if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      uint32_t t = warp_tot[threadIdx.x];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, t, d);
+        if (threadIdx.x >= d) t += y;
+      }
+      warp_tot[threadIdx.x] = t;  // inclusive totals of warps
+    }
+    __syncthreads();
+    uint32_t warp_base = (threadIdx.x >> 5) ? warp_tot[(threadIdx.x >> 5) - 1] : 0u;
+    uint32_t excl = base_s + warp_base + x - v;
+    if (idx < B) { o[idx] = excl; cu[idx] = excl; }
+    __syncthreads();
+    if (threadIdx.x == 1023) base_s = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) o[B] = base_s;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K5: bucket accumulation.  G lanes cooperate on one bucket.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_aniels(ge_aniels& q, const uint4* __restrict__ niels, uint32_t e) {
+  const uint4* p = niels + (size_t)(e & 0x7fffffffu) * 6;
+  load_fe_ldg(q.yplusx, p);
+  load_fe_ldg(q.yminusx, p + 2);
+  load_fe_ldg(q.xy2d, p + 4);
+}
+
+__device__ __forceinline__ void shfl_down_ext(ge_ext& r, const ge_ext& p, int off, int width) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    r.X.v[i] = __shfl_down_sync(0xffffffffu, p.X.v[i], off, width);
+    r.Y.v[i] = __shfl_down_sync(0xffffffffu, p.Y.v[i], off, width);
+    r.Z.v[i] = __shfl_down_sync(0xffffffffu, p.Z.v[i], off, width);
+    r.T.v[i] = __shfl_down_sync(0xffffffffu, p.T.v[i], off, width);
+  }
+}
+
+template <int G>
+__global__ void __launch_bounds__(128) k_accumulate(const uint4* __restrict__ niels, const uint32_t* __restrict__ sorted,
+                                                    const uint32_t* __restrict__ offs, size_t n, uint32_t B,
+                                                    uint32_t total_buckets, uint4* __restrict__ buckets) {
+  const uint32_t gid = (uint32_t)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) / G);
+  const uint32_t lane = threadIdx.x % G;
+  uint32_t start = 0, end = 0;
+  const uint32_t* base = sorted;
+  if (gid < total_buckets) {
+    uint32_t w = gid / B, b = gid % B;
+    const uint32_t* o = offs + (size_t)w * (B + 1) + b;
+    start = o[0];
+    end = o[1];
+    base = sorted + (size_t)w * n;
+  }
+  ge_ext acc;
+  ge_identity(acc);
+  uint32_t i = start + lane;
+  ge_aniels cur;
+  uint32_t e_cur = 0;
+  if (i < end) {
+    e_cur = __ldg(base + i);
+    load_aniels(cur, niels, e_cur);
+  }
+  while (i < end) {
+    uint32_t inext = i + G;
+    ge_aniels nxt;
+    uint32_t e_nxt = 0;
+    if (inext < end) {  // software prefetch of the next gather while this addition runs
+      e_nxt = __ldg(base + inext);
+      load_aniels(nxt, niels, e_nxt);
+    }
+    ge_aniels_cneg(cur, e_cur >> 31);
+    ge_madd(acc, acc, cur);
+    cur = nxt;
+    e_cur = e_nxt;
+    i = inext;
+  }
+  // tree reduction across the G lanes
+#pragma unroll
+  for (int off = G / 2; off >= 1; off >>= 1) {
+    ge_ext other;
+    shfl_down_ext(other, acc, off, G);
+    ge_add(acc, acc, other);
+  }
+  if (lane == 0 && gid < total_buckets) store_ext(buckets + (size_t)gid * 8, acc);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K6: bucket reduction  S = sum_{i=0}^{m-1} (i+1) x_i  by chunked running sums (zero-based weights inside).
+//   chunk k (items kL .. kL+L-1):  T_k = sum x,  U_k = sum_j j * x_{kL+j}
+//   V(x) = sum_k U_k + L * V(T),  Tot(x) = Tot(T)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_chunk_reduce(const uint4* __restrict__ in, uint32_t m, int W,
+                                                      uint4* __restrict__ outT, uint4* __restrict__ outU) {
+  const uint32_t chunks = m / ZKP_CHUNK_L;
+  uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= chunks * (uint32_t)W) return;
+  uint32_t w = tid / chunks, k = tid % chunks;
+  const uint4* x = in + ((size_t)w * m + (size_t)k * ZKP_CHUNK_L) * 8;
+  ge_ext run, acc, p;
+  ge_identity(run);
+  ge_identity(acc);
+#pragma unroll 1
+  for (int j = ZKP_CHUNK_L - 1; j >= 1; j--) {
+    load_ext(p, x + (size_t)j * 8);
+    ge_add(run, run, p);
+    ge_add(acc, acc, run);
+  }
+  load_ext(p, x);
+  ge_add(run, run, p);
+  store_ext(outT + ((size_t)w * chunks + k) * 8, run);
+  store_ext(outU + ((size_t)w * chunks + k) * 8, acc);
+}
+
+// per-window sum of `cnt` points: one block of 256 threads per window
+__global__ void __launch_bounds__(256) k_tree_sum(const uint4* __restrict__ in, uint32_t cnt, uint4* __restrict__ out) {
+  __shared__ uint4 sm[8 * 8];  // one ext per warp
+  const int w = blockIdx.x;
+  const uint4* x = in + (size_t)w * cnt * 8;
+  ge_ext acc, p;
+  ge_identity(acc);
+  for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+    load_ext(p, x + (size_t)i * 8);
+    ge_add(acc, acc, p);
+  }
+#pragma unroll 1
+  for (int off = 16; off >= 1; off >>= 1) {
+    shfl_down_ext(p, acc, off, 32);
+    ge_add(acc, acc, p);
+  }
+  if ((threadIdx.x & 31) == 0) store_ext(sm + (threadIdx.x >> 5) * 8, acc);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    load_ext(acc, sm);
+    for (int k = 1; k < (int)(blockDim.x >> 5); k++) {
+      load_ext(p, sm + k * 8);
+      ge_add(acc, acc, p);
+    }
+    store_ext(out + (size_t)w * 8, acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K7: finish.  usum[level][W] (nl levels), last[W][m_last] = the items of the final (short) level.
+// One block, W threads for the per-window part, thread 0 for the Horner over windows + encode.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64) k_finish(const uint4* __restrict__ usum, int nl, const uint4* __restrict__ last,
+                                               uint32_t m_last, int W, int c, size_t n, const int* __restrict__ flags,
+                                               msm_result* __restrict__ res, uint4* __restrict__ partial_out) {
+  __shared__ uint4 sw[64 * 8];
+  const int w = threadIdx.x;
+  if (w < W) {
+    // final level: V = sum k*x_k (zero-based), Tot = sum x_k, by running sums from the top
+    ge_ext run, acc, p;
+    ge_identity(run);
+    ge_identity(acc);
+    const uint4* x = last + (size_t)w * m_last * 8;
+    for (int j = (int)m_last - 1; j >= 1; j--) {
+      load_ext(p, x + (size_t)j * 8);
+      ge_add(run, run, p);
+      ge_add(acc, acc, run);
+    }
+    load_ext(p, x);
+    ge_add(run, run, p);  // Tot
+    // Horner over the chunk levels: V = U[l] + L * V
+    for (int l = nl - 1; l >= 0; l--) {
+      for (int d = 0; d < ZKP_CHUNK_LOG; d++) ge_double(acc, acc);
+      load_ext(p, usum + ((size_t)l * W + w) * 8);
+      ge_add(acc, acc, p);
+    }
+    ge_add(acc, acc, run);  // weights are one-based: S = V + Tot
+    store_ext(sw + w * 8, acc);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ge_ext tot, p;
+    load_ext(tot, sw + (W - 1) * 8);
+    for (int ww = W - 2; ww >= 0; ww--) {
+      for (int d = 0; d < c; d++) ge_double(tot, tot);
+      load_ext(p, sw + ww * 8);
+      ge_add(tot, tot, p);
+    }
+    if (partial_out) store_ext(partial_out, tot);
+    uint32_t enc[8];
+    ristretto_encode(enc, tot);
+    uint32_t z = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { res->enc[i] = enc[i]; z |= enc[i]; }
+    int bad_pt = flags[0], bad_sc = flags[1];
+    int status = 0;
+    long long first_bad = -1;
+    if (bad_pt != 0x7fffffff) { status = 1; first_bad = bad_pt; }
+    else if (bad_sc != 0x7fffffff) { status = 3; first_bad = bad_sc; }
+    res->status = status;
+    res->is_identity = (z == 0) ? 1 : 0;
+    res->first_bad = first_bad;
+  }
+}
+
+// n == 0: the empty sum
+__global__ void k_empty_result(msm_result* res) {
+  for (int i = 0; i < 8; i++) res->enc[i] = 0;
+  res->status = 0;
+  res->is_identity = 1;
+  res->first_bad = -1;
+}
+
+__global__ void k_init_flags(int* flags) {
+  flags[0] = 0x7fffffff;
+  flags[1] = 0x7fffffff;
+}
+
+}  // namespace zkp

@@ -1,0 +1,216 @@
+// Batched small MSMs: one thread per MSM, M independent MSMs described CSR-style.
+//
+//   k_small_msm_vt   variable time; replaces Straus::optional_multiscalar_mul (curve25519-dalek 2.x
+//                    backend/serial/scalar_mul/straus.rs [ext], sizes < 190) as called per constraint at
+//                    /root/reference/src/toolbox/verifier.rs:97-106 and per proof at verifier.rs:162-166.
+//                    Signed binary (NAF) digits taken from k and 3k, no tables: registers only.
+//   k_small_msm_ct   constant time; replaces Straus::multiscalar_mul (radix-16 signed digits, table of
+//                    1P..8P, full-table scan) as called per constraint at /root/reference/src/toolbox/prover.rs:94-97,
+//                    fused with the compress of append_blinding_commitment (toolbox/mod.rs:204).
+//                    No branch and no address depends on a scalar: digits come from k + 0x88..8 (so that
+//                    nibble - 8 is the signed digit, no carry chain), every table entry is read for every
+//                    digit and the selection is arithmetic masking; checked in SASS.
+// Outputs are ristretto encodings, so they are byte-identical to the reference's whatever the digit set.
+#pragma once
+#include "kernels.cuh"
+
+namespace zkp {
+
+// ---- preparation passes (one thread per term) -------------------------------------------------------------
+
+// decompress to affine Niels; an invalid encoding is marked by an all-zero first element (y+x is never 0 on
+// the curve)
+__global__ void __launch_bounds__(256) k_decompress_valid(const uint4* __restrict__ enc, size_t n,
+                                                          uint4* __restrict__ niels) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t w[8];
+  load_words8(w, enc + 2 * i);
+  fe x, y, t;
+  uint32_t ok = ristretto_decode(x, y, t, w);
+  ge_aniels q;
+  ge_aniels_from_affine(q, x, y, t);
+  if (!ok) fe_zero(q.yplusx);
+  uint4* o = niels + 6 * i;
+  store_fe(o, q.yplusx);
+  store_fe(o + 2, q.yminusx);
+  store_fe(o + 4, q.xy2d);
+}
+
+// vartime scalars: kk = min(s, l-s) with the fold sign in bit 255, k3 = 3*kk; non-canonical -> kk word7 = ~0
+__global__ void __launch_bounds__(256) k_prep_scalars_vt(const uint4* __restrict__ scalars, size_t n,
+                                                         uint4* __restrict__ kk, uint4* __restrict__ k3) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t s[8], k[8], t[8], u[8];
+  load_words8(s, scalars + 2 * i);
+  uint32_t neg;
+  uint32_t canonical = sc_fold_sign(k, neg, s);
+  add8(t, k, k);
+  add8(u, t, k);  // 3k < 2^254
+  k[7] |= neg << 31;
+  if (!canonical) k[7] = 0xffffffffu;
+  kk[2 * i] = make_uint4(k[0], k[1], k[2], k[3]);
+  kk[2 * i + 1] = make_uint4(k[4], k[5], k[6], k[7]);
+  k3[2 * i] = make_uint4(u[0], u[1], u[2], u[3]);
+  k3[2 * i + 1] = make_uint4(u[4], u[5], u[6], u[7]);
+}
+
+__global__ void __launch_bounds__(64) k_small_msm_vt(const uint32_t* __restrict__ kk, const uint32_t* __restrict__ k3,
+                                                     const uint4* __restrict__ niels,
+                                                     const unsigned long long* __restrict__ offsets, size_t M,
+                                                     uint4* __restrict__ out, int* __restrict__ status) {
+  size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= M) return;
+  const size_t lo = offsets[j], hi = offsets[j + 1];
+  int st = 0;
+  for (size_t t = lo; t < hi; t++) {
+    uint4 first = __ldg(niels + 6 * t), second = __ldg(niels + 6 * t + 1);
+    if ((first.x | first.y | first.z | first.w | second.x | second.y | second.z | second.w) == 0) st = 1;
+    if (__ldg(kk + 8 * t + 7) == 0xffffffffu && st == 0) st = 3;
+  }
+  if (st != 0) {
+    status[j] = st;
+    out[2 * j] = make_uint4(0, 0, 0, 0);
+    out[2 * j + 1] = make_uint4(0, 0, 0, 0);
+    return;
+  }
+  ge_ext acc;
+  ge_identity(acc);
+  bool started = false;
+  // digit_i = bit_{i+1}(3k) - bit_{i+1}(k), i = 253 .. 0   (3k < 2^254)
+  for (int i = 253; i >= 0; i--) {
+    if (started) ge_double(acc, acc);
+    const int b = i + 1, wi = b >> 5, sh = b & 31;
+    for (size_t t = lo; t < hi; t++) {
+      uint32_t w3 = __ldg(k3 + 8 * t + wi), w1 = __ldg(kk + 8 * t + wi);
+      if (wi == 7) w1 &= 0x7fffffffu;
+      int d = (int)((w3 >> sh) & 1u) - (int)((w1 >> sh) & 1u);
+      if (d != 0) {
+        uint32_t neg = (__ldg(kk + 8 * t + 7) >> 31) ^ (d < 0 ? 1u : 0u);
+        ge_aniels q;
+        load_aniels(q, niels, (uint32_t)t);
+        ge_aniels_cneg(q, neg);
+        ge_madd(acc, acc, q);
+        started = true;
+      }
+    }
+  }
+  uint32_t enc[8];
+  ristretto_encode(enc, acc);
+  out[2 * j] = make_uint4(enc[0], enc[1], enc[2], enc[3]);
+  out[2 * j + 1] = make_uint4(enc[4], enc[5], enc[6], enc[7]);
+  status[j] = 0;
+}
+
+// ---- constant-time path ----------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256) k_decompress_ext(const uint4* __restrict__ enc, size_t n, uint4* __restrict__ ext,
+                                                        int* __restrict__ flags) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t w[8];
+  load_words8(w, enc + 2 * i);
+  ge_ext p;
+  uint32_t ok = ristretto_decode(p.X, p.Y, p.T, w);
+  fe_one(p.Z);
+  if (!ok) {
+    ge_identity(p);
+    atomicMin(&flags[0], (int)i);
+  }
+  store_ext(ext + 8 * i, p);
+}
+
+__global__ void __launch_bounds__(256) k_limbs_to_ext(const unsigned long long* __restrict__ limbs, size_t n,
+                                                      uint4* __restrict__ ext) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  ge_ext p;
+  load_ext_limbs51(p, limbs + 20 * i);
+  store_ext(ext + 8 * i, p);
+}
+
+__device__ __forceinline__ void store_pniels(uint4* o, const ge_pniels& q) {
+  store_fe(o, q.YplusX); store_fe(o + 2, q.YminusX); store_fe(o + 4, q.Z); store_fe(o + 6, q.T2d);
+}
+
+// per term: table of 1P..8P as projective Niels (8 x 128 B) and the biased scalar k + 0x88..8
+__global__ void __launch_bounds__(128) k_build_tables(const uint4* __restrict__ ext, const uint4* __restrict__ scalars,
+                                                      size_t n, uint4* __restrict__ tables, uint4* __restrict__ biased,
+                                                      int* __restrict__ flags) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  ge_ext p, m;
+  load_ext(p, ext + 8 * i);
+  ge_pniels pn, cur;
+  ge_to_pniels(pn, p);
+  uint4* tab = tables + i * 64;
+  store_pniels(tab, pn);
+  m = p;
+#pragma unroll 1
+  for (int k = 1; k < 8; k++) {
+    ge_add_pniels(m, m, pn);
+    ge_to_pniels(cur, m);
+    store_pniels(tab + 8 * k, cur);
+  }
+  uint32_t s[8], l[8], d[8], bias[8], r[8];
+  load_words8(s, scalars + 2 * i);
+  sc_load_l(l);
+  uint32_t canonical = sub8(d, s, l);
+  if (!canonical) atomicMin(&flags[1], (int)i);
+#pragma unroll
+  for (int k = 0; k < 8; k++) bias[k] = 0x88888888u;
+  add8(r, s, bias);
+  biased[2 * i] = make_uint4(r[0], r[1], r[2], r[3]);
+  biased[2 * i + 1] = make_uint4(r[4], r[5], r[6], r[7]);
+}
+
+__global__ void __launch_bounds__(64) k_small_msm_ct(const uint32_t* __restrict__ biased, const uint4* __restrict__ tables,
+                                                     const unsigned long long* __restrict__ offsets, size_t M,
+                                                     uint4* __restrict__ out) {
+  size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= M) return;
+  const size_t lo = offsets[j], hi = offsets[j + 1];   // public
+  ge_ext acc;
+  ge_identity(acc);
+#pragma unroll 1
+  for (int w = 63; w >= 0; w--) {
+    ge_double(acc, acc);
+    ge_double(acc, acc);
+    ge_double(acc, acc);
+    ge_double(acc, acc);
+#pragma unroll 1
+    for (size_t t = lo; t < hi; t++) {
+      uint32_t word = __ldg(biased + 8 * t + (w >> 3));
+      int d = (int)((word >> ((w & 7) * 4)) & 15u) - 8;   // signed digit in [-8, 7]
+      uint32_t sign = (uint32_t)d >> 31;
+      uint32_t mag = (uint32_t)((d ^ -(int)sign) + (int)sign);
+      // constant-time lookup: start from the identity, scan all eight entries
+      ge_pniels sel;
+      fe_one(sel.YplusX); fe_one(sel.YminusX); fe_one(sel.Z); fe_zero(sel.T2d);
+      const uint4* tab = tables + t * 64;
+#pragma unroll 1
+      for (uint32_t e = 1; e <= 8; e++) {
+        uint32_t mask = 0u - (uint32_t)(mag == e);
+        const uint4* ent = tab + 8 * (e - 1);
+        uint32_t* dst = (uint32_t*)&sel;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          uint4 v = __ldg(ent + q);
+          dst[4 * q + 0] ^= mask & (dst[4 * q + 0] ^ v.x);
+          dst[4 * q + 1] ^= mask & (dst[4 * q + 1] ^ v.y);
+          dst[4 * q + 2] ^= mask & (dst[4 * q + 2] ^ v.z);
+          dst[4 * q + 3] ^= mask & (dst[4 * q + 3] ^ v.w);
+        }
+      }
+      ge_pniels_cneg(sel, sign);
+      ge_add_pniels(acc, acc, sel);
+    }
+  }
+  uint32_t enc[8];
+  ristretto_encode(enc, acc);
+  out[2 * j] = make_uint4(enc[0], enc[1], enc[2], enc[3]);
+  out[2 * j + 1] = make_uint4(enc[4], enc[5], enc[6], enc[7]);
+}
+
+}  // namespace zkp
