@@ -33,8 +33,10 @@ def make(n, bits=252):
     return sc, base[idx]
 
 
-stream = torch.cuda.current_stream()
+stream = torch.cuda.Stream()
+torch.cuda.set_stream(stream)
 eng.set_stream(stream.cuda_stream)
+eng.set_option("profile", 1)
 res = torch.zeros(64, dtype=torch.uint8, device="cuda")
 
 
@@ -58,6 +60,8 @@ def time_dev(n, reps=3, **opts):
     status = int(np.frombuffer(st[32:36].tobytes(), dtype=np.int32)[0])
     for k in opts:
         eng.set_option(k, 0)
+    sm = eng.stage_ms()
+    print("    stages:", " ".join("%s=%.3f" % (k, v) if isinstance(v, float) else "%s=%d" % (k, v) for k, v in sm.items()), flush=True)
     return best, status
 
 

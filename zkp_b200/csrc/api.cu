@@ -32,6 +32,11 @@ struct zkp_ctx {
   devbuf in_scalars, in_points, niels, hist, offs, cursor, sorted, buckets, lvlT[2], lvlU, usum, flags, result,
       aux0, aux1, aux2, sk0, sk1, tables;
   void* h_result = nullptr;  // pinned, 64 bytes
+  // optional per-stage timing of the vartime MSM ("profile" option): events around each stage
+  int profile = 0;
+  cudaEvent_t ev[10] = {};
+  float stage_ms[9] = {};
+  int last_window = 0, last_lanes = 0;
 };
 
 #define CUDA_TRY(ctx, call)                                                            \
@@ -146,6 +151,11 @@ extern "C" int32_t zkp_ctx_set_option(zkp_ctx* ctx, const char* key, int64_t val
   } else if (!strcmp(key, "window_cap")) {
     if (value < 4 || value > 24) return ZKP_ERR_SIZE;
     ctx->window_cap = (int)value;
+  } else if (!strcmp(key, "profile")) {
+    ctx->profile = value ? 1 : 0;
+    if (ctx->profile && !ctx->ev[0])
+      for (int i = 0; i < 10; i++)
+        if (cudaEventCreate(&ctx->ev[i]) != cudaSuccess) return ZKP_ERR_CUDA;
   } else if (!strcmp(key, "lanes")) {
     if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8 && value != 16 && value != 32)
       return ZKP_ERR_SIZE;
@@ -161,6 +171,16 @@ extern "C" int32_t zkp_ctx_synchronize(zkp_ctx* ctx) {
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return ZKP_OK;
+}
+
+// diagnostic: stage 0..6 = decompress, recode+hist, scan, scatter, accumulate, bucket-reduce, finish;
+// 100 = window width used, 101 = lanes per bucket used
+extern "C" double zkp_ctx_stage_ms(zkp_ctx* ctx, int32_t stage) {
+  if (!ctx) return -1.0;
+  if (stage == 100) return ctx->last_window;
+  if (stage == 101) return ctx->last_lanes;
+  if (stage < 0 || stage > 6) return -1.0;
+  return ctx->stage_ms[stage];
 }
 
 extern "C" const char* zkp_last_error(zkp_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
@@ -229,7 +249,11 @@ static int32_t msm_vartime_launch(zkp_ctx* ctx, const void* d_scalars, const voi
   }
   ENSURE(ctx, ctx->usum, (size_t)8 * W * 128);
 
+#define STAGE(i) do { if (ctx->profile) cudaEventRecord(ctx->ev[i], st); } while (0)
+  ctx->last_window = c;
+  ctx->last_lanes = G;
   int* flags = (int*)ctx->flags.p;
+  STAGE(0);
   k_init_flags<<<1, 1, 0, st>>>(flags);
   LAUNCH_CHECK(ctx);
   CUDA_TRY(ctx, cudaMemsetAsync(ctx->hist.p, 0, (size_t)W * B * 4, st));
@@ -237,14 +261,18 @@ static int32_t msm_vartime_launch(zkp_ctx* ctx, const void* d_scalars, const voi
   const unsigned nb = (unsigned)((n + 255) / 256);
   k_decompress<<<nb, 256, 0, st>>>((const uint4*)d_points, n, (uint4*)ctx->niels.p, flags);
   LAUNCH_CHECK(ctx);
+  STAGE(1);
   k_recode<false><<<nb, 256, 0, st>>>((const uint4*)d_scalars, n, c, W, B, (uint32_t*)ctx->hist.p, nullptr, flags);
   LAUNCH_CHECK(ctx);
+  STAGE(2);
   k_scan<<<W, 1024, 0, st>>>((const uint32_t*)ctx->hist.p, B, (uint32_t*)ctx->offs.p, (uint32_t*)ctx->cursor.p);
   LAUNCH_CHECK(ctx);
+  STAGE(3);
   k_recode<true><<<nb, 256, 0, st>>>((const uint4*)d_scalars, n, c, W, B, (uint32_t*)ctx->cursor.p,
                                      (uint32_t*)ctx->sorted.p, flags);
   LAUNCH_CHECK(ctx);
 
+  STAGE(4);
   {
     const size_t threads = (size_t)total_buckets * G;
     const unsigned blocks = (unsigned)((threads + 127) / 128);
@@ -263,6 +291,7 @@ static int32_t msm_vartime_launch(zkp_ctx* ctx, const void* d_scalars, const voi
     LAUNCH_CHECK(ctx);
   }
 
+  STAGE(5);
   // bucket reduction levels
   const uint4* cur = (const uint4*)ctx->buckets.p;
   uint32_t m = B;
@@ -280,8 +309,15 @@ static int32_t msm_vartime_launch(zkp_ctx* ctx, const void* d_scalars, const voi
     m = chunks;
     nl++;
   }
+  STAGE(6);
   k_finish<<<1, 64, 0, st>>>((const uint4*)ctx->usum.p, nl, cur, m, W, c, n, flags, d_result, nullptr);
   LAUNCH_CHECK(ctx);
+  STAGE(7);
+  if (ctx->profile) {
+    CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev[7]));
+    for (int i = 0; i < 7; i++) cudaEventElapsedTime(&ctx->stage_ms[i], ctx->ev[i], ctx->ev[i + 1]);
+  }
+#undef STAGE
   return ZKP_OK;
 }
 

@@ -73,6 +73,15 @@ class Engine:
     def synchronize(self):
         self._check(self._lib.zkp_ctx_synchronize(self._ctx))
 
+    STAGES = ["decompress", "recode_hist", "scan", "scatter", "accumulate", "bucket_reduce", "finish"]
+
+    def stage_ms(self):
+        """Per-stage device times of the last vartime MSM (needs set_option('profile', 1))."""
+        d = {n: float(self._lib.zkp_ctx_stage_ms(self._ctx, i)) for i, n in enumerate(self.STAGES)}
+        d["window"] = int(self._lib.zkp_ctx_stage_ms(self._ctx, 100))
+        d["lanes"] = int(self._lib.zkp_ctx_stage_ms(self._ctx, 101))
+        return d
+
     @property
     def launch_count(self):
         return int(self._lib.zkp_ctx_launch_count(self._ctx))
