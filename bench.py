@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py -- proofs verified/sec (batch) for the CMZ'13 10-attribute credential on N B200s.
+
+Contract: `python bench.py --gpus N --steps K --warmup W` (under torchrun for N > 1) prints ONE JSON line on rank 0.
+
+Workload (BASELINE.json configs[3] scaled per GPU, weak scaling): every GPU batch-verifies 2^21 CMZ'13
+`cred_show_10` proofs = ONE combined multi-scalar multiplication of 12 + 24 * 2^21 = 50,331,660 terms
+(/root/reference/src/toolbox/batch_verifier.rs:219-230), so N = 8 is exactly configs[3] (2^24 proofs, one accept bit
+per GPU gathered over NCCL).  A "step" is one such verification.  Inputs are synthetic but valid (data:
+"synthetic"): coefficient scalars have the distribution batch_verifier.rs:173-206 produces (13 instance rows
+full-size, 11 commitment rows = -rho with 128-bit rho), points are 2^22 distinct valid ristretto255 encodings
+per GPU, and the scalars attached to each point cancel so the sum is the identity and every step must ACCEPT
+(checked every step; a flipped scalar must REJECT, checked once).  Host transcript hashing and the coefficient
+fold stay on the host by north_star and are outside this MSM-boundary metric.
+
+  value     device-resident: scalars+points already in HBM (3.2 GB per GPU > 126 MB L2), CUDA-event timed
+  e2e       same verification through the C ABI zkp_batch_verify() from pinned HOST buffers, H2D inside
+  roofline  the dominant kernel (k_decompress) against the HBM copy peak of MEASURED_PEAKS.json, plus the
+            integer-pipe figures that actually bound this path
+  cpu_baseline  the C port of the reference's serial u64 CPU algorithms (oracle/_ref) on all host threads
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+L = 2**252 + 27742317777372353535851937790883648493
+ROWS, NUM_S = 24, 12           # CMZ: 13 instance + 11 commitment rows, 12 static points
+FULL_ROWS = 13                  # rows 0..12 carry full-size coefficients, rows 13..23 are -rho (128-bit rho)
+BYTES_PER_PROOF = 1536          # 24 terms x (32 B scalar + 32 B point)   
+
+
+def _l_words():
+    return np.frombuffer(L.to_bytes(32, "little"), dtype=np.uint64).copy()
+
+
+def _sub_from_l(x):
+    """l - x for x (k,4) uint64 little-endian words with x < l; vectorised borrow chain."""
+    lw = _l_words()
+    out = np.empty_like(x)
+    borrow = np.zeros(x.shape[0], dtype=np.uint64)
+    for w in range(4):
+        a = np.full(x.shape[0], lw[w], dtype=np.uint64)
+        b = x[:, w]
+        d = a - b
+        b1 = (a < b).astype(np.uint64)
+        d2 = d - borrow
+        b2 = (d < borrow).astype(np.uint64)
+        out[:, w] = d2
+        borrow = b1 | b2
+    return out
+
+
+def _colsum_mod_l(x):
+    """sum over axis 0 of (t, k, 4)-word scalars, mod l, returned as python ints per k (t is small)."""
+    lo = (x & np.uint64(0xFFFFFFFF)).sum(axis=0, dtype=np.uint64)
+    hi = (x >> np.uint64(32)).sum(axis=0, dtype=np.uint64)
+    k = x.shape[1]
+    out = []
+    for i in range(k):
+        v = 0
+        for w in range(4):
+            v += (int(lo[i, w]) + (int(hi[i, w]) << 32)) << (64 * w)
+        out.append(v % L)
+    return out
+
+
+def make_cmz_batch(n_proofs, seed, n_points=None):
+    """Synthetic valid batch-verification MSM instance (see module docstring).
+    Returns (static_coeffs[12,32], instance_coeffs[24*N,32] row-major, point index arrays)."""
+    rng = np.random.default_rng(seed)
+    N = n_proofs
+    K = n_points or 2 * N
+    half = K // 2
+    sc = rng.integers(0, 2**64, size=(ROWS, N, 4), dtype=np.uint64)
+    sc[:FULL_ROWS, :, 3] &= np.uint64((1 << 60) - 1)          # < 2^252 < l
+    # commitment rows: -rho mod l with 128-bit rho  (batch_verifier.rs:183)
+    rho = sc[FULL_ROWS:].reshape(-1, 4).copy()
+    rho[:, 2:] = 0
+    sc[FULL_ROWS:] = _sub_from_l(rho).reshape(ROWS - FULL_ROWS, N, 4)
+    # term (row j, proof p) uses point (p mod half) + (j & 1) * half; make each point's scalars cancel by fixing
+    # the term in row 0 (even rows) / row 1 (odd rows) of proof p < half
+    return sc, K, half
+
+
+def finish_cancellation(sc, N, half):
+    """Overwrite rows 0 and 1 for proofs < half so that the scalars of every point sum to 0 mod l."""
+    for parity in (0, 1):
+        rows = sc[parity::2]                                   # (12, N, 4)
+        t = N // half
+        grp = rows.reshape(rows.shape[0], t, half, 4).reshape(rows.shape[0] * t, half, 4).copy()
+        grp[0] = 0                                             # the compensator slot (row `parity`, proofs < half)
+        sums = _colsum_mod_l(grp)
+        comp = np.zeros((half, 4), dtype=np.uint64)
+        for i, s in enumerate(sums):
+            v = (L - s) % L
+            comp[i] = np.frombuffer(v.to_bytes(32, "little"), dtype=np.uint64)
+        sc[parity, :half] = comp
+    return sc
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5),
+                              ("sw_power_cap", 6)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        busy = [s for s in sm if s > 500] or sm
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(sc_rows, pt_enc, sample_proofs, threads, steps=1):
+    """The C port of the reference's CPU path (oracle/_ref, kind "port") on a bounded sample of the SAME
+    workload: the first `sample_proofs` proofs' columns of every row, i.e. one MSM of 24*sample terms."""
+    from oracle import cref
+    s = np.ascontiguousarray(sc_rows[:, :sample_proofs]).reshape(-1, 32)
+    p = np.ascontiguousarray(pt_enc[:, :sample_proofs]).reshape(-1, 32)
+    best = 1e30
+    for _ in range(steps):
+        t = time.perf_counter()
+        out = cref.msm_vartime(s, p, threads=threads)
+        best = min(best, time.perf_counter() - t)
+        assert out is not None
+    return sample_proofs / best, best
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--log2-proofs", type=int, default=21, help="proofs per GPU (default 2^21)")
+    ap.add_argument("--cpu-sample-log2", type=int, default=14, help="proofs in the CPU baseline sample")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    N = 1 << args.log2_proofs
+    n_terms = NUM_S + ROWS * N
+    host_threads = os.cpu_count() or 1
+    config = {"workload": "CMZ13 cred_show_10 BatchVerifier::verify_batchable, 2^%d proofs per GPU "
+                          "(one %d-term ristretto255 MSM per GPU; BASELINE configs[3] at 8 GPUs)" % (args.log2_proofs, n_terms),
+              "proofs_per_gpu": N, "msm_terms_per_gpu": n_terms, "distinct_points_per_gpu": 2 * N,
+              "l2_policy": "inputs (3.2 GB/GPU) and workspace exceed the 126 MB L2; no explicit flush",
+              "parallelism": "proof-sharded x%d, 1 accept bit per GPU" % args.gpus}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        # the reference itself is Rust (no toolchain here): its CPU algorithms are timed through the C port
+        sample = 1 << args.cpu_sample_log2
+        sc, K, half = make_cmz_batch(sample, seed=1234, n_points=2 * sample)
+        sc = finish_cancellation(sc, sample, half)
+        from zkp_b200 import Engine  # points need a generator: valid encodings come from the engine if a GPU
+        pts = _host_points(2 * sample)   # is present, else from the oracle
+        pidx = (np.arange(sample) % half)[None, :] + (np.arange(ROWS) & 1)[:, None] * half
+        pt_rows = pts[pidx]
+        sc_rows = sc.view(np.uint8).reshape(ROWS, sample, 32)
+        for _ in range(args.warmup):
+            cpu_baseline(sc_rows, pt_rows, min(sample, 1 << 10), host_threads)
+        t0 = time.perf_counter()
+        rates = [cpu_baseline(sc_rows, pt_rows, sample, host_threads)[0] for _ in range(args.steps)]
+        dt = (time.perf_counter() - t0) / args.steps
+        v = float(np.median(rates))
+        line = {"impl": "reference", "metric": "proofs verified/sec (batch) CMZ13 10-attr credential", "value": v,
+                "unit": "proofs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u64", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": v, "unit": "proofs/s", "cores": host_threads, "kind": "port",
+                                 "sample": "%d proofs (%d-term MSM) per step, C port of dalek u64 serial backend, %d threads"
+                                           % (sample, ROWS * sample, host_threads)},
+                "e2e": {"value": v, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from zkp_b200 import Engine
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    eng = Engine(local_rank)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    eng.set_stream(stream.cuda_stream)
+
+    # ---- synthetic valid instance (per rank, different seed) ----------------------------------------------
+    t_setup = time.perf_counter()
+    sc, K, half = make_cmz_batch(N, seed=1000 + rank)
+    sc = finish_cancellation(sc, N, half)
+    pts = gpu_points(eng, K, seed=77 + rank)                       # (K,32) distinct valid encodings
+    pidx = (np.arange(N) % half)[None, :] + (np.arange(ROWS) & 1)[:, None] * half
+    inst_points = torch.from_numpy(pts)[torch.from_numpy(pidx.reshape(-1))].contiguous()   # (24N,32)
+    inst_coeffs = torch.from_numpy(sc.view(np.uint8).reshape(ROWS * N, 32))
+    static_points = torch.from_numpy(pts[:NUM_S].copy())
+    static_coeffs = torch.zeros(NUM_S, 32, dtype=torch.uint8)       # static rows: zero net coefficient
+    h_scal = torch.cat([static_coeffs, inst_coeffs]).pin_memory()
+    h_pts = torch.cat([static_points, inst_points]).pin_memory()
+    d_scal, d_pts = h_scal.cuda(non_blocking=True), h_pts.cuda(non_blocking=True)
+    d_res = torch.zeros(64, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    setup_s = time.perf_counter() - t_setup
+
+    def step_dev():
+        eng.msm_vartime_dev(d_scal.data_ptr(), d_pts.data_ptr(), n_terms, d_res.data_ptr())
+
+    def read_result():
+        r = d_res.cpu().numpy()
+        status, ident = np.frombuffer(r[32:40].tobytes(), dtype=np.int32)
+        return int(status), int(ident)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_dev()
+    torch.cuda.synchronize()
+    assert read_result() == (0, 1), "valid batch was not accepted: %r" % (read_result(),)
+    # negative control: one flipped coefficient byte must reject
+    d_bad = d_scal.clone()
+    d_bad[NUM_S + 5, 0] ^= 1
+    eng.msm_vartime_dev(d_bad.data_ptr(), d_pts.data_ptr(), n_terms, d_res.data_ptr())
+    torch.cuda.synchronize()
+    assert read_result() == (0, 0), "tampered batch was accepted"
+    del d_bad
+
+    # per-stage device times (CUDA events on the launching stream) for the roofline block
+    eng.set_option("profile", 1)
+    stage_acc = {}
+    for _ in range(2):
+        step_dev()
+        for k, v in eng.stage_ms().items():
+            stage_acc.setdefault(k, []).append(v)
+    eng.set_option("profile", 0)
+    stages = {k: float(np.mean(v)) for k, v in stage_acc.items()}
+
+    # ---- timed region: device-resident ---------------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    launches0 = eng.launch_count
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    accepts = 0
+    for _ in range(args.steps):
+        step_dev()
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    launches = eng.launch_count - launches0
+    ms_total = e0.elapsed_time(e1)
+    assert read_result() == (0, 1)
+
+    # ---- e2e through the C ABI with host buffers -------------------------------------------------------------
+    h_sc_np, h_pt_np = h_scal.numpy(), h_pts.numpy()
+    for _ in range(1):
+        ok, rc = eng.batch_verify(h_sc_np[:NUM_S], h_pt_np[:NUM_S], h_sc_np[NUM_S:], h_pt_np[NUM_S:], ROWS, N)
+        assert ok and rc == 0
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ok, rc = eng.batch_verify(h_sc_np[:NUM_S], h_pt_np[:NUM_S], h_sc_np[NUM_S:], h_pt_np[NUM_S:], ROWS, N)
+        accepts += int(ok)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    assert accepts == args.steps
+
+    # ---- gather: max time over ranks, accept bits over NCCL ---------------------------------------------------
+    tm = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    bits = torch.tensor([1 if accepts == args.steps else 0], dtype=torch.int32, device="cuda")
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        all_bits = [torch.zeros_like(bits) for _ in range(world)]
+        dist.all_gather(all_bits, bits)                         # the single NCCL gather of accept bits
+        accept_bitmap = [int(b.item()) for b in all_bits]
+    else:
+        accept_bitmap = [int(bits.item())]
+    ms_total, e2e_ms = float(tm[0].item()), float(tm[1].item())
+
+    if rank == 0:
+        ms_step = ms_total / args.steps
+        value = world * N / (ms_step * 1e-3)
+        e2e_value = world * N / (e2e_ms * 1e-3 / args.steps)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        dec_ms = stages.get("decompress", 0.0)
+        dom = max((k for k in stages if k not in ("window", "lanes")), key=lambda k: stages[k])
+        dec_bytes = n_terms * 128.0                              # 32 B encoding in + 96 B Niels point out per point
+        achieved = dec_bytes / (dec_ms * 1e-3) / 1e9 if dec_ms else 0.0
+        # integer-pipe view: field mults (254 S + 30 M per point) against the calibrated register-resident rate
+        fe_sq_rate = eng.bench_field(1, 2048)
+        fe_mul_rate = eng.bench_field(0, 2048)
+        dec_time_at_peak = n_terms * (254.0 / fe_sq_rate + 30.0 / fe_mul_rate)
+        roofline = {"bound": "hbm", "kernel": "k_decompress", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": dec_bytes, "kernel_ms": dec_ms,
+                    "whole_path_hbm": {"bytes_per_proof": BYTES_PER_PROOF,
+                                       "achieved_GBs": N * BYTES_PER_PROOF / (ms_step * 1e-3) / 1e9,
+                                       "frac": N * BYTES_PER_PROOF / (ms_step * 1e-3) / 1e9 / hbm_peak},
+                    "integer_pipe": {"fe_sq_per_s_calibrated": fe_sq_rate, "fe_mul_per_s_calibrated": fe_mul_rate,
+                                     "k_decompress_frac_of_calibrated": (dec_time_at_peak / (dec_ms * 1e-3)) if dec_ms else None},
+                    "stage_ms": stages, "dominant_stage": dom}
+        sample = 1 << args.cpu_sample_log2
+        sc_rows = sc.view(np.uint8).reshape(ROWS, N, 32)
+        pt_rows = inst_points.numpy().reshape(ROWS, N, 32)
+        cpu_v, cpu_t = cpu_baseline(sc_rows, pt_rows, sample, host_threads)
+        line = {"metric": "proofs verified/sec (batch) CMZ13 10-attr credential", "value": value, "unit": "proofs/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 (8x32-bit saturated limbs, 64-bit products)",
+                "data": "synthetic", "config": config,
+                "e2e": {"value": e2e_value, "unit": "proofs/s", "h2d_bytes_per_step": int(n_terms * 64),
+                        "d2h_bytes_per_step": 48, "ms_per_step": e2e_ms / args.steps,
+                        "api": "zkp_batch_verify (C ABI), pinned host buffers"},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+                "cpu_baseline": {"value": cpu_v, "unit": "proofs/s", "cores": host_threads, "kind": "port",
+                                 "sample": "first %d proofs of this workload (one %d-term MSM), C port of dalek's "
+                                           "serial u64 backend sharded over %d threads, %.2f s"
+                                           % (sample, ROWS * sample, host_threads, cpu_t)},
+                "accept_bits": accept_bitmap, "setup_s": setup_s}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def gpu_points(eng, K, seed):
+    """K distinct valid ristretto255 encodings r_k * B computed by the engine's constant-time batched path."""
+    rng = np.random.default_rng(seed)
+    r = rng.integers(0, 256, size=(K, 32), dtype=np.uint8)
+    r[:, 31] &= 0x0F
+    B = np.frombuffer(bytes.fromhex("e2f2ae0a6abc4e71a884a961c500515f58e30b6aa582dd8db6a65945e08d2d76"), dtype=np.uint8)
+    out = np.empty((K, 32), dtype=np.uint8)
+    chunk = 1 << 20
+    for lo in range(0, K, chunk):
+        m = min(chunk, K - lo)
+        pts = np.broadcast_to(B, (m, 32)).copy()
+        off = np.arange(m + 1, dtype=np.uint64)
+        out[lo:lo + m] = eng.msm_ct_batched(r[lo:lo + m], pts, off)
+    return out
+
+
+def _host_points(K):
+    """Valid encodings without a GPU (reference arm): oracle hash-to-group, cached."""
+    from tests import util_data as U
+    return np.frombuffer(b"".join(U.base_points(K)), dtype=np.uint8).reshape(K, 32).copy()
+
+
+if __name__ == "__main__":
+    main()

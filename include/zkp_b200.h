@@ -55,13 +55,14 @@ void zkp_ctx_destroy(zkp_ctx* ctx);
 /* Enqueue on the caller's stream (a cudaStream_t) from now on; NULL restores the context's own stream. */
 int32_t zkp_ctx_set_stream(zkp_ctx* ctx, void* cuda_stream);
 /* Tunables: "window" (Pippenger window width c, 0 = choose from n), "window_cap" (upper bound of the automatic
- * choice), "lanes" (lanes per bucket, 0 = auto), "profile" (0/1, see zkp_ctx_stage_ms). */
+ * choice), "chunk" (max sorted entries per accumulate work item, 0 = auto), "profile" (0/1, see
+ * zkp_ctx_stage_ms). */
 int32_t zkp_ctx_set_option(zkp_ctx* ctx, const char* key, int64_t value);
 int32_t zkp_ctx_synchronize(zkp_ctx* ctx);
 const char* zkp_last_error(zkp_ctx* ctx);
 /* Diagnostic: with option "profile"=1 every zkp_msm_vartime[_dev] call synchronises and records the device
  * time of its stages: 0 decompress, 1 recode+histogram, 2 scan, 3 scatter, 4 bucket accumulate, 5 bucket
- * reduce, 6 finish (ms).  stage 100 / 101 return the window width / lanes per bucket last used.          */
+ * reduce, 6 finish (ms).  stage 100 / 101 return the window width / chunk length last used.          */
 double zkp_ctx_stage_ms(zkp_ctx* ctx, int32_t stage);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 uint64_t zkp_ctx_launch_count(zkp_ctx* ctx);

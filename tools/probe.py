@@ -70,12 +70,13 @@ for lg in [8, 12, 16, 18, 20, 22]:
     print("n=2^%d  %.3f ms  %.3e terms/s status=%d" % (lg, ms, (1 << lg) / ms * 1e3, st), flush=True)
     out["msm_2^%d_ms" % lg] = ms
 eng.set_option("window_cap", 24)
-for c in [12, 14, 16, 18, 20]:
-    for g in ([0] if c != 16 else [0, 1, 2, 4, 8, 16, 32]):
+for c in [13, 14, 15, 16, 17, 18, 19, 20]:
+    for g in ([0] if c != 16 else [0, 32, 128, 1024]):
         try:
-            ms, st = time_dev(1 << 22, reps=2, window=c, lanes=g)
-            print("n=2^22 c=%d lanes=%d  %.3f ms status=%d" % (c, g, ms, st), flush=True)
-            out["msm_2^22_c%d_g%d_ms" % (c, g)] = ms
+            ms, st = time_dev(1 << 22, reps=2, window=c, chunk=g)
+            print("n=2^22 c=%d chunk=%d  %.3f ms status=%d" % (c, g, ms, st), flush=True)
+            out["msm_2^22_c%d_s%d_ms" % (c, g)] = ms
         except Exception as ex:
-            print("c=%d g=%d failed: %s" % (c, g, ex))
+            print("c=%d chunk=%d failed: %s" % (c, g, ex))
+# CMZ-like mix at 2^24 terms: 13/24 full-size, 11/24 128-bit-negated
 json.dump(out, open("gpurun_out/probe.json", "w"), indent=1)

@@ -25,12 +25,12 @@ struct zkp_ctx {
   cudaStream_t stream = nullptr;
   int window = 0;      // 0 = auto
   int lanes = 0;       // 0 = auto
-  int window_cap = 16; // upper bound for the automatic choice
+  int window_cap = 18; // upper bound for the automatic choice
   uint64_t launches = 0;
   std::string err;
   // workspace (grown on demand, reused across calls)
   devbuf in_scalars, in_points, niels, hist, offs, cursor, sorted, buckets, lvlT[2], lvlU, usum, flags, result,
-      aux0, aux1, aux2, sk0, sk1, tables;
+      aux0, aux1, aux2, sk0, sk1, tables, items, partials;
   void* h_result = nullptr;  // pinned, 64 bytes
   // optional per-stage timing of the vartime MSM ("profile" option): events around each stage
   int profile = 0;
@@ -129,7 +129,7 @@ extern "C" void zkp_ctx_destroy(zkp_ctx* ctx) {
   devbuf* bufs[] = {&ctx->in_scalars, &ctx->in_points, &ctx->niels, &ctx->hist, &ctx->offs, &ctx->cursor,
                     &ctx->sorted, &ctx->buckets, &ctx->lvlT[0], &ctx->lvlT[1], &ctx->lvlU, &ctx->usum,
                     &ctx->flags, &ctx->result, &ctx->aux0, &ctx->aux1, &ctx->aux2, &ctx->sk0, &ctx->sk1,
-                    &ctx->tables};
+                    &ctx->tables, &ctx->items, &ctx->partials};
   for (devbuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (ctx->h_result) cudaFreeHost(ctx->h_result);
@@ -156,9 +156,8 @@ extern "C" int32_t zkp_ctx_set_option(zkp_ctx* ctx, const char* key, int64_t val
     if (ctx->profile && !ctx->ev[0])
       for (int i = 0; i < 10; i++)
         if (cudaEventCreate(&ctx->ev[i]) != cudaSuccess) return ZKP_ERR_CUDA;
-  } else if (!strcmp(key, "lanes")) {
-    if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8 && value != 16 && value != 32)
-      return ZKP_ERR_SIZE;
+  } else if (!strcmp(key, "lanes") || !strcmp(key, "chunk")) {
+    if (value < 0 || value > (1 << 20)) return ZKP_ERR_SIZE;
     ctx->lanes = (int)value;
   } else {
     return ZKP_ERR_SIZE;
@@ -205,14 +204,6 @@ static int choose_window(const zkp_ctx* ctx, size_t n) {
   return best;
 }
 
-static int choose_lanes(const zkp_ctx* ctx, size_t n, uint32_t B) {
-  if (ctx->lanes) return ctx->lanes;
-  double mean = (double)n / (double)B;
-  int g = 1;
-  while (g < 32 && mean / (g * 2) >= 96.0) g *= 2;
-  return g;
-}
-
 // ---------------------------------------------------------------------------------------------------------
 // the variable-time MSM, device-resident and asynchronous
 // ---------------------------------------------------------------------------------------------------------
@@ -231,7 +222,6 @@ static int32_t msm_vartime_launch(zkp_ctx* ctx, const void* d_scalars, const voi
   const int c = choose_window(ctx, n);
   const int W = (253 + c - 1) / c;
   const uint32_t B = 1u << (c - 1);
-  const int G = choose_lanes(ctx, n, B);
   const uint32_t total_buckets = (uint32_t)W * B;
 
   ENSURE(ctx, ctx->niels, n * 96);
@@ -251,7 +241,6 @@ static int32_t msm_vartime_launch(zkp_ctx* ctx, const void* d_scalars, const voi
 
 #define STAGE(i) do { if (ctx->profile) cudaEventRecord(ctx->ev[i], st); } while (0)
   ctx->last_window = c;
-  ctx->last_lanes = G;
   int* flags = (int*)ctx->flags.p;
   STAGE(0);
   k_init_flags<<<1, 1, 0, st>>>(flags);
@@ -274,20 +263,39 @@ static int32_t msm_vartime_launch(zkp_ctx* ctx, const void* d_scalars, const voi
 
   STAGE(4);
   {
-    const size_t threads = (size_t)total_buckets * G;
-    const unsigned blocks = (unsigned)((threads + 127) / 128);
-    const uint4* ni = (const uint4*)ctx->niels.p;
-    const uint32_t* so = (const uint32_t*)ctx->sorted.p;
-    const uint32_t* of = (const uint32_t*)ctx->offs.p;
-    uint4* bk = (uint4*)ctx->buckets.p;
-    switch (G) {
-      case 1: k_accumulate<1><<<blocks, 128, 0, st>>>(ni, so, of, n, B, total_buckets, bk); break;
-      case 2: k_accumulate<2><<<blocks, 128, 0, st>>>(ni, so, of, n, B, total_buckets, bk); break;
-      case 4: k_accumulate<4><<<blocks, 128, 0, st>>>(ni, so, of, n, B, total_buckets, bk); break;
-      case 8: k_accumulate<8><<<blocks, 128, 0, st>>>(ni, so, of, n, B, total_buckets, bk); break;
-      case 16: k_accumulate<16><<<blocks, 128, 0, st>>>(ni, so, of, n, B, total_buckets, bk); break;
-      default: k_accumulate<32><<<blocks, 128, 0, st>>>(ni, so, of, n, B, total_buckets, bk); break;
+    // chunk length: about 2x the mean bucket load, but small enough to leave >= ~200k work items
+    const double mean = (double)n / (double)B;
+    uint32_t S = ctx->lanes ? (uint32_t)ctx->lanes : 0;   // "lanes" option doubles as an explicit chunk length
+    if (!S) {
+      double want = 2.0 * mean, cap = (double)n * W / 200000.0;
+      double v = want < cap ? want : cap;
+      if (v < 16.0) v = 16.0;
+      if (v > 4096.0) v = 4096.0;
+      S = (uint32_t)v;
     }
+    ctx->last_lanes = (int)S;
+    const size_t max_items = (size_t)total_buckets + ((size_t)W * n) / S + 1;
+    ENSURE(ctx, ctx->aux0, (size_t)total_buckets * 4);          // chunk counts
+    ENSURE(ctx, ctx->aux1, ((size_t)total_buckets + 1) * 4);    // item offsets
+    ENSURE(ctx, ctx->aux2, (size_t)total_buckets * 4);          // scan scratch (cursor output, unused)
+    ENSURE(ctx, ctx->items, max_items * 16);
+    ENSURE(ctx, ctx->partials, max_items * 128);
+    const unsigned tb = (total_buckets + 255) / 256;
+    k_plan<<<tb, 256, 0, st>>>((const uint32_t*)ctx->offs.p, B, total_buckets, S, (uint32_t*)ctx->aux0.p);
+    LAUNCH_CHECK(ctx);
+    k_scan<<<1, 1024, 0, st>>>((const uint32_t*)ctx->aux0.p, total_buckets, (uint32_t*)ctx->aux1.p,
+                               (uint32_t*)ctx->aux2.p);
+    LAUNCH_CHECK(ctx);
+    k_items<<<tb, 256, 0, st>>>((const uint32_t*)ctx->offs.p, (const uint32_t*)ctx->aux1.p, B, total_buckets, S,
+                                (work_item*)ctx->items.p);
+    LAUNCH_CHECK(ctx);
+    const unsigned blocks = (unsigned)((max_items + 127) / 128);
+    k_accumulate<<<blocks, 128, 0, st>>>((const uint4*)ctx->niels.p, (const uint32_t*)ctx->sorted.p,
+                                         (const work_item*)ctx->items.p, (const uint32_t*)ctx->aux1.p + total_buckets,
+                                         n, (uint4*)ctx->buckets.p, (uint4*)ctx->partials.p);
+    LAUNCH_CHECK(ctx);
+    k_merge<<<(total_buckets + 127) / 128, 128, 0, st>>>((const uint32_t*)ctx->aux1.p, total_buckets,
+                                                         (const uint4*)ctx->partials.p, (uint4*)ctx->buckets.p);
     LAUNCH_CHECK(ctx);
   }
 

@@ -8,7 +8,9 @@
 //   k_recode_hist     scalar -> sign fold -> signed digits; histogram of bucket loads  (hist[W][B])
 //   k_scan            exclusive scan per window                                         (offs[W][B+1], cursor)
 //   k_scatter         counting-sort scatter of (sign | term index) by bucket            (sorted[W][n])
-//   k_accumulate<G>   G lanes per bucket: gather Niels points, mixed additions, warp-shuffle tree reduce
+//   k_plan/k_items    cut buckets into work items of <= S entries (bounded work per thread for any digit mix)
+//   k_accumulate      one item per thread: gather Niels points (software-prefetched), mixed additions (7M)
+//   k_merge           add the partial sums of buckets that were cut
 //   k_chunk_reduce    running-sum reduction of bucket rows in chunks of L (recursive levels)
 //   k_tree_sum        per-window sums of the chunk partials
 //   k_finish          per-window Horner over levels, Horner over windows, ristretto encode, identity/status
@@ -223,24 +225,56 @@ __device__ __forceinline__ void shfl_down_ext(ge_ext& r, const ge_ext& p, int of
   }
 }
 
-template <int G>
-__global__ void __launch_bounds__(128) k_accumulate(const uint4* __restrict__ niels, const uint32_t* __restrict__ sorted,
-                                                    const uint32_t* __restrict__ offs, size_t n, uint32_t B,
-                                                    uint32_t total_buckets, uint4* __restrict__ buckets) {
-  const uint32_t gid = (uint32_t)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) / G);
-  const uint32_t lane = threadIdx.x % G;
-  uint32_t start = 0, end = 0;
-  const uint32_t* base = sorted;
-  if (gid < total_buckets) {
-    uint32_t w = gid / B, b = gid % B;
-    const uint32_t* o = offs + (size_t)w * (B + 1) + b;
-    start = o[0];
-    end = o[1];
-    base = sorted + (size_t)w * n;
+// Work items: every bucket is cut into chunks of at most S sorted entries, so the work per thread is bounded
+// whatever the digit distribution is (uniform scalars already overload the top window: after the sign fold its
+// digits span only a fraction of the buckets).  k_plan counts chunks per bucket, an exclusive scan gives each
+// bucket its first item, k_items writes the descriptors, k_accumulate sums one item per thread, k_merge adds
+// the partial sums of multi-chunk buckets.
+struct work_item { uint32_t start, end, out, wflag; };  // wflag = window | (partial ? 0x80000000 : 0)
+
+__global__ void __launch_bounds__(256) k_plan(const uint32_t* __restrict__ offs, uint32_t B, uint32_t total_buckets,
+                                              uint32_t S, uint32_t* __restrict__ chunk_cnt) {
+  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total_buckets) return;
+  uint32_t w = g / B, b = g % B;
+  const uint32_t* o = offs + (size_t)w * (B + 1) + b;
+  uint32_t cnt = o[1] - o[0];
+  chunk_cnt[g] = cnt == 0 ? 1u : (cnt + S - 1) / S;   // an empty bucket keeps one (empty) item: it writes the identity
+}
+
+__global__ void __launch_bounds__(256) k_items(const uint32_t* __restrict__ offs, const uint32_t* __restrict__ item_offs,
+                                               uint32_t B, uint32_t total_buckets, uint32_t S,
+                                               work_item* __restrict__ items) {
+  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total_buckets) return;
+  uint32_t w = g / B, b = g % B;
+  const uint32_t* o = offs + (size_t)w * (B + 1) + b;
+  uint32_t start = o[0], end = o[1];
+  uint32_t first = item_offs[g], cnt = item_offs[g + 1] - first;
+  if (cnt == 1) {
+    work_item it = {start, end, g, w};
+    items[first] = it;
+  } else {
+    for (uint32_t k = 0; k < cnt; k++) {
+      uint32_t s0 = start + k * S, e0 = min(s0 + S, end);
+      work_item it = {s0, e0, first + k, w | 0x80000000u};
+      items[first + k] = it;
+    }
   }
+}
+
+__global__ void __launch_bounds__(128, 4) k_accumulate(const uint4* __restrict__ niels, const uint32_t* __restrict__ sorted,
+                                                       const work_item* __restrict__ items,
+                                                       const uint32_t* __restrict__ n_items, size_t n,
+                                                       uint4* __restrict__ buckets, uint4* __restrict__ partials) {
+  const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= *n_items) return;
+  const uint4 raw = __ldg((const uint4*)items + id);
+  const uint32_t start = raw.x, end = raw.y, out = raw.z, wflag = raw.w;
+  const uint32_t* base = sorted + (size_t)(wflag & 0x7fffffffu) * n;
   ge_ext acc;
   ge_identity(acc);
-  uint32_t i = start + lane;
+  uint32_t i = start;
   ge_aniels cur;
   uint32_t e_cur = 0;
   if (i < end) {
@@ -248,7 +282,7 @@ __global__ void __launch_bounds__(128) k_accumulate(const uint4* __restrict__ ni
     load_aniels(cur, niels, e_cur);
   }
   while (i < end) {
-    uint32_t inext = i + G;
+    uint32_t inext = i + 1;
     ge_aniels nxt;
     uint32_t e_nxt = 0;
     if (inext < end) {  // software prefetch of the next gather while this addition runs
@@ -261,14 +295,24 @@ __global__ void __launch_bounds__(128) k_accumulate(const uint4* __restrict__ ni
     e_cur = e_nxt;
     i = inext;
   }
-  // tree reduction across the G lanes
-#pragma unroll
-  for (int off = G / 2; off >= 1; off >>= 1) {
-    ge_ext other;
-    shfl_down_ext(other, acc, off, G);
-    ge_add(acc, acc, other);
+  uint4* dst = (wflag >> 31) ? partials + (size_t)out * 8 : buckets + (size_t)out * 8;
+  store_ext(dst, acc);
+}
+
+// buckets with more than one chunk: add their partial sums
+__global__ void __launch_bounds__(128) k_merge(const uint32_t* __restrict__ item_offs, uint32_t total_buckets,
+                                               const uint4* __restrict__ partials, uint4* __restrict__ buckets) {
+  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total_buckets) return;
+  uint32_t first = item_offs[g], cnt = item_offs[g + 1] - first;
+  if (cnt <= 1) return;
+  ge_ext acc, p;
+  load_ext(acc, partials + (size_t)first * 8);
+  for (uint32_t k = 1; k < cnt; k++) {
+    load_ext(p, partials + (size_t)(first + k) * 8);
+    ge_add(acc, acc, p);
   }
-  if (lane == 0 && gid < total_buckets) store_ext(buckets + (size_t)gid * 8, acc);
+  store_ext(buckets + (size_t)g * 8, acc);
 }
 
 // ---------------------------------------------------------------------------------------------------------
