@@ -277,9 +277,11 @@ def main():
 
     # ---- timed region: device-resident ---------------------------------------------------------------------
     sampler = ClockSampler(local_rank)
+    sampler.start()
+    for _ in range(2):                 # keep the GPU busy while nvidia-smi starts sampling
+        step_dev()
     launches0 = eng.launch_count
     barrier()
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     accepts = 0
@@ -287,7 +289,6 @@ def main():
         step_dev()
     e1.record(stream)
     barrier()
-    clocks = sampler.stop()
     launches = eng.launch_count - launches0
     ms_total = e0.elapsed_time(e1)
     assert read_result() == (0, 1)
@@ -304,6 +305,7 @@ def main():
         accepts += int(ok)
     barrier()
     e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
     assert accepts == args.steps
 
     # ---- gather: max time over ranks, accept bits over NCCL ---------------------------------------------------

@@ -1,0 +1,71 @@
+/* zkp_b200_host.h -- flat C face of the host-side mirror of zkp's toolbox (zkp_b200/csrc/host/*.cpp).
+ *
+ * The C++ classes there (Prover, Verifier, BatchVerifier, Statement = the define_proof! mirror) follow
+ * /root/reference/src/toolbox/{prover,verifier,batch_verifier,mod}.rs and /root/reference/src/macros.rs:206-370;
+ * this header only makes them callable from ctypes for the parity tests and the benches.  All MSM / compress /
+ * decompress work inside goes through the device entry points of zkp_b200.h.
+ *
+ * A statement is described by flat arrays (what define_proof!{name, label, (secrets), (instance), (common) : ...}
+ * expands to): NUL-separated label strings and constraints in CSR form; point indices run over instance ++ common.
+ * Return values are the reference's ProofError: 0 Ok, 1 VerificationFailure, 2 BatchSizeMismatch, 3 engine failure.
+ */
+#ifndef ZKP_B200_HOST_H
+#define ZKP_B200_HOST_H
+#include <stddef.h>
+#include <stdint.h>
+#include "zkp_b200.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct zkph_statement zkph_statement;
+
+/* labels: `n_secrets + n_instance + n_common` NUL-terminated strings back to back (secrets, instance, common).
+ * constraint i: lhs point index lhs[i]; terms cons_off[i]..cons_off[i+1]-1 of (term_scalar[], term_point[]).  */
+zkph_statement* zkph_statement_new(const char* name, const char* label, const char* labels, int32_t n_secrets,
+                                   int32_t n_instance, int32_t n_common, int32_t n_constraints, const int32_t* lhs,
+                                   const int32_t* cons_off, const int32_t* term_scalar, const int32_t* term_point);
+void zkph_statement_free(zkph_statement* st);
+
+/* module::prove_compact / prove_batchable (macros.rs:261-278) for ONE proof.
+ * secrets[m][32], points[p][20 u64] (limb form, allocation order), rng_seed = stand-in for thread_rng.
+ * Outputs: encodings[p][32]; compact: challenge[32] + responses[m][32]; batchable: commitments[k][32] + responses. */
+int32_t zkph_prove(zkp_ctx* ctx, const zkph_statement* st, const uint8_t* transcript_label, size_t tl_len,
+                   const uint8_t* secrets, const uint64_t* points, const uint8_t* rng_seed, size_t seed_len,
+                   int32_t batchable, uint8_t* encodings, uint8_t* challenge, uint8_t* commitments, uint8_t* responses,
+                   uint8_t* blindings_out /* may be NULL */);
+
+/* module::verify_compact (macros.rs:314-322) */
+int32_t zkph_verify_compact(zkp_ctx* ctx, const zkph_statement* st, const uint8_t* transcript_label, size_t tl_len,
+                            const uint8_t* points_enc, const uint8_t* challenge, const uint8_t* responses,
+                            size_t n_responses);
+/* module::verify_batchable (macros.rs:325-333) */
+int32_t zkph_verify_batchable(zkp_ctx* ctx, const zkph_statement* st, const uint8_t* transcript_label, size_t tl_len,
+                              const uint8_t* points_enc, const uint8_t* commitments, size_t n_commitments,
+                              const uint8_t* responses, size_t n_responses, const uint8_t* rng_seed, size_t seed_len);
+
+/* module::batch_verify (macros.rs:336-370): instance_enc[n_instance][N][32], common_enc[n_common][32],
+ * commitments[N][k][32], responses[N][m][32].  coeff_out (optional) receives what the reference feeds the MSM:
+ * static_coeffs[num_s][32] ++ row-major instance matrix[(n_instance+k)][N][32]; points_out likewise.          */
+int32_t zkph_batch_verify(zkp_ctx* ctx, const zkph_statement* st, const uint8_t* transcript_label, size_t tl_len,
+                          size_t N, const uint8_t* instance_enc, const uint8_t* common_enc, const uint8_t* commitments,
+                          const uint8_t* responses, const uint8_t* rng_seed, size_t seed_len, int32_t threads,
+                          uint8_t* coeff_out, uint8_t* points_out, double* host_seconds /* hashing+fold, may be NULL */);
+
+/* N independent batchable proofs of one statement in three batched device calls (BASELINE configs[1]):
+ * secrets[N][m][32], points[N][p][20 u64], entropy[N][32] -> encodings[N][p][32], commitments[N][k][32],
+ * responses[N][m][32].  Per-proof results equal zkph_prove(batchable) with the same entropy.                 */
+int32_t zkph_prove_many(zkp_ctx* ctx, const zkph_statement* st, const uint8_t* transcript_label, size_t tl_len, size_t N,
+                        const uint8_t* secrets, const uint64_t* points, const uint8_t* entropy, int32_t threads,
+                        uint8_t* encodings, uint8_t* commitments, uint8_t* responses);
+
+/* host primitives exposed for parity tests */
+void zkph_scalar_mul(uint8_t* out32, const uint8_t* a32, const uint8_t* b32);
+void zkph_scalar_from_wide(uint8_t* out32, const uint8_t* in64);
+void zkph_merlin_test_vector(uint8_t* out32);
+void zkph_rng_bytes(const uint8_t* seed, size_t seed_len, uint8_t* out, size_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,147 @@
+"""GPU parity of the host mirror (C++ toolbox over the CUDA engine) against the oracle's restatement of the
+reference's Prover / Verifier / BatchVerifier: identical injected randomness => identical bytes."""
+import numpy as np
+import pytest
+
+from oracle import merlin as OM, msm as M, ristretto as R, scalar as S, toolbox as OT
+from tests import util_data as U
+from zkp_b200 import toolbox as PT
+
+pytestmark = pytest.mark.gpu
+
+
+def limbs(pt):
+    return [((c % R.P) >> (51 * j)) & ((1 << 51) - 1) for c in pt for j in range(5)]
+
+
+def sbytes(xs):
+    return np.frombuffer(b"".join(S.to_bytes(x) for x in xs), dtype=np.uint8).reshape(-1, 32)
+
+
+def dleq_instance(j=0):
+    G = R.BASEPOINT
+    H = R.hash_from_bytes_sha512(R.compress(G))
+    x = 89327492234 + j
+    return x, dict(A=R.pt_mul(x, G), B=R.pt_mul(x, H), H=H, G=G)
+
+
+def test_dleq_prove_verify_matches_oracle(engine):
+    """BASELINE configs[0] (DLEQ 1 prove + 1 verify) through the product path, byte-equal to the oracle."""
+    st, ost = PT.dleq_statement(), OT.DLEQ
+    x, pts = dleq_instance()
+    order = st.points
+    plimbs = np.array([limbs(pts[n]) for n in order], dtype=np.uint64)
+    for batchable in (False, True):
+        seed = b"seed-%d" % batchable
+        if batchable:
+            (com, resp), enc = st.prove_batchable(engine, b"DLEQTest", sbytes([x]), plimbs, seed)
+            op, oenc = ost.prove_batchable(OM.Transcript(b"DLEQTest"), dict(x=x), pts, OT.SeededRng(seed))
+            assert [bytes(c) for c in com] == op.commitments
+        else:
+            (chal, resp), enc = st.prove_compact(engine, b"DLEQTest", sbytes([x]), plimbs, seed)
+            op, oenc = ost.prove_compact(OM.Transcript(b"DLEQTest"), dict(x=x), pts, OT.SeededRng(seed))
+            assert chal == S.to_bytes(op.challenge)
+        assert [bytes(r) for r in resp] == [S.to_bytes(r) for r in op.responses]
+        assert [bytes(e) for e in enc] == [oenc[n] for n in order]
+        if batchable:
+            st.verify_batchable(engine, (com, resp), b"DLEQTest", enc, b"w")
+            bad = resp.copy()
+            bad[0, 0] ^= 1
+            with pytest.raises(PT.VerificationFailure):
+                st.verify_batchable(engine, (com, bad), b"DLEQTest", enc, b"w")
+            with pytest.raises(PT.VerificationFailure):      # wrong domain separator
+                st.verify_batchable(engine, (com, resp), b"DLEQTesu", enc, b"w")
+        else:
+            st.verify_compact(engine, (chal, resp), b"DLEQTest", enc)
+            bad = resp.copy()
+            bad[0, 0] ^= 1
+            with pytest.raises(PT.VerificationFailure):
+                st.verify_compact(engine, (chal, bad), b"DLEQTest", enc)
+            wrong = enc.copy()
+            wrong[0] = enc[1]                                   # wrong public point
+            with pytest.raises(PT.VerificationFailure):
+                st.verify_compact(engine, (chal, resp), b"DLEQTest", wrong)
+            with pytest.raises(PT.VerificationFailure):      # identity encoding rejected at allocation (mod.rs:191)
+                wrong[0] = 0
+                st.verify_compact(engine, (chal, resp), b"DLEQTest", wrong)
+            with pytest.raises(PT.VerificationFailure):      # undecodable point (verifier.rs:92)
+                wrong[0] = np.frombuffer(bytes.fromhex(U.golden("rfc9496.json")["bad_encodings"][6]), dtype=np.uint8)
+                st.verify_compact(engine, (chal, resp), b"DLEQTest", wrong)
+
+
+def _cmz_instances(N, seed):
+    rng = OT.SeededRng(seed)
+    ost = OT.CMZ10
+    common = {n: R.from_uniform_bytes(rng.bytes(64)) for n in ost.common}
+    secs, ptss = [], []
+    for _ in range(N):
+        sec = {n: int.from_bytes(rng.bytes(64), "little") % R.L for n in ost.secrets}
+        P, Q = R.from_uniform_bytes(rng.bytes(64)), R.from_uniform_bytes(rng.bytes(64))
+        pts = dict(common)
+        pts["P"], pts["Q"] = P, Q
+        for i in range(1, 11):
+            pts["C_%d" % i] = M.naive_msm([sec["m_%d" % i], sec["z_%d" % i]], [P, pts["A"]])
+        pts["V"] = M.naive_msm([sec["m_%d" % i] for i in range(1, 11)] + [sec["minus_z_Q"]],
+                               [pts["X_%d" % i] for i in range(1, 11)] + [Q])
+        secs.append(sec)
+        ptss.append(pts)
+    return secs, ptss
+
+
+def test_cmz_prove_many_and_batch_verify_match_oracle(engine):
+    st, ost = PT.cmz10_statement(), OT.CMZ10
+    N = 5
+    secs, ptss = _cmz_instances(N, b"cmz-gpu")
+    sec_arr = np.stack([sbytes([s[n] for n in st.secrets]) for s in secs])
+    pts_arr = np.array([[limbs(p[n]) for n in st.points] for p in ptss], dtype=np.uint64)
+    entropy = np.frombuffer(OT.SeededRng(b"entropy").bytes(32 * N), dtype=np.uint8).reshape(N, 32)
+    enc, com, resp = st.prove_many(engine, b"CMZ", sec_arr, pts_arr, entropy, threads=3)
+    oproofs = []
+    for j in range(N):
+        class OneShot:            # feeds the oracle prover the same 32 entropy bytes
+            def __init__(self, b): self.b = b
+            def bytes(self, n): return self.b
+        op, oenc = ost.prove_batchable(OM.Transcript(b"CMZ"), secs[j], ptss[j], OneShot(entropy[j].tobytes()))
+        assert [bytes(c) for c in com[j]] == op.commitments
+        assert [bytes(r) for r in resp[j]] == [S.to_bytes(r) for r in op.responses]
+        assert [bytes(e) for e in enc[j]] == [oenc[n] for n in st.points]
+        oproofs.append(op)
+    # single-proof paths on proof 0
+    st.verify_batchable(engine, (com[0], resp[0]), b"CMZ", enc[0], b"rho")
+    # batch verification: the MSM inputs equal the oracle's (same rho stream), and the verdicts agree
+    ni = len(st.instance)
+    inst = np.ascontiguousarray(enc[:, :ni].transpose(1, 0, 2))
+    comm = enc[0, ni:]
+    co, po, _ = st.batch_verify(engine, com, resp, b"CMZ", inst, comm, b"batch-rho", threads=2, want_msm_inputs=True)
+    oencs = {n: [bytes(enc[j, i]) for j in range(N)] for i, n in enumerate(st.instance)}
+    for i, n in enumerate(st.common):
+        oencs[n] = bytes(comm[i])
+    bv = ost.build_batch_verifier(N, [OM.Transcript(b"CMZ") for _ in range(N)], oencs)
+    oscal, opts = bv.batch_coeffs(oproofs, OT.SeededRng(b"batch-rho"))
+    assert [bytes(c) for c in co] == [S.to_bytes(s) for s in oscal]
+    assert [bytes(p) for p in po] == opts
+    bad = resp.copy()
+    bad[3, 7, 0] ^= 1
+    with pytest.raises(PT.VerificationFailure):
+        st.batch_verify(engine, com, bad, b"CMZ", inst, comm, b"batch-rho")
+    with pytest.raises(PT.BatchSizeMismatch):
+        st.batch_verify(engine, com, resp[:4], b"CMZ", inst, comm, b"batch-rho")
+    badc = com.copy()
+    badc[2, 4] = 0                                                  # identity commitment (mod.rs:215)
+    with pytest.raises(PT.VerificationFailure):
+        st.batch_verify(engine, badc, resp, b"CMZ", inst, comm, b"batch-rho")
+
+
+def test_dleq_batch_golden(engine):
+    """tests/zkp.rs:115-175 shape: 4 macro-form DLEQ proofs, golden fixture produced by the oracle."""
+    kb = U.golden("toolbox_kat.json")["dleq_batch"]
+    st = PT.dleq_statement()
+    h = lambda xs: np.frombuffer(b"".join(bytes.fromhex(x) for x in xs), dtype=np.uint8).reshape(-1, 32)
+    com = np.stack([h(p["commitments"]) for p in kb["proofs"]])
+    resp = np.stack([h(p["responses"]) for p in kb["proofs"]])
+    inst = np.stack([h(kb["A"]), h(kb["B"]), h(kb["H"])])
+    comm = h([kb["G"]])
+    co, po, _ = st.batch_verify(engine, com, resp, b"DLEQBatchTest", inst, comm, kb["verify_rng_seed"].encode(),
+                                want_msm_inputs=True)
+    assert [bytes(c).hex() for c in co] == kb["msm_scalars"]
+    assert [bytes(p).hex() for p in po] == kb["msm_points"]

@@ -8,9 +8,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libzkp_b200.so")
-SOURCES = ["api.cu"]
+SOURCES = ["api.cu", "host/merlin.cpp", "host/scalar.cpp", "host/toolbox.cpp", "host/host_api.cpp"]
 HEADERS = ["fe.cuh", "ge.cuh", "sc.cuh", "kernels.cuh", "small_msm.cuh", "bench_fe.cuh",
-           os.path.join("..", "..", "include", "zkp_b200.h")]
+           "host/merlin.hpp", "host/scalar.hpp", "host/toolbox.hpp",
+           os.path.join("..", "..", "include", "zkp_b200.h"), os.path.join("..", "..", "include", "zkp_b200_host.h")]
 
 
 def nvcc_path():
@@ -33,7 +34,7 @@ def build(force=False, verbose=False):
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+           "-Xcompiler", "-fPIC,-pthread", "-shared", "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

@@ -30,7 +30,7 @@ struct zkp_ctx {
   std::string err;
   // workspace (grown on demand, reused across calls)
   devbuf in_scalars, in_points, niels, hist, offs, cursor, sorted, buckets, lvlT[2], lvlU, usum, flags, result,
-      aux0, aux1, aux2, sk0, sk1, tables, items, partials;
+      aux0, aux1, aux2, sk0, sk1, tables, items, partials, multi;
   void* h_result = nullptr;  // pinned, 64 bytes
   // optional per-stage timing of the vartime MSM ("profile" option): events around each stage
   int profile = 0;
@@ -129,7 +129,7 @@ extern "C" void zkp_ctx_destroy(zkp_ctx* ctx) {
   devbuf* bufs[] = {&ctx->in_scalars, &ctx->in_points, &ctx->niels, &ctx->hist, &ctx->offs, &ctx->cursor,
                     &ctx->sorted, &ctx->buckets, &ctx->lvlT[0], &ctx->lvlT[1], &ctx->lvlU, &ctx->usum,
                     &ctx->flags, &ctx->result, &ctx->aux0, &ctx->aux1, &ctx->aux2, &ctx->sk0, &ctx->sk1,
-                    &ctx->tables, &ctx->items, &ctx->partials};
+                    &ctx->tables, &ctx->items, &ctx->partials, &ctx->multi};
   for (devbuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (ctx->h_result) cudaFreeHost(ctx->h_result);
@@ -286,16 +286,19 @@ static int32_t msm_vartime_launch(zkp_ctx* ctx, const void* d_scalars, const voi
     k_scan<<<1, 1024, 0, st>>>((const uint32_t*)ctx->aux0.p, total_buckets, (uint32_t*)ctx->aux1.p,
                                (uint32_t*)ctx->aux2.p);
     LAUNCH_CHECK(ctx);
+    ENSURE(ctx, ctx->multi, ((size_t)total_buckets + 4) * 4);
+    uint32_t* n_multi = (uint32_t*)ctx->multi.p;          // word 0 = counter, list starts at word 4
+    CUDA_TRY(ctx, cudaMemsetAsync(n_multi, 0, 16, st));
     k_items<<<tb, 256, 0, st>>>((const uint32_t*)ctx->offs.p, (const uint32_t*)ctx->aux1.p, B, total_buckets, S,
-                                (work_item*)ctx->items.p);
+                                (work_item*)ctx->items.p, n_multi + 4, n_multi);
     LAUNCH_CHECK(ctx);
     const unsigned blocks = (unsigned)((max_items + 127) / 128);
     k_accumulate<<<blocks, 128, 0, st>>>((const uint4*)ctx->niels.p, (const uint32_t*)ctx->sorted.p,
                                          (const work_item*)ctx->items.p, (const uint32_t*)ctx->aux1.p + total_buckets,
                                          n, (uint4*)ctx->buckets.p, (uint4*)ctx->partials.p);
     LAUNCH_CHECK(ctx);
-    k_merge<<<(total_buckets + 127) / 128, 128, 0, st>>>((const uint32_t*)ctx->aux1.p, total_buckets,
-                                                         (const uint4*)ctx->partials.p, (uint4*)ctx->buckets.p);
+    k_merge<<<148 * 8, 128, 0, st>>>((const uint32_t*)ctx->aux1.p, n_multi + 4, n_multi,
+                                     (const uint4*)ctx->partials.p, (uint4*)ctx->buckets.p);
     LAUNCH_CHECK(ctx);
   }
 

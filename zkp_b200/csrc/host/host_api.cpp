@@ -1,0 +1,216 @@
+// extern "C" face of the host mirror (include/zkp_b200_host.h).
+#include <chrono>
+#include <new>
+
+#include "../../../include/zkp_b200_host.h"
+#include "toolbox.hpp"
+
+using namespace zkp_host;
+
+struct zkph_statement { Statement st; };
+
+extern "C" zkph_statement* zkph_statement_new(const char* name, const char* label, const char* labels, int32_t n_secrets,
+                                              int32_t n_instance, int32_t n_common, int32_t n_constraints,
+                                              const int32_t* lhs, const int32_t* cons_off, const int32_t* term_scalar,
+                                              const int32_t* term_point) {
+  zkph_statement* h = new (std::nothrow) zkph_statement();
+  if (!h) return nullptr;
+  Statement& st = h->st;
+  st.name = name;
+  st.label = label;
+  const char* p = labels;
+  for (int i = 0; i < n_secrets + n_instance + n_common; i++) {
+    std::string s(p);
+    p += s.size() + 1;
+    if (i < n_secrets) st.secrets.push_back(s);
+    else if (i < n_secrets + n_instance) st.instance.push_back(s);
+    else st.common.push_back(s);
+  }
+  for (int i = 0; i < n_constraints; i++) {
+    LinComb lc;
+    for (int t = cons_off[i]; t < cons_off[i + 1]; t++) lc.push_back(std::make_pair((int)term_scalar[t], (int)term_point[t]));
+    st.constraints.push_back(std::make_pair((int)lhs[i], lc));
+  }
+  return h;
+}
+extern "C" void zkph_statement_free(zkph_statement* st) { delete st; }
+
+static Scalar load_scalar(const uint8_t* b) { return Scalar::from_bytes_mod_order(b); }
+
+extern "C" int32_t zkph_prove(zkp_ctx* ctx, const zkph_statement* h, const uint8_t* tl, size_t tl_len,
+                              const uint8_t* secrets, const uint64_t* points, const uint8_t* seed, size_t seed_len,
+                              int32_t batchable, uint8_t* encodings, uint8_t* challenge, uint8_t* commitments,
+                              uint8_t* responses, uint8_t* blindings_out) {
+  const Statement& st = h->st;
+  const size_t m = st.secrets.size(), p = st.num_points(), k = st.constraints.size();
+  std::vector<Scalar> sec(m);
+  for (size_t i = 0; i < m; i++) sec[i] = load_scalar(secrets + 32 * i);
+  std::vector<Limbs> pts(p);
+  for (size_t i = 0; i < p; i++) memcpy(pts[i].data(), points + 20 * i, 160);
+  Transcript t(tl, tl_len);
+  Rng rng(seed, seed_len);
+  // re-implemented inline (instead of stmt_prove) to hand the blindings back for parity tests
+  Prover pr(ctx, st.label, &t);
+  for (size_t i = 0; i < m; i++) pr.allocate_scalar(st.secrets[i], sec[i]);
+  for (size_t i = 0; i < p; i++) {
+    Enc e;
+    ProofError err;
+    pr.allocate_point(st.point_name(i), pts[i], &e, &err);
+    if (err != PROOF_OK) return err;
+    memcpy(encodings + 32 * i, e.data(), 32);
+  }
+  for (auto& c : st.constraints) pr.constrain(c.first, c.second);
+  ProofError e;
+  if (batchable) {
+    BatchableProof bp;
+    e = pr.prove_batchable(rng, &bp);
+    if (e != PROOF_OK) return e;
+    for (size_t i = 0; i < k; i++) memcpy(commitments + 32 * i, bp.commitments[i].data(), 32);
+    for (size_t i = 0; i < m; i++) bp.responses[i].to_bytes(responses + 32 * i);
+  } else {
+    CompactProof cp;
+    e = pr.prove_compact(rng, &cp);
+    if (e != PROOF_OK) return e;
+    cp.challenge.to_bytes(challenge);
+    for (size_t i = 0; i < m; i++) cp.responses[i].to_bytes(responses + 32 * i);
+  }
+  if (blindings_out)
+    for (size_t i = 0; i < m; i++) pr.last_blindings[i].to_bytes(blindings_out + 32 * i);
+  return PROOF_OK;
+}
+
+static std::vector<Enc> load_encs(const uint8_t* b, size_t n) {
+  std::vector<Enc> v(n);
+  for (size_t i = 0; i < n; i++) memcpy(v[i].data(), b + 32 * i, 32);
+  return v;
+}
+
+extern "C" int32_t zkph_verify_compact(zkp_ctx* ctx, const zkph_statement* h, const uint8_t* tl, size_t tl_len,
+                                       const uint8_t* points_enc, const uint8_t* challenge, const uint8_t* responses,
+                                       size_t n_responses) {
+  const Statement& st = h->st;
+  CompactProof cp;
+  // Scalar deserialisation in the reference rejects non-canonical bytes; mirror that as a failure
+  if (!Scalar::from_canonical_bytes(&cp.challenge, challenge)) return VerificationFailure;
+  cp.responses.resize(n_responses);
+  for (size_t i = 0; i < n_responses; i++)
+    if (!Scalar::from_canonical_bytes(&cp.responses[i], responses + 32 * i)) return VerificationFailure;
+  Transcript t(tl, tl_len);
+  return stmt_verify_compact(ctx, st, &t, load_encs(points_enc, st.num_points()), cp);
+}
+
+extern "C" int32_t zkph_verify_batchable(zkp_ctx* ctx, const zkph_statement* h, const uint8_t* tl, size_t tl_len,
+                                         const uint8_t* points_enc, const uint8_t* commitments, size_t n_commitments,
+                                         const uint8_t* responses, size_t n_responses, const uint8_t* seed,
+                                         size_t seed_len) {
+  const Statement& st = h->st;
+  BatchableProof bp;
+  bp.commitments = load_encs(commitments, n_commitments);
+  bp.responses.resize(n_responses);
+  for (size_t i = 0; i < n_responses; i++)
+    if (!Scalar::from_canonical_bytes(&bp.responses[i], responses + 32 * i)) return VerificationFailure;
+  Transcript t(tl, tl_len);
+  Rng rng(seed, seed_len);
+  return stmt_verify_batchable(ctx, st, &t, load_encs(points_enc, st.num_points()), bp, rng);
+}
+
+extern "C" int32_t zkph_batch_verify(zkp_ctx* ctx, const zkph_statement* h, const uint8_t* tl, size_t tl_len, size_t N,
+                                     const uint8_t* instance_enc, const uint8_t* common_enc, const uint8_t* commitments,
+                                     const uint8_t* responses, const uint8_t* seed, size_t seed_len, int32_t threads,
+                                     uint8_t* coeff_out, uint8_t* points_out, double* host_seconds) {
+  const Statement& st = h->st;
+  const size_t m = st.secrets.size(), k = st.constraints.size(), ni = st.instance.size(), nc = st.common.size();
+  auto t0 = std::chrono::steady_clock::now();
+  std::vector<BatchableProof> proofs(N);
+  for (size_t j = 0; j < N; j++) {
+    proofs[j].commitments = load_encs(commitments + j * k * 32, k);
+    proofs[j].responses.resize(m);
+    for (size_t i = 0; i < m; i++)
+      if (!Scalar::from_canonical_bytes(&proofs[j].responses[i], responses + (j * m + i) * 32)) return VerificationFailure;
+  }
+  std::vector<Transcript> transcripts(N, Transcript(tl, tl_len));
+  Rng rng(seed, seed_len);
+  ProofError err;
+  BatchVerifier bv(ctx, st.label, N, &transcripts, &err);
+  if (err != PROOF_OK) return err;
+  for (auto& s : st.secrets) bv.allocate_scalar(s);
+  std::vector<BatchPointVar> pv;
+  for (size_t i = 0; i < ni; i++) {
+    pv.push_back(bv.allocate_instance_point(st.instance[i], load_encs(instance_enc + i * N * 32, N), &err));
+    if (err != PROOF_OK) return err;
+  }
+  for (size_t i = 0; i < nc; i++) {
+    Enc e;
+    memcpy(e.data(), common_enc + 32 * i, 32);
+    pv.push_back(bv.allocate_static_point(st.common[i], e, &err));
+    if (err != PROOF_OK) return err;
+  }
+  for (auto& c : st.constraints) {
+    BatchLinComb lc;
+    for (auto& term : c.second) lc.push_back(std::make_pair(term.first, pv[term.second]));
+    bv.constrain(pv[c.first], lc);
+  }
+  std::vector<uint8_t> sc, ic, ip;
+  err = bv.batch_coeffs(proofs, rng, threads, &sc, &ic, &ip);
+  if (err != PROOF_OK) return err;
+  if (host_seconds) *host_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  std::vector<uint8_t> sp(nc * 32);
+  for (size_t s = 0; s < nc; s++) memcpy(&sp[32 * s], bv.static_points()[s].data(), 32);
+  if (coeff_out) {
+    memcpy(coeff_out, sc.data(), sc.size());
+    memcpy(coeff_out + sc.size(), ic.data(), ic.size());
+  }
+  if (points_out) {
+    memcpy(points_out, sp.data(), sp.size());
+    memcpy(points_out + sp.size(), ip.data(), ip.size());
+  }
+  int32_t accept = 0;
+  int64_t bad = -1;
+  int32_t rc = zkp_batch_verify(ctx, sc.data(), sp.data(), nc, ic.data(), ip.data(), bv.rows(), N, &accept, &bad);
+  if (rc == ZKP_ERR_POINT) return VerificationFailure;
+  if (rc != ZKP_OK) return EngineFailure;
+  return accept ? PROOF_OK : VerificationFailure;
+}
+
+extern "C" int32_t zkph_prove_many(zkp_ctx* ctx, const zkph_statement* h, const uint8_t* tl, size_t tl_len, size_t N,
+                                   const uint8_t* secrets, const uint64_t* points, const uint8_t* entropy,
+                                   int32_t threads, uint8_t* encodings, uint8_t* commitments, uint8_t* responses) {
+  const Statement& st = h->st;
+  const size_t m = st.secrets.size(), p = st.num_points(), k = st.constraints.size();
+  std::vector<Scalar> sec(N * m);
+  for (size_t i = 0; i < N * m; i++) sec[i] = load_scalar(secrets + 32 * i);
+  std::vector<BatchableProof> proofs;
+  std::vector<Enc> encs;
+  ProofError e = stmt_prove_many(ctx, st, std::string((const char*)tl, tl_len), N, sec.data(), (const Limbs*)points,
+                                 entropy, threads, &proofs, &encs);
+  if (e != PROOF_OK) return e;
+  memcpy(encodings, encs.data(), N * p * 32);
+  for (size_t j = 0; j < N; j++) {
+    for (size_t i = 0; i < k; i++) memcpy(commitments + (j * k + i) * 32, proofs[j].commitments[i].data(), 32);
+    for (size_t i = 0; i < m; i++) proofs[j].responses[i].to_bytes(responses + (j * m + i) * 32);
+  }
+  return PROOF_OK;
+}
+
+extern "C" void zkph_scalar_mul(uint8_t* out32, const uint8_t* a32, const uint8_t* b32) {
+  sc_mul(Scalar::from_bytes_mod_order(a32), Scalar::from_bytes_mod_order(b32)).to_bytes(out32);
+}
+extern "C" void zkph_scalar_from_wide(uint8_t* out32, const uint8_t* in64) {
+  Scalar::from_bytes_mod_order_wide(in64).to_bytes(out32);
+}
+extern "C" void zkph_merlin_test_vector(uint8_t* out32) {
+  Transcript t((const uint8_t*)"test protocol", 13);
+  t.append_message((const uint8_t*)"step1", 5, (const uint8_t*)"some data", 9);
+  uint8_t ch[32], big[1024];
+  memset(big, 0x63, 1024);
+  for (int i = 0; i < 32; i++) {
+    t.challenge_bytes((const uint8_t*)"challenge", 9, ch, 32);
+    t.append_message((const uint8_t*)"bigdata", 7, big, 1024);
+    t.append_message((const uint8_t*)"challengedata", 13, ch, 32);
+  }
+  memcpy(out32, ch, 32);
+}
+extern "C" void zkph_rng_bytes(const uint8_t* seed, size_t seed_len, uint8_t* out, size_t n) {
+  Rng r(seed, seed_len);
+  r.bytes(out, n);
+}

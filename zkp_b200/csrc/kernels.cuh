@@ -244,7 +244,8 @@ __global__ void __launch_bounds__(256) k_plan(const uint32_t* __restrict__ offs,
 
 __global__ void __launch_bounds__(256) k_items(const uint32_t* __restrict__ offs, const uint32_t* __restrict__ item_offs,
                                                uint32_t B, uint32_t total_buckets, uint32_t S,
-                                               work_item* __restrict__ items) {
+                                               work_item* __restrict__ items, uint32_t* __restrict__ multi,
+                                               uint32_t* __restrict__ n_multi) {
   uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= total_buckets) return;
   uint32_t w = g / B, b = g % B;
@@ -255,6 +256,7 @@ __global__ void __launch_bounds__(256) k_items(const uint32_t* __restrict__ offs
     work_item it = {start, end, g, w};
     items[first] = it;
   } else {
+    multi[atomicAdd(n_multi, 1u)] = g;   // buckets whose partial sums k_merge has to add
     for (uint32_t k = 0; k < cnt; k++) {
       uint32_t s0 = start + k * S, e0 = min(s0 + S, end);
       work_item it = {s0, e0, first + k, w | 0x80000000u};
@@ -299,20 +301,31 @@ __global__ void __launch_bounds__(128, 4) k_accumulate(const uint4* __restrict__
   store_ext(dst, acc);
 }
 
-// buckets with more than one chunk: add their partial sums
-__global__ void __launch_bounds__(128) k_merge(const uint32_t* __restrict__ item_offs, uint32_t total_buckets,
-                                               const uint4* __restrict__ partials, uint4* __restrict__ buckets) {
-  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= total_buckets) return;
-  uint32_t first = item_offs[g], cnt = item_offs[g + 1] - first;
-  if (cnt <= 1) return;
-  ge_ext acc, p;
-  load_ext(acc, partials + (size_t)first * 8);
-  for (uint32_t k = 1; k < cnt; k++) {
-    load_ext(p, partials + (size_t)(first + k) * 8);
-    ge_add(acc, acc, p);
+// buckets with more than one chunk: one warp per such bucket adds the partial sums (lanes stride over the
+// partials, then a warp-shuffle tree), so even a bucket that received every term is reduced in parallel.
+__global__ void __launch_bounds__(128) k_merge(const uint32_t* __restrict__ item_offs, const uint32_t* __restrict__ multi,
+                                               const uint32_t* __restrict__ n_multi, const uint4* __restrict__ partials,
+                                               uint4* __restrict__ buckets) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t total = *n_multi;
+  for (uint32_t idx = warp; idx < total; idx += nwarps) {
+    const uint32_t g = multi[idx];
+    const uint32_t first = item_offs[g], cnt = item_offs[g + 1] - first;
+    ge_ext acc, p;
+    ge_identity(acc);
+    for (uint32_t k = lane; k < cnt; k += 32) {
+      load_ext(p, partials + (size_t)(first + k) * 8);
+      ge_add(acc, acc, p);
+    }
+#pragma unroll 1
+    for (int off = 16; off >= 1; off >>= 1) {
+      shfl_down_ext(p, acc, off, 32);
+      ge_add(acc, acc, p);
+    }
+    if (lane == 0) store_ext(buckets + (size_t)g * 8, acc);
   }
-  store_ext(buckets + (size_t)g * 8, acc);
 }
 
 // ---------------------------------------------------------------------------------------------------------

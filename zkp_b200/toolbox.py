@@ -1,0 +1,187 @@
+"""Python face of the C++ host mirror of zkp's toolbox (include/zkp_b200_host.h -> zkp_b200/csrc/host/).
+
+`Statement` is what `define_proof!{name, label, (secrets), (instance), (common) : lhs = (s*P + ...), ...}` expands to
+(/root/reference/src/macros.rs:74-370): the same five module functions, same argument meaning, same errors.  All
+arithmetic on points happens on the GPU through the C ABI; hashing and scalar arithmetic run in the C++ host
+library.  Nothing here falls back to a CPU implementation of the hot path.
+"""
+import ctypes
+
+import numpy as np
+
+from . import native
+from .engine import Engine, _u8
+
+
+class ProofError(Exception):
+    """zkp::ProofError (/root/reference/src/errors.rs:4-11)."""
+
+
+class VerificationFailure(ProofError):
+    pass
+
+
+class BatchSizeMismatch(ProofError):
+    pass
+
+
+def _raise(rc):
+    if rc == 0:
+        return
+    if rc == 1:
+        raise VerificationFailure()
+    if rc == 2:
+        raise BatchSizeMismatch()
+    raise RuntimeError("zkp_b200 host/engine failure (code %d)" % rc)
+
+
+_bound = False
+
+
+def _lib():
+    global _bound
+    lib = native.load()
+    if not _bound:
+        vp, sz, i32 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int32
+        lib.zkph_statement_new.restype = vp
+        lib.zkph_statement_new.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, i32, i32, i32, i32, vp, vp, vp, vp]
+        lib.zkph_statement_free.argtypes = [vp]
+        lib.zkph_prove.argtypes = [vp, vp, vp, sz, vp, vp, vp, sz, i32, vp, vp, vp, vp, vp]
+        lib.zkph_verify_compact.argtypes = [vp, vp, vp, sz, vp, vp, vp, sz]
+        lib.zkph_verify_batchable.argtypes = [vp, vp, vp, sz, vp, vp, sz, vp, sz, vp, sz]
+        lib.zkph_batch_verify.argtypes = [vp, vp, vp, sz, sz, vp, vp, vp, vp, vp, sz, i32, vp, vp, vp]
+        lib.zkph_prove_many.argtypes = [vp, vp, vp, sz, sz, vp, vp, vp, i32, vp, vp, vp]
+        lib.zkph_scalar_mul.argtypes = [vp, vp, vp]
+        lib.zkph_scalar_from_wide.argtypes = [vp, vp]
+        lib.zkph_merlin_test_vector.argtypes = [vp]
+        lib.zkph_rng_bytes.argtypes = [vp, sz, vp, sz]
+        _bound = True
+    return lib
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+class Statement:
+    """define_proof! mirror.  constraints: [(lhs_name, [(secret_name, point_name), ...]), ...]."""
+
+    def __init__(self, name, label, secrets, instance, common, constraints):
+        self.name, self.label = name, label
+        self.secrets, self.instance, self.common = list(secrets), list(instance), list(common)
+        self.points = self.instance + self.common
+        self.constraints = [(l, list(r)) for l, r in constraints]
+        lib = _lib()
+        labels = b"".join(s.encode() + b"\0" for s in self.secrets + self.instance + self.common)
+        lhs = np.array([self.points.index(l) for l, _ in self.constraints], dtype=np.int32)
+        off = np.cumsum([0] + [len(r) for _, r in self.constraints]).astype(np.int32)
+        ts = np.array([self.secrets.index(s) for _, r in self.constraints for s, _ in r], dtype=np.int32)
+        tp = np.array([self.points.index(p) for _, r in self.constraints for _, p in r], dtype=np.int32)
+        self._keep = (labels, lhs, off, ts, tp)
+        self._h = lib.zkph_statement_new(name.encode(), label.encode(), labels, len(self.secrets), len(self.instance),
+                                         len(self.common), len(self.constraints), _p(lhs), _p(off), _p(ts), _p(tp))
+        self.m, self.p, self.k = len(self.secrets), len(self.points), len(self.constraints)
+
+    def __del__(self):
+        try:
+            _lib().zkph_statement_free(self._h)
+        except Exception:
+            pass
+
+    # ---- module::prove_compact / prove_batchable ------------------------------------------------------------
+    def _prove(self, eng, transcript_label, secrets, points_limbs, rng_seed, batchable):
+        lib = _lib()
+        sec = _u8(secrets, 32)
+        pts = np.ascontiguousarray(points_limbs, dtype=np.uint64).reshape(self.p, 20)
+        assert sec.shape[0] == self.m
+        enc = np.zeros((self.p, 32), np.uint8)
+        chal = np.zeros(32, np.uint8)
+        com = np.zeros((self.k, 32), np.uint8)
+        resp = np.zeros((self.m, 32), np.uint8)
+        blind = np.zeros((self.m, 32), np.uint8)
+        _raise(lib.zkph_prove(eng._ctx, self._h, transcript_label, len(transcript_label), _p(sec), _p(pts), rng_seed,
+                              len(rng_seed), 1 if batchable else 0, _p(enc), _p(chal), _p(com), _p(resp), _p(blind)))
+        return enc, chal, com, resp, blind
+
+    def prove_compact(self, eng, transcript_label, secrets, points_limbs, rng_seed):
+        """-> ((challenge, responses), encodings)   (macros.rs:261-268)"""
+        enc, chal, _, resp, _ = self._prove(eng, transcript_label, secrets, points_limbs, rng_seed, False)
+        return (chal.tobytes(), resp), enc
+
+    def prove_batchable(self, eng, transcript_label, secrets, points_limbs, rng_seed):
+        """-> ((commitments, responses), encodings)   (macros.rs:271-278)"""
+        enc, _, com, resp, _ = self._prove(eng, transcript_label, secrets, points_limbs, rng_seed, True)
+        return (com, resp), enc
+
+    # ---- module::verify_* -------------------------------------------------------------------------------------
+    def verify_compact(self, eng, proof, transcript_label, encodings):
+        chal, resp = proof
+        resp = _u8(resp, 32)
+        enc = _u8(encodings, 32)
+        assert enc.shape[0] == self.p
+        _raise(_lib().zkph_verify_compact(eng._ctx, self._h, transcript_label, len(transcript_label), _p(enc),
+                                          bytes(chal), _p(resp), resp.shape[0]))
+
+    def verify_batchable(self, eng, proof, transcript_label, encodings, rng_seed):
+        com, resp = proof
+        com, resp, enc = _u8(com, 32), _u8(resp, 32), _u8(encodings, 32)
+        assert enc.shape[0] == self.p
+        _raise(_lib().zkph_verify_batchable(eng._ctx, self._h, transcript_label, len(transcript_label), _p(enc), _p(com),
+                                            com.shape[0], _p(resp), resp.shape[0], rng_seed, len(rng_seed)))
+
+    # ---- module::batch_verify ---------------------------------------------------------------------------------
+    def batch_verify(self, eng, proofs_commitments, proofs_responses, transcript_label, instance_enc, common_enc,
+                     rng_seed, threads=0, want_msm_inputs=False):
+        """proofs_commitments (N,k,32), proofs_responses (N,m,32), instance_enc (n_instance,N,32), common_enc
+        (n_common,32).  Raises VerificationFailure / BatchSizeMismatch like the reference.  With
+        want_msm_inputs returns (scalars, points, host_seconds) exactly as fed to the MSM."""
+        com = np.ascontiguousarray(proofs_commitments, dtype=np.uint8)
+        resp = np.ascontiguousarray(proofs_responses, dtype=np.uint8)
+        inst = np.ascontiguousarray(instance_enc, dtype=np.uint8)
+        comm = np.ascontiguousarray(common_enc, dtype=np.uint8)
+        N = com.shape[0]
+        if resp.shape[0] != N or inst.shape[1] != N:
+            raise BatchSizeMismatch()
+        assert com.shape[1:] == (self.k, 32) and resp.shape[1:] == (self.m, 32) and inst.shape[0] == len(self.instance)
+        n = len(self.common) + (len(self.instance) + self.k) * N
+        co = np.zeros((n, 32), np.uint8) if want_msm_inputs else None
+        po = np.zeros((n, 32), np.uint8) if want_msm_inputs else None
+        hs = ctypes.c_double(0)
+        rc = _lib().zkph_batch_verify(eng._ctx, self._h, transcript_label, len(transcript_label), N, _p(inst), _p(comm),
+                                      _p(com), _p(resp), rng_seed, len(rng_seed), int(threads), _p(co), _p(po),
+                                      ctypes.byref(hs))
+        _raise(rc)
+        if want_msm_inputs:
+            return co, po, hs.value
+        return hs.value
+
+    # ---- N proofs at once (no counterpart in the reference; = N x prove_batchable) ----------------------------
+    def prove_many(self, eng, transcript_label, secrets, points_limbs, entropy, threads=0):
+        sec = np.ascontiguousarray(secrets, dtype=np.uint8).reshape(-1, self.m, 32)
+        N = sec.shape[0]
+        pts = np.ascontiguousarray(points_limbs, dtype=np.uint64).reshape(N, self.p, 20)
+        ent = np.ascontiguousarray(entropy, dtype=np.uint8).reshape(N, 32)
+        enc = np.zeros((N, self.p, 32), np.uint8)
+        com = np.zeros((N, self.k, 32), np.uint8)
+        resp = np.zeros((N, self.m, 32), np.uint8)
+        _raise(_lib().zkph_prove_many(eng._ctx, self._h, transcript_label, len(transcript_label), N, _p(sec), _p(pts),
+                                      _p(ent), int(threads), _p(enc), _p(com), _p(resp)))
+        return enc, com, resp
+
+
+def dleq_statement():
+    """define_proof! {dleq, "DLEQ proof", (x), (A, B, H), (G) : A = (x * G), B = (x * H)}  (benches/zkp.rs:49)"""
+    return Statement("dleq", "DLEQ proof", ["x"], ["A", "B", "H"], ["G"],
+                     [("A", [("x", "G")]), ("B", [("x", "H")])])
+
+
+def cmz10_statement():
+    """CMZ'13 credential presentation with 10 hidden attributes (/root/reference/benches/zkp.rs:27-46)."""
+    rng = range(1, 11)
+    return Statement(
+        "cred_show_10", "CMZ cred show n=10",
+        ["m_%d" % i for i in rng] + ["z_%d" % i for i in rng] + ["minus_z_Q"],
+        ["C_%d" % i for i in rng] + ["P", "Q", "V"],
+        ["X_%d" % i for i in rng] + ["A", "B"],
+        [("C_%d" % i, [("m_%d" % i, "P"), ("z_%d" % i, "A")]) for i in rng]
+        + [("V", [("m_%d" % i, "X_%d" % i) for i in rng] + [("minus_z_Q", "Q")])])
