@@ -168,6 +168,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log2-proofs", type=int, default=21, help="proofs per GPU (default 2^21)")
     ap.add_argument("--cpu-sample-log2", type=int, default=14, help="proofs in the CPU baseline sample")
+    ap.add_argument("--window", type=int, default=0, help="tuning: force the Pippenger window width")
+    ap.add_argument("--chunk", type=int, default=0, help="tuning: force the accumulate work-item length")
+    ap.add_argument("--sweep", default="", help="tuning: comma list of windows; prints stage times per window and exits")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -253,6 +256,21 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    if args.window:
+        eng.set_option("window", args.window)
+    if args.chunk:
+        eng.set_option("chunk", args.chunk)
+    if args.sweep:
+        eng.set_option("profile", 1)
+        for c in [int(x) for x in args.sweep.split(",")]:
+            eng.set_option("window", c)
+            step_dev()
+            step_dev()
+            st = eng.stage_ms()
+            tot = sum(v for k, v in st.items() if k not in ("window", "lanes"))
+            print("c=%d total=%.2f ms  " % (c, tot) + " ".join("%s=%.2f" % (k, v) for k, v in st.items()), flush=True)
+            assert read_result() == (0, 1)
+        return
     for _ in range(args.warmup):
         step_dev()
     torch.cuda.synchronize()
@@ -309,15 +327,13 @@ def main():
     assert accepts == args.steps
 
     # ---- gather: max time over ranks, accept bits over NCCL ---------------------------------------------------
+    from zkp_b200 import parallel
     tm = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device="cuda")
-    bits = torch.tensor([1 if accepts == args.steps else 0], dtype=torch.int32, device="cuda")
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        all_bits = [torch.zeros_like(bits) for _ in range(world)]
-        dist.all_gather(all_bits, bits)                         # the single NCCL gather of accept bits
-        accept_bitmap = [int(b.item()) for b in all_bits]
-    else:
-        accept_bitmap = [int(bits.item())]
+    # the single NCCL gather of accept bits (one per GPU shard)
+    accept_bitmap, verdict = parallel.gather_accept_bits(accepts == args.steps, device="cuda")
+    assert verdict
     ms_total, e2e_ms = float(tm[0].item()), float(tm[1].item())
 
     if rank == 0:

@@ -6,6 +6,7 @@
 #include <string.h>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/zkp_b200.h"
 #include "kernels.cuh"
@@ -37,6 +38,10 @@ struct zkp_ctx {
   cudaEvent_t ev[10] = {};
   float stage_ms[9] = {};
   int last_window = 0, last_lanes = 0;
+  // host-input pipeline: copies on copy_stream overlap the per-chunk kernels on `stream`
+  cudaStream_t copy_stream = nullptr;
+  std::vector<cudaEvent_t> chunk_ev;
+  size_t chunk_terms = (size_t)1 << 21;
 };
 
 #define CUDA_TRY(ctx, call)                                                            \
@@ -133,6 +138,10 @@ extern "C" void zkp_ctx_destroy(zkp_ctx* ctx) {
   for (devbuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (ctx->h_result) cudaFreeHost(ctx->h_result);
+  for (cudaEvent_t e : ctx->chunk_ev) cudaEventDestroy(e);
+  for (int i = 0; i < 10; i++)
+    if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -151,6 +160,9 @@ extern "C" int32_t zkp_ctx_set_option(zkp_ctx* ctx, const char* key, int64_t val
   } else if (!strcmp(key, "window_cap")) {
     if (value < 4 || value > 24) return ZKP_ERR_SIZE;
     ctx->window_cap = (int)value;
+  } else if (!strcmp(key, "chunk_terms")) {
+    if (value < 1024) return ZKP_ERR_SIZE;
+    ctx->chunk_terms = (size_t)value;
   } else if (!strcmp(key, "profile")) {
     ctx->profile = value ? 1 : 0;
     if (ctx->profile && !ctx->ev[0])
@@ -207,14 +219,14 @@ static int choose_window(const zkp_ctx* ctx, size_t n) {
 // ---------------------------------------------------------------------------------------------------------
 // the variable-time MSM, device-resident and asynchronous
 // ---------------------------------------------------------------------------------------------------------
-static int32_t msm_vartime_launch(zkp_ctx* ctx, const void* d_scalars, const void* d_points, size_t n,
-                                  msm_result* d_result) {
+struct msm_plan {
+  int c, W;
+  uint32_t B, total_buckets;
+};
+
+// phase A: choose the window, size the workspace, reset flags and histogram (on the compute stream)
+static int32_t msm_prepare(zkp_ctx* ctx, size_t n, msm_plan* pl) {
   cudaStream_t st = ctx->stream;
-  if (n == 0) {
-    k_empty_result<<<1, 1, 0, st>>>(d_result);
-    LAUNCH_CHECK(ctx);
-    return ZKP_OK;
-  }
   if (n >= 0x7fffffffull) {
     ctx->err = "n too large (>= 2^31 terms per call)";
     return ZKP_ERR_SIZE;
@@ -223,7 +235,7 @@ static int32_t msm_vartime_launch(zkp_ctx* ctx, const void* d_scalars, const voi
   const int W = (253 + c - 1) / c;
   const uint32_t B = 1u << (c - 1);
   const uint32_t total_buckets = (uint32_t)W * B;
-
+  pl->c = c; pl->W = W; pl->B = B; pl->total_buckets = total_buckets;
   ENSURE(ctx, ctx->niels, n * 96);
   ENSURE(ctx, ctx->hist, (size_t)W * B * 4);
   ENSURE(ctx, ctx->offs, (size_t)W * (B + 1) * 4);
@@ -238,27 +250,64 @@ static int32_t msm_vartime_launch(zkp_ctx* ctx, const void* d_scalars, const voi
     ENSURE(ctx, ctx->lvlU, (size_t)W * chunks0 * 128);
   }
   ENSURE(ctx, ctx->usum, (size_t)8 * W * 128);
-
-#define STAGE(i) do { if (ctx->profile) cudaEventRecord(ctx->ev[i], st); } while (0)
   ctx->last_window = c;
-  int* flags = (int*)ctx->flags.p;
-  STAGE(0);
-  k_init_flags<<<1, 1, 0, st>>>(flags);
+  k_init_flags<<<1, 1, 0, st>>>((int*)ctx->flags.p);
   LAUNCH_CHECK(ctx);
   CUDA_TRY(ctx, cudaMemsetAsync(ctx->hist.p, 0, (size_t)W * B * 4, st));
+  return ZKP_OK;
+}
 
+#define STAGE(i) do { if (ctx->profile) cudaEventRecord(ctx->ev[i], st); } while (0)
+
+// phase B: ingest terms [base, base+cnt): decompress the points, histogram the scalars' digits
+static int32_t msm_ingest(zkp_ctx* ctx, const msm_plan& pl, const void* d_scalars, const void* d_points, size_t base,
+                          size_t cnt, bool whole) {
+  cudaStream_t st = ctx->stream;
+  int* flags = (int*)ctx->flags.p;
+  const unsigned nb = (unsigned)((cnt + 255) / 256);
+  if (whole) STAGE(0);
+  k_decompress<<<nb, 256, 0, st>>>((const uint4*)d_points + 2 * base, cnt, (uint4*)ctx->niels.p + 6 * base, flags, base);
+  LAUNCH_CHECK(ctx);
+  if (whole) STAGE(1);
+  k_recode<false><<<nb, 256, 0, st>>>((const uint4*)d_scalars + 2 * base, cnt, pl.c, pl.W, pl.B,
+                                      (uint32_t*)ctx->hist.p, nullptr, flags, base);
+  LAUNCH_CHECK(ctx);
+  if (whole) STAGE(2);
+  return ZKP_OK;
+}
+
+static int32_t msm_finish(zkp_ctx* ctx, const msm_plan& pl, const void* d_scalars, size_t n, msm_result* d_result,
+                          bool whole);
+
+static int32_t msm_vartime_launch(zkp_ctx* ctx, const void* d_scalars, const void* d_points, size_t n,
+                                  msm_result* d_result) {
+  cudaStream_t st = ctx->stream;
+  if (n == 0) {
+    k_empty_result<<<1, 1, 0, st>>>(d_result);
+    LAUNCH_CHECK(ctx);
+    return ZKP_OK;
+  }
+  msm_plan pl;
+  int32_t r = msm_prepare(ctx, n, &pl);
+  if (r != ZKP_OK) return r;
+  r = msm_ingest(ctx, pl, d_scalars, d_points, 0, n, true);
+  if (r != ZKP_OK) return r;
+  return msm_finish(ctx, pl, d_scalars, n, d_result, true);
+}
+
+// phase C: counting sort by bucket, bucket accumulation, bucket reduction, Horner, encode
+static int32_t msm_finish(zkp_ctx* ctx, const msm_plan& pl, const void* d_scalars, size_t n, msm_result* d_result,
+                          bool whole) {
+  cudaStream_t st = ctx->stream;
+  const int c = pl.c, W = pl.W;
+  const uint32_t B = pl.B, total_buckets = pl.total_buckets;
+  int* flags = (int*)ctx->flags.p;
   const unsigned nb = (unsigned)((n + 255) / 256);
-  k_decompress<<<nb, 256, 0, st>>>((const uint4*)d_points, n, (uint4*)ctx->niels.p, flags);
-  LAUNCH_CHECK(ctx);
-  STAGE(1);
-  k_recode<false><<<nb, 256, 0, st>>>((const uint4*)d_scalars, n, c, W, B, (uint32_t*)ctx->hist.p, nullptr, flags);
-  LAUNCH_CHECK(ctx);
-  STAGE(2);
   k_scan<<<W, 1024, 0, st>>>((const uint32_t*)ctx->hist.p, B, (uint32_t*)ctx->offs.p, (uint32_t*)ctx->cursor.p);
   LAUNCH_CHECK(ctx);
-  STAGE(3);
+  if (whole) STAGE(3);
   k_recode<true><<<nb, 256, 0, st>>>((const uint4*)d_scalars, n, c, W, B, (uint32_t*)ctx->cursor.p,
-                                     (uint32_t*)ctx->sorted.p, flags);
+                                     (uint32_t*)ctx->sorted.p, flags, 0);
   LAUNCH_CHECK(ctx);
 
   STAGE(4);
@@ -324,12 +373,71 @@ static int32_t msm_vartime_launch(zkp_ctx* ctx, const void* d_scalars, const voi
   k_finish<<<1, 64, 0, st>>>((const uint4*)ctx->usum.p, nl, cur, m, W, c, n, flags, d_result, nullptr);
   LAUNCH_CHECK(ctx);
   STAGE(7);
-  if (ctx->profile) {
+  if (ctx->profile && whole) {
     CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev[7]));
     for (int i = 0; i < 7; i++) cudaEventElapsedTime(&ctx->stage_ms[i], ctx->ev[i], ctx->ev[i + 1]);
   }
 #undef STAGE
   return ZKP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host inputs: chunked H2D copies on a second stream overlap decompression / digit histograms of earlier chunks
+// ---------------------------------------------------------------------------------------------------------
+struct hseg {
+  const uint8_t* p;
+  size_t cnt;
+};
+
+static int32_t copy_range(zkp_ctx* ctx, const hseg* segs, int nseg, size_t lo, size_t hi, uint8_t* dst) {
+  size_t off = 0;
+  for (int k = 0; k < nseg; k++) {
+    size_t s0 = off, s1 = off + segs[k].cnt;
+    size_t a = lo > s0 ? lo : s0, b = hi < s1 ? hi : s1;
+    if (a < b)
+      CUDA_TRY(ctx, cudaMemcpyAsync(dst + a * 32, segs[k].p + (a - s0) * 32, (b - a) * 32, cudaMemcpyHostToDevice,
+                                    ctx->copy_stream));
+    off = s1;
+  }
+  return ZKP_OK;
+}
+
+static int32_t msm_from_host(zkp_ctx* ctx, const hseg* sc_segs, const hseg* pt_segs, int nseg, size_t n,
+                             msm_result* d_result) {
+  cudaStream_t st = ctx->stream;
+  if (n == 0) {
+    k_empty_result<<<1, 1, 0, st>>>(d_result);
+    LAUNCH_CHECK(ctx);
+    return ZKP_OK;
+  }
+  ENSURE(ctx, ctx->in_scalars, n * 32);
+  ENSURE(ctx, ctx->in_points, n * 32);
+  if (!ctx->copy_stream) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  msm_plan pl;
+  int32_t r = msm_prepare(ctx, n, &pl);
+  if (r != ZKP_OK) return r;
+  const size_t chunk = ctx->chunk_terms;
+  const size_t nchunks = (n + chunk - 1) / chunk;
+  while (ctx->chunk_ev.size() < nchunks + 1) {
+    cudaEvent_t e;
+    CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->chunk_ev.push_back(e);
+  }
+  // the copy stream must not overwrite the staging buffers before earlier work on `st` (a previous call) is done
+  CUDA_TRY(ctx, cudaEventRecord(ctx->chunk_ev[nchunks], st));
+  CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[nchunks], 0));
+  for (size_t k = 0; k < nchunks; k++) {
+    const size_t lo = k * chunk, hi = lo + chunk < n ? lo + chunk : n;
+    r = copy_range(ctx, pt_segs, nseg, lo, hi, (uint8_t*)ctx->in_points.p);
+    if (r != ZKP_OK) return r;
+    r = copy_range(ctx, sc_segs, nseg, lo, hi, (uint8_t*)ctx->in_scalars.p);
+    if (r != ZKP_OK) return r;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->chunk_ev[k], ctx->copy_stream));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->chunk_ev[k], 0));
+    r = msm_ingest(ctx, pl, ctx->in_scalars.p, ctx->in_points.p, lo, hi - lo, false);
+    if (r != ZKP_OK) return r;
+  }
+  return msm_finish(ctx, pl, ctx->in_scalars.p, n, d_result, false);
 }
 
 extern "C" int32_t zkp_msm_vartime_dev(zkp_ctx* ctx, const void* d_scalars, const void* d_points, size_t n,
@@ -362,13 +470,8 @@ extern "C" int32_t zkp_msm_vartime(zkp_ctx* ctx, const uint8_t* scalars, const u
   if (!ctx || (n && (!scalars || !points))) return ZKP_ERR_SIZE;
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   ENSURE(ctx, ctx->result, 64);
-  if (n) {
-    ENSURE(ctx, ctx->in_scalars, n * 32);
-    ENSURE(ctx, ctx->in_points, n * 32);
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->in_points.p, points, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->in_scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-  }
-  int32_t r = msm_vartime_launch(ctx, ctx->in_scalars.p, ctx->in_points.p, n, (msm_result*)ctx->result.p);
+  hseg ss = {scalars, n}, ps = {points, n};
+  int32_t r = msm_from_host(ctx, &ss, &ps, 1, n, (msm_result*)ctx->result.p);
   if (r != ZKP_OK) return r;
   return fetch_result(ctx, out32, is_identity, first_bad);
 }
@@ -384,22 +487,10 @@ extern "C" int32_t zkp_batch_verify(zkp_ctx* ctx, const uint8_t* static_coeffs, 
   const size_t n_inst = rows * batch, n = num_s + n_inst;
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   ENSURE(ctx, ctx->result, 64);
-  if (n) {
-    ENSURE(ctx, ctx->in_scalars, n * 32);
-    ENSURE(ctx, ctx->in_points, n * 32);
-    // scalar order: static ++ row-major instance matrix; point order: static ++ rows   (batch_verifier.rs:219-226)
-    uint8_t* ds = (uint8_t*)ctx->in_scalars.p;
-    uint8_t* dp = (uint8_t*)ctx->in_points.p;
-    if (n_inst) {
-      CUDA_TRY(ctx, cudaMemcpyAsync(dp + num_s * 32, instance_points, n_inst * 32, cudaMemcpyHostToDevice, ctx->stream));
-      CUDA_TRY(ctx, cudaMemcpyAsync(ds + num_s * 32, instance_coeffs, n_inst * 32, cudaMemcpyHostToDevice, ctx->stream));
-    }
-    if (num_s) {
-      CUDA_TRY(ctx, cudaMemcpyAsync(dp, static_points, num_s * 32, cudaMemcpyHostToDevice, ctx->stream));
-      CUDA_TRY(ctx, cudaMemcpyAsync(ds, static_coeffs, num_s * 32, cudaMemcpyHostToDevice, ctx->stream));
-    }
-  }
-  int32_t r = msm_vartime_launch(ctx, ctx->in_scalars.p, ctx->in_points.p, n, (msm_result*)ctx->result.p);
+  // scalar order: static ++ row-major instance matrix; point order: static ++ rows   (batch_verifier.rs:219-226)
+  hseg ss[2] = {{static_coeffs, num_s}, {instance_coeffs, n_inst}};
+  hseg ps[2] = {{static_points, num_s}, {instance_points, n_inst}};
+  int32_t r = msm_from_host(ctx, ss, ps, 2, n, (msm_result*)ctx->result.p);
   if (r != ZKP_OK) return r;
   int32_t ident = 0;
   r = fetch_result(ctx, nullptr, &ident, first_bad);

@@ -65,8 +65,9 @@ __device__ __forceinline__ void load_ext(ge_ext& q, const uint4* p) {
 // ---------------------------------------------------------------------------------------------------------
 // K1: decompression.  One thread per point; ~254 squarings + ~25 multiplications, all in registers.
 // ---------------------------------------------------------------------------------------------------------
+// `base` = global index of element 0 (chunked ingestion reports global indices of bad points)
 __global__ void __launch_bounds__(256) k_decompress(const uint4* __restrict__ enc, size_t n, uint4* __restrict__ niels,
-                                                    int* __restrict__ flags) {
+                                                    int* __restrict__ flags, size_t base) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint32_t w[8];
@@ -78,7 +79,7 @@ __global__ void __launch_bounds__(256) k_decompress(const uint4* __restrict__ en
     ge_aniels_from_affine(q, x, y, t);
   } else {
     ge_aniels_identity(q);
-    atomicMin(&flags[0], (int)i);
+    atomicMin(&flags[0], (int)(base + i));
   }
   uint4* o = niels + 6 * i;
   store_fe(o, q.yplusx);
@@ -133,7 +134,7 @@ template <bool SCATTER>
 __global__ void __launch_bounds__(256) k_recode(const uint4* __restrict__ scalars, size_t n, int c, int W, uint32_t B,
                                                 uint32_t* __restrict__ counters,  // hist[W][B] or cursor[W][B]
                                                 uint32_t* __restrict__ sorted,    // [W][n] (SCATTER only)
-                                                int* __restrict__ flags) {
+                                                int* __restrict__ flags, size_t base) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint32_t s[8], k[8];
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(256) k_recode(const uint4* __restrict__ scalar
   uint32_t neg;
   uint32_t canonical = sc_fold_sign(k, neg, s);
   if (!canonical) {
-    if (!SCATTER) atomicMin(&flags[1], (int)i);
+    if (!SCATTER) atomicMin(&flags[1], (int)(base + i));
     return;  // contributes nothing; the call fails with ZKP_ERR_SCALAR
   }
   uint32_t carry = 0;
