@@ -122,7 +122,8 @@ int32_t zkp_batch_verify(zkp_ctx* ctx, const uint8_t* static_coeffs, const uint8
 /* Device-side micro-benchmark of the field multiplier variants (roofline calibration):
  * runs `iters` dependent multiplies (or squarings) per thread over a full grid and returns the measured
  * rate in operations per second in *ops_per_sec.  kind: 0 = fe_mul (8x32 saturated), 1 = fe_sq,
- * 2 = 5x51-limb multiply (u64 products), 3 = 10x25.5-limb multiply.                                        */
+ * 2 = 5x51-limb multiply (u64 products), 3 = 10x25.5-limb multiply, 4 / 5 = 32 wide multiplies per
+ * iteration without / with carry chains (raw IMAD.WIDE issue rate; ops counted per iteration).             */
 int32_t zkp_bench_field(zkp_ctx* ctx, int32_t kind, int32_t iters, double* ops_per_sec);
 
 #ifdef __cplusplus

@@ -670,7 +670,7 @@ extern "C" int32_t zkp_msm_ct_batched(zkp_ctx* ctx, const uint8_t* scalars, cons
 // field-multiplier micro-benchmark
 // ---------------------------------------------------------------------------------------------------------
 extern "C" int32_t zkp_bench_field(zkp_ctx* ctx, int32_t kind, int32_t iters, double* ops_per_sec) {
-  if (!ctx || !ops_per_sec || iters <= 0 || kind < 0 || kind > 3) return ZKP_ERR_SIZE;
+  if (!ctx || !ops_per_sec || iters <= 0 || kind < 0 || kind > 5) return ZKP_ERR_SIZE;
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   int sms = 0;
   CUDA_TRY(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
@@ -686,7 +686,9 @@ extern "C" int32_t zkp_bench_field(zkp_ctx* ctx, int32_t kind, int32_t iters, do
       case 0: k_bench_mul32<<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, iters); break;
       case 1: k_bench_sq32<<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, iters); break;
       case 2: k_bench_mul51<<<blocks, threads, 0, ctx->stream>>>((unsigned long long*)ctx->aux0.p, iters); break;
-      default: k_bench_mul25<<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, iters); break;
+      case 3: k_bench_mul25<<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, iters); break;
+      case 4: k_bench_wide_plain<<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, iters); break;
+      default: k_bench_wide_carry<<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, iters); break;
     }
     LAUNCH_CHECK(ctx);
     CUDA_TRY(ctx, cudaEventRecord(e1, ctx->stream));

@@ -140,4 +140,53 @@ __global__ void __launch_bounds__(256) k_bench_mul25(uint32_t* out, int iters) {
   for (int i = 0; i < 10; i++) out[(size_t)gid * 16 + i] = a.v[i] ^ b.v[i];
 }
 
+
+// ---- raw wide-multiply issue rate with realistic operand variety: 32 IMAD.WIDE per iteration --------------
+// kind 4: plain mad.wide.u32 into eight independent 64-bit accumulators (no carries)
+__global__ void __launch_bounds__(256) k_bench_wide_plain(uint32_t* out, int iters) {
+  uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t a[8], b[4];
+  unsigned long long acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) { a[i] = gid * 2654435761u + i * 40503u + 1; acc[i] = gid + i; }
+#pragma unroll
+  for (int i = 0; i < 4; i++) b[i] = gid * 2246822519u + i * 3266489917u + 7;
+#pragma unroll 1
+  for (int k = 0; k < iters; k++) {
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+      for (int i = 0; i < 8; i++) acc[i] += (unsigned long long)a[(i + j) & 7] * b[j];
+    b[0] ^= (uint32_t)acc[0];
+  }
+  uint32_t x = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) x ^= (uint32_t)acc[i] ^ (uint32_t)(acc[i] >> 32);
+  out[gid] = x;
+}
+// kind 5: the same 32 products as eight carry chains of four (mad4), the shape fe_mul uses
+__global__ void __launch_bounds__(256) k_bench_wide_carry(uint32_t* out, int iters) {
+  uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t a[8], b[8], e[8], o[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    a[i] = gid * 2654435761u + i * 40503u + 1;
+    b[i] = gid * 2246822519u + i * 3266489917u + 7;
+    e[i] = gid + i; o[i] = gid ^ i;
+  }
+#pragma unroll 1
+  for (int k = 0; k < iters; k++) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      e[0] += mad4(e, a[0], a[2], a[4], a[6], b[2 * j]);
+      o[0] += mad4(o, a[1], a[3], a[5], a[7], b[2 * j + 1]);
+    }
+    b[0] ^= e[7];
+  }
+  uint32_t x = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) x ^= e[i] ^ o[i];
+  out[gid] = x;
+}
+
 }  // namespace zkp

@@ -122,16 +122,20 @@ extern "C" int32_t zkph_batch_verify(zkp_ctx* ctx, const zkph_statement* h, cons
   const size_t m = st.secrets.size(), k = st.constraints.size(), ni = st.instance.size(), nc = st.common.size();
   auto t0 = std::chrono::steady_clock::now();
   std::vector<BatchableProof> proofs(N);
-  for (size_t j = 0; j < N; j++) {
-    proofs[j].commitments = load_encs(commitments + j * k * 32, k);
-    proofs[j].responses.resize(m);
-    for (size_t i = 0; i < m; i++)
-      if (!Scalar::from_canonical_bytes(&proofs[j].responses[i], responses + (j * m + i) * 32)) return VerificationFailure;
-  }
+  std::vector<uint8_t> noncanon(1, 0);
+  parallel_for(N, threads, [&](size_t lo, size_t hi, int) {
+    for (size_t j = lo; j < hi; j++) {
+      proofs[j].commitments = load_encs(commitments + j * k * 32, k);
+      proofs[j].responses.resize(m);
+      for (size_t i = 0; i < m; i++)
+        if (!Scalar::from_canonical_bytes(&proofs[j].responses[i], responses + (j * m + i) * 32)) noncanon[0] = 1;
+    }
+  });
+  if (noncanon[0]) return VerificationFailure;
   std::vector<Transcript> transcripts(N, Transcript(tl, tl_len));
   Rng rng(seed, seed_len);
   ProofError err;
-  BatchVerifier bv(ctx, st.label, N, &transcripts, &err);
+  BatchVerifier bv(ctx, st.label, N, &transcripts, &err, threads, /*identical_transcripts=*/true);
   if (err != PROOF_OK) return err;
   for (auto& s : st.secrets) bv.allocate_scalar(s);
   std::vector<BatchPointVar> pv;
@@ -178,17 +182,21 @@ extern "C" int32_t zkph_prove_many(zkp_ctx* ctx, const zkph_statement* h, const 
   const Statement& st = h->st;
   const size_t m = st.secrets.size(), p = st.num_points(), k = st.constraints.size();
   std::vector<Scalar> sec(N * m);
-  for (size_t i = 0; i < N * m; i++) sec[i] = load_scalar(secrets + 32 * i);
+  parallel_for(N * m, threads, [&](size_t lo, size_t hi, int) {
+    for (size_t i = lo; i < hi; i++) sec[i] = load_scalar(secrets + 32 * i);
+  });
   std::vector<BatchableProof> proofs;
   std::vector<Enc> encs;
   ProofError e = stmt_prove_many(ctx, st, std::string((const char*)tl, tl_len), N, sec.data(), (const Limbs*)points,
                                  entropy, threads, &proofs, &encs);
   if (e != PROOF_OK) return e;
   memcpy(encodings, encs.data(), N * p * 32);
-  for (size_t j = 0; j < N; j++) {
-    for (size_t i = 0; i < k; i++) memcpy(commitments + (j * k + i) * 32, proofs[j].commitments[i].data(), 32);
-    for (size_t i = 0; i < m; i++) proofs[j].responses[i].to_bytes(responses + (j * m + i) * 32);
-  }
+  parallel_for(N, threads, [&](size_t lo, size_t hi, int) {
+    for (size_t j = lo; j < hi; j++) {
+      for (size_t i = 0; i < k; i++) memcpy(commitments + (j * k + i) * 32, proofs[j].commitments[i].data(), 32);
+      for (size_t i = 0; i < m; i++) proofs[j].responses[i].to_bytes(responses + (j * m + i) * 32);
+    }
+  });
   return PROOF_OK;
 }
 

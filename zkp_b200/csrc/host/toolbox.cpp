@@ -8,7 +8,7 @@ namespace zkp_host {
 // ---- helpers ---------------------------------------------------------------------------------------------
 static inline const uint8_t* U8(const std::string& s) { return (const uint8_t*)s.data(); }
 
-static void parallel_for(size_t n, int threads, const std::function<void(size_t, size_t, int)>& fn) {
+void parallel_for(size_t n, int threads, const std::function<void(size_t, size_t, int)>& fn) {
   if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
   if (threads < 1) threads = 1;
   if ((size_t)threads > n) threads = n ? (int)n : 1;
@@ -269,26 +269,54 @@ ProofError Verifier::verify_batchable(const BatchableProof& proof, Rng& rng) {
 
 // ---- BatchVerifier -----------------------------------------------------------------------------------------
 BatchVerifier::BatchVerifier(zkp_ctx* ctx, const std::string& proof_label, size_t batch_size,
-                             std::vector<Transcript>* transcripts, ProofError* err)
-    : ctx_(ctx), batch_size_(batch_size), transcripts_(transcripts), num_scalars_(0) {
+                             std::vector<Transcript>* transcripts, ProofError* err, int threads,
+                             bool identical_transcripts)
+    : ctx_(ctx), batch_size_(batch_size), transcripts_(transcripts), num_scalars_(0), threads_(threads),
+      uniform_(identical_transcripts) {
   if (transcripts->size() != batch_size) {
     *err = BatchSizeMismatch;
     return;
   }
-  for (auto& t : *transcripts_) domain_sep(t, proof_label);
+  if (uniform_ && batch_size_) {
+    domain_sep((*transcripts_)[0], proof_label);
+    broadcast_first();
+  } else {
+    parallel_for(batch_size_, threads_, [&](size_t lo, size_t hi, int) {
+      for (size_t j = lo; j < hi; j++) domain_sep((*transcripts_)[j], proof_label);
+    });
+  }
   *err = PROOF_OK;
 }
+void BatchVerifier::broadcast_first() {
+  parallel_for(batch_size_, threads_, [&](size_t lo, size_t hi, int) {
+    for (size_t j = lo ? lo : 1; j < hi; j++) (*transcripts_)[j] = (*transcripts_)[0];
+  });
+}
 int BatchVerifier::allocate_scalar(const std::string& label) {
-  for (auto& t : *transcripts_) append_scalar_var(t, label);
+  if (uniform_ && batch_size_) {
+    append_scalar_var((*transcripts_)[0], label);
+    broadcast_first();
+  } else {
+    parallel_for(batch_size_, threads_, [&](size_t lo, size_t hi, int) {
+      for (size_t j = lo; j < hi; j++) append_scalar_var((*transcripts_)[j], label);
+    });
+  }
   return num_scalars_++;
 }
 BatchPointVar BatchVerifier::allocate_static_point(const std::string& label, const Enc& assignment, ProofError* err) {
   BatchPointVar v = {true, -1};
-  for (auto& t : *transcripts_)
-    if (!validate_and_append_point_var(t, label, assignment)) {
-      *err = VerificationFailure;
-      return v;
-    }
+  if (is_identity_encoding(assignment) && batch_size_) {   // toolbox/mod.rs:191, first transcript already fails
+    *err = VerificationFailure;
+    return v;
+  }
+  if (uniform_ && batch_size_) {
+    append_point_var((*transcripts_)[0], label, assignment);
+    broadcast_first();
+  } else {
+    parallel_for(batch_size_, threads_, [&](size_t lo, size_t hi, int) {
+      for (size_t j = lo; j < hi; j++) append_point_var((*transcripts_)[j], label, assignment);
+    });
+  }
   static_points_.push_back(assignment);
   static_point_labels_.push_back(label);
   v.idx = (int)static_points_.size() - 1;
@@ -302,11 +330,16 @@ BatchPointVar BatchVerifier::allocate_instance_point(const std::string& label, c
     *err = BatchSizeMismatch;
     return v;
   }
-  for (size_t j = 0; j < batch_size_; j++)
-    if (!validate_and_append_point_var((*transcripts_)[j], label, assignments[j])) {
-      *err = VerificationFailure;
-      return v;
-    }
+  uniform_ = false;   // per-proof data from here on
+  std::vector<uint8_t> bad(1, 0);
+  parallel_for(batch_size_, threads_, [&](size_t lo, size_t hi, int) {
+    for (size_t j = lo; j < hi; j++)
+      if (!validate_and_append_point_var((*transcripts_)[j], label, assignments[j])) bad[0] = 1;
+  });
+  if (bad[0]) {
+    *err = VerificationFailure;
+    return v;
+  }
   instance_points_.push_back(assignments);
   instance_point_labels_.push_back(label);
   v.idx = (int)instance_points_.size() - 1;
@@ -445,7 +478,7 @@ ProofError stmt_batch_verify(zkp_ctx* ctx, const Statement& st, std::vector<Tran
                              const std::vector<std::vector<Enc>>& instance, const std::vector<Enc>& common,
                              const std::vector<BatchableProof>& proofs, Rng& rng, int threads) {
   ProofError err;
-  BatchVerifier bv(ctx, st.label, proofs.size(), transcripts, &err);
+  BatchVerifier bv(ctx, st.label, proofs.size(), transcripts, &err, threads);
   if (err != PROOF_OK) return err;
   if (instance.size() != st.instance.size() || common.size() != st.common.size()) return BatchSizeMismatch;
   for (auto& s : st.secrets) bv.allocate_scalar(s);

@@ -12,6 +12,7 @@
 // Rust shim).  Randomness the reference takes from thread_rng is injected (Rng) so runs are reproducible.
 #pragma once
 #include <array>
+#include <functional>
 #include <string>
 #include <utility>
 #include <vector>
@@ -52,6 +53,9 @@ bool validate_and_append_blinding_commitment(Transcript& t, const std::string& l
 Scalar get_challenge(Transcript& t, const std::string& label);
 
 typedef std::vector<std::pair<int, int>> LinComb;  // (scalar var, point var)
+
+// run fn(lo, hi, thread_index) over [0, n) on `threads` host threads (0 = all cores)
+void parallel_for(size_t n, int threads, const std::function<void(size_t, size_t, int)>& fn);
 
 class Prover {
  public:
@@ -99,8 +103,9 @@ typedef std::vector<std::pair<int, BatchPointVar>> BatchLinComb;
 class BatchVerifier {
  public:
   // transcripts.size() must equal batch_size, else *err = BatchSizeMismatch (batch_verifier.rs:72-74)
+  // `threads` host threads work on the per-proof transcripts (0 = all cores); the reference is single-threaded
   BatchVerifier(zkp_ctx* ctx, const std::string& proof_label, size_t batch_size, std::vector<Transcript>* transcripts,
-                ProofError* err);
+                ProofError* err, int threads = 1, bool identical_transcripts = false);
   int allocate_scalar(const std::string& label);
   BatchPointVar allocate_static_point(const std::string& label, const Enc& assignment, ProofError* err);
   BatchPointVar allocate_instance_point(const std::string& label, const std::vector<Enc>& assignments, ProofError* err);
@@ -119,6 +124,11 @@ class BatchVerifier {
   size_t batch_size_;
   std::vector<Transcript>* transcripts_;
   int num_scalars_;
+  int threads_;
+  // true while every transcript is known to hold the same state (caller passed identical copies and only
+  // batch-wide data has been absorbed): such appends are hashed once and the state is copied
+  bool uniform_;
+  void broadcast_first();
   std::vector<Enc> static_points_;
   std::vector<std::string> static_point_labels_;
   std::vector<std::vector<Enc>> instance_points_;
