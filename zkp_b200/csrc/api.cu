@@ -538,10 +538,22 @@ extern "C" int32_t zkp_compress_batch(zkp_ctx* ctx, const uint64_t* limbs_in, si
 // ---------------------------------------------------------------------------------------------------------
 // batched small MSMs (CSR)
 // ---------------------------------------------------------------------------------------------------------
+// MSM indices sorted by descending term count (counting sort): warps then hold MSMs of equal size
+static void size_order(const uint64_t* offsets, size_t M, std::vector<uint32_t>* order) {
+  const size_t CAP = 4096;
+  std::vector<size_t> cnt(CAP + 2, 0);
+  auto key = [&](size_t j) { size_t s = (size_t)(offsets[j + 1] - offsets[j]); return s > CAP ? CAP : s; };
+  for (size_t j = 0; j < M; j++) cnt[CAP - key(j)]++;
+  size_t acc = 0;
+  for (size_t b = 0; b <= CAP; b++) { size_t c = cnt[b]; cnt[b] = acc; acc += c; }
+  order->resize(M);
+  for (size_t j = 0; j < M; j++) (*order)[cnt[CAP - key(j)]++] = (uint32_t)j;
+}
+
 static int32_t check_offsets(zkp_ctx* ctx, const uint64_t* offsets, size_t M, size_t* total) {
   if (!offsets) return ZKP_ERR_SIZE;
-  if (offsets[0] != 0) {
-    ctx->err = "offsets[0] must be 0";
+  if (offsets[0] != 0 || M >= 0xffffffffull) {
+    ctx->err = "offsets[0] must be 0 and M < 2^32";
     return ZKP_ERR_SIZE;
   }
   for (size_t j = 0; j < M; j++)
@@ -584,9 +596,14 @@ extern "C" int32_t zkp_msm_vartime_batched(zkp_ctx* ctx, const uint8_t* scalars,
                                           (uint4*)ctx->sk1.p);
     LAUNCH_CHECK(ctx);
   }
+  std::vector<uint32_t> order;
+  size_order(offsets, M, &order);
+  ENSURE(ctx, ctx->multi, M * 4 + 16);
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->multi.p, order.data(), M * 4, cudaMemcpyHostToDevice, st));
   k_small_msm_vt<<<(unsigned)((M + 63) / 64), 64, 0, st>>>(
       (const uint32_t*)ctx->sk0.p, (const uint32_t*)ctx->sk1.p, (const uint4*)ctx->niels.p,
-      (const unsigned long long*)ctx->aux0.p, M, (uint4*)ctx->aux1.p, (int*)ctx->aux2.p);
+      (const unsigned long long*)ctx->aux0.p, (const uint32_t*)ctx->multi.p, M, (uint4*)ctx->aux1.p,
+      (int*)ctx->aux2.p);
   LAUNCH_CHECK(ctx);
   // status words -> valid bytes on the host
   int* hstat = (int*)malloc(M * 4);
@@ -653,9 +670,13 @@ extern "C" int32_t zkp_msm_ct_batched(zkp_ctx* ctx, const uint8_t* scalars, cons
                                                                     (int*)ctx->flags.p);
     LAUNCH_CHECK(ctx);
   }
+  std::vector<uint32_t> order;
+  size_order(offsets, M, &order);
+  ENSURE(ctx, ctx->multi, M * 4 + 16);
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->multi.p, order.data(), M * 4, cudaMemcpyHostToDevice, st));
   k_small_msm_ct<<<(unsigned)((M + 63) / 64), 64, 0, st>>>((const uint32_t*)ctx->sk0.p, (const uint4*)ctx->tables.p,
-                                                           (const unsigned long long*)ctx->aux0.p, M,
-                                                           (uint4*)ctx->aux1.p);
+                                                           (const unsigned long long*)ctx->aux0.p,
+                                                           (const uint32_t*)ctx->multi.p, M, (uint4*)ctx->aux1.p);
   LAUNCH_CHECK(ctx);
   int hflags[4];
   CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->aux1.p, M * 32, cudaMemcpyDeviceToHost, st));

@@ -58,10 +58,12 @@ __global__ void __launch_bounds__(256) k_prep_scalars_vt(const uint4* __restrict
 
 __global__ void __launch_bounds__(64) k_small_msm_vt(const uint32_t* __restrict__ kk, const uint32_t* __restrict__ k3,
                                                      const uint4* __restrict__ niels,
-                                                     const unsigned long long* __restrict__ offsets, size_t M,
+                                                     const unsigned long long* __restrict__ offsets,
+                                                     const uint32_t* __restrict__ order, size_t M,
                                                      uint4* __restrict__ out, int* __restrict__ status) {
-  size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= M) return;
+  size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= M) return;
+  const size_t j = order[tid];   // MSMs sorted by size so that the lanes of a warp do equal work
   const size_t lo = offsets[j], hi = offsets[j + 1];
   int st = 0;
   for (size_t t = lo; t < hi; t++) {
@@ -166,10 +168,12 @@ __global__ void __launch_bounds__(128) k_build_tables(const uint4* __restrict__ 
 }
 
 __global__ void __launch_bounds__(64) k_small_msm_ct(const uint32_t* __restrict__ biased, const uint4* __restrict__ tables,
-                                                     const unsigned long long* __restrict__ offsets, size_t M,
+                                                     const unsigned long long* __restrict__ offsets,
+                                                     const uint32_t* __restrict__ order, size_t M,
                                                      uint4* __restrict__ out) {
-  size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= M) return;
+  size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= M) return;
+  const size_t j = order[tid];   // public: MSMs sorted by (public) size so the lanes of a warp do equal work
   const size_t lo = offsets[j], hi = offsets[j + 1];   // public
   ge_ext acc;
   ge_identity(acc);
