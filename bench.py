@@ -170,6 +170,7 @@ def main():
     ap.add_argument("--cpu-sample-log2", type=int, default=14, help="proofs in the CPU baseline sample")
     ap.add_argument("--window", type=int, default=0, help="tuning: force the Pippenger window width")
     ap.add_argument("--chunk", type=int, default=0, help="tuning: force the accumulate work-item length")
+    ap.add_argument("--no-overlap", action="store_true", help="tuning: run the digit sort on the compute stream")
     ap.add_argument("--sweep", default="", help="tuning: comma list of windows; prints stage times per window and exits")
     args = ap.parse_args()
 
@@ -256,6 +257,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    if args.no_overlap:
+        eng.set_option("overlap", 0)
     if args.window:
         eng.set_option("window", args.window)
     if args.chunk:

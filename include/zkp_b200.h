@@ -56,7 +56,8 @@ void zkp_ctx_destroy(zkp_ctx* ctx);
 int32_t zkp_ctx_set_stream(zkp_ctx* ctx, void* cuda_stream);
 /* Tunables: "window" (Pippenger window width c, 0 = choose from n), "window_cap" (upper bound of the automatic
  * choice), "chunk" (max sorted entries per accumulate work item, 0 = auto), "profile" (0/1, see
- * zkp_ctx_stage_ms). */
+ * zkp_ctx_stage_ms; forces the stages to run back to back), "overlap" (0/1, default 1: the digit sort runs on a
+ * second stream concurrently with decompression), "chunk_terms" (H2D pipeline granularity of the host entry points). */
 int32_t zkp_ctx_set_option(zkp_ctx* ctx, const char* key, int64_t value);
 int32_t zkp_ctx_synchronize(zkp_ctx* ctx);
 const char* zkp_last_error(zkp_ctx* ctx);

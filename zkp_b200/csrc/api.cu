@@ -42,6 +42,11 @@ struct zkp_ctx {
   cudaStream_t copy_stream = nullptr;
   std::vector<cudaEvent_t> chunk_ev;
   size_t chunk_terms = (size_t)1 << 21;
+  // the digit sort (histogram, scan, scatter: L2-atomic bound) runs on a second, higher-priority stream
+  // concurrently with decompression (integer-multiply bound); joined before bucket accumulation
+  int overlap = 1;
+  cudaStream_t sort_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 #define CUDA_TRY(ctx, call)                                                            \
@@ -142,6 +147,9 @@ extern "C" void zkp_ctx_destroy(zkp_ctx* ctx) {
   for (int i = 0; i < 10; i++)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->sort_stream) cudaStreamDestroy(ctx->sort_stream);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -160,6 +168,8 @@ extern "C" int32_t zkp_ctx_set_option(zkp_ctx* ctx, const char* key, int64_t val
   } else if (!strcmp(key, "window_cap")) {
     if (value < 4 || value > 24) return ZKP_ERR_SIZE;
     ctx->window_cap = (int)value;
+  } else if (!strcmp(key, "overlap")) {
+    ctx->overlap = value ? 1 : 0;
   } else if (!strcmp(key, "chunk_terms")) {
     if (value < 1024) return ZKP_ERR_SIZE;
     ctx->chunk_terms = (size_t)value;
@@ -222,6 +232,7 @@ static int choose_window(const zkp_ctx* ctx, size_t n) {
 struct msm_plan {
   int c, W;
   uint32_t B, total_buckets;
+  cudaStream_t sort;   // stream of the digit sort: ctx->sort_stream when overlapping, else ctx->stream
 };
 
 // phase A: choose the window, size the workspace, reset flags and histogram (on the compute stream)
@@ -254,6 +265,19 @@ static int32_t msm_prepare(zkp_ctx* ctx, size_t n, msm_plan* pl) {
   k_init_flags<<<1, 1, 0, st>>>((int*)ctx->flags.p);
   LAUNCH_CHECK(ctx);
   CUDA_TRY(ctx, cudaMemsetAsync(ctx->hist.p, 0, (size_t)W * B * 4, st));
+  pl->sort = st;
+  if (ctx->overlap && !ctx->profile) {
+    if (!ctx->sort_stream) {
+      int lo = 0, hi = 0;
+      CUDA_TRY(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      CUDA_TRY(ctx, cudaStreamCreateWithPriority(&ctx->sort_stream, cudaStreamNonBlocking, hi));
+      CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+      CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    }
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, st));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->sort_stream, ctx->ev_fork, 0));
+    pl->sort = ctx->sort_stream;
+  }
   return ZKP_OK;
 }
 
@@ -269,8 +293,8 @@ static int32_t msm_ingest(zkp_ctx* ctx, const msm_plan& pl, const void* d_scalar
   k_decompress<<<nb, 256, 0, st>>>((const uint4*)d_points + 2 * base, cnt, (uint4*)ctx->niels.p + 6 * base, flags, base);
   LAUNCH_CHECK(ctx);
   if (whole) STAGE(1);
-  k_recode<false><<<nb, 256, 0, st>>>((const uint4*)d_scalars + 2 * base, cnt, pl.c, pl.W, pl.B,
-                                      (uint32_t*)ctx->hist.p, nullptr, flags, base);
+  k_recode<false><<<nb, 256, 0, pl.sort>>>((const uint4*)d_scalars + 2 * base, cnt, pl.c, pl.W, pl.B,
+                                           (uint32_t*)ctx->hist.p, nullptr, flags, base);
   LAUNCH_CHECK(ctx);
   if (whole) STAGE(2);
   return ZKP_OK;
@@ -303,12 +327,16 @@ static int32_t msm_finish(zkp_ctx* ctx, const msm_plan& pl, const void* d_scalar
   const uint32_t B = pl.B, total_buckets = pl.total_buckets;
   int* flags = (int*)ctx->flags.p;
   const unsigned nb = (unsigned)((n + 255) / 256);
-  k_scan<<<W, 1024, 0, st>>>((const uint32_t*)ctx->hist.p, B, (uint32_t*)ctx->offs.p, (uint32_t*)ctx->cursor.p);
+  k_scan<<<W, 1024, 0, pl.sort>>>((const uint32_t*)ctx->hist.p, B, (uint32_t*)ctx->offs.p, (uint32_t*)ctx->cursor.p);
   LAUNCH_CHECK(ctx);
   if (whole) STAGE(3);
-  k_recode<true><<<nb, 256, 0, st>>>((const uint4*)d_scalars, n, c, W, B, (uint32_t*)ctx->cursor.p,
-                                     (uint32_t*)ctx->sorted.p, flags, 0);
+  k_recode<true><<<nb, 256, 0, pl.sort>>>((const uint4*)d_scalars, n, c, W, B, (uint32_t*)ctx->cursor.p,
+                                          (uint32_t*)ctx->sorted.p, flags, 0);
   LAUNCH_CHECK(ctx);
+  if (pl.sort != st) {   // join: bucket accumulation needs both the Niels points and the sorted digits
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, pl.sort));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
+  }
 
   STAGE(4);
   {
@@ -434,6 +462,7 @@ static int32_t msm_from_host(zkp_ctx* ctx, const hseg* sc_segs, const hseg* pt_s
     if (r != ZKP_OK) return r;
     CUDA_TRY(ctx, cudaEventRecord(ctx->chunk_ev[k], ctx->copy_stream));
     CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->chunk_ev[k], 0));
+    if (pl.sort != st) CUDA_TRY(ctx, cudaStreamWaitEvent(pl.sort, ctx->chunk_ev[k], 0));
     r = msm_ingest(ctx, pl, ctx->in_scalars.p, ctx->in_points.p, lo, hi - lo, false);
     if (r != ZKP_OK) return r;
   }
