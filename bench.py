@@ -193,8 +193,7 @@ def main():
         sample = 1 << args.cpu_sample_log2
         sc, K, half = make_cmz_batch(sample, seed=1234, n_points=2 * sample)
         sc = finish_cancellation(sc, sample, half)
-        from zkp_b200 import Engine  # points need a generator: valid encodings come from the engine if a GPU
-        pts = _host_points(2 * sample)   # is present, else from the oracle
+        pts = _host_points(2 * sample)   # valid encodings made on the CPU (no GPU on this arm)
         pidx = (np.arange(sample) % half)[None, :] + (np.arange(ROWS) & 1)[:, None] * half
         pt_rows = pts[pidx]
         sc_rows = sc.view(np.uint8).reshape(ROWS, sample, 32)
@@ -405,10 +404,17 @@ def gpu_points(eng, K, seed):
     return out
 
 
-def _host_points(K):
-    """Valid encodings without a GPU (reference arm): oracle hash-to-group, cached."""
-    from tests import util_data as U
-    return np.frombuffer(b"".join(U.base_points(K)), dtype=np.uint8).reshape(K, 32).copy()
+def _host_points(K, distinct=4096):
+    """K valid encodings without a GPU (reference arm): r*B for `distinct` random r via the C port, tiled."""
+    from oracle import cref
+    rng = np.random.default_rng(4242)
+    d = min(K, distinct)
+    r = rng.integers(0, 256, size=(d, 32), dtype=np.uint8)
+    r[:, 31] &= 0x0F
+    B = np.frombuffer(bytes.fromhex("e2f2ae0a6abc4e71a884a961c500515f58e30b6aa582dd8db6a65945e08d2d76"), dtype=np.uint8)
+    out, valid = cref.msm_vartime_batched(r, np.broadcast_to(B, (d, 32)).copy(), np.arange(d + 1, dtype=np.uint64))
+    assert valid.all()
+    return out[np.arange(K) % d]
 
 
 if __name__ == "__main__":

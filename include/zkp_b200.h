@@ -56,8 +56,8 @@ void zkp_ctx_destroy(zkp_ctx* ctx);
 int32_t zkp_ctx_set_stream(zkp_ctx* ctx, void* cuda_stream);
 /* Tunables: "window" (Pippenger window width c, 0 = choose from n), "window_cap" (upper bound of the automatic
  * choice), "chunk" (max sorted entries per accumulate work item, 0 = auto), "profile" (0/1, see
- * zkp_ctx_stage_ms; forces the stages to run back to back), "overlap" (0/1, default 1: the digit sort runs on a
- * second stream concurrently with decompression), "chunk_terms" (H2D pipeline granularity of the host entry points). */
+ * zkp_ctx_stage_ms; forces the stages to run back to back), "overlap" (0/1, default 0: run the digit sort on a
+ * second stream concurrently with decompression; measured neutral), "chunk_terms" (H2D pipeline granularity of the host entry points). */
 int32_t zkp_ctx_set_option(zkp_ctx* ctx, const char* key, int64_t value);
 int32_t zkp_ctx_synchronize(zkp_ctx* ctx);
 const char* zkp_last_error(zkp_ctx* ctx);
@@ -124,8 +124,13 @@ int32_t zkp_batch_verify(zkp_ctx* ctx, const uint8_t* static_coeffs, const uint8
  * runs `iters` dependent multiplies (or squarings) per thread over a full grid and returns the measured
  * rate in operations per second in *ops_per_sec.  kind: 0 = fe_mul (8x32 saturated), 1 = fe_sq,
  * 2 = 5x51-limb multiply (u64 products), 3 = 10x25.5-limb multiply, 4 / 5 = 32 wide multiplies per
- * iteration without / with carry chains (raw IMAD.WIDE issue rate; ops counted per iteration).             */
+ * iteration without / with carry chains (raw IMAD.WIDE issue rate; ops counted per iteration), 6 / 7 =
+ * fe_mul / fe_sq with the shift-add reduction variant.                                                    */
 int32_t zkp_bench_field(zkp_ctx* ctx, int32_t kind, int32_t iters, double* ops_per_sec);
+
+/* Diagnostic: half of the warps run the integer fe_sq chain, the other half a DFMA chain (160 per fe_sq).
+ * mode 0 both, 1 integer warps only, 2 FP64 warps only; *ms_out = kernel time for `iters` squarings per thread. */
+int32_t zkp_bench_dual(zkp_ctx* ctx, int32_t mode, int32_t iters, double* ms_out);
 
 #ifdef __cplusplus
 }

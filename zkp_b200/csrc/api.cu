@@ -44,7 +44,7 @@ struct zkp_ctx {
   size_t chunk_terms = (size_t)1 << 21;
   // the digit sort (histogram, scan, scatter: L2-atomic bound) runs on a second, higher-priority stream
   // concurrently with decompression (integer-multiply bound); joined before bucket accumulation
-  int overlap = 1;
+  int overlap = 0;   // measured: no gain on B200 (159.2 vs 159.9 ms per step), kept as an option
   cudaStream_t sort_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
@@ -719,8 +719,36 @@ extern "C" int32_t zkp_msm_ct_batched(zkp_ctx* ctx, const uint8_t* scalars, cons
 // ---------------------------------------------------------------------------------------------------------
 // field-multiplier micro-benchmark
 // ---------------------------------------------------------------------------------------------------------
+// diagnostic: integer squaring warps and FP64 warps side by side; returns milliseconds
+extern "C" int32_t zkp_bench_dual(zkp_ctx* ctx, int32_t mode, int32_t iters, double* ms_out) {
+  if (!ctx || !ms_out || iters <= 0 || mode < 0 || mode > 2) return ZKP_ERR_SIZE;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  int sms = 0;
+  CUDA_TRY(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+  const int threads = 256, blocks = sms * 8;
+  ENSURE(ctx, ctx->aux0, (size_t)threads * blocks * 64);
+  cudaEvent_t e0, e1;
+  CUDA_TRY(ctx, cudaEventCreate(&e0));
+  CUDA_TRY(ctx, cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; rep++) {
+    CUDA_TRY(ctx, cudaEventRecord(e0, ctx->stream));
+    k_bench_dual<<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, iters, mode);
+    LAUNCH_CHECK(ctx);
+    CUDA_TRY(ctx, cudaEventRecord(e1, ctx->stream));
+    CUDA_TRY(ctx, cudaEventSynchronize(e1));
+    float ms = 0;
+    CUDA_TRY(ctx, cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms_out = best;
+  return ZKP_OK;
+}
+
 extern "C" int32_t zkp_bench_field(zkp_ctx* ctx, int32_t kind, int32_t iters, double* ops_per_sec) {
-  if (!ctx || !ops_per_sec || iters <= 0 || kind < 0 || kind > 5) return ZKP_ERR_SIZE;
+  if (!ctx || !ops_per_sec || iters <= 0 || kind < 0 || kind > 7) return ZKP_ERR_SIZE;
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   int sms = 0;
   CUDA_TRY(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
@@ -733,12 +761,15 @@ extern "C" int32_t zkp_bench_field(zkp_ctx* ctx, int32_t kind, int32_t iters, do
   for (int rep = 0; rep < 4; rep++) {
     CUDA_TRY(ctx, cudaEventRecord(e0, ctx->stream));
     switch (kind) {
-      case 0: k_bench_mul32<<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, iters); break;
-      case 1: k_bench_sq32<<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, iters); break;
+      case 0: k_bench_mul32<0><<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, iters); break;
+      case 1: k_bench_sq32<0><<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, iters); break;
+      case 6: k_bench_mul32<1><<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, iters); break;
+      case 7: k_bench_sq32<1><<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, iters); break;
       case 2: k_bench_mul51<<<blocks, threads, 0, ctx->stream>>>((unsigned long long*)ctx->aux0.p, iters); break;
       case 3: k_bench_mul25<<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, iters); break;
       case 4: k_bench_wide_plain<<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, iters); break;
-      default: k_bench_wide_carry<<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, iters); break;
+      case 5: k_bench_wide_carry<<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, iters); break;
+      default: break;
     }
     LAUNCH_CHECK(ctx);
     CUDA_TRY(ctx, cudaEventRecord(e1, ctx->stream));

@@ -7,6 +7,7 @@
 
 namespace zkp {
 
+template <int RED>
 __global__ void __launch_bounds__(256) k_bench_mul32(uint32_t* out, int iters) {
   uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
   fe a, b;
@@ -17,13 +18,14 @@ __global__ void __launch_bounds__(256) k_bench_mul32(uint32_t* out, int iters) {
   }
 #pragma unroll 1
   for (int k = 0; k < iters; k += 2) {
-    fe_mul(a, a, b);
-    fe_mul(b, b, a);
+    fe_mul_t<RED>(a, a, b);
+    fe_mul_t<RED>(b, b, a);
   }
 #pragma unroll
   for (int i = 0; i < 8; i++) out[(size_t)gid * 16 + i] = a.v[i] ^ b.v[i];
 }
 
+template <int RED>
 __global__ void __launch_bounds__(256) k_bench_sq32(uint32_t* out, int iters) {
   uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
   fe a;
@@ -31,8 +33,8 @@ __global__ void __launch_bounds__(256) k_bench_sq32(uint32_t* out, int iters) {
   for (int i = 0; i < 8; i++) a.v[i] = gid * 2654435761u + i * 40503u + 1;
 #pragma unroll 1
   for (int k = 0; k < iters; k += 2) {
-    fe_sq(a, a);
-    fe_sq(a, a);
+    fe_sq_t<RED>(a, a);
+    fe_sq_t<RED>(a, a);
   }
 #pragma unroll
   for (int i = 0; i < 8; i++) out[(size_t)gid * 16 + i] = a.v[i];
@@ -187,6 +189,44 @@ __global__ void __launch_bounds__(256) k_bench_wide_carry(uint32_t* out, int ite
 #pragma unroll
   for (int i = 0; i < 8; i++) x ^= e[i] ^ o[i];
   out[gid] = x;
+}
+
+
+// ---- can the FP64 pipe run beside the integer pipe?  Odd warps run the fe_sq chain, even warps run a chain of
+// DFMAs (16 independent accumulators, `fp64_per_iter` DFMAs per loop trip).  mode 0: both, 1: only integer warps
+// (the others exit), 2: only FP64 warps.  Reported through zkp_bench_dual.
+__global__ void __launch_bounds__(256) k_bench_dual(uint32_t* out, int iters, int mode) {
+  uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool int_warp = ((threadIdx.x >> 5) & 1) != 0;
+  if (int_warp) {
+    if (mode == 2) return;
+    fe a;
+#pragma unroll
+    for (int i = 0; i < 8; i++) a.v[i] = gid * 2654435761u + i * 40503u + 1;
+#pragma unroll 1
+    for (int k = 0; k < iters; k += 2) {
+      fe_sq(a, a);
+      fe_sq(a, a);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) out[(size_t)gid * 16 + i] = a.v[i];
+  } else {
+    if (mode == 1) return;
+    double acc[16], m = 1.0000001 + gid * 1e-9, c = 0.5;
+#pragma unroll
+    for (int i = 0; i < 16; i++) acc[i] = 1.0 + i + gid;
+#pragma unroll 1
+    for (int k = 0; k < iters; k += 2) {
+#pragma unroll
+      for (int r = 0; r < 20; r++)   // 2 x 160 DFMAs per trip = the op budget of two FP64 squarings
+#pragma unroll
+        for (int i = 0; i < 16; i++) acc[i] = fma(acc[i], m, c);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) s += acc[i];
+    out[(size_t)gid * 16] = (uint32_t)__double2loint(s);
+  }
 }
 
 }  // namespace zkp

@@ -350,8 +350,49 @@ ZKP_DEV void fe_reduce512(fe& r, const uint32_t* t) {
   for (int i = 0; i < 8; i++) r.v[i] = lo[i];
 }
 
+// Variant of fe_reduce512 that multiplies the high half by 38 = 2^5 + 2^2 + 2^1 with funnel shifts and adds on the
+// ALU pipe instead of eight wide IMADs on the (saturated) FMA pipe.  Selected with -DZKP_REDUCE_SHIFTADD.
+ZKP_DEV uint32_t shl_limb(uint32_t lo, uint32_t hi, int s) {
+#if ZKP_DEVICE_ASM
+  return __funnelshift_l(lo, hi, s);
+#else
+  return (hi << s) | (lo >> (32 - s));
+#endif
+}
+ZKP_DEV void fe_reduce512_shiftadd(fe& r, const uint32_t* t) {
+  uint32_t a5[9], a2[9], a1[9], s1[9], s2[9], lo[9];
+  const uint32_t* H = t + 8;
+  a5[0] = H[0] << 5; a2[0] = H[0] << 2; a1[0] = H[0] << 1;
+#pragma unroll
+  for (int i = 1; i < 8; i++) {
+    a5[i] = shl_limb(H[i - 1], H[i], 5);
+    a2[i] = shl_limb(H[i - 1], H[i], 2);
+    a1[i] = shl_limb(H[i - 1], H[i], 1);
+  }
+  a5[8] = H[7] >> 27; a2[8] = H[7] >> 30; a1[8] = H[7] >> 31;
+  uint32_t c = add8(s1, a5, a2);
+  s1[8] = a5[8] + a2[8] + c;
+  c = add8(s2, s1, a1);
+  s2[8] = s1[8] + a1[8] + c;           // 38*H as nine limbs, s2[8] <= 37
+  c = add8(lo, t, s2);
+  lo[8] = s2[8] + c;                   // weight 2^256, <= 38
+  uint32_t c3 = add_word8(lo, lo[8] * 38u);
+  lo[0] += 38u * c3;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = lo[i];
+}
+#ifndef ZKP_REDUCE_DEFAULT
+#define ZKP_REDUCE_DEFAULT 0   // 0 = wide-IMAD reduction, 1 = shift-add reduction
+#endif
+template <int RED>
+ZKP_DEV void fe_reduce512_sel(fe& r, const uint32_t* t) {
+  if (RED) fe_reduce512_shiftadd(r, t);
+  else fe_reduce512(r, t);
+}
+
 // r = a*b mod p (weak: r < 2^256)
-ZKP_DEV void fe_mul(fe& r, const fe& a, const fe& b) {
+template <int RED>
+ZKP_DEV void fe_mul_t(fe& r, const fe& a, const fe& b) {
   const uint32_t* A = a.v;
   const uint32_t* B = b.v;
   uint32_t E[17], O[17];
@@ -378,11 +419,13 @@ ZKP_DEV void fe_mul(fe& r, const fe& a, const fe& b) {
   t[0] = E[0];
   uint32_t c = add8(t + 1, E + 1, O);
   add8c(t + 9, E + 9, O + 8, c);   // t[16] = 0
-  fe_reduce512(r, t);
+  fe_reduce512_sel<RED>(r, t);
 }
+ZKP_DEV void fe_mul(fe& r, const fe& a, const fe& b) { fe_mul_t<ZKP_REDUCE_DEFAULT>(r, a, b); }
 
 // r = a^2 mod p
-ZKP_DEV void fe_sq(fe& r, const fe& a) {
+template <int RED>
+ZKP_DEV void fe_sq_t(fe& r, const fe& a) {
   const uint32_t* A = a.v;
   uint32_t E[17], O[17];
 #pragma unroll
@@ -422,8 +465,9 @@ ZKP_DEV void fe_sq(fe& r, const fe& a) {
   // add the squares a_i^2 at limb 2i
   uint32_t c2 = sqr4c(t, A[0], A[1], A[2], A[3], 0u);
   sqr4c(t + 8, A[4], A[5], A[6], A[7], c2);
-  fe_reduce512(r, t);
+  fe_reduce512_sel<RED>(r, t);
 }
+ZKP_DEV void fe_sq(fe& r, const fe& a) { fe_sq_t<ZKP_REDUCE_DEFAULT>(r, a); }
 
 // r = a + b
 ZKP_DEV void fe_add(fe& r, const fe& a, const fe& b) {

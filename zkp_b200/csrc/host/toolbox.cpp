@@ -277,49 +277,23 @@ BatchVerifier::BatchVerifier(zkp_ctx* ctx, const std::string& proof_label, size_
     *err = BatchSizeMismatch;
     return;
   }
-  if (uniform_ && batch_size_) {
-    domain_sep((*transcripts_)[0], proof_label);
-    broadcast_first();
-  } else {
-    parallel_for(batch_size_, threads_, [&](size_t lo, size_t hi, int) {
-      for (size_t j = lo; j < hi; j++) domain_sep((*transcripts_)[j], proof_label);
-    });
-  }
+  script_.push_back(Op{0, proof_label, 0});
   *err = PROOF_OK;
 }
-void BatchVerifier::broadcast_first() {
-  parallel_for(batch_size_, threads_, [&](size_t lo, size_t hi, int) {
-    for (size_t j = lo ? lo : 1; j < hi; j++) (*transcripts_)[j] = (*transcripts_)[0];
-  });
-}
 int BatchVerifier::allocate_scalar(const std::string& label) {
-  if (uniform_ && batch_size_) {
-    append_scalar_var((*transcripts_)[0], label);
-    broadcast_first();
-  } else {
-    parallel_for(batch_size_, threads_, [&](size_t lo, size_t hi, int) {
-      for (size_t j = lo; j < hi; j++) append_scalar_var((*transcripts_)[j], label);
-    });
-  }
+  script_.push_back(Op{1, label, 0});
   return num_scalars_++;
 }
 BatchPointVar BatchVerifier::allocate_static_point(const std::string& label, const Enc& assignment, ProofError* err) {
   BatchPointVar v = {true, -1};
-  if (is_identity_encoding(assignment) && batch_size_) {   // toolbox/mod.rs:191, first transcript already fails
+  if (is_identity_encoding(assignment) && batch_size_) {   // toolbox/mod.rs:191: the first transcript already fails
     *err = VerificationFailure;
     return v;
-  }
-  if (uniform_ && batch_size_) {
-    append_point_var((*transcripts_)[0], label, assignment);
-    broadcast_first();
-  } else {
-    parallel_for(batch_size_, threads_, [&](size_t lo, size_t hi, int) {
-      for (size_t j = lo; j < hi; j++) append_point_var((*transcripts_)[j], label, assignment);
-    });
   }
   static_points_.push_back(assignment);
   static_point_labels_.push_back(label);
   v.idx = (int)static_points_.size() - 1;
+  script_.push_back(Op{2, label, v.idx});
   *err = PROOF_OK;
   return v;
 }
@@ -330,21 +304,28 @@ BatchPointVar BatchVerifier::allocate_instance_point(const std::string& label, c
     *err = BatchSizeMismatch;
     return v;
   }
-  uniform_ = false;   // per-proof data from here on
-  std::vector<uint8_t> bad(1, 0);
-  parallel_for(batch_size_, threads_, [&](size_t lo, size_t hi, int) {
-    for (size_t j = lo; j < hi; j++)
-      if (!validate_and_append_point_var((*transcripts_)[j], label, assignments[j])) bad[0] = 1;
-  });
-  if (bad[0]) {
-    *err = VerificationFailure;
-    return v;
-  }
+  for (size_t j = 0; j < batch_size_; j++)
+    if (is_identity_encoding(assignments[j])) {
+      *err = VerificationFailure;
+      return v;
+    }
   instance_points_.push_back(assignments);
   instance_point_labels_.push_back(label);
   v.idx = (int)instance_points_.size() - 1;
+  script_.push_back(Op{3, label, v.idx});
   *err = PROOF_OK;
   return v;
+}
+void BatchVerifier::replay(Transcript& t, size_t j, size_t from, size_t to) const {
+  for (size_t o = from; o < to; o++) {
+    const Op& op = script_[o];
+    switch (op.kind) {
+      case 0: domain_sep(t, op.label); break;
+      case 1: append_scalar_var(t, op.label); break;
+      case 2: append_point_var(t, op.label, static_points_[op.idx]); break;
+      default: append_point_var(t, op.label, instance_points_[op.idx][j]); break;
+    }
+  }
 }
 
 ProofError BatchVerifier::batch_coeffs(const std::vector<BatchableProof>& proofs, Rng& rng, int threads,
@@ -355,11 +336,21 @@ ProofError BatchVerifier::batch_coeffs(const std::vector<BatchableProof>& proofs
   for (auto& p : proofs)
     if (p.commitments.size() != constraints_.size() || (int)p.responses.size() != num_scalars_) return VerificationFailure;
   const size_t num_s = static_points_.size(), num_i = instance_points_.size(), num_c = constraints_.size();
-  // commitments into the transcripts, then the challenges (batch_verifier.rs:152-167) -- independent per proof
+  // replay the recorded allocations (hashing the batch-wide prefix once when all transcripts started identical),
+  // then the commitments and the challenges (batch_verifier.rs:75-167) -- independent per proof
+  size_t prefix = 0;
+  Transcript prefix_state;
+  if (uniform_ && N) {
+    while (prefix < script_.size() && script_[prefix].kind != 3) prefix++;
+    prefix_state = (*transcripts_)[0];
+    replay(prefix_state, 0, 0, prefix);
+  }
   std::vector<Scalar> minus_c(N);
   std::vector<uint8_t> bad(N, 0);
   parallel_for(N, threads, [&](size_t lo, size_t hi, int) {
     for (size_t j = lo; j < hi; j++) {
+      if (prefix) (*transcripts_)[j] = prefix_state;
+      replay((*transcripts_)[j], j, prefix, script_.size());
       for (size_t i = 0; i < num_c; i++) {
         const BatchPointVar& lhs = constraints_[i].first;
         const std::string& label = lhs.is_static ? static_point_labels_[lhs.idx] : instance_point_labels_[lhs.idx];

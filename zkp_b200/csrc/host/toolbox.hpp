@@ -128,7 +128,11 @@ class BatchVerifier {
   // true while every transcript is known to hold the same state (caller passed identical copies and only
   // batch-wide data has been absorbed): such appends are hashed once and the state is copied
   bool uniform_;
-  void broadcast_first();
+  // allocation calls are recorded and replayed per transcript inside ONE parallel region at verification time
+  // (the reference hashes eagerly, transcript by transcript; the transcripts' final states are identical)
+  struct Op { int kind; std::string label; int idx; };   // kind: 0 dom-sep, 1 scalar, 2 static point, 3 instance point
+  std::vector<Op> script_;
+  void replay(Transcript& t, size_t j, size_t from, size_t to) const;
   std::vector<Enc> static_points_;
   std::vector<std::string> static_point_labels_;
   std::vector<std::vector<Enc>> instance_points_;

@@ -15,7 +15,7 @@ SYMBOLS = [
     "zkp_device_count", "zkp_ctx_create", "zkp_ctx_destroy", "zkp_ctx_set_stream", "zkp_ctx_set_option",
     "zkp_ctx_synchronize", "zkp_last_error", "zkp_ctx_launch_count", "zkp_decompress_batch", "zkp_compress_batch",
     "zkp_msm_vartime", "zkp_msm_vartime_dev", "zkp_msm_vartime_batched", "zkp_msm_ct_batched", "zkp_batch_verify",
-    "zkp_bench_field", "zkp_ctx_stage_ms",
+    "zkp_bench_field", "zkp_ctx_stage_ms", "zkp_bench_dual",
 ]
 
 _lib = None
@@ -70,6 +70,8 @@ def load():
     lib.zkp_batch_verify.restype = c_int32
     lib.zkp_bench_field.argtypes = [c_void_p, c_int32, c_int32, P(ctypes.c_double)]
     lib.zkp_bench_field.restype = c_int32
+    lib.zkp_bench_dual.argtypes = [c_void_p, c_int32, c_int32, P(ctypes.c_double)]
+    lib.zkp_bench_dual.restype = c_int32
     lib.zkp_ctx_stage_ms.argtypes = [c_void_p, c_int32]
     lib.zkp_ctx_stage_ms.restype = ctypes.c_double
     _lib = lib
