@@ -59,6 +59,25 @@ int32_t zkph_prove_many(zkp_ctx* ctx, const zkph_statement* st, const uint8_t* t
                         const uint8_t* secrets, const uint64_t* points, const uint8_t* entropy, int32_t threads,
                         uint8_t* encodings, uint8_t* commitments, uint8_t* responses);
 
+/* merlin::Transcript handles, for callers that drive the transcript themselves the way the reference's API takes
+ * `&mut Transcript` (e.g. /root/reference/tests/sig_and_vrf_example.rs:86-125: messages are appended before proving).
+ * The *_t entry points below mutate the handle exactly like the reference mutates its transcript.               */
+typedef struct zkph_transcript zkph_transcript;
+zkph_transcript* zkph_transcript_new(const uint8_t* label, size_t len);
+zkph_transcript* zkph_transcript_clone(const zkph_transcript* t);
+void zkph_transcript_free(zkph_transcript* t);
+void zkph_transcript_append_message(zkph_transcript* t, const uint8_t* label, size_t llen, const uint8_t* msg, size_t mlen);
+void zkph_transcript_challenge_bytes(zkph_transcript* t, const uint8_t* label, size_t llen, uint8_t* out, size_t n);
+int32_t zkph_prove_t(zkp_ctx* ctx, const zkph_statement* st, zkph_transcript* t, const uint8_t* secrets,
+                     const uint64_t* points, const uint8_t* rng_seed, size_t seed_len, int32_t batchable,
+                     uint8_t* encodings, uint8_t* challenge, uint8_t* commitments, uint8_t* responses,
+                     uint8_t* blindings_out);
+int32_t zkph_verify_compact_t(zkp_ctx* ctx, const zkph_statement* st, zkph_transcript* t, const uint8_t* points_enc,
+                              const uint8_t* challenge, const uint8_t* responses, size_t n_responses);
+int32_t zkph_verify_batchable_t(zkp_ctx* ctx, const zkph_statement* st, zkph_transcript* t, const uint8_t* points_enc,
+                                const uint8_t* commitments, size_t n_commitments, const uint8_t* responses,
+                                size_t n_responses, const uint8_t* rng_seed, size_t seed_len);
+
 /* host primitives exposed for parity tests */
 void zkph_scalar_mul(uint8_t* out32, const uint8_t* a32, const uint8_t* b32);
 void zkph_scalar_from_wide(uint8_t* out32, const uint8_t* in64);

@@ -8,6 +8,7 @@
 using namespace zkp_host;
 
 struct zkph_statement { Statement st; };
+struct zkph_transcript { Transcript t; };
 
 extern "C" zkph_statement* zkph_statement_new(const char* name, const char* label, const char* labels, int32_t n_secrets,
                                               int32_t n_instance, int32_t n_common, int32_t n_constraints,
@@ -37,17 +38,47 @@ extern "C" void zkph_statement_free(zkph_statement* st) { delete st; }
 
 static Scalar load_scalar(const uint8_t* b) { return Scalar::from_bytes_mod_order(b); }
 
+extern "C" zkph_transcript* zkph_transcript_new(const uint8_t* label, size_t len) {
+  zkph_transcript* h = new (std::nothrow) zkph_transcript();
+  if (h) h->t = Transcript(label, len);
+  return h;
+}
+extern "C" zkph_transcript* zkph_transcript_clone(const zkph_transcript* t) {
+  zkph_transcript* h = new (std::nothrow) zkph_transcript();
+  if (h) h->t = t->t;
+  return h;
+}
+extern "C" void zkph_transcript_free(zkph_transcript* t) { delete t; }
+extern "C" void zkph_transcript_append_message(zkph_transcript* t, const uint8_t* label, size_t llen, const uint8_t* msg,
+                                               size_t mlen) {
+  t->t.append_message(label, llen, msg, mlen);
+}
+extern "C" void zkph_transcript_challenge_bytes(zkph_transcript* t, const uint8_t* label, size_t llen, uint8_t* out,
+                                                size_t n) {
+  t->t.challenge_bytes(label, llen, out, n);
+}
+
 extern "C" int32_t zkph_prove(zkp_ctx* ctx, const zkph_statement* h, const uint8_t* tl, size_t tl_len,
                               const uint8_t* secrets, const uint64_t* points, const uint8_t* seed, size_t seed_len,
                               int32_t batchable, uint8_t* encodings, uint8_t* challenge, uint8_t* commitments,
                               uint8_t* responses, uint8_t* blindings_out) {
+  zkph_transcript tr;
+  tr.t = Transcript(tl, tl_len);
+  return zkph_prove_t(ctx, h, &tr, secrets, points, seed, seed_len, batchable, encodings, challenge, commitments,
+                      responses, blindings_out);
+}
+
+extern "C" int32_t zkph_prove_t(zkp_ctx* ctx, const zkph_statement* h, zkph_transcript* tr, const uint8_t* secrets,
+                                const uint64_t* points, const uint8_t* seed, size_t seed_len, int32_t batchable,
+                                uint8_t* encodings, uint8_t* challenge, uint8_t* commitments, uint8_t* responses,
+                                uint8_t* blindings_out) {
   const Statement& st = h->st;
+  Transcript& t = tr->t;
   const size_t m = st.secrets.size(), p = st.num_points(), k = st.constraints.size();
   std::vector<Scalar> sec(m);
   for (size_t i = 0; i < m; i++) sec[i] = load_scalar(secrets + 32 * i);
   std::vector<Limbs> pts(p);
   for (size_t i = 0; i < p; i++) memcpy(pts[i].data(), points + 20 * i, 160);
-  Transcript t(tl, tl_len);
   Rng rng(seed, seed_len);
   // re-implemented inline (instead of stmt_prove) to hand the blindings back for parity tests
   Prover pr(ctx, st.label, &t);
@@ -88,6 +119,13 @@ static std::vector<Enc> load_encs(const uint8_t* b, size_t n) {
 extern "C" int32_t zkph_verify_compact(zkp_ctx* ctx, const zkph_statement* h, const uint8_t* tl, size_t tl_len,
                                        const uint8_t* points_enc, const uint8_t* challenge, const uint8_t* responses,
                                        size_t n_responses) {
+  zkph_transcript tr;
+  tr.t = Transcript(tl, tl_len);
+  return zkph_verify_compact_t(ctx, h, &tr, points_enc, challenge, responses, n_responses);
+}
+extern "C" int32_t zkph_verify_compact_t(zkp_ctx* ctx, const zkph_statement* h, zkph_transcript* tr,
+                                         const uint8_t* points_enc, const uint8_t* challenge, const uint8_t* responses,
+                                         size_t n_responses) {
   const Statement& st = h->st;
   CompactProof cp;
   // Scalar deserialisation in the reference rejects non-canonical bytes; mirror that as a failure
@@ -95,23 +133,30 @@ extern "C" int32_t zkph_verify_compact(zkp_ctx* ctx, const zkph_statement* h, co
   cp.responses.resize(n_responses);
   for (size_t i = 0; i < n_responses; i++)
     if (!Scalar::from_canonical_bytes(&cp.responses[i], responses + 32 * i)) return VerificationFailure;
-  Transcript t(tl, tl_len);
-  return stmt_verify_compact(ctx, st, &t, load_encs(points_enc, st.num_points()), cp);
+  return stmt_verify_compact(ctx, st, &tr->t, load_encs(points_enc, st.num_points()), cp);
 }
 
 extern "C" int32_t zkph_verify_batchable(zkp_ctx* ctx, const zkph_statement* h, const uint8_t* tl, size_t tl_len,
                                          const uint8_t* points_enc, const uint8_t* commitments, size_t n_commitments,
                                          const uint8_t* responses, size_t n_responses, const uint8_t* seed,
                                          size_t seed_len) {
+  zkph_transcript tr;
+  tr.t = Transcript(tl, tl_len);
+  return zkph_verify_batchable_t(ctx, h, &tr, points_enc, commitments, n_commitments, responses, n_responses, seed,
+                                 seed_len);
+}
+extern "C" int32_t zkph_verify_batchable_t(zkp_ctx* ctx, const zkph_statement* h, zkph_transcript* tr,
+                                           const uint8_t* points_enc, const uint8_t* commitments, size_t n_commitments,
+                                           const uint8_t* responses, size_t n_responses, const uint8_t* seed,
+                                           size_t seed_len) {
   const Statement& st = h->st;
   BatchableProof bp;
   bp.commitments = load_encs(commitments, n_commitments);
   bp.responses.resize(n_responses);
   for (size_t i = 0; i < n_responses; i++)
     if (!Scalar::from_canonical_bytes(&bp.responses[i], responses + 32 * i)) return VerificationFailure;
-  Transcript t(tl, tl_len);
   Rng rng(seed, seed_len);
-  return stmt_verify_batchable(ctx, st, &t, load_encs(points_enc, st.num_points()), bp, rng);
+  return stmt_verify_batchable(ctx, st, &tr->t, load_encs(points_enc, st.num_points()), bp, rng);
 }
 
 extern "C" int32_t zkph_batch_verify(zkp_ctx* ctx, const zkph_statement* h, const uint8_t* tl, size_t tl_len, size_t N,

@@ -51,6 +51,16 @@ def _lib():
         lib.zkph_verify_batchable.argtypes = [vp, vp, vp, sz, vp, vp, sz, vp, sz, vp, sz]
         lib.zkph_batch_verify.argtypes = [vp, vp, vp, sz, sz, vp, vp, vp, vp, vp, sz, i32, vp, vp, vp]
         lib.zkph_prove_many.argtypes = [vp, vp, vp, sz, sz, vp, vp, vp, i32, vp, vp, vp]
+        lib.zkph_transcript_new.restype = vp
+        lib.zkph_transcript_new.argtypes = [vp, sz]
+        lib.zkph_transcript_clone.restype = vp
+        lib.zkph_transcript_clone.argtypes = [vp]
+        lib.zkph_transcript_free.argtypes = [vp]
+        lib.zkph_transcript_append_message.argtypes = [vp, vp, sz, vp, sz]
+        lib.zkph_transcript_challenge_bytes.argtypes = [vp, vp, sz, vp, sz]
+        lib.zkph_prove_t.argtypes = [vp, vp, vp, vp, vp, vp, sz, i32, vp, vp, vp, vp, vp]
+        lib.zkph_verify_compact_t.argtypes = [vp, vp, vp, vp, vp, vp, sz]
+        lib.zkph_verify_batchable_t.argtypes = [vp, vp, vp, vp, vp, sz, vp, sz, vp, sz]
         lib.zkph_scalar_mul.argtypes = [vp, vp, vp]
         lib.zkph_scalar_from_wide.argtypes = [vp, vp]
         lib.zkph_merlin_test_vector.argtypes = [vp]
@@ -61,6 +71,32 @@ def _lib():
 
 def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+class Transcript:
+    """merlin::Transcript (re-exported by the reference as zkp::Transcript, /root/reference/src/lib.rs:35), hashed
+    by the C++ host library.  Pass an instance wherever a transcript label (bytes) is accepted to drive the
+    transcript yourself, as the reference's `&mut Transcript` arguments allow."""
+
+    def __init__(self, label=None, _handle=None):
+        self._h = _handle if _handle is not None else _lib().zkph_transcript_new(bytes(label), len(label))
+
+    def clone(self):
+        return Transcript(_handle=_lib().zkph_transcript_clone(self._h))
+
+    def append_message(self, label, message):
+        _lib().zkph_transcript_append_message(self._h, bytes(label), len(label), bytes(message), len(message))
+
+    def challenge_bytes(self, label, n):
+        out = ctypes.create_string_buffer(n)
+        _lib().zkph_transcript_challenge_bytes(self._h, bytes(label), len(label), out, n)
+        return out.raw
+
+    def __del__(self):
+        try:
+            _lib().zkph_transcript_free(self._h)
+        except Exception:
+            pass
 
 
 class Statement:
@@ -99,8 +135,12 @@ class Statement:
         com = np.zeros((self.k, 32), np.uint8)
         resp = np.zeros((self.m, 32), np.uint8)
         blind = np.zeros((self.m, 32), np.uint8)
-        _raise(lib.zkph_prove(eng._ctx, self._h, transcript_label, len(transcript_label), _p(sec), _p(pts), rng_seed,
-                              len(rng_seed), 1 if batchable else 0, _p(enc), _p(chal), _p(com), _p(resp), _p(blind)))
+        if isinstance(transcript_label, Transcript):
+            _raise(lib.zkph_prove_t(eng._ctx, self._h, transcript_label._h, _p(sec), _p(pts), rng_seed, len(rng_seed),
+                                    1 if batchable else 0, _p(enc), _p(chal), _p(com), _p(resp), _p(blind)))
+        else:
+            _raise(lib.zkph_prove(eng._ctx, self._h, transcript_label, len(transcript_label), _p(sec), _p(pts), rng_seed,
+                                  len(rng_seed), 1 if batchable else 0, _p(enc), _p(chal), _p(com), _p(resp), _p(blind)))
         return enc, chal, com, resp, blind
 
     def prove_compact(self, eng, transcript_label, secrets, points_limbs, rng_seed):
@@ -119,15 +159,23 @@ class Statement:
         resp = _u8(resp, 32)
         enc = _u8(encodings, 32)
         assert enc.shape[0] == self.p
-        _raise(_lib().zkph_verify_compact(eng._ctx, self._h, transcript_label, len(transcript_label), _p(enc),
-                                          bytes(chal), _p(resp), resp.shape[0]))
+        if isinstance(transcript_label, Transcript):
+            _raise(_lib().zkph_verify_compact_t(eng._ctx, self._h, transcript_label._h, _p(enc), bytes(chal), _p(resp),
+                                                resp.shape[0]))
+        else:
+            _raise(_lib().zkph_verify_compact(eng._ctx, self._h, transcript_label, len(transcript_label), _p(enc),
+                                              bytes(chal), _p(resp), resp.shape[0]))
 
     def verify_batchable(self, eng, proof, transcript_label, encodings, rng_seed):
         com, resp = proof
         com, resp, enc = _u8(com, 32), _u8(resp, 32), _u8(encodings, 32)
         assert enc.shape[0] == self.p
-        _raise(_lib().zkph_verify_batchable(eng._ctx, self._h, transcript_label, len(transcript_label), _p(enc), _p(com),
-                                            com.shape[0], _p(resp), resp.shape[0], rng_seed, len(rng_seed)))
+        if isinstance(transcript_label, Transcript):
+            _raise(_lib().zkph_verify_batchable_t(eng._ctx, self._h, transcript_label._h, _p(enc), _p(com), com.shape[0],
+                                                  _p(resp), resp.shape[0], rng_seed, len(rng_seed)))
+        else:
+            _raise(_lib().zkph_verify_batchable(eng._ctx, self._h, transcript_label, len(transcript_label), _p(enc), _p(com),
+                                                com.shape[0], _p(resp), resp.shape[0], rng_seed, len(rng_seed)))
 
     # ---- module::batch_verify ---------------------------------------------------------------------------------
     def batch_verify(self, eng, proofs_commitments, proofs_responses, transcript_label, instance_enc, common_enc,
