@@ -40,6 +40,11 @@ void emul_madd(uint8_t* out, const uint8_t* pt128, const uint8_t* aff96, int neg
   ge_aniels q; ge_aniels_from_affine(q, x, y, t); ge_aniels_cneg(q, (uint32_t)neg);
   ge_ext r; ge_madd(r, ldp(pt128), q); memcpy(out, &r, 128);
 }
+void emul_madd_signed(uint8_t* out, const uint8_t* pt128, const uint8_t* aff96, int neg) {
+  fe x, y, t; memcpy(x.v, aff96, 32); memcpy(y.v, aff96 + 32, 32); memcpy(t.v, aff96 + 64, 32);
+  ge_aniels q; ge_aniels_from_affine(q, x, y, t);
+  ge_ext r; ge_madd_signed(r, ldp(pt128), q, (uint32_t)neg); memcpy(out, &r, 128);
+}
 void emul_add(uint8_t* out, const uint8_t* p, const uint8_t* q) { ge_ext r; ge_add(r, ldp(p), ldp(q)); memcpy(out, &r, 128); }
 void emul_double(uint8_t* out, const uint8_t* p) { ge_ext r; ge_double(r, ldp(p)); memcpy(out, &r, 128); }
 int emul_is_identity(const uint8_t* p) { return (int)ge_is_identity_coset(ldp(p)); }

@@ -104,6 +104,9 @@ def test_group_and_codec(lib):
             exp = R.pt_sub(p, q) if neg else R.pt_add(p, q)
             r = _pf(out.raw)
             assert R.on_curve(r) and R.compress(r) == R.compress(exp)
+            lib.emul_madd_signed(out, _pb(p), affs[i + 1], neg)
+            r = _pf(out.raw)
+            assert R.on_curve(r) and R.compress(r) == R.compress(exp)
         lib.emul_add(out, _pb(p), _pb(q))
         r, exp = _pf(out.raw), R.pt_add(p, q)
         assert R.on_curve(r) and (r[0] * exp[2] - exp[0] * r[2]) % P == 0 and (r[1] * exp[2] - exp[1] * r[2]) % P == 0

@@ -56,6 +56,30 @@ ZKP_DEV void ge_madd(ge_ext& r, const ge_ext& p, const ge_aniels& q) {
   fe_mul(r.T, e, h);
 }
 
+// r = p + (neg ? -q : q) with the sign folded into operand selection (no field negation, 32 selects):
+// -q swaps (y+x, y-x) and flips the sign of 2dxy, i.e. swaps F = D - C and G = D + C.
+ZKP_DEV void ge_madd_signed(ge_ext& r, const ge_ext& p, const ge_aniels& q, uint32_t neg) {
+  fe a, b, c, d, e, f0, g0, f, g, h, qa, qb;
+  fe_select(qa, q.yminusx, q.yplusx, neg);
+  fe_select(qb, q.yplusx, q.yminusx, neg);
+  fe_sub(a, p.Y, p.X);
+  fe_add(b, p.Y, p.X);
+  fe_mul(a, a, qa);
+  fe_mul(b, b, qb);
+  fe_mul(c, p.T, q.xy2d);
+  fe_add(d, p.Z, p.Z);
+  fe_sub(e, b, a);
+  fe_sub(f0, d, c);
+  fe_add(g0, d, c);
+  fe_select(f, f0, g0, neg);
+  fe_select(g, g0, f0, neg);
+  fe_add(h, b, a);
+  fe_mul(r.X, e, f);
+  fe_mul(r.Y, g, h);
+  fe_mul(r.Z, f, g);
+  fe_mul(r.T, e, h);
+}
+
 // conditional negation of an affine Niels point (branch-free): swap the first two, negate the third
 ZKP_DEV void ge_aniels_cneg(ge_aniels& q, uint32_t neg) {
   fe_cswap(q.yplusx, q.yminusx, neg);

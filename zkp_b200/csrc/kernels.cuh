@@ -292,8 +292,7 @@ __global__ void __launch_bounds__(128, 4) k_accumulate(const uint4* __restrict__
       e_nxt = __ldg(base + inext);
       load_aniels(nxt, niels, e_nxt);
     }
-    ge_aniels_cneg(cur, e_cur >> 31);
-    ge_madd(acc, acc, cur);
+    ge_madd_signed(acc, acc, cur, e_cur >> 31);
     cur = nxt;
     e_cur = e_nxt;
     i = inext;
