@@ -120,6 +120,31 @@ int32_t zkp_batch_verify(zkp_ctx* ctx, const uint8_t* static_coeffs, const uint8
                          const uint8_t* instance_coeffs, const uint8_t* instance_points, size_t rows, size_t batch,
                          int32_t* accept, int64_t* first_bad);
 
+/* SURVEY.md section 8f rows f1 + f2 ("next"): BatchVerifier::verify_batchable with the per-proof work on the device --
+ * Merlin transcripts and challenges (/root/reference/src/toolbox/batch_verifier.rs:115-167), random weights (:179),
+ * coefficient fold (:176-206) -- followed by the same combined MSM and identity test (:219-234).
+ * The statement is the define_proof! expansion (macros.rs:336-370): transcript order = instance points in order,
+ * then common (static) points, then one blinding commitment per constraint labelled with its lhs variable.      */
+typedef struct {
+  int32_t m, ni, nc, k;        /* secrets, instance points, common points, constraints                         */
+  const char* labels;          /* ni + nc NUL-terminated point labels back to back (instance first)             */
+  const int32_t* lhs;          /* [k] lhs point index over instance ++ common                                   */
+  const int32_t* cons_off;     /* [k+1] term ranges                                                             */
+  const int32_t* term_scalar;  /* secret index per term                                                         */
+  const int32_t* term_point;   /* point index per term, over instance ++ common                                 */
+} zkp_statement_desc;
+/* prefix_state: 53 little-endian uint32 = STROBE state (25 lanes as lo,hi), pos, pos_begin, cur_flags, of the
+ * transcript every proof starts from (user transcript + dom-sep + scalar labels; zkp_b200_host.h produces it).
+ * instance_enc[ni][N][32], common_enc[nc][32], commitments[N][k][32], responses[N][m][32], rho_seed[32]: the
+ * weights are rho_(i,j) = bytes [16i,16i+16) of SHAKE256(rho_seed || le64(j)) (stand-in for thread_rng).
+ * coeff_out / points_out (optional, n = nc + (ni+k)*N rows of 32 bytes) receive the MSM inputs for parity tests.
+ * Returns ZKP_ERR_POINT for an identity or undecodable encoding (VerificationFailure), ZKP_ERR_SCALAR for a
+ * non-canonical response, ZKP_ERR_SIZE if the statement exceeds 40 point variables per kind or 64 constraints.  */
+int32_t zkp_batch_verify_proofs(zkp_ctx* ctx, const zkp_statement_desc* st, const uint32_t* prefix_state, size_t N,
+                                const uint8_t* instance_enc, const uint8_t* common_enc, const uint8_t* commitments,
+                                const uint8_t* responses, const uint8_t* rho_seed, int32_t* accept, int64_t* first_bad,
+                                uint8_t* coeff_out, uint8_t* points_out);
+
 /* Device-side micro-benchmark of the field multiplier variants (roofline calibration):
  * runs `iters` dependent multiplies (or squarings) per thread over a full grid and returns the measured
  * rate in operations per second in *ops_per_sec.  kind: 0 = fe_mul (8x32 saturated), 1 = fe_sq,

@@ -52,6 +52,15 @@ int32_t zkph_batch_verify(zkp_ctx* ctx, const zkph_statement* st, const uint8_t*
                           const uint8_t* responses, const uint8_t* rng_seed, size_t seed_len, int32_t threads,
                           uint8_t* coeff_out, uint8_t* points_out, double* host_seconds /* hashing+fold, may be NULL */);
 
+/* module::batch_verify with the per-proof work on the DEVICE (SURVEY.md 8f rows f1 + f2): the host hashes only the
+ * batch-wide transcript prefix (user transcript + dom-sep + scalar labels) and hands everything else to
+ * zkp_batch_verify_proofs.  Same inputs as zkph_batch_verify; the weights are derived per proof from rho_seed[32]
+ * (see zkp_b200.h), so the MSM inputs equal zkph_batch_verify's only when that one is given the same derivation.  */
+int32_t zkph_batch_verify_device(zkp_ctx* ctx, const zkph_statement* st, const uint8_t* transcript_label, size_t tl_len,
+                                 size_t N, const uint8_t* instance_enc, const uint8_t* common_enc,
+                                 const uint8_t* commitments, const uint8_t* responses, const uint8_t* rho_seed32,
+                                 uint8_t* coeff_out, uint8_t* points_out);
+
 /* N independent batchable proofs of one statement in three batched device calls (BASELINE configs[1]):
  * secrets[N][m][32], points[N][p][20 u64], entropy[N][32] -> encodings[N][p][32], commitments[N][k][32],
  * responses[N][m][32].  Per-proof results equal zkph_prove(batchable) with the same entropy.                 */

@@ -44,6 +44,19 @@ class SeededRng:
         return int.from_bytes(self.bytes(16), "little")
 
 
+class PerProofRng:
+    """The weight derivation of zkp_batch_verify_proofs: rho_(i,j) = bytes [16i, 16i+16) of
+    SHAKE256(seed32 || le64(j)) -- a parallel stand-in for rand::thread_rng (batch_verifier.rs:179)."""
+
+    def __init__(self, seed32: bytes):
+        assert len(seed32) == 32
+        self.seed = bytes(seed32)
+
+    def rho(self, i, j):
+        import hashlib
+        return int.from_bytes(hashlib.shake_256(self.seed + int(j).to_bytes(8, "little")).digest(16 * (i + 1))[16 * i:], "little")
+
+
 # ---- TranscriptProtocol (toolbox/mod.rs:165-228) ---------------------------------------------------------
 def domain_sep(t, label):
     t.append_message(b"dom-sep", b"schnorrzkp/1.0/ristretto255")
@@ -259,7 +272,7 @@ class BatchVerifier:
         inst = [[0] * N for _ in range(num_i + num_c)]
         for i, (lhs, rhs) in enumerate(self.constraints):
             for j in range(N):
-                rho = rng.u128()
+                rho = rng.rho(i, j) if hasattr(rng, "rho") else rng.u128()
                 inst[num_i + i][j] = (inst[num_i + i][j] - rho) % R.L
                 if lhs[0] == "S":
                     static_coeffs[lhs[1]] = (static_coeffs[lhs[1]] + rho * minus_c[j]) % R.L

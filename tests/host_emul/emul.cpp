@@ -5,6 +5,8 @@
 #include "../../zkp_b200/csrc/fe.cuh"
 #include "../../zkp_b200/csrc/ge.cuh"
 #include "../../zkp_b200/csrc/sc.cuh"
+#include "../../zkp_b200/csrc/hash.cuh"
+#include "../../zkp_b200/csrc/scl.cuh"
 using namespace zkp;
 
 static fe ld(const uint8_t* p) { fe r; memcpy(r.v, p, 32); return r; }
@@ -57,4 +59,29 @@ int emul_recode(int32_t* digits, uint8_t* k32, int* neg, const uint8_t* s32, int
   for (int w = 0; w < W; w++) { uint32_t mag, dn; sc_digit(mag, dn, carry, k, w, c); digits[w] = dn ? -(int32_t)mag : (int32_t)mag; }
   return (int)can | ((int)carry << 1);
 }
+
+// ---- device hashing / scalar arithmetic mod l (hash.cuh, scl.cuh) ----
+void emul_keccak(uint64_t* st) { keccak_f1600_dev(st); }
+// Merlin transcript on the device state machine: new(label); a sequence of appends; challenge
+void emul_transcript_test(uint8_t* out32) {
+  strobe_t s; for (int i = 0; i < 25; i++) s.st[i] = 0;
+  uint8_t* b = (uint8_t*)s.st; const uint8_t init[6] = {1, 168, 1, 0, 1, 96};
+  memcpy(b, init, 6); memcpy(b + 6, "STROBEv1.0.2", 12); keccak_f1600_dev(s.st);
+  s.pos = 0; s.pos_begin = 0; s.cur_flags = 0;
+  strobe_meta_ad(s, (const uint8_t*)"Merlin v1.0", 11, false);
+  transcript_append(s, (const uint8_t*)"dom-sep", 7, (const uint8_t*)"test protocol", 13);
+  transcript_append(s, (const uint8_t*)"step1", 5, (const uint8_t*)"some data", 9);
+  uint8_t ch[32], big[1024]; memset(big, 0x63, 1024);
+  for (int i = 0; i < 32; i++) {
+    transcript_challenge(s, (const uint8_t*)"challenge", 9, ch, 32);
+    transcript_append(s, (const uint8_t*)"bigdata", 7, big, 1024);
+    transcript_append(s, (const uint8_t*)"challengedata", 13, ch, 32);
+  }
+  memcpy(out32, ch, 32);
+}
+void emul_shake(uint8_t* out, uint32_t n, const uint8_t* msg, uint32_t len) { shake256_short(out, n, msg, len); }
+void emul_scl_mul(uint8_t* r, const uint8_t* a, const uint8_t* b) { scl x, y, z; memcpy(x.v, a, 32); memcpy(y.v, b, 32); scl_mul(z, x, y); memcpy(r, z.v, 32); }
+void emul_scl_add(uint8_t* r, const uint8_t* a, const uint8_t* b) { scl x, y, z; memcpy(x.v, a, 32); memcpy(y.v, b, 32); scl_add(z, x, y); memcpy(r, z.v, 32); }
+void emul_scl_sub(uint8_t* r, const uint8_t* a, const uint8_t* b) { scl x, y, z; memcpy(x.v, a, 32); memcpy(y.v, b, 32); scl_sub(z, x, y); memcpy(r, z.v, 32); }
+void emul_scl_wide(uint8_t* r, const uint8_t* a64) { scl z; scl_from_wide(z, a64); memcpy(r, z.v, 32); }
 }

@@ -132,6 +132,65 @@ def test_cmz_prove_many_and_batch_verify_match_oracle(engine):
         st.batch_verify(engine, badc, resp, b"CMZ", inst, comm, b"batch-rho")
 
 
+def test_batch_verify_device_front_end_matches_oracle(engine):
+    """zkp_batch_verify_proofs (transcripts, challenges, weights, coefficient fold on the GPU): the MSM inputs it
+    builds are byte-equal to the oracle's BatchVerifier with the same per-proof weight derivation."""
+    st, ost = PT.cmz10_statement(), OT.CMZ10
+    N = 6
+    secs, ptss = _cmz_instances(N, b"cmz-dev")
+    sec_arr = np.stack([sbytes([s[n] for n in st.secrets]) for s in secs])
+    pts_arr = np.array([[limbs(p[n]) for n in st.points] for p in ptss], dtype=np.uint64)
+    entropy = np.frombuffer(OT.SeededRng(b"entropy2").bytes(32 * N), dtype=np.uint8).reshape(N, 32)
+    enc, com, resp = st.prove_many(engine, b"CMZ", sec_arr, pts_arr, entropy, threads=2)
+    ni = len(st.instance)
+    inst = np.ascontiguousarray(enc[:, :ni].transpose(1, 0, 2))
+    comm = enc[0, ni:]
+    seed = bytes(range(32))
+    co, po = st.batch_verify_device(engine, com, resp, b"CMZ", inst, comm, seed, want_msm_inputs=True)
+    oproofs = [OT.BatchableProof([bytes(c) for c in com[j]], [int.from_bytes(bytes(r), "little") for r in resp[j]])
+               for j in range(N)]
+    oencs = {n: [bytes(enc[j, i]) for j in range(N)] for i, n in enumerate(st.instance)}
+    for i, n in enumerate(st.common):
+        oencs[n] = bytes(comm[i])
+    bv = ost.build_batch_verifier(N, [OM.Transcript(b"CMZ") for _ in range(N)], oencs)
+    oscal, opts = bv.batch_coeffs(oproofs, OT.PerProofRng(seed))
+    assert [bytes(p) for p in po] == opts
+    assert [bytes(c) for c in co] == [S.to_bytes(s) for s in oscal]
+    # verdicts
+    bad = resp.copy()
+    bad[2, 5, 0] ^= 1
+    with pytest.raises(PT.VerificationFailure):
+        st.batch_verify_device(engine, com, bad, b"CMZ", inst, comm, seed)
+    with pytest.raises(PT.VerificationFailure):           # wrong transcript label
+        st.batch_verify_device(engine, com, resp, b"CMY", inst, comm, seed)
+    badc = com.copy()
+    badc[4, 3] = 0                                          # identity commitment (mod.rs:215)
+    with pytest.raises(PT.VerificationFailure):
+        st.batch_verify_device(engine, badc, resp, b"CMZ", inst, comm, seed)
+    noncanon = resp.copy()
+    noncanon[1, 0] = 0xFF                                   # response >= l
+    with pytest.raises(PT.VerificationFailure):
+        st.batch_verify_device(engine, com, noncanon, b"CMZ", inst, comm, seed)
+    # DLEQ (static lhs-free statement with a static rhs point) through the same path
+    dst, odst = PT.dleq_statement(), OT.DLEQ
+    G = R.BASEPOINT
+    H = R.hash_from_bytes_sha512(R.compress(G))
+    Nd = 9
+    xs = [89327492234 + j for j in range(Nd)]
+    dl = np.array([[limbs(R.pt_mul(x, G)), limbs(R.pt_mul(x, H)), limbs(H), limbs(G)] for x in xs], dtype=np.uint64)
+    ent = np.frombuffer(OT.SeededRng(b"e3").bytes(32 * Nd), dtype=np.uint8).reshape(Nd, 32)
+    denc, dcom, dresp = dst.prove_many(engine, b"DLEQBatchTest", np.stack([sbytes([x]) for x in xs]), dl, ent, threads=2)
+    dinst = np.ascontiguousarray(denc[:, :3].transpose(1, 0, 2))
+    co, po = dst.batch_verify_device(engine, dcom, dresp, b"DLEQBatchTest", dinst, denc[0, 3:], seed, want_msm_inputs=True)
+    oproofs = [OT.BatchableProof([bytes(c) for c in dcom[j]], [int.from_bytes(bytes(r), "little") for r in dresp[j]])
+               for j in range(Nd)]
+    oencs = {"A": [bytes(e) for e in denc[:, 0]], "B": [bytes(e) for e in denc[:, 1]], "H": [bytes(e) for e in denc[:, 2]],
+             "G": bytes(denc[0, 3])}
+    bv = odst.build_batch_verifier(Nd, [OM.Transcript(b"DLEQBatchTest") for _ in range(Nd)], oencs)
+    oscal, opts = bv.batch_coeffs(oproofs, OT.PerProofRng(seed))
+    assert [bytes(p) for p in po] == opts and [bytes(c) for c in co] == [S.to_bytes(s) for s in oscal]
+
+
 def test_dleq_batch_golden(engine):
     """tests/zkp.rs:115-175 shape: 4 macro-form DLEQ proofs, golden fixture produced by the oracle."""
     kb = U.golden("toolbox_kat.json")["dleq_batch"]

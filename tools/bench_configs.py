@@ -137,8 +137,18 @@ def main():
         raise SystemExit("tampered CMZ batch accepted")
     except PT.VerificationFailure:
         pass
+    seed = bytes(range(32))
+    st.batch_verify_device(eng, com[:64], resp[:64], b"CMZ", np.ascontiguousarray(inst[:, :64]), enc[0, ni:], seed)
+    t_dev, _ = timed(lambda: st.batch_verify_device(eng, com, resp, b"CMZ", inst, enc[0, ni:], seed), 2)
+    try:
+        st.batch_verify_device(eng, com, bad, b"CMZ", inst, enc[0, ni:], seed)
+        raise SystemExit("tampered CMZ batch accepted by the device front end")
+    except PT.VerificationFailure:
+        pass
     res["cmz_batch_verify_real_proofs"] = {"proofs": N, "total_s": t_bv, "host_hash_and_fold_s": hs,
-                                           "proofs_per_s_end_to_end_incl_host": N / t_bv}
+                                           "proofs_per_s_end_to_end_incl_host": N / t_bv,
+                                           "device_front_end_total_s": t_dev,
+                                           "proofs_per_s_device_front_end": N / t_dev}
     print("cmz batch verify (real proofs)", res["cmz_batch_verify_real_proofs"], flush=True)
 
     # ---- configs[2]: DLEQ batch verify 2^20 -------------------------------------------------------------------
@@ -180,7 +190,10 @@ def main():
     ms = e0.elapsed_time(e1) / 3
     r = d_res.cpu().numpy()
     assert tuple(np.frombuffer(r[32:40].tobytes(), dtype=np.int32)) == (0, 1)
+    st.batch_verify_device(eng, com[:64], resp[:64], b"DLEQBatchTest", np.ascontiguousarray(inst[:, :64]), enc2[0, 3:], bytes(32))
+    t_dev, _ = timed(lambda: st.batch_verify_device(eng, com, resp, b"DLEQBatchTest", inst, enc2[0, 3:], bytes(range(32))), 2)
     res["config2_dleq_batch_verify"] = {"proofs": N, "msm_terms": int(co.shape[0]), "msm_device_ms": ms,
+                                        "device_front_end_total_s": t_dev, "proofs_per_s_device_front_end": N / t_dev,
                                         "proofs_per_s_msm_device": N / (ms * 1e-3),
                                         "whole_host_path_s": t_bv, "host_hash_and_fold_s": hs,
                                         "proofs_per_s_incl_host": N / t_bv, "prove_many_s": t_prove}

@@ -12,6 +12,7 @@
 #include "kernels.cuh"
 #include "small_msm.cuh"
 #include "bench_fe.cuh"
+#include "bv_kernels.cuh"
 
 using namespace zkp;
 
@@ -31,7 +32,7 @@ struct zkp_ctx {
   std::string err;
   // workspace (grown on demand, reused across calls)
   devbuf in_scalars, in_points, niels, hist, offs, cursor, sorted, buckets, lvlT[2], lvlU, usum, flags, result,
-      aux0, aux1, aux2, sk0, sk1, tables, items, partials, multi;
+      aux0, aux1, aux2, sk0, sk1, tables, items, partials, multi, bv_com, bv_resp, bv_part, bv_misc;
   void* h_result = nullptr;  // pinned, 64 bytes
   // optional per-stage timing of the vartime MSM ("profile" option): events around each stage
   int profile = 0;
@@ -139,7 +140,8 @@ extern "C" void zkp_ctx_destroy(zkp_ctx* ctx) {
   devbuf* bufs[] = {&ctx->in_scalars, &ctx->in_points, &ctx->niels, &ctx->hist, &ctx->offs, &ctx->cursor,
                     &ctx->sorted, &ctx->buckets, &ctx->lvlT[0], &ctx->lvlT[1], &ctx->lvlU, &ctx->usum,
                     &ctx->flags, &ctx->result, &ctx->aux0, &ctx->aux1, &ctx->aux2, &ctx->sk0, &ctx->sk1,
-                    &ctx->tables, &ctx->items, &ctx->partials, &ctx->multi};
+                    &ctx->tables, &ctx->items, &ctx->partials, &ctx->multi, &ctx->bv_com, &ctx->bv_resp, &ctx->bv_part,
+                    &ctx->bv_misc};
   for (devbuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (ctx->h_result) cudaFreeHost(ctx->h_result);
@@ -520,6 +522,149 @@ extern "C" int32_t zkp_batch_verify(zkp_ctx* ctx, const uint8_t* static_coeffs, 
   hseg ss[2] = {{static_coeffs, num_s}, {instance_coeffs, n_inst}};
   hseg ps[2] = {{static_points, num_s}, {instance_points, n_inst}};
   int32_t r = msm_from_host(ctx, ss, ps, 2, n, (msm_result*)ctx->result.p);
+  if (r != ZKP_OK) return r;
+  int32_t ident = 0;
+  r = fetch_result(ctx, nullptr, &ident, first_bad);
+  if (r != ZKP_OK) return r;
+  *accept = ident;
+  return ZKP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// batch verification from proofs: transcripts, challenges, weights and coefficient fold on the device
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int32_t zkp_batch_verify_proofs(zkp_ctx* ctx, const zkp_statement_desc* sd, const uint32_t* prefix_state,
+                                           size_t N, const uint8_t* instance_enc, const uint8_t* common_enc,
+                                           const uint8_t* commitments, const uint8_t* responses,
+                                           const uint8_t* rho_seed, int32_t* accept, int64_t* first_bad,
+                                           uint8_t* coeff_out, uint8_t* points_out) {
+  if (!ctx || !sd || !prefix_state || !accept || !rho_seed) return ZKP_ERR_SIZE;
+  *accept = 0;
+  if (first_bad) *first_bad = -1;
+  const int m = sd->m, ni = sd->ni, nc = sd->nc, k = sd->k;
+  if (m < 0 || ni < 0 || nc < 0 || k < 0 || ni > ZKP_BV_MAX_VARS || nc > ZKP_BV_MAX_VARS || k > ZKP_BV_MAX_CONS) {
+    ctx->err = "statement too large for the device front end";
+    return ZKP_ERR_SIZE;
+  }
+  if (N && ((ni && !instance_enc) || (k && !commitments) || (m && !responses))) return ZKP_ERR_SIZE;
+  if (nc && !common_enc) return ZKP_ERR_SIZE;
+  for (int s0 = 0; s0 < nc; s0++) {   // identity encoding of a static point fails at allocation (toolbox/mod.rs:191)
+    uint8_t o = 0;
+    for (int b = 0; b < 32; b++) o |= common_enc[32 * s0 + b];
+    if (!o && N) return ZKP_ERR_POINT;
+  }
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  // ---- flatten the statement: label offsets, transcript script, constraint arrays ----
+  std::vector<uint32_t> loff, llen;
+  const char* lp = sd->labels;
+  std::vector<uint8_t> pool;
+  for (int i = 0; i < ni + nc; i++) {
+    size_t len = strlen(lp);
+    loff.push_back((uint32_t)pool.size());
+    llen.push_back((uint32_t)len);
+    pool.insert(pool.end(), lp, lp + len);
+    lp += len + 1;
+  }
+  const int n_terms = k ? sd->cons_off[k] : 0;
+  std::vector<bv_op> ops;
+  for (int i = 0; i < ni; i++) ops.push_back(bv_op{0u, loff[i], llen[i], (uint32_t)i});
+  for (int i = 0; i < nc; i++) ops.push_back(bv_op{1u, loff[ni + i], llen[ni + i], (uint32_t)i});
+  std::vector<int32_t> lhs_kind(k), lhs_idx(k), tkind(n_terms), tidx(n_terms);
+  for (int c = 0; c < k; c++) {
+    const int l = sd->lhs[c];
+    if (l < 0 || l >= ni + nc) return ZKP_ERR_SIZE;
+    lhs_kind[c] = l >= ni;
+    lhs_idx[c] = l >= ni ? l - ni : l;
+    ops.push_back(bv_op{2u, loff[l], llen[l], (uint32_t)c});
+  }
+  for (int q = 0; q < n_terms; q++) {
+    const int pnt = sd->term_point[q];
+    if (pnt < 0 || pnt >= ni + nc || sd->term_scalar[q] < 0 || sd->term_scalar[q] >= m) return ZKP_ERR_SIZE;
+    tkind[q] = pnt >= ni;
+    tidx[q] = pnt >= ni ? pnt - ni : pnt;
+  }
+  // one small device blob: prefix(53 w) | rho_seed(32 B) | pool | ops | int arrays
+  auto pad16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+  const size_t o_prefix = 0, o_seed = pad16(53 * 4), o_pool = o_seed + 32, o_ops = pad16(o_pool + pool.size()),
+               o_lk = pad16(o_ops + ops.size() * sizeof(bv_op)), o_li = pad16(o_lk + k * 4), o_co = pad16(o_li + k * 4),
+               o_ts = pad16(o_co + (k + 1) * 4), o_tk = pad16(o_ts + n_terms * 4), o_ti = pad16(o_tk + n_terms * 4),
+               blob_sz = pad16(o_ti + n_terms * 4) + 16;
+  std::vector<uint8_t> blob(blob_sz, 0);
+  memcpy(&blob[o_prefix], prefix_state, 53 * 4);
+  memcpy(&blob[o_seed], rho_seed, 32);
+  if (!pool.empty()) memcpy(&blob[o_pool], pool.data(), pool.size());
+  if (!ops.empty()) memcpy(&blob[o_ops], ops.data(), ops.size() * sizeof(bv_op));
+  if (k) {
+    memcpy(&blob[o_lk], lhs_kind.data(), k * 4);
+    memcpy(&blob[o_li], lhs_idx.data(), k * 4);
+    memcpy(&blob[o_co], sd->cons_off, (k + 1) * 4);
+  }
+  if (n_terms) {
+    memcpy(&blob[o_ts], sd->term_scalar, n_terms * 4);
+    memcpy(&blob[o_tk], tkind.data(), n_terms * 4);
+    memcpy(&blob[o_ti], tidx.data(), n_terms * 4);
+  }
+  const size_t rows = (size_t)ni + k, n = (size_t)nc + rows * N;
+  ENSURE(ctx, ctx->bv_misc, blob_sz);
+  ENSURE(ctx, ctx->in_scalars, n * 32 + 32);
+  ENSURE(ctx, ctx->in_points, n * 32 + 32);
+  ENSURE(ctx, ctx->bv_com, (size_t)k * N * 32 + 32);
+  ENSURE(ctx, ctx->bv_resp, (size_t)m * N * 32 + 32);
+  ENSURE(ctx, ctx->result, 64);
+  ENSURE(ctx, ctx->flags, 16);
+  const unsigned nblocks = (unsigned)((N + 127) / 128);
+  ENSURE(ctx, ctx->bv_part, (size_t)(nblocks ? nblocks : 1) * (nc ? nc : 1) * 32);
+  uint8_t* dm = (uint8_t*)ctx->bv_misc.p;
+  CUDA_TRY(ctx, cudaMemcpyAsync(dm, blob.data(), blob_sz, cudaMemcpyHostToDevice, st));
+  uint8_t* dpts = (uint8_t*)ctx->in_points.p;
+  if (nc) CUDA_TRY(ctx, cudaMemcpyAsync(dpts, common_enc, (size_t)nc * 32, cudaMemcpyHostToDevice, st));
+  if (ni && N)
+    CUDA_TRY(ctx, cudaMemcpyAsync(dpts + (size_t)nc * 32, instance_enc, (size_t)ni * N * 32, cudaMemcpyHostToDevice, st));
+  if (k && N) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->bv_com.p, commitments, (size_t)k * N * 32, cudaMemcpyHostToDevice, st));
+  if (m && N) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->bv_resp.p, responses, (size_t)m * N * 32, cudaMemcpyHostToDevice, st));
+  k_init_flags<<<1, 1, 0, st>>>((int*)ctx->flags.p);
+  LAUNCH_CHECK(ctx);
+  if (N) {
+    bv_desc d;
+    d.m = m; d.ni = ni; d.nc = nc; d.k = k; d.n_ops = (int)ops.size(); d.n_terms = n_terms;
+    d.ops = (const bv_op*)(dm + o_ops);
+    d.labels = dm + o_pool;
+    d.lhs_kind = (const int32_t*)(dm + o_lk);
+    d.lhs_idx = (const int32_t*)(dm + o_li);
+    d.cons_off = (const int32_t*)(dm + o_co);
+    d.term_scalar = (const int32_t*)(dm + o_ts);
+    d.term_pkind = (const int32_t*)(dm + o_tk);
+    d.term_pidx = (const int32_t*)(dm + o_ti);
+    k_bv_prepare<<<nblocks, 128, 0, st>>>(d, (const uint32_t*)(dm + o_prefix), N, dpts + (size_t)nc * 32, dpts,
+                                          (const uint8_t*)ctx->bv_com.p, (const uint8_t*)ctx->bv_resp.p, dm + o_seed,
+                                          (uint8_t*)ctx->in_scalars.p, dpts, (uint8_t*)ctx->bv_part.p, nullptr,
+                                          (int*)ctx->flags.p);
+    LAUNCH_CHECK(ctx);
+  }
+  if (nc) {
+    if (N) {
+      k_bv_static_sum<<<1, 256, 0, st>>>((const uint8_t*)ctx->bv_part.p, (int)nblocks, nc, (uint8_t*)ctx->in_scalars.p);
+      LAUNCH_CHECK(ctx);
+    } else {
+      CUDA_TRY(ctx, cudaMemsetAsync(ctx->in_scalars.p, 0, (size_t)nc * 32, st));
+    }
+  }
+  // front-end failures (identity encodings, non-canonical responses) are reported before the MSM result
+  int hflags[4];
+  CUDA_TRY(ctx, cudaMemcpyAsync(hflags, ctx->flags.p, 16, cudaMemcpyDeviceToHost, st));
+  if (coeff_out) CUDA_TRY(ctx, cudaMemcpyAsync(coeff_out, ctx->in_scalars.p, n * 32, cudaMemcpyDeviceToHost, st));
+  if (points_out) CUDA_TRY(ctx, cudaMemcpyAsync(points_out, ctx->in_points.p, n * 32, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  if (hflags[0] != 0x7fffffff) {
+    if (first_bad) *first_bad = hflags[0];
+    return ZKP_ERR_POINT;
+  }
+  if (hflags[1] != 0x7fffffff) {
+    if (first_bad) *first_bad = hflags[1];
+    return ZKP_ERR_SCALAR;
+  }
+  int32_t r = msm_vartime_launch(ctx, ctx->in_scalars.p, ctx->in_points.p, n, (msm_result*)ctx->result.p);
   if (r != ZKP_OK) return r;
   int32_t ident = 0;
   r = fetch_result(ctx, nullptr, &ident, first_bad);

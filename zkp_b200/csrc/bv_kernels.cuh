@@ -1,0 +1,181 @@
+// BatchVerifier::verify_batchable front end on the device (SURVEY.md section 8f rows f1 + f2, "next"):
+// per-proof Merlin transcripts, challenges, random weights and the coefficient fold of
+// /root/reference/src/toolbox/batch_verifier.rs:152-206, producing exactly the scalar / point vectors the reference
+// feeds to optional_multiscalar_mul at :219-228 -- which then run through the same MSM kernels (kernels.cuh).
+// One thread per proof.  The statement arrives as flat arrays (the define_proof! expansion, macros.rs:336-370).
+#pragma once
+#include "hash.cuh"
+#include "kernels.cuh"
+#include "scl.cuh"
+
+namespace zkp {
+
+#define ZKP_BV_MAX_VARS 40   // instance or static point variables per statement (CMZ: 13 / 12)
+#define ZKP_BV_MAX_CONS 64   // constraints per statement (CMZ: 11)
+
+struct bv_op {         // one recorded transcript operation after the batch-wide prefix
+  uint32_t kind;       // 0 instance point, 1 static point, 2 blinding commitment
+  uint32_t label_off, label_len;
+  uint32_t idx;        // variable / constraint index
+};
+
+struct bv_desc {       // device copy of the statement
+  int m, ni, nc, k, n_ops, n_terms;
+  const bv_op* ops;                 // [n_ops]
+  const uint8_t* labels;            // label byte pool
+  const int32_t* lhs_kind;          // [k] 0 instance / 1 static
+  const int32_t* lhs_idx;           // [k]
+  const int32_t* cons_off;          // [k+1]
+  const int32_t* term_scalar;       // [n_terms]
+  const int32_t* term_pkind;        // [n_terms]
+  const int32_t* term_pidx;         // [n_terms]
+};
+
+__device__ __forceinline__ void load32(uint8_t* dst, const uint8_t* src) {
+  const uint4* p = (const uint4*)src;
+  uint4 a = __ldg(p), b = __ldg(p + 1);
+  uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    dst[4 * i] = (uint8_t)w[i]; dst[4 * i + 1] = (uint8_t)(w[i] >> 8);
+    dst[4 * i + 2] = (uint8_t)(w[i] >> 16); dst[4 * i + 3] = (uint8_t)(w[i] >> 24);
+  }
+}
+__device__ __forceinline__ void load_scl(scl& s, const uint8_t* src) {
+  const uint4* p = (const uint4*)src;
+  uint4 a = __ldg(p), b = __ldg(p + 1);
+  s.v[0] = a.x; s.v[1] = a.y; s.v[2] = a.z; s.v[3] = a.w; s.v[4] = b.x; s.v[5] = b.y; s.v[6] = b.z; s.v[7] = b.w;
+}
+__device__ __forceinline__ void store_scl(uint8_t* dst, const scl& s) {
+  uint4* p = (uint4*)dst;
+  p[0] = make_uint4(s.v[0], s.v[1], s.v[2], s.v[3]);
+  p[1] = make_uint4(s.v[4], s.v[5], s.v[6], s.v[7]);
+}
+
+// Per proof j: replay the transcript, derive the challenge, draw the weights, fold the coefficients.
+//   prefix        strobe state shared by all proofs (user transcript + dom-sep + scalar labels), 53 words
+//   instance_enc  [ni][N][32]   commitments [N][k][32]   responses [N][m][32]   common_enc [nc][32]
+//   msm_scalars   [nc + (ni+k)*N][32]  (static part written by k_bv_static_sum)
+//   msm_points    [nc + (ni+k)*N][32]  (static + instance rows are copied by the host; commitment rows written here)
+//   static_part   [gridDim.x][nc][32]  per-block partial sums of the static coefficients
+//   flags[2]      set to the first proof index with an identity encoding or a non-canonical response
+__global__ void __launch_bounds__(128) k_bv_prepare(bv_desc d, const uint32_t* __restrict__ prefix, size_t N,
+                                                    const uint8_t* __restrict__ instance_enc,
+                                                    const uint8_t* __restrict__ common_enc,
+                                                    const uint8_t* __restrict__ commitments,
+                                                    const uint8_t* __restrict__ responses,
+                                                    const uint8_t* __restrict__ rho_seed, uint8_t* __restrict__ msm_scalars,
+                                                    uint8_t* __restrict__ msm_points, uint8_t* __restrict__ static_part,
+                                                    uint8_t* __restrict__ minus_c_out, int* __restrict__ flags) {
+  __shared__ scl red[128];
+  const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = j < N;
+  scl inst[ZKP_BV_MAX_VARS], stat[ZKP_BV_MAX_VARS];
+  for (int i = 0; i < d.ni; i++) scl_zero(inst[i]);
+  for (int i = 0; i < d.nc; i++) scl_zero(stat[i]);
+  if (live) {
+    // ---- transcript (batch_verifier.rs:115-134 instance points, :100-112 static points, :152-160 commitments) ----
+    strobe_t s;
+#pragma unroll
+    for (int i = 0; i < 25; i++) s.st[i] = (uint64_t)prefix[2 * i] | ((uint64_t)prefix[2 * i + 1] << 32);
+    s.pos = prefix[50]; s.pos_begin = prefix[51]; s.cur_flags = prefix[52];
+    uint8_t enc[32];
+    bool bad = false;
+    for (int o = 0; o < d.n_ops; o++) {
+      const bv_op op = d.ops[o];
+      const uint8_t* src = op.kind == 0 ? instance_enc + ((size_t)op.idx * N + j) * 32
+                         : op.kind == 1 ? common_enc + (size_t)op.idx * 32
+                                        : commitments + ((size_t)j * d.k + op.idx) * 32;
+      load32(enc, src);
+      uint32_t any = 0;
+#pragma unroll
+      for (int b = 0; b < 32; b++) any |= enc[b];
+      if (any == 0) bad = true;   // identity encoding (toolbox/mod.rs:191, :215)
+      if (op.kind == 2) {
+        transcript_append(s, (const uint8_t*)"blindcom", 8, d.labels + op.label_off, op.label_len);
+        uint4* dst = (uint4*)(msm_points + ((size_t)d.nc + (size_t)(d.ni + op.idx) * N + j) * 32);
+        const uint4* s4 = (const uint4*)src;
+        dst[0] = __ldg(s4);
+        dst[1] = __ldg(s4 + 1);
+      } else {
+        transcript_append(s, (const uint8_t*)"ptvar", 5, d.labels + op.label_off, op.label_len);
+      }
+      transcript_append(s, (const uint8_t*)"val", 3, enc, 32);
+    }
+    if (bad) atomicMin(&flags[0], (int)j);
+    uint8_t wide[64];
+    transcript_challenge(s, (const uint8_t*)"chal", 4, wide, 64);
+    scl c, minus_c;
+    scl_from_wide(c, wide);
+    scl_neg(minus_c, c);
+    if (minus_c_out) store_scl(minus_c_out + j * 32, minus_c);
+    // ---- weights: rho_i = bytes [16 i, 16 i + 16) of SHAKE256(seed || le64(j))  (stand-in for thread_rng, :179) ----
+    uint8_t msg[40];
+#pragma unroll
+    for (int b = 0; b < 32; b++) msg[b] = rho_seed[b];
+#pragma unroll
+    for (int b = 0; b < 8; b++) msg[32 + b] = (uint8_t)((unsigned long long)j >> (8 * b));
+    uint8_t all[16 * ZKP_BV_MAX_CONS];
+    shake256_short(all, (uint32_t)(16 * d.k), msg, 40);
+    // ---- coefficient fold (batch_verifier.rs:176-206) ----
+    for (int i = 0; i < d.k; i++) {
+      scl rho;
+#pragma unroll
+      for (int w = 0; w < 4; w++)
+        rho.v[w] = (uint32_t)all[16 * i + 4 * w] | ((uint32_t)all[16 * i + 4 * w + 1] << 8) |
+                   ((uint32_t)all[16 * i + 4 * w + 2] << 16) | ((uint32_t)all[16 * i + 4 * w + 3] << 24);
+      rho.v[4] = rho.v[5] = rho.v[6] = rho.v[7] = 0;
+      scl t;
+      scl_neg(t, rho);   // instance_coeffs[(num_i + i, j)] -= rho
+      store_scl(msm_scalars + ((size_t)d.nc + (size_t)(d.ni + i) * N + j) * 32, t);
+      scl_mul(t, rho, minus_c);
+      if (d.lhs_kind[i]) scl_add(stat[d.lhs_idx[i]], stat[d.lhs_idx[i]], t);
+      else scl_add(inst[d.lhs_idx[i]], inst[d.lhs_idx[i]], t);
+      for (int q = d.cons_off[i]; q < d.cons_off[i + 1]; q++) {
+        scl resp;
+        load_scl(resp, responses + ((size_t)j * d.m + d.term_scalar[q]) * 32);
+        if (!scl_is_canonical(resp.v)) atomicMin(&flags[1], (int)j);
+        scl_mul(t, rho, resp);
+        const int pi = d.term_pidx[q];
+        if (d.term_pkind[q]) scl_add(stat[pi], stat[pi], t);
+        else scl_add(inst[pi], inst[pi], t);
+      }
+    }
+    for (int i = 0; i < d.ni; i++) store_scl(msm_scalars + ((size_t)d.nc + (size_t)i * N + j) * 32, inst[i]);
+  }
+  // ---- block partial sums of the static coefficients ----
+  for (int sidx = 0; sidx < d.nc; sidx++) {
+    red[threadIdx.x] = stat[sidx];
+    __syncthreads();
+    for (int off = 64; off >= 1; off >>= 1) {
+      if ((int)threadIdx.x < off) scl_add(red[threadIdx.x], red[threadIdx.x], red[threadIdx.x + off]);
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) store_scl(static_part + ((size_t)blockIdx.x * d.nc + sidx) * 32, red[0]);
+    __syncthreads();
+  }
+}
+
+// static_coeffs[s] = sum over blocks of static_part[b][s]; one block, thread per (strided) partial
+__global__ void __launch_bounds__(256) k_bv_static_sum(const uint8_t* __restrict__ static_part, int nblocks, int nc,
+                                                       uint8_t* __restrict__ msm_scalars) {
+  __shared__ scl red[256];
+  for (int sidx = 0; sidx < nc; sidx++) {
+    scl acc, t;
+    scl_zero(acc);
+    for (int b = threadIdx.x; b < nblocks; b += blockDim.x) {
+      load_scl(t, static_part + ((size_t)b * nc + sidx) * 32);
+      scl_add(acc, acc, t);
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int off = 128; off >= 1; off >>= 1) {
+      if ((int)threadIdx.x < off) scl_add(red[threadIdx.x], red[threadIdx.x], red[threadIdx.x + off]);
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) store_scl(msm_scalars + (size_t)sidx * 32, red[0]);
+    __syncthreads();
+  }
+}
+
+}  // namespace zkp

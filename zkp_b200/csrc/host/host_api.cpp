@@ -221,6 +221,49 @@ extern "C" int32_t zkph_batch_verify(zkp_ctx* ctx, const zkph_statement* h, cons
   return accept ? PROOF_OK : VerificationFailure;
 }
 
+extern "C" int32_t zkph_batch_verify_device(zkp_ctx* ctx, const zkph_statement* h, const uint8_t* tl, size_t tl_len,
+                                            size_t N, const uint8_t* instance_enc, const uint8_t* common_enc,
+                                            const uint8_t* commitments, const uint8_t* responses,
+                                            const uint8_t* rho_seed32, uint8_t* coeff_out, uint8_t* points_out) {
+  const Statement& st = h->st;
+  // batch-wide transcript prefix: Transcript::new(label), dom-sep, scalar labels (macros.rs:346-350)
+  Transcript t(tl, tl_len);
+  domain_sep(t, st.label);
+  for (auto& s : st.secrets) append_scalar_var(t, s);
+  uint32_t prefix[53];
+  t.export_state(prefix);
+  std::string labels;
+  for (auto& s : st.instance) labels += s + std::string(1, '\0');
+  for (auto& s : st.common) labels += s + std::string(1, '\0');
+  std::vector<int32_t> lhs, off(1, 0), ts, tp;
+  for (auto& c : st.constraints) {
+    lhs.push_back(c.first);
+    for (auto& term : c.second) {
+      ts.push_back(term.first);
+      tp.push_back(term.second);
+    }
+    off.push_back((int32_t)ts.size());
+  }
+  zkp_statement_desc d;
+  d.m = (int32_t)st.secrets.size();
+  d.ni = (int32_t)st.instance.size();
+  d.nc = (int32_t)st.common.size();
+  d.k = (int32_t)st.constraints.size();
+  d.labels = labels.c_str();
+  d.lhs = lhs.data();
+  d.cons_off = off.data();
+  d.term_scalar = ts.data();
+  d.term_point = tp.data();
+  int32_t accept = 0;
+  int64_t bad = -1;
+  int32_t rc = zkp_batch_verify_proofs(ctx, &d, prefix, N, instance_enc, common_enc, commitments, responses, rho_seed32,
+                                       &accept, &bad, coeff_out, points_out);
+  if (rc == ZKP_ERR_POINT || rc == ZKP_ERR_SCALAR) return VerificationFailure;
+  if (rc == ZKP_ERR_SIZE) return BatchSizeMismatch;
+  if (rc != ZKP_OK) return EngineFailure;
+  return accept ? PROOF_OK : VerificationFailure;
+}
+
 extern "C" int32_t zkph_prove_many(zkp_ctx* ctx, const zkph_statement* h, const uint8_t* tl, size_t tl_len, size_t N,
                                    const uint8_t* secrets, const uint64_t* points, const uint8_t* entropy,
                                    int32_t threads, uint8_t* encodings, uint8_t* commitments, uint8_t* responses) {

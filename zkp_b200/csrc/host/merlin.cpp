@@ -51,6 +51,15 @@ Strobe128::Strobe128(const uint8_t* protocol_label, size_t len) {
   pos_ = pos_begin_ = cur_flags_ = 0;
   meta_ad(protocol_label, len, false);
 }
+void Strobe128::export_state(uint32_t out[53]) const {
+  for (int i = 0; i < 25; i++) {
+    out[2 * i] = (uint32_t)st_.lanes[i];
+    out[2 * i + 1] = (uint32_t)(st_.lanes[i] >> 32);
+  }
+  out[50] = pos_;
+  out[51] = pos_begin_;
+  out[52] = cur_flags_;
+}
 void Strobe128::run_f() {
   st_.bytes[pos_] ^= pos_begin_;
   st_.bytes[pos_ + 1] ^= 0x04;

@@ -21,6 +21,8 @@ class Strobe128 {
   void ad(const uint8_t* data, size_t len, bool more);
   void prf(uint8_t* out, size_t len, bool more);
   void key(const uint8_t* data, size_t len, bool more);
+  // 53 little-endian words: 25 lanes as (lo, hi), pos, pos_begin, cur_flags -- the layout zkp_batch_verify_proofs takes
+  void export_state(uint32_t out[53]) const;
 
  private:
   static const int R = 166;
@@ -64,6 +66,7 @@ class Transcript {
   void append_message(const uint8_t* label, size_t llen, const uint8_t* msg, size_t mlen);
   void challenge_bytes(const uint8_t* label, size_t llen, uint8_t* dest, size_t dlen);
   TranscriptRngBuilder build_rng() const { return TranscriptRngBuilder(strobe_); }
+  void export_state(uint32_t out[53]) const { strobe_.export_state(out); }
 
  private:
   Strobe128 strobe_;

@@ -1,0 +1,190 @@
+// Scalars mod l = 2^252 + c on the device (8 x 32-bit limbs, always fully reduced).
+//
+// SURVEY.md section 8f-2 ("next" row): the coefficient fold of /root/reference/src/toolbox/batch_verifier.rs:173-206 and
+// the challenge reduction of toolbox/mod.rs:223-227 (Scalar::from_bytes_mod_order_wide, curve25519-dalek scalar.rs
+// [ext]) next to the MSM.  Not a hot loop (42 multiplications per CMZ proof against ~7.5*10^5 integer instructions
+// of point arithmetic), so it is plain portable C: the same source runs in the host-emulation tests.
+#pragma once
+#include <stdint.h>
+#include "fe.cuh"
+
+namespace zkp {
+
+struct scl { uint32_t v[8]; };
+
+// c = l - 2^252 (125 bits), little-endian limbs
+ZKP_DEV uint32_t scl_c(int i) {
+  const uint32_t C[4] = {0x5cf5d3edu, 0x5812631au, 0xa2f79cd6u, 0x14def9deu};
+  return C[i];
+}
+ZKP_DEV uint32_t scl_l(int i) {
+  const uint32_t L[8] = {0x5cf5d3edu, 0x5812631au, 0xa2f79cd6u, 0x14def9deu, 0, 0, 0, 0x10000000u};
+  return L[i];
+}
+
+// r[0..n) = a - b, returns borrow
+template <int N>
+ZKP_DEV uint32_t limbs_sub(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  uint64_t br = 0;
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    uint64_t d = (uint64_t)a[i] - b[i] - br;
+    r[i] = (uint32_t)d;
+    br = (d >> 32) & 1;
+  }
+  return (uint32_t)br;
+}
+template <int N>
+ZKP_DEV uint32_t limbs_add(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  uint64_t c = 0;
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    uint64_t s = (uint64_t)a[i] + b[i] + c;
+    r[i] = (uint32_t)s;
+    c = s >> 32;
+  }
+  return (uint32_t)c;
+}
+// r[0..NA+NB) = a * b
+template <int NA, int NB>
+ZKP_DEV void limbs_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+#pragma unroll
+  for (int i = 0; i < NA + NB; i++) r[i] = 0;
+#pragma unroll
+  for (int i = 0; i < NA; i++) {
+    uint64_t carry = 0;
+#pragma unroll
+    for (int j = 0; j < NB; j++) {
+      uint64_t p = (uint64_t)a[i] * b[j] + r[i + j] + carry;
+      r[i + j] = (uint32_t)p;
+      carry = p >> 32;
+    }
+    r[i + NB] = (uint32_t)carry;
+  }
+}
+
+// conditional r -= l while r >= l (r < 4l on entry), r has 8 limbs (+ optional 9th handled by caller)
+ZKP_DEV void scl_final_sub(uint32_t* r) {
+  uint32_t l[8], t[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) l[i] = scl_l(i);
+#pragma unroll 1
+  for (int k = 0; k < 4; k++) {
+    uint32_t br = limbs_sub<8>(t, r, l);
+    uint32_t keep = 0u - br;  // borrow -> keep r
+#pragma unroll
+    for (int i = 0; i < 8; i++) r[i] = (r[i] & keep) | (t[i] & ~keep);
+  }
+}
+
+// x (16 limbs, any 512-bit value) mod l
+ZKP_DEV void scl_reduce512(scl& out, const uint32_t* x) {
+  // x = xh * 2^252 + xl
+  uint32_t xl[8], xh[9];
+#pragma unroll
+  for (int i = 0; i < 8; i++) xl[i] = x[i];
+  xl[7] &= 0x0fffffffu;
+#pragma unroll
+  for (int i = 0; i < 9; i++) {
+    uint32_t lo = x[7 + i] >> 28;
+    uint32_t hi = (7 + i + 1 < 16) ? (x[8 + i] << 4) : 0u;
+    xh[i] = lo | hi;
+  }
+  uint32_t c[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) c[i] = scl_c(i);
+  // y = c * xh (13 limbs, < 2^385) = yh * 2^252 + yl
+  uint32_t y[13];
+  limbs_mul<9, 4>(y, xh, c);
+  uint32_t yl[8], yh[5];
+#pragma unroll
+  for (int i = 0; i < 8; i++) yl[i] = y[i];
+  yl[7] &= 0x0fffffffu;
+#pragma unroll
+  for (int i = 0; i < 5; i++) {
+    uint32_t lo = y[7 + i] >> 28;
+    uint32_t hi = (8 + i < 13) ? (y[8 + i] << 4) : 0u;
+    yh[i] = lo | hi;
+  }
+  // z = c * yh (9 limbs, < 2^258) = zh * 2^252 + zl, zh < 2^6
+  uint32_t z[9];
+  limbs_mul<5, 4>(z, yh, c);
+  uint32_t zl[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) zl[i] = z[i];
+  zl[7] &= 0x0fffffffu;
+  uint32_t zh = (z[7] >> 28) | (z[8] << 4);
+  // w = c * zh (5 limbs, < 2^131)
+  uint32_t w[8], zh1[1] = {zh}, w5[5];
+  limbs_mul<1, 4>(w5, zh1, c);
+#pragma unroll
+  for (int i = 0; i < 8; i++) w[i] = i < 5 ? w5[i] : 0u;
+  // x = xl - yl + zl - w  (mod l); every term < 2^252 < l: r = (xl + zl) + 2l - yl - w  in [0, 4l)
+  uint32_t r[8], l2[8];
+  limbs_add<8>(r, xl, zl);  // < 2^253
+  uint64_t cy = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {  // 2l
+    uint64_t s = ((uint64_t)scl_l(i) << 1) + cy;
+    l2[i] = (uint32_t)s;
+    cy = s >> 32;
+  }
+  limbs_add<8>(r, r, l2);   // < 2^253 + 2^254 < 2^255
+  limbs_sub<8>(r, r, yl);
+  limbs_sub<8>(r, r, w);    // still >= 0: 2l > yl + w
+  scl_final_sub(r);
+#pragma unroll
+  for (int i = 0; i < 8; i++) out.v[i] = r[i];
+}
+
+ZKP_DEV void scl_from_wide(scl& out, const uint8_t* b64) {
+  uint32_t x[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++)
+    x[i] = (uint32_t)b64[4 * i] | ((uint32_t)b64[4 * i + 1] << 8) | ((uint32_t)b64[4 * i + 2] << 16) |
+           ((uint32_t)b64[4 * i + 3] << 24);
+  scl_reduce512(out, x);
+}
+ZKP_DEV void scl_mul(scl& r, const scl& a, const scl& b) {
+  uint32_t x[16];
+  limbs_mul<8, 8>(x, a.v, b.v);
+  scl_reduce512(r, x);
+}
+ZKP_DEV void scl_add(scl& r, const scl& a, const scl& b) {
+  uint32_t t[8], u[8], l[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) l[i] = scl_l(i);
+  limbs_add<8>(t, a.v, b.v);  // < 2^254: no carry
+  uint32_t br = limbs_sub<8>(u, t, l);
+  uint32_t keep = 0u - br;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = (t[i] & keep) | (u[i] & ~keep);
+}
+ZKP_DEV void scl_sub(scl& r, const scl& a, const scl& b) {
+  uint32_t t[8], u[8], l[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) l[i] = scl_l(i);
+  uint32_t br = limbs_sub<8>(t, a.v, b.v);
+  limbs_add<8>(u, t, l);
+  uint32_t fix = 0u - br;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = (u[i] & fix) | (t[i] & ~fix);
+}
+ZKP_DEV void scl_zero(scl& r) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = 0;
+}
+ZKP_DEV void scl_neg(scl& r, const scl& a) {
+  scl z;
+  scl_zero(z);
+  scl_sub(r, z, a);
+}
+// canonical check of 8 words
+ZKP_DEV uint32_t scl_is_canonical(const uint32_t* w) {
+  uint32_t t[8], l[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) l[i] = scl_l(i);
+  return limbs_sub<8>(t, w, l);  // borrow <=> w < l
+}
+
+}  // namespace zkp

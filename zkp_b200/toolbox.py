@@ -51,6 +51,7 @@ def _lib():
         lib.zkph_verify_batchable.argtypes = [vp, vp, vp, sz, vp, vp, sz, vp, sz, vp, sz]
         lib.zkph_batch_verify.argtypes = [vp, vp, vp, sz, sz, vp, vp, vp, vp, vp, sz, i32, vp, vp, vp]
         lib.zkph_prove_many.argtypes = [vp, vp, vp, sz, sz, vp, vp, vp, i32, vp, vp, vp]
+        lib.zkph_batch_verify_device.argtypes = [vp, vp, vp, sz, sz, vp, vp, vp, vp, vp, vp, vp]
         lib.zkph_transcript_new.restype = vp
         lib.zkph_transcript_new.argtypes = [vp, sz]
         lib.zkph_transcript_clone.restype = vp
@@ -202,6 +203,29 @@ class Statement:
         if want_msm_inputs:
             return co, po, hs.value
         return hs.value
+
+    def batch_verify_device(self, eng, proofs_commitments, proofs_responses, transcript_label, instance_enc, common_enc,
+                            rho_seed32, want_msm_inputs=False):
+        """module::batch_verify with transcripts, challenges, weights and the coefficient fold on the GPU
+        (zkp_batch_verify_proofs).  Same arguments as batch_verify; rho_seed32 seeds the per-proof weights."""
+        com = np.ascontiguousarray(proofs_commitments, dtype=np.uint8)
+        resp = np.ascontiguousarray(proofs_responses, dtype=np.uint8)
+        inst = np.ascontiguousarray(instance_enc, dtype=np.uint8)
+        comm = np.ascontiguousarray(common_enc, dtype=np.uint8)
+        N = com.shape[0]
+        if resp.shape[0] != N or inst.shape[1] != N:
+            raise BatchSizeMismatch()
+        assert com.shape[1:] == (self.k, 32) and resp.shape[1:] == (self.m, 32) and inst.shape[0] == len(self.instance)
+        assert len(rho_seed32) == 32
+        n = len(self.common) + (len(self.instance) + self.k) * N
+        co = np.zeros((n, 32), np.uint8) if want_msm_inputs else None
+        po = np.zeros((n, 32), np.uint8) if want_msm_inputs else None
+        rc = _lib().zkph_batch_verify_device(eng._ctx, self._h, transcript_label, len(transcript_label), N, _p(inst),
+                                             _p(comm), _p(com), _p(resp), bytes(rho_seed32), _p(co), _p(po))
+        if want_msm_inputs and rc in (0, 1):
+            self._last_msm_inputs = (co, po)
+        _raise(rc)
+        return (co, po) if want_msm_inputs else None
 
     # ---- N proofs at once (no counterpart in the reference; = N x prove_batchable) ----------------------------
     def prove_many(self, eng, transcript_label, secrets, points_limbs, entropy, threads=0):
