@@ -145,6 +145,9 @@ int32_t zkp_batch_verify_proofs(zkp_ctx* ctx, const zkp_statement_desc* st, cons
                                 const uint8_t* responses, const uint8_t* rho_seed, int32_t* accept, int64_t* first_bad,
                                 uint8_t* coeff_out, uint8_t* points_out);
 
+/* Self-test of the device hashing code: out32 receives Merlin's published conformance vector (a8c933f5...). */
+int32_t zkp_selftest_hash(zkp_ctx* ctx, uint8_t* out32);
+
 /* Device-side micro-benchmark of the field multiplier variants (roofline calibration):
  * runs `iters` dependent multiplies (or squarings) per thread over a full grid and returns the measured
  * rate in operations per second in *ops_per_sec.  kind: 0 = fe_mul (8x32 saturated), 1 = fe_sq,

@@ -132,6 +132,14 @@ def test_cmz_prove_many_and_batch_verify_match_oracle(engine):
         st.batch_verify(engine, badc, resp, b"CMZ", inst, comm, b"batch-rho")
 
 
+def test_device_merlin_selftest(engine):
+    """Keccak-f / STROBE / Merlin on the device reproduce Merlin's published conformance vector."""
+    import ctypes
+    buf = ctypes.create_string_buffer(32)
+    assert engine._lib.zkp_selftest_hash(engine._ctx, buf) == 0
+    assert buf.raw.hex() == U.golden("merlin.json")["complex"]
+
+
 def test_batch_verify_device_front_end_matches_oracle(engine):
     """zkp_batch_verify_proofs (transcripts, challenges, weights, coefficient fold on the GPU): the MSM inputs it
     builds are byte-equal to the oracle's BatchVerifier with the same per-proof weight derivation."""

@@ -9,9 +9,16 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libzkp_b200.so")
 SOURCES = ["api.cu", "host/merlin.cpp", "host/scalar.cpp", "host/toolbox.cpp", "host/host_api.cpp"]
-HEADERS = ["fe.cuh", "ge.cuh", "sc.cuh", "kernels.cuh", "small_msm.cuh", "bench_fe.cuh",
-           "host/merlin.hpp", "host/scalar.hpp", "host/toolbox.hpp",
-           os.path.join("..", "..", "include", "zkp_b200.h"), os.path.join("..", "..", "include", "zkp_b200_host.h")]
+
+
+def _headers():
+    """Every header the library is built from (any change triggers a rebuild)."""
+    out = []
+    for d in (CSRC, os.path.join(CSRC, "host"), os.path.join(HERE, "..", "include")):
+        for f in sorted(os.listdir(d)):
+            if f.endswith((".cuh", ".hpp", ".h")):
+                out.append(os.path.join(d, f))
+    return out
 
 
 def nvcc_path():
@@ -25,7 +32,7 @@ def _stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+    return any(os.path.getmtime(f) > t for f in [os.path.join(CSRC, s) for s in SOURCES] + _headers())
 
 
 def build(force=False, verbose=False):

@@ -864,6 +864,18 @@ extern "C" int32_t zkp_msm_ct_batched(zkp_ctx* ctx, const uint8_t* scalars, cons
 // ---------------------------------------------------------------------------------------------------------
 // field-multiplier micro-benchmark
 // ---------------------------------------------------------------------------------------------------------
+// self-test of the device hashing: Merlin's conformance vector computed on the GPU
+extern "C" int32_t zkp_selftest_hash(zkp_ctx* ctx, uint8_t* out32) {
+  if (!ctx || !out32) return ZKP_ERR_SIZE;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  ENSURE(ctx, ctx->result, 64);
+  k_selftest_merlin<<<1, 1, 0, ctx->stream>>>((uint8_t*)ctx->result.p);
+  LAUNCH_CHECK(ctx);
+  CUDA_TRY(ctx, cudaMemcpyAsync(out32, ctx->result.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return ZKP_OK;
+}
+
 // diagnostic: integer squaring warps and FP64 warps side by side; returns milliseconds
 extern "C" int32_t zkp_bench_dual(zkp_ctx* ctx, int32_t mode, int32_t iters, double* ms_out) {
   if (!ctx || !ms_out || iters <= 0 || mode < 0 || mode > 2) return ZKP_ERR_SIZE;

@@ -156,6 +156,32 @@ __global__ void __launch_bounds__(128) k_bv_prepare(bv_desc d, const uint32_t* _
   }
 }
 
+// self-test: Merlin's published conformance vector computed by one device thread (zkp_selftest_hash)
+__global__ void k_selftest_merlin(uint8_t* out32) {
+  strobe_t s;
+  for (int i = 0; i < 25; i++) s.st[i] = 0;
+  const uint8_t init[18] = {1, 168, 1, 0, 1, 96, 'S', 'T', 'R', 'O', 'B', 'E', 'v', '1', '.', '0', '.', '2'};
+  for (int i = 0; i < 18; i++) st_xor_byte(s, i, init[i]);
+  keccak_f1600_dev(s.st);
+  s.pos = 0; s.pos_begin = 0; s.cur_flags = 0;
+  strobe_meta_ad(s, (const uint8_t*)"Merlin v1.0", 11, false);
+  transcript_append(s, (const uint8_t*)"dom-sep", 7, (const uint8_t*)"test protocol", 13);
+  transcript_append(s, (const uint8_t*)"step1", 5, (const uint8_t*)"some data", 9);
+  uint8_t ch[32], big[64];
+  for (int i = 0; i < 64; i++) big[i] = 0x63;
+  for (int r = 0; r < 32; r++) {
+    transcript_challenge(s, (const uint8_t*)"challenge", 9, ch, 32);
+    // append_message("bigdata", 1024 x 0x63) in 64-byte pieces
+    uint8_t l4[4] = {0, 4, 0, 0};
+    strobe_meta_ad(s, (const uint8_t*)"bigdata", 7, false);
+    strobe_meta_ad(s, l4, 4, true);
+    strobe_ad(s, big, 64, false);
+    for (int q = 1; q < 16; q++) strobe_ad(s, big, 64, true);
+    transcript_append(s, (const uint8_t*)"challengedata", 13, ch, 32);
+  }
+  for (int i = 0; i < 32; i++) out32[i] = ch[i];
+}
+
 // static_coeffs[s] = sum over blocks of static_part[b][s]; one block, thread per (strided) partial
 __global__ void __launch_bounds__(256) k_bv_static_sum(const uint8_t* __restrict__ static_part, int nblocks, int nc,
                                                        uint8_t* __restrict__ msm_scalars) {
