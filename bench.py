@@ -170,6 +170,7 @@ def main():
     ap.add_argument("--cpu-sample-log2", type=int, default=14, help="proofs in the CPU baseline sample")
     ap.add_argument("--window", type=int, default=0, help="tuning: force the Pippenger window width")
     ap.add_argument("--chunk", type=int, default=0, help="tuning: force the accumulate work-item length")
+    ap.add_argument("--no-proofs-leg", action="store_true", help="skip the e2e_from_proofs leg (real proofs, device front end)")
     ap.add_argument("--no-overlap", action="store_true", help="tuning: run the digit sort on the compute stream")
     ap.add_argument("--sweep", default="", help="tuning: comma list of windows; prints stage times per window and exits")
     args = ap.parse_args()
@@ -328,15 +329,54 @@ def main():
     clocks = sampler.stop()
     assert accepts == args.steps
 
+    # ---- e2e from PROOFS: 2^16 real CMZ proofs (made here with the engine) tiled to 2^21 batch entries; transcripts,
+    # challenges, weights, coefficient fold and MSM all on the GPU (zkp_batch_verify_proofs, SURVEY 8f f1+f2) ----------
+    proofs_leg = None
+    if not args.no_proofs_leg:
+        from tools.workloads import cmz_instances
+        from zkp_b200 import toolbox as PT
+        eng.set_stream(None)
+        n_real = min(N, 1 << 16)
+        st_cmz, sec, limbs, enc_pts = cmz_instances(eng, n_real, np.random.default_rng(500 + rank))
+        entropy = np.random.default_rng(600 + rank).integers(0, 256, size=(n_real, 32), dtype=np.uint8)
+        enc_p, com, resp = st_cmz.prove_many(eng, b"CMZ", sec, limbs, entropy, threads=host_threads)
+        del limbs
+        reps = N // n_real
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+        inst_h = pin(np.tile(np.ascontiguousarray(enc_p[:, :13].transpose(1, 0, 2)), (1, reps, 1)))
+        com_h = pin(np.tile(com, (reps, 1, 1)))
+        resp_h = pin(np.tile(resp, (reps, 1, 1)))
+        common_h = np.ascontiguousarray(enc_p[0, 13:])
+        seed = bytes(range(32))
+        st_cmz.batch_verify_device(eng, com_h, resp_h, b"CMZ", inst_h, common_h, seed)          # warm-up + must accept
+        bad = resp_h[:n_real].copy()
+        bad[7, 3, 0] ^= 1
+        try:
+            st_cmz.batch_verify_device(eng, com_h[:n_real], bad, b"CMZ", np.ascontiguousarray(inst_h[:, :n_real]),
+                                       common_h, seed)
+            raise SystemExit("tampered proof accepted by the device front end")
+        except PT.VerificationFailure:
+            pass
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            st_cmz.batch_verify_device(eng, com_h, resp_h, b"CMZ", inst_h, common_h, seed)
+        barrier()
+        proofs_leg = {"seconds": (time.perf_counter() - t0) / args.steps,
+                      "h2d_bytes_per_step": int(inst_h.nbytes + com_h.nbytes + resp_h.nbytes + common_h.nbytes),
+                      "distinct_real_proofs": int(n_real)}
+        del inst_h, com_h, resp_h
+
     # ---- gather: max time over ranks, accept bits over NCCL ---------------------------------------------------
     from zkp_b200 import parallel
-    tm = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    tm = torch.tensor([ms_total, e2e_s * 1e3, (proofs_leg["seconds"] if proofs_leg else 0.0) * 1e3],
+                      dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
     # the single NCCL gather of accept bits (one per GPU shard)
     accept_bitmap, verdict = parallel.gather_accept_bits(accepts == args.steps, device="cuda")
     assert verdict
-    ms_total, e2e_ms = float(tm[0].item()), float(tm[1].item())
+    ms_total, e2e_ms, proofs_ms = float(tm[0].item()), float(tm[1].item()), float(tm[2].item())
 
     if rank == 0:
         ms_step = ms_total / args.steps
@@ -383,6 +423,14 @@ def main():
                                            "serial u64 backend sharded over %d threads, %.2f s"
                                            % (sample, ROWS * sample, host_threads, cpu_t)},
                 "accept_bits": accept_bitmap, "setup_s": setup_s}
+        if proofs_leg:
+            line["e2e_from_proofs"] = {
+                "value": world * N / (proofs_ms * 1e-3), "unit": "proofs/s", "ms_per_step": proofs_ms,
+                "h2d_bytes_per_step": proofs_leg["h2d_bytes_per_step"], "d2h_bytes_per_step": 48,
+                "api": "zkp_batch_verify_proofs via zkph_batch_verify_device (C ABI), pinned host buffers",
+                "what": "Merlin transcripts, challenges, per-proof weights, coefficient fold AND the MSM on the GPU "
+                        "(SURVEY 8f rows f1+f2); %d distinct real CMZ proofs tiled to 2^%d batch entries with distinct "
+                        "weights; accept checked, tampered response rejected" % (proofs_leg["distinct_real_proofs"], args.log2_proofs)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
