@@ -606,68 +606,94 @@ extern "C" int32_t zkp_batch_verify_proofs(zkp_ctx* ctx, const zkp_statement_des
     memcpy(&blob[o_ti], tidx.data(), n_terms * 4);
   }
   const size_t rows = (size_t)ni + k, n = (size_t)nc + rows * N;
+  if (n >= 0x7fffffffull) return ZKP_ERR_SIZE;
+  const size_t chunk = ctx->chunk_terms / (rows ? rows : 1) > 1024 ? (ctx->chunk_terms * 4 / (rows ? rows : 1)) & ~(size_t)127
+                                                                    : 1024;   // proofs per chunk (multiple of 128)
+  const size_t nchunks = N ? (N + chunk - 1) / chunk : 0;
   ENSURE(ctx, ctx->bv_misc, blob_sz);
   ENSURE(ctx, ctx->in_scalars, n * 32 + 32);
   ENSURE(ctx, ctx->in_points, n * 32 + 32);
   ENSURE(ctx, ctx->bv_com, (size_t)k * N * 32 + 32);
   ENSURE(ctx, ctx->bv_resp, (size_t)m * N * 32 + 32);
   ENSURE(ctx, ctx->result, 64);
-  ENSURE(ctx, ctx->flags, 16);
-  const unsigned nblocks = (unsigned)((N + 127) / 128);
-  ENSURE(ctx, ctx->bv_part, (size_t)(nblocks ? nblocks : 1) * (nc ? nc : 1) * 32);
-  uint8_t* dm = (uint8_t*)ctx->bv_misc.p;
-  CUDA_TRY(ctx, cudaMemcpyAsync(dm, blob.data(), blob_sz, cudaMemcpyHostToDevice, st));
-  uint8_t* dpts = (uint8_t*)ctx->in_points.p;
-  if (nc) CUDA_TRY(ctx, cudaMemcpyAsync(dpts, common_enc, (size_t)nc * 32, cudaMemcpyHostToDevice, st));
-  if (ni && N)
-    CUDA_TRY(ctx, cudaMemcpyAsync(dpts + (size_t)nc * 32, instance_enc, (size_t)ni * N * 32, cudaMemcpyHostToDevice, st));
-  if (k && N) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->bv_com.p, commitments, (size_t)k * N * 32, cudaMemcpyHostToDevice, st));
-  if (m && N) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->bv_resp.p, responses, (size_t)m * N * 32, cudaMemcpyHostToDevice, st));
-  k_init_flags<<<1, 1, 0, st>>>((int*)ctx->flags.p);
-  LAUNCH_CHECK(ctx);
-  if (N) {
-    bv_desc d;
-    d.m = m; d.ni = ni; d.nc = nc; d.k = k; d.n_ops = (int)ops.size(); d.n_terms = n_terms;
-    d.ops = (const bv_op*)(dm + o_ops);
-    d.labels = dm + o_pool;
-    d.lhs_kind = (const int32_t*)(dm + o_lk);
-    d.lhs_idx = (const int32_t*)(dm + o_li);
-    d.cons_off = (const int32_t*)(dm + o_co);
-    d.term_scalar = (const int32_t*)(dm + o_ts);
-    d.term_pkind = (const int32_t*)(dm + o_tk);
-    d.term_pidx = (const int32_t*)(dm + o_ti);
-    k_bv_prepare<<<nblocks, 128, 0, st>>>(d, (const uint32_t*)(dm + o_prefix), N, dpts + (size_t)nc * 32, dpts,
-                                          (const uint8_t*)ctx->bv_com.p, (const uint8_t*)ctx->bv_resp.p, dm + o_seed,
-                                          (uint8_t*)ctx->in_scalars.p, dpts, (uint8_t*)ctx->bv_part.p, nullptr,
-                                          (int*)ctx->flags.p);
-    LAUNCH_CHECK(ctx);
+  const unsigned nblocks_total = (unsigned)(nchunks * ((chunk + 127) / 128) + 1);
+  ENSURE(ctx, ctx->bv_part, (size_t)nblocks_total * (nc ? nc : 1) * 32);
+  if (!ctx->copy_stream) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  while (ctx->chunk_ev.size() < nchunks + 1) {
+    cudaEvent_t e;
+    CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->chunk_ev.push_back(e);
   }
-  if (nc) {
-    if (N) {
-      k_bv_static_sum<<<1, 256, 0, st>>>((const uint8_t*)ctx->bv_part.p, (int)nblocks, nc, (uint8_t*)ctx->in_scalars.p);
-      LAUNCH_CHECK(ctx);
-    } else {
-      CUDA_TRY(ctx, cudaMemsetAsync(ctx->in_scalars.p, 0, (size_t)nc * 32, st));
+  uint8_t* dm = (uint8_t*)ctx->bv_misc.p;
+  uint8_t* dpts = (uint8_t*)ctx->in_points.p;
+  uint8_t* dsc = (uint8_t*)ctx->in_scalars.p;
+  CUDA_TRY(ctx, cudaMemcpyAsync(dm, blob.data(), blob_sz, cudaMemcpyHostToDevice, st));
+  if (nc) CUDA_TRY(ctx, cudaMemcpyAsync(dpts, common_enc, (size_t)nc * 32, cudaMemcpyHostToDevice, st));
+  if (n == 0) {
+    k_empty_result<<<1, 1, 0, st>>>((msm_result*)ctx->result.p);
+    LAUNCH_CHECK(ctx);
+    int32_t ident0 = 0;
+    int32_t r0 = fetch_result(ctx, nullptr, &ident0, first_bad);
+    if (r0 != ZKP_OK) return r0;
+    *accept = ident0;
+    return ZKP_OK;
+  }
+  msm_plan pl;
+  int32_t r = msm_prepare(ctx, n, &pl);   // sizes the MSM workspace, resets flags and the digit histogram
+  if (r != ZKP_OK) return r;
+  bv_desc d;
+  d.m = m; d.ni = ni; d.nc = nc; d.k = k; d.n_ops = (int)ops.size(); d.n_terms = n_terms;
+  d.ops = (const bv_op*)(dm + o_ops);
+  d.labels = dm + o_pool;
+  d.lhs_kind = (const int32_t*)(dm + o_lk);
+  d.lhs_idx = (const int32_t*)(dm + o_li);
+  d.cons_off = (const int32_t*)(dm + o_co);
+  d.term_scalar = (const int32_t*)(dm + o_ts);
+  d.term_pkind = (const int32_t*)(dm + o_tk);
+  d.term_pidx = (const int32_t*)(dm + o_ti);
+  // the copy stream must not run ahead of earlier work on `st` that still uses the staging buffers
+  CUDA_TRY(ctx, cudaEventRecord(ctx->chunk_ev[nchunks], st));
+  CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[nchunks], 0));
+  unsigned block_base = 0;
+  for (size_t cidx = 0; cidx < nchunks; cidx++) {
+    const size_t j0 = cidx * chunk, cnt = j0 + chunk < N ? chunk : N - j0;
+    // H2D of this chunk: instance slab (ni rows of cnt encodings), commitments and responses of cnt proofs
+    if (ni)
+      CUDA_TRY(ctx, cudaMemcpy2DAsync(dpts + ((size_t)nc + j0) * 32, N * 32, instance_enc + j0 * 32, N * 32, cnt * 32,
+                                      (size_t)ni, cudaMemcpyHostToDevice, ctx->copy_stream));
+    if (k)
+      CUDA_TRY(ctx, cudaMemcpyAsync((uint8_t*)ctx->bv_com.p + j0 * k * 32, commitments + j0 * k * 32, cnt * k * 32,
+                                    cudaMemcpyHostToDevice, ctx->copy_stream));
+    if (m)
+      CUDA_TRY(ctx, cudaMemcpyAsync((uint8_t*)ctx->bv_resp.p + j0 * m * 32, responses + j0 * m * 32, cnt * m * 32,
+                                    cudaMemcpyHostToDevice, ctx->copy_stream));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->chunk_ev[cidx], ctx->copy_stream));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->chunk_ev[cidx], 0));
+    if (pl.sort != st) CUDA_TRY(ctx, cudaStreamWaitEvent(pl.sort, ctx->chunk_ev[cidx], 0));
+    const unsigned nb = (unsigned)((cnt + 127) / 128);
+    k_bv_prepare<<<nb, 128, 0, st>>>(d, (const uint32_t*)(dm + o_prefix), N, dpts + (size_t)nc * 32, dpts,
+                                     (const uint8_t*)ctx->bv_com.p, (const uint8_t*)ctx->bv_resp.p, dm + o_seed, dsc, dpts,
+                                     (uint8_t*)ctx->bv_part.p, nullptr, (int*)ctx->flags.p, j0, cnt, block_base);
+    LAUNCH_CHECK(ctx);
+    block_base += nb;
+    // the slabs of this chunk are complete (points and coefficients): decompress them and histogram their digits
+    for (size_t row = 0; row < rows; row++) {
+      r = msm_ingest(ctx, pl, dsc, dpts, (size_t)nc + row * N + j0, cnt, false);
+      if (r != ZKP_OK) return r;
     }
   }
-  // front-end failures (identity encodings, non-canonical responses) are reported before the MSM result
-  int hflags[4];
-  CUDA_TRY(ctx, cudaMemcpyAsync(hflags, ctx->flags.p, 16, cudaMemcpyDeviceToHost, st));
-  if (coeff_out) CUDA_TRY(ctx, cudaMemcpyAsync(coeff_out, ctx->in_scalars.p, n * 32, cudaMemcpyDeviceToHost, st));
-  if (points_out) CUDA_TRY(ctx, cudaMemcpyAsync(points_out, ctx->in_points.p, n * 32, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(ctx, cudaStreamSynchronize(st));
-  if (hflags[0] != 0x7fffffff) {
-    if (first_bad) *first_bad = hflags[0];
-    return ZKP_ERR_POINT;
+  if (nc) {
+    k_bv_static_sum<<<1, 256, 0, st>>>((const uint8_t*)ctx->bv_part.p, (int)block_base, nc, dsc);
+    LAUNCH_CHECK(ctx);
+    r = msm_ingest(ctx, pl, dsc, dpts, 0, (size_t)nc, false);
+    if (r != ZKP_OK) return r;
   }
-  if (hflags[1] != 0x7fffffff) {
-    if (first_bad) *first_bad = hflags[1];
-    return ZKP_ERR_SCALAR;
-  }
-  int32_t r = msm_vartime_launch(ctx, ctx->in_scalars.p, ctx->in_points.p, n, (msm_result*)ctx->result.p);
+  r = msm_finish(ctx, pl, dsc, n, (msm_result*)ctx->result.p, false);
   if (r != ZKP_OK) return r;
+  if (coeff_out) CUDA_TRY(ctx, cudaMemcpyAsync(coeff_out, dsc, n * 32, cudaMemcpyDeviceToHost, st));
+  if (points_out) CUDA_TRY(ctx, cudaMemcpyAsync(points_out, dpts, n * 32, cudaMemcpyDeviceToHost, st));
   int32_t ident = 0;
-  r = fetch_result(ctx, nullptr, &ident, first_bad);
+  r = fetch_result(ctx, nullptr, &ident, first_bad);   // identity encodings / bad points -> 1, bad responses -> 3
   if (r != ZKP_OK) return r;
   *accept = ident;
   return ZKP_OK;

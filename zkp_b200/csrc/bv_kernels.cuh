@@ -66,10 +66,13 @@ __global__ void __launch_bounds__(128) k_bv_prepare(bv_desc d, const uint32_t* _
                                                     const uint8_t* __restrict__ responses,
                                                     const uint8_t* __restrict__ rho_seed, uint8_t* __restrict__ msm_scalars,
                                                     uint8_t* __restrict__ msm_points, uint8_t* __restrict__ static_part,
-                                                    uint8_t* __restrict__ minus_c_out, int* __restrict__ flags) {
+                                                    uint8_t* __restrict__ minus_c_out, int* __restrict__ flags,
+                                                    size_t j0, size_t cnt, unsigned block_base) {
+  // proofs [j0, j0 + cnt) of the batch (chunked ingestion: H2D of the next chunk overlaps this kernel)
   __shared__ scl red[128];
-  const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = j < N;
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t j = j0 + tid;
+  const bool live = tid < cnt;
   scl inst[ZKP_BV_MAX_VARS], stat[ZKP_BV_MAX_VARS];
   for (int i = 0; i < d.ni; i++) scl_zero(inst[i]);
   for (int i = 0; i < d.nc; i++) scl_zero(stat[i]);
@@ -151,7 +154,7 @@ __global__ void __launch_bounds__(128) k_bv_prepare(bv_desc d, const uint32_t* _
       if ((int)threadIdx.x < off) scl_add(red[threadIdx.x], red[threadIdx.x], red[threadIdx.x + off]);
       __syncthreads();
     }
-    if (threadIdx.x == 0) store_scl(static_part + ((size_t)blockIdx.x * d.nc + sidx) * 32, red[0]);
+    if (threadIdx.x == 0) store_scl(static_part + ((size_t)(block_base + blockIdx.x) * d.nc + sidx) * 32, red[0]);
     __syncthreads();
   }
 }
