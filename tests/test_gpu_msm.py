@@ -149,3 +149,48 @@ def test_batch_verify_dleq_golden(engine):
     bad[3, 0] ^= 1
     ok, rc = engine.batch_verify(bad[:num_s], pts[:num_s], bad[num_s:], pts[num_s:], rows, batch)
     assert not ok and rc == 0
+
+
+def test_host_pipeline_chunking_overlap_and_profile_options(engine):
+    """The chunked H2D pipeline (several chunks, ragged tail), the second-stream sort and the profiling mode all
+    give the same bytes."""
+    case = U.golden("msm_seeded.json")["cases"][1]
+    base = U.base_points(case["K"])
+    sc = U.random_scalars(case["n"], seed=case["seed"])
+    pts = np.frombuffer(b"".join(base[i % case["K"]] for i in range(case["n"])), dtype=np.uint8).reshape(-1, 32)
+    try:
+        for opts in ({"chunk_terms": 4096}, {"chunk_terms": 4096, "overlap": 1}, {"profile": 1}, {"overlap": 1}):
+            for k, v in opts.items():
+                engine.set_option(k, v)
+            enc, _, _ = engine.msm_vartime(sc, pts)
+            assert enc.hex() == case["expected"], opts
+            if "profile" in opts:
+                st = engine.stage_ms()
+                assert st["decompress"] > 0 and st["accumulate"] > 0 and 4 <= st["window"] <= 24
+            engine.set_option("profile", 0)
+            engine.set_option("overlap", 0)
+            engine.set_option("chunk_terms", 1 << 21)
+    finally:
+        engine.set_option("profile", 0)
+        engine.set_option("overlap", 0)
+        engine.set_option("chunk_terms", 1 << 21)
+
+
+def test_abi_misuse_is_reported_not_crashed(engine):
+    import ctypes
+    from zkp_b200 import native
+    lib, ctx = engine._lib, engine._ctx
+    out = (ctypes.c_uint8 * 32)()
+    assert lib.zkp_msm_vartime(ctx, None, None, 5, out, None, None) == native.ZKP_ERR_SIZE
+    assert lib.zkp_msm_vartime(None, None, None, 0, out, None, None) == native.ZKP_ERR_SIZE
+    assert lib.zkp_ctx_set_option(ctx, b"window", 99) == native.ZKP_ERR_SIZE
+    assert lib.zkp_ctx_set_option(ctx, b"no-such-option", 1) == native.ZKP_ERR_SIZE
+    assert lib.zkp_msm_vartime_dev(ctx, ctypes.c_void_p(8), ctypes.c_void_p(16), 4, ctypes.c_void_p(32)) == native.ZKP_ERR_SIZE
+    bad_off = np.array([0, 5, 3], dtype=np.uint64)      # decreasing offsets
+    s = np.zeros((5, 32), np.uint8)
+    o = np.zeros((2, 32), np.uint8)
+    v = np.zeros(2, np.uint8)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    assert lib.zkp_msm_vartime_batched(ctx, p(s), p(s), p(bad_off), 2, p(o), p(v)) == native.ZKP_ERR_SIZE
+    acc = ctypes.c_int32(7)
+    assert lib.zkp_batch_verify(ctx, None, None, 0, None, None, 0, 0, ctypes.byref(acc), None) == 0 and acc.value == 1

@@ -199,6 +199,37 @@ def test_batch_verify_device_front_end_matches_oracle(engine):
     assert [bytes(p) for p in po] == opts and [bytes(c) for c in co] == [S.to_bytes(s) for s in oscal]
 
 
+def test_device_front_end_edge_shapes(engine):
+    """N = 1, an empty batch, and a statement whose constraint has a STATIC lhs (static_coeffs path of
+    batch_verifier.rs:187-189) through both the host mirror and the device front end."""
+    st = PT.Statement("pk", "PK proof", ["x"], ["A"], ["G", "Q"], [("A", [("x", "G")]), ("Q", [("x", "G")])])
+    ost = OT.Statement("pk", "PK proof", ["x"], ["A"], ["G", "Q"], [("A", [("x", "G")]), ("Q", [("x", "G")])])
+    G = R.BASEPOINT
+    x = 123456789
+    Q = R.pt_mul(x, G)                  # the same secret for every proof, so the static lhs Q is consistent
+    seed = bytes(range(1, 33))
+    for N in (1, 4):
+        pts = np.array([[limbs(Q), limbs(G), limbs(Q)] for _ in range(N)], dtype=np.uint64)
+        ent = np.frombuffer(OT.SeededRng(b"pk%d" % N).bytes(32 * N), dtype=np.uint8).reshape(N, 32)
+        enc, com, resp = st.prove_many(engine, b"PK", np.stack([sbytes([x])] * N), pts, ent, threads=1)
+        inst = np.ascontiguousarray(enc[:, :1].transpose(1, 0, 2))
+        st.batch_verify(engine, com, resp, b"PK", inst, enc[0, 1:], b"r")
+        co, po = st.batch_verify_device(engine, com, resp, b"PK", inst, enc[0, 1:], seed, want_msm_inputs=True)
+        oproofs = [OT.BatchableProof([bytes(c) for c in com[j]], [int.from_bytes(bytes(r), "little") for r in resp[j]])
+                   for j in range(N)]
+        oencs = {"A": [bytes(e) for e in enc[:, 0]], "G": bytes(enc[0, 1]), "Q": bytes(enc[0, 2])}
+        bv = ost.build_batch_verifier(N, [OM.Transcript(b"PK") for _ in range(N)], oencs)
+        oscal, opts = bv.batch_coeffs(oproofs, OT.PerProofRng(seed))
+        assert [bytes(p) for p in po] == opts and [bytes(c) for c in co] == [S.to_bytes(s) for s in oscal]
+        bad = resp.copy()
+        bad[0, 0, 1] ^= 4
+        with pytest.raises(PT.VerificationFailure):
+            st.batch_verify_device(engine, com, bad, b"PK", inst, enc[0, 1:], seed)
+    # empty batch: the sum over no proofs is the identity -> accepted, like the reference's empty MSM
+    st.batch_verify_device(engine, np.zeros((0, 2, 32), np.uint8), np.zeros((0, 1, 32), np.uint8), b"PK",
+                           np.zeros((1, 0, 32), np.uint8), enc[0, 1:], seed)
+
+
 def test_dleq_batch_golden(engine):
     """tests/zkp.rs:115-175 shape: 4 macro-form DLEQ proofs, golden fixture produced by the oracle."""
     kb = U.golden("toolbox_kat.json")["dleq_batch"]

@@ -18,7 +18,7 @@ P = R.P
 def lib():
     src = os.path.join(HERE, "host_emul", "emul.cpp")
     out = os.path.join(HERE, "host_emul", "libemul.so")
-    deps = [src] + [os.path.join(HERE, "..", "zkp_b200", "csrc", f) for f in ("fe.cuh", "ge.cuh", "sc.cuh")]
+    deps = [src] + [os.path.join(HERE, "..", "zkp_b200", "csrc", f) for f in ("fe.cuh", "ge.cuh", "sc.cuh", "hash.cuh", "scl.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         subprocess.check_call(["g++", "-O1", "-shared", "-fPIC", "-DZKP_HOST_EMUL", "-x", "c++", src, "-o", out])
     return ctypes.CDLL(out)
@@ -140,3 +140,28 @@ def test_scalar_recode(lib):
                 assert k == min(s, L - s) and neg.value == (k != s)
                 assert sum(d * (1 << (c * i)) for i, d in enumerate(dg)) == k
                 assert all(abs(d) <= 1 << (c - 1) for d in dg)
+
+
+def test_device_hash_and_scalar_logic(lib):
+    """hash.cuh / scl.cuh (device Keccak, STROBE, Merlin, SHAKE weights, scalars mod l) compiled for the host."""
+    import hashlib
+    from tests import util_data as U
+    o = ctypes.create_string_buffer(32)
+    lib.emul_transcript_test(o)
+    assert o.raw.hex() == U.golden("merlin.json")["complex"]
+    for n, m in [(16, b"abc"), (176, b"seed" * 8 + b"\x01" * 8), (300, b"x" * 135), (136, b"")]:
+        out = ctypes.create_string_buffer(n)
+        lib.emul_shake(out, n, m, len(m))
+        assert out.raw == hashlib.shake_256(m).digest(n)
+    L = R.L
+    rnd = random.Random(9)
+    vals = [0, 1, L - 1, 2**252 - 1, 2**252, L - 2] + [rnd.randrange(L) for _ in range(150)]
+    for a in vals:
+        for b in rnd.sample(vals, 6):
+            for f, op in ((lib.emul_scl_mul, lambda x, y: x * y), (lib.emul_scl_add, lambda x, y: x + y),
+                          (lib.emul_scl_sub, lambda x, y: x - y)):
+                f(o, a.to_bytes(32, "little"), b.to_bytes(32, "little"))
+                assert int.from_bytes(o.raw, "little") == op(a, b) % L
+    for w in [0, 2**512 - 1, (L << 256) - 1, L << 200, L * L - 1] + [rnd.getrandbits(512) for _ in range(300)]:
+        lib.emul_scl_wide(o, w.to_bytes(64, "little"))
+        assert int.from_bytes(o.raw, "little") == w % L

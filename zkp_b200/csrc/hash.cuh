@@ -95,10 +95,21 @@ void strobe_run_f(strobe_t& s) {
   s.pos = 0;
   s.pos_begin = 0;
 }
+// absorb: bytes are gathered into one 64-bit word per state lane touched (one read-modify-write per lane instead
+// of one per byte); a group never crosses a lane or the rate boundary
 ZKP_DEV void strobe_absorb(strobe_t& s, const uint8_t* d, uint32_t n) {
-  for (uint32_t i = 0; i < n; i++) {
-    st_xor_byte(s, s.pos, d[i]);
-    if (++s.pos == ZKP_STROBE_R) strobe_run_f(s);
+  while (n) {
+    const uint32_t off = s.pos & 7u;
+    uint32_t take = 8u - off;
+    if (take > n) take = n;
+    if (take > ZKP_STROBE_R - s.pos) take = ZKP_STROBE_R - s.pos;
+    uint64_t w = 0;
+    for (uint32_t b = 0; b < take; b++) w |= (uint64_t)d[b] << (8u * b);
+    s.st[s.pos >> 3] ^= w << (8u * off);
+    s.pos += take;
+    d += take;
+    n -= take;
+    if (s.pos == ZKP_STROBE_R) strobe_run_f(s);
   }
 }
 ZKP_DEV void strobe_squeeze(strobe_t& s, uint8_t* out, uint32_t n) {
