@@ -65,7 +65,7 @@ void emul_keccak(uint64_t* st) { keccak_f1600_dev(st); }
 // Merlin transcript on the device state machine: new(label); a sequence of appends; challenge
 void emul_transcript_test(uint8_t* out32) {
   strobe_t s; for (int i = 0; i < 25; i++) s.st[i] = 0;
-  uint8_t* b = (uint8_t*)s.st; const uint8_t init[6] = {1, 168, 1, 0, 1, 96};
+  uint8_t* b = st_bytes(s); const uint8_t init[6] = {1, 168, 1, 0, 1, 96};
   memcpy(b, init, 6); memcpy(b + 6, "STROBEv1.0.2", 12); keccak_f1600_dev(s.st);
   s.pos = 0; s.pos_begin = 0; s.cur_flags = 0;
   strobe_meta_ad(s, (const uint8_t*)"Merlin v1.0", 11, false);

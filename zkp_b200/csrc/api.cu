@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <new>
 #include <string>
@@ -443,6 +444,15 @@ static int32_t msm_from_host(zkp_ctx* ctx, const hseg* sc_segs, const hseg* pt_s
   ENSURE(ctx, ctx->in_scalars, n * 32);
   ENSURE(ctx, ctx->in_points, n * 32);
   if (!ctx->copy_stream) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  if (ctx->profile) {   // per-stage timing wants the stages back to back: copy everything first, then one pass
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    int32_t rc = copy_range(ctx, pt_segs, nseg, 0, n, (uint8_t*)ctx->in_points.p);
+    if (rc != ZKP_OK) return rc;
+    rc = copy_range(ctx, sc_segs, nseg, 0, n, (uint8_t*)ctx->in_scalars.p);
+    if (rc != ZKP_OK) return rc;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    return msm_vartime_launch(ctx, ctx->in_scalars.p, ctx->in_points.p, n, d_result);
+  }
   msm_plan pl;
   int32_t r = msm_prepare(ctx, n, &pl);
   if (r != ZKP_OK) return r;

@@ -31,6 +31,9 @@ struct bv_desc {       // device copy of the statement
   const int32_t* term_pidx;         // [n_terms]
 };
 
+// Labels are spelled as local byte arrays (no string literals in device code).
+#define ZKP_LABEL(name, ...) const uint8_t name[] = {__VA_ARGS__}
+
 __device__ __forceinline__ void load32(uint8_t* dst, const uint8_t* src) {
   const uint4* p = (const uint4*)src;
   uint4 a = __ldg(p), b = __ldg(p + 1);
@@ -82,6 +85,10 @@ __global__ void __launch_bounds__(128) k_bv_prepare(bv_desc d, const uint32_t* _
 #pragma unroll
     for (int i = 0; i < 25; i++) s.st[i] = (uint64_t)prefix[2 * i] | ((uint64_t)prefix[2 * i + 1] << 32);
     s.pos = prefix[50]; s.pos_begin = prefix[51]; s.cur_flags = prefix[52];
+    ZKP_LABEL(L_BLINDCOM, 'b', 'l', 'i', 'n', 'd', 'c', 'o', 'm');
+    ZKP_LABEL(L_PTVAR, 'p', 't', 'v', 'a', 'r');
+    ZKP_LABEL(L_VAL, 'v', 'a', 'l');
+    ZKP_LABEL(L_CHAL, 'c', 'h', 'a', 'l');
     uint8_t enc[32];
     bool bad = false;
     for (int o = 0; o < d.n_ops; o++) {
@@ -95,19 +102,19 @@ __global__ void __launch_bounds__(128) k_bv_prepare(bv_desc d, const uint32_t* _
       for (int b = 0; b < 32; b++) any |= enc[b];
       if (any == 0) bad = true;   // identity encoding (toolbox/mod.rs:191, :215)
       if (op.kind == 2) {
-        transcript_append(s, (const uint8_t*)"blindcom", 8, d.labels + op.label_off, op.label_len);
+        transcript_append(s, L_BLINDCOM, 8, d.labels + op.label_off, op.label_len);
         uint4* dst = (uint4*)(msm_points + ((size_t)d.nc + (size_t)(d.ni + op.idx) * N + j) * 32);
         const uint4* s4 = (const uint4*)src;
         dst[0] = __ldg(s4);
         dst[1] = __ldg(s4 + 1);
       } else {
-        transcript_append(s, (const uint8_t*)"ptvar", 5, d.labels + op.label_off, op.label_len);
+        transcript_append(s, L_PTVAR, 5, d.labels + op.label_off, op.label_len);
       }
-      transcript_append(s, (const uint8_t*)"val", 3, enc, 32);
+      transcript_append(s, L_VAL, 3, enc, 32);
     }
     if (bad) atomicMin(&flags[0], (int)j);
     uint8_t wide[64];
-    transcript_challenge(s, (const uint8_t*)"chal", 4, wide, 64);
+    transcript_challenge(s, L_CHAL, 4, wide, 64);
     scl c, minus_c;
     scl_from_wide(c, wide);
     scl_neg(minus_c, c);
@@ -164,23 +171,31 @@ __global__ void k_selftest_merlin(uint8_t* out32) {
   strobe_t s;
   for (int i = 0; i < 25; i++) s.st[i] = 0;
   const uint8_t init[18] = {1, 168, 1, 0, 1, 96, 'S', 'T', 'R', 'O', 'B', 'E', 'v', '1', '.', '0', '.', '2'};
-  for (int i = 0; i < 18; i++) st_xor_byte(s, i, init[i]);
+  for (int i = 0; i < 18; i++) st_bytes(s)[i] ^= init[i];
   keccak_f1600_dev(s.st);
   s.pos = 0; s.pos_begin = 0; s.cur_flags = 0;
-  strobe_meta_ad(s, (const uint8_t*)"Merlin v1.0", 11, false);
-  transcript_append(s, (const uint8_t*)"dom-sep", 7, (const uint8_t*)"test protocol", 13);
-  transcript_append(s, (const uint8_t*)"step1", 5, (const uint8_t*)"some data", 9);
+  ZKP_LABEL(L_MERLIN, 'M', 'e', 'r', 'l', 'i', 'n', ' ', 'v', '1', '.', '0');
+  ZKP_LABEL(L_DOMSEP, 'd', 'o', 'm', '-', 's', 'e', 'p');
+  ZKP_LABEL(L_PROTO, 't', 'e', 's', 't', ' ', 'p', 'r', 'o', 't', 'o', 'c', 'o', 'l');
+  ZKP_LABEL(L_STEP1, 's', 't', 'e', 'p', '1');
+  ZKP_LABEL(L_SOME, 's', 'o', 'm', 'e', ' ', 'd', 'a', 't', 'a');
+  ZKP_LABEL(L_CHALLENGE, 'c', 'h', 'a', 'l', 'l', 'e', 'n', 'g', 'e');
+  ZKP_LABEL(L_BIGDATA, 'b', 'i', 'g', 'd', 'a', 't', 'a');
+  ZKP_LABEL(L_CHDATA, 'c', 'h', 'a', 'l', 'l', 'e', 'n', 'g', 'e', 'd', 'a', 't', 'a');
+  strobe_meta_ad(s, L_MERLIN, 11, false);
+  transcript_append(s, L_DOMSEP, 7, L_PROTO, 13);
+  transcript_append(s, L_STEP1, 5, L_SOME, 9);
   uint8_t ch[32], big[64];
   for (int i = 0; i < 64; i++) big[i] = 0x63;
   for (int r = 0; r < 32; r++) {
-    transcript_challenge(s, (const uint8_t*)"challenge", 9, ch, 32);
+    transcript_challenge(s, L_CHALLENGE, 9, ch, 32);
     // append_message("bigdata", 1024 x 0x63) in 64-byte pieces
     uint8_t l4[4] = {0, 4, 0, 0};
-    strobe_meta_ad(s, (const uint8_t*)"bigdata", 7, false);
+    strobe_meta_ad(s, L_BIGDATA, 7, false);
     strobe_meta_ad(s, l4, 4, true);
     strobe_ad(s, big, 64, false);
     for (int q = 1; q < 16; q++) strobe_ad(s, big, 64, true);
-    transcript_append(s, (const uint8_t*)"challengedata", 13, ch, 32);
+    transcript_append(s, L_CHDATA, 13, ch, 32);
   }
   for (int i = 0; i < 32; i++) out32[i] = ch[i];
 }

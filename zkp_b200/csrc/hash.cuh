@@ -65,6 +65,13 @@ struct strobe_t {
   uint32_t pos, pos_begin, cur_flags;
 };
 
+// strobe_run_f is compiled out of line on the device (code size: ~3.6k instructions, several call sites)
+#if ZKP_DEVICE_ASM
+#define ZKP_DEV_NOINLINE __device__ __noinline__
+#else
+#define ZKP_DEV_NOINLINE static
+#endif
+
 #define ZKP_STROBE_R 166u
 #define ZKP_FLAG_I 1u
 #define ZKP_FLAG_A 2u
@@ -72,50 +79,34 @@ struct strobe_t {
 #define ZKP_FLAG_M 16u
 #define ZKP_FLAG_K 32u
 
-ZKP_DEV void st_xor_byte(strobe_t& s, uint32_t pos, uint32_t b) { s.st[pos >> 3] ^= (uint64_t)b << ((pos & 7) * 8); }
-ZKP_DEV void st_set_byte(strobe_t& s, uint32_t pos, uint32_t b) {
-  const int sh = (pos & 7) * 8;
-  s.st[pos >> 3] = (s.st[pos >> 3] & ~(0xffULL << sh)) | ((uint64_t)b << sh);
-}
-ZKP_DEV uint32_t st_get_byte(const strobe_t& s, uint32_t pos) { return (uint32_t)(s.st[pos >> 3] >> ((pos & 7) * 8)) & 0xffu; }
+// Byte view of the state (little-endian lanes; char aliasing).  STROBE is byte-oriented and the rate (166) is not a
+// multiple of 8, so the state is addressed as bytes in local memory; an earlier variant that assembled bytes into the
+// lanes with variable 64-bit shifts produced wrong states on the device (though not in host emulation) and was dropped.
+// tests/test_gpu_toolbox.py::test_device_merlin_selftest guards this code with Merlin's conformance vector.
+ZKP_DEV uint8_t* st_bytes(strobe_t& s) { return (uint8_t*)s.st; }
 
-// Kept out of line on the device: the permutation is ~3.6k instructions reached from five call sites, and the
-// fully inlined variant was observed to produce wrong states once an absorb crossed the rate boundary (round-1
-// bisect against the host emulation; tests/test_gpu_toolbox.py::test_device_merlin_selftest guards it).
-#if ZKP_DEVICE_ASM
-__device__ __noinline__
-#else
-static
-#endif
-void strobe_run_f(strobe_t& s) {
-  st_xor_byte(s, s.pos, s.pos_begin);
-  st_xor_byte(s, s.pos + 1, 0x04);
-  st_xor_byte(s, ZKP_STROBE_R + 1, 0x80);
+// Kept out of line on the device: the permutation is ~3.6k instructions reached from several call sites.
+ZKP_DEV_NOINLINE void strobe_run_f(strobe_t& s) {
+  uint8_t* b = st_bytes(s);
+  b[s.pos] ^= (uint8_t)s.pos_begin;
+  b[s.pos + 1] ^= 0x04;
+  b[ZKP_STROBE_R + 1] ^= 0x80;
   keccak_f1600_dev(s.st);
   s.pos = 0;
   s.pos_begin = 0;
 }
-// absorb: bytes are gathered into one 64-bit word per state lane touched (one read-modify-write per lane instead
-// of one per byte); a group never crosses a lane or the rate boundary
 ZKP_DEV void strobe_absorb(strobe_t& s, const uint8_t* d, uint32_t n) {
-  while (n) {
-    const uint32_t off = s.pos & 7u;
-    uint32_t take = 8u - off;
-    if (take > n) take = n;
-    if (take > ZKP_STROBE_R - s.pos) take = ZKP_STROBE_R - s.pos;
-    uint64_t w = 0;
-    for (uint32_t b = 0; b < take; b++) w |= (uint64_t)d[b] << (8u * b);
-    s.st[s.pos >> 3] ^= w << (8u * off);
-    s.pos += take;
-    d += take;
-    n -= take;
-    if (s.pos == ZKP_STROBE_R) strobe_run_f(s);
+  uint8_t* b = st_bytes(s);
+  for (uint32_t i = 0; i < n; i++) {
+    b[s.pos] ^= d[i];
+    if (++s.pos == ZKP_STROBE_R) strobe_run_f(s);
   }
 }
 ZKP_DEV void strobe_squeeze(strobe_t& s, uint8_t* out, uint32_t n) {
+  uint8_t* b = st_bytes(s);
   for (uint32_t i = 0; i < n; i++) {
-    out[i] = (uint8_t)st_get_byte(s, s.pos);
-    st_set_byte(s, s.pos, 0);
+    out[i] = b[s.pos];
+    b[s.pos] = 0;
     if (++s.pos == ZKP_STROBE_R) strobe_run_f(s);
   }
 }
