@@ -397,8 +397,15 @@ def main():
         fe_sq_rate = eng.bench_field(1, 2048)
         fe_mul_rate = eng.bench_field(0, 2048)
         dec_time_at_peak = n_terms * (254.0 / fe_sq_rate + 30.0 / fe_mul_rate)
+        traffic, traffic_src = None, None
+        try:   # dram__bytes_read.sum + dram__bytes_write.sum of k_decompress from the committed ncu --set full capture
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r01_decompress_ncu.json")))
+            traffic = prof["traffic_bytes_per_launch"] * (n_terms / prof["n_points"])
+            traffic_src = "profiles/r01_decompress_ncu.json (ncu --set full at n=%d, scaled by n)" % prof["n_points"]
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": "k_decompress", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": dec_bytes, "kernel_ms": dec_ms,
                     "whole_path_hbm": {"bytes_per_proof": BYTES_PER_PROOF,
                                        "achieved_GBs": N * BYTES_PER_PROOF / (ms_step * 1e-3) / 1e9,
