@@ -292,6 +292,12 @@ static int32_t msm_ingest(zkp_ctx* ctx, const msm_plan& pl, const void* d_scalar
   cudaStream_t st = ctx->stream;
   int* flags = (int*)ctx->flags.p;
   const unsigned nb = (unsigned)((cnt + 255) / 256);
+  if (!ctx->profile && pl.sort == st) {   // fused: histogram reductions ride along with the decompression
+    k_ingest<<<nb, 256, 0, st>>>((const uint4*)d_points + 2 * base, (const uint4*)d_scalars + 2 * base, cnt,
+                                 (uint4*)ctx->niels.p + 6 * base, pl.c, pl.W, pl.B, (uint32_t*)ctx->hist.p, flags, base);
+    LAUNCH_CHECK(ctx);
+    return ZKP_OK;
+  }
   if (whole) STAGE(0);
   k_decompress<<<nb, 256, 0, st>>>((const uint4*)d_points + 2 * base, cnt, (uint4*)ctx->niels.p + 6 * base, flags, base);
   LAUNCH_CHECK(ctx);

@@ -161,6 +161,46 @@ __global__ void __launch_bounds__(256) k_recode(const uint4* __restrict__ scalar
   }
 }
 
+// K1+K2 fused: the digit histogram of term i is issued (fire-and-forget L2 reductions) before the ~31k-instruction
+// decompression of point i, whose LSU pipe is otherwise idle.  Used outside profiling mode.
+__global__ void __launch_bounds__(256) k_ingest(const uint4* __restrict__ enc, const uint4* __restrict__ scalars, size_t n,
+                                                uint4* __restrict__ niels, int c, int W, uint32_t B,
+                                                uint32_t* __restrict__ hist, int* __restrict__ flags, size_t base) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  {
+    uint32_t s[8], k[8];
+    load_words8(s, scalars + 2 * i);
+    uint32_t neg;
+    uint32_t canonical = sc_fold_sign(k, neg, s);
+    if (!canonical) {
+      atomicMin(&flags[1], (int)(base + i));
+    } else {
+      uint32_t carry = 0;
+      for (int w = 0; w < W; w++) {
+        uint32_t mag, dneg;
+        sc_digit(mag, dneg, carry, k, w, c);
+        if (mag != 0) atomicAdd(hist + (size_t)w * B + (mag - 1), 1u);
+      }
+    }
+  }
+  uint32_t w8[8];
+  load_words8(w8, enc + 2 * i);
+  fe x, y, t;
+  uint32_t ok = ristretto_decode(x, y, t, w8);
+  ge_aniels q;
+  if (ok) {
+    ge_aniels_from_affine(q, x, y, t);
+  } else {
+    ge_aniels_identity(q);
+    atomicMin(&flags[0], (int)(base + i));
+  }
+  uint4* o = niels + 6 * i;
+  store_fe(o, q.yplusx);
+  store_fe(o + 2, q.yminusx);
+  store_fe(o + 4, q.xy2d);
+}
+
 // K3: per-window exclusive scan.  One block (1024 threads) per window.
 __global__ void __launch_bounds__(1024) k_scan(const uint32_t* __restrict__ hist, uint32_t B,
                                                uint32_t* __restrict__ offs,    // [W][B+1]
