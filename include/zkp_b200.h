@@ -153,7 +153,9 @@ int32_t zkp_selftest_hash(zkp_ctx* ctx, uint8_t* out32);
  * rate in operations per second in *ops_per_sec.  kind: 0 = fe_mul (8x32 saturated), 1 = fe_sq,
  * 2 = 5x51-limb multiply (u64 products), 3 = 10x25.5-limb multiply, 4 / 5 = 32 wide multiplies per
  * iteration without / with carry chains (raw IMAD.WIDE issue rate; ops counted per iteration), 6 / 7 =
- * fe_mul / fe_sq with the shift-add reduction variant.                                                    */
+ * fe_mul / fe_sq with the shift-add reduction variant, 8 / 9 = fe_mul / fe_sq with the variable-time tail
+ * (cold-branch carry fold; what decompression and bucket accumulation run), 10 / 11 = signed mixed point
+ * addition (7 M, the bucket-accumulation step) with constant-time / variable-time tails.                  */
 int32_t zkp_bench_field(zkp_ctx* ctx, int32_t kind, int32_t iters, double* ops_per_sec);
 
 /* Diagnostic: half of the warps run the integer fe_sq chain, the other half a DFMA chain (160 per fe_sq).

@@ -3,6 +3,7 @@
 // nothing in zkp_b200/ loads this library.
 #include <cstring>
 #include "../../zkp_b200/csrc/fe.cuh"
+#include "../../zkp_b200/csrc/fe64.cuh"
 #include "../../zkp_b200/csrc/ge.cuh"
 #include "../../zkp_b200/csrc/sc.cuh"
 #include "../../zkp_b200/csrc/hash.cuh"
@@ -18,11 +19,57 @@ void emul_fe_mul(uint8_t* r, const uint8_t* a, const uint8_t* b) { fe x; fe_mul(
 void emul_fe_sq(uint8_t* r, const uint8_t* a) { fe x; fe_sq(x, ld(a)); st(r, x); }
 void emul_fe_add(uint8_t* r, const uint8_t* a, const uint8_t* b) { fe x; fe_add(x, ld(a), ld(b)); st(r, x); }
 void emul_fe_sub(uint8_t* r, const uint8_t* a, const uint8_t* b) { fe x; fe_sub(x, ld(a), ld(b)); st(r, x); }
+// the variable-time tails (cold-branch carry fold) used by decompression and bucket accumulation
+void emul_fe_mul_vt(uint8_t* r, const uint8_t* a, const uint8_t* b) { fe x; fe_mul_vt(x, ld(a), ld(b)); st(r, x); }
+void emul_fe_sq_vt(uint8_t* r, const uint8_t* a) { fe x; fe_sq_vt(x, ld(a)); st(r, x); }
+void emul_fe_add_vt(uint8_t* r, const uint8_t* a, const uint8_t* b) { fe x; fe_add_vt(x, ld(a), ld(b)); st(r, x); }
+void emul_fe_sub_vt(uint8_t* r, const uint8_t* a, const uint8_t* b) { fe x; fe_sub_vt(x, ld(a), ld(b)); st(r, x); }
+void emul_fe_pow22523_vt(uint8_t* r, const uint8_t* a) { fe x; fe_pow22523<true>(x, ld(a)); st(r, x); }
 void emul_fe_canon(uint8_t* r, const uint8_t* a) { fe x; fe_canon(x, ld(a)); st(r, x); }
 void emul_fe_invert(uint8_t* r, const uint8_t* a) { fe x; fe_invert(x, ld(a)); st(r, x); }
 void emul_fe_pow22523(uint8_t* r, const uint8_t* a) { fe x; fe_pow22523(x, ld(a)); st(r, x); }
 void emul_fe_from_limbs51(uint8_t* r, const uint64_t* l) { fe x; fe_from_limbs51(x, l); st(r, x); }
 void emul_fe_to_limbs51(uint64_t* l, const uint8_t* a) { fe_to_limbs51(l, ld(a)); }
+
+// ---- the FP64 twin of the field arithmetic (fe64.cuh): in/out as 32-byte integers; `max_q` (optional) receives the
+// largest |limb / weight| seen in the result, for the exactness bounds
+static double fe64_maxq(const fe64& x) {
+  double m = 0;
+  for (int i = 0; i < 12; i++) { double q = fabs(ldexp(x.v[i], -ZKP_FE64_OFF(i))); if (q > m) m = q; }
+  return m;
+}
+void emul_fe64_roundtrip(uint8_t* r, const uint8_t* a) { fe64 x; fe64_from_fe(x, ld(a)); fe y; fe64_to_fe(y, x); st(r, y); }
+double emul_fe64_sq(uint8_t* r, const uint8_t* a, int n) {
+  fe64 x; fe64_from_fe(x, ld(a)); double m = 0;
+  for (int i = 0; i < n; i++) { fe64_sq(x, x); double q = fe64_maxq(x); if (q > m) m = q; }
+  fe y; fe64_to_fe(y, x); st(r, y); return m;
+}
+double emul_fe64_mul(uint8_t* r, const uint8_t* a, const uint8_t* b) {
+  fe64 x, y, z; fe64_from_fe(x, ld(a)); fe64_from_fe(y, ld(b)); fe64_mul(z, x, y);
+  fe o; fe64_to_fe(o, z); st(r, o); return fe64_maxq(z);
+}
+void emul_fe_pow22523_fp64(uint8_t* r, const uint8_t* a) { fe x; fe_pow22523_fp64(x, ld(a)); st(r, x); }
+// limbs are integers times their weight, and columns stay below 2^53: returns the largest |column| / 2^(o_k) of a^2
+// computed in long double beside the double computation (0 if any limb is not an integer multiple of its weight)
+double emul_fe64_column_bound(const uint8_t* a) {
+  fe64 x; fe64_from_fe(x, ld(a));
+  double worst = 0;
+  for (int rep = 0; rep < 3; rep++) {
+    for (int i = 0; i < 12; i++) { double q = ldexp(x.v[i], -ZKP_FE64_OFF(i)); if (q != floor(q)) return 0; }
+    for (int k = 0; k < 12; k++) {
+      long double s = 0;
+      for (int i = 0; i < 12; i++) for (int j = 0; j < 12; j++) {
+        long double p = fabsl((long double)x.v[i] * x.v[j]);
+        if (i + j == k) s += p;
+        if (i + j == k + 12) s += p * 19.0L * ldexpl(1.0L, -255);
+      }
+      double b = (double)ldexpl(s, -ZKP_FE64_OFF(k));
+      if (b > worst) worst = b;
+    }
+    fe64_sq(x, x);
+  }
+  return worst;
+}
 
 // ---- group / ristretto ----
 static ge_ext ldp(const uint8_t* p) { ge_ext r; memcpy(&r, p, 128); return r; }
@@ -30,6 +77,12 @@ static ge_ext ldp(const uint8_t* p) { ge_ext r; memcpy(&r, p, 128); return r; }
 int emul_decode(uint8_t* out, const uint8_t* enc) {
   uint32_t w[8]; memcpy(w, enc, 32);
   fe x, y, t; uint32_t ok = ristretto_decode(x, y, t, w);
+  memcpy(out, x.v, 32); memcpy(out + 32, y.v, 32); memcpy(out + 64, t.v, 32);
+  return (int)ok;
+}
+int emul_decode_vt(uint8_t* out, const uint8_t* enc) {
+  uint32_t w[8]; memcpy(w, enc, 32);
+  fe x, y, t; uint32_t ok = ristretto_decode<true>(x, y, t, w);
   memcpy(out, x.v, 32); memcpy(out + 32, y.v, 32); memcpy(out + 64, t.v, 32);
   return (int)ok;
 }
@@ -46,6 +99,11 @@ void emul_madd_signed(uint8_t* out, const uint8_t* pt128, const uint8_t* aff96, 
   fe x, y, t; memcpy(x.v, aff96, 32); memcpy(y.v, aff96 + 32, 32); memcpy(t.v, aff96 + 64, 32);
   ge_aniels q; ge_aniels_from_affine(q, x, y, t);
   ge_ext r; ge_madd_signed(r, ldp(pt128), q, (uint32_t)neg); memcpy(out, &r, 128);
+}
+void emul_madd_signed_vt(uint8_t* out, const uint8_t* pt128, const uint8_t* aff96, int neg) {
+  fe x, y, t; memcpy(x.v, aff96, 32); memcpy(y.v, aff96 + 32, 32); memcpy(t.v, aff96 + 64, 32);
+  ge_aniels q; ge_aniels_from_affine(q, x, y, t);
+  ge_ext r; ge_madd_signed<true>(r, ldp(pt128), q, (uint32_t)neg); memcpy(out, &r, 128);
 }
 void emul_add(uint8_t* out, const uint8_t* p, const uint8_t* q) { ge_ext r; ge_add(r, ldp(p), ldp(q)); memcpy(out, &r, 128); }
 void emul_double(uint8_t* out, const uint8_t* p) { ge_ext r; ge_double(r, ldp(p)); memcpy(out, &r, 128); }

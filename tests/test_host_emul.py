@@ -18,9 +18,9 @@ P = R.P
 def lib():
     src = os.path.join(HERE, "host_emul", "emul.cpp")
     out = os.path.join(HERE, "host_emul", "libemul.so")
-    deps = [src] + [os.path.join(HERE, "..", "zkp_b200", "csrc", f) for f in ("fe.cuh", "ge.cuh", "sc.cuh", "hash.cuh", "scl.cuh")]
+    deps = [src] + [os.path.join(HERE, "..", "zkp_b200", "csrc", f) for f in ("fe.cuh", "fe64.cuh", "ge.cuh", "sc.cuh", "hash.cuh", "scl.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
-        subprocess.check_call(["g++", "-O1", "-shared", "-fPIC", "-DZKP_HOST_EMUL", "-x", "c++", src, "-o", out])
+        subprocess.check_call(["g++", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-DZKP_HOST_EMUL", "-x", "c++", src, "-o", out])
     return ctypes.CDLL(out)
 
 
@@ -43,15 +43,54 @@ def test_field_ops(lib):
     vals = edge + [rnd.getrandbits(256) for _ in range(150)] + [rnd.getrandbits(256) | (2**256 - 2**200) for _ in range(30)]
     for a in vals:
         assert _c1(lib.emul_fe_sq, a) % P == a * a % P
+        assert _c1(lib.emul_fe_sq_vt, a) == _c1(lib.emul_fe_sq, a)
         assert _c1(lib.emul_fe_canon, a) == a % P
         for b in rnd.sample(vals, 8) + edge:
             assert _c2(lib.emul_fe_mul, a, b) % P == a * b % P
             assert _c2(lib.emul_fe_add, a, b) % P == (a + b) % P
             assert _c2(lib.emul_fe_sub, a, b) % P == (a - b) % P
+            # the variable-time tails return the very same 256-bit representative as the constant-time ones
+            assert _c2(lib.emul_fe_mul_vt, a, b) == _c2(lib.emul_fe_mul, a, b)
+            assert _c2(lib.emul_fe_add_vt, a, b) == _c2(lib.emul_fe_add, a, b)
+            assert _c2(lib.emul_fe_sub_vt, a, b) == _c2(lib.emul_fe_sub, a, b)
+    # operands that drive the cold branches of the tails: a carry / borrow leaving limb 0, rippling through all-ones or
+    # all-zero limbs, and wrapping past 2^256 / below 0 a second time
+    M = 2**256
+    cold = [(M - 1, 1), (M - 1, M - 1), (M - 38, 38), (M - 37, 75), (M - 1, 38), (2**255, 2**255), (M - 2**32, 2**32 + 5),
+            (0, 1), (0, M - 1), (37, 38), (5, M - 20), (2**32, 2**32 + 1), (2**224, 2**224 + 1), (0, 2**255), (1, 39),
+            (M - 19, M - 19), (M - 2**32 + 1, 2**32 - 1 + 38)]
+    for a, b in cold + [(b, a) for a, b in cold]:
+        for f_vt, f_ct, op in ((lib.emul_fe_add_vt, lib.emul_fe_add, lambda x, y: x + y),
+                               (lib.emul_fe_sub_vt, lib.emul_fe_sub, lambda x, y: x - y),
+                               (lib.emul_fe_mul_vt, lib.emul_fe_mul, lambda x, y: x * y)):
+            r = _c2(f_vt, a, b)
+            assert r == _c2(f_ct, a, b) and r % P == op(a, b) % P
+    # products whose first-pass sum lo + 38*hi = c8*2^256 + x has limb 0 of x within 38*c8 of 2^32: the carry out of
+    # limb 0 in the tail of fe_reduce512 (probability ~1e-7 for random operands, so constructed: b = S / a mod 2p)
+    M2P = M - 38
+    found = 0
+    for trial in range(4000):
+        c8 = rnd.randrange(1, 38)
+        hi_limbs = rnd.choice([0, M - 2**32, rnd.getrandbits(224) << 32])   # all-zero / all-ones / random upper limbs
+        x = hi_limbs + 2**32 - 1 - rnd.randrange(38 * c8)
+        S = c8 * M + x
+        a = rnd.getrandbits(256) | 1
+        if a % P == 0:
+            continue
+        b = S * pow(a, -1, M2P) % M2P
+        t = a * b
+        lo9 = (t % M) + 38 * (t >> 256)
+        if (lo9 & 0xFFFFFFFF) + 38 * (lo9 >> 256) < 2**32:
+            continue
+        found += 1
+        r = _c2(lib.emul_fe_mul_vt, a, b)
+        assert r == _c2(lib.emul_fe_mul, a, b) and r % P == a * b % P
+    assert found >= 20, found
     for a in vals[:40]:
         if a % P:
             assert _c1(lib.emul_fe_invert, a) * a % P == 1
         assert _c1(lib.emul_fe_pow22523, a) % P == pow(a, (P - 5) // 8, P)
+        assert _c1(lib.emul_fe_pow22523_vt, a) == _c1(lib.emul_fe_pow22523, a)
     # 51-bit limb interface, including unreduced limbs up to 2^54
     for _ in range(50):
         limbs = [rnd.getrandbits(54) for _ in range(5)]
@@ -63,6 +102,43 @@ def test_field_ops(lib):
         out = (ctypes.c_uint64 * 5)()
         lib.emul_fe_to_limbs51(out, r.raw)
         assert sum(int(out[i]) << (51 * i) for i in range(5)) == val % P and all(int(o) < 2**51 for o in out)
+
+
+def test_fp64_field(lib):
+    """fe64.cuh: the FP64-pipe twin of the field arithmetic is exact (same residues as the integer path and the oracle),
+    its limbs stay integral and balanced, and its columns stay below 2^53."""
+    rnd = random.Random(11)
+    lib.emul_fe64_sq.restype = ctypes.c_double
+    lib.emul_fe64_mul.restype = ctypes.c_double
+    lib.emul_fe64_column_bound.restype = ctypes.c_double
+    M = 2**256
+    edge = [0, 1, 2, 19, P - 1, P, P + 1, 2**255 - 1, 2**255, M - 1, M - 38, 2 * P, (M - 1) // 3, 2**234, 2**234 - 1,
+            sum(((1 << 21) - 1) << o for o in (0, 22, 43, 64, 85, 107, 128, 149, 170, 192, 213, 234)),      # limbs at +max
+            sum((1 << 21) << o for o in (0, 22, 43, 64, 85, 107, 128, 149, 170, 192, 213, 234)) % M]        # limbs at the rounding tie
+    vals = edge + [rnd.getrandbits(256) for _ in range(200)]
+    r = ctypes.create_string_buffer(32)
+    for a in vals:
+        ab = a.to_bytes(32, "little")
+        lib.emul_fe64_roundtrip(r, ab)
+        v = int.from_bytes(r.raw, "little")
+        assert v % P == a % P and v < M
+        for n in (1, 2, 7):
+            mq = lib.emul_fe64_sq(r, ab, n)
+            assert int.from_bytes(r.raw, "little") % P == pow(a, 2**n, P)
+            assert mq <= 2**21 + 2**13          # balanced limbs (+ the slack of the two second-round carries)
+        cb = lib.emul_fe64_column_bound(ab)      # 0 would also flag a limb that is not an integer multiple of its weight
+        assert cb < 2**52 and (cb > 0) == (a % P != 0)
+        for b in rnd.sample(vals, 6) + edge[:8]:
+            mq = lib.emul_fe64_mul(r, ab, b.to_bytes(32, "little"))
+            assert int.from_bytes(r.raw, "little") % P == a * b % P
+            assert mq <= 2**21 + 2**13
+    for a in vals[:60]:
+        lib.emul_fe_pow22523_fp64(r, a.to_bytes(32, "little"))
+        assert int.from_bytes(r.raw, "little") % P == pow(a, (P - 5) // 8, P)
+    # a long squaring chain keeps the invariants (what the 254-squaring exponentiation relies on)
+    a = rnd.getrandbits(255)
+    mq = lib.emul_fe64_sq(r, a.to_bytes(32, "little"), 2000)
+    assert int.from_bytes(r.raw, "little") % P == pow(a, 2**2000, P) and mq <= 2**21 + 2**13
 
 
 def _pb(p):
@@ -89,6 +165,8 @@ def test_group_and_codec(lib):
         assert lib.emul_decode(a, e) == 1
         d = R.decompress(e)
         assert [int.from_bytes(a.raw[i * 32:(i + 1) * 32], "little") % P for i in range(3)] == [d[0], d[1], d[3]]
+        a2 = ctypes.create_string_buffer(96)
+        assert lib.emul_decode_vt(a2, e) == 1 and a2.raw == a.raw
         affs.append(a.raw)
     for _ in range(300):
         e = rnd.randbytes(32)
@@ -96,6 +174,7 @@ def test_group_and_codec(lib):
             e = e[:31] + bytes([e[31] & 0x7F])
         a = ctypes.create_string_buffer(96)
         assert lib.emul_decode(a, e) == (R.decompress(e) is not None)
+        assert lib.emul_decode_vt(a, e) == (R.decompress(e) is not None)
     for i in range(len(pts) - 2):
         p, q = pts[i], pts[i + 1]
         out = ctypes.create_string_buffer(128)
@@ -107,6 +186,9 @@ def test_group_and_codec(lib):
             lib.emul_madd_signed(out, _pb(p), affs[i + 1], neg)
             r = _pf(out.raw)
             assert R.on_curve(r) and R.compress(r) == R.compress(exp)
+            out2 = ctypes.create_string_buffer(128)
+            lib.emul_madd_signed_vt(out2, _pb(p), affs[i + 1], neg)
+            assert out2.raw == out.raw
         lib.emul_add(out, _pb(p), _pb(q))
         r, exp = _pf(out.raw), R.pt_add(p, q)
         assert R.on_curve(r) and (r[0] * exp[2] - exp[0] * r[2]) % P == 0 and (r[1] * exp[2] - exp[1] * r[2]) % P == 0

@@ -7,7 +7,10 @@ from zkp_b200 import Engine  # noqa: E402
 
 eng = Engine(0)
 names = ["fe_mul 8x32", "fe_sq 8x32", "fe51_mul 5x51", "fe25_mul 10x25.5", "32 plain IMAD.WIDE / iter", "32 carry-chained IMAD.WIDE / iter",
-         "fe_mul 8x32, shift-add reduce", "fe_sq 8x32, shift-add reduce"]
+         "fe_mul 8x32, shift-add reduce", "fe_sq 8x32, shift-add reduce", "fe_mul 8x32, vartime tail", "fe_sq 8x32, vartime tail",
+         "mixed point addition (7M), ct tails", "mixed point addition (7M), vartime tails",
+         "squaring chain, 8 int warps / block", "squaring chain, 6 int + 2 FP64 warps", "squaring chain, 5 int + 3 FP64 warps",
+         "squaring chain, 4 int + 4 FP64 warps", "squaring chain, 8 FP64 warps"]
 out = {}
 for k, n in enumerate(names):
     r = eng.bench_field(k, 2048)

@@ -947,7 +947,7 @@ extern "C" int32_t zkp_bench_dual(zkp_ctx* ctx, int32_t mode, int32_t iters, dou
 }
 
 extern "C" int32_t zkp_bench_field(zkp_ctx* ctx, int32_t kind, int32_t iters, double* ops_per_sec) {
-  if (!ctx || !ops_per_sec || iters <= 0 || kind < 0 || kind > 7) return ZKP_ERR_SIZE;
+  if (!ctx || !ops_per_sec || iters <= 0 || kind < 0 || kind > 16) return ZKP_ERR_SIZE;
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   int sms = 0;
   CUDA_TRY(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
@@ -957,13 +957,26 @@ extern "C" int32_t zkp_bench_field(zkp_ctx* ctx, int32_t kind, int32_t iters, do
   CUDA_TRY(ctx, cudaEventCreate(&e0));
   CUDA_TRY(ctx, cudaEventCreate(&e1));
   float best = 1e30f;
+  // kinds 12..16 (dynamic pool): `iters` squarings per thread of the usual grid, cut into units of 32 lanes x 256
+  const int pool_units = (int)(((long long)threads * blocks / 32) * iters / 256);
+  ENSURE(ctx, ctx->aux1, 256);
   for (int rep = 0; rep < 4; rep++) {
+    if (kind >= 12) CUDA_TRY(ctx, cudaMemsetAsync(ctx->aux1.p, 0, 4, ctx->stream));
     CUDA_TRY(ctx, cudaEventRecord(e0, ctx->stream));
     switch (kind) {
-      case 0: k_bench_mul32<0><<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, iters); break;
-      case 1: k_bench_sq32<0><<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, iters); break;
-      case 6: k_bench_mul32<1><<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, iters); break;
-      case 7: k_bench_sq32<1><<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, iters); break;
+      case 0: k_bench_mul32<0, false><<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, iters); break;
+      case 1: k_bench_sq32<0, false><<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, iters); break;
+      case 6: k_bench_mul32<1, false><<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, iters); break;
+      case 7: k_bench_sq32<1, false><<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, iters); break;
+      case 8: k_bench_mul32<0, true><<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, iters); break;
+      case 9: k_bench_sq32<0, true><<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, iters); break;
+      case 10: k_bench_madd<false><<<blocks * 2, threads / 2, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, iters); break;
+      case 11: k_bench_madd<true><<<blocks * 2, threads / 2, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, iters); break;
+      case 12: k_bench_sq_mixed<0><<<sms * 2, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, pool_units, (unsigned int*)ctx->aux1.p); break;
+      case 13: k_bench_sq_mixed<2><<<sms * 2, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, pool_units, (unsigned int*)ctx->aux1.p); break;
+      case 14: k_bench_sq_mixed<3><<<sms * 2, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, pool_units, (unsigned int*)ctx->aux1.p); break;
+      case 15: k_bench_sq_mixed<4><<<sms * 2, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, pool_units, (unsigned int*)ctx->aux1.p); break;
+      case 16: k_bench_sq_mixed<8><<<sms * 2, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, pool_units, (unsigned int*)ctx->aux1.p); break;
       case 2: k_bench_mul51<<<blocks, threads, 0, ctx->stream>>>((unsigned long long*)ctx->aux0.p, iters); break;
       case 3: k_bench_mul25<<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, iters); break;
       case 4: k_bench_wide_plain<<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, iters); break;
@@ -979,6 +992,7 @@ extern "C" int32_t zkp_bench_field(zkp_ctx* ctx, int32_t kind, int32_t iters, do
   }
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
-  *ops_per_sec = (double)threads * blocks * (double)iters / (best * 1e-3);
+  if (kind >= 12) *ops_per_sec = (double)pool_units * 32.0 * 256.0 / (best * 1e-3);
+  else *ops_per_sec = (double)threads * blocks * (double)iters / (best * 1e-3);
   return ZKP_OK;
 }

@@ -4,10 +4,12 @@
 // hidden and the measured rate is the pipe's throughput for that instruction mix.
 #pragma once
 #include "fe.cuh"
+#include "ge.cuh"
+#include "fe64.cuh"
 
 namespace zkp {
 
-template <int RED>
+template <int RED, bool VT>
 __global__ void __launch_bounds__(256) k_bench_mul32(uint32_t* out, int iters) {
   uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
   fe a, b;
@@ -18,14 +20,14 @@ __global__ void __launch_bounds__(256) k_bench_mul32(uint32_t* out, int iters) {
   }
 #pragma unroll 1
   for (int k = 0; k < iters; k += 2) {
-    fe_mul_t<RED>(a, a, b);
-    fe_mul_t<RED>(b, b, a);
+    fe_mul_t<RED, VT>(a, a, b);
+    fe_mul_t<RED, VT>(b, b, a);
   }
 #pragma unroll
   for (int i = 0; i < 8; i++) out[(size_t)gid * 16 + i] = a.v[i] ^ b.v[i];
 }
 
-template <int RED>
+template <int RED, bool VT>
 __global__ void __launch_bounds__(256) k_bench_sq32(uint32_t* out, int iters) {
   uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
   fe a;
@@ -33,11 +35,71 @@ __global__ void __launch_bounds__(256) k_bench_sq32(uint32_t* out, int iters) {
   for (int i = 0; i < 8; i++) a.v[i] = gid * 2654435761u + i * 40503u + 1;
 #pragma unroll 1
   for (int k = 0; k < iters; k += 2) {
-    fe_sq_t<RED>(a, a);
-    fe_sq_t<RED>(a, a);
+    fe_sq_t<RED, VT>(a, a);
+    fe_sq_t<RED, VT>(a, a);
   }
 #pragma unroll
   for (int i = 0; i < 8; i++) out[(size_t)gid * 16 + i] = a.v[i];
+}
+
+// ---- signed mixed addition chain (the inner operation of bucket accumulation): acc += (+/-) q, register-resident
+template <bool VT>
+__global__ void __launch_bounds__(128, 4) k_bench_madd(uint32_t* out, int iters) {
+  uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+  ge_ext acc;
+  ge_aniels q;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    acc.X.v[i] = gid * 2654435761u + i * 40503u + 1;
+    acc.Y.v[i] = gid * 2246822519u + i * 3266489917u + 7;
+    acc.Z.v[i] = gid * 668265263u + i * 374761393u + 3;
+    acc.T.v[i] = gid * 2870177450u + i * 2147483647u + 5;
+    q.yplusx.v[i] = gid * 1597334677u + i * 3812015801u + 11;
+    q.yminusx.v[i] = gid * 958689277u + i * 1103515245u + 13;
+    q.xy2d.v[i] = gid * 3323815723u + i * 12345u + 17;
+  }
+#pragma unroll 1
+  for (int k = 0; k < iters; k++) ge_madd_signed<VT>(acc, acc, q, (uint32_t)k & 1u);
+#pragma unroll
+  for (int i = 0; i < 8; i++) out[(size_t)gid * 16 + i] = acc.X.v[i] ^ acc.Y.v[i] ^ acc.Z.v[i] ^ acc.T.v[i];
+}
+
+// ---- integer and FP64 squaring chains side by side: warps [0, NFP) of every 8-warp block square on the FP64 pipe
+// (fe64_sq), the others on the integer pipes (fe_sq, variable-time tail).  Work is handed out dynamically: a warp
+// takes the next unit (a chain of 256 squarings per lane) from a global counter until `units` are done, so slower
+// warps simply take fewer units -- the schedule k_decompress uses.  Figure of merit: squarings per second over all
+// warps (zkp_bench_field kinds 12..16 = NFP 0, 2, 3, 4, 8).
+template <int NFP>
+__global__ void __launch_bounds__(256, 2) k_bench_sq_mixed(uint32_t* out, int units, unsigned int* counter) {
+  const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31;
+  const bool fp = (int)(threadIdx.x >> 5) < NFP;
+  uint32_t x = 0;
+  for (;;) {
+    unsigned int u = 0;
+    if (lane == 0) u = atomicAdd(counter, 1u);
+    u = __shfl_sync(0xffffffffu, u, 0);
+    if (u >= (unsigned int)units) break;
+    fe a;
+#pragma unroll
+    for (int i = 0; i < 8; i++) a.v[i] = (u * 32 + lane) * 2654435761u + i * 40503u + 1;
+    if (fp) {
+      fe64 t;
+      fe64_from_fe(t, a);
+#pragma unroll 1
+      for (int k = 0; k < 256; k++) fe64_sq(t, t);
+      fe64_to_fe(a, t);
+    } else {
+#pragma unroll 1
+      for (int k = 0; k < 256; k += 2) {
+        fe_sq_vt(a, a);
+        fe_sq_vt(a, a);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) x ^= a.v[i];
+  }
+  out[gid] = x;
 }
 
 // ---- 5 x 51-bit limbs, 64x64->128 products (the layout of dalek's u64 backend, FieldElement51::mul [ext]) --

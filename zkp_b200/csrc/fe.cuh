@@ -329,10 +329,154 @@ ZKP_DEV uint32_t sub_word8(uint32_t* r, uint32_t k) {
 #endif
 }
 
+// r[0..14] = a[0..14] + b[0..14] as ONE carry chain (the caller knows the sum fits: no carry out)
+ZKP_DEV void add15(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+#if ZKP_DEVICE_ASM
+  asm("add.cc.u32 %0, %15, %30;\n\t"
+      "addc.cc.u32 %1, %16, %31;\n\t"
+      "addc.cc.u32 %2, %17, %32;\n\t"
+      "addc.cc.u32 %3, %18, %33;\n\t"
+      "addc.cc.u32 %4, %19, %34;\n\t"
+      "addc.cc.u32 %5, %20, %35;\n\t"
+      "addc.cc.u32 %6, %21, %36;\n\t"
+      "addc.cc.u32 %7, %22, %37;\n\t"
+      "addc.cc.u32 %8, %23, %38;\n\t"
+      "addc.cc.u32 %9, %24, %39;\n\t"
+      "addc.cc.u32 %10, %25, %40;\n\t"
+      "addc.cc.u32 %11, %26, %41;\n\t"
+      "addc.cc.u32 %12, %27, %42;\n\t"
+      "addc.cc.u32 %13, %28, %43;\n\t"
+      "addc.u32 %14, %29, %44;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+        "r"(a[8]), "r"(a[9]), "r"(a[10]), "r"(a[11]), "r"(a[12]), "r"(a[13]), "r"(a[14]),
+        "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]),
+        "r"(b[8]), "r"(b[9]), "r"(b[10]), "r"(b[11]), "r"(b[12]), "r"(b[13]), "r"(b[14]));
+#else
+  uint64_t c = 0;
+  uint32_t t[15];
+  for (int i = 0; i < 15; i++) {
+    uint64_t s = (uint64_t)a[i] + b[i] + c;
+    t[i] = (uint32_t)s;
+    c = s >> 32;
+  }
+  for (int i = 0; i < 15; i++) r[i] = t[i];
+#endif
+}
+
+// r[0..7] = a[0..7] + b[0..7], carry out dropped (the caller knows there is none)
+ZKP_DEV void add8_nc(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+#if ZKP_DEVICE_ASM
+  asm("add.cc.u32 %0, %8, %16;\n\t"
+      "addc.cc.u32 %1, %9, %17;\n\t"
+      "addc.cc.u32 %2, %10, %18;\n\t"
+      "addc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, %20;\n\t"
+      "addc.cc.u32 %5, %13, %21;\n\t"
+      "addc.cc.u32 %6, %14, %22;\n\t"
+      "addc.u32 %7, %15, %23;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+        "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+#else
+  uint64_t c = 0;
+  uint32_t t[8];
+  for (int i = 0; i < 8; i++) {
+    uint64_t s = (uint64_t)a[i] + b[i] + c;
+    t[i] = (uint32_t)s;
+    c = s >> 32;
+  }
+  for (int i = 0; i < 8; i++) r[i] = t[i];
+#endif
+}
+
+// acc[0..15] += (a0^2, ..., a7^2) laid out as eight 64-bit pairs, ONE carry chain (the sum fits in 512 bits)
+ZKP_DEV void sqr8(uint32_t* acc, const uint32_t* a) {
+#if ZKP_DEVICE_ASM
+  asm("mad.lo.cc.u32 %0, %16, %16, %0;\n\t"
+      "madc.hi.cc.u32 %1, %16, %16, %1;\n\t"
+      "madc.lo.cc.u32 %2, %17, %17, %2;\n\t"
+      "madc.hi.cc.u32 %3, %17, %17, %3;\n\t"
+      "madc.lo.cc.u32 %4, %18, %18, %4;\n\t"
+      "madc.hi.cc.u32 %5, %18, %18, %5;\n\t"
+      "madc.lo.cc.u32 %6, %19, %19, %6;\n\t"
+      "madc.hi.cc.u32 %7, %19, %19, %7;\n\t"
+      "madc.lo.cc.u32 %8, %20, %20, %8;\n\t"
+      "madc.hi.cc.u32 %9, %20, %20, %9;\n\t"
+      "madc.lo.cc.u32 %10, %21, %21, %10;\n\t"
+      "madc.hi.cc.u32 %11, %21, %21, %11;\n\t"
+      "madc.lo.cc.u32 %12, %22, %22, %12;\n\t"
+      "madc.hi.cc.u32 %13, %22, %22, %13;\n\t"
+      "madc.lo.cc.u32 %14, %23, %23, %14;\n\t"
+      "madc.hi.u32 %15, %23, %23, %15;"
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]),
+        "+r"(acc[7]), "+r"(acc[8]), "+r"(acc[9]), "+r"(acc[10]), "+r"(acc[11]), "+r"(acc[12]), "+r"(acc[13]),
+        "+r"(acc[14]), "+r"(acc[15])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]));
+#else
+  uint64_t c = 0;
+  for (int k = 0; k < 8; k++) {
+    uint64_t p = (uint64_t)a[k] * a[k];
+    uint64_t lo = (uint64_t)acc[2 * k] + (uint32_t)p + c;
+    acc[2 * k] = (uint32_t)lo;
+    uint64_t hi = (uint64_t)acc[2 * k + 1] + (uint32_t)(p >> 32) + (lo >> 32);
+    acc[2 * k + 1] = (uint32_t)hi;
+    c = hi >> 32;
+  }
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------------
+// tails: r[0..7] (+|-)= k with the 2^256 wrap folded back as 38.  k is small (< 2^12), so a carry out of limb 0
+// has probability ~ k / 2^32.  The constant-time form always ripples through the eight limbs; the variable-time
+// form (VT, public data only: decompression and bucket accumulation of the verifier's MSM) tests limb 0 and takes
+// a cold branch.  Both produce the same value.
+// ------------------------------------------------------------------------------------------------------
+template <bool VT>
+ZKP_DEV void fe_tail_add(uint32_t* r, uint32_t k) {
+  if (VT) {
+    r[0] += k;
+    if (r[0] < k) {   // carry out of limb 0: cold
+      uint32_t c = 1u;
+#pragma unroll
+      for (int i = 1; i < 8; i++) {
+        r[i] += c;
+        c = (r[i] < c) ? 1u : 0u;
+      }
+      r[0] += 38u * c;   // wrapped past 2^256: r is tiny, cannot carry again
+    }
+  } else {
+    uint32_t c = add_word8(r, k);
+    r[0] += 38u * c;
+  }
+}
+template <bool VT>
+ZKP_DEV void fe_tail_sub(uint32_t* r, uint32_t k) {
+  if (VT) {
+    uint32_t old = r[0];
+    r[0] -= k;
+    if (old < k) {   // borrow out of limb 0: cold
+      uint32_t b = 1u;
+#pragma unroll
+      for (int i = 1; i < 8; i++) {
+        uint32_t o = r[i];
+        r[i] -= b;
+        b = (o < b) ? 1u : 0u;
+      }
+      r[0] -= 38u * b;   // wrapped below 0: r is just under 2^256, cannot borrow again
+    }
+  } else {
+    uint32_t b = sub_word8(r, k);
+    r[0] -= 38u * b;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------
 // reduction of a 16-limb product t (value < 2^512) to 8 limbs (< 2^256): 2^256 = 38 (mod p)
 // ------------------------------------------------------------------------------------------------------
-ZKP_DEV void fe_reduce512(fe& r, const uint32_t* t) {
+template <bool VT>
+ZKP_DEV void fe_reduce512_t(fe& r, const uint32_t* t) {
   uint32_t lo[9], od[8];
 #pragma unroll
   for (int i = 0; i < 8; i++) lo[i] = t[i];
@@ -343,12 +487,12 @@ ZKP_DEV void fe_reduce512(fe& r, const uint32_t* t) {
   mulw(od[2], od[3], t[11], 38u);
   mulw(od[4], od[5], t[13], 38u);
   mulw(od[6], od[7], t[15], 38u);
-  add8(lo + 1, lo + 1, od);        // lo[8] <= 1 + 37 + 1: no carry out
-  uint32_t c3 = add_word8(lo, lo[8] * 38u);
-  lo[0] += 38u * c3;  // if c3, lo is tiny: cannot carry again
+  add8_nc(lo + 1, lo + 1, od);        // lo[8] <= 1 + 37 + 1: no carry out
+  fe_tail_add<VT>(lo, lo[8] * 38u);
 #pragma unroll
   for (int i = 0; i < 8; i++) r.v[i] = lo[i];
 }
+ZKP_DEV void fe_reduce512(fe& r, const uint32_t* t) { fe_reduce512_t<false>(r, t); }
 
 // Variant of fe_reduce512 that multiplies the high half by 38 = 2^5 + 2^2 + 2^1 with funnel shifts and adds on the
 // ALU pipe instead of eight wide IMADs on the (saturated) FMA pipe.  Selected with -DZKP_REDUCE_SHIFTADD.
@@ -384,14 +528,14 @@ ZKP_DEV void fe_reduce512_shiftadd(fe& r, const uint32_t* t) {
 #ifndef ZKP_REDUCE_DEFAULT
 #define ZKP_REDUCE_DEFAULT 0   // 0 = wide-IMAD reduction, 1 = shift-add reduction
 #endif
-template <int RED>
+template <int RED, bool VT>
 ZKP_DEV void fe_reduce512_sel(fe& r, const uint32_t* t) {
   if (RED) fe_reduce512_shiftadd(r, t);
-  else fe_reduce512(r, t);
+  else fe_reduce512_t<VT>(r, t);
 }
 
 // r = a*b mod p (weak: r < 2^256)
-template <int RED>
+template <int RED, bool VT = false>
 ZKP_DEV void fe_mul_t(fe& r, const fe& a, const fe& b) {
   const uint32_t* A = a.v;
   const uint32_t* B = b.v;
@@ -414,17 +558,17 @@ ZKP_DEV void fe_mul_t(fe& r, const fe& a, const fe& b) {
       mad4(O + i + 1, A[1], A[3], A[5], A[7], B[i + 1]);
     }
   }
-  // t = E + (O << 32)
-  uint32_t t[17];
+  // t = E + (O << 32): one 15-limb chain (E[16] = O[15] = 0 and the product fits in 512 bits)
+  uint32_t t[16];
   t[0] = E[0];
-  uint32_t c = add8(t + 1, E + 1, O);
-  add8c(t + 9, E + 9, O + 8, c);   // t[16] = 0
-  fe_reduce512_sel<RED>(r, t);
+  add15(t + 1, E + 1, O);
+  fe_reduce512_sel<RED, VT>(r, t);
 }
-ZKP_DEV void fe_mul(fe& r, const fe& a, const fe& b) { fe_mul_t<ZKP_REDUCE_DEFAULT>(r, a, b); }
+ZKP_DEV void fe_mul(fe& r, const fe& a, const fe& b) { fe_mul_t<ZKP_REDUCE_DEFAULT, false>(r, a, b); }
+ZKP_DEV void fe_mul_vt(fe& r, const fe& a, const fe& b) { fe_mul_t<ZKP_REDUCE_DEFAULT, true>(r, a, b); }
 
 // r = a^2 mod p
-template <int RED>
+template <int RED, bool VT = false>
 ZKP_DEV void fe_sq_t(fe& r, const fe& a) {
   const uint32_t* A = a.v;
   uint32_t E[17], O[17];
@@ -453,41 +597,47 @@ ZKP_DEV void fe_sq_t(fe& r, const fe& a) {
   // row 6: j=7 -> O[12,13]
   mad1(O + 12, A[7], A[6]);
   // cross = E + (O << 32): limbs 1..15
-  uint32_t x[17];
+  uint32_t x[16];
   x[0] = 0;
-  uint32_t c = add8(x + 1, E + 1, O);
-  add8c(x + 9, E + 9, O + 8, c);   // x[15] picks up the last carry, x[16] = 0
+  add15(x + 1, E + 1, O);          // one chain; x[15] picks up the last carry
   // double it (funnel shifts: independent, no carry chain)
   uint32_t t[16];
   t[0] = 0;
 #pragma unroll
   for (int i = 1; i < 16; i++) t[i] = (x[i] << 1) | (x[i - 1] >> 31);
-  // add the squares a_i^2 at limb 2i
-  uint32_t c2 = sqr4c(t, A[0], A[1], A[2], A[3], 0u);
-  sqr4c(t + 8, A[4], A[5], A[6], A[7], c2);
-  fe_reduce512_sel<RED>(r, t);
+  // add the squares a_i^2 at limb 2i: one chain of eight fused lo/hi pairs
+  sqr8(t, A);
+  fe_reduce512_sel<RED, VT>(r, t);
 }
-ZKP_DEV void fe_sq(fe& r, const fe& a) { fe_sq_t<ZKP_REDUCE_DEFAULT>(r, a); }
+ZKP_DEV void fe_sq(fe& r, const fe& a) { fe_sq_t<ZKP_REDUCE_DEFAULT, false>(r, a); }
+ZKP_DEV void fe_sq_vt(fe& r, const fe& a) { fe_sq_t<ZKP_REDUCE_DEFAULT, true>(r, a); }
 
 // r = a + b
-ZKP_DEV void fe_add(fe& r, const fe& a, const fe& b) {
+template <bool VT>
+ZKP_DEV void fe_add_t(fe& r, const fe& a, const fe& b) {
   uint32_t t[8];
   uint32_t c = add8(t, a.v, b.v);
-  uint32_t c2 = add_word8(t, 38u * c);
-  t[0] += 38u * c2;
+  fe_tail_add<VT>(t, 38u * c);
 #pragma unroll
   for (int i = 0; i < 8; i++) r.v[i] = t[i];
 }
+ZKP_DEV void fe_add(fe& r, const fe& a, const fe& b) { fe_add_t<false>(r, a, b); }
+ZKP_DEV void fe_add_vt(fe& r, const fe& a, const fe& b) { fe_add_t<true>(r, a, b); }
 
 // r = a - b
-ZKP_DEV void fe_sub(fe& r, const fe& a, const fe& b) {
+template <bool VT>
+ZKP_DEV void fe_sub_t(fe& r, const fe& a, const fe& b) {
   uint32_t t[8];
   uint32_t br = sub8(t, a.v, b.v);
-  uint32_t b2 = sub_word8(t, 38u * br);
-  t[0] -= 38u * b2;
+  fe_tail_sub<VT>(t, 38u * br);
 #pragma unroll
   for (int i = 0; i < 8; i++) r.v[i] = t[i];
 }
+ZKP_DEV void fe_sub(fe& r, const fe& a, const fe& b) { fe_sub_t<false>(r, a, b); }
+ZKP_DEV void fe_sub_vt(fe& r, const fe& a, const fe& b) { fe_sub_t<true>(r, a, b); }
+// policy-dispatched spellings used by the templated chains below and in ge.cuh
+template <bool VT> ZKP_DEV void fe_mulx(fe& r, const fe& a, const fe& b) { fe_mul_t<ZKP_REDUCE_DEFAULT, VT>(r, a, b); }
+template <bool VT> ZKP_DEV void fe_sqx(fe& r, const fe& a) { fe_sq_t<ZKP_REDUCE_DEFAULT, VT>(r, a); }
 
 ZKP_DEV void fe_zero(fe& r) {
 #pragma unroll
@@ -572,38 +722,40 @@ ZKP_DEV void fe_cneg(fe& r, const fe& a, uint32_t neg) {
 ZKP_DEV void fe_abs(fe& r, const fe& a) { fe_cneg(r, a, fe_is_negative(a)); }
 
 // r = a^(2^k)
+template <bool VT = false>
 ZKP_DEV void fe_sqn(fe& r, const fe& a, int k) {
   fe t = a;
 #if ZKP_DEVICE_ASM
 #pragma unroll 1
 #endif
-  for (int i = 0; i < k; i++) fe_sq(t, t);
+  for (int i = 0; i < k; i++) fe_sqx<VT>(t, t);
   r = t;
 }
 
 // a^(2^250 - 1) and a^11 (the shared head of invert and pow22523; dalek field.rs pow22501 [ext])
+template <bool VT = false>
 ZKP_DEV void fe_pow22501(fe& t19, fe& t3, const fe& a) {
   fe t0, t1, t2, t4, t5, t6, t7, t8, t9, t10, t11, t12, t13, t14, t15, t16, t17, t18;
-  fe_sq(t0, a);          // 2
-  fe_sqn(t1, t0, 2);     // 8
-  fe_mul(t2, a, t1);     // 9
-  fe_mul(t3, t0, t2);    // 11
-  fe_sq(t4, t3);         // 22
-  fe_mul(t5, t2, t4);    // 31 = 2^5-1
-  fe_sqn(t6, t5, 5);
-  fe_mul(t7, t6, t5);    // 2^10-1
-  fe_sqn(t8, t7, 10);
-  fe_mul(t9, t8, t7);    // 2^20-1
-  fe_sqn(t10, t9, 20);
-  fe_mul(t11, t10, t9);  // 2^40-1
-  fe_sqn(t12, t11, 10);
-  fe_mul(t13, t12, t7);  // 2^50-1
-  fe_sqn(t14, t13, 50);
-  fe_mul(t15, t14, t13); // 2^100-1
-  fe_sqn(t16, t15, 100);
-  fe_mul(t17, t16, t15); // 2^200-1
-  fe_sqn(t18, t17, 50);
-  fe_mul(t19, t18, t13); // 2^250-1
+  fe_sqx<VT>(t0, a);          // 2
+  fe_sqn<VT>(t1, t0, 2);      // 8
+  fe_mulx<VT>(t2, a, t1);     // 9
+  fe_mulx<VT>(t3, t0, t2);    // 11
+  fe_sqx<VT>(t4, t3);         // 22
+  fe_mulx<VT>(t5, t2, t4);    // 31 = 2^5-1
+  fe_sqn<VT>(t6, t5, 5);
+  fe_mulx<VT>(t7, t6, t5);    // 2^10-1
+  fe_sqn<VT>(t8, t7, 10);
+  fe_mulx<VT>(t9, t8, t7);    // 2^20-1
+  fe_sqn<VT>(t10, t9, 20);
+  fe_mulx<VT>(t11, t10, t9);  // 2^40-1
+  fe_sqn<VT>(t12, t11, 10);
+  fe_mulx<VT>(t13, t12, t7);  // 2^50-1
+  fe_sqn<VT>(t14, t13, 50);
+  fe_mulx<VT>(t15, t14, t13); // 2^100-1
+  fe_sqn<VT>(t16, t15, 100);
+  fe_mulx<VT>(t17, t16, t15); // 2^200-1
+  fe_sqn<VT>(t18, t17, 50);
+  fe_mulx<VT>(t19, t18, t13); // 2^250-1
 }
 // a^(p-2)
 ZKP_DEV void fe_invert(fe& r, const fe& a) {
@@ -613,11 +765,12 @@ ZKP_DEV void fe_invert(fe& r, const fe& a) {
   fe_mul(r, t20, t3);
 }
 // a^((p-5)/8) = a^(2^252 - 3)
+template <bool VT = false>
 ZKP_DEV void fe_pow22523(fe& r, const fe& a) {
   fe t19, t3, t20;
-  fe_pow22501(t19, t3, a);
-  fe_sqn(t20, t19, 2);
-  fe_mul(r, a, t20);
+  fe_pow22501<VT>(t19, t3, a);
+  fe_sqn<VT>(t20, t19, 2);
+  fe_mulx<VT>(r, a, t20);
 }
 
 // 32 little-endian bytes (as 8 words) -> element; bit 255 is ignored like dalek's from_bytes.

@@ -58,26 +58,28 @@ ZKP_DEV void ge_madd(ge_ext& r, const ge_ext& p, const ge_aniels& q) {
 
 // r = p + (neg ? -q : q) with the sign folded into operand selection (no field negation, 32 selects):
 // -q swaps (y+x, y-x) and flips the sign of 2dxy, i.e. swaps F = D - C and G = D + C.
+// VT selects the variable-time tails of fe.cuh (public data only: the verifier's bucket accumulation).
+template <bool VT = false>
 ZKP_DEV void ge_madd_signed(ge_ext& r, const ge_ext& p, const ge_aniels& q, uint32_t neg) {
   fe a, b, c, d, e, f0, g0, f, g, h, qa, qb;
   fe_select(qa, q.yminusx, q.yplusx, neg);
   fe_select(qb, q.yplusx, q.yminusx, neg);
-  fe_sub(a, p.Y, p.X);
-  fe_add(b, p.Y, p.X);
-  fe_mul(a, a, qa);
-  fe_mul(b, b, qb);
-  fe_mul(c, p.T, q.xy2d);
-  fe_add(d, p.Z, p.Z);
-  fe_sub(e, b, a);
-  fe_sub(f0, d, c);
-  fe_add(g0, d, c);
+  fe_sub_t<VT>(a, p.Y, p.X);
+  fe_add_t<VT>(b, p.Y, p.X);
+  fe_mulx<VT>(a, a, qa);
+  fe_mulx<VT>(b, b, qb);
+  fe_mulx<VT>(c, p.T, q.xy2d);
+  fe_add_t<VT>(d, p.Z, p.Z);
+  fe_sub_t<VT>(e, b, a);
+  fe_sub_t<VT>(f0, d, c);
+  fe_add_t<VT>(g0, d, c);
   fe_select(f, f0, g0, neg);
   fe_select(g, g0, f0, neg);
-  fe_add(h, b, a);
-  fe_mul(r.X, e, f);
-  fe_mul(r.Y, g, h);
-  fe_mul(r.Z, f, g);
-  fe_mul(r.T, e, h);
+  fe_add_t<VT>(h, b, a);
+  fe_mulx<VT>(r.X, e, f);
+  fe_mulx<VT>(r.Y, g, h);
+  fe_mulx<VT>(r.Z, f, g);
+  fe_mulx<VT>(r.T, e, h);
 }
 
 // conditional negation of an affine Niels point (branch-free): swap the first two, negate the third
@@ -154,16 +156,17 @@ ZKP_DEV void ge_neg(ge_ext& r, const ge_ext& p) {
 ZKP_DEV uint32_t ge_is_identity_coset(const ge_ext& p) { return fe_is_zero(p.X) | fe_is_zero(p.Y); }
 
 // (was_square, r) = sqrt_ratio_i(1, v)   RFC 9496 4.2 with u = 1
+template <bool VT = false>
 ZKP_DEV uint32_t fe_invsqrt(fe& r, const fe& v) {
   fe v3, v7, t, check, one, m1, mi;
-  fe_sq(v3, v);
-  fe_mul(v3, v3, v);
-  fe_sq(v7, v3);
-  fe_mul(v7, v7, v);
-  fe_pow22523(t, v7);
-  fe_mul(t, t, v3);          // r = v^3 * (v^7)^((p-5)/8)
-  fe_sq(check, t);
-  fe_mul(check, check, v);   // v * r^2
+  fe_sqx<VT>(v3, v);
+  fe_mulx<VT>(v3, v3, v);
+  fe_sqx<VT>(v7, v3);
+  fe_mulx<VT>(v7, v7, v);
+  fe_pow22523<VT>(t, v7);
+  fe_mulx<VT>(t, t, v3);          // r = v^3 * (v^7)^((p-5)/8)
+  fe_sqx<VT>(check, t);
+  fe_mulx<VT>(check, check, v);   // v * r^2
   fe_one(one);
   fe_neg(m1, one);
   fe_neg(mi, fe_SQRT_M1());
@@ -179,6 +182,7 @@ ZKP_DEV uint32_t fe_invsqrt(fe& r, const fe& v) {
 
 // RFC 9496 4.3.1.  w = the 32 encoding bytes as 8 little-endian words.  Returns 1 if valid.
 // Output: affine extended coordinates (x, y, 1, t) delivered as x, y, t.
+template <bool VT = false>
 ZKP_DEV uint32_t ristretto_decode(fe& x, fe& y, fe& t, const uint32_t* w) {
   fe s, ss, u1, u2, u2sq, v, inv, dx, dy, one, tmp;
   fe_from_words(s, w);
@@ -199,7 +203,7 @@ ZKP_DEV uint32_t ristretto_decode(fe& x, fe& y, fe& t, const uint32_t* w) {
   fe_neg(tmp, tmp);
   fe_sub(v, tmp, u2sq);       // v = -(D*u1^2) - u2^2
   fe_mul(tmp, v, u2sq);
-  uint32_t sq = fe_invsqrt(inv, tmp);
+  uint32_t sq = fe_invsqrt<VT>(inv, tmp);
   fe_mul(dx, inv, u2);
   fe_mul(dy, inv, dx);
   fe_mul(dy, dy, v);

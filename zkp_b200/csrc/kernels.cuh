@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(256) k_decompress(const uint4* __restrict__ en
   uint32_t w[8];
   load_words8(w, enc + 2 * i);
   fe x, y, t;
-  uint32_t ok = ristretto_decode(x, y, t, w);
+  uint32_t ok = ristretto_decode<true>(x, y, t, w);
   ge_aniels q;
   if (ok) {
     ge_aniels_from_affine(q, x, y, t);
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(256) k_ingest(const uint4* __restrict__ enc, c
   uint32_t w8[8];
   load_words8(w8, enc + 2 * i);
   fe x, y, t;
-  uint32_t ok = ristretto_decode(x, y, t, w8);
+  uint32_t ok = ristretto_decode<true>(x, y, t, w8);
   ge_aniels q;
   if (ok) {
     ge_aniels_from_affine(q, x, y, t);
@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(128, 4) k_accumulate(const uint4* __restrict__
       e_nxt = __ldg(base + inext);
       load_aniels(nxt, niels, e_nxt);
     }
-    ge_madd_signed(acc, acc, cur, e_cur >> 31);
+    ge_madd_signed<true>(acc, acc, cur, e_cur >> 31);
     cur = nxt;
     e_cur = e_nxt;
     i = inext;
