@@ -47,6 +47,7 @@ struct zkp_ctx {
   // the digit sort (histogram, scan, scatter: L2-atomic bound) runs on a second, higher-priority stream
   // concurrently with decompression (integer-multiply bound); joined before bucket accumulation
   int overlap = 0;   // measured: no gain on B200 (159.2 vs 159.9 ms per step), kept as an option
+  int fused_sort = 1;  // histogram and scatter ride under the two halves of the decompression (k_ingest2)
   cudaStream_t sort_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
@@ -173,6 +174,8 @@ extern "C" int32_t zkp_ctx_set_option(zkp_ctx* ctx, const char* key, int64_t val
     ctx->window_cap = (int)value;
   } else if (!strcmp(key, "overlap")) {
     ctx->overlap = value ? 1 : 0;
+  } else if (!strcmp(key, "fused_sort")) {
+    ctx->fused_sort = value ? 1 : 0;
   } else if (!strcmp(key, "chunk_terms")) {
     if (value < 1024) return ZKP_ERR_SIZE;
     ctx->chunk_terms = (size_t)value;
@@ -310,7 +313,33 @@ static int32_t msm_ingest(zkp_ctx* ctx, const msm_plan& pl, const void* d_scalar
 }
 
 static int32_t msm_finish(zkp_ctx* ctx, const msm_plan& pl, const void* d_scalars, size_t n, msm_result* d_result,
-                          bool whole);
+                          bool whole, bool sorted_done = false);
+
+// one launch of the two-phase ingestion (kernels.cuh k_ingest2): points [p_lo, p_lo + p_cnt), terms [sA_lo, +sA_cnt) and
+// [sB_lo, +sB_cnt) of the scalar array; MODE 0 histograms their digits, MODE 1 scatters them
+template <int MODE>
+static int32_t launch_ingest2(zkp_ctx* ctx, const msm_plan& pl, const void* d_scalars, const void* d_points, size_t n,
+                              size_t p_lo, size_t p_cnt, size_t sA_lo, size_t sA_cnt, size_t sB_lo, size_t sB_cnt) {
+  size_t threads = p_cnt > sA_cnt ? p_cnt : sA_cnt;
+  if (sB_cnt > threads) threads = sB_cnt;
+  if (!threads) return ZKP_OK;
+  k_ingest2<MODE><<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(
+      (const uint4*)d_points, p_lo, p_cnt, (uint4*)ctx->niels.p, (const uint4*)d_scalars, sA_lo, sA_cnt, sB_lo, sB_cnt, n,
+      pl.c, pl.W, pl.B, MODE == 0 ? (uint32_t*)ctx->hist.p : (uint32_t*)ctx->cursor.p, (uint32_t*)ctx->sorted.p,
+      (int*)ctx->flags.p);
+  LAUNCH_CHECK(ctx);
+  return ZKP_OK;
+}
+// the same with one contiguous scalar range [s_lo, s_lo + s_cnt) cut into two halves
+template <int MODE>
+static int32_t launch_ingest2_range(zkp_ctx* ctx, const msm_plan& pl, const void* d_scalars, const void* d_points, size_t n,
+                                    size_t p_lo, size_t p_cnt, size_t s_lo, size_t s_cnt) {
+  const size_t half = (s_cnt + 1) / 2;
+  return launch_ingest2<MODE>(ctx, pl, d_scalars, d_points, n, p_lo, p_cnt, s_lo, half, s_lo + half, s_cnt - half);
+}
+static bool use_fused_sort(const zkp_ctx* ctx, const msm_plan& pl) {
+  return !ctx->profile && pl.sort == ctx->stream && ctx->fused_sort;
+}
 
 static int32_t msm_vartime_launch(zkp_ctx* ctx, const void* d_scalars, const void* d_points, size_t n,
                                   msm_result* d_result) {
@@ -323,6 +352,17 @@ static int32_t msm_vartime_launch(zkp_ctx* ctx, const void* d_scalars, const voi
   msm_plan pl;
   int32_t r = msm_prepare(ctx, n, &pl);
   if (r != ZKP_OK) return r;
+  if (use_fused_sort(ctx, pl)) {
+    // phase 1: first half of the points + histogram of all scalars; scan; phase 2: second half + scatter of all scalars
+    const size_t half_p = (n + 1) / 2;
+    r = launch_ingest2_range<0>(ctx, pl, d_scalars, d_points, n, 0, half_p, 0, n);
+    if (r != ZKP_OK) return r;
+    k_scan<<<pl.W, 1024, 0, st>>>((const uint32_t*)ctx->hist.p, pl.B, (uint32_t*)ctx->offs.p, (uint32_t*)ctx->cursor.p);
+    LAUNCH_CHECK(ctx);
+    r = launch_ingest2_range<1>(ctx, pl, d_scalars, d_points, n, half_p, n - half_p, 0, n);
+    if (r != ZKP_OK) return r;
+    return msm_finish(ctx, pl, d_scalars, n, d_result, true, true);
+  }
   r = msm_ingest(ctx, pl, d_scalars, d_points, 0, n, true);
   if (r != ZKP_OK) return r;
   return msm_finish(ctx, pl, d_scalars, n, d_result, true);
@@ -330,18 +370,20 @@ static int32_t msm_vartime_launch(zkp_ctx* ctx, const void* d_scalars, const voi
 
 // phase C: counting sort by bucket, bucket accumulation, bucket reduction, Horner, encode
 static int32_t msm_finish(zkp_ctx* ctx, const msm_plan& pl, const void* d_scalars, size_t n, msm_result* d_result,
-                          bool whole) {
+                          bool whole, bool sorted_done) {
   cudaStream_t st = ctx->stream;
   const int c = pl.c, W = pl.W;
   const uint32_t B = pl.B, total_buckets = pl.total_buckets;
   int* flags = (int*)ctx->flags.p;
   const unsigned nb = (unsigned)((n + 255) / 256);
-  k_scan<<<W, 1024, 0, pl.sort>>>((const uint32_t*)ctx->hist.p, B, (uint32_t*)ctx->offs.p, (uint32_t*)ctx->cursor.p);
-  LAUNCH_CHECK(ctx);
-  if (whole) STAGE(3);
-  k_recode<true><<<nb, 256, 0, pl.sort>>>((const uint4*)d_scalars, n, c, W, B, (uint32_t*)ctx->cursor.p,
-                                          (uint32_t*)ctx->sorted.p, flags, 0);
-  LAUNCH_CHECK(ctx);
+  if (!sorted_done) {
+    k_scan<<<W, 1024, 0, pl.sort>>>((const uint32_t*)ctx->hist.p, B, (uint32_t*)ctx->offs.p, (uint32_t*)ctx->cursor.p);
+    LAUNCH_CHECK(ctx);
+    if (whole) STAGE(3);
+    k_recode<true><<<nb, 256, 0, pl.sort>>>((const uint4*)d_scalars, n, c, W, B, (uint32_t*)ctx->cursor.p,
+                                            (uint32_t*)ctx->sorted.p, flags, 0);
+    LAUNCH_CHECK(ctx);
+  }
   if (pl.sort != st) {   // join: bucket accumulation needs both the Niels points and the sorted digits
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, pl.sort));
     CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
@@ -472,6 +514,39 @@ static int32_t msm_from_host(zkp_ctx* ctx, const hseg* sc_segs, const hseg* pt_s
   // the copy stream must not overwrite the staging buffers before earlier work on `st` (a previous call) is done
   CUDA_TRY(ctx, cudaEventRecord(ctx->chunk_ev[nchunks], st));
   CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[nchunks], 0));
+  if (use_fused_sort(ctx, pl)) {
+    // two-phase ingestion over the chunk pipeline: the first K1 point chunks travel with ALL the scalars (cut into K1
+    // slices) and carry the digit histogram; after the scan the remaining point chunks carry the scatter
+    const size_t K1 = (nchunks + 1) / 2, K2 = nchunks - K1;
+    for (size_t k = 0; k < nchunks; k++) {
+      const size_t lo = k * chunk, hi = lo + chunk < n ? lo + chunk : n;
+      const bool first = k < K1;
+      const size_t kk = first ? k : k - K1, parts = first ? K1 : K2;
+      const size_t s_lo = n / parts * kk + (n % parts) * kk / parts, s_hi = n / parts * (kk + 1) + (n % parts) * (kk + 1) / parts;
+      r = copy_range(ctx, pt_segs, nseg, lo, hi, (uint8_t*)ctx->in_points.p);
+      if (r != ZKP_OK) return r;
+      if (first) {
+        r = copy_range(ctx, sc_segs, nseg, s_lo, s_hi, (uint8_t*)ctx->in_scalars.p);
+        if (r != ZKP_OK) return r;
+      }
+      CUDA_TRY(ctx, cudaEventRecord(ctx->chunk_ev[k], ctx->copy_stream));
+      CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->chunk_ev[k], 0));
+      if (k == K1) {
+        k_scan<<<pl.W, 1024, 0, st>>>((const uint32_t*)ctx->hist.p, pl.B, (uint32_t*)ctx->offs.p, (uint32_t*)ctx->cursor.p);
+        LAUNCH_CHECK(ctx);
+      }
+      if (first) r = launch_ingest2_range<0>(ctx, pl, ctx->in_scalars.p, ctx->in_points.p, n, lo, hi - lo, s_lo, s_hi - s_lo);
+      else r = launch_ingest2_range<1>(ctx, pl, ctx->in_scalars.p, ctx->in_points.p, n, lo, hi - lo, s_lo, s_hi - s_lo);
+      if (r != ZKP_OK) return r;
+    }
+    if (K2 == 0) {   // a single chunk: the scatter has no points to ride under
+      k_scan<<<pl.W, 1024, 0, st>>>((const uint32_t*)ctx->hist.p, pl.B, (uint32_t*)ctx->offs.p, (uint32_t*)ctx->cursor.p);
+      LAUNCH_CHECK(ctx);
+      r = launch_ingest2_range<1>(ctx, pl, ctx->in_scalars.p, ctx->in_points.p, n, 0, 0, 0, n);
+      if (r != ZKP_OK) return r;
+    }
+    return msm_finish(ctx, pl, ctx->in_scalars.p, n, d_result, false, true);
+  }
   for (size_t k = 0; k < nchunks; k++) {
     const size_t lo = k * chunk, hi = lo + chunk < n ? lo + chunk : n;
     r = copy_range(ctx, pt_segs, nseg, lo, hi, (uint8_t*)ctx->in_points.p);

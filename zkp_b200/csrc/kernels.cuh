@@ -201,6 +201,68 @@ __global__ void __launch_bounds__(256) k_ingest(const uint4* __restrict__ enc, c
   store_fe(o + 4, q.xy2d);
 }
 
+// Two-phase ingestion: every thread first issues the digit work of up to two terms -- MODE 0: histogram reductions,
+// MODE 1: counting-sort scatter (atomic cursor + 4-byte store) -- and then decompresses one point.  The L2 atomics and
+// scattered stores ride under the ~31k-instruction decode whose LSU pipe is otherwise idle, so with
+//   phase 1 = first half of the points + histogram of ALL scalars,  scan,  phase 2 = second half + scatter of ALL scalars
+// neither the histogram nor the scatter costs a separate pass.  Thread t takes the terms sA_lo + t (t < sA_cnt) and
+// sB_lo + t (t < sB_cnt) and the point p_lo + t (t < p_cnt); all indices are global term indices.
+template <int MODE>
+__device__ __forceinline__ void ingest_digits(const uint4* __restrict__ scalars, size_t i, size_t n, int c, int W, uint32_t B,
+                                              uint32_t* __restrict__ counters, uint32_t* __restrict__ sorted,
+                                              int* __restrict__ flags) {
+  uint32_t s[8], k[8];
+  load_words8(s, scalars + 2 * i);
+  uint32_t neg;
+  uint32_t canonical = sc_fold_sign(k, neg, s);
+  if (!canonical) {
+    if (MODE == 0) atomicMin(&flags[1], (int)i);
+    return;   // contributes nothing; the call fails with ZKP_ERR_SCALAR
+  }
+  uint32_t carry = 0;
+  for (int w = 0; w < W; w++) {
+    uint32_t mag, dneg;
+    sc_digit(mag, dneg, carry, k, w, c);
+    if (mag != 0) {
+      uint32_t* ctr = counters + (size_t)w * B + (mag - 1);
+      if (MODE == 0) {
+        atomicAdd(ctr, 1u);
+      } else {
+        uint32_t pos = atomicAdd(ctr, 1u);
+        sorted[(size_t)w * n + pos] = (uint32_t)i | ((neg ^ dneg) << 31);
+      }
+    }
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k_ingest2(const uint4* __restrict__ enc, size_t p_lo, size_t p_cnt,
+                                                 uint4* __restrict__ niels, const uint4* __restrict__ scalars, size_t sA_lo,
+                                                 size_t sA_cnt, size_t sB_lo, size_t sB_cnt, size_t n, int c, int W,
+                                                 uint32_t B, uint32_t* __restrict__ counters,
+                                                 uint32_t* __restrict__ sorted, int* __restrict__ flags) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < sA_cnt) ingest_digits<MODE>(scalars, sA_lo + t, n, c, W, B, counters, sorted, flags);
+  if (t < sB_cnt) ingest_digits<MODE>(scalars, sB_lo + t, n, c, W, B, counters, sorted, flags);
+  if (t >= p_cnt) return;
+  const size_t i = p_lo + t;
+  uint32_t w8[8];
+  load_words8(w8, enc + 2 * i);
+  fe x, y, tt;
+  uint32_t ok = ristretto_decode<true>(x, y, tt, w8);
+  ge_aniels q;
+  if (ok) {
+    ge_aniels_from_affine(q, x, y, tt);
+  } else {
+    ge_aniels_identity(q);
+    atomicMin(&flags[0], (int)i);
+  }
+  uint4* o = niels + 6 * i;
+  store_fe(o, q.yplusx);
+  store_fe(o + 2, q.yminusx);
+  store_fe(o + 4, q.xy2d);
+}
+
 // K3: per-window exclusive scan.  One block (1024 threads) per window.
 __global__ void __launch_bounds__(1024) k_scan(const uint32_t* __restrict__ hist, uint32_t B,
                                                uint32_t* __restrict__ offs,    // [W][B+1]
