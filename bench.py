@@ -172,6 +172,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=0, help="tuning: force the accumulate work-item length")
     ap.add_argument("--no-proofs-leg", action="store_true", help="skip the e2e_from_proofs leg (real proofs, device front end)")
     ap.add_argument("--no-overlap", action="store_true", help="tuning: run the digit sort on the compute stream")
+    ap.add_argument("--chunk-terms-log2", type=int, default=0, help="tuning: H2D pipeline chunk (terms) for the e2e leg")
     ap.add_argument("--no-fused-sort", action="store_true", help="tuning: separate scatter pass instead of the two-phase ingestion")
     ap.add_argument("--sweep", default="", help="tuning: comma list of windows; prints stage times per window and exits")
     args = ap.parse_args()
@@ -262,6 +263,8 @@ def main():
         eng.set_option("overlap", 0)
     if args.no_fused_sort:
         eng.set_option("fused_sort", 0)
+    if args.chunk_terms_log2:
+        eng.set_option("chunk_terms", 1 << args.chunk_terms_log2)
     if args.window:
         eng.set_option("window", args.window)
     if args.chunk:

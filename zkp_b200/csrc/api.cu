@@ -33,7 +33,7 @@ struct zkp_ctx {
   std::string err;
   // workspace (grown on demand, reused across calls)
   devbuf in_scalars, in_points, niels, hist, offs, cursor, sorted, buckets, lvlT[2], lvlU, usum, flags, result,
-      aux0, aux1, aux2, sk0, sk1, tables, items, partials, multi, bv_com, bv_resp, bv_part, bv_misc;
+      aux0, aux1, aux2, sk0, sk1, tables, items, partials, multi, bv_com, bv_resp, bv_part, bv_misc, len_hist, order;
   void* h_result = nullptr;  // pinned, 64 bytes
   // optional per-stage timing of the vartime MSM ("profile" option): events around each stage
   int profile = 0;
@@ -47,6 +47,7 @@ struct zkp_ctx {
   // the digit sort (histogram, scan, scatter: L2-atomic bound) runs on a second, higher-priority stream
   // concurrently with decompression (integer-multiply bound); joined before bucket accumulation
   int overlap = 0;   // measured: no gain on B200 (159.2 vs 159.9 ms per step), kept as an option
+  int balance = 1;     // size-ordered work items in the bucket accumulation (equal-length items share a warp)
   int fused_sort = 1;  // histogram and scatter ride under the two halves of the decompression (k_ingest2)
   cudaStream_t sort_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -143,7 +144,7 @@ extern "C" void zkp_ctx_destroy(zkp_ctx* ctx) {
                     &ctx->sorted, &ctx->buckets, &ctx->lvlT[0], &ctx->lvlT[1], &ctx->lvlU, &ctx->usum,
                     &ctx->flags, &ctx->result, &ctx->aux0, &ctx->aux1, &ctx->aux2, &ctx->sk0, &ctx->sk1,
                     &ctx->tables, &ctx->items, &ctx->partials, &ctx->multi, &ctx->bv_com, &ctx->bv_resp, &ctx->bv_part,
-                    &ctx->bv_misc};
+                    &ctx->bv_misc, &ctx->len_hist, &ctx->order};
   for (devbuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (ctx->h_result) cudaFreeHost(ctx->h_result);
@@ -174,6 +175,8 @@ extern "C" int32_t zkp_ctx_set_option(zkp_ctx* ctx, const char* key, int64_t val
     ctx->window_cap = (int)value;
   } else if (!strcmp(key, "overlap")) {
     ctx->overlap = value ? 1 : 0;
+  } else if (!strcmp(key, "balance")) {
+    ctx->balance = value ? 1 : 0;
   } else if (!strcmp(key, "fused_sort")) {
     ctx->fused_sort = value ? 1 : 0;
   } else if (!strcmp(key, "chunk_terms")) {
@@ -421,9 +424,26 @@ static int32_t msm_finish(zkp_ctx* ctx, const msm_plan& pl, const void* d_scalar
                                 (work_item*)ctx->items.p, n_multi + 4, n_multi);
     LAUNCH_CHECK(ctx);
     const unsigned blocks = (unsigned)((max_items + 127) / 128);
+    const uint32_t* n_items = (const uint32_t*)ctx->aux1.p + total_buckets;
+    const uint32_t* order = nullptr;
+    if (ctx->balance && max_items >= 4096) {
+      // counting sort of the item ids by length (longest first): equal-length items share a warp
+      ENSURE(ctx, ctx->len_hist, (3 * (size_t)S + 8) * 4);                // histogram [S+1] | offsets [S+2] | cursor [S+1]
+      ENSURE(ctx, ctx->order, max_items * 4);
+      uint32_t* lh = (uint32_t*)ctx->len_hist.p;
+      CUDA_TRY(ctx, cudaMemsetAsync(lh, 0, ((size_t)S + 1) * 4, st));
+      const unsigned ib = (unsigned)((max_items + 255) / 256);
+      k_len_hist<<<ib, 256, 0, st>>>((const work_item*)ctx->items.p, n_items, S, lh);
+      LAUNCH_CHECK(ctx);
+      k_scan<<<1, 1024, 0, st>>>(lh, S + 1, lh + S + 1, lh + 2 * S + 3);
+      LAUNCH_CHECK(ctx);
+      k_len_scatter<<<ib, 256, 0, st>>>((const work_item*)ctx->items.p, n_items, S, lh + 2 * S + 3, (uint32_t*)ctx->order.p);
+      LAUNCH_CHECK(ctx);
+      order = (const uint32_t*)ctx->order.p;
+    }
     k_accumulate<<<blocks, 128, 0, st>>>((const uint4*)ctx->niels.p, (const uint32_t*)ctx->sorted.p,
-                                         (const work_item*)ctx->items.p, (const uint32_t*)ctx->aux1.p + total_buckets,
-                                         n, (uint4*)ctx->buckets.p, (uint4*)ctx->partials.p);
+                                         (const work_item*)ctx->items.p, order, n_items, n, (uint4*)ctx->buckets.p,
+                                         (uint4*)ctx->partials.p);
     LAUNCH_CHECK(ctx);
     k_merge<<<148 * 8, 128, 0, st>>>((const uint32_t*)ctx->aux1.p, n_multi + 4, n_multi,
                                      (const uint4*)ctx->partials.p, (uint4*)ctx->buckets.p);
@@ -746,6 +766,8 @@ extern "C" int32_t zkp_batch_verify_proofs(zkp_ctx* ctx, const zkp_statement_des
   CUDA_TRY(ctx, cudaEventRecord(ctx->chunk_ev[nchunks], st));
   CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[nchunks], 0));
   unsigned block_base = 0;
+  const bool fused = use_fused_sort(ctx, pl);
+  const size_t R1 = rows / 2;   // rows decompressed during phase 1 (the others during phase 2)
   for (size_t cidx = 0; cidx < nchunks; cidx++) {
     const size_t j0 = cidx * chunk, cnt = j0 + chunk < N ? chunk : N - j0;
     // H2D of this chunk: instance slab (ni rows of cnt encodings), commitments and responses of cnt proofs
@@ -767,19 +789,48 @@ extern "C" int32_t zkp_batch_verify_proofs(zkp_ctx* ctx, const zkp_statement_des
                                      (uint8_t*)ctx->bv_part.p, nullptr, (int*)ctx->flags.p, j0, cnt, block_base);
     LAUNCH_CHECK(ctx);
     block_base += nb;
-    // the slabs of this chunk are complete (points and coefficients): decompress them and histogram their digits
-    for (size_t row = 0; row < rows; row++) {
-      r = msm_ingest(ctx, pl, dsc, dpts, (size_t)nc + row * N + j0, cnt, false);
-      if (r != ZKP_OK) return r;
+    // the slabs of this chunk are complete (points and coefficients)
+    if (fused) {
+      // phase 1 of the two-phase ingestion: histogram every slab, decompress the slabs of the first R1 rows
+      for (size_t row = 0; row < R1; row++) {
+        const size_t a = (size_t)nc + row * N + j0, b = (size_t)nc + (row + R1) * N + j0;
+        r = launch_ingest2<0>(ctx, pl, dsc, dpts, n, a, cnt, a, cnt, b, cnt);
+        if (r != ZKP_OK) return r;
+      }
+      for (size_t row = 2 * R1; row < rows; row++) {   // odd row count: the last row's histogram on its own
+        r = launch_ingest2<0>(ctx, pl, dsc, dpts, n, 0, 0, (size_t)nc + row * N + j0, cnt, 0, 0);
+        if (r != ZKP_OK) return r;
+      }
+    } else {
+      for (size_t row = 0; row < rows; row++) {
+        r = msm_ingest(ctx, pl, dsc, dpts, (size_t)nc + row * N + j0, cnt, false);
+        if (r != ZKP_OK) return r;
+      }
     }
   }
   if (nc) {
     k_bv_static_sum<<<1, 256, 0, st>>>((const uint8_t*)ctx->bv_part.p, (int)block_base, nc, dsc);
     LAUNCH_CHECK(ctx);
-    r = msm_ingest(ctx, pl, dsc, dpts, 0, (size_t)nc, false);
+    if (fused) r = launch_ingest2<0>(ctx, pl, dsc, dpts, n, 0, (size_t)nc, 0, (size_t)nc, 0, 0);
+    else r = msm_ingest(ctx, pl, dsc, dpts, 0, (size_t)nc, false);
     if (r != ZKP_OK) return r;
   }
-  r = msm_finish(ctx, pl, dsc, n, (msm_result*)ctx->result.p, false);
+  if (fused) {
+    // phase 2: the remaining rows are decompressed while the digits of all rows are scattered (two rows per launch)
+    k_scan<<<pl.W, 1024, 0, st>>>((const uint32_t*)ctx->hist.p, pl.B, (uint32_t*)ctx->offs.p, (uint32_t*)ctx->cursor.p);
+    LAUNCH_CHECK(ctx);
+    for (size_t q = 0; q < rows - R1; q++) {
+      const size_t ra = 2 * q, rb = 2 * q + 1;
+      r = launch_ingest2<1>(ctx, pl, dsc, dpts, n, (size_t)nc + (R1 + q) * N, N, (size_t)nc + ra * N, ra < rows ? N : 0,
+                            (size_t)nc + rb * N, rb < rows ? N : 0);
+      if (r != ZKP_OK) return r;
+    }
+    if (nc) {
+      r = launch_ingest2<1>(ctx, pl, dsc, dpts, n, 0, 0, 0, (size_t)nc, 0, 0);
+      if (r != ZKP_OK) return r;
+    }
+  }
+  r = msm_finish(ctx, pl, dsc, n, (msm_result*)ctx->result.p, false, fused);
   if (r != ZKP_OK) return r;
   if (coeff_out) CUDA_TRY(ctx, cudaMemcpyAsync(coeff_out, dsc, n * 32, cudaMemcpyDeviceToHost, st));
   if (points_out) CUDA_TRY(ctx, cudaMemcpyAsync(points_out, dpts, n * 32, cudaMemcpyDeviceToHost, st));

@@ -368,12 +368,45 @@ __global__ void __launch_bounds__(256) k_items(const uint32_t* __restrict__ offs
   }
 }
 
-__global__ void __launch_bounds__(128, 4) k_accumulate(const uint4* __restrict__ niels, const uint32_t* __restrict__ sorted,
-                                                       const work_item* __restrict__ items,
-                                                       const uint32_t* __restrict__ n_items, size_t n,
-                                                       uint4* __restrict__ buckets, uint4* __restrict__ partials) {
+// Lane balance: the items of a warp should be equally long (a warp runs until its longest item is done; bucket loads
+// are Poisson, 768 +- 28 at the bench size).  A counting sort of the item ids by length, longest first, gives every
+// warp 32 items of (almost) the same length.  len_hist[S + 1] must be zero on entry.
+__global__ void __launch_bounds__(256) k_len_hist(const work_item* __restrict__ items, const uint32_t* __restrict__ n_items,
+                                                  uint32_t S, uint32_t* __restrict__ len_hist) {
   const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= *n_items) return;
+  const uint4 raw = __ldg((const uint4*)items + id);
+  const uint32_t len = raw.y - raw.x;
+  // warp-aggregated: lanes with the same length elect one lane to add the group's size
+  const uint32_t key = S - (len > S ? S : len);
+  const uint32_t peers = __match_any_sync(__activemask(), key);
+  if ((uint32_t)(__ffs(peers) - 1) == (threadIdx.x & 31)) atomicAdd(len_hist + key, (uint32_t)__popc(peers));
+}
+__global__ void __launch_bounds__(256) k_len_scatter(const work_item* __restrict__ items, const uint32_t* __restrict__ n_items,
+                                                     uint32_t S, uint32_t* __restrict__ len_cursor,
+                                                     uint32_t* __restrict__ order) {
+  const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= *n_items) return;
+  const uint4 raw = __ldg((const uint4*)items + id);
+  const uint32_t len = raw.y - raw.x;
+  const uint32_t key = S - (len > S ? S : len);
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t peers = __match_any_sync(__activemask(), key);
+  const uint32_t leader = (uint32_t)(__ffs(peers) - 1);
+  uint32_t base = 0;
+  if (leader == lane) base = atomicAdd(len_cursor + key, (uint32_t)__popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  order[base + __popc(peers & ((1u << lane) - 1u))] = id;
+}
+
+__global__ void __launch_bounds__(128, 4) k_accumulate(const uint4* __restrict__ niels, const uint32_t* __restrict__ sorted,
+                                                       const work_item* __restrict__ items,
+                                                       const uint32_t* __restrict__ order,
+                                                       const uint32_t* __restrict__ n_items, size_t n,
+                                                       uint4* __restrict__ buckets, uint4* __restrict__ partials) {
+  const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= *n_items) return;
+  const uint32_t id = order ? __ldg(order + slot) : slot;
   const uint4 raw = __ldg((const uint4*)items + id);
   const uint32_t start = raw.x, end = raw.y, out = raw.z, wflag = raw.w;
   const uint32_t* base = sorted + (size_t)(wflag & 0x7fffffffu) * n;
