@@ -36,6 +36,7 @@ L = 2**252 + 27742317777372353535851937790883648493
 ROWS, NUM_S = 24, 12           # CMZ: 13 instance + 11 commitment rows, 12 static points
 FULL_ROWS = 13                  # rows 0..12 carry full-size coefficients, rows 13..23 are -rho (128-bit rho)
 BYTES_PER_PROOF = 1536          # 24 terms x (32 B scalar + 32 B point)   
+BUCKET_ADDS_PER_PROOF = 13 * 15 + 11 * 8   # window 17: 15 digits for the full-size rows, 8 for the 128-bit (-rho) rows
 
 
 def _l_words():
@@ -318,6 +319,7 @@ def main():
     barrier()
     launches = eng.launch_count - launches0
     ms_total = e0.elapsed_time(e1)
+    live = eng.live_ms()            # events around the dominant kernels of the last TIMED step (always recorded)
     assert read_result() == (0, 1)
 
     # ---- e2e through the C ABI with host buffers -------------------------------------------------------------
@@ -395,30 +397,45 @@ def main():
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-        dec_ms = stages.get("decompress", 0.0)
         dom = max((k for k in stages if k not in ("window", "lanes")), key=lambda k: stages[k])
-        dec_bytes = n_terms * 128.0                              # 32 B encoding in + 96 B Niels point out per point
-        achieved = dec_bytes / (dec_ms * 1e-3) / 1e9 if dec_ms else 0.0
-        # integer-pipe view: field mults (254 S + 30 M per point) against the calibrated register-resident rate
-        fe_sq_rate = eng.bench_field(1, 2048)
-        fe_mul_rate = eng.bench_field(0, 2048)
-        dec_time_at_peak = n_terms * (254.0 / fe_sq_rate + 30.0 / fe_mul_rate)
+        # The dominant kernel of a step is k_ingest2: two launches, each decompresses half of the points (32 B in, 96 B
+        # out per point) and reads all the scalars (32 B per term) for the digit histogram (phase 1) / scatter (phase 2).
+        ing = [live.get("ingest_phase1", -1.0), live.get("ingest_phase2", -1.0)]
+        ing_ms = float(np.mean(ing)) if min(ing) > 0 else 0.0
+        ing_bytes = n_terms * (0.5 * 128.0 + 32.0)               # algorithmic bytes of ONE launch
+        achieved = ing_bytes / (ing_ms * 1e-3) / 1e9 if ing_ms else 0.0
+        # integer-pipe view: field mults (254 S + 30 M per point) against the calibrated register-resident rates
+        fe_sq_rate = eng.bench_field(9, 2048)                     # variable-time tails: what the kernel runs
+        fe_mul_rate = eng.bench_field(8, 2048)
+        madd_rate = eng.bench_field(11, 512)
+        dec_time_at_peak = 0.5 * n_terms * (254.0 / fe_sq_rate + 30.0 / fe_mul_rate)
+        acc_ms = live.get("accumulate", -1.0)
         traffic, traffic_src = None, None
-        try:   # dram__bytes_read.sum + dram__bytes_write.sum of k_decompress from the committed ncu --set full capture
-            prof = json.load(open(os.path.join(ROOT, "profiles", "r01_decompress_ncu.json")))
-            traffic = prof["traffic_bytes_per_launch"] * (n_terms / prof["n_points"])
-            traffic_src = "profiles/r01_decompress_ncu.json (ncu --set full at n=%d, scaled by n)" % prof["n_points"]
+        try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ingest_ncu.json")))
+            traffic = prof["traffic_bytes_per_launch"] * (n_terms / prof["n_terms"])
+            traffic_src = ("profiles/r01_ingest_ncu.json (ncu --set full at n=%d, mean of the two launches, scaled by n)"
+                           % prof["n_terms"])
         except Exception:
             pass
-        roofline = {"bound": "hbm", "kernel": "k_decompress", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+        roofline = {"bound": "hbm", "kernel": "k_ingest2 (2 launches per step: decompress half of the points + digit "
+                                              "histogram / scatter of all scalars)",
+                    "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                     "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": dec_bytes, "kernel_ms": dec_ms,
+                    "algorithmic_bytes_per_launch": ing_bytes, "kernel_ms": ing_ms, "kernel_ms_each": ing,
+                    "share_of_step": (sum(ing) / ms_step) if ing_ms else None,
                     "whole_path_hbm": {"bytes_per_proof": BYTES_PER_PROOF,
                                        "achieved_GBs": N * BYTES_PER_PROOF / (ms_step * 1e-3) / 1e9,
                                        "frac": N * BYTES_PER_PROOF / (ms_step * 1e-3) / 1e9 / hbm_peak},
-                    "integer_pipe": {"fe_sq_per_s_calibrated": fe_sq_rate, "fe_mul_per_s_calibrated": fe_mul_rate,
-                                     "k_decompress_frac_of_calibrated": (dec_time_at_peak / (dec_ms * 1e-3)) if dec_ms else None},
-                    "stage_ms": stages, "dominant_stage": dom}
+                    "integer_pipe": {"what": "the path is bound by IMAD.WIDE issue (profiles/r01_issue_model.md), not by "
+                                             "HBM: kernel time against the register-resident field-op rates of this run",
+                                     "fe_sq_per_s_calibrated": fe_sq_rate, "fe_mul_per_s_calibrated": fe_mul_rate,
+                                     "madd_per_s_calibrated": madd_rate,
+                                     "k_ingest2_frac_of_calibrated": (dec_time_at_peak / (ing_ms * 1e-3)) if ing_ms else None,
+                                     "k_accumulate_ms": acc_ms if acc_ms > 0 else None,
+                                     "k_accumulate_frac_of_calibrated":
+                                         (BUCKET_ADDS_PER_PROOF * N / madd_rate / (acc_ms * 1e-3)) if acc_ms > 0 else None},
+                    "stage_ms_unfused_profile_mode": stages, "dominant_stage_unfused": dom}
         sample = 1 << args.cpu_sample_log2
         sc_rows = sc.view(np.uint8).reshape(ROWS, N, 32)
         pt_rows = inst_points.numpy().reshape(ROWS, N, 32)

@@ -39,6 +39,10 @@ struct zkp_ctx {
   int profile = 0;
   cudaEvent_t ev[10] = {};
   float stage_ms[9] = {};
+  // always-on timing of the two ingestion launches of the device-resident fused path (stages 7, 8) and of the
+  // bucket accumulation kernel (stage 9): three event pairs per call, read back lazily by zkp_ctx_stage_ms
+  cudaEvent_t ev_live[6] = {};
+  bool live_valid = false;
   int last_window = 0, last_lanes = 0;
   // host-input pipeline: copies on copy_stream overlap the per-chunk kernels on `stream`
   cudaStream_t copy_stream = nullptr;
@@ -151,6 +155,8 @@ extern "C" void zkp_ctx_destroy(zkp_ctx* ctx) {
   for (cudaEvent_t e : ctx->chunk_ev) cudaEventDestroy(e);
   for (int i = 0; i < 10; i++)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  for (int i = 0; i < 6; i++)
+    if (ctx->ev_live[i]) cudaEventDestroy(ctx->ev_live[i]);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->sort_stream) cudaStreamDestroy(ctx->sort_stream);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
@@ -209,6 +215,16 @@ extern "C" double zkp_ctx_stage_ms(zkp_ctx* ctx, int32_t stage) {
   if (!ctx) return -1.0;
   if (stage == 100) return ctx->last_window;
   if (stage == 101) return ctx->last_lanes;
+  if (stage >= 7 && stage <= 9) {   // live events of the last fused device-resident call (the caller has synchronised)
+    if (!ctx->live_valid) return -1.0;
+    float ms = 0;
+    const int i = 2 * (stage - 7);
+    if (cudaEventElapsedTime(&ms, ctx->ev_live[i], ctx->ev_live[i + 1]) != cudaSuccess) {
+      cudaGetLastError();
+      return -1.0;
+    }
+    return ms;
+  }
   if (stage < 0 || stage > 6) return -1.0;
   return ctx->stage_ms[stage];
 }
@@ -251,6 +267,7 @@ static int32_t msm_prepare(zkp_ctx* ctx, size_t n, msm_plan* pl) {
     ctx->err = "n too large (>= 2^31 terms per call)";
     return ZKP_ERR_SIZE;
   }
+  ctx->live_valid = false;
   const int c = choose_window(ctx, n);
   const int W = (253 + c - 1) / c;
   const uint32_t B = 1u << (c - 1);
@@ -358,12 +375,20 @@ static int32_t msm_vartime_launch(zkp_ctx* ctx, const void* d_scalars, const voi
   if (use_fused_sort(ctx, pl)) {
     // phase 1: first half of the points + histogram of all scalars; scan; phase 2: second half + scatter of all scalars
     const size_t half_p = (n + 1) / 2;
+    if (!ctx->ev_live[0])
+      for (int i = 0; i < 6; i++) CUDA_TRY(ctx, cudaEventCreate(&ctx->ev_live[i]));
+    ctx->live_valid = false;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_live[0], st));
     r = launch_ingest2_range<0>(ctx, pl, d_scalars, d_points, n, 0, half_p, 0, n);
     if (r != ZKP_OK) return r;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_live[1], st));
     k_scan<<<pl.W, 1024, 0, st>>>((const uint32_t*)ctx->hist.p, pl.B, (uint32_t*)ctx->offs.p, (uint32_t*)ctx->cursor.p);
     LAUNCH_CHECK(ctx);
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_live[2], st));
     r = launch_ingest2_range<1>(ctx, pl, d_scalars, d_points, n, half_p, n - half_p, 0, n);
     if (r != ZKP_OK) return r;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_live[3], st));
+    ctx->live_valid = true;
     return msm_finish(ctx, pl, d_scalars, n, d_result, true, true);
   }
   r = msm_ingest(ctx, pl, d_scalars, d_points, 0, n, true);
@@ -441,10 +466,12 @@ static int32_t msm_finish(zkp_ctx* ctx, const msm_plan& pl, const void* d_scalar
       LAUNCH_CHECK(ctx);
       order = (const uint32_t*)ctx->order.p;
     }
+    if (ctx->live_valid) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_live[4], st));
     k_accumulate<<<blocks, 128, 0, st>>>((const uint4*)ctx->niels.p, (const uint32_t*)ctx->sorted.p,
                                          (const work_item*)ctx->items.p, order, n_items, n, (uint4*)ctx->buckets.p,
                                          (uint4*)ctx->partials.p);
     LAUNCH_CHECK(ctx);
+    if (ctx->live_valid) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_live[5], st));
     k_merge<<<148 * 8, 128, 0, st>>>((const uint32_t*)ctx->aux1.p, n_multi + 4, n_multi,
                                      (const uint4*)ctx->partials.p, (uint4*)ctx->buckets.p);
     LAUNCH_CHECK(ctx);

@@ -82,6 +82,12 @@ class Engine:
         d["lanes"] = int(self._lib.zkp_ctx_stage_ms(self._ctx, 101))
         return d
 
+    def live_ms(self):
+        """Device times of the dominant kernels of the LAST device-resident MSM, from events that are always recorded
+        (no profiling mode): the two ingestion launches and the bucket accumulation.  Call after synchronising."""
+        names = ("ingest_phase1", "ingest_phase2", "accumulate")
+        return {n: float(self._lib.zkp_ctx_stage_ms(self._ctx, 7 + i)) for i, n in enumerate(names)}
+
     @property
     def launch_count(self):
         return int(self._lib.zkp_ctx_launch_count(self._ctx))
