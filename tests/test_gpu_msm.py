@@ -176,6 +176,67 @@ def test_host_pipeline_chunking_overlap_and_profile_options(engine):
         engine.set_option("chunk_terms", 1 << 21)
 
 
+def test_two_phase_ingestion_and_item_balance_options(engine):
+    """The two-phase ingestion (histogram / scatter riding under the two halves of the decompression: k_ingest2) and the
+    size-ordered accumulation give the same bytes as the separate passes, for odd and even chunk counts, a single
+    chunk, odd term counts, and through the device-resident entry point (zkp_msm_vartime_dev)."""
+    import torch
+    case = U.golden("msm_seeded.json")["cases"][1]
+    base = U.base_points(case["K"])
+    sc = U.random_scalars(case["n"], seed=case["seed"])
+    pts = np.frombuffer(b"".join(base[i % case["K"]] for i in range(case["n"])), dtype=np.uint8).reshape(-1, 32)
+    n = case["n"]
+    from oracle import msm as M
+    odd = 4097
+    exp_odd = M.msm_bytes([sc[i].tobytes() for i in range(odd)], [pts[i].tobytes() for i in range(odd)])
+    try:
+        for fused in (1, 0):
+            for balance in (1, 0):
+                engine.set_option("fused_sort", fused)
+                engine.set_option("balance", balance)
+                for chunk in (1 << 21, 4096, 5000, n // 3 + 1, n):       # 1 chunk, many, ragged, 3 chunks (odd), exactly 1
+                    engine.set_option("chunk_terms", max(chunk, 1024))
+                    enc, _, _ = engine.msm_vartime(sc, pts)
+                    assert enc.hex() == case["expected"], (fused, balance, chunk)
+                engine.set_option("chunk_terms", 1024)
+                enc, _, _ = engine.msm_vartime(sc[:odd], pts[:odd])
+                assert enc == exp_odd, (fused, balance)
+                # device-resident entry point
+                d_sc = torch.from_numpy(sc).cuda()
+                d_pt = torch.from_numpy(pts.copy()).cuda()
+                d_res = torch.zeros(64, dtype=torch.uint8, device="cuda")
+                for cnt, exp in ((n, bytes.fromhex(case["expected"])), (odd, exp_odd), (1, None)):
+                    engine.msm_vartime_dev(d_sc.data_ptr(), d_pt.data_ptr(), cnt, d_res.data_ptr())
+                    engine.synchronize()
+                    r = d_res.cpu().numpy()
+                    assert int(np.frombuffer(r[32:36].tobytes(), dtype=np.int32)[0]) == 0
+                    if exp is not None:
+                        assert r[:32].tobytes() == exp, (fused, balance, cnt)
+                    else:
+                        assert r[:32].tobytes() == M.msm_bytes([sc[0].tobytes()], [pts[0].tobytes()])
+                if fused:
+                    live = engine.live_ms()
+                    assert live["ingest_phase1"] > 0 and live["ingest_phase2"] > 0 and live["accumulate"] > 0
+        # an invalid point / a non-canonical scalar in either half is reported with its index by the fused path
+        engine.set_option("fused_sort", 1)
+        engine.set_option("chunk_terms", 4096)
+        from zkp_b200 import EngineError
+        for idx in (3, n - 2):
+            bad = pts.copy()
+            bad[idx] = 0xFF
+            enc, _, first_bad = engine.msm_vartime(sc, bad)
+            assert enc is None and first_bad == idx
+            bs = sc.copy()
+            bs[idx] = 0xFF
+            with pytest.raises(EngineError) as ei:
+                engine.msm_vartime(bs, pts)
+            assert ei.value.code == 3
+    finally:
+        engine.set_option("fused_sort", 1)
+        engine.set_option("balance", 1)
+        engine.set_option("chunk_terms", 1 << 21)
+
+
 def test_abi_misuse_is_reported_not_crashed(engine):
     import ctypes
     from zkp_b200 import native
