@@ -218,6 +218,8 @@ def main():
         print(json.dumps(line))
         return
 
+    # NCCL prints its version banner / debug lines to stdout by default: keep stdout for the one JSON line
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
     from zkp_b200 import Engine

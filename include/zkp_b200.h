@@ -145,6 +145,19 @@ int32_t zkp_batch_verify_proofs(zkp_ctx* ctx, const zkp_statement_desc* st, cons
                                 const uint8_t* responses, const uint8_t* rho_seed, int32_t* accept, int64_t* first_bad,
                                 uint8_t* coeff_out, uint8_t* points_out);
 
+/* Batch proving with the per-proof work of Prover::prove_impl (/root/reference/src/toolbox/prover.rs:76-112) on the
+ * device: allocate_point compressions (toolbox/mod.rs:180), transcript replay, the synthetic-nonce blindings of
+ * prover.rs:78-89 (TranscriptRng rekeyed with every secret and finalized with entropy[j], the stand-in for thread_rng),
+ * the k constant-time MSMs + compress per proof (prover.rs:93-103), challenge and responses s*c + b (:106-109).
+ * secrets[N][m][32] canonical, points[N][p][20 u64] (p = ni + nc, FieldElement51 limbs X,Y,Z,T, the statement's
+ * allocation order instance ++ common), entropy[N][32] -> encodings_out[N][p][32], commitments_out[N][k][32],
+ * responses_out[N][m][32]; blindings_out[N][m][32] optional (parity tests).  prefix_state as for
+ * zkp_batch_verify_proofs.  Proof j equals what the reference's prover produces from the same transcript, secrets and
+ * entropy.  Returns ZKP_ERR_SCALAR for a non-canonical secret.                                                     */
+int32_t zkp_prove_batch(zkp_ctx* ctx, const zkp_statement_desc* st, const uint32_t* prefix_state, size_t N,
+                        const uint8_t* secrets, const uint64_t* points, const uint8_t* entropy, uint8_t* encodings_out,
+                        uint8_t* commitments_out, uint8_t* responses_out, uint8_t* blindings_out);
+
 /* Self-test of the device hashing code: out32 receives Merlin's published conformance vector (a8c933f5...). */
 int32_t zkp_selftest_hash(zkp_ctx* ctx, uint8_t* out32);
 

@@ -68,6 +68,12 @@ int32_t zkph_prove_many(zkp_ctx* ctx, const zkph_statement* st, const uint8_t* t
                         const uint8_t* secrets, const uint64_t* points, const uint8_t* entropy, int32_t threads,
                         uint8_t* encodings, uint8_t* commitments, uint8_t* responses);
 
+/* The same N proofs with the per-proof transcript / nonce / response work on the DEVICE (zkp_prove_batch, SURVEY.md 8f-1
+ * for the prover): the host hashes only the batch-wide transcript prefix.  Byte-identical to zkph_prove_many.          */
+int32_t zkph_prove_many_device(zkp_ctx* ctx, const zkph_statement* st, const uint8_t* transcript_label, size_t tl_len,
+                               size_t N, const uint8_t* secrets, const uint64_t* points, const uint8_t* entropy,
+                               uint8_t* encodings, uint8_t* commitments, uint8_t* responses);
+
 /* merlin::Transcript handles, for callers that drive the transcript themselves the way the reference's API takes
  * `&mut Transcript` (e.g. /root/reference/tests/sig_and_vrf_example.rs:86-125: messages are appended before proving).
  * The *_t entry points below mutate the handle exactly like the reference mutates its transcript.               */

@@ -137,6 +137,20 @@ void emul_transcript_test(uint8_t* out32) {
   }
   memcpy(out32, ch, 32);
 }
+// TranscriptRng on the device state machine (prover front end): Transcript("test protocol"), one append, then
+// build_rng -> rekey with n_w witnesses of 32 bytes -> finalize(entropy) -> n_out draws of 64 bytes
+void emul_transcript_rng(uint8_t* out, const uint8_t* witnesses, int n_w, const uint8_t* entropy32, int n_out) {
+  strobe_t s; for (int i = 0; i < 25; i++) s.st[i] = 0;
+  uint8_t* b = st_bytes(s); const uint8_t init[6] = {1, 168, 1, 0, 1, 96};
+  memcpy(b, init, 6); memcpy(b + 6, "STROBEv1.0.2", 12); keccak_f1600_dev(s.st);
+  s.pos = 0; s.pos_begin = 0; s.cur_flags = 0;
+  strobe_meta_ad(s, (const uint8_t*)"Merlin v1.0", 11, false);
+  transcript_append(s, (const uint8_t*)"dom-sep", 7, (const uint8_t*)"test protocol", 13);
+  transcript_append(s, (const uint8_t*)"step1", 5, (const uint8_t*)"some data", 9);
+  for (int i = 0; i < n_w; i++) rng_rekey_with_witness(s, (const uint8_t*)"", 0, witnesses + 32 * i, 32);
+  rng_finalize(s, entropy32);
+  for (int i = 0; i < n_out; i++) rng_fill_bytes(s, out + 64 * i, 64);
+}
 void emul_shake(uint8_t* out, uint32_t n, const uint8_t* msg, uint32_t len) { shake256_short(out, n, msg, len); }
 void emul_scl_mul(uint8_t* r, const uint8_t* a, const uint8_t* b) { scl x, y, z; memcpy(x.v, a, 32); memcpy(y.v, b, 32); scl_mul(z, x, y); memcpy(r, z.v, 32); }
 void emul_scl_add(uint8_t* r, const uint8_t* a, const uint8_t* b) { scl x, y, z; memcpy(x.v, a, 32); memcpy(y.v, b, 32); scl_add(z, x, y); memcpy(r, z.v, 32); }

@@ -199,6 +199,65 @@ def test_batch_verify_device_front_end_matches_oracle(engine):
     assert [bytes(p) for p in po] == opts and [bytes(c) for c in co] == [S.to_bytes(s) for s in oscal]
 
 
+def test_prove_many_device_front_end_matches_host_and_oracle(engine):
+    """zkp_prove_batch (allocate_point compressions, transcript replay, TranscriptRng blindings, constant-time MSMs,
+    challenge and responses on the GPU) is byte-identical to the host mirror and to the oracle prover given the same
+    entropy: CMZ (11 constraints, 31 terms), DLEQ, a statement with a static lhs, N = 1, and an empty batch."""
+    st, ost = PT.cmz10_statement(), OT.CMZ10
+    N = 7
+    secs, ptss = _cmz_instances(N, b"cmz-pv")
+    sec_arr = np.stack([sbytes([s[n] for n in st.secrets]) for s in secs])
+    pts_arr = np.array([[limbs(p[n]) for n in st.points] for p in ptss], dtype=np.uint64)
+    entropy = np.frombuffer(OT.SeededRng(b"entropy-pv").bytes(32 * N), dtype=np.uint8).reshape(N, 32)
+    enc_h, com_h, resp_h = st.prove_many(engine, b"CMZ", sec_arr, pts_arr, entropy, threads=2)
+    enc_d, com_d, resp_d = st.prove_many_device(engine, b"CMZ", sec_arr, pts_arr, entropy)
+    assert (enc_d == enc_h).all() and (com_d == com_h).all() and (resp_d == resp_h).all()
+
+    class OneShot:
+        def __init__(self, b): self.b = b
+        def bytes(self, n): return self.b
+    for j in (0, N - 1):
+        op, oenc = ost.prove_batchable(OM.Transcript(b"CMZ"), secs[j], ptss[j], OneShot(entropy[j].tobytes()))
+        assert [bytes(c) for c in com_d[j]] == op.commitments
+        assert [bytes(r) for r in resp_d[j]] == [S.to_bytes(r) for r in op.responses]
+        assert [bytes(e) for e in enc_d[j]] == [oenc[n] for n in st.points]
+    # the device-made proofs verify (single and batch), a different transcript label gives different proofs
+    st.verify_batchable(engine, (com_d[3], resp_d[3]), b"CMZ", enc_d[3], b"rho")
+    ni = len(st.instance)
+    st.batch_verify_device(engine, com_d, resp_d, b"CMZ", np.ascontiguousarray(enc_d[:, :ni].transpose(1, 0, 2)), enc_d[0, ni:],
+                           bytes(range(32)))
+    _, com_x, _ = st.prove_many_device(engine, b"CMY", sec_arr, pts_arr, entropy)
+    assert (com_x != com_d).any()
+    # N = 1 and the empty batch
+    e1, c1, r1 = st.prove_many_device(engine, b"CMZ", sec_arr[:1], pts_arr[:1], entropy[:1])
+    assert (e1 == enc_h[:1]).all() and (c1 == com_h[:1]).all() and (r1 == resp_h[:1]).all()
+    e0, c0, r0 = st.prove_many_device(engine, b"CMZ", sec_arr[:0], pts_arr[:0], entropy[:0])
+    assert e0.shape[0] == 0 and c0.shape[0] == 0 and r0.shape[0] == 0
+    # a non-canonical secret is refused
+    bad = sec_arr.copy()
+    bad[2, 4] = 0xFF
+    with pytest.raises(Exception):
+        st.prove_many_device(engine, b"CMZ", bad, pts_arr, entropy)
+    # DLEQ and a statement with a static left-hand side
+    dst = PT.dleq_statement()
+    G = R.BASEPOINT
+    H = R.hash_from_bytes_sha512(R.compress(G))
+    xs = [89327492234 + j for j in range(9)]
+    dl = np.array([[limbs(R.pt_mul(x, G)), limbs(R.pt_mul(x, H)), limbs(H), limbs(G)] for x in xs], dtype=np.uint64)
+    ent = np.frombuffer(OT.SeededRng(b"e-pv").bytes(32 * 9), dtype=np.uint8).reshape(9, 32)
+    dsec = np.stack([sbytes([x]) for x in xs])
+    a = dst.prove_many(engine, b"DLEQBatchTest", dsec, dl, ent, threads=2)
+    b = dst.prove_many_device(engine, b"DLEQBatchTest", dsec, dl, ent)
+    assert all((x == y).all() for x, y in zip(a, b))
+    pk = PT.Statement("pk", "PK proof", ["x"], ["A"], ["G", "Q"], [("A", [("x", "G")]), ("Q", [("x", "G")])])
+    Q = R.pt_mul(123456789, G)
+    pts = np.array([[limbs(Q), limbs(G), limbs(Q)] for _ in range(4)], dtype=np.uint64)
+    ent = np.frombuffer(OT.SeededRng(b"pk-pv").bytes(32 * 4), dtype=np.uint8).reshape(4, 32)
+    a = pk.prove_many(engine, b"PK", np.stack([sbytes([123456789])] * 4), pts, ent, threads=1)
+    b = pk.prove_many_device(engine, b"PK", np.stack([sbytes([123456789])] * 4), pts, ent)
+    assert all((x == y).all() for x, y in zip(a, b))
+
+
 def test_device_front_end_edge_shapes(engine):
     """N = 1, an empty batch, and a statement whose constraint has a STATIC lhs (static_coeffs path of
     batch_verifier.rs:187-189) through both the host mirror and the device front end."""

@@ -231,6 +231,22 @@ def test_device_hash_and_scalar_logic(lib):
     o = ctypes.create_string_buffer(32)
     lib.emul_transcript_test(o)
     assert o.raw.hex() == U.golden("merlin.json")["complex"]
+    # TranscriptRng (prover front end: rekey with witnesses, finalize with entropy, 64-byte draws) against the oracle
+    from oracle import merlin as OM
+    rr = random.Random(21)
+    for n_w, n_out in ((0, 1), (1, 1), (3, 4), (21, 21)):
+        wit = [rr.randbytes(32) for _ in range(n_w)]
+        ent = rr.randbytes(32)
+        t = OM.Transcript(b"test protocol")
+        t.append_message(b"step1", b"some data")
+        bld = t.build_rng()
+        for w in wit:
+            bld.rekey_with_witness_bytes(b"", w)
+        rng = bld.finalize(ent)
+        exp = b"".join(rng.fill_bytes(64) for _ in range(n_out))
+        out = ctypes.create_string_buffer(64 * n_out)
+        lib.emul_transcript_rng(out, b"".join(wit), n_w, ent, n_out)
+        assert out.raw == exp, (n_w, n_out)
     for n, m in [(16, b"abc"), (176, b"seed" * 8 + b"\x01" * 8), (300, b"x" * 135), (136, b"")]:
         out = ctypes.create_string_buffer(n)
         lib.emul_shake(out, n, m, len(m))

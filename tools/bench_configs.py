@@ -56,6 +56,10 @@ def main():
     st.prove_many(eng, b"CMZ", sec[:256], limbs[:256], entropy[:256], threads=threads)     # warm-up
     t_prove, (enc, com, resp) = timed(lambda: st.prove_many(eng, b"CMZ", sec, limbs, entropy, threads=threads))
     assert (enc == enc_expected).all()
+    # the same proofs with the per-proof transcript / nonce / response work on the GPU (zkp_prove_batch)
+    st.prove_many_device(eng, b"CMZ", sec[:256], limbs[:256], entropy[:256])               # warm-up
+    t_prove_dev, (enc_d, com_d, resp_d) = timed(lambda: st.prove_many_device(eng, b"CMZ", sec, limbs, entropy), 2)
+    assert (enc_d == enc).all() and (com_d == com).all() and (resp_d == resp).all()
     # device part alone: the N*11 constant-time MSMs + compressions from prepared inputs
     k_terms = [2] * 10 + [11]
     sc_idx = [i for c in range(10) for i in (c, 10 + c)] + list(range(10)) + [20]
@@ -68,6 +72,7 @@ def main():
     t_ct, _ = timed(lambda: eng.msm_ct_batched(ct_sc, ct_pt, off, limbs=True))
     t_cmp, _ = timed(lambda: eng.compress_batch(limbs.reshape(-1, 20)))
     res["config1_cmz_prove"] = {"proofs": N, "prove_many_s": t_prove, "proofs_per_s": N / t_prove,
+                                "prove_many_device_s": t_prove_dev, "proofs_per_s_device_front_end": N / t_prove_dev,
                                 "device_ct_msm_plus_compress_s": t_ct, "ct_msms_per_s": N * 11 / t_ct,
                                 "device_compress_25_points_per_proof_s": t_cmp,
                                 "note": "prove_many = batched compress + host Merlin/blindings (%d threads) + one "

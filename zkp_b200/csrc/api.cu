@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include <new>
 #include <string>
 #include <vector>
@@ -14,6 +15,7 @@
 #include "small_msm.cuh"
 #include "bench_fe.cuh"
 #include "bv_kernels.cuh"
+#include "pv_kernels.cuh"
 
 using namespace zkp;
 
@@ -33,7 +35,8 @@ struct zkp_ctx {
   std::string err;
   // workspace (grown on demand, reused across calls)
   devbuf in_scalars, in_points, niels, hist, offs, cursor, sorted, buckets, lvlT[2], lvlU, usum, flags, result,
-      aux0, aux1, aux2, sk0, sk1, tables, items, partials, multi, bv_com, bv_resp, bv_part, bv_misc, len_hist, order;
+      aux0, aux1, aux2, sk0, sk1, tables, items, partials, multi, bv_com, bv_resp, bv_part, bv_misc, len_hist, order,
+      pv_limbs, pv_enc, pv_sec, pv_ent, pv_state, pv_blind, pv_resp, pv_misc;
   void* h_result = nullptr;  // pinned, 64 bytes
   // optional per-stage timing of the vartime MSM ("profile" option): events around each stage
   int profile = 0;
@@ -148,7 +151,8 @@ extern "C" void zkp_ctx_destroy(zkp_ctx* ctx) {
                     &ctx->sorted, &ctx->buckets, &ctx->lvlT[0], &ctx->lvlT[1], &ctx->lvlU, &ctx->usum,
                     &ctx->flags, &ctx->result, &ctx->aux0, &ctx->aux1, &ctx->aux2, &ctx->sk0, &ctx->sk1,
                     &ctx->tables, &ctx->items, &ctx->partials, &ctx->multi, &ctx->bv_com, &ctx->bv_resp, &ctx->bv_part,
-                    &ctx->bv_misc, &ctx->len_hist, &ctx->order};
+                    &ctx->bv_misc, &ctx->len_hist, &ctx->order, &ctx->pv_limbs, &ctx->pv_enc, &ctx->pv_sec, &ctx->pv_ent,
+                    &ctx->pv_state, &ctx->pv_blind, &ctx->pv_resp, &ctx->pv_misc};
   for (devbuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (ctx->h_result) cudaFreeHost(ctx->h_result);
@@ -865,6 +869,141 @@ extern "C" int32_t zkp_batch_verify_proofs(zkp_ctx* ctx, const zkp_statement_des
   r = fetch_result(ctx, nullptr, &ident, first_bad);   // identity encodings / bad points -> 1, bad responses -> 3
   if (r != ZKP_OK) return r;
   *accept = ident;
+  return ZKP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// batch proving: N proofs of one statement, per-proof transcript / nonce / response work on the device
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int32_t zkp_prove_batch(zkp_ctx* ctx, const zkp_statement_desc* sd, const uint32_t* prefix_state, size_t N,
+                                   const uint8_t* secrets, const uint64_t* points, const uint8_t* entropy,
+                                   uint8_t* encodings_out, uint8_t* commitments_out, uint8_t* responses_out,
+                                   uint8_t* blindings_out) {
+  if (!ctx || !sd || !prefix_state) return ZKP_ERR_SIZE;
+  const int m = sd->m, ni = sd->ni, nc = sd->nc, k = sd->k, p = ni + nc;
+  if (m < 0 || ni < 0 || nc < 0 || k < 0 || p > 2 * ZKP_BV_MAX_VARS || k > ZKP_BV_MAX_CONS) return ZKP_ERR_SIZE;
+  if (!N) return ZKP_OK;
+  if ((m && (!secrets || !responses_out)) || (p && (!points || !encodings_out)) || (k && !commitments_out) || !entropy)
+    return ZKP_ERR_SIZE;
+  const int n_terms = k ? sd->cons_off[k] : 0;
+  if ((double)N * (n_terms > p ? n_terms : p) > 1.5e9) return ZKP_ERR_SIZE;
+  for (int c = 0; c < k; c++)
+    if (sd->lhs[c] < 0 || sd->lhs[c] >= p || sd->cons_off[c + 1] < sd->cons_off[c]) return ZKP_ERR_SIZE;
+  for (int q = 0; q < n_terms; q++)
+    if (sd->term_point[q] < 0 || sd->term_point[q] >= p || sd->term_scalar[q] < 0 || sd->term_scalar[q] >= m)
+      return ZKP_ERR_SIZE;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  // ---- statement blob: prefix | label pool | label offsets/lengths | lhs | cons_off | term arrays | schedule slots ----
+  std::vector<uint32_t> loff, llen;
+  std::vector<uint8_t> pool;
+  const char* lp = sd->labels;
+  for (int i = 0; i < p; i++) {
+    size_t len = strlen(lp);
+    loff.push_back((uint32_t)pool.size());
+    llen.push_back((uint32_t)len);
+    pool.insert(pool.end(), lp, lp + len);
+    lp += len + 1;
+  }
+  // MSM schedule: constraints ordered by (public) size, largest first, so that the lanes of a warp do equal work
+  std::vector<int32_t> by_size(k), slot(k);
+  for (int c = 0; c < k; c++) by_size[c] = c;
+  std::stable_sort(by_size.begin(), by_size.end(), [&](int a, int b) {
+    return sd->cons_off[a + 1] - sd->cons_off[a] > sd->cons_off[b + 1] - sd->cons_off[b];
+  });
+  for (int r0 = 0; r0 < k; r0++) slot[by_size[r0]] = r0;
+  auto pad16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+  const size_t o_prefix = 0, o_pool = pad16(53 * 4), o_lo = pad16(o_pool + pool.size()), o_ll = pad16(o_lo + (size_t)p * 4),
+               o_lhs = pad16(o_ll + (size_t)p * 4), o_co = pad16(o_lhs + (size_t)k * 4), o_ts = pad16(o_co + (size_t)(k + 1) * 4),
+               o_tp = pad16(o_ts + (size_t)n_terms * 4), o_sl = pad16(o_tp + (size_t)n_terms * 4),
+               blob_sz = pad16(o_sl + (size_t)k * 4) + 16;
+  std::vector<uint8_t> blob(blob_sz, 0);
+  memcpy(&blob[o_prefix], prefix_state, 53 * 4);
+  if (!pool.empty()) memcpy(&blob[o_pool], pool.data(), pool.size());
+  if (p) { memcpy(&blob[o_lo], loff.data(), (size_t)p * 4); memcpy(&blob[o_ll], llen.data(), (size_t)p * 4); }
+  if (k) { memcpy(&blob[o_lhs], sd->lhs, (size_t)k * 4); memcpy(&blob[o_sl], slot.data(), (size_t)k * 4); }
+  memcpy(&blob[o_co], sd->cons_off, (size_t)(k + 1) * 4);
+  if (n_terms) { memcpy(&blob[o_ts], sd->term_scalar, (size_t)n_terms * 4); memcpy(&blob[o_tp], sd->term_point, (size_t)n_terms * 4); }
+  const size_t total = N * (size_t)n_terms, M = N * (size_t)k;
+  ENSURE(ctx, ctx->pv_misc, blob_sz);
+  ENSURE(ctx, ctx->pv_limbs, N * (size_t)p * 160 + 160);
+  ENSURE(ctx, ctx->pv_enc, N * (size_t)p * 32 + 32);
+  ENSURE(ctx, ctx->pv_sec, N * (size_t)m * 32 + 32);
+  ENSURE(ctx, ctx->pv_ent, N * 32);
+  ENSURE(ctx, ctx->pv_state, N * 56 * 4);
+  ENSURE(ctx, ctx->pv_blind, N * (size_t)m * 32 + 32);
+  ENSURE(ctx, ctx->pv_resp, N * (size_t)m * 32 + 32);
+  ENSURE(ctx, ctx->in_scalars, total * 32 + 32);
+  ENSURE(ctx, ctx->niels, total * 128 + 128);
+  ENSURE(ctx, ctx->tables, total * 1024 + 1024);
+  ENSURE(ctx, ctx->sk0, total * 32 + 32);
+  ENSURE(ctx, ctx->aux0, (M + 1) * 8);
+  ENSURE(ctx, ctx->aux1, M * 32 + 32);
+  ENSURE(ctx, ctx->multi, M * 4 + 16);
+  ENSURE(ctx, ctx->flags, 16);
+  uint8_t* dm = (uint8_t*)ctx->pv_misc.p;
+  CUDA_TRY(ctx, cudaMemcpyAsync(dm, blob.data(), blob_sz, cudaMemcpyHostToDevice, st));
+  if (p) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->pv_limbs.p, points, N * (size_t)p * 160, cudaMemcpyHostToDevice, st));
+  if (m) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->pv_sec.p, secrets, N * (size_t)m * 32, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->pv_ent.p, entropy, N * 32, cudaMemcpyHostToDevice, st));
+  k_init_flags<<<1, 1, 0, st>>>((int*)ctx->flags.p);
+  LAUNCH_CHECK(ctx);
+  pv_desc d;
+  d.m = m; d.p = p; d.k = k; d.n_terms = n_terms;
+  d.label_off = (const uint32_t*)(dm + o_lo);
+  d.label_len = (const uint32_t*)(dm + o_ll);
+  d.labels = dm + o_pool;
+  d.lhs = (const int32_t*)(dm + o_lhs);
+  d.cons_off = (const int32_t*)(dm + o_co);
+  d.term_scalar = (const int32_t*)(dm + o_ts);
+  d.term_point = (const int32_t*)(dm + o_tp);
+  d.cons_slot = (const int32_t*)(dm + o_sl);
+  // (1) every allocate_point compression (toolbox/mod.rs:180)
+  if (p) {
+    k_compress_limbs<<<(unsigned)((N * p + 255) / 256), 256, 0, st>>>((const unsigned long long*)ctx->pv_limbs.p, N * p,
+                                                                      (uint4*)ctx->pv_enc.p);
+    LAUNCH_CHECK(ctx);
+  }
+  // (2) transcripts up to the commitments + synthetic-nonce blindings (prover.rs:78-89)
+  k_pv_blind<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(d, (const uint32_t*)(dm + o_prefix), N, (const uint8_t*)ctx->pv_enc.p,
+                                                          (const uint8_t*)ctx->pv_sec.p, (const uint8_t*)ctx->pv_ent.p,
+                                                          (uint32_t*)ctx->pv_state.p, (uint8_t*)ctx->pv_blind.p,
+                                                          (int*)ctx->flags.p);
+  LAUNCH_CHECK(ctx);
+  // (3) the N*k constant-time MSMs + compress (prover.rs:93-103)
+  if (M) {
+    size_t gthreads = total > M ? total : M;
+    if (!gthreads) gthreads = 1;
+    k_pv_gather<<<(unsigned)((gthreads + 255) / 256), 256, 0, st>>>(d, N, (const unsigned long long*)ctx->pv_limbs.p,
+                                                                    (const uint8_t*)ctx->pv_blind.p, (uint4*)ctx->in_scalars.p,
+                                                                    (uint4*)ctx->niels.p, (unsigned long long*)ctx->aux0.p,
+                                                                    (uint32_t*)ctx->multi.p);
+    LAUNCH_CHECK(ctx);
+    if (total) {
+      k_build_tables<<<(unsigned)((total + 127) / 128), 128, 0, st>>>((const uint4*)ctx->niels.p, (const uint4*)ctx->in_scalars.p,
+                                                                      total, (uint4*)ctx->tables.p, (uint4*)ctx->sk0.p,
+                                                                      (int*)ctx->flags.p + 2);   // blindings are canonical
+      LAUNCH_CHECK(ctx);
+    }
+    k_small_msm_ct<<<(unsigned)((M + 63) / 64), 64, 0, st>>>((const uint32_t*)ctx->sk0.p, (const uint4*)ctx->tables.p,
+                                                             (const unsigned long long*)ctx->aux0.p,
+                                                             (const uint32_t*)ctx->multi.p, M, (uint4*)ctx->aux1.p);
+    LAUNCH_CHECK(ctx);
+  }
+  // (4) commitments into the transcript, challenge, responses (prover.rs:98-109)
+  k_pv_finish<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(d, N, (const uint32_t*)ctx->pv_state.p, (const uint8_t*)ctx->aux1.p,
+                                                           (const uint8_t*)ctx->pv_sec.p, (const uint8_t*)ctx->pv_blind.p,
+                                                           (uint8_t*)ctx->pv_resp.p);
+  LAUNCH_CHECK(ctx);
+  int hflags[4];
+  if (p) CUDA_TRY(ctx, cudaMemcpyAsync(encodings_out, ctx->pv_enc.p, N * (size_t)p * 32, cudaMemcpyDeviceToHost, st));
+  if (k) CUDA_TRY(ctx, cudaMemcpyAsync(commitments_out, ctx->aux1.p, M * 32, cudaMemcpyDeviceToHost, st));
+  if (m) CUDA_TRY(ctx, cudaMemcpyAsync(responses_out, ctx->pv_resp.p, N * (size_t)m * 32, cudaMemcpyDeviceToHost, st));
+  if (m && blindings_out)
+    CUDA_TRY(ctx, cudaMemcpyAsync(blindings_out, ctx->pv_blind.p, N * (size_t)m * 32, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(hflags, ctx->flags.p, 16, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  if (hflags[1] != 0x7fffffff) return ZKP_ERR_SCALAR;   // a non-canonical secret
   return ZKP_OK;
 }
 

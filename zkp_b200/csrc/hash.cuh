@@ -149,6 +149,38 @@ ZKP_DEV void transcript_challenge(strobe_t& s, const uint8_t* label, uint32_t ll
   strobe_prf(s, out, n, false);
 }
 
+// STROBE KEY operation (flags A|C: the state bytes are overwritten, not xored) -- merlin strobe.rs `key` [ext]
+ZKP_DEV void strobe_overwrite(strobe_t& s, const uint8_t* d, uint32_t n) {
+  uint8_t* b = st_bytes(s);
+  for (uint32_t i = 0; i < n; i++) {
+    b[s.pos] = d[i];
+    if (++s.pos == ZKP_STROBE_R) strobe_run_f(s);
+  }
+}
+ZKP_DEV void strobe_key(strobe_t& s, const uint8_t* d, uint32_t n, bool more) {
+  strobe_begin_op(s, ZKP_FLAG_A | ZKP_FLAG_C, more);
+  strobe_overwrite(s, d, n);
+}
+// merlin TranscriptRngBuilder::rekey_with_witness_bytes / finalize and TranscriptRng::fill_bytes [ext]
+ZKP_DEV void rng_rekey_with_witness(strobe_t& s, const uint8_t* label, uint32_t llen, const uint8_t* w, uint32_t wlen) {
+  uint8_t l4[4];
+  l4[0] = (uint8_t)wlen; l4[1] = (uint8_t)(wlen >> 8); l4[2] = (uint8_t)(wlen >> 16); l4[3] = (uint8_t)(wlen >> 24);
+  strobe_meta_ad(s, label, llen, false);
+  strobe_meta_ad(s, l4, 4, true);
+  strobe_key(s, w, wlen, false);
+}
+ZKP_DEV void rng_finalize(strobe_t& s, const uint8_t* entropy32) {
+  const uint8_t L_RNG[3] = {'r', 'n', 'g'};
+  strobe_meta_ad(s, L_RNG, 3, false);
+  strobe_key(s, entropy32, 32, false);
+}
+ZKP_DEV void rng_fill_bytes(strobe_t& s, uint8_t* out, uint32_t n) {
+  uint8_t l4[4];
+  l4[0] = (uint8_t)n; l4[1] = (uint8_t)(n >> 8); l4[2] = (uint8_t)(n >> 16); l4[3] = (uint8_t)(n >> 24);
+  strobe_meta_ad(s, l4, 4, false);
+  strobe_prf(s, out, n, false);
+}
+
 // SHAKE-256 of a short message (< 136 bytes), first `n` output bytes: the per-proof weight generator
 ZKP_DEV void shake256_short(uint8_t* out, uint32_t n, const uint8_t* msg, uint32_t len) {
   uint64_t st[25];

@@ -264,6 +264,51 @@ extern "C" int32_t zkph_batch_verify_device(zkp_ctx* ctx, const zkph_statement* 
   return accept ? PROOF_OK : VerificationFailure;
 }
 
+// statement -> flat descriptor of zkp_b200.h (labels of instance ++ common points, constraint CSR)
+struct flat_stmt {
+  std::string labels;
+  std::vector<int32_t> lhs, off, ts, tp;
+  zkp_statement_desc d;
+  explicit flat_stmt(const Statement& st) : off(1, 0) {
+    for (auto& s : st.instance) labels += s + std::string(1, '\0');
+    for (auto& s : st.common) labels += s + std::string(1, '\0');
+    for (auto& c : st.constraints) {
+      lhs.push_back(c.first);
+      for (auto& term : c.second) {
+        ts.push_back(term.first);
+        tp.push_back(term.second);
+      }
+      off.push_back((int32_t)ts.size());
+    }
+    d.m = (int32_t)st.secrets.size();
+    d.ni = (int32_t)st.instance.size();
+    d.nc = (int32_t)st.common.size();
+    d.k = (int32_t)st.constraints.size();
+    d.labels = labels.c_str();
+    d.lhs = lhs.data();
+    d.cons_off = off.data();
+    d.term_scalar = ts.data();
+    d.term_point = tp.data();
+  }
+};
+
+extern "C" int32_t zkph_prove_many_device(zkp_ctx* ctx, const zkph_statement* h, const uint8_t* tl, size_t tl_len, size_t N,
+                                          const uint8_t* secrets, const uint64_t* points, const uint8_t* entropy,
+                                          uint8_t* encodings, uint8_t* commitments, uint8_t* responses) {
+  const Statement& st = h->st;
+  // batch-wide transcript prefix: Transcript::new(label), dom-sep, scalar labels (macros.rs:206-214)
+  Transcript t(tl, tl_len);
+  domain_sep(t, st.label);
+  for (auto& s : st.secrets) append_scalar_var(t, s);
+  uint32_t prefix[53];
+  t.export_state(prefix);
+  flat_stmt f(st);
+  int32_t rc = zkp_prove_batch(ctx, &f.d, prefix, N, secrets, points, entropy, encodings, commitments, responses, nullptr);
+  if (rc == ZKP_ERR_SIZE) return BatchSizeMismatch;
+  if (rc != ZKP_OK) return EngineFailure;
+  return PROOF_OK;
+}
+
 extern "C" int32_t zkph_prove_many(zkp_ctx* ctx, const zkph_statement* h, const uint8_t* tl, size_t tl_len, size_t N,
                                    const uint8_t* secrets, const uint64_t* points, const uint8_t* entropy,
                                    int32_t threads, uint8_t* encodings, uint8_t* commitments, uint8_t* responses) {

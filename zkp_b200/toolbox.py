@@ -52,6 +52,7 @@ def _lib():
         lib.zkph_batch_verify.argtypes = [vp, vp, vp, sz, sz, vp, vp, vp, vp, vp, sz, i32, vp, vp, vp]
         lib.zkph_prove_many.argtypes = [vp, vp, vp, sz, sz, vp, vp, vp, i32, vp, vp, vp]
         lib.zkph_batch_verify_device.argtypes = [vp, vp, vp, sz, sz, vp, vp, vp, vp, vp, vp, vp]
+        lib.zkph_prove_many_device.argtypes = [vp, vp, vp, sz, sz, vp, vp, vp, vp, vp, vp]
         lib.zkph_transcript_new.restype = vp
         lib.zkph_transcript_new.argtypes = [vp, sz]
         lib.zkph_transcript_clone.restype = vp
@@ -238,6 +239,21 @@ class Statement:
         resp = np.zeros((N, self.m, 32), np.uint8)
         _raise(_lib().zkph_prove_many(eng._ctx, self._h, transcript_label, len(transcript_label), N, _p(sec), _p(pts),
                                       _p(ent), int(threads), _p(enc), _p(com), _p(resp)))
+        return enc, com, resp
+
+
+    def prove_many_device(self, eng, transcript_label, secrets, points_limbs, entropy):
+        """prove_many with the per-proof transcript, nonce and response work on the GPU (zkp_prove_batch): the host hashes
+        only the batch-wide transcript prefix.  Byte-identical to prove_many."""
+        sec = np.ascontiguousarray(secrets, dtype=np.uint8).reshape(-1, self.m, 32)
+        N = sec.shape[0]
+        pts = np.ascontiguousarray(points_limbs, dtype=np.uint64).reshape(N, self.p, 20)
+        ent = np.ascontiguousarray(entropy, dtype=np.uint8).reshape(N, 32)
+        enc = np.zeros((N, self.p, 32), np.uint8)
+        com = np.zeros((N, self.k, 32), np.uint8)
+        resp = np.zeros((N, self.m, 32), np.uint8)
+        _raise(_lib().zkph_prove_many_device(eng._ctx, self._h, transcript_label, len(transcript_label), N, _p(sec), _p(pts),
+                                             _p(ent), _p(enc), _p(com), _p(resp)))
         return enc, com, resp
 
 
