@@ -60,6 +60,12 @@ def main():
     st.prove_many_device(eng, b"CMZ", sec[:256], limbs[:256], entropy[:256])               # warm-up
     t_prove_dev, (enc_d, com_d, resp_d) = timed(lambda: st.prove_many_device(eng, b"CMZ", sec, limbs, entropy), 2)
     assert (enc_d == enc).all() and (com_d == com).all() and (resp_d == resp).all()
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    sec_p, limbs_p, ent_p = pin(sec), pin(limbs), pin(entropy)
+    outs = tuple(torch.zeros(shp, dtype=torch.uint8).pin_memory().numpy() for shp in ((N, 25, 32), (N, 11, 32), (N, 21, 32)))
+    t_prove_pin, (enc_d, com_d, resp_d) = timed(
+        lambda: st.prove_many_device(eng, b"CMZ", sec_p, limbs_p, ent_p, out=outs), 3)
+    assert (enc_d == enc).all() and (com_d == com).all() and (resp_d == resp).all()
     # device part alone: the N*11 constant-time MSMs + compressions from prepared inputs
     k_terms = [2] * 10 + [11]
     sc_idx = [i for c in range(10) for i in (c, 10 + c)] + list(range(10)) + [20]
@@ -73,6 +79,8 @@ def main():
     t_cmp, _ = timed(lambda: eng.compress_batch(limbs.reshape(-1, 20)))
     res["config1_cmz_prove"] = {"proofs": N, "prove_many_s": t_prove, "proofs_per_s": N / t_prove,
                                 "prove_many_device_s": t_prove_dev, "proofs_per_s_device_front_end": N / t_prove_dev,
+                                "prove_many_device_pinned_s": t_prove_pin,
+                                "proofs_per_s_device_front_end_pinned": N / t_prove_pin,
                                 "device_ct_msm_plus_compress_s": t_ct, "ct_msms_per_s": N * 11 / t_ct,
                                 "device_compress_25_points_per_proof_s": t_cmp,
                                 "note": "prove_many = batched compress + host Merlin/blindings (%d threads) + one "

@@ -935,7 +935,7 @@ extern "C" int32_t zkp_prove_batch(zkp_ctx* ctx, const zkp_statement_desc* sd, c
   ENSURE(ctx, ctx->pv_resp, N * (size_t)m * 32 + 32);
   ENSURE(ctx, ctx->in_scalars, total * 32 + 32);
   ENSURE(ctx, ctx->niels, total * 128 + 128);
-  ENSURE(ctx, ctx->tables, total * 1024 + 1024);
+  ENSURE(ctx, ctx->tables, ((N + 31) / 32 * 32) * (size_t)n_terms * 1024 + 1024);   // interleaved in groups of 32 proofs
   ENSURE(ctx, ctx->sk0, total * 32 + 32);
   ENSURE(ctx, ctx->aux0, (M + 1) * 8);
   ENSURE(ctx, ctx->aux1, M * 32 + 32);
@@ -980,14 +980,15 @@ extern "C" int32_t zkp_prove_batch(zkp_ctx* ctx, const zkp_statement_desc* sd, c
                                                                     (uint32_t*)ctx->multi.p);
     LAUNCH_CHECK(ctx);
     if (total) {
-      k_build_tables<<<(unsigned)((total + 127) / 128), 128, 0, st>>>((const uint4*)ctx->niels.p, (const uint4*)ctx->in_scalars.p,
-                                                                      total, (uint4*)ctx->tables.p, (uint4*)ctx->sk0.p,
-                                                                      (int*)ctx->flags.p + 2);   // blindings are canonical
+      k_build_tables<true><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(
+          (const uint4*)ctx->niels.p, (const uint4*)ctx->in_scalars.p, total, (uint32_t)n_terms, (uint4*)ctx->tables.p,
+          (uint4*)ctx->sk0.p, (int*)ctx->flags.p + 2);   // blindings are canonical
       LAUNCH_CHECK(ctx);
     }
-    k_small_msm_ct<<<(unsigned)((M + 63) / 64), 64, 0, st>>>((const uint32_t*)ctx->sk0.p, (const uint4*)ctx->tables.p,
-                                                             (const unsigned long long*)ctx->aux0.p,
-                                                             (const uint32_t*)ctx->multi.p, M, (uint4*)ctx->aux1.p);
+    k_small_msm_ct<true><<<(unsigned)((M + 63) / 64), 64, 0, st>>>((const uint32_t*)ctx->sk0.p, (const uint4*)ctx->tables.p,
+                                                                   (const unsigned long long*)ctx->aux0.p,
+                                                                   (const uint32_t*)ctx->multi.p, M, (uint32_t)n_terms,
+                                                                   (uint4*)ctx->aux1.p);
     LAUNCH_CHECK(ctx);
   }
   // (4) commitments into the transcript, challenge, responses (prover.rs:98-109)
@@ -1172,19 +1173,19 @@ extern "C" int32_t zkp_msm_ct_batched(zkp_ctx* ctx, const uint8_t* scalars, cons
   if (total) {
     ENSURE(ctx, ctx->tables, total * 1024);
     ENSURE(ctx, ctx->sk0, total * 32 + 32);
-    k_build_tables<<<(unsigned)((total + 127) / 128), 128, 0, st>>>((const uint4*)ctx->niels.p,
-                                                                    (const uint4*)ctx->in_scalars.p, total,
-                                                                    (uint4*)ctx->tables.p, (uint4*)ctx->sk0.p,
-                                                                    (int*)ctx->flags.p);
+    k_build_tables<false><<<(unsigned)((total + 127) / 128), 128, 0, st>>>((const uint4*)ctx->niels.p,
+                                                                           (const uint4*)ctx->in_scalars.p, total, 1u,
+                                                                           (uint4*)ctx->tables.p, (uint4*)ctx->sk0.p,
+                                                                           (int*)ctx->flags.p);
     LAUNCH_CHECK(ctx);
   }
   std::vector<uint32_t> order;
   size_order(offsets, M, &order);
   ENSURE(ctx, ctx->multi, M * 4 + 16);
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->multi.p, order.data(), M * 4, cudaMemcpyHostToDevice, st));
-  k_small_msm_ct<<<(unsigned)((M + 63) / 64), 64, 0, st>>>((const uint32_t*)ctx->sk0.p, (const uint4*)ctx->tables.p,
-                                                           (const unsigned long long*)ctx->aux0.p,
-                                                           (const uint32_t*)ctx->multi.p, M, (uint4*)ctx->aux1.p);
+  k_small_msm_ct<false><<<(unsigned)((M + 63) / 64), 64, 0, st>>>((const uint32_t*)ctx->sk0.p, (const uint4*)ctx->tables.p,
+                                                                  (const unsigned long long*)ctx->aux0.p,
+                                                                  (const uint32_t*)ctx->multi.p, M, 1u, (uint4*)ctx->aux1.p);
   LAUNCH_CHECK(ctx);
   int hflags[4];
   CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->aux1.p, M * 32, cudaMemcpyDeviceToHost, st));

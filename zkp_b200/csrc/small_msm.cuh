@@ -136,24 +136,47 @@ __device__ __forceinline__ void store_pniels(uint4* o, const ge_pniels& q) {
   store_fe(o, q.YplusX); store_fe(o + 2, q.YminusX); store_fe(o + 4, q.Z); store_fe(o + 6, q.T2d);
 }
 
-// per term: table of 1P..8P as projective Niels (8 x 128 B) and the biased scalar k + 0x88..8
+// per term: table of 1P..8P as projective Niels (8 x 128 B) and the biased scalar k + 0x88..8.
+// Table layouts (uint4 units; entry e = 1..8, word q = 0..7):
+//   IL = false  tables[t * 64 + 8 (e-1) + q]                                  one contiguous KB per term (any CSR shape)
+//   IL = true   tables[((g * T + r) * 64 + 8 (e-1) + q) * 32 + l]             term t = j * T + r of proof j = 32 g + l:
+//               the 32 proofs of a group are interleaved 16 bytes at a time, so the warp of k_small_msm_ct that works on
+//               the same constraint of 32 consecutive proofs reads every table word with ONE coalesced 512-byte access
+//               (batch proving: all proofs share the statement, T terms each)
+template <bool IL>
+__device__ __forceinline__ size_t ct_table_index(size_t t, uint32_t T) {
+  if (!IL) return t * 64;
+  const size_t j = t / T, r = t % T;
+  return ((j >> 5) * T + r) * 64 * 32 + (j & 31);
+}
+template <bool IL>
 __global__ void __launch_bounds__(128) k_build_tables(const uint4* __restrict__ ext, const uint4* __restrict__ scalars,
-                                                      size_t n, uint4* __restrict__ tables, uint4* __restrict__ biased,
-                                                      int* __restrict__ flags) {
+                                                      size_t n, uint32_t T, uint4* __restrict__ tables,
+                                                      uint4* __restrict__ biased, int* __restrict__ flags) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  const size_t stride = IL ? 32 : 1;
   ge_ext p, m;
   load_ext(p, ext + 8 * i);
   ge_pniels pn, cur;
   ge_to_pniels(pn, p);
-  uint4* tab = tables + i * 64;
-  store_pniels(tab, pn);
+  uint4* tab = tables + ct_table_index<IL>(i, T);
+  auto put = [&](int e, const ge_pniels& q) {   // entry e (0-based)
+    uint4* o = tab + (size_t)(8 * e) * stride;
+    const fe* f[4] = {&q.YplusX, &q.YminusX, &q.Z, &q.T2d};
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      o[(size_t)(2 * c) * stride] = make_uint4(f[c]->v[0], f[c]->v[1], f[c]->v[2], f[c]->v[3]);
+      o[(size_t)(2 * c + 1) * stride] = make_uint4(f[c]->v[4], f[c]->v[5], f[c]->v[6], f[c]->v[7]);
+    }
+  };
+  put(0, pn);
   m = p;
 #pragma unroll 1
   for (int k = 1; k < 8; k++) {
     ge_add_pniels(m, m, pn);
     ge_to_pniels(cur, m);
-    store_pniels(tab + 8 * k, cur);
+    put(k, cur);
   }
   uint32_t s[8], l[8], d[8], bias[8], r[8];
   load_words8(s, scalars + 2 * i);
@@ -167,14 +190,17 @@ __global__ void __launch_bounds__(128) k_build_tables(const uint4* __restrict__ 
   biased[2 * i + 1] = make_uint4(r[4], r[5], r[6], r[7]);
 }
 
+template <bool IL>
 __global__ void __launch_bounds__(64) k_small_msm_ct(const uint32_t* __restrict__ biased, const uint4* __restrict__ tables,
                                                      const unsigned long long* __restrict__ offsets,
-                                                     const uint32_t* __restrict__ order, size_t M,
+                                                     const uint32_t* __restrict__ order, size_t M, uint32_t T,
                                                      uint4* __restrict__ out) {
   size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= M) return;
   const size_t j = order[tid];   // public: MSMs sorted by (public) size so the lanes of a warp do equal work
   const size_t lo = offsets[j], hi = offsets[j + 1];   // public
+  // table of the first term; consecutive terms of one MSM belong to one proof, so their tables are `tstep` apart
+  const size_t tab0 = ct_table_index<IL>(lo, T), tstep = IL ? (size_t)64 * 32 : 64;
   ge_ext acc;
   ge_identity(acc);
 #pragma unroll 1
@@ -192,15 +218,16 @@ __global__ void __launch_bounds__(64) k_small_msm_ct(const uint32_t* __restrict_
       // constant-time lookup: start from the identity, scan all eight entries
       ge_pniels sel;
       fe_one(sel.YplusX); fe_one(sel.YminusX); fe_one(sel.Z); fe_zero(sel.T2d);
-      const uint4* tab = tables + t * 64;
+      const size_t stride = IL ? 32 : 1;
+      const uint4* tab = tables + tab0 + (t - lo) * tstep;   // public: depends on the term index only
 #pragma unroll 1
       for (uint32_t e = 1; e <= 8; e++) {
         uint32_t mask = 0u - (uint32_t)(mag == e);
-        const uint4* ent = tab + 8 * (e - 1);
+        const uint4* ent = tab + (size_t)(8 * (e - 1)) * stride;
         uint32_t* dst = (uint32_t*)&sel;
 #pragma unroll
         for (int q = 0; q < 8; q++) {
-          uint4 v = __ldg(ent + q);
+          uint4 v = __ldg(ent + (size_t)q * stride);
           dst[4 * q + 0] ^= mask & (dst[4 * q + 0] ^ v.x);
           dst[4 * q + 1] ^= mask & (dst[4 * q + 1] ^ v.y);
           dst[4 * q + 2] ^= mask & (dst[4 * q + 2] ^ v.z);

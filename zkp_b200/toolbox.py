@@ -242,16 +242,23 @@ class Statement:
         return enc, com, resp
 
 
-    def prove_many_device(self, eng, transcript_label, secrets, points_limbs, entropy):
+    def prove_many_device(self, eng, transcript_label, secrets, points_limbs, entropy, out=None):
         """prove_many with the per-proof transcript, nonce and response work on the GPU (zkp_prove_batch): the host hashes
-        only the batch-wide transcript prefix.  Byte-identical to prove_many."""
+        only the batch-wide transcript prefix.  Byte-identical to prove_many.  `out` = preallocated (encodings[N][p][32],
+        commitments[N][k][32], responses[N][m][32]) uint8 arrays; inputs and outputs in pinned host memory avoid the
+        staging copies of pageable transfers, which otherwise dominate the call."""
         sec = np.ascontiguousarray(secrets, dtype=np.uint8).reshape(-1, self.m, 32)
         N = sec.shape[0]
         pts = np.ascontiguousarray(points_limbs, dtype=np.uint64).reshape(N, self.p, 20)
         ent = np.ascontiguousarray(entropy, dtype=np.uint8).reshape(N, 32)
-        enc = np.zeros((N, self.p, 32), np.uint8)
-        com = np.zeros((N, self.k, 32), np.uint8)
-        resp = np.zeros((N, self.m, 32), np.uint8)
+        if out is not None:
+            enc, com, resp = out
+            for a, shp in ((enc, (N, self.p, 32)), (com, (N, self.k, 32)), (resp, (N, self.m, 32))):
+                if a.dtype != np.uint8 or a.shape != shp or not a.flags["C_CONTIGUOUS"]:
+                    raise ValueError("out arrays must be C-contiguous uint8 of shapes [N][p][32], [N][k][32], [N][m][32]")
+        else:
+            enc, com, resp = (np.zeros((N, self.p, 32), np.uint8), np.zeros((N, self.k, 32), np.uint8),
+                              np.zeros((N, self.m, 32), np.uint8))
         _raise(_lib().zkph_prove_many_device(eng._ctx, self._h, transcript_label, len(transcript_label), N, _p(sec), _p(pts),
                                              _p(ent), _p(enc), _p(com), _p(resp)))
         return enc, com, resp
