@@ -15,8 +15,9 @@ fold stay on the host by north_star and are outside this MSM-boundary metric.
 
   value     device-resident: scalars+points already in HBM (3.2 GB per GPU > 126 MB L2), CUDA-event timed
   e2e       same verification through the C ABI zkp_batch_verify() from pinned HOST buffers, H2D inside
-  roofline  the dominant kernel (k_decompress) against the HBM copy peak of MEASURED_PEAKS.json, plus the
-            integer-pipe figures that actually bound this path
+  roofline  the dominant kernel (k_ingest2: decompression + digit sort, two launches per step, timed live with CUDA
+            events inside the timed steps) against the HBM copy peak of MEASURED_PEAKS.json, plus the integer-pipe
+            figures that actually bound this path
   cpu_baseline  the C port of the reference's serial u64 CPU algorithms (oracle/_ref) on all host threads
 """
 import argparse
