@@ -175,6 +175,7 @@ def main():
     ap.add_argument("--no-proofs-leg", action="store_true", help="skip the e2e_from_proofs leg (real proofs, device front end)")
     ap.add_argument("--no-overlap", action="store_true", help="tuning: run the digit sort on the compute stream")
     ap.add_argument("--chunk-terms-log2", type=int, default=0, help="tuning: H2D pipeline chunk (terms) for the e2e leg")
+    ap.add_argument("--ingest-variant", type=int, default=-1, help="tuning: occupancy point of k_ingest2 (0..3)")
     ap.add_argument("--no-fused-sort", action="store_true", help="tuning: separate scatter pass instead of the two-phase ingestion")
     ap.add_argument("--sweep", default="", help="tuning: comma list of windows; prints stage times per window and exits")
     args = ap.parse_args()
@@ -267,6 +268,8 @@ def main():
         eng.set_option("overlap", 0)
     if args.no_fused_sort:
         eng.set_option("fused_sort", 0)
+    if args.ingest_variant >= 0:
+        eng.set_option("ingest_variant", args.ingest_variant)
     if args.chunk_terms_log2:
         eng.set_option("chunk_terms", 1 << args.chunk_terms_log2)
     if args.window:

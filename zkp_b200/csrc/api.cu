@@ -55,6 +55,7 @@ struct zkp_ctx {
   // concurrently with decompression (integer-multiply bound); joined before bucket accumulation
   int overlap = 0;   // measured: no gain on B200 (159.2 vs 159.9 ms per step), kept as an option
   int balance = 1;     // size-ordered work items in the bucket accumulation (equal-length items share a warp)
+  int ingest_variant = 2;   // occupancy point of k_ingest2 (kernels.cuh ZKP_INGEST_*)
   int fused_sort = 1;  // histogram and scatter ride under the two halves of the decompression (k_ingest2)
   cudaStream_t sort_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -187,6 +188,9 @@ extern "C" int32_t zkp_ctx_set_option(zkp_ctx* ctx, const char* key, int64_t val
     ctx->overlap = value ? 1 : 0;
   } else if (!strcmp(key, "balance")) {
     ctx->balance = value ? 1 : 0;
+  } else if (!strcmp(key, "ingest_variant")) {
+    if (value < 0 || value > 3) return ZKP_ERR_SIZE;
+    ctx->ingest_variant = (int)value;
   } else if (!strcmp(key, "fused_sort")) {
     ctx->fused_sort = value ? 1 : 0;
   } else if (!strcmp(key, "chunk_terms")) {
@@ -347,10 +351,19 @@ static int32_t launch_ingest2(zkp_ctx* ctx, const msm_plan& pl, const void* d_sc
   size_t threads = p_cnt > sA_cnt ? p_cnt : sA_cnt;
   if (sB_cnt > threads) threads = sB_cnt;
   if (!threads) return ZKP_OK;
-  k_ingest2<MODE><<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(
-      (const uint4*)d_points, p_lo, p_cnt, (uint4*)ctx->niels.p, (const uint4*)d_scalars, sA_lo, sA_cnt, sB_lo, sB_cnt, n,
-      pl.c, pl.W, pl.B, MODE == 0 ? (uint32_t*)ctx->hist.p : (uint32_t*)ctx->cursor.p, (uint32_t*)ctx->sorted.p,
-      (int*)ctx->flags.p);
+#define ZKP_LAUNCH_INGEST(VAR)                                                                                              \
+  k_ingest2<MODE, VAR><<<(unsigned)((threads + ZKP_INGEST_THREADS(VAR) - 1) / ZKP_INGEST_THREADS(VAR)),                     \
+                         ZKP_INGEST_THREADS(VAR), 0, ctx->stream>>>(                                                        \
+      (const uint4*)d_points, p_lo, p_cnt, (uint4*)ctx->niels.p, (const uint4*)d_scalars, sA_lo, sA_cnt, sB_lo, sB_cnt, n,  \
+      pl.c, pl.W, pl.B, MODE == 0 ? (uint32_t*)ctx->hist.p : (uint32_t*)ctx->cursor.p, (uint32_t*)ctx->sorted.p,            \
+      (int*)ctx->flags.p)
+  switch (ctx->ingest_variant) {
+    case 1: ZKP_LAUNCH_INGEST(1); break;
+    case 2: ZKP_LAUNCH_INGEST(2); break;
+    case 3: ZKP_LAUNCH_INGEST(3); break;
+    default: ZKP_LAUNCH_INGEST(0); break;
+  }
+#undef ZKP_LAUNCH_INGEST
   LAUNCH_CHECK(ctx);
   return ZKP_OK;
 }

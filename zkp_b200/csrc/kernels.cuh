@@ -235,8 +235,13 @@ __device__ __forceinline__ void ingest_digits(const uint4* __restrict__ scalars,
   }
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(256) k_ingest2(const uint4* __restrict__ enc, size_t p_lo, size_t p_cnt,
+// VAR picks the occupancy point (block size, minimum resident blocks): 0 = 256 threads, 106 registers, 16 warps/SM;
+// 1 = (128, 5): <= 96 registers, 20 warps/SM; 2 = (256, 3) and 3 = (128, 6): <= 80 registers, 24 warps/SM.
+#define ZKP_INGEST_THREADS(VAR) ((VAR) == 0 || (VAR) == 2 ? 256 : 128)
+#define ZKP_INGEST_MINBLK(VAR) ((VAR) == 0 ? 1 : (VAR) == 1 ? 5 : (VAR) == 2 ? 3 : 6)
+template <int MODE, int VAR>
+__global__ void __launch_bounds__(ZKP_INGEST_THREADS(VAR), ZKP_INGEST_MINBLK(VAR))
+    k_ingest2(const uint4* __restrict__ enc, size_t p_lo, size_t p_cnt,
                                                  uint4* __restrict__ niels, const uint4* __restrict__ scalars, size_t sA_lo,
                                                  size_t sA_cnt, size_t sB_lo, size_t sB_cnt, size_t n, int c, int W,
                                                  uint32_t B, uint32_t* __restrict__ counters,
