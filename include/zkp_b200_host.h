@@ -74,6 +74,23 @@ int32_t zkph_prove_many_device(zkp_ctx* ctx, const zkph_statement* st, const uin
                                size_t N, const uint8_t* secrets, const uint64_t* points, const uint8_t* entropy,
                                uint8_t* encodings, uint8_t* commitments, uint8_t* responses);
 
+/* Wire format of /root/reference/src/proofs.rs as the reference's tests serialize it (bincode 1.x defaults,
+ * tests/zkp.rs:53-54, :96-97):  CompactProof = challenge[32] | u64 m | responses[m][32];
+ * BatchableProof = u64 k | commitments[k][32] | u64 m | responses[m][32]  (little-endian; scalars must be canonical).
+ * Return codes: 0 ok, 1 VerificationFailure, 2 BatchSizeMismatch, ZKPH_MALFORMED for input bincode would refuse.   */
+#define ZKPH_MALFORMED 4
+size_t zkph_compact_proof_size(size_t m);
+size_t zkph_batchable_proof_size(size_t k, size_t m);
+int32_t zkph_compact_proof_serialize(const uint8_t* challenge, const uint8_t* responses, size_t m, uint8_t* out);
+int32_t zkph_batchable_proof_serialize(const uint8_t* commitments, size_t k, const uint8_t* responses, size_t m,
+                                       uint8_t* out);
+int32_t zkph_compact_proof_parse(const uint8_t* buf, size_t len, size_t m_cap, uint8_t* challenge, uint8_t* responses,
+                                 size_t* m_out, size_t* consumed);
+/* N concatenated serialized BatchableProofs of one statement -> the SoA arrays of zkph_batch_verify(_device):
+ * commitments[N][k][32], responses[N][m][32].  first_bad (optional) = index of the offending proof.             */
+int32_t zkph_batchable_proofs_parse(const uint8_t* buf, size_t len, size_t N, size_t k, size_t m, uint8_t* commitments,
+                                    uint8_t* responses, int32_t threads, int64_t* first_bad);
+
 /* merlin::Transcript handles, for callers that drive the transcript themselves the way the reference's API takes
  * `&mut Transcript` (e.g. /root/reference/tests/sig_and_vrf_example.rs:86-125: messages are appended before proving).
  * The *_t entry points below mutate the handle exactly like the reference mutates its transcript.               */

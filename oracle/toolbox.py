@@ -377,3 +377,42 @@ def dleq_statement(cs, x, A, B, G, H):
     """benches/dleq.rs:37-47 (hand-written constraint-API form)."""
     cs.constrain(A, [(x, G)])
     cs.constrain(B, [(x, H)])
+
+
+# ---- wire format of /root/reference/src/proofs.rs:14-32 under bincode 1.x defaults (tests/zkp.rs:53-54, :96-97) ---------
+# little-endian fixed-width integers; Vec<T> = u64 length + items; Scalar / CompressedRistretto = 32 raw bytes
+# (curve25519-dalek 2.x serde impls [ext]; Scalar deserialisation rejects non-canonical encodings).
+def serialize_compact(challenge, responses):
+    return S.to_bytes(challenge) + len(responses).to_bytes(8, "little") + b"".join(S.to_bytes(r) for r in responses)
+
+
+def serialize_batchable(proof):
+    return (len(proof.commitments).to_bytes(8, "little") + b"".join(proof.commitments)
+            + len(proof.responses).to_bytes(8, "little") + b"".join(S.to_bytes(r) for r in proof.responses))
+
+
+def _scalar_canonical(b):
+    v = int.from_bytes(b, "little")
+    if v >= R.L:
+        raise ValueError("scalar was not canonically encoded")
+    return v
+
+
+def parse_batchable(buf, off=0):
+    """-> (BatchableProof, next offset); raises ValueError like bincode::deserialize would."""
+    def take(n):
+        nonlocal off
+        if off + n > len(buf):
+            raise ValueError("unexpected end of input")
+        b = buf[off:off + n]
+        off += n
+        return b
+    k = int.from_bytes(take(8), "little")
+    if k > (len(buf) - off) // 32:
+        raise ValueError("length prefix exceeds input")
+    coms = [bytes(take(32)) for _ in range(k)]
+    m = int.from_bytes(take(8), "little")
+    if m > (len(buf) - off) // 32:
+        raise ValueError("length prefix exceeds input")
+    resp = [_scalar_canonical(take(32)) for _ in range(m)]
+    return BatchableProof(coms, resp), off

@@ -88,6 +88,46 @@ def _cmz_instances(N, seed):
     return secs, ptss
 
 
+def test_serialized_proofs_round_trip_like_the_reference_tests(engine):
+    """/root/reference/tests/zkp.rs:31-112 and :115-175 with the wire step they contain: prove, `bincode::serialize`,
+    `deserialize`, verify -- compact, batchable, and a batch of serialized proofs parsed straight into the SoA arrays of
+    the batch verifier (host path and device front end)."""
+    st = PT.dleq_statement()
+    x, pts = dleq_instance()
+    plimbs = np.array([limbs(pts[n]) for n in st.points], dtype=np.uint64)
+    (chal, resp), enc = st.prove_compact(engine, b"DLEQTest", sbytes([x]), plimbs, b"s1")
+    wire = PT.serialize_compact(np.frombuffer(chal, np.uint8), resp)
+    assert len(wire) == 32 + 8 + 32                                     # m + 1 32-byte elements + the Vec length
+    c2, r2 = PT.parse_compact(wire, st.m)
+    st.verify_compact(engine, (bytes(c2), r2), b"DLEQTest", enc)
+    (com, resp), enc = st.prove_batchable(engine, b"DLEQTest", sbytes([x]), plimbs, b"s2")
+    wire = PT.serialize_batchable(com, resp)
+    assert len(wire) == 8 + 32 * 2 + 8 + 32
+    cm, rs = PT.parse_batchable_many(wire, 1, st.k, st.m)
+    st.verify_batchable(engine, (cm[0], rs[0]), b"DLEQTest", enc, b"w")
+    # a stream of serialized CMZ proofs -> batch verification
+    cst = PT.cmz10_statement()
+    N = 6
+    secs, ptss = _cmz_instances(N, b"cmz-wire")
+    sec_arr = np.stack([sbytes([s_[n] for n in cst.secrets]) for s_ in secs])
+    pts_arr = np.array([[limbs(p[n]) for n in cst.points] for p in ptss], dtype=np.uint64)
+    entropy = np.frombuffer(OT.SeededRng(b"entropy-wire").bytes(32 * N), dtype=np.uint8).reshape(N, 32)
+    enc, com, resp = cst.prove_many_device(engine, b"CMZ", sec_arr, pts_arr, entropy)
+    stream = b"".join(PT.serialize_batchable(com[j], resp[j]) for j in range(N))
+    assert len(stream) == N * (8 + 32 * 11 + 8 + 32 * 21)
+    com2, resp2 = PT.parse_batchable_many(stream, N, cst.k, cst.m, threads=2)
+    assert (com2 == com).all() and (resp2 == resp).all()
+    ni = len(cst.instance)
+    inst = np.ascontiguousarray(enc[:, :ni].transpose(1, 0, 2))
+    cst.batch_verify(engine, com2, resp2, b"CMZ", inst, enc[0, ni:], b"rho", threads=2)
+    cst.batch_verify_device(engine, com2, resp2, b"CMZ", inst, enc[0, ni:], bytes(range(32)))
+    tampered = bytearray(stream)
+    tampered[3 * (8 + 32 * 11 + 8 + 32 * 21) + 8 + 5] ^= 1                  # a commitment byte of proof 3
+    com3, resp3 = PT.parse_batchable_many(bytes(tampered), N, cst.k, cst.m)
+    with pytest.raises(PT.VerificationFailure):
+        cst.batch_verify_device(engine, com3, resp3, b"CMZ", inst, enc[0, ni:], bytes(range(32)))
+
+
 def test_cmz_prove_many_and_batch_verify_match_oracle(engine):
     st, ost = PT.cmz10_statement(), OT.CMZ10
     N = 5

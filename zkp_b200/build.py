@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libzkp_b200.so")
-SOURCES = ["api.cu", "host/merlin.cpp", "host/scalar.cpp", "host/toolbox.cpp", "host/host_api.cpp"]
+SOURCES = ["api.cu", "host/merlin.cpp", "host/scalar.cpp", "host/toolbox.cpp", "host/host_api.cpp", "host/wire.cpp"]
 
 
 def _headers():

@@ -25,6 +25,10 @@ class BatchSizeMismatch(ProofError):
     pass
 
 
+class MalformedProof(ValueError):
+    """Input the reference's `bincode::deserialize` would refuse (truncated, trailing bytes, non-canonical scalar)."""
+
+
 def _raise(rc):
     if rc == 0:
         return
@@ -32,6 +36,8 @@ def _raise(rc):
         raise VerificationFailure()
     if rc == 2:
         raise BatchSizeMismatch()
+    if rc == 4:
+        raise MalformedProof()
     raise RuntimeError("zkp_b200 host/engine failure (code %d)" % rc)
 
 
@@ -53,6 +59,14 @@ def _lib():
         lib.zkph_prove_many.argtypes = [vp, vp, vp, sz, sz, vp, vp, vp, i32, vp, vp, vp]
         lib.zkph_batch_verify_device.argtypes = [vp, vp, vp, sz, sz, vp, vp, vp, vp, vp, vp, vp]
         lib.zkph_prove_many_device.argtypes = [vp, vp, vp, sz, sz, vp, vp, vp, vp, vp, vp]
+        lib.zkph_compact_proof_size.restype = sz
+        lib.zkph_compact_proof_size.argtypes = [sz]
+        lib.zkph_batchable_proof_size.restype = sz
+        lib.zkph_batchable_proof_size.argtypes = [sz, sz]
+        lib.zkph_compact_proof_serialize.argtypes = [vp, vp, sz, vp]
+        lib.zkph_batchable_proof_serialize.argtypes = [vp, sz, vp, sz, vp]
+        lib.zkph_compact_proof_parse.argtypes = [vp, sz, sz, vp, vp, vp, vp]
+        lib.zkph_batchable_proofs_parse.argtypes = [vp, sz, sz, sz, sz, vp, vp, i32, vp]
         lib.zkph_transcript_new.restype = vp
         lib.zkph_transcript_new.argtypes = [vp, sz]
         lib.zkph_transcript_clone.restype = vp
@@ -262,6 +276,46 @@ class Statement:
         _raise(_lib().zkph_prove_many_device(eng._ctx, self._h, transcript_label, len(transcript_label), N, _p(sec), _p(pts),
                                              _p(ent), _p(enc), _p(com), _p(resp)))
         return enc, com, resp
+
+
+# ---- wire format of src/proofs.rs (bincode 1.x defaults, as /root/reference/tests/zkp.rs:53-54, :96-97 use it) --------
+def serialize_compact(challenge, responses):
+    r = np.ascontiguousarray(responses, dtype=np.uint8).reshape(-1, 32)
+    c = np.ascontiguousarray(challenge, dtype=np.uint8).reshape(32)
+    out = np.zeros(int(_lib().zkph_compact_proof_size(r.shape[0])), np.uint8)
+    _raise(_lib().zkph_compact_proof_serialize(_p(c), _p(r), r.shape[0], _p(out)))
+    return out.tobytes()
+
+
+def parse_compact(buf, m):
+    """-> (challenge[32], responses[m][32]); VerificationFailure if the proof carries another number of responses."""
+    b = np.frombuffer(bytes(buf), dtype=np.uint8)
+    c, r = np.zeros(32, np.uint8), np.zeros((m, 32), np.uint8)
+    m_out, used = ctypes.c_size_t(0), ctypes.c_size_t(0)
+    _raise(_lib().zkph_compact_proof_parse(_p(b), b.size, m, _p(c), _p(r), ctypes.byref(m_out), ctypes.byref(used)))
+    if m_out.value != m:
+        raise VerificationFailure()
+    if used.value != b.size:
+        raise MalformedProof()
+    return c, r
+
+
+def serialize_batchable(commitments, responses):
+    k = np.ascontiguousarray(commitments, dtype=np.uint8).reshape(-1, 32)
+    r = np.ascontiguousarray(responses, dtype=np.uint8).reshape(-1, 32)
+    out = np.zeros(int(_lib().zkph_batchable_proof_size(k.shape[0], r.shape[0])), np.uint8)
+    _raise(_lib().zkph_batchable_proof_serialize(_p(k), k.shape[0], _p(r), r.shape[0], _p(out)))
+    return out.tobytes()
+
+
+def parse_batchable_many(buf, N, k, m, threads=0):
+    """N concatenated serialized BatchableProofs of one statement -> (commitments[N][k][32], responses[N][m][32]), the
+    arrays batch_verify / batch_verify_device take."""
+    b = np.frombuffer(buf, dtype=np.uint8) if not isinstance(buf, np.ndarray) else buf
+    com, resp = np.zeros((N, k, 32), np.uint8), np.zeros((N, m, 32), np.uint8)
+    bad = ctypes.c_int64(-1)
+    _raise(_lib().zkph_batchable_proofs_parse(_p(b), b.size, N, k, m, _p(com), _p(resp), int(threads), ctypes.byref(bad)))
+    return com, resp
 
 
 def dleq_statement():
