@@ -59,6 +59,10 @@ void parallel_for(size_t n, int threads, const std::function<void(size_t, size_t
 
 class Prover {
  public:
+  // the associated types of the SchnorrCS trait (toolbox/mod.rs:86-98), so generic statements can be written once
+  typedef int ScalarVar;
+  typedef int PointVar;
+  typedef LinComb LC;
   Prover(zkp_ctx* ctx, const std::string& proof_label, Transcript* transcript);
   int allocate_scalar(const std::string& label, const Scalar& assignment);
   // compresses on the device (toolbox/mod.rs:180) and returns the encoding like the reference does
@@ -81,6 +85,9 @@ class Prover {
 
 class Verifier {
  public:
+  typedef int ScalarVar;
+  typedef int PointVar;
+  typedef LinComb LC;
   Verifier(zkp_ctx* ctx, const std::string& proof_label, Transcript* transcript);
   int allocate_scalar(const std::string& label);
   int allocate_point(const std::string& label, const Enc& assignment, ProofError* err);
@@ -102,6 +109,9 @@ typedef std::vector<std::pair<int, BatchPointVar>> BatchLinComb;
 
 class BatchVerifier {
  public:
+  typedef int ScalarVar;
+  typedef BatchPointVar PointVar;
+  typedef BatchLinComb LC;
   // transcripts.size() must equal batch_size, else *err = BatchSizeMismatch (batch_verifier.rs:72-74)
   // `threads` host threads work on the per-proof transcripts (0 = all cores); the reference is single-threaded
   BatchVerifier(zkp_ctx* ctx, const std::string& proof_label, size_t batch_size, std::vector<Transcript>* transcripts,
