@@ -147,6 +147,30 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this rank (CPU affinity, hence first-touch placement of its pinned host buffers) to the NUMA node its GPU hangs
+    off: with 8 ranks pulling 3.2 GB per step each from one host, cross-socket reads are what limits the end-to-end leg.
+    Plumbing only; silently does nothing where sysfs does not tell."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return {"numa_node": node, "cpus": len(cpus)}
+    except Exception:
+        pass
+    return None
+
+
 def cpu_baseline(sc_rows, pt_enc, sample_proofs, threads, steps=1):
     """The C port of the reference's CPU path (oracle/_ref, kind "port") on a bounded sample of the SAME
     workload: the first `sample_proofs` proofs' columns of every row, i.e. one MSM of 24*sample terms."""
@@ -176,6 +200,7 @@ def main():
     ap.add_argument("--no-overlap", action="store_true", help="tuning: run the digit sort on the compute stream")
     ap.add_argument("--chunk-terms-log2", type=int, default=0, help="tuning: H2D pipeline chunk (terms) for the e2e leg")
     ap.add_argument("--ingest-variant", type=int, default=-1, help="tuning: occupancy point of k_ingest2 (0..3)")
+    ap.add_argument("--no-numa-bind", action="store_true", help="tuning: do not pin ranks to their GPU's NUMA node")
     ap.add_argument("--no-fused-sort", action="store_true", help="tuning: separate scatter pass instead of the two-phase ingestion")
     ap.add_argument("--sweep", default="", help="tuning: comma list of windows; prints stage times per window and exits")
     args = ap.parse_args()
@@ -227,6 +252,8 @@ def main():
     from zkp_b200 import Engine
 
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 and not args.no_numa_bind else None
+    host_threads = len(os.sched_getaffinity(0))     # what this rank may actually use
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     eng = Engine(local_rank)
@@ -445,7 +472,8 @@ def main():
         sample = 1 << args.cpu_sample_log2
         sc_rows = sc.view(np.uint8).reshape(ROWS, N, 32)
         pt_rows = inst_points.numpy().reshape(ROWS, N, 32)
-        cpu_v, cpu_t = cpu_baseline(sc_rows, pt_rows, sample, host_threads)
+        # the CPU baseline is taken at N = 1 only (the other ranks would compete for the same host cores)
+        cpu_v, cpu_t = cpu_baseline(sc_rows, pt_rows, sample, host_threads) if world == 1 else (None, 0.0)
         line = {"metric": "proofs verified/sec (batch) CMZ13 10-attr credential", "value": value, "unit": "proofs/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 (8x32-bit saturated limbs, 64-bit products)",
@@ -454,11 +482,13 @@ def main():
                         "d2h_bytes_per_step": 48, "ms_per_step": e2e_ms / args.steps,
                         "api": "zkp_batch_verify (C ABI), pinned host buffers"},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
-                "cpu_baseline": {"value": cpu_v, "unit": "proofs/s", "cores": host_threads, "kind": "port",
-                                 "sample": "first %d proofs of this workload (one %d-term MSM), C port of dalek's "
-                                           "serial u64 backend sharded over %d threads, %.2f s"
-                                           % (sample, ROWS * sample, host_threads, cpu_t)},
-                "accept_bits": accept_bitmap, "setup_s": setup_s}
+                "cpu_baseline": ({"value": cpu_v, "unit": "proofs/s", "cores": host_threads, "kind": "port",
+                                  "sample": "first %d proofs of this workload (one %d-term MSM), C port of dalek's "
+                                            "serial u64 backend sharded over %d threads, %.2f s"
+                                            % (sample, ROWS * sample, host_threads, cpu_t)} if world == 1 else
+                                 {"value": None, "unit": "proofs/s", "cores": 0, "kind": "port",
+                                  "sample": "taken at N = 1 only (bench.py --gpus 1)"}),
+                "accept_bits": accept_bitmap, "setup_s": setup_s, "numa_binding_rank0": numa}
         if proofs_leg:
             line["e2e_from_proofs"] = {
                 "value": world * N / (proofs_ms * 1e-3), "unit": "proofs/s", "ms_per_step": proofs_ms,

@@ -298,6 +298,65 @@ def test_prove_many_device_front_end_matches_host_and_oracle(engine):
     assert all((x == y).all() for x, y in zip(a, b))
 
 
+def test_compiled_transcript_script_equals_bytewise_strobe(engine):
+    """k_bv_prepare2 (host-compiled STROBE framing, block-wise absorb) against k_bv_prepare (byte-wise STROBE on the
+    device) and the oracle: identical MSM inputs for CMZ, DLEQ and for statements whose label lengths walk the per-proof
+    values across every alignment and block boundary of the 166-byte rate (values split over two blocks, headers ending
+    exactly on a boundary)."""
+    G = R.BASEPOINT
+    seed = bytes(range(7, 39))
+    def both(st, N, tl, com, resp, inst, comm):
+        outs = []
+        for compiled in (1, 0):
+            engine.set_option("bv_compiled", compiled)
+            try:
+                outs.append(st.batch_verify_device(engine, com, resp, tl, inst, comm, seed, want_msm_inputs=True))
+            finally:
+                engine.set_option("bv_compiled", 1)
+        assert (outs[0][0] == outs[1][0]).all() and (outs[0][1] == outs[1][1]).all()
+        return outs[0]
+    # CMZ
+    st, ost = PT.cmz10_statement(), OT.CMZ10
+    N = 5
+    secs, ptss = _cmz_instances(N, b"cmz-script")
+    sec_arr = np.stack([sbytes([s_[n] for n in st.secrets]) for s_ in secs])
+    pts_arr = np.array([[limbs(p[n]) for n in st.points] for p in ptss], dtype=np.uint64)
+    entropy = np.frombuffer(OT.SeededRng(b"entropy-script").bytes(32 * N), dtype=np.uint8).reshape(N, 32)
+    enc, com, resp = st.prove_many_device(engine, b"CMZ", sec_arr, pts_arr, entropy)
+    ni = len(st.instance)
+    co, po = both(st, N, b"CMZ", com, resp, np.ascontiguousarray(enc[:, :ni].transpose(1, 0, 2)), enc[0, ni:])
+    oproofs = [OT.BatchableProof([bytes(c) for c in com[j]], [int.from_bytes(bytes(r), "little") for r in resp[j]])
+               for j in range(N)]
+    oencs = {n: [bytes(enc[j, i]) for j in range(N)] for i, n in enumerate(st.instance)}
+    for i, n in enumerate(st.common):
+        oencs[n] = bytes(enc[0, ni + i])
+    bv = ost.build_batch_verifier(N, [OM.Transcript(b"CMZ") for _ in range(N)], oencs)
+    oscal, opts = bv.batch_coeffs(oproofs, OT.PerProofRng(seed))
+    assert [bytes(p) for p in po] == opts and [bytes(c) for c in co] == [S.to_bytes(s_) for s_ in oscal]
+    # label lengths 1 .. 60 and transcript labels of several lengths: every alignment of the values in the rate block
+    x = 987654321
+    A = R.pt_mul(x, G)
+    for L in list(range(1, 61, 3)) + [166, 167, 200]:
+        names = ["A" * L, "G" + "g" * (L // 2), "Q" + "q" * (L % 7)]
+        pk = PT.Statement("pk", "PK proof " + "p" * (L % 11), ["x"], [names[0]], [names[1], names[2]],
+                          [(names[0], [("x", names[1])]), (names[2], [("x", names[1])])])
+        opk = OT.Statement("pk", "PK proof " + "p" * (L % 11), ["x"], [names[0]], [names[1], names[2]],
+                           [(names[0], [("x", names[1])]), (names[2], [("x", names[1])])])
+        Np = 3
+        pts = np.array([[limbs(A), limbs(G), limbs(A)] for _ in range(Np)], dtype=np.uint64)
+        ent = np.frombuffer(OT.SeededRng(b"pk-script%d" % L).bytes(32 * Np), dtype=np.uint8).reshape(Np, 32)
+        tl = b"T" * (1 + L % 5)
+        e2, c2, r2 = pk.prove_many_device(engine, tl, np.stack([sbytes([x])] * Np), pts, ent)
+        inst = np.ascontiguousarray(e2[:, :1].transpose(1, 0, 2))
+        co, po = both(pk, Np, tl, c2, r2, inst, e2[0, 1:])
+        oproofs = [OT.BatchableProof([bytes(c) for c in c2[j]], [int.from_bytes(bytes(r), "little") for r in r2[j]])
+                   for j in range(Np)]
+        oencs = {names[0]: [bytes(e) for e in e2[:, 0]], names[1]: bytes(e2[0, 1]), names[2]: bytes(e2[0, 2])}
+        bv = opk.build_batch_verifier(Np, [OM.Transcript(tl) for _ in range(Np)], oencs)
+        oscal, opts = bv.batch_coeffs(oproofs, OT.PerProofRng(seed))
+        assert [bytes(p) for p in po] == opts and [bytes(c) for c in co] == [S.to_bytes(s_) for s_ in oscal], L
+
+
 def test_device_front_end_edge_shapes(engine):
     """N = 1, an empty batch, and a statement whose constraint has a STATIC lhs (static_coeffs path of
     batch_verifier.rs:187-189) through both the host mirror and the device front end."""

@@ -55,6 +55,7 @@ struct zkp_ctx {
   // concurrently with decompression (integer-multiply bound); joined before bucket accumulation
   int overlap = 0;   // measured: no gain on B200 (159.2 vs 159.9 ms per step), kept as an option
   int balance = 1;     // size-ordered work items in the bucket accumulation (equal-length items share a warp)
+  int bv_compiled = 1;      // batch-verification front end: host-compiled transcript script (k_bv_prepare2)
   int ingest_variant = 2;   // occupancy point of k_ingest2 (kernels.cuh ZKP_INGEST_*)
   int fused_sort = 1;  // histogram and scatter ride under the two halves of the decompression (k_ingest2)
   cudaStream_t sort_stream = nullptr;
@@ -188,6 +189,8 @@ extern "C" int32_t zkp_ctx_set_option(zkp_ctx* ctx, const char* key, int64_t val
     ctx->overlap = value ? 1 : 0;
   } else if (!strcmp(key, "balance")) {
     ctx->balance = value ? 1 : 0;
+  } else if (!strcmp(key, "bv_compiled")) {
+    ctx->bv_compiled = value ? 1 : 0;
   } else if (!strcmp(key, "ingest_variant")) {
     if (value < 0 || value > 3) return ZKP_ERR_SIZE;
     ctx->ingest_variant = (int)value;
@@ -686,6 +689,79 @@ extern "C" int32_t zkp_batch_verify(zkp_ctx* ctx, const uint8_t* static_coeffs, 
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Symbolic STROBE-128 over the per-proof transcript script of a batch (bv_kernels.cuh k_bv_prepare2): records the
+// constant bytes of every rate block and where the per-proof 32-byte values land.  Mirrors merlin 2.0 strobe.rs [ext]
+// exactly as csrc/hash.cuh and host/merlin.cpp do (begin_op framing, run_f padding, forced run_f of C-flagged ops).
+// ---------------------------------------------------------------------------------------------------------
+struct bv_script {
+  static const uint32_t R = 166;
+  uint32_t pos, pos_begin;
+  std::vector<uint8_t> cur;                 // 168 bytes of the block under construction
+  std::vector<uint64_t> tmpl;               // [nblocks][21]
+  std::vector<uint32_t> seg_start;          // [nblocks + 1]
+  std::vector<bv_seg> segs;
+  bv_script(uint32_t p, uint32_t pb) : pos(p), pos_begin(pb), cur(168, 0), seg_start(1, 0) {}
+  void run_f() {
+    cur[pos] ^= (uint8_t)pos_begin;
+    cur[pos + 1] ^= 0x04;
+    cur[R + 1] ^= 0x80;
+    for (int l = 0; l < 21; l++) {
+      uint64_t v = 0;
+      for (int b = 7; b >= 0; b--) v = (v << 8) | cur[8 * l + b];
+      tmpl.push_back(v);
+    }
+    seg_start.push_back((uint32_t)segs.size());
+    std::fill(cur.begin(), cur.end(), 0);
+    pos = 0;
+    pos_begin = 0;
+  }
+  void absorb(const uint8_t* d, size_t n) {
+    for (size_t i = 0; i < n; i++) {
+      cur[pos] ^= d[i];
+      if (++pos == R) run_f();
+    }
+  }
+  void absorb_value(uint32_t kind, uint32_t idx) {   // 32 per-proof bytes, split at block boundaries
+    uint32_t done = 0;
+    while (done < 32) {
+      const uint32_t room = R - pos, take = 32 - done < room ? 32 - done : room;
+      bv_seg sg;
+      memset(&sg, 0, sizeof sg);
+      sg.kind = kind; sg.idx = idx; sg.src_off = done; sg.len = take; sg.shift = (int32_t)pos - (int32_t)done;
+      segs.push_back(sg);
+      pos += take;
+      done += take;
+      if (pos == R) run_f();
+    }
+  }
+  void begin_op(uint32_t flags, bool more) {
+    if (more) return;
+    uint8_t hdr[2] = {(uint8_t)pos_begin, (uint8_t)flags};
+    pos_begin = pos + 1;
+    absorb(hdr, 2);
+    if ((flags & (ZKP_FLAG_C | ZKP_FLAG_K)) && pos != 0) run_f();
+  }
+  void meta_ad(const uint8_t* d, size_t n, bool more) { begin_op(ZKP_FLAG_M | ZKP_FLAG_A, more); absorb(d, n); }
+  void append_header(const char* label, const uint8_t* l2, size_t l2len) {   // append_message(label, <l2len bytes>) minus the data
+    uint8_t l4[4] = {(uint8_t)l2len, (uint8_t)(l2len >> 8), (uint8_t)(l2len >> 16), (uint8_t)(l2len >> 24)};
+    (void)l2;
+    meta_ad((const uint8_t*)label, strlen(label), false);
+    meta_ad(l4, 4, true);
+    begin_op(ZKP_FLAG_A, false);
+  }
+  void append_const(const char* label, const uint8_t* msg, size_t n) { append_header(label, msg, n); absorb(msg, n); }
+  void append_value(const char* label, uint32_t kind, uint32_t idx) { append_header(label, nullptr, 32); absorb_value(kind, idx); }
+  void challenge(const char* label, uint32_t n) {   // up to the forced run_f of prf; the squeeze reads the fresh state
+    uint8_t l4[4] = {(uint8_t)n, (uint8_t)(n >> 8), (uint8_t)(n >> 16), (uint8_t)(n >> 24)};
+    meta_ad((const uint8_t*)label, strlen(label), false);
+    meta_ad(l4, 4, true);
+    // the two header bytes leave pos != 0 (forced run_f) or end exactly on the block boundary (run_f inside absorb):
+    // either way the block is closed here and the squeeze starts at byte 0 of the permuted state
+    begin_op(ZKP_FLAG_I | ZKP_FLAG_A | ZKP_FLAG_C, false);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------
 // batch verification from proofs: transcripts, challenges, weights and coefficient fold on the device
 // ---------------------------------------------------------------------------------------------------------
 extern "C" int32_t zkp_batch_verify_proofs(zkp_ctx* ctx, const zkp_statement_desc* sd, const uint32_t* prefix_state,
@@ -739,13 +815,42 @@ extern "C" int32_t zkp_batch_verify_proofs(zkp_ctx* ctx, const zkp_statement_des
     tkind[q] = pnt >= ni;
     tidx[q] = pnt >= ni ? pnt - ni : pnt;
   }
-  // one small device blob: prefix(53 w) | rho_seed(32 B) | pool | ops | int arrays
+  // the compiled transcript script (k_bv_prepare2): allocation order instance, static, then the commitments
+  bv_script script(prefix_state[50], prefix_state[51]);
+  {
+    const char* q = sd->labels;
+    std::vector<std::string> names;
+    for (int i = 0; i < ni + nc; i++) {
+      names.push_back(std::string(q));
+      q += names.back().size() + 1;
+    }
+    for (int i = 0; i < ni; i++) {
+      script.append_const("ptvar", (const uint8_t*)names[i].data(), names[i].size());
+      script.append_value("val", 0u, (uint32_t)i);
+    }
+    for (int i = 0; i < nc; i++) {
+      script.append_const("ptvar", (const uint8_t*)names[ni + i].data(), names[ni + i].size());
+      script.append_const("val", common_enc + 32 * (size_t)i, 32);
+    }
+    for (int c = 0; c < k; c++) {
+      const std::string& nm = names[sd->lhs[c]];
+      script.append_const("blindcom", (const uint8_t*)nm.data(), nm.size());
+      script.append_value("val", 2u, (uint32_t)c);
+    }
+    script.challenge("chal", 64);
+  }
+  const int script_blocks = (int)(script.tmpl.size() / 21);
+  // one small device blob: prefix(53 w) | rho_seed(32 B) | pool | ops | int arrays | block templates | segments
   auto pad16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
   const size_t o_prefix = 0, o_seed = pad16(53 * 4), o_pool = o_seed + 32, o_ops = pad16(o_pool + pool.size()),
                o_lk = pad16(o_ops + ops.size() * sizeof(bv_op)), o_li = pad16(o_lk + k * 4), o_co = pad16(o_li + k * 4),
                o_ts = pad16(o_co + (k + 1) * 4), o_tk = pad16(o_ts + n_terms * 4), o_ti = pad16(o_tk + n_terms * 4),
-               blob_sz = pad16(o_ti + n_terms * 4) + 16;
+               o_tm = pad16(o_ti + n_terms * 4), o_ss = pad16(o_tm + script.tmpl.size() * 8),
+               o_sg = pad16(o_ss + script.seg_start.size() * 4), blob_sz = pad16(o_sg + script.segs.size() * sizeof(bv_seg)) + 16;
   std::vector<uint8_t> blob(blob_sz, 0);
+  if (!script.tmpl.empty()) memcpy(&blob[o_tm], script.tmpl.data(), script.tmpl.size() * 8);
+  memcpy(&blob[o_ss], script.seg_start.data(), script.seg_start.size() * 4);
+  if (!script.segs.empty()) memcpy(&blob[o_sg], script.segs.data(), script.segs.size() * sizeof(bv_seg));
   memcpy(&blob[o_prefix], prefix_state, 53 * 4);
   memcpy(&blob[o_seed], rho_seed, 32);
   if (!pool.empty()) memcpy(&blob[o_pool], pool.data(), pool.size());
@@ -828,9 +933,16 @@ extern "C" int32_t zkp_batch_verify_proofs(zkp_ctx* ctx, const zkp_statement_des
     CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->chunk_ev[cidx], 0));
     if (pl.sort != st) CUDA_TRY(ctx, cudaStreamWaitEvent(pl.sort, ctx->chunk_ev[cidx], 0));
     const unsigned nb = (unsigned)((cnt + 127) / 128);
-    k_bv_prepare<<<nb, 128, 0, st>>>(d, (const uint32_t*)(dm + o_prefix), N, dpts + (size_t)nc * 32, dpts,
-                                     (const uint8_t*)ctx->bv_com.p, (const uint8_t*)ctx->bv_resp.p, dm + o_seed, dsc, dpts,
-                                     (uint8_t*)ctx->bv_part.p, nullptr, (int*)ctx->flags.p, j0, cnt, block_base);
+    if (ctx->bv_compiled)
+      k_bv_prepare2<<<nb, 128, 0, st>>>(d, (const uint32_t*)(dm + o_prefix), N, dpts + (size_t)nc * 32,
+                                        (const uint8_t*)ctx->bv_com.p, (const uint8_t*)ctx->bv_resp.p, dm + o_seed,
+                                        script_blocks, (const unsigned long long*)(dm + o_tm),
+                                        (const uint32_t*)(dm + o_ss), (const bv_seg*)(dm + o_sg), dsc, dpts,
+                                        (uint8_t*)ctx->bv_part.p, nullptr, (int*)ctx->flags.p, j0, cnt, block_base);
+    else
+      k_bv_prepare<<<nb, 128, 0, st>>>(d, (const uint32_t*)(dm + o_prefix), N, dpts + (size_t)nc * 32, dpts,
+                                       (const uint8_t*)ctx->bv_com.p, (const uint8_t*)ctx->bv_resp.p, dm + o_seed, dsc, dpts,
+                                       (uint8_t*)ctx->bv_part.p, nullptr, (int*)ctx->flags.p, j0, cnt, block_base);
     LAUNCH_CHECK(ctx);
     block_base += nb;
     // the slabs of this chunk are complete (points and coefficients)

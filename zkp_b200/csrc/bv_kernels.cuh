@@ -166,6 +166,146 @@ __global__ void __launch_bounds__(128) k_bv_prepare(bv_desc d, const uint32_t* _
   }
 }
 
+// -----------------------------------------------------------------------------------------------------------------
+// The same front end with the transcript COMPILED on the host.  Every proof of a batch follows the same script (same
+// labels, same lengths), so STROBE's framing -- operation headers, length fields, labels, the batch-wide static point
+// encodings, the padding bytes of every run_f and the block boundaries -- is identical for all proofs and only the 32-byte
+// per-proof values (instance encodings, commitments) differ.  The host runs a symbolic STROBE over the script
+// (api.cu bv_compile_script) and hands over
+//   tmpl[nblocks][21]   the constant bytes of every 168-byte rate block (166 rate bytes + the two padding positions)
+//   segs[]              where the bytes [src_off, src_off + len) of per-proof value (kind, idx) land in which block
+// and a thread absorbs block b as  state[0..20] ^= tmpl[b] ^ (its values shifted into place), Keccak-f in registers:
+// no byte loops, no local-memory state (the byte-wise k_bv_prepare spends ~4x its instruction-issue time there).
+// The challenge is the first 64 bytes of the state after the last block (the script ends with the forced run_f of `prf`).
+// -----------------------------------------------------------------------------------------------------------------
+struct bv_seg {
+  uint32_t kind;      // 0 instance point, 2 blinding commitment
+  uint32_t idx;       // variable / constraint index
+  uint32_t src_off;   // first byte of the value used by this segment
+  uint32_t len;       // bytes
+  int32_t shift;      // dst_off - src_off: byte position of value byte 0 in the block (may be negative)
+  uint32_t pad[3];
+};
+
+__global__ void __launch_bounds__(128) k_bv_prepare2(bv_desc d, const uint32_t* __restrict__ prefix, size_t N,
+                                                     const uint8_t* __restrict__ instance_enc,
+                                                     const uint8_t* __restrict__ commitments,
+                                                     const uint8_t* __restrict__ responses,
+                                                     const uint8_t* __restrict__ rho_seed, int nblocks,
+                                                     const unsigned long long* __restrict__ tmpl,
+                                                     const uint32_t* __restrict__ seg_start,   // [nblocks + 1]
+                                                     const bv_seg* __restrict__ segs, uint8_t* __restrict__ msm_scalars,
+                                                     uint8_t* __restrict__ msm_points, uint8_t* __restrict__ static_part,
+                                                     uint8_t* __restrict__ minus_c_out, int* __restrict__ flags, size_t j0,
+                                                     size_t cnt, unsigned block_base) {
+  __shared__ unsigned long long buf[21][128];   // the rate block under construction, one column per thread
+  __shared__ scl red[128];
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t j = j0 + tid;
+  const bool live = tid < cnt;
+  const int tx = threadIdx.x;
+  scl inst[ZKP_BV_MAX_VARS], stat[ZKP_BV_MAX_VARS];
+  for (int i = 0; i < d.ni; i++) scl_zero(inst[i]);
+  for (int i = 0; i < d.nc; i++) scl_zero(stat[i]);
+  if (live) {
+    uint64_t st[25];
+#pragma unroll
+    for (int i = 0; i < 25; i++) st[i] = (uint64_t)prefix[2 * i] | ((uint64_t)prefix[2 * i + 1] << 32);
+    bool bad = false;
+    for (int b = 0; b < nblocks; b++) {
+#pragma unroll
+      for (int l = 0; l < 21; l++) buf[l][tx] = __ldg(tmpl + (size_t)b * 21 + l);
+      for (uint32_t si = seg_start[b]; si < seg_start[b + 1]; si++) {
+        const bv_seg sg = segs[si];
+        const uint8_t* src = sg.kind == 0 ? instance_enc + ((size_t)sg.idx * N + j) * 32
+                                          : commitments + ((size_t)j * d.k + sg.idx) * 32;
+        const uint4 a = __ldg((const uint4*)src), c = __ldg((const uint4*)src + 1);
+        uint64_t w[4] = {(uint64_t)a.x | ((uint64_t)a.y << 32), (uint64_t)a.z | ((uint64_t)a.w << 32),
+                         (uint64_t)c.x | ((uint64_t)c.y << 32), (uint64_t)c.z | ((uint64_t)c.w << 32)};
+        if (sg.src_off == 0) {   // first (or only) piece of this value: the checks and copies done once per value
+          if ((w[0] | w[1] | w[2] | w[3]) == 0) bad = true;   // identity encoding (toolbox/mod.rs:191, :215)
+          if (sg.kind == 2) {
+            uint4* dst = (uint4*)(msm_points + ((size_t)d.nc + (size_t)(d.ni + sg.idx) * N + j) * 32);
+            dst[0] = a;
+            dst[1] = c;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          // bytes of word q inside [src_off, src_off + len)
+          const int lo = (int)sg.src_off - 8 * q, hi = (int)(sg.src_off + sg.len) - 8 * q;   // range within the word
+          if (hi <= 0 || lo >= 8) continue;
+          uint64_t v = w[q];
+          if (lo > 0) v &= ~0ULL << (8 * lo);
+          if (hi < 8) v &= ~0ULL >> (8 * (8 - hi));
+          const int pos = sg.shift + 8 * q;            // byte position of this word's byte 0 (may be negative)
+          const int lane = pos >> 3, r = pos & 7;      // arithmetic shift: floor division
+          if (r == 0) {
+            if (lane >= 0 && lane < 21) buf[lane][tx] ^= v;
+          } else {
+            if (lane >= 0 && lane < 21) buf[lane][tx] ^= v << (8 * r);
+            if (lane + 1 >= 0 && lane + 1 < 21) buf[lane + 1][tx] ^= v >> (64 - 8 * r);
+          }
+        }
+      }
+#pragma unroll
+      for (int l = 0; l < 21; l++) st[l] ^= buf[l][tx];
+      keccak_f1600_dev(st);
+    }
+    if (bad) atomicMin(&flags[0], (int)j);
+    uint8_t wide[64];
+#pragma unroll
+    for (int i = 0; i < 64; i++) wide[i] = (uint8_t)(st[i >> 3] >> (8 * (i & 7)));
+    scl c, minus_c;
+    scl_from_wide(c, wide);
+    scl_neg(minus_c, c);
+    if (minus_c_out) store_scl(minus_c_out + j * 32, minus_c);
+    // ---- weights and coefficient fold: identical to k_bv_prepare ----
+    uint8_t msg[40];
+#pragma unroll
+    for (int b = 0; b < 32; b++) msg[b] = rho_seed[b];
+#pragma unroll
+    for (int b = 0; b < 8; b++) msg[32 + b] = (uint8_t)((unsigned long long)j >> (8 * b));
+    uint8_t all[16 * ZKP_BV_MAX_CONS];
+    shake256_short(all, (uint32_t)(16 * d.k), msg, 40);
+    for (int i = 0; i < d.k; i++) {
+      scl rho;
+#pragma unroll
+      for (int w4 = 0; w4 < 4; w4++)
+        rho.v[w4] = (uint32_t)all[16 * i + 4 * w4] | ((uint32_t)all[16 * i + 4 * w4 + 1] << 8) |
+                    ((uint32_t)all[16 * i + 4 * w4 + 2] << 16) | ((uint32_t)all[16 * i + 4 * w4 + 3] << 24);
+      rho.v[4] = rho.v[5] = rho.v[6] = rho.v[7] = 0;
+      scl t;
+      scl_neg(t, rho);   // instance_coeffs[(num_i + i, j)] -= rho
+      store_scl(msm_scalars + ((size_t)d.nc + (size_t)(d.ni + i) * N + j) * 32, t);
+      scl_mul(t, rho, minus_c);
+      if (d.lhs_kind[i]) scl_add(stat[d.lhs_idx[i]], stat[d.lhs_idx[i]], t);
+      else scl_add(inst[d.lhs_idx[i]], inst[d.lhs_idx[i]], t);
+      for (int q = d.cons_off[i]; q < d.cons_off[i + 1]; q++) {
+        scl resp;
+        load_scl(resp, responses + ((size_t)j * d.m + d.term_scalar[q]) * 32);
+        if (!scl_is_canonical(resp.v)) atomicMin(&flags[1], (int)j);
+        scl_mul(t, rho, resp);
+        const int pi = d.term_pidx[q];
+        if (d.term_pkind[q]) scl_add(stat[pi], stat[pi], t);
+        else scl_add(inst[pi], inst[pi], t);
+      }
+    }
+    for (int i = 0; i < d.ni; i++) store_scl(msm_scalars + ((size_t)d.nc + (size_t)i * N + j) * 32, inst[i]);
+  }
+  // ---- block partial sums of the static coefficients ----
+  for (int sidx = 0; sidx < d.nc; sidx++) {
+    red[threadIdx.x] = stat[sidx];
+    __syncthreads();
+    for (int off = 64; off >= 1; off >>= 1) {
+      if ((int)threadIdx.x < off) scl_add(red[threadIdx.x], red[threadIdx.x], red[threadIdx.x + off]);
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) store_scl(static_part + ((size_t)(block_base + blockIdx.x) * d.nc + sidx) * 32, red[0]);
+    __syncthreads();
+  }
+}
+
 // self-test: Merlin's published conformance vector computed by one device thread (zkp_selftest_hash)
 __global__ void k_selftest_merlin(uint8_t* out32) {
   strobe_t s;
