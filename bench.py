@@ -37,7 +37,12 @@ L = 2**252 + 27742317777372353535851937790883648493
 ROWS, NUM_S = 24, 12           # CMZ: 13 instance + 11 commitment rows, 12 static points
 FULL_ROWS = 13                  # rows 0..12 carry full-size coefficients, rows 13..23 are -rho (128-bit rho)
 BYTES_PER_PROOF = 1536          # 24 terms x (32 B scalar + 32 B point)   
-BUCKET_ADDS_PER_PROOF = 13 * 15 + 11 * 8   # window 17: 15 digits for the full-size rows, 8 for the 128-bit (-rho) rows
+
+
+def bucket_adds_per_proof(c):
+    """Non-zero signed c-bit digits per proof: 13 full-size rows (253 bits after the sign fold) and 11 rows of -rho with
+    128-bit rho (129 bits with the carry)."""
+    return FULL_ROWS * -(-253 // c) + (ROWS - FULL_ROWS) * -(-129 // c)
 
 
 def _l_words():
@@ -467,7 +472,8 @@ def main():
                                      "k_ingest2_frac_of_calibrated": (dec_time_at_peak / (ing_ms * 1e-3)) if ing_ms else None,
                                      "k_accumulate_ms": acc_ms if acc_ms > 0 else None,
                                      "k_accumulate_frac_of_calibrated":
-                                         (BUCKET_ADDS_PER_PROOF * N / madd_rate / (acc_ms * 1e-3)) if acc_ms > 0 else None},
+                                         (bucket_adds_per_proof(int(stages.get("window", 19))) * N / madd_rate / (acc_ms * 1e-3))
+                                         if acc_ms > 0 else None},
                     "stage_ms_unfused_profile_mode": stages, "dominant_stage_unfused": dom}
         sample = 1 << args.cpu_sample_log2
         sc_rows = sc.view(np.uint8).reshape(ROWS, N, 32)

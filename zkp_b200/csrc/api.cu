@@ -30,13 +30,13 @@ struct zkp_ctx {
   cudaStream_t stream = nullptr;
   int window = 0;      // 0 = auto
   int lanes = 0;       // 0 = auto
-  int window_cap = 18; // upper bound for the automatic choice
+  int window_cap = 19; // upper bound for the automatic choice (measured optimum at 5*10^7 terms: 19 ~ 20 < 18 < 17)
   uint64_t launches = 0;
   std::string err;
   // workspace (grown on demand, reused across calls)
   devbuf in_scalars, in_points, niels, hist, offs, cursor, sorted, buckets, lvlT[2], lvlU, usum, flags, result,
       aux0, aux1, aux2, sk0, sk1, tables, items, partials, multi, bv_com, bv_resp, bv_part, bv_misc, len_hist, order,
-      pv_limbs, pv_enc, pv_sec, pv_ent, pv_state, pv_blind, pv_resp, pv_misc;
+      pv_limbs, pv_enc, pv_sec, pv_ent, pv_state, pv_blind, pv_resp, pv_misc, scan_tmp;
   void* h_result = nullptr;  // pinned, 64 bytes
   // optional per-stage timing of the vartime MSM ("profile" option): events around each stage
   int profile = 0;
@@ -154,7 +154,7 @@ extern "C" void zkp_ctx_destroy(zkp_ctx* ctx) {
                     &ctx->flags, &ctx->result, &ctx->aux0, &ctx->aux1, &ctx->aux2, &ctx->sk0, &ctx->sk1,
                     &ctx->tables, &ctx->items, &ctx->partials, &ctx->multi, &ctx->bv_com, &ctx->bv_resp, &ctx->bv_part,
                     &ctx->bv_misc, &ctx->len_hist, &ctx->order, &ctx->pv_limbs, &ctx->pv_enc, &ctx->pv_sec, &ctx->pv_ent,
-                    &ctx->pv_state, &ctx->pv_blind, &ctx->pv_resp, &ctx->pv_misc};
+                    &ctx->pv_state, &ctx->pv_blind, &ctx->pv_resp, &ctx->pv_misc, &ctx->scan_tmp};
   for (devbuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (ctx->h_result) cudaFreeHost(ctx->h_result);
@@ -459,9 +459,22 @@ static int32_t msm_finish(zkp_ctx* ctx, const msm_plan& pl, const void* d_scalar
     const unsigned tb = (total_buckets + 255) / 256;
     k_plan<<<tb, 256, 0, st>>>((const uint32_t*)ctx->offs.p, B, total_buckets, S, (uint32_t*)ctx->aux0.p);
     LAUNCH_CHECK(ctx);
-    k_scan<<<1, 1024, 0, st>>>((const uint32_t*)ctx->aux0.p, total_buckets, (uint32_t*)ctx->aux1.p,
-                               (uint32_t*)ctx->aux2.p);
-    LAUNCH_CHECK(ctx);
+    if (total_buckets <= 65536) {
+      k_scan<<<1, 1024, 0, st>>>((const uint32_t*)ctx->aux0.p, total_buckets, (uint32_t*)ctx->aux1.p,
+                                 (uint32_t*)ctx->aux2.p);
+      LAUNCH_CHECK(ctx);
+    } else {
+      // long arrays: tiles of 4096, scan of the tile totals (<= 2^20 tiles would still fit one block's loop), add back
+      const uint32_t tiles = (total_buckets + ZKP_SCAN_TILE - 1) / ZKP_SCAN_TILE;
+      ENSURE(ctx, ctx->scan_tmp, ((size_t)tiles * 3 + 8) * 4);
+      uint32_t* tt = (uint32_t*)ctx->scan_tmp.p;            // totals [tiles] | offsets [tiles + 1] | cursor (unused) [tiles]
+      k_scan_tiles<<<tiles, 1024, 0, st>>>((const uint32_t*)ctx->aux0.p, total_buckets, (uint32_t*)ctx->aux1.p, tt);
+      LAUNCH_CHECK(ctx);
+      k_scan<<<1, 1024, 0, st>>>(tt, tiles, tt + tiles, tt + 2 * tiles + 1);
+      LAUNCH_CHECK(ctx);
+      k_scan_add<<<(total_buckets + 1023) / 1024, 1024, 0, st>>>((uint32_t*)ctx->aux1.p, total_buckets, tt + tiles);
+      LAUNCH_CHECK(ctx);
+    }
     ENSURE(ctx, ctx->multi, ((size_t)total_buckets + 4) * 4);
     uint32_t* n_multi = (uint32_t*)ctx->multi.p;          // word 0 = counter, list starts at word 4
     CUDA_TRY(ctx, cudaMemsetAsync(n_multi, 0, 16, st));

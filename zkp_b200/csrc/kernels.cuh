@@ -313,6 +313,52 @@ __global__ void __launch_bounds__(1024) k_scan(const uint32_t* __restrict__ hist
   if (threadIdx.x == 0) o[B] = base_s;
 }
 
+// Multi-block exclusive scan of a long uint32 array (the item offsets over all W * B buckets): each block of 1024
+// threads scans 4096 elements and publishes its total, one block scans the totals, a third pass adds them back.
+// out has n + 1 entries (out[n] = grand total).
+#define ZKP_SCAN_TILE 4096
+__global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ out,
+                                                     uint32_t* __restrict__ tile_tot) {
+  __shared__ uint32_t warp_tot[32];
+  const uint32_t base = blockIdx.x * ZKP_SCAN_TILE + threadIdx.x * 4;
+  uint32_t v[4], sum = 0;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    v[i] = base + i < n ? in[base + i] : 0u;
+    sum += v[i];
+  }
+  uint32_t x = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+    if ((threadIdx.x & 31) >= d) x += y;
+  }
+  if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = x;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    uint32_t t = warp_tot[threadIdx.x];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, t, d);
+      if (threadIdx.x >= d) t += y;
+    }
+    warp_tot[threadIdx.x] = t;
+  }
+  __syncthreads();
+  uint32_t excl = ((threadIdx.x >> 5) ? warp_tot[(threadIdx.x >> 5) - 1] : 0u) + x - sum;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    if (base + i < n) out[base + i] = excl;
+    excl += v[i];
+  }
+  if (threadIdx.x == 1023) tile_tot[blockIdx.x] = excl;
+}
+__global__ void __launch_bounds__(1024) k_scan_add(uint32_t* __restrict__ out, uint32_t n, const uint32_t* __restrict__ tile_offs) {
+  const uint32_t i = blockIdx.x * 1024 + threadIdx.x;
+  if (i < n) out[i] += tile_offs[i / ZKP_SCAN_TILE];
+  if (i == 0) out[n] = tile_offs[(n + ZKP_SCAN_TILE - 1) / ZKP_SCAN_TILE];
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // K5: bucket accumulation.  G lanes cooperate on one bucket.
 // ---------------------------------------------------------------------------------------------------------
