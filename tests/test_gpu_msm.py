@@ -108,6 +108,49 @@ def test_msm_linearity_full_size(engine):
     assert enc == U.tiled_expected(sc, base)
 
 
+def test_msm_bench_scale_properties(engine):
+    """At the size class of the bench (2^22 terms: window 17+, two-phase ingestion over two chunks, multi-block item scan,
+    length-sorted accumulation) the oracle is too slow, so size-independent properties decide: the tiling identity against
+    a 256-term oracle MSM, additivity MSM(all) = MSM(first part) + MSM(rest) with the sum taken by the engine itself, a
+    cancelling instance (s and l - s on the same point) that must give the identity, and one flipped bit that must not."""
+    n, K = 1 << 22, 256
+    base = U.base_points(K)
+    sc = U.random_scalars(n, seed=4242)
+    pts = np.frombuffer(b"".join(base[i % K] for i in range(K)) * (n // K), dtype=np.uint8).reshape(-1, 32)
+    enc, ident, _ = engine.msm_vartime(sc, pts)
+    assert enc == U.tiled_expected(sc, base) and not ident
+    cut = 1234567
+    e1, _, _ = engine.msm_vartime(sc[:cut], pts[:cut])
+    e2, _, _ = engine.msm_vartime(sc[cut:], pts[cut:])
+    one = np.zeros((2, 32), np.uint8)
+    one[:, 0] = 1
+    esum, _, _ = engine.msm_vartime(one, np.frombuffer(e1 + e2, dtype=np.uint8).reshape(2, 32))
+    assert esum == enc
+    # cancelling pairs: term i and term i + n/2 carry s and l - s on the same point
+    half = n // 2
+    L = R.L
+    s_lo = sc[:half].copy()
+    lw = np.frombuffer(L.to_bytes(32, "little"), dtype=np.uint64)
+    a = s_lo.view(np.uint64).reshape(half, 4)
+    neg = np.empty_like(a)
+    borrow = np.zeros(half, dtype=np.uint64)
+    for w in range(4):
+        d = lw[w] - a[:, w]
+        b1 = (lw[w] < a[:, w]).astype(np.uint64)
+        d2 = d - borrow
+        b2 = (d < borrow).astype(np.uint64)
+        neg[:, w] = d2
+        borrow = b1 | b2
+    zero = (a == 0).all(axis=1)
+    neg[zero] = 0
+    both = np.concatenate([s_lo, neg.view(np.uint8).reshape(half, 32)])
+    enc0, ident0, _ = engine.msm_vartime(both, pts)          # pts[i + half] == pts[i] because half is a multiple of K
+    assert ident0 and enc0 == bytes(32)
+    both[777, 0] ^= 1
+    enc1, ident1, _ = engine.msm_vartime(both, pts)
+    assert not ident1
+
+
 def test_small_batched_vartime(engine):
     kats = [k for k in U.golden("msm_kat.json")["kats"] if k["n"] <= 36]
     scal = np.concatenate([_h(k["scalars"]) for k in kats])
