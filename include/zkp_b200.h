@@ -145,6 +145,18 @@ int32_t zkp_batch_verify_proofs(zkp_ctx* ctx, const zkp_statement_desc* st, cons
                                 const uint8_t* responses, const uint8_t* rho_seed, int32_t* accept, int64_t* first_bad,
                                 uint8_t* coeff_out, uint8_t* points_out);
 
+/* Single-verdict mode over shards (one BatchVerifier batch whose proofs -- the columns of the instance matrix of
+ * /root/reference/src/toolbox/batch_verifier.rs:174 -- are cut over several GPUs or calls): zkp_batch_verify_partial takes
+ * the same arguments as zkp_batch_verify for ONE shard (the static coefficients may all go to one shard) and returns
+ * the shard's MSM sum as an extended point in FieldElement51 limb form (X, Y, Z, T: 20 x u64) instead of a verdict;
+ * zkp_partials_verdict adds `count` such points and applies the identity test of batch_verifier.rs:230 to the sum
+ * (enc_out32 optional: the encoding of the sum).  The sums cross ranks with one all-gather of 160 bytes per rank.     */
+int32_t zkp_batch_verify_partial(zkp_ctx* ctx, const uint8_t* static_coeffs, const uint8_t* static_points, size_t num_s,
+                                 const uint8_t* instance_coeffs, const uint8_t* instance_points, size_t rows, size_t batch,
+                                 uint64_t* partial_limbs_out, int64_t* first_bad);
+int32_t zkp_partials_verdict(zkp_ctx* ctx, const uint64_t* partial_limbs, size_t count, int32_t* accept,
+                             uint8_t* enc_out32);
+
 /* Batch proving with the per-proof work of Prover::prove_impl (/root/reference/src/toolbox/prover.rs:76-112) on the
  * device: allocate_point compressions (toolbox/mod.rs:180), transcript replay, the synthetic-nonce blindings of
  * prover.rs:78-89 (TranscriptRng rekeyed with every secret and finalized with entropy[j], the stand-in for thread_rng),

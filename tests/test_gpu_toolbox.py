@@ -357,6 +357,61 @@ def test_compiled_transcript_script_equals_bytewise_strobe(engine):
         assert [bytes(p) for p in po] == opts and [bytes(c) for c in co] == [S.to_bytes(s_) for s_ in oscal], L
 
 
+def test_single_verdict_mode_over_shards(engine):
+    """SURVEY 8e, single-verdict mode: ONE BatchVerifier batch (one weight stream, one static coefficient vector) cut by
+    proofs into shards; the shards' partial sums (zkp_batch_verify_partial) are individually NOT the identity when the
+    static coefficients all travel with shard 0, their sum is (zkp_partials_verdict) -- exactly the reference's verdict."""
+    st = PT.cmz10_statement()
+    N = 9
+    secs, ptss = _cmz_instances(N, b"cmz-shards")
+    sec_arr = np.stack([sbytes([s_[n] for n in st.secrets]) for s_ in secs])
+    pts_arr = np.array([[limbs(p[n]) for n in st.points] for p in ptss], dtype=np.uint64)
+    entropy = np.frombuffer(OT.SeededRng(b"entropy-shards").bytes(32 * N), dtype=np.uint8).reshape(N, 32)
+    enc, com, resp = st.prove_many_device(engine, b"CMZ", sec_arr, pts_arr, entropy)
+    ni, nc = len(st.instance), len(st.common)
+    inst = np.ascontiguousarray(enc[:, :ni].transpose(1, 0, 2))
+    co, po, _ = st.batch_verify(engine, com, resp, b"CMZ", inst, enc[0, ni:], b"one-rho-stream", threads=2, want_msm_inputs=True)
+    rows = ni + st.k
+    sc_static, sc_inst = co[:nc], co[nc:].reshape(rows, N, 32)
+    pt_static, pt_inst = po[:nc], po[nc:].reshape(rows, N, 32)
+    from zkp_b200 import parallel
+    for world in (1, 2, 3):
+        partials = []
+        for rank in range(world):
+            lo, hi = parallel.shard_range(N, rank, world)
+            s_sc = sc_static if rank == 0 else sc_static[:0]
+            s_pt = pt_static if rank == 0 else pt_static[:0]
+            part = engine.batch_verify_partial(s_sc, s_pt, np.ascontiguousarray(sc_inst[:, lo:hi]).reshape(-1, 32),
+                                               np.ascontiguousarray(pt_inst[:, lo:hi]).reshape(-1, 32), rows, hi - lo)
+            assert part is not None and part.shape == (4, 5)
+            partials.append(part)
+        ok, enc_sum = engine.partials_verdict(np.stack(partials))
+        assert ok and enc_sum == bytes(32)
+        if world > 1:
+            alone, e0 = engine.partials_verdict(partials[0])
+            assert not alone and e0 != bytes(32)        # shard 0 carries all static coefficients: not the identity by itself
+    # a tampered coefficient in one shard voids the single verdict; an invalid encoding is reported by its shard
+    bad = sc_inst.copy()
+    bad[3, N - 1, 0] ^= 1
+    lo, hi = parallel.shard_range(N, 1, 2)
+    p0 = engine.batch_verify_partial(sc_static, pt_static, np.ascontiguousarray(sc_inst[:, :lo]).reshape(-1, 32),
+                                     np.ascontiguousarray(pt_inst[:, :lo]).reshape(-1, 32), rows, lo)
+    p1 = engine.batch_verify_partial(sc_static[:0], pt_static[:0], np.ascontiguousarray(bad[:, lo:hi]).reshape(-1, 32),
+                                     np.ascontiguousarray(pt_inst[:, lo:hi]).reshape(-1, 32), rows, hi - lo)
+    ok, _ = engine.partials_verdict(np.stack([p0, p1]))
+    assert not ok
+    badp = pt_inst.copy()
+    badp[2, lo] = 0xFF
+    assert engine.batch_verify_partial(sc_static[:0], pt_static[:0], np.ascontiguousarray(sc_inst[:, lo:hi]).reshape(-1, 32),
+                                       np.ascontiguousarray(badp[:, lo:hi]).reshape(-1, 32), rows, hi - lo) is None
+    # the empty shard contributes the identity
+    pe = engine.batch_verify_partial(sc_static[:0], pt_static[:0], sc_static[:0], pt_static[:0], rows, 0)
+    ok, _ = engine.partials_verdict(np.stack([p0, pe]))
+    assert not ok                                        # p0 alone is only part of the batch
+    ok, _ = engine.partials_verdict(pe)
+    assert ok
+
+
 def test_device_front_end_edge_shapes(engine):
     """N = 1, an empty batch, and a statement whose constraint has a STATIC lhs (static_coeffs path of
     batch_verifier.rs:187-189) through both the host mirror and the device front end."""

@@ -26,6 +26,14 @@ def _worker(rank, world, port, bad_rank, q):
     lo, hi = parallel.shard_range(N, rank, world)
     assert mine.shape == (3, hi - lo, 32) and (mine == rows[:, lo:hi]).all()
     bits, verdict = parallel.gather_accept_bits(rank != bad_rank)
+    # single-verdict mode plumbing: 160-byte partial sums in rank order; a rank with an invalid shard voids the gather
+    part = (np.arange(20, dtype=np.uint64) + np.uint64(1000 * rank) + np.uint64(1 << 63)).reshape(4, 5)
+    allp = parallel.gather_partial_sums(part)
+    assert allp.shape == (world, 20) and allp.dtype == np.uint64
+    for r in range(world):
+        assert (allp[r] == np.arange(20, dtype=np.uint64) + np.uint64(1000 * r) + np.uint64(1 << 63)).all()
+    voided = parallel.gather_partial_sums(None if rank == bad_rank else part)
+    assert (voided is None) == (bad_rank >= 0)
     q.put((rank, lo, hi, bits, verdict))
     dist.destroy_process_group()
 

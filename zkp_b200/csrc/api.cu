@@ -36,7 +36,7 @@ struct zkp_ctx {
   // workspace (grown on demand, reused across calls)
   devbuf in_scalars, in_points, niels, hist, offs, cursor, sorted, buckets, lvlT[2], lvlU, usum, flags, result,
       aux0, aux1, aux2, sk0, sk1, tables, items, partials, multi, bv_com, bv_resp, bv_part, bv_misc, len_hist, order,
-      pv_limbs, pv_enc, pv_sec, pv_ent, pv_state, pv_blind, pv_resp, pv_misc, scan_tmp;
+      pv_limbs, pv_enc, pv_sec, pv_ent, pv_state, pv_blind, pv_resp, pv_misc, scan_tmp, partial_buf;
   void* h_result = nullptr;  // pinned, 64 bytes
   // optional per-stage timing of the vartime MSM ("profile" option): events around each stage
   int profile = 0;
@@ -55,6 +55,7 @@ struct zkp_ctx {
   // concurrently with decompression (integer-multiply bound); joined before bucket accumulation
   int overlap = 0;   // measured: no gain on B200 (159.2 vs 159.9 ms per step), kept as an option
   int balance = 1;     // size-ordered work items in the bucket accumulation (equal-length items share a warp)
+  void* partial_out = nullptr;   // when set, k_finish also stores the MSM result as an extended point (single-verdict mode)
   int bv_compiled = 1;      // batch-verification front end: host-compiled transcript script (k_bv_prepare2)
   int ingest_variant = 2;   // occupancy point of k_ingest2 (kernels.cuh ZKP_INGEST_*)
   int fused_sort = 1;  // histogram and scatter ride under the two halves of the decompression (k_ingest2)
@@ -154,7 +155,7 @@ extern "C" void zkp_ctx_destroy(zkp_ctx* ctx) {
                     &ctx->flags, &ctx->result, &ctx->aux0, &ctx->aux1, &ctx->aux2, &ctx->sk0, &ctx->sk1,
                     &ctx->tables, &ctx->items, &ctx->partials, &ctx->multi, &ctx->bv_com, &ctx->bv_resp, &ctx->bv_part,
                     &ctx->bv_misc, &ctx->len_hist, &ctx->order, &ctx->pv_limbs, &ctx->pv_enc, &ctx->pv_sec, &ctx->pv_ent,
-                    &ctx->pv_state, &ctx->pv_blind, &ctx->pv_resp, &ctx->pv_misc, &ctx->scan_tmp};
+                    &ctx->pv_state, &ctx->pv_blind, &ctx->pv_resp, &ctx->pv_misc, &ctx->scan_tmp, &ctx->partial_buf};
   for (devbuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (ctx->h_result) cudaFreeHost(ctx->h_result);
@@ -529,7 +530,7 @@ static int32_t msm_finish(zkp_ctx* ctx, const msm_plan& pl, const void* d_scalar
     nl++;
   }
   STAGE(6);
-  k_finish<<<1, 64, 0, st>>>((const uint4*)ctx->usum.p, nl, cur, m, W, c, n, flags, d_result, nullptr);
+  k_finish<<<1, 64, 0, st>>>((const uint4*)ctx->usum.p, nl, cur, m, W, c, n, flags, d_result, (uint4*)ctx->partial_out);
   LAUNCH_CHECK(ctx);
   STAGE(7);
   if (ctx->profile && whole) {
@@ -696,6 +697,58 @@ extern "C" int32_t zkp_batch_verify(zkp_ctx* ctx, const uint8_t* static_coeffs, 
   if (r != ZKP_OK) return r;
   int32_t ident = 0;
   r = fetch_result(ctx, nullptr, &ident, first_bad);
+  if (r != ZKP_OK) return r;
+  *accept = ident;
+  return ZKP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// single-verdict mode over shards: partial sums out, verdict on their sum
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int32_t zkp_batch_verify_partial(zkp_ctx* ctx, const uint8_t* static_coeffs, const uint8_t* static_points,
+                                            size_t num_s, const uint8_t* instance_coeffs, const uint8_t* instance_points,
+                                            size_t rows, size_t batch, uint64_t* partial_limbs_out, int64_t* first_bad) {
+  if (!ctx || !partial_limbs_out) return ZKP_ERR_SIZE;
+  if ((num_s && (!static_coeffs || !static_points)) || (rows * batch && (!instance_coeffs || !instance_points)))
+    return ZKP_ERR_SIZE;
+  if (batch && rows > ((size_t)1 << 40) / batch) return ZKP_ERR_SIZE;
+  const size_t n_inst = rows * batch, n = num_s + n_inst;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  ENSURE(ctx, ctx->result, 64);
+  ENSURE(ctx, ctx->partial_buf, 128 + 160);
+  cudaStream_t st = ctx->stream;
+  if (n == 0) {   // the empty sum: the identity (0 : 1 : 1 : 0)
+    memset(partial_limbs_out, 0, 160);
+    partial_limbs_out[5] = 1;
+    partial_limbs_out[10] = 1;
+    if (first_bad) *first_bad = -1;
+    return ZKP_OK;
+  }
+  hseg ss[2] = {{static_coeffs, num_s}, {instance_coeffs, n_inst}};
+  hseg ps[2] = {{static_points, num_s}, {instance_points, n_inst}};
+  ctx->partial_out = ctx->partial_buf.p;
+  int32_t r = msm_from_host(ctx, ss, ps, 2, n, (msm_result*)ctx->result.p);
+  ctx->partial_out = nullptr;
+  if (r != ZKP_OK) return r;
+  k_ext_to_limbs<<<1, 1, 0, st>>>((const uint4*)ctx->partial_buf.p, (unsigned long long*)((uint8_t*)ctx->partial_buf.p + 128));
+  LAUNCH_CHECK(ctx);
+  CUDA_TRY(ctx, cudaMemcpyAsync(partial_limbs_out, (uint8_t*)ctx->partial_buf.p + 128, 160, cudaMemcpyDeviceToHost, st));
+  return fetch_result(ctx, nullptr, nullptr, first_bad);   // reports invalid points / scalars of this shard
+}
+
+extern "C" int32_t zkp_partials_verdict(zkp_ctx* ctx, const uint64_t* partial_limbs, size_t count, int32_t* accept,
+                                        uint8_t* enc_out32) {
+  if (!ctx || !accept || (count && !partial_limbs)) return ZKP_ERR_SIZE;
+  *accept = 0;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  ENSURE(ctx, ctx->result, 64);
+  ENSURE(ctx, ctx->aux0, count * 160 + 160);
+  cudaStream_t st = ctx->stream;
+  if (count) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->aux0.p, partial_limbs, count * 160, cudaMemcpyHostToDevice, st));
+  k_sum_partials<<<1, 1, 0, st>>>((const unsigned long long*)ctx->aux0.p, count, (msm_result*)ctx->result.p);
+  LAUNCH_CHECK(ctx);
+  int32_t ident = 0;
+  int32_t r = fetch_result(ctx, enc_out32, &ident, nullptr);
   if (r != ZKP_OK) return r;
   *accept = ident;
   return ZKP_OK;

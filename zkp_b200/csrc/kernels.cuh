@@ -626,6 +626,33 @@ __global__ void __launch_bounds__(64) k_finish(const uint4* __restrict__ usum, i
   }
 }
 
+// Single-verdict mode across shards: a shard's MSM result leaves the device as an extended point in
+// FieldElement51 limb form (X, Y, Z, T: 20 x u64, the layout of include/zkp_b200.h), the verdict is taken on the sum.
+__global__ void k_ext_to_limbs(const uint4* __restrict__ ext, unsigned long long* __restrict__ limbs) {
+  ge_ext p;
+  load_ext(p, ext);
+  fe_to_limbs51((uint64_t*)limbs, p.X);
+  fe_to_limbs51((uint64_t*)limbs + 5, p.Y);
+  fe_to_limbs51((uint64_t*)limbs + 10, p.Z);
+  fe_to_limbs51((uint64_t*)limbs + 15, p.T);
+}
+// sum of `count` limb-form points, ristretto encode, coset-aware identity test (one thread: count is the shard count)
+__global__ void k_sum_partials(const unsigned long long* __restrict__ limbs, size_t count, msm_result* __restrict__ res) {
+  ge_ext acc, p;
+  ge_identity(acc);
+  for (size_t i = 0; i < count; i++) {
+    load_ext_limbs51(p, limbs + 20 * i);
+    ge_add(acc, acc, p);
+  }
+  uint32_t enc[8];
+  ristretto_encode(enc, acc);
+  uint32_t z = 0;
+  for (int i = 0; i < 8; i++) { res->enc[i] = enc[i]; z |= enc[i]; }
+  res->status = 0;
+  res->is_identity = (z == 0) ? 1 : 0;
+  res->first_bad = -1;
+}
+
 // n == 0: the empty sum
 __global__ void k_empty_result(msm_result* res) {
   for (int i = 0; i < 8; i++) res->enc[i] = 0;

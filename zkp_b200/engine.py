@@ -125,6 +125,28 @@ class Engine:
         self._check(rc, ok=(native.ZKP_OK, native.ZKP_ERR_POINT))
         return bool(acc.value) and rc == native.ZKP_OK, rc
 
+    def batch_verify_partial(self, static_coeffs, static_points, instance_coeffs, instance_points, rows, batch):
+        """One shard of a batch in single-verdict mode: returns the shard's MSM sum as a (4, 5) uint64 limb-form point
+        (X, Y, Z, T), or None for an invalid point encoding (VerificationFailure)."""
+        sc, sp = _u8(static_coeffs, 32), _u8(static_points, 32)
+        ic, ip = _u8(instance_coeffs, 32), _u8(instance_points, 32)
+        if sc.shape[0] != sp.shape[0] or ic.shape[0] != rows * batch or ip.shape[0] != rows * batch:
+            raise EngineError(native.ZKP_ERR_SIZE, "batch_verify_partial: inconsistent sizes")
+        out = np.zeros((4, 5), dtype=np.uint64)
+        bad = ctypes.c_int64(-1)
+        rc = self._lib.zkp_batch_verify_partial(self._ctx, _ptr(sc), _ptr(sp), sc.shape[0], _ptr(ic), _ptr(ip), int(rows),
+                                                int(batch), _ptr(out), ctypes.byref(bad))
+        self._check(rc, ok=(native.ZKP_OK, native.ZKP_ERR_POINT))
+        return out if rc == native.ZKP_OK else None
+
+    def partials_verdict(self, partials):
+        """Identity test (batch_verifier.rs:230) on the sum of the shards' partial sums: (accept, encoding of the sum)."""
+        p = np.ascontiguousarray(partials, dtype=np.uint64).reshape(-1, 20)
+        acc = ctypes.c_int32(0)
+        enc = np.zeros(32, dtype=np.uint8)
+        self._check(self._lib.zkp_partials_verdict(self._ctx, _ptr(p), p.shape[0], ctypes.byref(acc), _ptr(enc)))
+        return bool(acc.value), enc.tobytes()
+
     def decompress_batch(self, encodings):
         e = _u8(encodings, 32)
         n = e.shape[0]

@@ -31,3 +31,25 @@ def gather_accept_bits(accept, device=None, group=None):
     dist.all_gather(out, mine, group=group)
     bits = [int(t.item()) for t in out]
     return bits, all(bits)
+
+
+def gather_partial_sums(partial_limbs, device=None, group=None):
+    """Single-verdict mode: all-gather every rank's partial MSM sum -- one extended point in limb form,
+    20 x uint64 = 160 bytes per rank -- and return the (world, 20) array every rank feeds to Engine.partials_verdict.
+    A rank whose shard held an invalid encoding passes None: the batch is rejected (VerificationFailure)."""
+    import numpy as np
+    ok = partial_limbs is not None
+    mine = np.zeros(21, dtype=np.int64)
+    if ok:
+        mine[:20] = np.ascontiguousarray(partial_limbs, dtype=np.uint64).reshape(20).view(np.int64)
+        mine[20] = 1
+    if not (dist.is_available() and dist.is_initialized()):
+        return (mine[:20].view(np.uint64).reshape(1, 20) if ok else None)
+    world = dist.get_world_size(group)
+    t = torch.from_numpy(mine).to(device) if device is not None else torch.from_numpy(mine)
+    out = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(out, t, group=group)
+    arr = np.stack([o.cpu().numpy() for o in out])
+    if not (arr[:, 20] == 1).all():
+        return None
+    return np.ascontiguousarray(arr[:, :20]).view(np.uint64)
