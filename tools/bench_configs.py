@@ -26,6 +26,9 @@ def main():
     ap.add_argument("--log2-cmz", type=int, default=16)
     ap.add_argument("--log2-dleq", type=int, default=20)
     ap.add_argument("--sweep-max", type=int, default=22)
+    ap.add_argument("--cpu-port", action="store_true",
+                    help="also time the C port of the reference's CPU algorithms (oracle/_ref) beside the raw MSM sweep, as "
+                         "bench.py's cpu_baseline leg does; it doubles as a byte-for-byte check of the GPU results")
     ap.add_argument("--out", default="gpurun_out/configs.json")
     args = ap.parse_args()
     eng = Engine(0)
@@ -111,6 +114,32 @@ def main():
                                            "proofs_per_s_device_front_end": N / t_dev}
     print("cmz batch verify (real proofs)", res["cmz_batch_verify_real_proofs"], flush=True)
 
+    # ---- configs[3], bitmap mode: the batch cut into sub-batches, one accept bit each (the bits are what the ranks
+    # all-gather); one tampered proof must clear exactly its sub-batch's bit ---------------------------------------
+    K_sub = 16
+    S_sub = N // K_sub
+    bad_j = 5 * S_sub + 17
+    bad = resp.copy()
+    bad[bad_j, 2, 0] ^= 1
+
+    def bitmap(responses):
+        bits = []
+        for q in range(K_sub):
+            lo, hi = q * S_sub, (q + 1) * S_sub
+            try:
+                st.batch_verify_device(eng, com[lo:hi], responses[lo:hi], b"CMZ", np.ascontiguousarray(inst[:, lo:hi]),
+                                       enc[0, ni:], seed)
+                bits.append(1)
+            except PT.VerificationFailure:
+                bits.append(0)
+        return bits
+    t_bits, bits_ok = timed(lambda: bitmap(resp), 2)
+    bits_bad = bitmap(bad)
+    assert bits_ok == [1] * K_sub and bits_bad == [1] * 5 + [0] + [1] * (K_sub - 6), (bits_ok, bits_bad)
+    res["config3_bitmap_mode"] = {"proofs": N, "sub_batches": K_sub, "proofs_per_sub_batch": S_sub, "total_s": t_bits,
+                                  "proofs_per_s": N / t_bits, "bitmap_valid": bits_ok, "bitmap_one_tampered_proof": bits_bad}
+    print("config3-bitmap", res["config3_bitmap_mode"], flush=True)
+
     # ---- configs[2]: DLEQ batch verify 2^20 -------------------------------------------------------------------
     N = 1 << args.log2_dleq
     st = PT.dleq_statement()
@@ -160,7 +189,9 @@ def main():
     print("config2", res["config2_dleq_batch_verify"], flush=True)
 
     # ---- configs[4]: raw MSM sweep ------------------------------------------------------------------------------
-    from oracle import cref
+    cref = None
+    if args.cpu_port:        # baseline leg only (like bench.py's cpu_baseline): never on the product path
+        from oracle import cref
     K = 1 << 16
     pool = mults_of_base(eng, rand_scalars(rng, (K,)))
     sweep = []
@@ -181,7 +212,7 @@ def main():
         ms = e0.elapsed_time(e1) / reps
         gpu_enc = d_res.cpu().numpy()[:32].tobytes()
         row = {"log2_n": lg, "gpu_ms": ms, "gpu_terms_per_s": n / (ms * 1e-3)}
-        if lg <= 18:
+        if cref is not None and lg <= 18:
             t = time.perf_counter()
             cpu_enc = cref.msm_vartime(sc, pt, threads=threads)
             dt = time.perf_counter() - t
