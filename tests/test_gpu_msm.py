@@ -280,6 +280,33 @@ def test_two_phase_ingestion_and_item_balance_options(engine):
         engine.set_option("chunk_terms", 1 << 21)
 
 
+def test_maximum_sizes_are_refused_not_attempted(engine):
+    """Term indices travel in 31 bits of the sorted entries, so one call takes fewer than 2^31 - 1 terms: larger requests
+    come back as ZKP_ERR_SIZE before any allocation or launch (device-resident and batch entry points), and the batch
+    entry points refuse rows * batch products that overflow."""
+    import ctypes
+    import torch
+    from zkp_b200 import native
+    lib, ctx = engine._lib, engine._ctx
+    d = torch.zeros(256, dtype=torch.uint8, device="cuda")
+    before = engine.launch_count
+    for n in (2**31 - 1, 2**31, 2**40):
+        rc = lib.zkp_msm_vartime_dev(ctx, ctypes.c_void_p(d.data_ptr()), ctypes.c_void_p(d.data_ptr()), n,
+                                     ctypes.c_void_p(d.data_ptr()))
+        assert rc == native.ZKP_ERR_SIZE, n
+    acc = ctypes.c_int32(7)
+    buf = np.zeros((4, 32), np.uint8)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    assert lib.zkp_batch_verify(ctx, None, None, 0, p(buf), p(buf), 2**30, 2**30, ctypes.byref(acc), None) == native.ZKP_ERR_SIZE
+    assert lib.zkp_batch_verify(ctx, None, None, 0, p(buf), p(buf), 2**62, 8, ctypes.byref(acc), None) == native.ZKP_ERR_SIZE
+    assert lib.zkp_batch_verify(ctx, None, None, 0, p(buf), p(buf), 2**16, 2**16, ctypes.byref(acc), None) == native.ZKP_ERR_SIZE
+    assert acc.value == 0
+    assert engine.launch_count == before
+    # the engine still works afterwards
+    enc, ident, _ = engine.msm_vartime(b"", b"")
+    assert enc == bytes(32) and ident
+
+
 def test_abi_misuse_is_reported_not_crashed(engine):
     import ctypes
     from zkp_b200 import native

@@ -570,6 +570,10 @@ static int32_t msm_from_host(zkp_ctx* ctx, const hseg* sc_segs, const hseg* pt_s
     LAUNCH_CHECK(ctx);
     return ZKP_OK;
   }
+  if (n >= 0x7fffffffull) {   // refuse before staging anything (msm_prepare has the same bound)
+    ctx->err = "n too large (>= 2^31 - 1 terms per call)";
+    return ZKP_ERR_SIZE;
+  }
   ENSURE(ctx, ctx->in_scalars, n * 32);
   ENSURE(ctx, ctx->in_points, n * 32);
   if (!ctx->copy_stream) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
