@@ -69,7 +69,9 @@ def test_dleq_prove_verify_matches_oracle(engine):
                 st.verify_compact(engine, (chal, resp), b"DLEQTest", wrong)
 
 
-def _cmz_instances(N, seed):
+def _cmz_instances(N, seed, fresh_common=False):
+    """fresh_common is accepted for readability at the call site: the common points are derived from `seed` anyway, so
+    a different seed gives different common points."""
     rng = OT.SeededRng(seed)
     ost = OT.CMZ10
     common = {n: R.from_uniform_bytes(rng.bytes(64)) for n in ost.common}
@@ -268,6 +270,23 @@ def test_prove_many_device_front_end_matches_host_and_oracle(engine):
                            bytes(range(32)))
     _, com_x, _ = st.prove_many_device(engine, b"CMY", sec_arr, pts_arr, entropy)
     assert (com_x != com_d).any()
+    # shared constant-time tables of the batch-static points on / off give the same bytes; a batch whose "common" points
+    # differ between proofs (legal: every proof carries its own assignments) falls back to per-proof tables
+    engine.set_option("share_static_tables", 0)
+    try:
+        e_n, c_n, r_n = st.prove_many_device(engine, b"CMZ", sec_arr, pts_arr, entropy)
+    finally:
+        engine.set_option("share_static_tables", 1)
+    assert (e_n == enc_d).all() and (c_n == com_d).all() and (r_n == resp_d).all()
+    secs2, ptss2 = _cmz_instances(2, b"cmz-pv-other-common", fresh_common=True)
+    mixed_pts = pts_arr.copy()
+    mixed_pts[N - 1] = np.array([limbs(ptss2[0][n]) for n in st.points], dtype=np.uint64)
+    mixed_sec = sec_arr.copy()
+    mixed_sec[N - 1] = sbytes([secs2[0][n] for n in st.secrets])
+    e_m, c_m, r_m = st.prove_many_device(engine, b"CMZ", mixed_sec, mixed_pts, entropy)
+    e_h, c_h, r_h = st.prove_many(engine, b"CMZ", mixed_sec, mixed_pts, entropy, threads=2)
+    assert (e_m == e_h).all() and (c_m == c_h).all() and (r_m == r_h).all()
+    st.verify_batchable(engine, (c_m[N - 1], r_m[N - 1]), b"CMZ", e_m[N - 1], b"rho")
     # N = 1 and the empty batch
     e1, c1, r1 = st.prove_many_device(engine, b"CMZ", sec_arr[:1], pts_arr[:1], entropy[:1])
     assert (e1 == enc_h[:1]).all() and (c1 == com_h[:1]).all() and (r1 == resp_h[:1]).all()

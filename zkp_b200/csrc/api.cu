@@ -36,7 +36,7 @@ struct zkp_ctx {
   // workspace (grown on demand, reused across calls)
   devbuf in_scalars, in_points, niels, hist, offs, cursor, sorted, buckets, lvlT[2], lvlU, usum, flags, result,
       aux0, aux1, aux2, sk0, sk1, tables, items, partials, multi, bv_com, bv_resp, bv_part, bv_misc, len_hist, order,
-      pv_limbs, pv_enc, pv_sec, pv_ent, pv_state, pv_blind, pv_resp, pv_misc, scan_tmp, partial_buf;
+      pv_limbs, pv_enc, pv_sec, pv_ent, pv_state, pv_blind, pv_resp, pv_misc, scan_tmp, partial_buf, pv_static;
   void* h_result = nullptr;  // pinned, 64 bytes
   // optional per-stage timing of the vartime MSM ("profile" option): events around each stage
   int profile = 0;
@@ -56,6 +56,7 @@ struct zkp_ctx {
   int overlap = 0;   // measured: no gain on B200 (159.2 vs 159.9 ms per step), kept as an option
   int balance = 1;     // size-ordered work items in the bucket accumulation (equal-length items share a warp)
   void* partial_out = nullptr;   // when set, k_finish also stores the MSM result as an extended point (single-verdict mode)
+  int share_static_tables = 1;   // batch proving: one constant-time table per batch-static point
   int bv_compiled = 1;      // batch-verification front end: host-compiled transcript script (k_bv_prepare2)
   int ingest_variant = 2;   // occupancy point of k_ingest2 (kernels.cuh ZKP_INGEST_*)
   int fused_sort = 1;  // histogram and scatter ride under the two halves of the decompression (k_ingest2)
@@ -155,7 +156,7 @@ extern "C" void zkp_ctx_destroy(zkp_ctx* ctx) {
                     &ctx->flags, &ctx->result, &ctx->aux0, &ctx->aux1, &ctx->aux2, &ctx->sk0, &ctx->sk1,
                     &ctx->tables, &ctx->items, &ctx->partials, &ctx->multi, &ctx->bv_com, &ctx->bv_resp, &ctx->bv_part,
                     &ctx->bv_misc, &ctx->len_hist, &ctx->order, &ctx->pv_limbs, &ctx->pv_enc, &ctx->pv_sec, &ctx->pv_ent,
-                    &ctx->pv_state, &ctx->pv_blind, &ctx->pv_resp, &ctx->pv_misc, &ctx->scan_tmp, &ctx->partial_buf};
+                    &ctx->pv_state, &ctx->pv_blind, &ctx->pv_resp, &ctx->pv_misc, &ctx->scan_tmp, &ctx->partial_buf, &ctx->pv_static};
   for (devbuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (ctx->h_result) cudaFreeHost(ctx->h_result);
@@ -190,6 +191,8 @@ extern "C" int32_t zkp_ctx_set_option(zkp_ctx* ctx, const char* key, int64_t val
     ctx->overlap = value ? 1 : 0;
   } else if (!strcmp(key, "balance")) {
     ctx->balance = value ? 1 : 0;
+  } else if (!strcmp(key, "share_static_tables")) {
+    ctx->share_static_tables = value ? 1 : 0;
   } else if (!strcmp(key, "bv_compiled")) {
     ctx->bv_compiled = value ? 1 : 0;
   } else if (!strcmp(key, "ingest_variant")) {
@@ -1111,14 +1114,27 @@ extern "C" int32_t zkp_prove_batch(zkp_ctx* ctx, const zkp_statement_desc* sd, c
   const size_t o_prefix = 0, o_pool = pad16(53 * 4), o_lo = pad16(o_pool + pool.size()), o_ll = pad16(o_lo + (size_t)p * 4),
                o_lhs = pad16(o_ll + (size_t)p * 4), o_co = pad16(o_lhs + (size_t)k * 4), o_ts = pad16(o_co + (size_t)(k + 1) * 4),
                o_tp = pad16(o_ts + (size_t)n_terms * 4), o_sl = pad16(o_tp + (size_t)n_terms * 4),
-               blob_sz = pad16(o_sl + (size_t)k * 4) + 16;
+               o_sh = pad16(o_sl + (size_t)k * 4), blob_sz = pad16(o_sh + (size_t)n_terms * 4) + 16;
+  // batch-static bases: the statement's common points are the same for every proof when the caller says so
+  // (points_are_uniform): their constant-time tables are built once and shared
+  // (the caller passes a copy per proof, as the reference's per-proof assignments do: k_pv_gather compares every copy
+  // with proof 0's on the device and the call is redone without sharing if one differs)
+  std::vector<int32_t> term_shared(n_terms, -1);
+  const bool share = ctx->share_static_tables && nc > 0 && N > 1;
+  if (share)
+    for (int q = 0; q < n_terms; q++)
+      if (sd->term_point[q] >= ni) term_shared[q] = sd->term_point[q] - ni;
   std::vector<uint8_t> blob(blob_sz, 0);
   memcpy(&blob[o_prefix], prefix_state, 53 * 4);
   if (!pool.empty()) memcpy(&blob[o_pool], pool.data(), pool.size());
   if (p) { memcpy(&blob[o_lo], loff.data(), (size_t)p * 4); memcpy(&blob[o_ll], llen.data(), (size_t)p * 4); }
   if (k) { memcpy(&blob[o_lhs], sd->lhs, (size_t)k * 4); memcpy(&blob[o_sl], slot.data(), (size_t)k * 4); }
   memcpy(&blob[o_co], sd->cons_off, (size_t)(k + 1) * 4);
-  if (n_terms) { memcpy(&blob[o_ts], sd->term_scalar, (size_t)n_terms * 4); memcpy(&blob[o_tp], sd->term_point, (size_t)n_terms * 4); }
+  if (n_terms) {
+    memcpy(&blob[o_ts], sd->term_scalar, (size_t)n_terms * 4);
+    memcpy(&blob[o_tp], sd->term_point, (size_t)n_terms * 4);
+    memcpy(&blob[o_sh], term_shared.data(), (size_t)n_terms * 4);
+  }
   const size_t total = N * (size_t)n_terms, M = N * (size_t)k;
   ENSURE(ctx, ctx->pv_misc, blob_sz);
   ENSURE(ctx, ctx->pv_limbs, N * (size_t)p * 160 + 160);
@@ -1143,8 +1159,10 @@ extern "C" int32_t zkp_prove_batch(zkp_ctx* ctx, const zkp_statement_desc* sd, c
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->pv_ent.p, entropy, N * 32, cudaMemcpyHostToDevice, st));
   k_init_flags<<<1, 1, 0, st>>>((int*)ctx->flags.p);
   LAUNCH_CHECK(ctx);
+  CUDA_TRY(ctx, cudaMemsetAsync((int*)ctx->flags.p + 2, 0, 8, st));   // flags[2]: a common point differs between proofs
   pv_desc d;
-  d.m = m; d.p = p; d.k = k; d.n_terms = n_terms;
+  d.m = m; d.p = p; d.k = k; d.n_terms = n_terms; d.ni = ni;
+  d.term_shared = (const int32_t*)(dm + o_sh);
   d.label_off = (const uint32_t*)(dm + o_lo);
   d.label_len = (const uint32_t*)(dm + o_ll);
   d.labels = dm + o_pool;
@@ -1172,18 +1190,36 @@ extern "C" int32_t zkp_prove_batch(zkp_ctx* ctx, const zkp_statement_desc* sd, c
     k_pv_gather<<<(unsigned)((gthreads + 255) / 256), 256, 0, st>>>(d, N, (const unsigned long long*)ctx->pv_limbs.p,
                                                                     (const uint8_t*)ctx->pv_blind.p, (uint4*)ctx->in_scalars.p,
                                                                     (uint4*)ctx->niels.p, (unsigned long long*)ctx->aux0.p,
-                                                                    (uint32_t*)ctx->multi.p);
+                                                                    (uint32_t*)ctx->multi.p, share ? (int*)ctx->flags.p + 2 : nullptr);
     LAUNCH_CHECK(ctx);
+    const int32_t* shared_of = share ? d.term_shared : nullptr;
+    uint4* shared_tables = nullptr;
+    if (share) {
+      // tables of the nc batch-static points, built once from proof 0's copy (all copies were compared above)
+      ENSURE(ctx, ctx->pv_static, (size_t)nc * (128 + 1024 + 32 + 32) + 256);
+      uint8_t* ps = (uint8_t*)ctx->pv_static.p;
+      uint4* s_ext = (uint4*)ps;
+      shared_tables = (uint4*)(ps + (size_t)nc * 128);
+      uint4* s_zero = (uint4*)(ps + (size_t)nc * (128 + 1024));            // dummy scalars (zero: canonical)
+      uint4* s_bias = (uint4*)(ps + (size_t)nc * (128 + 1024 + 32));
+      CUDA_TRY(ctx, cudaMemsetAsync(s_zero, 0, (size_t)nc * 32, st));
+      k_limbs_to_ext<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>((const unsigned long long*)ctx->pv_limbs.p + (size_t)ni * 20,
+                                                                   (size_t)nc, s_ext);
+      LAUNCH_CHECK(ctx);
+      k_build_tables<false><<<(unsigned)((nc + 127) / 128), 128, 0, st>>>(s_ext, s_zero, (size_t)nc, 1u, shared_tables, s_bias,
+                                                                          (int*)ctx->flags.p + 2);
+      LAUNCH_CHECK(ctx);
+    }
     if (total) {
       k_build_tables<true><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(
           (const uint4*)ctx->niels.p, (const uint4*)ctx->in_scalars.p, total, (uint32_t)n_terms, (uint4*)ctx->tables.p,
-          (uint4*)ctx->sk0.p, (int*)ctx->flags.p + 2);   // blindings are canonical
+          (uint4*)ctx->sk0.p, (int*)ctx->flags.p + 2, shared_of);   // blindings are canonical
       LAUNCH_CHECK(ctx);
     }
     k_small_msm_ct<true><<<(unsigned)((M + 63) / 64), 64, 0, st>>>((const uint32_t*)ctx->sk0.p, (const uint4*)ctx->tables.p,
                                                                    (const unsigned long long*)ctx->aux0.p,
                                                                    (const uint32_t*)ctx->multi.p, M, (uint32_t)n_terms,
-                                                                   (uint4*)ctx->aux1.p);
+                                                                   (uint4*)ctx->aux1.p, shared_of, shared_tables);
     LAUNCH_CHECK(ctx);
   }
   // (4) commitments into the transcript, challenge, responses (prover.rs:98-109)
@@ -1200,6 +1236,13 @@ extern "C" int32_t zkp_prove_batch(zkp_ctx* ctx, const zkp_statement_desc* sd, c
   CUDA_TRY(ctx, cudaMemcpyAsync(hflags, ctx->flags.p, 16, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(ctx, cudaStreamSynchronize(st));
   if (hflags[1] != 0x7fffffff) return ZKP_ERR_SCALAR;   // a non-canonical secret
+  if (share && hflags[2] != 0) {   // the "common" points were not common after all: per-proof tables for every term
+    ctx->share_static_tables = 0;
+    int32_t rc = zkp_prove_batch(ctx, sd, prefix_state, N, secrets, points, entropy, encodings_out, commitments_out,
+                                 responses_out, blindings_out);
+    ctx->share_static_tables = 1;
+    return rc;
+  }
   return ZKP_OK;
 }
 

@@ -16,7 +16,8 @@
 namespace zkp {
 
 struct pv_desc {       // device copy of the statement (points indexed over instance ++ common, as allocated)
-  int m, p, k, n_terms;
+  int m, p, k, n_terms, ni;
+  const int32_t* term_shared;       // [n_terms] index of the common point a term uses, -1 for an instance point
   const uint32_t* label_off;        // [p]
   const uint32_t* label_len;        // [p]
   const uint8_t* labels;            // label byte pool
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(128) k_pv_blind(pv_desc d, const uint32_t* __r
 __global__ void __launch_bounds__(256) k_pv_gather(pv_desc d, size_t N, const unsigned long long* __restrict__ limbs,
                                                    const uint8_t* __restrict__ blind, uint4* __restrict__ scalars_flat,
                                                    uint4* __restrict__ ext_flat, unsigned long long* __restrict__ offsets,
-                                                   uint32_t* __restrict__ order) {
+                                                   uint32_t* __restrict__ order, int* __restrict__ not_uniform) {
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t T = (size_t)d.n_terms;
   if (t < N * T) {
@@ -89,8 +90,17 @@ __global__ void __launch_bounds__(256) k_pv_gather(pv_desc d, size_t N, const un
     const uint4* src = (const uint4*)(blind + ((size_t)j * d.m + d.term_scalar[q]) * 32);
     scalars_flat[2 * t] = src[0];
     scalars_flat[2 * t + 1] = src[1];
+    const unsigned long long* lp = limbs + ((size_t)j * d.p + d.term_point[q]) * 20;
+    if (not_uniform && d.term_shared[q] >= 0) {
+      // a batch-static base: its table is shared, so this proof's copy must equal proof 0's (public data)
+      const unsigned long long* l0 = limbs + (size_t)d.term_point[q] * 20;
+      unsigned long long diff = 0;
+#pragma unroll
+      for (int i = 0; i < 20; i++) diff |= lp[i] ^ l0[i];
+      if (diff) atomicExch(not_uniform, 1);
+    }
     ge_ext pt;
-    load_ext_limbs51(pt, limbs + ((size_t)j * d.p + d.term_point[q]) * 20);
+    load_ext_limbs51(pt, lp);
     store_ext(ext_flat + 8 * t, pt);
   }
   if (t < N * (size_t)d.k) {

@@ -149,12 +149,29 @@ __device__ __forceinline__ size_t ct_table_index(size_t t, uint32_t T) {
   const size_t j = t / T, r = t % T;
   return ((j >> 5) * T + r) * 64 * 32 + (j & 31);
 }
+// shared_of (batch proving, optional): shared_of[r] >= 0 says that term r of every proof uses the batch-static point with
+// that index, whose table is built ONCE (k_build_tables<false> over the static points) and read by all proofs; such
+// terms only get their biased scalar here.  (in CMZ 21 of the 31 prover terms use batch-static bases.)
 template <bool IL>
 __global__ void __launch_bounds__(128) k_build_tables(const uint4* __restrict__ ext, const uint4* __restrict__ scalars,
                                                       size_t n, uint32_t T, uint4* __restrict__ tables,
-                                                      uint4* __restrict__ biased, int* __restrict__ flags) {
+                                                      uint4* __restrict__ biased, int* __restrict__ flags,
+                                                      const int32_t* __restrict__ shared_of = nullptr) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  {
+    uint32_t s[8], l[8], d[8], bias[8], r[8];
+    load_words8(s, scalars + 2 * i);
+    sc_load_l(l);
+    uint32_t canonical = sub8(d, s, l);
+    if (!canonical) atomicMin(&flags[1], (int)i);
+#pragma unroll
+    for (int k = 0; k < 8; k++) bias[k] = 0x88888888u;
+    add8(r, s, bias);
+    biased[2 * i] = make_uint4(r[0], r[1], r[2], r[3]);
+    biased[2 * i + 1] = make_uint4(r[4], r[5], r[6], r[7]);
+  }
+  if (shared_of && shared_of[i % T] >= 0) return;   // public: depends on the statement only
   const size_t stride = IL ? 32 : 1;
   ge_ext p, m;
   load_ext(p, ext + 8 * i);
@@ -178,29 +195,22 @@ __global__ void __launch_bounds__(128) k_build_tables(const uint4* __restrict__ 
     ge_to_pniels(cur, m);
     put(k, cur);
   }
-  uint32_t s[8], l[8], d[8], bias[8], r[8];
-  load_words8(s, scalars + 2 * i);
-  sc_load_l(l);
-  uint32_t canonical = sub8(d, s, l);
-  if (!canonical) atomicMin(&flags[1], (int)i);
-#pragma unroll
-  for (int k = 0; k < 8; k++) bias[k] = 0x88888888u;
-  add8(r, s, bias);
-  biased[2 * i] = make_uint4(r[0], r[1], r[2], r[3]);
-  biased[2 * i + 1] = make_uint4(r[4], r[5], r[6], r[7]);
 }
 
 template <bool IL>
 __global__ void __launch_bounds__(64) k_small_msm_ct(const uint32_t* __restrict__ biased, const uint4* __restrict__ tables,
                                                      const unsigned long long* __restrict__ offsets,
                                                      const uint32_t* __restrict__ order, size_t M, uint32_t T,
-                                                     uint4* __restrict__ out) {
+                                                     uint4* __restrict__ out,
+                                                     const int32_t* __restrict__ shared_of = nullptr,
+                                                     const uint4* __restrict__ shared_tables = nullptr) {
   size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= M) return;
   const size_t j = order[tid];   // public: MSMs sorted by (public) size so the lanes of a warp do equal work
   const size_t lo = offsets[j], hi = offsets[j + 1];   // public
   // table of the first term; consecutive terms of one MSM belong to one proof, so their tables are `tstep` apart
   const size_t tab0 = ct_table_index<IL>(lo, T), tstep = IL ? (size_t)64 * 32 : 64;
+  const uint32_t r0 = shared_of ? (uint32_t)(lo % T) : 0u;   // index of the first term within its proof
   ge_ext acc;
   ge_identity(acc);
 #pragma unroll 1
@@ -218,8 +228,15 @@ __global__ void __launch_bounds__(64) k_small_msm_ct(const uint32_t* __restrict_
       // constant-time lookup: start from the identity, scan all eight entries
       ge_pniels sel;
       fe_one(sel.YplusX); fe_one(sel.YminusX); fe_one(sel.Z); fe_zero(sel.T2d);
-      const size_t stride = IL ? 32 : 1;
+      size_t stride = IL ? 32 : 1;
       const uint4* tab = tables + tab0 + (t - lo) * tstep;   // public: depends on the term index only
+      if (shared_of) {   // batch-static base: one table for all proofs (the whole warp reads the same addresses)
+        const int32_t sh = shared_of[r0 + (uint32_t)(t - lo)];
+        if (sh >= 0) {
+          tab = shared_tables + (size_t)sh * 64;
+          stride = 1;
+        }
+      }
 #pragma unroll 1
       for (uint32_t e = 1; e <= 8; e++) {
         uint32_t mask = 0u - (uint32_t)(mag == e);
