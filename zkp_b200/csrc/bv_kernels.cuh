@@ -55,6 +55,60 @@ __device__ __forceinline__ void store_scl(uint8_t* dst, const scl& s) {
   p[1] = make_uint4(s.v[4], s.v[5], s.v[6], s.v[7]);
 }
 
+// Weights and coefficient fold of proof j, shared by both front-end kernels:
+//   rho_i = bytes [16 i, 16 i + 16) of SHAKE256(seed || le64(j))  (stand-in for thread_rng, batch_verifier.rs:179)
+//   fold: batch_verifier.rs:176-206.  inst / stat accumulate the coefficients of the instance / static points.
+__device__ __forceinline__ void bv_weights_and_fold(const bv_desc& d, size_t j, size_t N, const scl& minus_c,
+                                                    const uint8_t* __restrict__ rho_seed,
+                                                    const uint8_t* __restrict__ responses, uint8_t* __restrict__ msm_scalars,
+                                                    scl* inst, scl* stat, int* __restrict__ flags) {
+  uint8_t msg[40];
+#pragma unroll
+  for (int b = 0; b < 32; b++) msg[b] = rho_seed[b];
+#pragma unroll
+  for (int b = 0; b < 8; b++) msg[32 + b] = (uint8_t)((unsigned long long)j >> (8 * b));
+  uint8_t all[16 * ZKP_BV_MAX_CONS];
+  shake256_short(all, (uint32_t)(16 * d.k), msg, 40);
+  for (int i = 0; i < d.k; i++) {
+    scl rho;
+#pragma unroll
+    for (int w = 0; w < 4; w++)
+      rho.v[w] = (uint32_t)all[16 * i + 4 * w] | ((uint32_t)all[16 * i + 4 * w + 1] << 8) |
+                 ((uint32_t)all[16 * i + 4 * w + 2] << 16) | ((uint32_t)all[16 * i + 4 * w + 3] << 24);
+    rho.v[4] = rho.v[5] = rho.v[6] = rho.v[7] = 0;
+    scl t;
+    scl_neg(t, rho);   // instance_coeffs[(num_i + i, j)] -= rho
+    store_scl(msm_scalars + ((size_t)d.nc + (size_t)(d.ni + i) * N + j) * 32, t);
+    scl_mul(t, rho, minus_c);
+    if (d.lhs_kind[i]) scl_add(stat[d.lhs_idx[i]], stat[d.lhs_idx[i]], t);
+    else scl_add(inst[d.lhs_idx[i]], inst[d.lhs_idx[i]], t);
+    for (int q = d.cons_off[i]; q < d.cons_off[i + 1]; q++) {
+      scl resp;
+      load_scl(resp, responses + ((size_t)j * d.m + d.term_scalar[q]) * 32);
+      if (!scl_is_canonical(resp.v)) atomicMin(&flags[1], (int)j);
+      scl_mul(t, rho, resp);
+      const int pi = d.term_pidx[q];
+      if (d.term_pkind[q]) scl_add(stat[pi], stat[pi], t);
+      else scl_add(inst[pi], inst[pi], t);
+    }
+  }
+  for (int i = 0; i < d.ni; i++) store_scl(msm_scalars + ((size_t)d.nc + (size_t)i * N + j) * 32, inst[i]);
+}
+// block partial sums of the static coefficients (all 128 threads of the block take part)
+__device__ __forceinline__ void bv_static_block_sums(const bv_desc& d, const scl* stat, scl* red,
+                                                     uint8_t* __restrict__ static_part, unsigned block_index) {
+  for (int sidx = 0; sidx < d.nc; sidx++) {
+    red[threadIdx.x] = stat[sidx];
+    __syncthreads();
+    for (int off = 64; off >= 1; off >>= 1) {
+      if ((int)threadIdx.x < off) scl_add(red[threadIdx.x], red[threadIdx.x], red[threadIdx.x + off]);
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) store_scl(static_part + ((size_t)block_index * d.nc + sidx) * 32, red[0]);
+    __syncthreads();
+  }
+}
+
 // Per proof j: replay the transcript, derive the challenge, draw the weights, fold the coefficients.
 //   prefix        strobe state shared by all proofs (user transcript + dom-sep + scalar labels), 53 words
 //   instance_enc  [ni][N][32]   commitments [N][k][32]   responses [N][m][32]   common_enc [nc][32]
@@ -119,51 +173,9 @@ __global__ void __launch_bounds__(128) k_bv_prepare(bv_desc d, const uint32_t* _
     scl_from_wide(c, wide);
     scl_neg(minus_c, c);
     if (minus_c_out) store_scl(minus_c_out + j * 32, minus_c);
-    // ---- weights: rho_i = bytes [16 i, 16 i + 16) of SHAKE256(seed || le64(j))  (stand-in for thread_rng, :179) ----
-    uint8_t msg[40];
-#pragma unroll
-    for (int b = 0; b < 32; b++) msg[b] = rho_seed[b];
-#pragma unroll
-    for (int b = 0; b < 8; b++) msg[32 + b] = (uint8_t)((unsigned long long)j >> (8 * b));
-    uint8_t all[16 * ZKP_BV_MAX_CONS];
-    shake256_short(all, (uint32_t)(16 * d.k), msg, 40);
-    // ---- coefficient fold (batch_verifier.rs:176-206) ----
-    for (int i = 0; i < d.k; i++) {
-      scl rho;
-#pragma unroll
-      for (int w = 0; w < 4; w++)
-        rho.v[w] = (uint32_t)all[16 * i + 4 * w] | ((uint32_t)all[16 * i + 4 * w + 1] << 8) |
-                   ((uint32_t)all[16 * i + 4 * w + 2] << 16) | ((uint32_t)all[16 * i + 4 * w + 3] << 24);
-      rho.v[4] = rho.v[5] = rho.v[6] = rho.v[7] = 0;
-      scl t;
-      scl_neg(t, rho);   // instance_coeffs[(num_i + i, j)] -= rho
-      store_scl(msm_scalars + ((size_t)d.nc + (size_t)(d.ni + i) * N + j) * 32, t);
-      scl_mul(t, rho, minus_c);
-      if (d.lhs_kind[i]) scl_add(stat[d.lhs_idx[i]], stat[d.lhs_idx[i]], t);
-      else scl_add(inst[d.lhs_idx[i]], inst[d.lhs_idx[i]], t);
-      for (int q = d.cons_off[i]; q < d.cons_off[i + 1]; q++) {
-        scl resp;
-        load_scl(resp, responses + ((size_t)j * d.m + d.term_scalar[q]) * 32);
-        if (!scl_is_canonical(resp.v)) atomicMin(&flags[1], (int)j);
-        scl_mul(t, rho, resp);
-        const int pi = d.term_pidx[q];
-        if (d.term_pkind[q]) scl_add(stat[pi], stat[pi], t);
-        else scl_add(inst[pi], inst[pi], t);
-      }
-    }
-    for (int i = 0; i < d.ni; i++) store_scl(msm_scalars + ((size_t)d.nc + (size_t)i * N + j) * 32, inst[i]);
+    bv_weights_and_fold(d, j, N, minus_c, rho_seed, responses, msm_scalars, inst, stat, flags);
   }
-  // ---- block partial sums of the static coefficients ----
-  for (int sidx = 0; sidx < d.nc; sidx++) {
-    red[threadIdx.x] = stat[sidx];
-    __syncthreads();
-    for (int off = 64; off >= 1; off >>= 1) {
-      if ((int)threadIdx.x < off) scl_add(red[threadIdx.x], red[threadIdx.x], red[threadIdx.x + off]);
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) store_scl(static_part + ((size_t)(block_base + blockIdx.x) * d.nc + sidx) * 32, red[0]);
-    __syncthreads();
-  }
+  bv_static_block_sums(d, stat, red, static_part, block_base + blockIdx.x);
 }
 
 // -----------------------------------------------------------------------------------------------------------------
@@ -260,50 +272,9 @@ __global__ void __launch_bounds__(128) k_bv_prepare2(bv_desc d, const uint32_t* 
     scl_from_wide(c, wide);
     scl_neg(minus_c, c);
     if (minus_c_out) store_scl(minus_c_out + j * 32, minus_c);
-    // ---- weights and coefficient fold: identical to k_bv_prepare ----
-    uint8_t msg[40];
-#pragma unroll
-    for (int b = 0; b < 32; b++) msg[b] = rho_seed[b];
-#pragma unroll
-    for (int b = 0; b < 8; b++) msg[32 + b] = (uint8_t)((unsigned long long)j >> (8 * b));
-    uint8_t all[16 * ZKP_BV_MAX_CONS];
-    shake256_short(all, (uint32_t)(16 * d.k), msg, 40);
-    for (int i = 0; i < d.k; i++) {
-      scl rho;
-#pragma unroll
-      for (int w4 = 0; w4 < 4; w4++)
-        rho.v[w4] = (uint32_t)all[16 * i + 4 * w4] | ((uint32_t)all[16 * i + 4 * w4 + 1] << 8) |
-                    ((uint32_t)all[16 * i + 4 * w4 + 2] << 16) | ((uint32_t)all[16 * i + 4 * w4 + 3] << 24);
-      rho.v[4] = rho.v[5] = rho.v[6] = rho.v[7] = 0;
-      scl t;
-      scl_neg(t, rho);   // instance_coeffs[(num_i + i, j)] -= rho
-      store_scl(msm_scalars + ((size_t)d.nc + (size_t)(d.ni + i) * N + j) * 32, t);
-      scl_mul(t, rho, minus_c);
-      if (d.lhs_kind[i]) scl_add(stat[d.lhs_idx[i]], stat[d.lhs_idx[i]], t);
-      else scl_add(inst[d.lhs_idx[i]], inst[d.lhs_idx[i]], t);
-      for (int q = d.cons_off[i]; q < d.cons_off[i + 1]; q++) {
-        scl resp;
-        load_scl(resp, responses + ((size_t)j * d.m + d.term_scalar[q]) * 32);
-        if (!scl_is_canonical(resp.v)) atomicMin(&flags[1], (int)j);
-        scl_mul(t, rho, resp);
-        const int pi = d.term_pidx[q];
-        if (d.term_pkind[q]) scl_add(stat[pi], stat[pi], t);
-        else scl_add(inst[pi], inst[pi], t);
-      }
-    }
-    for (int i = 0; i < d.ni; i++) store_scl(msm_scalars + ((size_t)d.nc + (size_t)i * N + j) * 32, inst[i]);
+    bv_weights_and_fold(d, j, N, minus_c, rho_seed, responses, msm_scalars, inst, stat, flags);
   }
-  // ---- block partial sums of the static coefficients ----
-  for (int sidx = 0; sidx < d.nc; sidx++) {
-    red[threadIdx.x] = stat[sidx];
-    __syncthreads();
-    for (int off = 64; off >= 1; off >>= 1) {
-      if ((int)threadIdx.x < off) scl_add(red[threadIdx.x], red[threadIdx.x], red[threadIdx.x + off]);
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) store_scl(static_part + ((size_t)(block_base + blockIdx.x) * d.nc + sidx) * 32, red[0]);
-    __syncthreads();
-  }
+  bv_static_block_sums(d, stat, red, static_part, block_base + blockIdx.x);
 }
 
 // self-test: Merlin's published conformance vector computed by one device thread (zkp_selftest_hash)
