@@ -170,6 +170,13 @@ int32_t zkp_prove_batch(zkp_ctx* ctx, const zkp_statement_desc* st, const uint32
                         const uint8_t* secrets, const uint64_t* points, const uint8_t* entropy, uint8_t* encodings_out,
                         uint8_t* commitments_out, uint8_t* responses_out, uint8_t* blindings_out);
 
+/* Test hook (no GPU needed): compiles the batch-verification transcript script of `st` (what zkp_batch_verify_proofs
+ * hands to the device) and executes it on the host for ONE proof (instance_enc[ni][32], commitments[k][32]):
+ * challenge_out64 receives the 64 challenge bytes, *n_blocks_out (optional) the number of Keccak-f blocks.          */
+int32_t zkp_selftest_bv_script(const zkp_statement_desc* st, const uint32_t* prefix_state, const uint8_t* instance_enc,
+                               const uint8_t* common_enc, const uint8_t* commitments, uint8_t* challenge_out64,
+                               int32_t* n_blocks_out);
+
 /* Self-test of the device hashing code: out32 receives Merlin's published conformance vector (a8c933f5...). */
 int32_t zkp_selftest_hash(zkp_ctx* ctx, uint8_t* out32);
 

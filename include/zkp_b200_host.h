@@ -99,6 +99,7 @@ zkph_transcript* zkph_transcript_new(const uint8_t* label, size_t len);
 zkph_transcript* zkph_transcript_clone(const zkph_transcript* t);
 void zkph_transcript_free(zkph_transcript* t);
 void zkph_transcript_append_message(zkph_transcript* t, const uint8_t* label, size_t llen, const uint8_t* msg, size_t mlen);
+void zkph_transcript_export_state(const zkph_transcript* t, uint32_t out53[53]);   /* the prefix_state of zkp_b200.h */
 void zkph_transcript_challenge_bytes(zkph_transcript* t, const uint8_t* label, size_t llen, uint8_t* out, size_t n);
 int32_t zkph_prove_t(zkp_ctx* ctx, const zkph_statement* st, zkph_transcript* t, const uint8_t* secrets,
                      const uint64_t* points, const uint8_t* rng_seed, size_t seed_len, int32_t batchable,

@@ -115,3 +115,72 @@ def test_wire_format_matches_oracle_and_rejects_what_bincode_rejects():
         PT.parse_compact(ser[:-5], m)
     with pytest.raises(PT.MalformedProof):
         PT.parse_compact(L.to_bytes(32, "little") + ser[32:], m)             # non-canonical challenge
+
+
+def test_compiled_transcript_script_on_the_host():
+    """The symbolic STROBE that compiles a batch's transcript script for the device (api.cu bv_script, executed here on
+    the host by zkp_selftest_bv_script) gives the challenge bytes of the byte-wise Merlin (host mirror AND oracle) for
+    statements whose label lengths walk the per-proof values across every alignment of the 166-byte rate, including
+    values split over two blocks and headers ending exactly on a block boundary."""
+    import numpy as np
+    lib = native.load()
+    hl = PT._lib()
+    vp, sz = ctypes.c_void_p, ctypes.c_size_t
+    hl.zkph_transcript_export_state.argtypes = [vp, vp]
+
+    class Desc(ctypes.Structure):
+        _fields_ = [("m", ctypes.c_int32), ("ni", ctypes.c_int32), ("nc", ctypes.c_int32), ("k", ctypes.c_int32),
+                    ("labels", ctypes.c_char_p), ("lhs", vp), ("cons_off", vp), ("term_scalar", vp), ("term_point", vp)]
+    lib.zkp_selftest_bv_script.argtypes = [ctypes.POINTER(Desc), vp, vp, vp, vp, vp, ctypes.POINTER(ctypes.c_int32)]
+    lib.zkp_selftest_bv_script.restype = ctypes.c_int32
+    rnd = random.Random(77)
+    seen_blocks = set()
+    for trial in range(120):
+        ni, nc, k = rnd.randrange(0, 5), rnd.randrange(0, 4), rnd.randrange(0, 6)
+        if ni + nc == 0:
+            nc = 1
+        names = [("v%d" % i) + "x" * rnd.choice([0, 1, 2, 5, 17, 40, 100, 160, 170]) for i in range(ni + nc)]
+        lhs = [rnd.randrange(ni + nc) for _ in range(k)]
+        tl = b"T" * rnd.randrange(1, 40)
+        plabel = b"proof" + b"p" * rnd.randrange(0, 30)
+        secrets = ["s%d" % i for i in range(rnd.randrange(0, 4))]
+        inst = [rnd.randbytes(32) for _ in range(ni)]
+        comm = [rnd.randbytes(32) for _ in range(nc)]
+        coms = [rnd.randbytes(32) for _ in range(k)]
+        # reference: byte-wise Merlin (oracle), in the order of batch_verifier.rs / macros.rs:348-365
+        t = OM.Transcript(tl)
+        OT.domain_sep(t, plabel)
+        for s_ in secrets:
+            OT.append_scalar_var(t, s_.encode())
+        # prefix state from the host mirror's transcript fed the same bytes
+        h = hl.zkph_transcript_new(tl, len(tl))
+        hl.zkph_transcript_append_message(h, b"dom-sep", 7, b"schnorrzkp/1.0/ristretto255", 27)
+        hl.zkph_transcript_append_message(h, b"dom-sep", 7, plabel, len(plabel))
+        for s_ in secrets:
+            hl.zkph_transcript_append_message(h, b"scvar", 5, s_.encode(), len(s_))
+        prefix = (ctypes.c_uint32 * 53)()
+        hl.zkph_transcript_export_state(h, prefix)
+        for i in range(ni):
+            t.append_message(b"ptvar", names[i].encode())
+            t.append_message(b"val", inst[i])
+        for i in range(nc):
+            t.append_message(b"ptvar", names[ni + i].encode())
+            t.append_message(b"val", comm[i])
+        for c in range(k):
+            t.append_message(b"blindcom", names[lhs[c]].encode())
+            t.append_message(b"val", coms[c])
+        expected = t.challenge_bytes(b"chal", 64)
+        hl.zkph_transcript_free(h)
+        lab = b"".join(n.encode() + b"\0" for n in names)
+        lhs_a = np.array(lhs, dtype=np.int32)
+        off_a = np.zeros(k + 1, dtype=np.int32)
+        empty = np.zeros(1, dtype=np.int32)
+        d = Desc(len(secrets), ni, nc, k, lab, lhs_a.ctypes.data, off_a.ctypes.data, empty.ctypes.data, empty.ctypes.data)
+        out = ctypes.create_string_buffer(64)
+        nb = ctypes.c_int32(0)
+        ib, cb, kb = b"".join(inst) or b"\0", b"".join(comm) or b"\0", b"".join(coms) or b"\0"
+        rc = lib.zkp_selftest_bv_script(ctypes.byref(d), prefix, ib, cb, kb, out, ctypes.byref(nb))
+        assert rc == 0
+        assert out.raw == expected, (trial, ni, nc, k, [len(n) for n in names])
+        seen_blocks.add(nb.value)
+    assert len(seen_blocks) >= 4        # scripts of very different lengths were exercised

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../include/zkp_b200.h"
+#include "host/merlin.hpp"
 #include "kernels.cuh"
 #include "small_msm.cuh"
 #include "bench_fe.cuh"
@@ -834,6 +835,70 @@ struct bv_script {
   }
 };
 
+// the per-proof script of BatchVerifier (batch_verifier.rs:100-134, :152-167): instance points, static points, commitments,
+// challenge -- in the allocation order of the define_proof! expansion (macros.rs:348-365)
+static void bv_compile_batch_verify(bv_script& script, const zkp_statement_desc* sd, const uint8_t* common_enc) {
+  const int ni = sd->ni, nc = sd->nc, k = sd->k;
+  const char* q = sd->labels;
+  std::vector<std::string> names;
+  for (int i = 0; i < ni + nc; i++) {
+    names.push_back(std::string(q));
+    q += names.back().size() + 1;
+  }
+  for (int i = 0; i < ni; i++) {
+    script.append_const("ptvar", (const uint8_t*)names[i].data(), names[i].size());
+    script.append_value("val", 0u, (uint32_t)i);
+  }
+  for (int i = 0; i < nc; i++) {
+    script.append_const("ptvar", (const uint8_t*)names[ni + i].data(), names[ni + i].size());
+    script.append_const("val", common_enc + 32 * (size_t)i, 32);
+  }
+  for (int c = 0; c < k; c++) {
+    const std::string& nm = names[sd->lhs[c]];
+    script.append_const("blindcom", (const uint8_t*)nm.data(), nm.size());
+    script.append_value("val", 2u, (uint32_t)c);
+  }
+  script.challenge("chal", 64);
+}
+
+// Host execution of a compiled script for ONE proof (what a thread of k_bv_prepare2 does): the 64 challenge bytes.
+// Test hook: lets the CPU suite check the script compiler against the byte-wise Merlin of host/merlin.cpp.
+extern "C" int32_t zkp_selftest_bv_script(const zkp_statement_desc* sd, const uint32_t* prefix_state,
+                                          const uint8_t* instance_enc, const uint8_t* common_enc,
+                                          const uint8_t* commitments, uint8_t* challenge_out64, int32_t* n_blocks_out) {
+  if (!sd || !prefix_state || !challenge_out64) return ZKP_ERR_SIZE;
+  for (int c = 0; c < sd->k; c++)
+    if (sd->lhs[c] < 0 || sd->lhs[c] >= sd->ni + sd->nc) return ZKP_ERR_SIZE;
+  bv_script script(prefix_state[50], prefix_state[51]);
+  bv_compile_batch_verify(script, sd, common_enc);
+  uint64_t st[25];
+  for (int i = 0; i < 25; i++) st[i] = (uint64_t)prefix_state[2 * i] | ((uint64_t)prefix_state[2 * i + 1] << 32);
+  const int nb = (int)(script.tmpl.size() / 21);
+  for (int b = 0; b < nb; b++) {
+    uint8_t blk[168];
+    for (int l = 0; l < 21; l++)
+      for (int x = 0; x < 8; x++) blk[8 * l + x] = (uint8_t)(script.tmpl[(size_t)b * 21 + l] >> (8 * x));
+    for (uint32_t si = script.seg_start[b]; si < script.seg_start[b + 1]; si++) {
+      const bv_seg& sg = script.segs[si];
+      const uint8_t* src = sg.kind == 0 ? instance_enc + 32 * (size_t)sg.idx : commitments + 32 * (size_t)sg.idx;
+      for (uint32_t x = 0; x < sg.len; x++) {
+        const int pos = sg.shift + (int)(sg.src_off + x);
+        if (pos < 0 || pos >= 166) return ZKP_ERR_CUDA;   // a segment must stay inside the rate
+        blk[pos] ^= src[sg.src_off + x];
+      }
+    }
+    for (int l = 0; l < 21; l++) {
+      uint64_t v = 0;
+      for (int x = 7; x >= 0; x--) v = (v << 8) | blk[8 * l + x];
+      st[l] ^= v;
+    }
+    zkp_host::keccak_f1600(st);
+  }
+  for (int i = 0; i < 64; i++) challenge_out64[i] = (uint8_t)(st[i >> 3] >> (8 * (i & 7)));
+  if (n_blocks_out) *n_blocks_out = nb;
+  return ZKP_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // batch verification from proofs: transcripts, challenges, weights and coefficient fold on the device
 // ---------------------------------------------------------------------------------------------------------
@@ -890,28 +955,7 @@ extern "C" int32_t zkp_batch_verify_proofs(zkp_ctx* ctx, const zkp_statement_des
   }
   // the compiled transcript script (k_bv_prepare2): allocation order instance, static, then the commitments
   bv_script script(prefix_state[50], prefix_state[51]);
-  {
-    const char* q = sd->labels;
-    std::vector<std::string> names;
-    for (int i = 0; i < ni + nc; i++) {
-      names.push_back(std::string(q));
-      q += names.back().size() + 1;
-    }
-    for (int i = 0; i < ni; i++) {
-      script.append_const("ptvar", (const uint8_t*)names[i].data(), names[i].size());
-      script.append_value("val", 0u, (uint32_t)i);
-    }
-    for (int i = 0; i < nc; i++) {
-      script.append_const("ptvar", (const uint8_t*)names[ni + i].data(), names[ni + i].size());
-      script.append_const("val", common_enc + 32 * (size_t)i, 32);
-    }
-    for (int c = 0; c < k; c++) {
-      const std::string& nm = names[sd->lhs[c]];
-      script.append_const("blindcom", (const uint8_t*)nm.data(), nm.size());
-      script.append_value("val", 2u, (uint32_t)c);
-    }
-    script.challenge("chal", 64);
-  }
+  bv_compile_batch_verify(script, sd, common_enc);
   const int script_blocks = (int)(script.tmpl.size() / 21);
   // one small device blob: prefix(53 w) | rho_seed(32 B) | pool | ops | int arrays | block templates | segments
   auto pad16 = [](size_t x) { return (x + 15) & ~(size_t)15; };

@@ -53,6 +53,7 @@ extern "C" void zkph_transcript_append_message(zkph_transcript* t, const uint8_t
                                                size_t mlen) {
   t->t.append_message(label, llen, msg, mlen);
 }
+extern "C" void zkph_transcript_export_state(const zkph_transcript* t, uint32_t out53[53]) { t->t.export_state(out53); }
 extern "C" void zkph_transcript_challenge_bytes(zkph_transcript* t, const uint8_t* label, size_t llen, uint8_t* out,
                                                 size_t n) {
   t->t.challenge_bytes(label, llen, out, n);
