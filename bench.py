@@ -250,8 +250,11 @@ def main():
         print(json.dumps(line))
         return
 
-    # NCCL prints its version banner / debug lines to stdout by default: keep stdout for the one JSON line
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # stdout carries exactly ONE JSON line: libraries that write to file descriptor 1 from C (NCCL prints its version
+    # banner there) are sent to stderr for the duration of the run, and the line is written to the saved descriptor
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     from zkp_b200 import Engine
@@ -503,7 +506,7 @@ def main():
                 "what": "Merlin transcripts, challenges, per-proof weights, coefficient fold AND the MSM on the GPU "
                         "(SURVEY 8f rows f1+f2); %d distinct real CMZ proofs tiled to 2^%d batch entries with distinct "
                         "weights; accept checked, tampered response rejected" % (proofs_leg["distinct_real_proofs"], args.log2_proofs)}
-        print(json.dumps(line))
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

@@ -263,3 +263,30 @@ def test_device_hash_and_scalar_logic(lib):
     for w in [0, 2**512 - 1, (L << 256) - 1, L << 200, L * L - 1] + [rnd.getrandbits(512) for _ in range(300)]:
         lib.emul_scl_wide(o, w.to_bytes(64, "little"))
         assert int.from_bytes(o.raw, "little") == w % L
+
+
+def test_field_ops_property_based(lib):
+    """hypothesis over the whole 256-bit input space, biased towards limb boundaries: the integer field ops (constant- and
+    variable-time tails) and their FP64 twins agree with big-int arithmetic mod p."""
+    from hypothesis import given, settings, strategies as st_
+    lib.emul_fe64_sq.restype = ctypes.c_double
+    lib.emul_fe64_mul.restype = ctypes.c_double
+    limb = st_.one_of(st_.sampled_from([0, 1, 2, 18, 19, 37, 38, 2**31 - 1, 2**31, 2**32 - 39, 2**32 - 38, 2**32 - 19, 2**32 - 2,
+                                        2**32 - 1]), st_.integers(0, 2**32 - 1))
+    elem = st_.lists(limb, min_size=8, max_size=8).map(lambda ws: sum(w << (32 * i) for i, w in enumerate(ws)))
+
+    @settings(max_examples=300, deadline=None)
+    @given(elem, elem)
+    def check(a, b):
+        r = ctypes.create_string_buffer(32)
+        assert _c2(lib.emul_fe_mul, a, b) % P == a * b % P
+        assert _c2(lib.emul_fe_mul_vt, a, b) == _c2(lib.emul_fe_mul, a, b)
+        assert _c1(lib.emul_fe_sq_vt, a) % P == a * a % P
+        assert _c2(lib.emul_fe_add_vt, a, b) % P == (a + b) % P and _c2(lib.emul_fe_add_vt, a, b) == _c2(lib.emul_fe_add, a, b)
+        assert _c2(lib.emul_fe_sub_vt, a, b) % P == (a - b) % P and _c2(lib.emul_fe_sub_vt, a, b) == _c2(lib.emul_fe_sub, a, b)
+        assert _c1(lib.emul_fe_canon, a) == a % P
+        assert lib.emul_fe64_mul(r, a.to_bytes(32, "little"), b.to_bytes(32, "little")) <= 2**21 + 2**13
+        assert int.from_bytes(r.raw, "little") % P == a * b % P
+        lib.emul_fe64_sq(r, a.to_bytes(32, "little"), 3)
+        assert int.from_bytes(r.raw, "little") % P == pow(a, 8, P)
+    check()
