@@ -153,6 +153,7 @@ void emul_transcript_rng(uint8_t* out, const uint8_t* witnesses, int n_w, const 
 }
 void emul_shake(uint8_t* out, uint32_t n, const uint8_t* msg, uint32_t len) { shake256_short(out, n, msg, len); }
 void emul_scl_mul(uint8_t* r, const uint8_t* a, const uint8_t* b) { scl x, y, z; memcpy(x.v, a, 32); memcpy(y.v, b, 32); scl_mul(z, x, y); memcpy(r, z.v, 32); }
+void emul_scl_mul_128(uint8_t* r, const uint8_t* a, const uint8_t* b) { scl x, y, z; memcpy(x.v, a, 32); memcpy(y.v, b, 32); scl_mul_128(z, x, y); memcpy(r, z.v, 32); }
 void emul_scl_add(uint8_t* r, const uint8_t* a, const uint8_t* b) { scl x, y, z; memcpy(x.v, a, 32); memcpy(y.v, b, 32); scl_add(z, x, y); memcpy(r, z.v, 32); }
 void emul_scl_sub(uint8_t* r, const uint8_t* a, const uint8_t* b) { scl x, y, z; memcpy(x.v, a, 32); memcpy(y.v, b, 32); scl_sub(z, x, y); memcpy(r, z.v, 32); }
 void emul_scl_wide(uint8_t* r, const uint8_t* a64) { scl z; scl_from_wide(z, a64); memcpy(r, z.v, 32); }

@@ -260,6 +260,11 @@ def test_device_hash_and_scalar_logic(lib):
                           (lib.emul_scl_sub, lambda x, y: x - y)):
                 f(o, a.to_bytes(32, "little"), b.to_bytes(32, "little"))
                 assert int.from_bytes(o.raw, "little") == op(a, b) % L
+    # the 128-bit-weight product of the coefficient fold (scl_mul_128: 4 x 8 limbs, short reduction)
+    for a in [0, 1, 2**128 - 1, 2**127, 2**64, 2**128 - 2**64] + [rnd.getrandbits(128) for _ in range(300)]:
+        for b in [0, 1, L - 1, L - 2, 2**252 - 1, 2**252, L // 2] + [rnd.randrange(L) for _ in range(4)]:
+            lib.emul_scl_mul_128(o, a.to_bytes(32, "little"), b.to_bytes(32, "little"))
+            assert int.from_bytes(o.raw, "little") == a * b % L, (a, b)
     for w in [0, 2**512 - 1, (L << 256) - 1, L << 200, L * L - 1] + [rnd.getrandbits(512) for _ in range(300)]:
         lib.emul_scl_wide(o, w.to_bytes(64, "little"))
         assert int.from_bytes(o.raw, "little") == w % L

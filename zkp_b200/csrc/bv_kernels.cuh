@@ -79,14 +79,14 @@ __device__ __forceinline__ void bv_weights_and_fold(const bv_desc& d, size_t j, 
     scl t;
     scl_neg(t, rho);   // instance_coeffs[(num_i + i, j)] -= rho
     store_scl(msm_scalars + ((size_t)d.nc + (size_t)(d.ni + i) * N + j) * 32, t);
-    scl_mul(t, rho, minus_c);
+    scl_mul_128(t, rho, minus_c);
     if (d.lhs_kind[i]) scl_add(stat[d.lhs_idx[i]], stat[d.lhs_idx[i]], t);
     else scl_add(inst[d.lhs_idx[i]], inst[d.lhs_idx[i]], t);
     for (int q = d.cons_off[i]; q < d.cons_off[i + 1]; q++) {
       scl resp;
       load_scl(resp, responses + ((size_t)j * d.m + d.term_scalar[q]) * 32);
       if (!scl_is_canonical(resp.v)) atomicMin(&flags[1], (int)j);
-      scl_mul(t, rho, resp);
+      scl_mul_128(t, rho, resp);
       const int pi = d.term_pidx[q];
       if (d.term_pkind[q]) scl_add(stat[pi], stat[pi], t);
       else scl_add(inst[pi], inst[pi], t);
