@@ -165,7 +165,8 @@ int32_t zkp_partials_verdict(zkp_ctx* ctx, const uint64_t* partial_limbs, size_t
  * allocation order instance ++ common), entropy[N][32] -> encodings_out[N][p][32], commitments_out[N][k][32],
  * responses_out[N][m][32]; blindings_out[N][m][32] optional (parity tests).  prefix_state as for
  * zkp_batch_verify_proofs.  Proof j equals what the reference's prover produces from the same transcript, secrets and
- * entropy.  Returns ZKP_ERR_SCALAR for a non-canonical secret.                                                     */
+ * entropy.  Batches larger than the "prove_chunk" option (default 2^17 proofs) run as slices over one workspace.
+ * Returns ZKP_ERR_SCALAR for a non-canonical secret.                                                               */
 int32_t zkp_prove_batch(zkp_ctx* ctx, const zkp_statement_desc* st, const uint32_t* prefix_state, size_t N,
                         const uint8_t* secrets, const uint64_t* points, const uint8_t* entropy, uint8_t* encodings_out,
                         uint8_t* commitments_out, uint8_t* responses_out, uint8_t* blindings_out);

@@ -287,6 +287,13 @@ def test_prove_many_device_front_end_matches_host_and_oracle(engine):
     e_h, c_h, r_h = st.prove_many(engine, b"CMZ", mixed_sec, mixed_pts, entropy, threads=2)
     assert (e_m == e_h).all() and (c_m == c_h).all() and (r_m == r_h).all()
     st.verify_batchable(engine, (c_m[N - 1], r_m[N - 1]), b"CMZ", e_m[N - 1], b"rho")
+    # large batches run as slices (here: 3 proofs per slice, a ragged last slice): same bytes
+    engine.set_option("prove_chunk", 3)
+    try:
+        e_s, c_s, r_s = st.prove_many_device(engine, b"CMZ", sec_arr, pts_arr, entropy)
+    finally:
+        engine.set_option("prove_chunk", 1 << 17)
+    assert (e_s == enc_d).all() and (c_s == com_d).all() and (r_s == resp_d).all()
     # N = 1 and the empty batch
     e1, c1, r1 = st.prove_many_device(engine, b"CMZ", sec_arr[:1], pts_arr[:1], entropy[:1])
     assert (e1 == enc_h[:1]).all() and (c1 == com_h[:1]).all() and (r1 == resp_h[:1]).all()

@@ -57,6 +57,7 @@ struct zkp_ctx {
   int overlap = 0;   // measured: no gain on B200 (159.2 vs 159.9 ms per step), kept as an option
   int balance = 1;     // size-ordered work items in the bucket accumulation (equal-length items share a warp)
   void* partial_out = nullptr;   // when set, k_finish also stores the MSM result as an extended point (single-verdict mode)
+  size_t prove_chunk = (size_t)1 << 17;   // proofs per slice of zkp_prove_batch (4 GB of tables for CMZ)
   int share_static_tables = 1;   // batch proving: one constant-time table per batch-static point
   int bv_compiled = 1;      // batch-verification front end: host-compiled transcript script (k_bv_prepare2)
   int ingest_variant = 2;   // occupancy point of k_ingest2 (kernels.cuh ZKP_INGEST_*)
@@ -192,6 +193,9 @@ extern "C" int32_t zkp_ctx_set_option(zkp_ctx* ctx, const char* key, int64_t val
     ctx->overlap = value ? 1 : 0;
   } else if (!strcmp(key, "balance")) {
     ctx->balance = value ? 1 : 0;
+  } else if (!strcmp(key, "prove_chunk")) {
+    if (value < 1) return ZKP_ERR_SIZE;
+    ctx->prove_chunk = (size_t)value;
   } else if (!strcmp(key, "share_static_tables")) {
     ctx->share_static_tables = value ? 1 : 0;
   } else if (!strcmp(key, "bv_compiled")) {
@@ -1128,7 +1132,21 @@ extern "C" int32_t zkp_prove_batch(zkp_ctx* ctx, const zkp_statement_desc* sd, c
   if ((m && (!secrets || !responses_out)) || (p && (!points || !encodings_out)) || (k && !commitments_out) || !entropy)
     return ZKP_ERR_SIZE;
   const int n_terms = k ? sd->cons_off[k] : 0;
-  if ((double)N * (n_terms > p ? n_terms : p) > 1.5e9) return ZKP_ERR_SIZE;
+  // large batches run as slices of at most `prove_chunk` proofs: the constant-time tables take 1 KB per term
+  // (31 KB per CMZ proof), and the slices reuse one workspace
+  if (N > ctx->prove_chunk) {
+    for (size_t lo = 0; lo < N; lo += ctx->prove_chunk) {
+      const size_t cnt = N - lo < ctx->prove_chunk ? N - lo : ctx->prove_chunk;
+      int32_t rc = zkp_prove_batch(ctx, sd, prefix_state, cnt, secrets ? secrets + lo * (size_t)m * 32 : nullptr,
+                                   points ? points + lo * (size_t)p * 20 : nullptr, entropy + lo * 32,
+                                   encodings_out ? encodings_out + lo * (size_t)p * 32 : nullptr,
+                                   commitments_out ? commitments_out + lo * (size_t)k * 32 : nullptr,
+                                   responses_out ? responses_out + lo * (size_t)m * 32 : nullptr,
+                                   blindings_out ? blindings_out + lo * (size_t)m * 32 : nullptr);
+      if (rc != ZKP_OK) return rc;
+    }
+    return ZKP_OK;
+  }
   for (int c = 0; c < k; c++)
     if (sd->lhs[c] < 0 || sd->lhs[c] >= p || sd->cons_off[c + 1] < sd->cons_off[c]) return ZKP_ERR_SIZE;
   for (int q = 0; q < n_terms; q++)
