@@ -573,6 +573,48 @@ __global__ void __launch_bounds__(256) k_tree_sum(const uint4* __restrict__ in, 
 // K7: finish.  usum[level][W] (nl levels), last[W][m_last] = the items of the final (short) level.
 // One block, W threads for the per-window part, thread 0 for the Horner over windows + encode.
 // ---------------------------------------------------------------------------------------------------------
+// One doubling shared by lanes 0..3 of a warp (all four hold the same point before and after): lane i squares one of
+// X, Y, Z, X+Y, the results are exchanged by shuffles, the four lanes form E, F, G, H redundantly and lane i computes one
+// of the four products.  Per doubling a lane runs 1 squaring + 1 product + 7 additions + 64 shuffles instead of 4 + 4 + 6
+// field operations: the serial doubling chains that bound the latency of a call (k_finish: ~253 in a row) shrink ~3x.
+// Same instruction stream on every lane (operands are picked with selects), so the shuffles are convergent.
+__device__ __forceinline__ void shfl4_fe(fe& out, const fe& mine, int src) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) out.v[i] = __shfl_sync(0xfu, mine.v[i], src);
+}
+__device__ __forceinline__ void ge_double_coop4(ge_ext& p, int lane) {
+  const uint32_t l1 = lane == 1, l2 = lane == 2, l3 = lane == 3, l0 = lane == 0;
+  fe in, xpy, sq, dbl;
+  fe_add(xpy, p.X, p.Y);
+  fe_select(in, p.X, p.Y, l1);
+  fe_select(in, in, p.Z, l2);
+  fe_select(in, in, xpy, l3);
+  fe_sq(sq, in);
+  fe_add(dbl, sq, sq);
+  fe_select(sq, sq, dbl, l2);          // lane 2 carries 2 Z^2
+  fe xx, yy, zz2, xy2, e, f, g, h;
+  shfl4_fe(xx, sq, 0);
+  shfl4_fe(yy, sq, 1);
+  shfl4_fe(zz2, sq, 2);
+  shfl4_fe(xy2, sq, 3);
+  fe_add(h, yy, xx);                   // Y' = YY + XX
+  fe_sub(g, yy, xx);                   // Z' = YY - XX
+  fe_sub(e, xy2, h);                   // X' = (X+Y)^2 - YY - XX
+  fe_sub(f, zz2, g);                   // T' = 2ZZ - Z'
+  // lane 0: E F (X), lane 1: H G (Y), lane 2: G F (Z), lane 3: E H (T)
+  fe a, b, r;
+  fe_select(a, e, h, l1);
+  fe_select(a, a, g, l2);
+  fe_select(b, f, g, l1);
+  fe_select(b, b, h, l3);
+  (void)l0;
+  fe_mul(r, a, b);
+  shfl4_fe(p.X, r, 0);
+  shfl4_fe(p.Y, r, 1);
+  shfl4_fe(p.Z, r, 2);
+  shfl4_fe(p.T, r, 3);
+}
+
 __global__ void __launch_bounds__(64) k_finish(const uint4* __restrict__ usum, int nl, const uint4* __restrict__ last,
                                                uint32_t m_last, int W, int c, size_t n, const int* __restrict__ flags,
                                                msm_result* __restrict__ res, uint4* __restrict__ partial_out) {
@@ -601,14 +643,18 @@ __global__ void __launch_bounds__(64) k_finish(const uint4* __restrict__ usum, i
     store_ext(sw + w * 8, acc);
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 4) {
+    // Horner over the windows: ~253 doublings in a row, shared by lanes 0..3 (ge_double_coop4); the W - 1 additions are
+    // done redundantly by the four lanes so that they keep holding the same point
     ge_ext tot, p;
     load_ext(tot, sw + (W - 1) * 8);
     for (int ww = W - 2; ww >= 0; ww--) {
-      for (int d = 0; d < c; d++) ge_double(tot, tot);
+#pragma unroll 1
+      for (int d = 0; d < c; d++) ge_double_coop4(tot, (int)threadIdx.x);
       load_ext(p, sw + ww * 8);
       ge_add(tot, tot, p);
     }
+    if (threadIdx.x != 0) return;
     if (partial_out) store_ext(partial_out, tot);
     uint32_t enc[8];
     ristretto_encode(enc, tot);
