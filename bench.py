@@ -205,6 +205,7 @@ def main():
     ap.add_argument("--no-overlap", action="store_true", help="tuning: run the digit sort on the compute stream")
     ap.add_argument("--chunk-terms-log2", type=int, default=0, help="tuning: H2D pipeline chunk (terms) for the e2e leg")
     ap.add_argument("--ingest-variant", type=int, default=-1, help="tuning: occupancy point of k_ingest2 (0..3)")
+    ap.add_argument("--phase1-percent", type=int, default=0, help="tuning: share of point chunks in the first ingestion phase (e2e)")
     ap.add_argument("--no-numa-bind", action="store_true", help="tuning: do not pin ranks to their GPU's NUMA node")
     ap.add_argument("--no-fused-sort", action="store_true", help="tuning: separate scatter pass instead of the two-phase ingestion")
     ap.add_argument("--sweep", default="", help="tuning: comma list of windows; prints stage times per window and exits")
@@ -303,6 +304,8 @@ def main():
         eng.set_option("overlap", 0)
     if args.no_fused_sort:
         eng.set_option("fused_sort", 0)
+    if args.phase1_percent:
+        eng.set_option("phase1_percent", args.phase1_percent)
     if args.ingest_variant >= 0:
         eng.set_option("ingest_variant", args.ingest_variant)
     if args.chunk_terms_log2:
