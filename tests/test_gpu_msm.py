@@ -159,6 +159,14 @@ def test_small_batched_vartime(engine):
     out, valid = engine.msm_vartime_batched(scal, pts, off)
     assert valid.all()
     assert [bytes(o).hex() for o in out] == [k["expected"] for k in kats]
+    # one thread per MSM (throughput schedule) and four lanes per MSM (latency schedule) give the same bytes
+    for coop in (0, 1 << 20):
+        engine.set_option("coop_max_msms", coop)
+        try:
+            o2, v2 = engine.msm_vartime_batched(scal, pts, off)
+        finally:
+            engine.set_option("coop_max_msms", 8192)
+        assert v2.all() and (o2 == out).all(), coop
     # one bad point invalidates only its MSM
     g = U.golden("rfc9496.json")
     pts2 = pts.copy()

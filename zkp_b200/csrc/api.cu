@@ -58,6 +58,7 @@ struct zkp_ctx {
   int balance = 1;     // size-ordered work items in the bucket accumulation (equal-length items share a warp)
   void* partial_out = nullptr;   // when set, k_finish also stores the MSM result as an extended point (single-verdict mode)
   size_t prove_chunk = (size_t)1 << 17;   // proofs per slice of zkp_prove_batch (4 GB of tables for CMZ)
+  int coop_max_msms = 8192;  // batched small vartime MSMs: up to this many run with four lanes per MSM (latency)
   int phase1_percent = 50;   // share of the host-path point chunks decompressed under the histogram (first phase)
   int share_static_tables = 1;   // batch proving: one constant-time table per batch-static point
   int bv_compiled = 1;      // batch-verification front end: host-compiled transcript script (k_bv_prepare2)
@@ -194,6 +195,9 @@ extern "C" int32_t zkp_ctx_set_option(zkp_ctx* ctx, const char* key, int64_t val
     ctx->overlap = value ? 1 : 0;
   } else if (!strcmp(key, "balance")) {
     ctx->balance = value ? 1 : 0;
+  } else if (!strcmp(key, "coop_max_msms")) {
+    if (value < 0) return ZKP_ERR_SIZE;
+    ctx->coop_max_msms = (int)value;
   } else if (!strcmp(key, "phase1_percent")) {
     if (value < 1 || value > 100) return ZKP_ERR_SIZE;
     ctx->phase1_percent = (int)value;
@@ -1418,10 +1422,16 @@ extern "C" int32_t zkp_msm_vartime_batched(zkp_ctx* ctx, const uint8_t* scalars,
   size_order(offsets, M, &order);
   ENSURE(ctx, ctx->multi, M * 4 + 16);
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->multi.p, order.data(), M * 4, cudaMemcpyHostToDevice, st));
-  k_small_msm_vt<<<(unsigned)((M + 63) / 64), 64, 0, st>>>(
-      (const uint32_t*)ctx->sk0.p, (const uint32_t*)ctx->sk1.p, (const uint4*)ctx->niels.p,
-      (const unsigned long long*)ctx->aux0.p, (const uint32_t*)ctx->multi.p, M, (uint4*)ctx->aux1.p,
-      (int*)ctx->aux2.p);
+  if (M <= (size_t)ctx->coop_max_msms)   // too few MSMs to fill the GPU with one thread each: four lanes per MSM (latency)
+    k_small_msm_vt<true><<<(unsigned)((4 * M + 63) / 64), 64, 0, st>>>(
+        (const uint32_t*)ctx->sk0.p, (const uint32_t*)ctx->sk1.p, (const uint4*)ctx->niels.p,
+        (const unsigned long long*)ctx->aux0.p, (const uint32_t*)ctx->multi.p, M, (uint4*)ctx->aux1.p,
+        (int*)ctx->aux2.p);
+  else
+    k_small_msm_vt<false><<<(unsigned)((M + 63) / 64), 64, 0, st>>>(
+        (const uint32_t*)ctx->sk0.p, (const uint32_t*)ctx->sk1.p, (const uint4*)ctx->niels.p,
+        (const unsigned long long*)ctx->aux0.p, (const uint32_t*)ctx->multi.p, M, (uint4*)ctx->aux1.p,
+        (int*)ctx->aux2.p);
   LAUNCH_CHECK(ctx);
   // status words -> valid bytes on the host
   int* hstat = (int*)malloc(M * 4);

@@ -573,17 +573,36 @@ __global__ void __launch_bounds__(256) k_tree_sum(const uint4* __restrict__ in, 
 // K7: finish.  usum[level][W] (nl levels), last[W][m_last] = the items of the final (short) level.
 // One block, W threads for the per-window part, thread 0 for the Horner over windows + encode.
 // ---------------------------------------------------------------------------------------------------------
-// One doubling shared by lanes 0..3 of a warp (all four hold the same point before and after): lane i squares one of
-// X, Y, Z, X+Y, the results are exchanged by shuffles, the four lanes form E, F, G, H redundantly and lane i computes one
-// of the four products.  Per doubling a lane runs 1 squaring + 1 product + 7 additions + 64 shuffles instead of 4 + 4 + 6
-// field operations: the serial doubling chains that bound the latency of a call (k_finish: ~253 in a row) shrink ~3x.
-// Same instruction stream on every lane (operands are picked with selects), so the shuffles are convergent.
-__device__ __forceinline__ void shfl4_fe(fe& out, const fe& mine, int src) {
+// Point operations shared by a group of four adjacent lanes (all four hold the same point before and after):
+//   doubling   lane i squares one of X, Y, Z, X+Y; the results are exchanged by shuffles; the four lanes form E, F, G, H
+//              redundantly; lane i computes one of the four products
+//   mixed add  lanes 0..2 compute (Y1-X1)(y2-x2), (Y1+X1)(y2+x2), T1 * 2d x2 y2; exchange; then the same four products
+// Per operation a lane runs two field multiplications (plus additions and 56-64 shuffles) instead of seven or eight: the
+// serial chains that bound the LATENCY of a call (k_finish: ~253 doublings in a row; a single proof's MSMs) shrink ~2-3x.
+// The instruction stream is the same on every lane (operands are picked with selects), so the shuffles are convergent.
+// gmask / gbase: the lane mask of the group and its first lane within the warp.
+__device__ __forceinline__ void shflg_fe(fe& out, const fe& mine, int src, unsigned gmask, int gbase) {
 #pragma unroll
-  for (int i = 0; i < 8; i++) out.v[i] = __shfl_sync(0xfu, mine.v[i], src);
+  for (int i = 0; i < 8; i++) out.v[i] = __shfl_sync(gmask, mine.v[i], gbase + src);
 }
-__device__ __forceinline__ void ge_double_coop4(ge_ext& p, int lane) {
-  const uint32_t l1 = lane == 1, l2 = lane == 2, l3 = lane == 3, l0 = lane == 0;
+__device__ __forceinline__ void ge_efgh_products_coop(ge_ext& p, const fe& e, const fe& f, const fe& g, const fe& h, int sub,
+                                                      unsigned gmask, int gbase) {
+  // lane 0: E F (X), lane 1: G H (Y), lane 2: F G (Z), lane 3: E H (T)
+  const uint32_t l1 = sub == 1, l2 = sub == 2, l3 = sub == 3;
+  fe a, b, r;
+  fe_select(a, e, g, l1);
+  fe_select(a, a, f, l2);
+  fe_select(b, f, h, l1);
+  fe_select(b, b, g, l2);
+  fe_select(b, b, h, l3);
+  fe_mul(r, a, b);
+  shflg_fe(p.X, r, 0, gmask, gbase);
+  shflg_fe(p.Y, r, 1, gmask, gbase);
+  shflg_fe(p.Z, r, 2, gmask, gbase);
+  shflg_fe(p.T, r, 3, gmask, gbase);
+}
+__device__ __forceinline__ void ge_double_coop4(ge_ext& p, int sub, unsigned gmask = 0xfu, int gbase = 0) {
+  const uint32_t l1 = sub == 1, l2 = sub == 2, l3 = sub == 3;
   fe in, xpy, sq, dbl;
   fe_add(xpy, p.X, p.Y);
   fe_select(in, p.X, p.Y, l1);
@@ -593,26 +612,38 @@ __device__ __forceinline__ void ge_double_coop4(ge_ext& p, int lane) {
   fe_add(dbl, sq, sq);
   fe_select(sq, sq, dbl, l2);          // lane 2 carries 2 Z^2
   fe xx, yy, zz2, xy2, e, f, g, h;
-  shfl4_fe(xx, sq, 0);
-  shfl4_fe(yy, sq, 1);
-  shfl4_fe(zz2, sq, 2);
-  shfl4_fe(xy2, sq, 3);
-  fe_add(h, yy, xx);                   // Y' = YY + XX
-  fe_sub(g, yy, xx);                   // Z' = YY - XX
-  fe_sub(e, xy2, h);                   // X' = (X+Y)^2 - YY - XX
-  fe_sub(f, zz2, g);                   // T' = 2ZZ - Z'
-  // lane 0: E F (X), lane 1: H G (Y), lane 2: G F (Z), lane 3: E H (T)
-  fe a, b, r;
-  fe_select(a, e, h, l1);
-  fe_select(a, a, g, l2);
-  fe_select(b, f, g, l1);
-  fe_select(b, b, h, l3);
-  (void)l0;
-  fe_mul(r, a, b);
-  shfl4_fe(p.X, r, 0);
-  shfl4_fe(p.Y, r, 1);
-  shfl4_fe(p.Z, r, 2);
-  shfl4_fe(p.T, r, 3);
+  shflg_fe(xx, sq, 0, gmask, gbase);
+  shflg_fe(yy, sq, 1, gmask, gbase);
+  shflg_fe(zz2, sq, 2, gmask, gbase);
+  shflg_fe(xy2, sq, 3, gmask, gbase);
+  fe_add(h, yy, xx);                   // H = YY + XX
+  fe_sub(g, yy, xx);                   // G = YY - XX
+  fe_sub(e, xy2, h);                   // E = (X+Y)^2 - YY - XX
+  fe_sub(f, zz2, g);                   // F = 2ZZ - G
+  // doubling: X' = E F, Y' = G H, Z' = F G, T' = E H   (ge_double: r.X = e f, r.Y = h g, r.Z = g f, r.T = e h)
+  ge_efgh_products_coop(p, e, f, g, h, sub, gmask, gbase);
+}
+__device__ __forceinline__ void ge_madd_coop4(ge_ext& p, const ge_aniels& q, int sub, unsigned gmask, int gbase) {
+  const uint32_t l1 = sub == 1, l2 = sub == 2;
+  fe ymx, ypx, a, b, r;
+  fe_sub(ymx, p.Y, p.X);
+  fe_add(ypx, p.Y, p.X);
+  fe_select(a, ymx, ypx, l1);
+  fe_select(a, a, p.T, l2);
+  fe_select(b, q.yminusx, q.yplusx, l1);
+  fe_select(b, b, q.xy2d, l2);
+  fe_mul(r, a, b);                     // lane 0: A, lane 1: B, lane 2: C (lane 3 repeats A)
+  fe A, B, C, d, e, f, g, h;
+  shflg_fe(A, r, 0, gmask, gbase);
+  shflg_fe(B, r, 1, gmask, gbase);
+  shflg_fe(C, r, 2, gmask, gbase);
+  fe_add(d, p.Z, p.Z);
+  fe_sub(e, B, A);
+  fe_sub(f, d, C);
+  fe_add(g, d, C);
+  fe_add(h, B, A);
+  // ge_madd: r.X = e f, r.Y = g h, r.Z = f g, r.T = e h
+  ge_efgh_products_coop(p, e, f, g, h, sub, gmask, gbase);
 }
 
 __global__ void __launch_bounds__(64) k_finish(const uint4* __restrict__ usum, int nl, const uint4* __restrict__ last,
