@@ -187,6 +187,14 @@ def test_small_batched_ct(engine):
     assert valid.all()
     out = engine.msm_ct_batched(scal, limbs, off, limbs=True)
     assert [bytes(o).hex() for o in out] == [k["expected"] for k in kats]
+    # throughput schedule (one thread per MSM) and latency schedule (four lanes per MSM): same bytes
+    for coop in (0, 1 << 20):
+        engine.set_option("coop_max_msms", coop)
+        try:
+            o2 = engine.msm_ct_batched(scal, pts, off)
+        finally:
+            engine.set_option("coop_max_msms", 8192)
+        assert [bytes(o).hex() for o in o2] == [k["expected"] for k in kats], coop
 
 
 def test_batch_verify_dleq_golden(engine):

@@ -1502,9 +1502,14 @@ extern "C" int32_t zkp_msm_ct_batched(zkp_ctx* ctx, const uint8_t* scalars, cons
   size_order(offsets, M, &order);
   ENSURE(ctx, ctx->multi, M * 4 + 16);
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->multi.p, order.data(), M * 4, cudaMemcpyHostToDevice, st));
-  k_small_msm_ct<false><<<(unsigned)((M + 63) / 64), 64, 0, st>>>((const uint32_t*)ctx->sk0.p, (const uint4*)ctx->tables.p,
-                                                                  (const unsigned long long*)ctx->aux0.p,
-                                                                  (const uint32_t*)ctx->multi.p, M, 1u, (uint4*)ctx->aux1.p);
+  if (M <= (size_t)ctx->coop_max_msms)   // few MSMs (a single proof's constraints): four lanes per MSM, latency schedule
+    k_small_msm_ct<false, true><<<(unsigned)((4 * M + 63) / 64), 64, 0, st>>>(
+        (const uint32_t*)ctx->sk0.p, (const uint4*)ctx->tables.p, (const unsigned long long*)ctx->aux0.p,
+        (const uint32_t*)ctx->multi.p, M, 1u, (uint4*)ctx->aux1.p);
+  else
+    k_small_msm_ct<false, false><<<(unsigned)((M + 63) / 64), 64, 0, st>>>(
+        (const uint32_t*)ctx->sk0.p, (const uint4*)ctx->tables.p, (const unsigned long long*)ctx->aux0.p,
+        (const uint32_t*)ctx->multi.p, M, 1u, (uint4*)ctx->aux1.p);
   LAUNCH_CHECK(ctx);
   int hflags[4];
   CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->aux1.p, M * 32, cudaMemcpyDeviceToHost, st));

@@ -646,6 +646,32 @@ __device__ __forceinline__ void ge_madd_coop4(ge_ext& p, const ge_aniels& q, int
   ge_efgh_products_coop(p, e, f, g, h, sub, gmask, gbase);
 }
 
+// p += q (projective Niels) shared by four lanes: the four products of the first round take one lane each
+__device__ __forceinline__ void ge_add_pniels_coop4(ge_ext& p, const ge_pniels& q, int sub, unsigned gmask, int gbase) {
+  const uint32_t l1 = sub == 1, l2 = sub == 2, l3 = sub == 3;
+  fe ymx, ypx, a, b, r;
+  fe_sub(ymx, p.Y, p.X);
+  fe_add(ypx, p.Y, p.X);
+  fe_select(a, ymx, ypx, l1);
+  fe_select(a, a, p.T, l2);
+  fe_select(a, a, p.Z, l3);
+  fe_select(b, q.YminusX, q.YplusX, l1);
+  fe_select(b, b, q.T2d, l2);
+  fe_select(b, b, q.Z, l3);
+  fe_mul(r, a, b);                     // lane 0: A, lane 1: B, lane 2: C, lane 3: Z1 Z2
+  fe A, B, C, d, e, f, g, h;
+  shflg_fe(A, r, 0, gmask, gbase);
+  shflg_fe(B, r, 1, gmask, gbase);
+  shflg_fe(C, r, 2, gmask, gbase);
+  shflg_fe(d, r, 3, gmask, gbase);
+  fe_add(d, d, d);
+  fe_sub(e, B, A);
+  fe_sub(f, d, C);
+  fe_add(g, d, C);
+  fe_add(h, B, A);
+  ge_efgh_products_coop(p, e, f, g, h, sub, gmask, gbase);
+}
+
 __global__ void __launch_bounds__(64) k_finish(const uint4* __restrict__ usum, int nl, const uint4* __restrict__ last,
                                                uint32_t m_last, int W, int c, size_t n, const int* __restrict__ flags,
                                                msm_result* __restrict__ res, uint4* __restrict__ partial_out) {

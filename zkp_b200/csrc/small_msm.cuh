@@ -212,14 +212,20 @@ __global__ void __launch_bounds__(128) k_build_tables(const uint4* __restrict__ 
   }
 }
 
-template <bool IL>
+// COOP: four adjacent lanes share one MSM (kernels.cuh ge_double_coop4 / ge_add_pniels_coop4; every lane scans the whole
+// table, so the lookup stays constant time and the lanes stay in lock step): the latency schedule for small batches.
+template <bool IL, bool COOP = false>
 __global__ void __launch_bounds__(64) k_small_msm_ct(const uint32_t* __restrict__ biased, const uint4* __restrict__ tables,
                                                      const unsigned long long* __restrict__ offsets,
                                                      const uint32_t* __restrict__ order, size_t M, uint32_t T,
                                                      uint4* __restrict__ out,
                                                      const int32_t* __restrict__ shared_of = nullptr,
                                                      const uint4* __restrict__ shared_tables = nullptr) {
-  size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t thread = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t tid = COOP ? thread >> 2 : thread;
+  const int sub = COOP ? (int)(threadIdx.x & 3) : 0;
+  const int gbase = (int)(threadIdx.x & 31 & ~3);
+  const unsigned gmask = 0xfu << gbase;
   if (tid >= M) return;
   const size_t j = order[tid];   // public: MSMs sorted by (public) size so the lanes of a warp do equal work
   const size_t lo = offsets[j], hi = offsets[j + 1];   // public
@@ -230,10 +236,15 @@ __global__ void __launch_bounds__(64) k_small_msm_ct(const uint32_t* __restrict_
   ge_identity(acc);
 #pragma unroll 1
   for (int w = 63; w >= 0; w--) {
-    ge_double(acc, acc);
-    ge_double(acc, acc);
-    ge_double(acc, acc);
-    ge_double(acc, acc);
+    if (COOP) {
+#pragma unroll 1
+      for (int dd = 0; dd < 4; dd++) ge_double_coop4(acc, sub, gmask, gbase);
+    } else {
+      ge_double(acc, acc);
+      ge_double(acc, acc);
+      ge_double(acc, acc);
+      ge_double(acc, acc);
+    }
 #pragma unroll 1
     for (size_t t = lo; t < hi; t++) {
       uint32_t word = __ldg(biased + 8 * t + (w >> 3));
@@ -267,9 +278,11 @@ __global__ void __launch_bounds__(64) k_small_msm_ct(const uint32_t* __restrict_
         }
       }
       ge_pniels_cneg(sel, sign);
-      ge_add_pniels(acc, acc, sel);
+      if (COOP) ge_add_pniels_coop4(acc, sel, sub, gmask, gbase);
+      else ge_add_pniels(acc, acc, sel);
     }
   }
+  if (sub != 0) return;
   uint32_t enc[8];
   ristretto_encode(enc, acc);
   out[2 * j] = make_uint4(enc[0], enc[1], enc[2], enc[3]);
