@@ -1,4 +1,4 @@
-/* zkp_b200_host.h -- flat C face of the host-side mirror of zkp's toolbox (zkp_b200/csrc/host/*.cpp).
+/* zkp_b200_host.h -- flat C face of the host-side mirror of zkp's toolbox (zkp_b200/csrc/host/ .cpp sources).
  *
  * The C++ classes there (Prover, Verifier, BatchVerifier, Statement = the define_proof! mirror) follow
  * /root/reference/src/toolbox/{prover,verifier,batch_verifier,mod}.rs and /root/reference/src/macros.rs:206-370;

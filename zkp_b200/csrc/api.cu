@@ -709,7 +709,7 @@ extern "C" int32_t zkp_batch_verify(zkp_ctx* ctx, const uint8_t* static_coeffs, 
                                     size_t rows, size_t batch, int32_t* accept, int64_t* first_bad) {
   if (!ctx || !accept) return ZKP_ERR_SIZE;
   *accept = 0;
-  if ((num_s && (!static_coeffs || !static_points)) || (rows * batch && (!instance_coeffs || !instance_points)))
+  if ((num_s && (!static_coeffs || !static_points)) || (rows && batch && (!instance_coeffs || !instance_points)))
     return ZKP_ERR_SIZE;
   if (batch && rows > ((size_t)1 << 40) / batch) return ZKP_ERR_SIZE;
   const size_t n_inst = rows * batch, n = num_s + n_inst;
@@ -734,7 +734,7 @@ extern "C" int32_t zkp_batch_verify_partial(zkp_ctx* ctx, const uint8_t* static_
                                             size_t num_s, const uint8_t* instance_coeffs, const uint8_t* instance_points,
                                             size_t rows, size_t batch, uint64_t* partial_limbs_out, int64_t* first_bad) {
   if (!ctx || !partial_limbs_out) return ZKP_ERR_SIZE;
-  if ((num_s && (!static_coeffs || !static_points)) || (rows * batch && (!instance_coeffs || !instance_points)))
+  if ((num_s && (!static_coeffs || !static_points)) || (rows && batch && (!instance_coeffs || !instance_points)))
     return ZKP_ERR_SIZE;
   if (batch && rows > ((size_t)1 << 40) / batch) return ZKP_ERR_SIZE;
   const size_t n_inst = rows * batch, n = num_s + n_inst;

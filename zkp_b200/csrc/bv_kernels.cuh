@@ -118,11 +118,11 @@ __device__ __forceinline__ void bv_static_block_sums(const bv_desc& d, const scl
 //   flags[2]      set to the first proof index with an identity encoding or a non-canonical response
 __global__ void __launch_bounds__(128) k_bv_prepare(bv_desc d, const uint32_t* __restrict__ prefix, size_t N,
                                                     const uint8_t* __restrict__ instance_enc,
-                                                    const uint8_t* __restrict__ common_enc,
+                                                    const uint8_t* common_enc,
                                                     const uint8_t* __restrict__ commitments,
                                                     const uint8_t* __restrict__ responses,
                                                     const uint8_t* __restrict__ rho_seed, uint8_t* __restrict__ msm_scalars,
-                                                    uint8_t* __restrict__ msm_points, uint8_t* __restrict__ static_part,
+                                                    uint8_t* msm_points, uint8_t* __restrict__ static_part,
                                                     uint8_t* __restrict__ minus_c_out, int* __restrict__ flags,
                                                     size_t j0, size_t cnt, unsigned block_base) {
   // proofs [j0, j0 + cnt) of the batch (chunked ingestion: H2D of the next chunk overlaps this kernel)

@@ -496,7 +496,7 @@ ProofError stmt_prove_many(zkp_ctx* ctx, const Statement& st, const std::string&
   const size_t m = st.secrets.size(), p = st.num_points(), k = st.constraints.size();
   // (1) every allocate_point compression of every proof in one device call (toolbox/mod.rs:180)
   encodings->resize(N * p);
-  if (N * p && zkp_compress_batch(ctx, points[0].data(), N * p, (*encodings)[0].data()) != ZKP_OK) return EngineFailure;
+  if (N && p && zkp_compress_batch(ctx, points[0].data(), N * p, (*encodings)[0].data()) != ZKP_OK) return EngineFailure;
   // (2) per proof: transcript up to the commitments, synthetic-nonce blindings (prover.rs:78-89)
   size_t terms = 0;
   for (auto& c : st.constraints) terms += c.second.size();
@@ -528,7 +528,7 @@ ProofError stmt_prove_many(zkp_ctx* ctx, const Statement& st, const std::string&
   offsets[N * k] = N * terms;
   // (3) all N*k constant-time MSMs + compressions in one device call (prover.rs:93-103)
   std::vector<uint8_t> coms(N * k * 32 + 32);
-  if (N * k && zkp_msm_ct_batched(ctx, sc.data(), pts.data(), ZKP_POINTS_LIMBS51, offsets.data(), N * k, coms.data()) != ZKP_OK)
+  if (N && k && zkp_msm_ct_batched(ctx, sc.data(), pts.data(), ZKP_POINTS_LIMBS51, offsets.data(), N * k, coms.data()) != ZKP_OK)
     return EngineFailure;
   // (4) per proof: commitments into the transcript, challenge, responses (prover.rs:98-109)
   proofs->resize(N);
