@@ -184,3 +184,47 @@ def test_compiled_transcript_script_on_the_host():
         assert out.raw == expected, (trial, ni, nc, k, [len(n) for n in names])
         seen_blocks.add(nb.value)
     assert len(seen_blocks) >= 4        # scripts of very different lengths were exercised
+
+
+def test_inconsistent_statement_descriptions_are_refused():
+    """A flattened statement is used as sizes and indices by the engine: descriptions whose ranges do not add up
+    (negative counts, decreasing or non-zero-based term offsets, out-of-range lhs, missing arrays) come back as
+    ZKP_ERR_SIZE -- no crash, no exception through the C ABI (api.cu statement_ok / guarded)."""
+    import numpy as np
+    lib = native.load()
+    vp = ctypes.c_void_p
+
+    class Desc(ctypes.Structure):
+        _fields_ = [("m", ctypes.c_int32), ("ni", ctypes.c_int32), ("nc", ctypes.c_int32), ("k", ctypes.c_int32),
+                    ("labels", ctypes.c_char_p), ("lhs", vp), ("cons_off", vp), ("term_scalar", vp), ("term_point", vp)]
+    lib.zkp_selftest_bv_script.argtypes = [ctypes.POINTER(Desc), vp, vp, vp, vp, vp, ctypes.POINTER(ctypes.c_int32)]
+    lib.zkp_selftest_bv_script.restype = ctypes.c_int32
+    prefix = (ctypes.c_uint32 * 53)()
+    out = ctypes.create_string_buffer(64)
+    buf = b"\1" * 256
+    lab = b"A\0B\0"
+    lhs = np.array([0, 1], dtype=np.int32)
+    ts = np.array([0, 0], dtype=np.int32)
+    tp = np.array([1, 0], dtype=np.int32)
+
+    def call(m, ni, nc, k, lhs_a, off, ts_a=ts, tp_a=tp, labels=lab):
+        off_a = np.array(off, dtype=np.int32)
+        d = Desc(m, ni, nc, k, labels, lhs_a.ctypes.data if lhs_a is not None else None, off_a.ctypes.data,
+                 ts_a.ctypes.data if ts_a is not None else None, tp_a.ctypes.data if tp_a is not None else None)
+        return lib.zkp_selftest_bv_script(ctypes.byref(d), prefix, buf, buf, buf, out, None)
+
+    assert call(1, 1, 1, 2, lhs, [0, 1, 2]) == 0                           # the well-formed statement
+    assert call(1, 1, 1, 2, lhs, [0, 2, 1]) == native.ZKP_ERR_SIZE         # decreasing term offsets
+    assert call(1, 1, 1, 2, lhs, [1, 1, 2]) == native.ZKP_ERR_SIZE         # offsets not starting at 0
+    assert call(1, 1, 1, 2, lhs, [0, 1, -5]) == native.ZKP_ERR_SIZE        # negative term count
+    assert call(1, 1, 1, 2, lhs, [0, 1, 1 << 30]) == native.ZKP_ERR_SIZE   # absurd term count
+    assert call(1, 1, 1, 2, np.array([0, 2], dtype=np.int32), [0, 1, 2]) == native.ZKP_ERR_SIZE   # lhs out of range
+    assert call(1, 1, 1, 2, np.array([-1, 0], dtype=np.int32), [0, 1, 2]) == native.ZKP_ERR_SIZE
+    assert call(1, 1, 1, 2, lhs, [0, 1, 2], tp_a=np.array([2, 0], dtype=np.int32)) == native.ZKP_ERR_SIZE   # term point
+    assert call(1, 1, 1, 2, lhs, [0, 1, 2], ts_a=np.array([1, 0], dtype=np.int32)) == native.ZKP_ERR_SIZE   # term scalar
+    assert call(1, 1, 1, 2, lhs, [0, 1, 2], ts_a=None) == native.ZKP_ERR_SIZE                               # missing array
+    assert call(1, 1, 1, 2, None, [0, 1, 2]) == native.ZKP_ERR_SIZE
+    assert call(1, -1, 1, 0, lhs, [0]) == native.ZKP_ERR_SIZE              # negative counts
+    assert call(1, 1, 1, -2, lhs, [0]) == native.ZKP_ERR_SIZE
+    assert call(1, 1, 1, 0, lhs, [0], labels=None) == native.ZKP_ERR_SIZE  # labels missing
+    assert call(1, 1000, 1, 0, lhs, [0]) == native.ZKP_ERR_SIZE            # more variables than the front end holds

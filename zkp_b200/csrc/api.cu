@@ -780,6 +780,43 @@ extern "C" int32_t zkp_partials_verdict(zkp_ctx* ctx, const uint64_t* partial_li
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// entry points that build host-side containers: nothing may unwind through the C ABI
+// ---------------------------------------------------------------------------------------------------------
+template <class F>
+static int32_t guarded(zkp_ctx* ctx, F&& body) {
+  try {
+    return body();
+  } catch (const std::bad_alloc&) {
+    if (ctx) ctx->err = "host allocation failed";
+    return ZKP_ERR_NOMEM;
+  } catch (const std::exception& e) {
+    if (ctx) ctx->err = std::string("host exception: ") + e.what();
+    return ZKP_ERR_SIZE;
+  } catch (...) {
+    return ZKP_ERR_SIZE;
+  }
+}
+
+// a flattened statement is used as sizes and indices: check it once, before anything is derived from it
+static bool statement_ok(const zkp_statement_desc* sd) {
+  const int m = sd->m, ni = sd->ni, nc = sd->nc, k = sd->k;
+  if (m < 0 || ni < 0 || nc < 0 || k < 0) return false;
+  if (ni > 2 * ZKP_BV_MAX_VARS || nc > 2 * ZKP_BV_MAX_VARS || k > ZKP_BV_MAX_CONS) return false;
+  const int p = ni + nc;
+  if (p && !sd->labels) return false;
+  if (!k) return true;
+  if (!sd->lhs || !sd->cons_off || sd->cons_off[0] != 0) return false;
+  for (int c = 0; c < k; c++)
+    if (sd->lhs[c] < 0 || sd->lhs[c] >= p || sd->cons_off[c + 1] < sd->cons_off[c]) return false;
+  const int n_terms = sd->cons_off[k];
+  if (n_terms > (1 << 20)) return false;
+  if (n_terms && (!sd->term_scalar || !sd->term_point)) return false;
+  for (int q = 0; q < n_terms; q++)
+    if (sd->term_point[q] < 0 || sd->term_point[q] >= p || sd->term_scalar[q] < 0 || sd->term_scalar[q] >= m) return false;
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Symbolic STROBE-128 over the per-proof transcript script of a batch (bv_kernels.cuh k_bv_prepare2): records the
 // constant bytes of every rate block and where the per-proof 32-byte values land.  Mirrors merlin 2.0 strobe.rs [ext]
 // exactly as csrc/hash.cuh and host/merlin.cpp do (begin_op framing, run_f padding, forced run_f of C-flagged ops).
@@ -883,9 +920,9 @@ static void bv_compile_batch_verify(bv_script& script, const zkp_statement_desc*
 extern "C" int32_t zkp_selftest_bv_script(const zkp_statement_desc* sd, const uint32_t* prefix_state,
                                           const uint8_t* instance_enc, const uint8_t* common_enc,
                                           const uint8_t* commitments, uint8_t* challenge_out64, int32_t* n_blocks_out) {
-  if (!sd || !prefix_state || !challenge_out64) return ZKP_ERR_SIZE;
-  for (int c = 0; c < sd->k; c++)
-    if (sd->lhs[c] < 0 || sd->lhs[c] >= sd->ni + sd->nc) return ZKP_ERR_SIZE;
+  if (!sd || !prefix_state || !challenge_out64 || !statement_ok(sd)) return ZKP_ERR_SIZE;
+  if ((sd->ni && !instance_enc) || (sd->nc && !common_enc) || (sd->k && !commitments)) return ZKP_ERR_SIZE;
+  return guarded(nullptr, [&]() -> int32_t {
   bv_script script(prefix_state[50], prefix_state[51]);
   bv_compile_batch_verify(script, sd, common_enc);
   uint64_t st[25];
@@ -914,21 +951,26 @@ extern "C" int32_t zkp_selftest_bv_script(const zkp_statement_desc* sd, const ui
   for (int i = 0; i < 64; i++) challenge_out64[i] = (uint8_t)(st[i >> 3] >> (8 * (i & 7)));
   if (n_blocks_out) *n_blocks_out = nb;
   return ZKP_OK;
+  });
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // batch verification from proofs: transcripts, challenges, weights and coefficient fold on the device
 // ---------------------------------------------------------------------------------------------------------
-extern "C" int32_t zkp_batch_verify_proofs(zkp_ctx* ctx, const zkp_statement_desc* sd, const uint32_t* prefix_state,
-                                           size_t N, const uint8_t* instance_enc, const uint8_t* common_enc,
-                                           const uint8_t* commitments, const uint8_t* responses,
-                                           const uint8_t* rho_seed, int32_t* accept, int64_t* first_bad,
-                                           uint8_t* coeff_out, uint8_t* points_out) {
+static int32_t batch_verify_proofs_impl(zkp_ctx* ctx, const zkp_statement_desc* sd, const uint32_t* prefix_state,
+                                        size_t N, const uint8_t* instance_enc, const uint8_t* common_enc,
+                                        const uint8_t* commitments, const uint8_t* responses,
+                                        const uint8_t* rho_seed, int32_t* accept, int64_t* first_bad,
+                                        uint8_t* coeff_out, uint8_t* points_out) {
   if (!ctx || !sd || !prefix_state || !accept || !rho_seed) return ZKP_ERR_SIZE;
   *accept = 0;
   if (first_bad) *first_bad = -1;
   const int m = sd->m, ni = sd->ni, nc = sd->nc, k = sd->k;
-  if (m < 0 || ni < 0 || nc < 0 || k < 0 || ni > ZKP_BV_MAX_VARS || nc > ZKP_BV_MAX_VARS || k > ZKP_BV_MAX_CONS) {
+  if (!statement_ok(sd)) {
+    ctx->err = "inconsistent statement description";
+    return ZKP_ERR_SIZE;
+  }
+  if (ni > ZKP_BV_MAX_VARS || nc > ZKP_BV_MAX_VARS) {
     ctx->err = "statement too large for the device front end";
     return ZKP_ERR_SIZE;
   }
@@ -1130,17 +1172,30 @@ extern "C" int32_t zkp_batch_verify_proofs(zkp_ctx* ctx, const zkp_statement_des
   *accept = ident;
   return ZKP_OK;
 }
+extern "C" int32_t zkp_batch_verify_proofs(zkp_ctx* ctx, const zkp_statement_desc* sd, const uint32_t* prefix_state,
+                                           size_t N, const uint8_t* instance_enc, const uint8_t* common_enc,
+                                           const uint8_t* commitments, const uint8_t* responses,
+                                           const uint8_t* rho_seed, int32_t* accept, int64_t* first_bad,
+                                           uint8_t* coeff_out, uint8_t* points_out) {
+  return guarded(ctx, [&]() -> int32_t {
+    return batch_verify_proofs_impl(ctx, sd, prefix_state, N, instance_enc, common_enc, commitments, responses, rho_seed,
+                                    accept, first_bad, coeff_out, points_out);
+  });
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // batch proving: N proofs of one statement, per-proof transcript / nonce / response work on the device
 // ---------------------------------------------------------------------------------------------------------
-extern "C" int32_t zkp_prove_batch(zkp_ctx* ctx, const zkp_statement_desc* sd, const uint32_t* prefix_state, size_t N,
-                                   const uint8_t* secrets, const uint64_t* points, const uint8_t* entropy,
-                                   uint8_t* encodings_out, uint8_t* commitments_out, uint8_t* responses_out,
-                                   uint8_t* blindings_out) {
+static int32_t prove_batch_impl(zkp_ctx* ctx, const zkp_statement_desc* sd, const uint32_t* prefix_state, size_t N,
+                                const uint8_t* secrets, const uint64_t* points, const uint8_t* entropy,
+                                uint8_t* encodings_out, uint8_t* commitments_out, uint8_t* responses_out,
+                                uint8_t* blindings_out) {
   if (!ctx || !sd || !prefix_state) return ZKP_ERR_SIZE;
+  if (!statement_ok(sd) || sd->ni + sd->nc > 2 * ZKP_BV_MAX_VARS) {
+    ctx->err = "inconsistent or oversized statement description";
+    return ZKP_ERR_SIZE;
+  }
   const int m = sd->m, ni = sd->ni, nc = sd->nc, k = sd->k, p = ni + nc;
-  if (m < 0 || ni < 0 || nc < 0 || k < 0 || p > 2 * ZKP_BV_MAX_VARS || k > ZKP_BV_MAX_CONS) return ZKP_ERR_SIZE;
   if (!N) return ZKP_OK;
   if ((m && (!secrets || !responses_out)) || (p && (!points || !encodings_out)) || (k && !commitments_out) || !entropy)
     return ZKP_ERR_SIZE;
@@ -1160,11 +1215,6 @@ extern "C" int32_t zkp_prove_batch(zkp_ctx* ctx, const zkp_statement_desc* sd, c
     }
     return ZKP_OK;
   }
-  for (int c = 0; c < k; c++)
-    if (sd->lhs[c] < 0 || sd->lhs[c] >= p || sd->cons_off[c + 1] < sd->cons_off[c]) return ZKP_ERR_SIZE;
-  for (int q = 0; q < n_terms; q++)
-    if (sd->term_point[q] < 0 || sd->term_point[q] >= p || sd->term_scalar[q] < 0 || sd->term_scalar[q] >= m)
-      return ZKP_ERR_SIZE;
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   // ---- statement blob: prefix | label pool | label offsets/lengths | lhs | cons_off | term arrays | schedule slots ----
@@ -1204,7 +1254,7 @@ extern "C" int32_t zkp_prove_batch(zkp_ctx* ctx, const zkp_statement_desc* sd, c
   if (!pool.empty()) memcpy(&blob[o_pool], pool.data(), pool.size());
   if (p) { memcpy(&blob[o_lo], loff.data(), (size_t)p * 4); memcpy(&blob[o_ll], llen.data(), (size_t)p * 4); }
   if (k) { memcpy(&blob[o_lhs], sd->lhs, (size_t)k * 4); memcpy(&blob[o_sl], slot.data(), (size_t)k * 4); }
-  memcpy(&blob[o_co], sd->cons_off, (size_t)(k + 1) * 4);
+  if (k) memcpy(&blob[o_co], sd->cons_off, (size_t)(k + 1) * 4);
   if (n_terms) {
     memcpy(&blob[o_ts], sd->term_scalar, (size_t)n_terms * 4);
     memcpy(&blob[o_tp], sd->term_point, (size_t)n_terms * 4);
@@ -1320,6 +1370,15 @@ extern "C" int32_t zkp_prove_batch(zkp_ctx* ctx, const zkp_statement_desc* sd, c
   }
   return ZKP_OK;
 }
+extern "C" int32_t zkp_prove_batch(zkp_ctx* ctx, const zkp_statement_desc* sd, const uint32_t* prefix_state, size_t N,
+                                   const uint8_t* secrets, const uint64_t* points, const uint8_t* entropy,
+                                   uint8_t* encodings_out, uint8_t* commitments_out, uint8_t* responses_out,
+                                   uint8_t* blindings_out) {
+  return guarded(ctx, [&]() -> int32_t {
+    return prove_batch_impl(ctx, sd, prefix_state, N, secrets, points, entropy, encodings_out, commitments_out,
+                            responses_out, blindings_out);
+  });
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // batched decompress / compress
@@ -1419,7 +1478,12 @@ extern "C" int32_t zkp_msm_vartime_batched(zkp_ctx* ctx, const uint8_t* scalars,
     LAUNCH_CHECK(ctx);
   }
   std::vector<uint32_t> order;
-  size_order(offsets, M, &order);
+  try {
+    size_order(offsets, M, &order);
+  } catch (...) {
+    ctx->err = "host allocation failed";
+    return ZKP_ERR_NOMEM;
+  }
   ENSURE(ctx, ctx->multi, M * 4 + 16);
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->multi.p, order.data(), M * 4, cudaMemcpyHostToDevice, st));
   if (M <= (size_t)ctx->coop_max_msms)   // too few MSMs to fill the GPU with one thread each: four lanes per MSM (latency)
@@ -1499,7 +1563,12 @@ extern "C" int32_t zkp_msm_ct_batched(zkp_ctx* ctx, const uint8_t* scalars, cons
     LAUNCH_CHECK(ctx);
   }
   std::vector<uint32_t> order;
-  size_order(offsets, M, &order);
+  try {
+    size_order(offsets, M, &order);
+  } catch (...) {
+    ctx->err = "host allocation failed";
+    return ZKP_ERR_NOMEM;
+  }
   ENSURE(ctx, ctx->multi, M * 4 + 16);
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->multi.p, order.data(), M * 4, cudaMemcpyHostToDevice, st));
   if (M <= (size_t)ctx->coop_max_msms)   // few MSMs (a single proof's constraints): four lanes per MSM, latency schedule
@@ -1523,6 +1592,14 @@ extern "C" int32_t zkp_msm_ct_batched(zkp_ctx* ctx, const uint8_t* scalars, cons
 // ---------------------------------------------------------------------------------------------------------
 // field-multiplier micro-benchmark
 // ---------------------------------------------------------------------------------------------------------
+struct event_pair {   // scoped events of the diagnostics below
+  cudaEvent_t a = nullptr, b = nullptr;
+  ~event_pair() {
+    if (a) cudaEventDestroy(a);
+    if (b) cudaEventDestroy(b);
+  }
+};
+
 // self-test of the device hashing: Merlin's conformance vector computed on the GPU
 extern "C" int32_t zkp_selftest_hash(zkp_ctx* ctx, uint8_t* out32) {
   if (!ctx || !out32) return ZKP_ERR_SIZE;
@@ -1543,9 +1620,10 @@ extern "C" int32_t zkp_bench_dual(zkp_ctx* ctx, int32_t mode, int32_t iters, dou
   CUDA_TRY(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
   const int threads = 256, blocks = sms * 8;
   ENSURE(ctx, ctx->aux0, (size_t)threads * blocks * 64);
-  cudaEvent_t e0, e1;
-  CUDA_TRY(ctx, cudaEventCreate(&e0));
-  CUDA_TRY(ctx, cudaEventCreate(&e1));
+  event_pair evp;
+  CUDA_TRY(ctx, cudaEventCreate(&evp.a));
+  CUDA_TRY(ctx, cudaEventCreate(&evp.b));
+  cudaEvent_t &e0 = evp.a, &e1 = evp.b;
   float best = 1e30f;
   for (int rep = 0; rep < 4; rep++) {
     CUDA_TRY(ctx, cudaEventRecord(e0, ctx->stream));
@@ -1557,8 +1635,6 @@ extern "C" int32_t zkp_bench_dual(zkp_ctx* ctx, int32_t mode, int32_t iters, dou
     CUDA_TRY(ctx, cudaEventElapsedTime(&ms, e0, e1));
     if (rep > 0 && ms < best) best = ms;
   }
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
   *ms_out = best;
   return ZKP_OK;
 }
@@ -1570,9 +1646,10 @@ extern "C" int32_t zkp_bench_field(zkp_ctx* ctx, int32_t kind, int32_t iters, do
   CUDA_TRY(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
   const int threads = 256, blocks = sms * 8;
   ENSURE(ctx, ctx->aux0, (size_t)threads * blocks * 64);
-  cudaEvent_t e0, e1;
-  CUDA_TRY(ctx, cudaEventCreate(&e0));
-  CUDA_TRY(ctx, cudaEventCreate(&e1));
+  event_pair evp;
+  CUDA_TRY(ctx, cudaEventCreate(&evp.a));
+  CUDA_TRY(ctx, cudaEventCreate(&evp.b));
+  cudaEvent_t &e0 = evp.a, &e1 = evp.b;
   float best = 1e30f;
   // kinds 12..16 (dynamic pool): `iters` squarings per thread of the usual grid, cut into units of 32 lanes x 256
   const int pool_units = (int)(((long long)threads * blocks / 32) * iters / 256);
@@ -1607,8 +1684,6 @@ extern "C" int32_t zkp_bench_field(zkp_ctx* ctx, int32_t kind, int32_t iters, do
     CUDA_TRY(ctx, cudaEventElapsedTime(&ms, e0, e1));
     if (rep > 0 && ms < best) best = ms;
   }
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
   if (kind >= 12) *ops_per_sec = (double)pool_units * 32.0 * 256.0 / (best * 1e-3);
   else *ops_per_sec = (double)threads * blocks * (double)iters / (best * 1e-3);
   return ZKP_OK;
