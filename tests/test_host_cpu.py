@@ -228,3 +228,27 @@ def test_inconsistent_statement_descriptions_are_refused():
     assert call(1, 1, 1, -2, lhs, [0]) == native.ZKP_ERR_SIZE
     assert call(1, 1, 1, 0, lhs, [0], labels=None) == native.ZKP_ERR_SIZE  # labels missing
     assert call(1, 1000, 1, 0, lhs, [0]) == native.ZKP_ERR_SIZE            # more variables than the front end holds
+
+
+def test_host_statement_constructor_refuses_bad_indices():
+    """zkph_statement_new checks every index of the flattened statement (host_api.cpp) and returns NULL instead of
+    building a Statement the classes behind it would index out of range with."""
+    import numpy as np
+    hl = PT._lib()
+    vp, i32 = ctypes.c_void_p, ctypes.c_int32
+    labels = b"x\0A\0G\0"
+
+    def new(ns, ni, nc, k, lhs, off, ts, tp):
+        a = [np.array(v, dtype=np.int32) for v in (lhs, off, ts, tp)]
+        h = hl.zkph_statement_new(b"n", b"l", labels, ns, ni, nc, k, *[x.ctypes.data for x in a])
+        if h:
+            hl.zkph_statement_free(h)
+        return bool(h)
+
+    assert new(1, 1, 1, 1, [0], [0, 1], [0], [1])
+    assert not new(1, 1, 1, 1, [2], [0, 1], [0], [1])        # lhs beyond the points
+    assert not new(1, 1, 1, 1, [0], [0, 1], [1], [1])        # secret index beyond the secrets
+    assert not new(1, 1, 1, 1, [0], [0, 1], [0], [-1])       # negative point index
+    assert not new(1, 1, 1, 1, [0], [1, 1], [0], [1])        # offsets not starting at 0
+    assert not new(1, 1, 1, 2, [0, 0], [0, 1, 0], [0], [1])  # decreasing offsets
+    assert not new(-1, 1, 1, 0, [0], [0], [0], [0])          # negative count

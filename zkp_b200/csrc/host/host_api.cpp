@@ -1,4 +1,5 @@
 // extern "C" face of the host mirror (include/zkp_b200_host.h).
+#include <atomic>
 #include <chrono>
 #include <new>
 
@@ -10,27 +11,54 @@ using namespace zkp_host;
 struct zkph_statement { Statement st; };
 struct zkph_transcript { Transcript t; };
 
+// nothing may unwind through the C face: host allocation failures and the like come back as EngineFailure
+template <class F>
+static int32_t guarded(F&& body) {
+  try {
+    return body();
+  } catch (...) {
+    return EngineFailure;
+  }
+}
+
 extern "C" zkph_statement* zkph_statement_new(const char* name, const char* label, const char* labels, int32_t n_secrets,
                                               int32_t n_instance, int32_t n_common, int32_t n_constraints,
                                               const int32_t* lhs, const int32_t* cons_off, const int32_t* term_scalar,
                                               const int32_t* term_point) {
-  zkph_statement* h = new (std::nothrow) zkph_statement();
-  if (!h) return nullptr;
-  Statement& st = h->st;
-  st.name = name;
-  st.label = label;
-  const char* p = labels;
-  for (int i = 0; i < n_secrets + n_instance + n_common; i++) {
-    std::string s(p);
-    p += s.size() + 1;
-    if (i < n_secrets) st.secrets.push_back(s);
-    else if (i < n_secrets + n_instance) st.instance.push_back(s);
-    else st.common.push_back(s);
+  // every index of the description is checked here, once: the classes behind it index with them freely
+  if (!name || !label || n_secrets < 0 || n_instance < 0 || n_common < 0 || n_constraints < 0) return nullptr;
+  const int n_points = n_instance + n_common;
+  if ((n_secrets + n_points) && !labels) return nullptr;
+  if (n_constraints) {
+    if (!lhs || !cons_off || cons_off[0] != 0) return nullptr;
+    for (int i = 0; i < n_constraints; i++)
+      if (lhs[i] < 0 || lhs[i] >= n_points || cons_off[i + 1] < cons_off[i]) return nullptr;
+    if (cons_off[n_constraints] && (!term_scalar || !term_point)) return nullptr;
+    for (int t = 0; t < cons_off[n_constraints]; t++)
+      if (term_scalar[t] < 0 || term_scalar[t] >= n_secrets || term_point[t] < 0 || term_point[t] >= n_points) return nullptr;
   }
-  for (int i = 0; i < n_constraints; i++) {
-    LinComb lc;
-    for (int t = cons_off[i]; t < cons_off[i + 1]; t++) lc.push_back(std::make_pair((int)term_scalar[t], (int)term_point[t]));
-    st.constraints.push_back(std::make_pair((int)lhs[i], lc));
+  zkph_statement* h = nullptr;
+  try {
+    h = new zkph_statement();
+    Statement& st = h->st;
+    st.name = name;
+    st.label = label;
+    const char* p = labels;
+    for (int i = 0; i < n_secrets + n_points; i++) {
+      std::string s(p);
+      p += s.size() + 1;
+      if (i < n_secrets) st.secrets.push_back(s);
+      else if (i < n_secrets + n_instance) st.instance.push_back(s);
+      else st.common.push_back(s);
+    }
+    for (int i = 0; i < n_constraints; i++) {
+      LinComb lc;
+      for (int t = cons_off[i]; t < cons_off[i + 1]; t++) lc.push_back(std::make_pair((int)term_scalar[t], (int)term_point[t]));
+      st.constraints.push_back(std::make_pair((int)lhs[i], lc));
+    }
+  } catch (...) {
+    delete h;
+    return nullptr;
   }
   return h;
 }
@@ -63,16 +91,19 @@ extern "C" int32_t zkph_prove(zkp_ctx* ctx, const zkph_statement* h, const uint8
                               const uint8_t* secrets, const uint64_t* points, const uint8_t* seed, size_t seed_len,
                               int32_t batchable, uint8_t* encodings, uint8_t* challenge, uint8_t* commitments,
                               uint8_t* responses, uint8_t* blindings_out) {
+  return guarded([&]() -> int32_t {
   zkph_transcript tr;
   tr.t = Transcript(tl, tl_len);
   return zkph_prove_t(ctx, h, &tr, secrets, points, seed, seed_len, batchable, encodings, challenge, commitments,
                       responses, blindings_out);
+  });
 }
 
 extern "C" int32_t zkph_prove_t(zkp_ctx* ctx, const zkph_statement* h, zkph_transcript* tr, const uint8_t* secrets,
                                 const uint64_t* points, const uint8_t* seed, size_t seed_len, int32_t batchable,
                                 uint8_t* encodings, uint8_t* challenge, uint8_t* commitments, uint8_t* responses,
                                 uint8_t* blindings_out) {
+  return guarded([&]() -> int32_t {
   const Statement& st = h->st;
   Transcript& t = tr->t;
   const size_t m = st.secrets.size(), p = st.num_points(), k = st.constraints.size();
@@ -109,6 +140,7 @@ extern "C" int32_t zkph_prove_t(zkp_ctx* ctx, const zkph_statement* h, zkph_tran
   if (blindings_out)
     for (size_t i = 0; i < m; i++) pr.last_blindings[i].to_bytes(blindings_out + 32 * i);
   return PROOF_OK;
+  });
 }
 
 static std::vector<Enc> load_encs(const uint8_t* b, size_t n) {
@@ -120,13 +152,16 @@ static std::vector<Enc> load_encs(const uint8_t* b, size_t n) {
 extern "C" int32_t zkph_verify_compact(zkp_ctx* ctx, const zkph_statement* h, const uint8_t* tl, size_t tl_len,
                                        const uint8_t* points_enc, const uint8_t* challenge, const uint8_t* responses,
                                        size_t n_responses) {
+  return guarded([&]() -> int32_t {
   zkph_transcript tr;
   tr.t = Transcript(tl, tl_len);
   return zkph_verify_compact_t(ctx, h, &tr, points_enc, challenge, responses, n_responses);
+  });
 }
 extern "C" int32_t zkph_verify_compact_t(zkp_ctx* ctx, const zkph_statement* h, zkph_transcript* tr,
                                          const uint8_t* points_enc, const uint8_t* challenge, const uint8_t* responses,
                                          size_t n_responses) {
+  return guarded([&]() -> int32_t {
   const Statement& st = h->st;
   CompactProof cp;
   // Scalar deserialisation in the reference rejects non-canonical bytes; mirror that as a failure
@@ -135,21 +170,25 @@ extern "C" int32_t zkph_verify_compact_t(zkp_ctx* ctx, const zkph_statement* h, 
   for (size_t i = 0; i < n_responses; i++)
     if (!Scalar::from_canonical_bytes(&cp.responses[i], responses + 32 * i)) return VerificationFailure;
   return stmt_verify_compact(ctx, st, &tr->t, load_encs(points_enc, st.num_points()), cp);
+  });
 }
 
 extern "C" int32_t zkph_verify_batchable(zkp_ctx* ctx, const zkph_statement* h, const uint8_t* tl, size_t tl_len,
                                          const uint8_t* points_enc, const uint8_t* commitments, size_t n_commitments,
                                          const uint8_t* responses, size_t n_responses, const uint8_t* seed,
                                          size_t seed_len) {
+  return guarded([&]() -> int32_t {
   zkph_transcript tr;
   tr.t = Transcript(tl, tl_len);
   return zkph_verify_batchable_t(ctx, h, &tr, points_enc, commitments, n_commitments, responses, n_responses, seed,
                                  seed_len);
+  });
 }
 extern "C" int32_t zkph_verify_batchable_t(zkp_ctx* ctx, const zkph_statement* h, zkph_transcript* tr,
                                            const uint8_t* points_enc, const uint8_t* commitments, size_t n_commitments,
                                            const uint8_t* responses, size_t n_responses, const uint8_t* seed,
                                            size_t seed_len) {
+  return guarded([&]() -> int32_t {
   const Statement& st = h->st;
   BatchableProof bp;
   bp.commitments = load_encs(commitments, n_commitments);
@@ -158,26 +197,28 @@ extern "C" int32_t zkph_verify_batchable_t(zkp_ctx* ctx, const zkph_statement* h
     if (!Scalar::from_canonical_bytes(&bp.responses[i], responses + 32 * i)) return VerificationFailure;
   Rng rng(seed, seed_len);
   return stmt_verify_batchable(ctx, st, &tr->t, load_encs(points_enc, st.num_points()), bp, rng);
+  });
 }
 
 extern "C" int32_t zkph_batch_verify(zkp_ctx* ctx, const zkph_statement* h, const uint8_t* tl, size_t tl_len, size_t N,
                                      const uint8_t* instance_enc, const uint8_t* common_enc, const uint8_t* commitments,
                                      const uint8_t* responses, const uint8_t* seed, size_t seed_len, int32_t threads,
                                      uint8_t* coeff_out, uint8_t* points_out, double* host_seconds) {
+  return guarded([&]() -> int32_t {
   const Statement& st = h->st;
   const size_t m = st.secrets.size(), k = st.constraints.size(), ni = st.instance.size(), nc = st.common.size();
   auto t0 = std::chrono::steady_clock::now();
   std::vector<BatchableProof> proofs(N);
-  std::vector<uint8_t> noncanon(1, 0);
+  std::atomic<int> noncanon(0);
   parallel_for(N, threads, [&](size_t lo, size_t hi, int) {
     for (size_t j = lo; j < hi; j++) {
       proofs[j].commitments = load_encs(commitments + j * k * 32, k);
       proofs[j].responses.resize(m);
       for (size_t i = 0; i < m; i++)
-        if (!Scalar::from_canonical_bytes(&proofs[j].responses[i], responses + (j * m + i) * 32)) noncanon[0] = 1;
+        if (!Scalar::from_canonical_bytes(&proofs[j].responses[i], responses + (j * m + i) * 32)) noncanon.store(1);
     }
   });
-  if (noncanon[0]) return VerificationFailure;
+  if (noncanon.load()) return VerificationFailure;
   std::vector<Transcript> transcripts(N, Transcript(tl, tl_len));
   Rng rng(seed, seed_len);
   ProofError err;
@@ -220,49 +261,7 @@ extern "C" int32_t zkph_batch_verify(zkp_ctx* ctx, const zkph_statement* h, cons
   if (rc == ZKP_ERR_POINT) return VerificationFailure;
   if (rc != ZKP_OK) return EngineFailure;
   return accept ? PROOF_OK : VerificationFailure;
-}
-
-extern "C" int32_t zkph_batch_verify_device(zkp_ctx* ctx, const zkph_statement* h, const uint8_t* tl, size_t tl_len,
-                                            size_t N, const uint8_t* instance_enc, const uint8_t* common_enc,
-                                            const uint8_t* commitments, const uint8_t* responses,
-                                            const uint8_t* rho_seed32, uint8_t* coeff_out, uint8_t* points_out) {
-  const Statement& st = h->st;
-  // batch-wide transcript prefix: Transcript::new(label), dom-sep, scalar labels (macros.rs:346-350)
-  Transcript t(tl, tl_len);
-  domain_sep(t, st.label);
-  for (auto& s : st.secrets) append_scalar_var(t, s);
-  uint32_t prefix[53];
-  t.export_state(prefix);
-  std::string labels;
-  for (auto& s : st.instance) labels += s + std::string(1, '\0');
-  for (auto& s : st.common) labels += s + std::string(1, '\0');
-  std::vector<int32_t> lhs, off(1, 0), ts, tp;
-  for (auto& c : st.constraints) {
-    lhs.push_back(c.first);
-    for (auto& term : c.second) {
-      ts.push_back(term.first);
-      tp.push_back(term.second);
-    }
-    off.push_back((int32_t)ts.size());
-  }
-  zkp_statement_desc d;
-  d.m = (int32_t)st.secrets.size();
-  d.ni = (int32_t)st.instance.size();
-  d.nc = (int32_t)st.common.size();
-  d.k = (int32_t)st.constraints.size();
-  d.labels = labels.c_str();
-  d.lhs = lhs.data();
-  d.cons_off = off.data();
-  d.term_scalar = ts.data();
-  d.term_point = tp.data();
-  int32_t accept = 0;
-  int64_t bad = -1;
-  int32_t rc = zkp_batch_verify_proofs(ctx, &d, prefix, N, instance_enc, common_enc, commitments, responses, rho_seed32,
-                                       &accept, &bad, coeff_out, points_out);
-  if (rc == ZKP_ERR_POINT || rc == ZKP_ERR_SCALAR) return VerificationFailure;
-  if (rc == ZKP_ERR_SIZE) return BatchSizeMismatch;
-  if (rc != ZKP_OK) return EngineFailure;
-  return accept ? PROOF_OK : VerificationFailure;
+  });
 }
 
 // statement -> flat descriptor of zkp_b200.h (labels of instance ++ common points, constraint CSR)
@@ -293,9 +292,34 @@ struct flat_stmt {
   }
 };
 
+extern "C" int32_t zkph_batch_verify_device(zkp_ctx* ctx, const zkph_statement* h, const uint8_t* tl, size_t tl_len,
+                                            size_t N, const uint8_t* instance_enc, const uint8_t* common_enc,
+                                            const uint8_t* commitments, const uint8_t* responses,
+                                            const uint8_t* rho_seed32, uint8_t* coeff_out, uint8_t* points_out) {
+  return guarded([&]() -> int32_t {
+  const Statement& st = h->st;
+  // batch-wide transcript prefix: Transcript::new(label), dom-sep, scalar labels (macros.rs:346-350)
+  Transcript t(tl, tl_len);
+  domain_sep(t, st.label);
+  for (auto& s : st.secrets) append_scalar_var(t, s);
+  uint32_t prefix[53];
+  t.export_state(prefix);
+  flat_stmt f(st);
+  int32_t accept = 0;
+  int64_t bad = -1;
+  int32_t rc = zkp_batch_verify_proofs(ctx, &f.d, prefix, N, instance_enc, common_enc, commitments, responses, rho_seed32,
+                                       &accept, &bad, coeff_out, points_out);
+  if (rc == ZKP_ERR_POINT || rc == ZKP_ERR_SCALAR) return VerificationFailure;
+  if (rc == ZKP_ERR_SIZE) return BatchSizeMismatch;
+  if (rc != ZKP_OK) return EngineFailure;
+  return accept ? PROOF_OK : VerificationFailure;
+  });
+}
+
 extern "C" int32_t zkph_prove_many_device(zkp_ctx* ctx, const zkph_statement* h, const uint8_t* tl, size_t tl_len, size_t N,
                                           const uint8_t* secrets, const uint64_t* points, const uint8_t* entropy,
                                           uint8_t* encodings, uint8_t* commitments, uint8_t* responses) {
+  return guarded([&]() -> int32_t {
   const Statement& st = h->st;
   // batch-wide transcript prefix: Transcript::new(label), dom-sep, scalar labels (macros.rs:206-214)
   Transcript t(tl, tl_len);
@@ -308,11 +332,13 @@ extern "C" int32_t zkph_prove_many_device(zkp_ctx* ctx, const zkph_statement* h,
   if (rc == ZKP_ERR_SIZE) return BatchSizeMismatch;
   if (rc != ZKP_OK) return EngineFailure;
   return PROOF_OK;
+  });
 }
 
 extern "C" int32_t zkph_prove_many(zkp_ctx* ctx, const zkph_statement* h, const uint8_t* tl, size_t tl_len, size_t N,
                                    const uint8_t* secrets, const uint64_t* points, const uint8_t* entropy,
                                    int32_t threads, uint8_t* encodings, uint8_t* commitments, uint8_t* responses) {
+  return guarded([&]() -> int32_t {
   const Statement& st = h->st;
   const size_t m = st.secrets.size(), p = st.num_points(), k = st.constraints.size();
   std::vector<Scalar> sec(N * m);
@@ -332,6 +358,7 @@ extern "C" int32_t zkph_prove_many(zkp_ctx* ctx, const zkph_statement* h, const 
     }
   });
   return PROOF_OK;
+  });
 }
 
 extern "C" void zkph_scalar_mul(uint8_t* out32, const uint8_t* a32, const uint8_t* b32) {

@@ -132,6 +132,8 @@ class Statement:
         self._keep = (labels, lhs, off, ts, tp)
         self._h = lib.zkph_statement_new(name.encode(), label.encode(), labels, len(self.secrets), len(self.instance),
                                          len(self.common), len(self.constraints), _p(lhs), _p(off), _p(ts), _p(tp))
+        if not self._h:
+            raise ValueError("inconsistent statement description (zkph_statement_new refused it)")
         self.m, self.p, self.k = len(self.secrets), len(self.points), len(self.constraints)
 
     def __del__(self):
