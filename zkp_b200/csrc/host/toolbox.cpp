@@ -1,5 +1,6 @@
 #include "toolbox.hpp"
 
+#include <exception>
 #include <functional>
 #include <thread>
 
@@ -16,14 +17,33 @@ void parallel_for(size_t n, int threads, const std::function<void(size_t, size_t
     fn(0, n, 0);
     return;
   }
+  // an exception inside a worker (a failed allocation) is carried back to the caller instead of ending the process
   std::vector<std::thread> pool;
+  std::vector<std::exception_ptr> failed(threads);
   size_t per = n / threads, rem = n % threads, lo = 0;
   for (int t = 0; t < threads; t++) {
     size_t cnt = per + ((size_t)t < rem ? 1 : 0);
-    pool.emplace_back(fn, lo, lo + cnt, t);
+    const size_t a = lo, b = lo + cnt;
+    try {
+      pool.emplace_back([&fn, &failed, a, b, t]() {
+        try {
+          fn(a, b, t);
+        } catch (...) {
+          failed[t] = std::current_exception();
+        }
+      });
+    } catch (...) {   // no more threads: this range runs here
+      try {
+        fn(a, b, t);
+      } catch (...) {
+        failed[t] = std::current_exception();
+      }
+    }
     lo += cnt;
   }
   for (auto& th : pool) th.join();
+  for (auto& f : failed)
+    if (f) std::rethrow_exception(f);
 }
 
 Rng::Rng(const uint8_t* seed, size_t len) {

@@ -76,7 +76,7 @@ extern "C" int32_t zkph_batchable_proofs_parse(const uint8_t* buf, size_t len, s
   if (first_bad) *first_bad = -1;
   if (N && (!buf || (k && !commitments) || (m && !responses))) return ZKPH_MALFORMED;
   const size_t one = zkph_batchable_proof_size(k, m);
-  if (N && len / N == one && len % N == 0) {
+  if (N && len / N == one && len % N == 0) try {
     // the common case: every proof has the expected shape, so proof j sits at j * one -- parse in parallel
     int nthr = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
     if (nthr < 1) nthr = 1;
@@ -105,6 +105,8 @@ extern "C" int32_t zkph_batchable_proofs_parse(const uint8_t* buf, size_t len, s
     if (rc == PROOF_OK) return PROOF_OK;
     if (rc == ZKPH_MALFORMED) { if (first_bad) *first_bad = fb; return rc; }
     // fall through to the sequential walk for the exact error of a batch with irregular shapes
+  } catch (...) {
+    // no memory for the worker bookkeeping: the sequential walk below needs none
   }
   size_t off = 0;
   for (size_t j = 0; j < N; j++) {
