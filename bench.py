@@ -176,16 +176,28 @@ def bind_to_gpu_numa_node(local_rank):
     return None
 
 
-def cpu_baseline(sc_rows, pt_enc, sample_proofs, threads, steps=1):
-    """The C port of the reference's CPU path (oracle/_ref, kind "port") on a bounded sample of the SAME
-    workload: the first `sample_proofs` proofs' columns of every row, i.e. one MSM of 24*sample terms."""
+def cpu_backend():
+    """Which restatement of the reference's CPU path this host can run: the 4-way vector one (the reference's
+    `simd_backend`, oracle/c/ref_ifma.h: needs AVX-512 IFMA) or the serial u64 one (its default backend)."""
     from oracle import cref
+    if cref.simd_available():
+        return True, "simd_backend restatement (4-way AVX-512 IFMA point arithmetic, serial decompression)"
+    return False, "u64 serial backend restatement (this CPU lacks avx512ifma: no vector backend)"
+
+
+def cpu_baseline(sc_rows, pt_enc, sample_proofs, threads, steps=1, simd=None):
+    """The C port of the reference's CPU path (oracle/_ref, kind "port") on a bounded sample of the SAME
+    workload: the first `sample_proofs` proofs' columns of every row, i.e. one MSM of 24*sample terms.
+    simd=None picks the vector backend when the CPU has it (the stronger baseline)."""
+    from oracle import cref
+    if simd is None:
+        simd = cpu_backend()[0]
     s = np.ascontiguousarray(sc_rows[:, :sample_proofs]).reshape(-1, 32)
     p = np.ascontiguousarray(pt_enc[:, :sample_proofs]).reshape(-1, 32)
     best = 1e30
     for _ in range(steps):
         t = time.perf_counter()
-        out = cref.msm_vartime(s, p, threads=threads)
+        out = cref.msm_vartime(s, p, threads=threads, simd=simd)
         best = min(best, time.perf_counter() - t)
         assert out is not None
     return sample_proofs / best, best
@@ -198,7 +210,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log2-proofs", type=int, default=21, help="proofs per GPU (default 2^21)")
-    ap.add_argument("--cpu-sample-log2", type=int, default=14, help="proofs in the CPU baseline sample")
+    ap.add_argument("--cpu-sample-log2", type=int, default=16, help="proofs in the CPU baseline sample")
     ap.add_argument("--window", type=int, default=0, help="tuning: force the Pippenger window width")
     ap.add_argument("--chunk", type=int, default=0, help="tuning: force the accumulate work-item length")
     ap.add_argument("--no-proofs-leg", action="store_true", help="skip the e2e_from_proofs leg (real proofs, device front end)")
@@ -240,13 +252,17 @@ def main():
         rates = [cpu_baseline(sc_rows, pt_rows, sample, host_threads)[0] for _ in range(args.steps)]
         dt = (time.perf_counter() - t0) / args.steps
         v = float(np.median(rates))
+        simd, backend = cpu_backend()
+        u64_v = cpu_baseline(sc_rows, pt_rows, sample, host_threads, simd=False)[0] if simd else v
         line = {"impl": "reference", "metric": "proofs verified/sec (batch) CMZ13 10-attr credential", "value": v,
                 "unit": "proofs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u64", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": v, "unit": "proofs/s", "cores": host_threads, "kind": "port",
-                                 "sample": "%d proofs (%d-term MSM) per step, C port of dalek u64 serial backend, %d threads"
-                                           % (sample, ROWS * sample, host_threads)},
+                                 "backend": backend, "u64_serial_backend_value": u64_v,
+                                 "sample": "%d proofs (%d-term MSM) per step, C port of dalek's CPU algorithms (%s), %d threads"
+                                           % (sample, ROWS * sample, "vector backend" if simd else "u64 serial backend",
+                                              host_threads)},
                 "e2e": {"value": v, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -487,6 +503,8 @@ def main():
         # the CPU baseline is taken at N = 1 only (the other ranks would compete for the same host cores)
         cpu_v, cpu_t = cpu_baseline(sc_rows, pt_rows, sample, host_threads) if world == 1 else (None, 0.0)
         cpu_1 = cpu_baseline(sc_rows, pt_rows, max(256, sample // 8), 1)[0] if world == 1 else None   # what `cargo bench` would see
+        cpu_simd, cpu_backend_name = cpu_backend() if world == 1 else (False, "")
+        cpu_u64 = (cpu_baseline(sc_rows, pt_rows, sample, host_threads, simd=False)[0] if cpu_simd else cpu_v) if world == 1 else None
         line = {"metric": "proofs verified/sec (batch) CMZ13 10-attr credential", "value": value, "unit": "proofs/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 (8x32-bit saturated limbs, 64-bit products)",
@@ -496,10 +514,12 @@ def main():
                         "api": "zkp_batch_verify (C ABI), pinned host buffers"},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
                 "cpu_baseline": ({"value": cpu_v, "unit": "proofs/s", "cores": host_threads, "kind": "port",
-                                  "single_thread_value": cpu_1,
+                                  "single_thread_value": cpu_1, "backend": cpu_backend_name,
+                                  "u64_serial_backend_value": cpu_u64,
                                   "sample": "first %d proofs of this workload (one %d-term MSM), C port of dalek's "
-                                            "serial u64 backend sharded over %d threads, %.2f s"
-                                            % (sample, ROWS * sample, host_threads, cpu_t)} if world == 1 else
+                                            "CPU algorithms (%s) sharded over %d threads, %.2f s"
+                                            % (sample, ROWS * sample, "vector backend" if cpu_simd else "u64 serial backend",
+                                               host_threads, cpu_t)} if world == 1 else
                                  {"value": None, "unit": "proofs/s", "cores": 0, "kind": "port",
                                   "sample": "taken at N = 1 only (bench.py --gpus 1)"}),
                 "accept_bits": accept_bitmap, "setup_s": setup_s, "numa_binding_rank0": numa}

@@ -11,7 +11,8 @@ SRC = os.path.join(HERE, "ref_u64.c")
 
 
 def build(force=False):
-    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= os.path.getmtime(SRC):
+    newest = max(os.path.getmtime(SRC), os.path.getmtime(os.path.join(HERE, "ref_ifma.h")))
+    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= newest:
         return LIB
     os.makedirs(OUTDIR, exist_ok=True)
     # -march=native is deliberately NOT used: the .so is built here and runs on the GPU box's host CPU

@@ -10,6 +10,7 @@
  *   scalar.rs                        to_radix_16, non_adjacent_form(5), to_radix_2w
  *   backend/serial/scalar_mul/       straus.rs (CT radix-16; vartime NAF-5), pippenger.rs (w = 6/7/8)
  *   edwards.rs                       optional_multiscalar_mul: size < 190 -> Straus, else Pippenger
+ *   backend/vector                   the 4-way vector field and point types of `simd_backend`: ref_ifma.h (included below)
  * as reached from /root/reference/src/toolbox/prover.rs:94, verifier.rs:90,97,162,164,
  * batch_verifier.rs:219-230, toolbox/mod.rs:180,204.  The crate sources are not under /root/reference
  * (Cargo dependency), so this follows the published algorithms; it is pinned by the same golden vectors as
@@ -337,6 +338,8 @@ static void pippenger(ge* out, const uint8_t* scalars, const ge* pts, size_t n) 
   free(dig); free(pn); free(buckets);
 }
 
+#include "ref_ifma.h"   /* the 4-way vector restatement (simd_backend); defines REF_HAVE_SIMD and ref_simd_available() */
+
 static pthread_once_t init_once = PTHREAD_ONCE_INIT;
 static void init_consts(void) {
   static const uint8_t d[32] = {0xa3, 0x78, 0x59, 0x13, 0xca, 0x4d, 0xeb, 0x75, 0xab, 0xd8, 0x41, 0x41, 0x4d, 0x0a, 0x70, 0x00,
@@ -354,33 +357,56 @@ static void init_consts(void) {
 
 /* ---- exported C API (ctypes) ---- */
 /* optional_multiscalar_mul over encodings with dalek's dispatch; returns 0 ok / 1 invalid point (first_bad) */
-static int msm_vartime_points(ge* out, const uint8_t* scalars, const uint8_t* points, size_t n, int64_t* first_bad) {
+/* simd = 0: the serial u64 backend; simd = 1: the vector backend (decompression is serial in both, as in the crate) */
+static int msm_vartime_points(ge* out, const uint8_t* scalars, const uint8_t* points, size_t n, int64_t* first_bad, int simd) {
   ge* pts = (ge*)malloc((n ? n : 1) * sizeof(ge));
   for (size_t i = 0; i < n; i++)
     if (!ristretto_decode(&pts[i], points + 32 * i)) { if (first_bad) *first_bad = (int64_t)i; free(pts); return 1; }
+#if REF_HAVE_SIMD
+  if (simd) msm_dispatch_simd(out, scalars, pts, n); else
+#endif
   if (n < 190) straus_vt(out, scalars, pts, n); else pippenger(out, scalars, pts, n);
   free(pts);
   return 0;
 }
-int ref_msm_vartime(const uint8_t* scalars, const uint8_t* points, size_t n, uint8_t* out32, int64_t* first_bad) {
+static int msm_vartime_any(const uint8_t* scalars, const uint8_t* points, size_t n, uint8_t* out32, int64_t* first_bad, int simd) {
   pthread_once(&init_once, init_consts);
   ge r;
-  int rc = msm_vartime_points(&r, scalars, points, n, first_bad);
+  int rc = msm_vartime_points(&r, scalars, points, n, first_bad, simd);
   if (rc) return rc;
   ristretto_encode(out32, &r);
   return 0;
 }
+int ref_msm_vartime(const uint8_t* scalars, const uint8_t* points, size_t n, uint8_t* out32, int64_t* first_bad) {
+  return msm_vartime_any(scalars, points, n, out32, first_bad, 0);
+}
+/* the same through the vector backend; -1 when this cpu cannot run it */
+int ref_msm_vartime_simd(const uint8_t* scalars, const uint8_t* points, size_t n, uint8_t* out32, int64_t* first_bad) {
+  if (!ref_simd_available()) return -1;
+  return msm_vartime_any(scalars, points, n, out32, first_bad, 1);
+}
 
-typedef struct { const uint8_t *s, *p; size_t n; ge out; int rc; int64_t bad; } shard_t;
+typedef struct { const uint8_t *s, *p; size_t n; ge out; int rc; int64_t bad; int simd; } shard_t;
 static void* shard_run(void* a) {
   shard_t* s = (shard_t*)a;
   s->bad = -1;
-  s->rc = msm_vartime_points(&s->out, s->s, s->p, s->n, &s->bad);
+  s->rc = msm_vartime_points(&s->out, s->s, s->p, s->n, &s->bad, s->simd);
   return NULL;
 }
 /* the same MSM sharded over `threads` host threads (independent sub-sums added at the end) */
+static int msm_vartime_mt_any(const uint8_t* scalars, const uint8_t* points, size_t n, int threads, uint8_t* out32,
+                              int64_t* first_bad, int simd);
 int ref_msm_vartime_mt(const uint8_t* scalars, const uint8_t* points, size_t n, int threads, uint8_t* out32,
                        int64_t* first_bad) {
+  return msm_vartime_mt_any(scalars, points, n, threads, out32, first_bad, 0);
+}
+int ref_msm_vartime_mt_simd(const uint8_t* scalars, const uint8_t* points, size_t n, int threads, uint8_t* out32,
+                            int64_t* first_bad) {
+  if (!ref_simd_available()) return -1;
+  return msm_vartime_mt_any(scalars, points, n, threads, out32, first_bad, 1);
+}
+static int msm_vartime_mt_any(const uint8_t* scalars, const uint8_t* points, size_t n, int threads, uint8_t* out32,
+                              int64_t* first_bad, int simd) {
   pthread_once(&init_once, init_consts);
   if (threads < 1) threads = 1;
   if ((size_t)threads > n) threads = n ? (int)n : 1;
@@ -389,7 +415,7 @@ int ref_msm_vartime_mt(const uint8_t* scalars, const uint8_t* points, size_t n, 
   size_t per = n / threads, rem = n % threads, off = 0;
   for (int t = 0; t < threads; t++) {
     size_t cnt = per + ((size_t)t < rem ? 1 : 0);
-    sh[t].s = scalars + 32 * off; sh[t].p = points + 32 * off; sh[t].n = cnt;
+    sh[t].s = scalars + 32 * off; sh[t].p = points + 32 * off; sh[t].n = cnt; sh[t].simd = simd;
     off += cnt;
     pthread_create(&th[t], NULL, shard_run, &sh[t]);
   }

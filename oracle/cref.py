@@ -15,6 +15,10 @@ def load():
         vp, sz = ctypes.c_void_p, ctypes.c_size_t
         lib.ref_msm_vartime.argtypes = [vp, vp, sz, vp, ctypes.POINTER(ctypes.c_int64)]
         lib.ref_msm_vartime_mt.argtypes = [vp, vp, sz, ctypes.c_int, vp, ctypes.POINTER(ctypes.c_int64)]
+        lib.ref_msm_vartime_simd.argtypes = [vp, vp, sz, vp, ctypes.POINTER(ctypes.c_int64)]
+        lib.ref_msm_vartime_mt_simd.argtypes = [vp, vp, sz, ctypes.c_int, vp, ctypes.POINTER(ctypes.c_int64)]
+        lib.ref_simd_available.restype = ctypes.c_int
+        lib.ref_simd_selftest_fe.argtypes = [vp, vp, vp, vp]
         lib.ref_msm_ct_batched.argtypes = [vp, vp, vp, sz, vp]
         lib.ref_msm_vartime_batched.argtypes = [vp, vp, vp, sz, vp, vp]
         lib.ref_decompress.argtypes = [vp, sz, vp, vp]
@@ -35,17 +39,41 @@ def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
-def msm_vartime(scalars, points, threads=1):
-    """optional_multiscalar_mul with dalek's dispatch; returns encoding bytes or None."""
+def simd_available():
+    """True when this CPU can run the 4-way vector restatement of the reference's simd_backend (oracle/c/ref_ifma.h)."""
+    return bool(load().ref_simd_available())
+
+
+def msm_vartime(scalars, points, threads=1, simd=False):
+    """optional_multiscalar_mul with dalek's dispatch; returns encoding bytes or None.
+    simd=True runs the vector backend (raises when the CPU lacks AVX-512 IFMA: callers check simd_available())."""
     lib = load()
     s, p = _a(scalars), _a(points)
     out = np.zeros(32, dtype=np.uint8)
     bad = ctypes.c_int64(-1)
-    if threads == 1:
+    if simd:
+        if threads == 1:
+            rc = lib.ref_msm_vartime_simd(_p(s), _p(p), s.shape[0], _p(out), ctypes.byref(bad))
+        else:
+            rc = lib.ref_msm_vartime_mt_simd(_p(s), _p(p), s.shape[0], int(threads), _p(out), ctypes.byref(bad))
+        if rc < 0:
+            raise RuntimeError("vector backend unavailable on this CPU (needs avx2, avx512f, avx512vl, avx512ifma)")
+    elif threads == 1:
         rc = lib.ref_msm_vartime(_p(s), _p(p), s.shape[0], _p(out), ctypes.byref(bad))
     else:
         rc = lib.ref_msm_vartime_mt(_p(s), _p(p), s.shape[0], int(threads), _p(out), ctypes.byref(bad))
     return None if rc else out.tobytes()
+
+
+def simd_field_selftest(a, b):
+    """(a*b, a*a) of four field-element pairs through the vector field; a, b: uint64 [4][5] radix-2^51 limbs."""
+    lib = load()
+    a = np.ascontiguousarray(a, dtype=np.uint64).reshape(4, 5)
+    b = np.ascontiguousarray(b, dtype=np.uint64).reshape(4, 5)
+    m, q = np.zeros((4, 5), np.uint64), np.zeros((4, 5), np.uint64)
+    if lib.ref_simd_selftest_fe(_p(a), _p(b), _p(m), _p(q)) != 0:
+        raise RuntimeError("vector backend unavailable on this CPU")
+    return m, q
 
 
 def msm_ct_batched(scalars, points, offsets):

@@ -97,6 +97,58 @@ def test_msm_kats_python_and_c():
         assert cref.msm_vartime(sc, pts, threads=4).hex() == case["expected"]
 
 
+def _needs_vector_cpu():
+    if not cref.simd_available():
+        pytest.skip("this CPU lacks avx512ifma/avx512vl: the vector restatement of simd_backend cannot run here")
+
+
+def test_vector_backend_field_against_big_integers():
+    """oracle/c/ref_ifma.h: four-lane radix-2^51 multiplication and squaring (vpmadd52) against Python integers,
+    including the extreme operands p-1, p-2, 0, 1 and outputs inside the bound the next multiplication needs."""
+    _needs_vector_cpu()
+    P = 2**255 - 19
+    rnd = random.Random(5)
+    limbs = lambda x: [(x >> (51 * i)) & ((1 << 51) - 1) for i in range(5)]
+    val = lambda l: sum(int(v) << (51 * i) for i, v in enumerate(l)) % P
+    for t in range(600):
+        a = [rnd.randrange(P) for _ in range(4)]
+        b = [rnd.randrange(P) for _ in range(4)]
+        if t == 0:
+            a, b = [0, 1, P - 1, P - 2], [P - 1, P - 1, P - 1, 0]
+        if t == 1:   # unreduced but legal inputs: every limb at 2^51 - 1 (the value 2^255 - 1 = p + 18)
+            a = b = [2**255 - 1] * 4
+        m, q = cref.simd_field_selftest([limbs(x) for x in a], [limbs(x) for x in b])
+        for j in range(4):
+            assert val(m[j]) == a[j] * b[j] % P, (t, j)
+            assert val(q[j]) == a[j] * a[j] % P, (t, j)
+            assert max(int(v) for v in m[j]) < 2**52 and max(int(v) for v in q[j]) < 2**52
+
+
+def test_vector_backend_msm_equals_serial_port():
+    """The vector restatement of the reference's simd_backend gives the bytes of the serial u64 port -- on the golden
+    KATs and on seeded MSMs at every dispatch boundary (Straus < 190 <= Pippenger; window 6 / 7 / 8 at 500 / 800),
+    single- and multi-threaded; an undecodable point fails the same way."""
+    _needs_vector_cpu()
+    for kat in U.golden("msm_kat.json")["kats"]:
+        sc, pt = _h(kat["scalars"]), _h(kat["points"])
+        assert cref.msm_vartime(sc, pt, simd=True).hex() == kat["expected"], kat["n"]
+    base = U.base_points(64)
+    for n in (0, 1, 2, 5, 64, 189, 190, 300, 499, 500, 799, 800, 3000):
+        sc = U.random_scalars(n, seed=n + 1)
+        pts = np.frombuffer(b"".join(base[(7 * i + n) % 64] for i in range(n)), dtype=np.uint8).reshape(-1, 32)
+        want = cref.msm_vartime(sc, pts)
+        assert cref.msm_vartime(sc, pts, simd=True) == want, n
+        assert cref.msm_vartime(sc, pts, threads=3, simd=True) == want, n
+    for case in U.golden("msm_seeded.json")["cases"]:
+        sc = U.random_scalars(case["n"], seed=case["seed"])
+        bp = U.base_points(case["K"])
+        pts = np.frombuffer(b"".join(bp[i % case["K"]] for i in range(case["n"])), dtype=np.uint8).reshape(-1, 32)
+        assert cref.msm_vartime(sc, pts, threads=4, simd=True).hex() == case["expected"]
+    bad = np.array(pts[:300])
+    bad[123] = 0xFF
+    assert cref.msm_vartime(sc[:300], bad, simd=True) is None
+
+
 def test_c_port_codec_and_batched():
     g = U.golden("rfc9496.json")
     good = [bytes.fromhex(x) for x in g["multiples_of_generator"]] + U.base_points(30)
