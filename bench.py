@@ -497,7 +497,7 @@ def main():
                                          (bucket_adds_per_proof(int(stages.get("window", 19))) * N / madd_rate / (acc_ms * 1e-3))
                                          if acc_ms > 0 else None},
                     "stage_ms_unfused_profile_mode": stages, "dominant_stage_unfused": dom}
-        sample = 1 << args.cpu_sample_log2
+        sample = min(1 << args.cpu_sample_log2, N)
         sc_rows = sc.view(np.uint8).reshape(ROWS, N, 32)
         pt_rows = inst_points.numpy().reshape(ROWS, N, 32)
         # the CPU baseline is taken at N = 1 only (the other ranks would compete for the same host cores)

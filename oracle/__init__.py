@@ -41,5 +41,5 @@ What pins the oracle instead (tests/test_oracle_*.py, all run on CPU):
 Modules: field25519 / ristretto (group), scalar (mod l + dalek recodings), msm (dalek's Straus CT, Straus
 vartime NAF-5, Pippenger), merlin (Keccak-f, STROBE-128, Transcript, TranscriptRng), toolbox (Prover /
 Verifier / BatchVerifier flows), sodium (libsodium loader for cross-checks), c/ (C restatement of the
-serial u64 backend = the timed CPU baseline).
+serial u64 backend and, in ref_ifma.h, of the 4-way vector `simd_backend` = the timed CPU baselines).
 """
