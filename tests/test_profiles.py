@@ -10,7 +10,8 @@ def _load(name):
 
 
 def test_bench_records_carry_the_contract_keys():
-    for name, gpus in (("bench_r01_s2.json", 1), ("bench_r01_s2_2gpu.json", 2), ("bench_r01_s2_8gpu.json", 8)):
+    for name, gpus in (("bench_r01_s3.json", 1), ("bench_r01_s2.json", 1), ("bench_r01_s2_2gpu.json", 2),
+                       ("bench_r01_s2_8gpu.json", 8)):
         d = _load(name)
         for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
                     "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
@@ -34,3 +35,9 @@ def test_roofline_traffic_record_matches_the_bench_size():
     assert abs(p["traffic_bytes_per_launch"] - sum(p["traffic_bytes_each_launch"]) / 2) < 1
     assert d["roofline"]["traffic"] == p["traffic_bytes_per_launch"]
     assert p["algorithmic_bytes_per_launch"] == d["roofline"]["algorithmic_bytes_per_launch"]
+
+
+def test_cpu_baseline_of_the_latest_record_names_its_backend():
+    c = _load("bench_r01_s3.json")["cpu_baseline"]
+    assert c["kind"] == "port" and c["cores"] >= 1 and "backend" in c
+    assert c["value"] >= c["u64_serial_backend_value"] > c["single_thread_value"] > 0
