@@ -178,6 +178,12 @@ int32_t zkp_selftest_bv_script(const zkp_statement_desc* st, const uint32_t* pre
                                const uint8_t* common_enc, const uint8_t* commitments, uint8_t* challenge_out64,
                                int32_t* n_blocks_out);
 
+/* Test hook (no GPU needed): the chunk boundaries the host-input pipeline of zkp_msm_vartime / zkp_batch_verify uses for
+ * n terms with the "chunk_terms", "phase1_percent" and "ramp_chunks" options given: bounds_out[0..count] (cap entries
+ * available), *k1_out = chunks in the first ingestion phase.  Returns the chunk count, -1 on bad arguments.           */
+int64_t zkp_selftest_chunk_schedule(size_t n, size_t chunk, int32_t phase1_percent, int32_t ramp, size_t* bounds_out,
+                                    size_t cap, size_t* k1_out);
+
 /* Self-test of the device hashing code: out32 receives Merlin's published conformance vector (a8c933f5...). */
 int32_t zkp_selftest_hash(zkp_ctx* ctx, uint8_t* out32);
 

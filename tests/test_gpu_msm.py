@@ -255,8 +255,16 @@ def test_two_phase_ingestion_and_item_balance_options(engine):
                 engine.set_option("balance", balance)
                 for chunk in (1 << 21, 4096, 5000, n // 3 + 1, n):       # 1 chunk, many, ragged, 3 chunks (odd), exactly 1
                     engine.set_option("chunk_terms", max(chunk, 1024))
-                    enc, _, _ = engine.msm_vartime(sc, pts)
-                    assert enc.hex() == case["expected"], (fused, balance, chunk)
+                    for ramp in (1, 0):                                  # ramped and uniform chunk schedules
+                        engine.set_option("ramp_chunks", ramp)
+                        enc, _, _ = engine.msm_vartime(sc, pts)
+                        assert enc.hex() == case["expected"], (fused, balance, chunk, ramp)
+                    engine.set_option("ramp_chunks", 1)
+                    for pct in (1, 30, 100):                             # phase boundary at either end and off-centre
+                        engine.set_option("phase1_percent", pct)
+                        enc, _, _ = engine.msm_vartime(sc, pts)
+                        assert enc.hex() == case["expected"], (fused, balance, chunk, pct)
+                    engine.set_option("phase1_percent", 50)
                 engine.set_option("chunk_terms", 1024)
                 enc, _, _ = engine.msm_vartime(sc[:odd], pts[:odd])
                 assert enc == exp_odd, (fused, balance)
@@ -293,6 +301,8 @@ def test_two_phase_ingestion_and_item_balance_options(engine):
     finally:
         engine.set_option("fused_sort", 1)
         engine.set_option("balance", 1)
+        engine.set_option("ramp_chunks", 1)
+        engine.set_option("phase1_percent", 50)
         engine.set_option("chunk_terms", 1 << 21)
 
 

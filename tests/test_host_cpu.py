@@ -252,3 +252,45 @@ def test_host_statement_constructor_refuses_bad_indices():
     assert not new(1, 1, 1, 1, [0], [1, 1], [0], [1])        # offsets not starting at 0
     assert not new(1, 1, 1, 2, [0, 0], [0, 1, 0], [0], [1])  # decreasing offsets
     assert not new(-1, 1, 1, 0, [0], [0], [0], [0])          # negative count
+
+
+def test_host_input_chunk_schedule_properties():
+    """The chunk schedule of the host-input pipeline (api.cu chunk_schedule, read through zkp_selftest_chunk_schedule):
+    boundaries strictly increase from 0 to n, every chunk is non-empty and at most 2 * chunk_terms long, the phase
+    boundary sits where the phase-1 share says, the ramped schedule starts (and ends its first phase) with chunks of
+    chunk_terms / 8, and the chunk count stays within a small factor of the uniform schedule's."""
+    import numpy as np
+    lib = native.load()
+    sz = ctypes.c_size_t
+    lib.zkp_selftest_chunk_schedule.argtypes = [sz, sz, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, sz,
+                                                ctypes.POINTER(sz)]
+    lib.zkp_selftest_chunk_schedule.restype = ctypes.c_int64
+    rnd = random.Random(11)
+    cases = [(50331660, 1 << 21, 50), (1, 1024, 50), (1025, 1024, 50), (2049, 1024, 1), (4097, 1024, 100),
+             (20000, 4096, 50), (20000, 5000, 50), ((1 << 31) - 2, 1 << 21, 50)]
+    cases += [(rnd.randrange(1, 1 << 24), rnd.choice([1024, 4096, 5000, 1 << 16, 1 << 21]), rnd.randrange(1, 101))
+              for _ in range(300)]
+    for n, chunk, pct in cases:
+        for ramp in (1, 0):
+            cap = n // 1024 + 64
+            b = np.zeros(cap, dtype=np.uint64)
+            k1 = sz(0)
+            cnt = lib.zkp_selftest_chunk_schedule(n, chunk, pct, ramp, b.ctypes.data, cap, ctypes.byref(k1))
+            assert cnt >= 1, (n, chunk, pct, ramp)
+            bb = [int(x) for x in b[:cnt + 1]]
+            sizes = [bb[i + 1] - bb[i] for i in range(cnt)]
+            assert bb[0] == 0 and bb[-1] == n and min(sizes) >= 1, (n, chunk, pct, ramp)
+            assert 1 <= k1.value <= cnt
+            uniform = (n + chunk - 1) // chunk
+            if ramp and n > chunk:
+                small = max(chunk // 8, 1024)
+                p1 = max(1, n // 100 * pct + (n % 100) * pct // 100)
+                assert bb[k1.value] == p1 and max(sizes) <= 2 * chunk
+                assert sizes[0] == min(small, (p1 + 1) // 2)
+                assert cnt <= uniform + 24                       # ramps add O(log) chunks, not a multiple
+                if p1 >= 8 * small:
+                    assert sizes[k1.value - 1] <= small          # phase 1 ends on a small chunk
+                if n - p1 >= 4 * small:
+                    assert sizes[k1.value] == small              # phase 2 starts on a small chunk
+            else:
+                assert cnt == uniform and max(sizes) <= chunk

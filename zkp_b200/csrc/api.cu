@@ -64,6 +64,7 @@ struct zkp_ctx {
   int bv_compiled = 1;      // batch-verification front end: host-compiled transcript script (k_bv_prepare2)
   int ingest_variant = 2;   // occupancy point of k_ingest2 (kernels.cuh ZKP_INGEST_*)
   int fused_sort = 1;  // histogram and scatter ride under the two halves of the decompression (k_ingest2)
+  int ramp_chunks = 1; // host-input pipeline: chunk sizes ramp up from chunk_terms / 8 (and down again at the end of phase 1)
   cudaStream_t sort_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
@@ -213,6 +214,8 @@ extern "C" int32_t zkp_ctx_set_option(zkp_ctx* ctx, const char* key, int64_t val
     ctx->ingest_variant = (int)value;
   } else if (!strcmp(key, "fused_sort")) {
     ctx->fused_sort = value ? 1 : 0;
+  } else if (!strcmp(key, "ramp_chunks")) {
+    ctx->ramp_chunks = value ? 1 : 0;
   } else if (!strcmp(key, "chunk_terms")) {
     if (value < 1024) return ZKP_ERR_SIZE;
     ctx->chunk_terms = (size_t)value;
@@ -578,6 +581,78 @@ static int32_t copy_range(zkp_ctx* ctx, const hseg* segs, int nseg, size_t lo, s
   return ZKP_OK;
 }
 
+// Chunk boundaries of one ingestion phase over the points [lo, hi): sizes double from `small` up to `big`, and with
+// `mirror` they shrink again towards the end.  A small first chunk starts the kernels early; a small last chunk matters
+// when the phase is copy-bound (phase 1 moves all the scalars: its H2D time equals its compute time at the bench size),
+// because the kernel of the last chunk can only start when its last byte has arrived; large chunks in between keep the
+// number of launches (one partial wave each) low.
+static void phase_bounds(size_t lo, size_t hi, size_t small, size_t big, bool mirror, std::vector<size_t>* out) {
+  const size_t len = hi - lo;
+  if (!len) return;
+  std::vector<size_t> up;
+  const size_t target = mirror ? (len + 1) / 2 : len;
+  size_t c = small, sum = 0;
+  while (sum < target) {
+    const size_t step = c < target - sum ? c : target - sum;
+    up.push_back(step);
+    sum += step;
+    if (c < big) c = 2 * c < big ? 2 * c : big;
+  }
+  size_t pos = lo;
+  for (size_t v : up) {
+    pos += v;
+    out->push_back(pos);
+  }
+  if (mirror) {
+    size_t rest = len - sum;   // <= sum, short by at most one term: taken off the first mirrored chunk(s)
+    for (size_t i = up.size(); i-- > 0 && rest;) {
+      const size_t v = up[i] < rest ? up[i] : rest;
+      pos += v;
+      rest -= v;
+      out->push_back(pos);
+    }
+  }
+}
+
+// The chunk boundaries of one host-input MSM of n > 0 terms and the number K1 of phase-1 chunks.
+static void chunk_schedule(size_t n, size_t chunk, int phase1_percent, bool ramp, std::vector<size_t>* bnd, size_t* K1) {
+  bnd->clear();
+  bnd->push_back(0);
+  if (ramp && n > chunk) {
+    const size_t pct = (size_t)phase1_percent;
+    size_t P1 = n / 100 * pct + (n % 100) * pct / 100;
+    if (P1 < 1) P1 = 1;
+    const size_t small = chunk / 8 > 1024 ? chunk / 8 : 1024;
+    phase_bounds(0, P1, small, 2 * chunk, true, bnd);
+    *K1 = bnd->size() - 1;
+    phase_bounds(P1, n, small, 2 * chunk, false, bnd);
+  } else {
+    for (size_t lo = chunk; lo < n; lo += chunk) bnd->push_back(lo);
+    bnd->push_back(n);
+    const size_t nch = bnd->size() - 1;
+    size_t k1 = (nch * (size_t)phase1_percent + 99) / 100;
+    if (k1 < 1) k1 = 1;
+    if (k1 > nch) k1 = nch;
+    *K1 = k1;
+  }
+}
+// test hook (no GPU needed): the schedule msm_from_host would use; returns the number of chunks (or -1 if cap is too small)
+extern "C" int64_t zkp_selftest_chunk_schedule(size_t n, size_t chunk, int32_t phase1_percent, int32_t ramp,
+                                               size_t* bounds_out, size_t cap, size_t* k1_out) {
+  if (!n || chunk < 1024 || phase1_percent < 1 || phase1_percent > 100 || !bounds_out || !k1_out) return -1;
+  try {
+    std::vector<size_t> bnd;
+    size_t K1 = 0;
+    chunk_schedule(n, chunk, phase1_percent, ramp != 0, &bnd, &K1);
+    if (bnd.size() > cap) return -1;
+    for (size_t i = 0; i < bnd.size(); i++) bounds_out[i] = bnd[i];
+    *k1_out = K1;
+    return (int64_t)bnd.size() - 1;
+  } catch (...) {
+    return -1;
+  }
+}
+
 static int32_t msm_from_host(zkp_ctx* ctx, const hseg* sc_segs, const hseg* pt_segs, int nseg, size_t n,
                              msm_result* d_result) {
   cudaStream_t st = ctx->stream;
@@ -606,7 +681,17 @@ static int32_t msm_from_host(zkp_ctx* ctx, const hseg* sc_segs, const hseg* pt_s
   int32_t r = msm_prepare(ctx, n, &pl);
   if (r != ZKP_OK) return r;
   const size_t chunk = ctx->chunk_terms;
-  const size_t nchunks = (n + chunk - 1) / chunk;
+  const bool fused = use_fused_sort(ctx, pl);
+  // chunk k = points [bnd[k], bnd[k + 1]); the first K1 chunks form phase 1 of the two-phase ingestion
+  std::vector<size_t> bnd;
+  size_t K1 = 0;
+  try {
+    chunk_schedule(n, chunk, ctx->phase1_percent, fused && ctx->ramp_chunks, &bnd, &K1);
+  } catch (...) {
+    ctx->err = "host allocation failed";
+    return ZKP_ERR_NOMEM;
+  }
+  const size_t nchunks = bnd.size() - 1;
   while (ctx->chunk_ev.size() < nchunks + 1) {
     cudaEvent_t e;
     CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -615,20 +700,17 @@ static int32_t msm_from_host(zkp_ctx* ctx, const hseg* sc_segs, const hseg* pt_s
   // the copy stream must not overwrite the staging buffers before earlier work on `st` (a previous call) is done
   CUDA_TRY(ctx, cudaEventRecord(ctx->chunk_ev[nchunks], st));
   CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[nchunks], 0));
-  if (use_fused_sort(ctx, pl)) {
-    // two-phase ingestion over the chunk pipeline: the first K1 point chunks travel with ALL the scalars (cut into K1
-    // slices) and carry the digit histogram; after the scan the remaining point chunks carry the scatter
-    // share of the point chunks in phase 1 (which also waits for all the scalars): measured end to end at the bench
-    // size, 50 % -> 136.3 ms, 60 % -> 137.6 ms, 70 % -> 141.6 ms per step, so the halves stay equal
-    size_t K1 = (nchunks * (size_t)ctx->phase1_percent + 99) / 100;
-    if (K1 < 1) K1 = 1;
-    if (K1 > nchunks) K1 = nchunks;
-    const size_t K2 = nchunks - K1;
+  if (fused) {
+    // two-phase ingestion over the chunk pipeline: the point chunks of phase 1 travel with ALL the scalars (cut into
+    // slices in proportion to the chunks) and carry the digit histogram; after the scan the remaining point chunks carry
+    // the scatter.  Share of the points in phase 1 (which also waits for all the scalars): measured end to end at the
+    // bench size, 50 % -> 136.3 ms, 60 % -> 137.6 ms, 70 % -> 141.6 ms per step, so the halves stay equal
+    const size_t K2 = nchunks - K1, P1 = bnd[K1];
     for (size_t k = 0; k < nchunks; k++) {
-      const size_t lo = k * chunk, hi = lo + chunk < n ? lo + chunk : n;
+      const size_t lo = bnd[k], hi = bnd[k + 1];
       const bool first = k < K1;
-      const size_t kk = first ? k : k - K1, parts = first ? K1 : K2;
-      const size_t s_lo = n / parts * kk + (n % parts) * kk / parts, s_hi = n / parts * (kk + 1) + (n % parts) * (kk + 1) / parts;
+      const size_t ps = first ? 0 : P1, plen = first ? P1 : n - P1;
+      const size_t s_lo = n * (lo - ps) / plen, s_hi = n * (hi - ps) / plen;   // n < 2^31: no overflow
       r = copy_range(ctx, pt_segs, nseg, lo, hi, (uint8_t*)ctx->in_points.p);
       if (r != ZKP_OK) return r;
       if (first) {
@@ -645,7 +727,7 @@ static int32_t msm_from_host(zkp_ctx* ctx, const hseg* sc_segs, const hseg* pt_s
       else r = launch_ingest2_range<1>(ctx, pl, ctx->in_scalars.p, ctx->in_points.p, n, lo, hi - lo, s_lo, s_hi - s_lo);
       if (r != ZKP_OK) return r;
     }
-    if (K2 == 0) {   // a single chunk: the scatter has no points to ride under
+    if (K2 == 0) {   // every point went through phase 1: the scatter has no points to ride under
       k_scan<<<pl.W, 1024, 0, st>>>((const uint32_t*)ctx->hist.p, pl.B, (uint32_t*)ctx->offs.p, (uint32_t*)ctx->cursor.p);
       LAUNCH_CHECK(ctx);
       r = launch_ingest2_range<1>(ctx, pl, ctx->in_scalars.p, ctx->in_points.p, n, 0, 0, 0, n);
@@ -654,7 +736,7 @@ static int32_t msm_from_host(zkp_ctx* ctx, const hseg* sc_segs, const hseg* pt_s
     return msm_finish(ctx, pl, ctx->in_scalars.p, n, d_result, false, true);
   }
   for (size_t k = 0; k < nchunks; k++) {
-    const size_t lo = k * chunk, hi = lo + chunk < n ? lo + chunk : n;
+    const size_t lo = bnd[k], hi = bnd[k + 1];
     r = copy_range(ctx, pt_segs, nseg, lo, hi, (uint8_t*)ctx->in_points.p);
     if (r != ZKP_OK) return r;
     r = copy_range(ctx, sc_segs, nseg, lo, hi, (uint8_t*)ctx->in_scalars.p);

@@ -15,7 +15,7 @@ SYMBOLS = [
     "zkp_device_count", "zkp_ctx_create", "zkp_ctx_destroy", "zkp_ctx_set_stream", "zkp_ctx_set_option",
     "zkp_ctx_synchronize", "zkp_last_error", "zkp_ctx_launch_count", "zkp_decompress_batch", "zkp_compress_batch",
     "zkp_msm_vartime", "zkp_msm_vartime_dev", "zkp_msm_vartime_batched", "zkp_msm_ct_batched", "zkp_batch_verify",
-    "zkp_bench_field", "zkp_ctx_stage_ms", "zkp_bench_dual", "zkp_batch_verify_proofs", "zkp_selftest_hash", "zkp_prove_batch", "zkp_batch_verify_partial", "zkp_partials_verdict", "zkp_selftest_bv_script",
+    "zkp_bench_field", "zkp_ctx_stage_ms", "zkp_bench_dual", "zkp_batch_verify_proofs", "zkp_selftest_hash", "zkp_prove_batch", "zkp_batch_verify_partial", "zkp_partials_verdict", "zkp_selftest_bv_script", "zkp_selftest_chunk_schedule",
 ]
 
 _lib = None
