@@ -255,16 +255,18 @@ def test_two_phase_ingestion_and_item_balance_options(engine):
                 engine.set_option("balance", balance)
                 for chunk in (1 << 21, 4096, 5000, n // 3 + 1, n):       # 1 chunk, many, ragged, 3 chunks (odd), exactly 1
                     engine.set_option("chunk_terms", max(chunk, 1024))
-                    for ramp in (1, 0):                                  # ramped and uniform chunk schedules
+                    for ramp, dual in ((1, 0), (0, 0), (0, 1), (1, 1)):   # ramped / uniform chunks, one / two streams
                         engine.set_option("ramp_chunks", ramp)
+                        engine.set_option("dual_stream", dual)
                         enc, _, _ = engine.msm_vartime(sc, pts)
-                        assert enc.hex() == case["expected"], (fused, balance, chunk, ramp)
-                    engine.set_option("ramp_chunks", 1)
-                    for pct in (1, 30, 100):                             # phase boundary at either end and off-centre
-                        engine.set_option("phase1_percent", pct)
-                        enc, _, _ = engine.msm_vartime(sc, pts)
-                        assert enc.hex() == case["expected"], (fused, balance, chunk, pct)
-                    engine.set_option("phase1_percent", 50)
+                        assert enc.hex() == case["expected"], (fused, balance, chunk, ramp, dual)
+                        for pct in (1, 30, 100):                         # phase boundary at either end and off-centre
+                            engine.set_option("phase1_percent", pct)
+                            enc, _, _ = engine.msm_vartime(sc, pts)
+                            assert enc.hex() == case["expected"], (fused, balance, chunk, ramp, dual, pct)
+                        engine.set_option("phase1_percent", 50)
+                    engine.set_option("ramp_chunks", 0)
+                    engine.set_option("dual_stream", 0)
                 engine.set_option("chunk_terms", 1024)
                 enc, _, _ = engine.msm_vartime(sc[:odd], pts[:odd])
                 assert enc == exp_odd, (fused, balance)
@@ -288,20 +290,23 @@ def test_two_phase_ingestion_and_item_balance_options(engine):
         engine.set_option("fused_sort", 1)
         engine.set_option("chunk_terms", 4096)
         from zkp_b200 import EngineError
-        for idx in (3, n - 2):
-            bad = pts.copy()
-            bad[idx] = 0xFF
-            enc, _, first_bad = engine.msm_vartime(sc, bad)
-            assert enc is None and first_bad == idx
-            bs = sc.copy()
-            bs[idx] = 0xFF
-            with pytest.raises(EngineError) as ei:
-                engine.msm_vartime(bs, pts)
-            assert ei.value.code == 3
+        for dual in (0, 1):
+            engine.set_option("dual_stream", dual)
+            for idx in (3, n - 2):
+                bad = pts.copy()
+                bad[idx] = 0xFF
+                enc, _, first_bad = engine.msm_vartime(sc, bad)
+                assert enc is None and first_bad == idx
+                bs = sc.copy()
+                bs[idx] = 0xFF
+                with pytest.raises(EngineError) as ei:
+                    engine.msm_vartime(bs, pts)
+                assert ei.value.code == 3
     finally:
         engine.set_option("fused_sort", 1)
         engine.set_option("balance", 1)
-        engine.set_option("ramp_chunks", 1)
+        engine.set_option("ramp_chunks", 0)
+        engine.set_option("dual_stream", 0)
         engine.set_option("phase1_percent", 50)
         engine.set_option("chunk_terms", 1 << 21)
 

@@ -64,7 +64,14 @@ struct zkp_ctx {
   int bv_compiled = 1;      // batch-verification front end: host-compiled transcript script (k_bv_prepare2)
   int ingest_variant = 2;   // occupancy point of k_ingest2 (kernels.cuh ZKP_INGEST_*)
   int fused_sort = 1;  // histogram and scatter ride under the two halves of the decompression (k_ingest2)
-  int ramp_chunks = 1; // host-input pipeline: chunk sizes ramp up from chunk_terms / 8 (and down again at the end of phase 1)
+  // host-input pipeline: ramped chunk sizes (from chunk_terms / 8 up to 2 * chunk_terms, down again at the end of phase 1).
+  // Measured at the bench size: 138.6 ms per step against 135.8 ms with uniform chunks -- phase 1 is copy-bound, so every
+  // chunk larger than its predecessor leaves the SMs idle while it arrives.  Off; kept as an option.
+  int ramp_chunks = 0;
+  // host-input pipeline: the chunk kernels alternate between two streams, so the last partial wave of one chunk's kernel
+  // overlaps the first blocks of the next (the digit work is order-independent); joined at the scan and at the end
+  int dual_stream = 0;
+  cudaStream_t aux_stream = nullptr;
   cudaStream_t sort_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
@@ -172,6 +179,7 @@ extern "C" void zkp_ctx_destroy(zkp_ctx* ctx) {
     if (ctx->ev_live[i]) cudaEventDestroy(ctx->ev_live[i]);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->sort_stream) cudaStreamDestroy(ctx->sort_stream);
+  if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -216,6 +224,8 @@ extern "C" int32_t zkp_ctx_set_option(zkp_ctx* ctx, const char* key, int64_t val
     ctx->fused_sort = value ? 1 : 0;
   } else if (!strcmp(key, "ramp_chunks")) {
     ctx->ramp_chunks = value ? 1 : 0;
+  } else if (!strcmp(key, "dual_stream")) {
+    ctx->dual_stream = value ? 1 : 0;
   } else if (!strcmp(key, "chunk_terms")) {
     if (value < 1024) return ZKP_ERR_SIZE;
     ctx->chunk_terms = (size_t)value;
@@ -328,6 +338,8 @@ static int32_t msm_prepare(zkp_ctx* ctx, size_t n, msm_plan* pl) {
       int lo = 0, hi = 0;
       CUDA_TRY(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
       CUDA_TRY(ctx, cudaStreamCreateWithPriority(&ctx->sort_stream, cudaStreamNonBlocking, hi));
+    }
+    if (!ctx->ev_fork) {
       CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
       CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     }
@@ -370,13 +382,15 @@ static int32_t msm_finish(zkp_ctx* ctx, const msm_plan& pl, const void* d_scalar
 // [sB_lo, +sB_cnt) of the scalar array; MODE 0 histograms their digits, MODE 1 scatters them
 template <int MODE>
 static int32_t launch_ingest2(zkp_ctx* ctx, const msm_plan& pl, const void* d_scalars, const void* d_points, size_t n,
-                              size_t p_lo, size_t p_cnt, size_t sA_lo, size_t sA_cnt, size_t sB_lo, size_t sB_cnt) {
+                              size_t p_lo, size_t p_cnt, size_t sA_lo, size_t sA_cnt, size_t sB_lo, size_t sB_cnt,
+                              cudaStream_t on = nullptr) {
+  const cudaStream_t launch_stream = on ? on : ctx->stream;
   size_t threads = p_cnt > sA_cnt ? p_cnt : sA_cnt;
   if (sB_cnt > threads) threads = sB_cnt;
   if (!threads) return ZKP_OK;
 #define ZKP_LAUNCH_INGEST(VAR)                                                                                              \
   k_ingest2<MODE, VAR><<<(unsigned)((threads + ZKP_INGEST_THREADS(VAR) - 1) / ZKP_INGEST_THREADS(VAR)),                     \
-                         ZKP_INGEST_THREADS(VAR), 0, ctx->stream>>>(                                                        \
+                         ZKP_INGEST_THREADS(VAR), 0, launch_stream>>>(                                                      \
       (const uint4*)d_points, p_lo, p_cnt, (uint4*)ctx->niels.p, (const uint4*)d_scalars, sA_lo, sA_cnt, sB_lo, sB_cnt, n,  \
       pl.c, pl.W, pl.B, MODE == 0 ? (uint32_t*)ctx->hist.p : (uint32_t*)ctx->cursor.p, (uint32_t*)ctx->sorted.p,            \
       (int*)ctx->flags.p)
@@ -393,9 +407,9 @@ static int32_t launch_ingest2(zkp_ctx* ctx, const msm_plan& pl, const void* d_sc
 // the same with one contiguous scalar range [s_lo, s_lo + s_cnt) cut into two halves
 template <int MODE>
 static int32_t launch_ingest2_range(zkp_ctx* ctx, const msm_plan& pl, const void* d_scalars, const void* d_points, size_t n,
-                                    size_t p_lo, size_t p_cnt, size_t s_lo, size_t s_cnt) {
+                                    size_t p_lo, size_t p_cnt, size_t s_lo, size_t s_cnt, cudaStream_t on = nullptr) {
   const size_t half = (s_cnt + 1) / 2;
-  return launch_ingest2<MODE>(ctx, pl, d_scalars, d_points, n, p_lo, p_cnt, s_lo, half, s_lo + half, s_cnt - half);
+  return launch_ingest2<MODE>(ctx, pl, d_scalars, d_points, n, p_lo, p_cnt, s_lo, half, s_lo + half, s_cnt - half, on);
 }
 static bool use_fused_sort(const zkp_ctx* ctx, const msm_plan& pl) {
   return !ctx->profile && pl.sort == ctx->stream && ctx->fused_sort;
@@ -706,11 +720,26 @@ static int32_t msm_from_host(zkp_ctx* ctx, const hseg* sc_segs, const hseg* pt_s
     // the scatter.  Share of the points in phase 1 (which also waits for all the scalars): measured end to end at the
     // bench size, 50 % -> 136.3 ms, 60 % -> 137.6 ms, 70 % -> 141.6 ms per step, so the halves stay equal
     const size_t K2 = nchunks - K1, P1 = bnd[K1];
+    // two compute streams: odd chunks run on the auxiliary stream (fork after the preparation, join around the scan
+    // and before the bucket phase)
+    const bool dual = ctx->dual_stream && nchunks > 2;
+    cudaStream_t aux = st;
+    if (dual) {
+      if (!ctx->aux_stream) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+      if (!ctx->ev_fork) {
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+      }
+      aux = ctx->aux_stream;
+      CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, st));
+      CUDA_TRY(ctx, cudaStreamWaitEvent(aux, ctx->ev_fork, 0));
+    }
     for (size_t k = 0; k < nchunks; k++) {
       const size_t lo = bnd[k], hi = bnd[k + 1];
       const bool first = k < K1;
       const size_t ps = first ? 0 : P1, plen = first ? P1 : n - P1;
       const size_t s_lo = n * (lo - ps) / plen, s_hi = n * (hi - ps) / plen;   // n < 2^31: no overflow
+      const cudaStream_t sk = (k & 1) ? aux : st;
       r = copy_range(ctx, pt_segs, nseg, lo, hi, (uint8_t*)ctx->in_points.p);
       if (r != ZKP_OK) return r;
       if (first) {
@@ -718,14 +747,26 @@ static int32_t msm_from_host(zkp_ctx* ctx, const hseg* sc_segs, const hseg* pt_s
         if (r != ZKP_OK) return r;
       }
       CUDA_TRY(ctx, cudaEventRecord(ctx->chunk_ev[k], ctx->copy_stream));
-      CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->chunk_ev[k], 0));
-      if (k == K1) {
+      if (k == K1) {   // the scan needs every histogram launch of both streams; the scatter launches need the scan
+        if (dual) {
+          CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, aux));
+          CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
+        }
         k_scan<<<pl.W, 1024, 0, st>>>((const uint32_t*)ctx->hist.p, pl.B, (uint32_t*)ctx->offs.p, (uint32_t*)ctx->cursor.p);
         LAUNCH_CHECK(ctx);
+        if (dual) {
+          CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, st));
+          CUDA_TRY(ctx, cudaStreamWaitEvent(aux, ctx->ev_fork, 0));
+        }
       }
-      if (first) r = launch_ingest2_range<0>(ctx, pl, ctx->in_scalars.p, ctx->in_points.p, n, lo, hi - lo, s_lo, s_hi - s_lo);
-      else r = launch_ingest2_range<1>(ctx, pl, ctx->in_scalars.p, ctx->in_points.p, n, lo, hi - lo, s_lo, s_hi - s_lo);
+      CUDA_TRY(ctx, cudaStreamWaitEvent(sk, ctx->chunk_ev[k], 0));
+      if (first) r = launch_ingest2_range<0>(ctx, pl, ctx->in_scalars.p, ctx->in_points.p, n, lo, hi - lo, s_lo, s_hi - s_lo, sk);
+      else r = launch_ingest2_range<1>(ctx, pl, ctx->in_scalars.p, ctx->in_points.p, n, lo, hi - lo, s_lo, s_hi - s_lo, sk);
       if (r != ZKP_OK) return r;
+    }
+    if (dual) {   // everything the auxiliary stream did is ordered before what follows on `st`
+      CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, aux));
+      CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
     }
     if (K2 == 0) {   // every point went through phase 1: the scatter has no points to ride under
       k_scan<<<pl.W, 1024, 0, st>>>((const uint32_t*)ctx->hist.p, pl.B, (uint32_t*)ctx->offs.p, (uint32_t*)ctx->cursor.p);
