@@ -57,7 +57,12 @@ int32_t zkp_ctx_set_stream(zkp_ctx* ctx, void* cuda_stream);
 /* Tunables: "window" (Pippenger window width c, 0 = choose from n), "window_cap" (upper bound of the automatic
  * choice), "chunk" (max sorted entries per accumulate work item, 0 = auto), "profile" (0/1, see
  * zkp_ctx_stage_ms; forces the stages to run back to back), "overlap" (0/1, default 0: run the digit sort on a
- * second stream concurrently with decompression; measured neutral), "chunk_terms" (H2D pipeline granularity of the host entry points). */
+ * second stream concurrently with decompression; measured neutral), "chunk_terms" (terms per H2D chunk of the host-input MSM,
+ * default 2^19), "dual_stream" (0/1, default 1: the chunk kernels alternate between two streams), "ramp_chunks" (0/1,
+ * default 0: growing chunk sizes; measured slower), "phase1_percent" (share of the points decompressed under the digit
+ * histogram, default 50), "bv_chunk_terms" (slab size of zkp_batch_verify_proofs, default 2^21), "fused_sort",
+ * "balance", "ingest_variant", "bv_compiled", "share_static_tables", "prove_chunk", "coop_max_msms" (ablation
+ * switches documented in DESIGN.md). */
 int32_t zkp_ctx_set_option(zkp_ctx* ctx, const char* key, int64_t value);
 int32_t zkp_ctx_synchronize(zkp_ctx* ctx);
 const char* zkp_last_error(zkp_ctx* ctx);

@@ -228,11 +228,11 @@ def test_host_pipeline_chunking_overlap_and_profile_options(engine):
                 assert st["decompress"] > 0 and st["accumulate"] > 0 and 4 <= st["window"] <= 24
             engine.set_option("profile", 0)
             engine.set_option("overlap", 0)
-            engine.set_option("chunk_terms", 1 << 21)
+            engine.set_option("chunk_terms", 1 << 19)
     finally:
         engine.set_option("profile", 0)
         engine.set_option("overlap", 0)
-        engine.set_option("chunk_terms", 1 << 21)
+        engine.set_option("chunk_terms", 1 << 19)
 
 
 def test_two_phase_ingestion_and_item_balance_options(engine):
@@ -266,7 +266,7 @@ def test_two_phase_ingestion_and_item_balance_options(engine):
                             assert enc.hex() == case["expected"], (fused, balance, chunk, ramp, dual, pct)
                         engine.set_option("phase1_percent", 50)
                     engine.set_option("ramp_chunks", 0)
-                    engine.set_option("dual_stream", 0)
+                    engine.set_option("dual_stream", 1)
                 engine.set_option("chunk_terms", 1024)
                 enc, _, _ = engine.msm_vartime(sc[:odd], pts[:odd])
                 assert enc == exp_odd, (fused, balance)
@@ -306,9 +306,9 @@ def test_two_phase_ingestion_and_item_balance_options(engine):
         engine.set_option("fused_sort", 1)
         engine.set_option("balance", 1)
         engine.set_option("ramp_chunks", 0)
-        engine.set_option("dual_stream", 0)
+        engine.set_option("dual_stream", 1)
         engine.set_option("phase1_percent", 50)
-        engine.set_option("chunk_terms", 1 << 21)
+        engine.set_option("chunk_terms", 1 << 19)
 
 
 def test_maximum_sizes_are_refused_not_attempted(engine):

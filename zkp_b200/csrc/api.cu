@@ -51,7 +51,12 @@ struct zkp_ctx {
   // host-input pipeline: copies on copy_stream overlap the per-chunk kernels on `stream`
   cudaStream_t copy_stream = nullptr;
   std::vector<cudaEvent_t> chunk_ev;
-  size_t chunk_terms = (size_t)1 << 21;
+  // terms per H2D chunk of the host-input MSM.  Phase 1 of the ingestion is copy-bound, so a step ends one chunk's copy
+  // plus one chunk's kernel after the ideal: small chunks, with their kernels alternating between two streams so that the
+  // per-launch partial waves overlap.  Measured at the bench size (e2e per step): 2^21 on one stream 135.8 ms,
+  // 2^20 on two 132.3 ms, 2^19 on two 130.6 ms (device-resident inputs: 129.5 ms)
+  size_t chunk_terms = (size_t)1 << 19;
+  size_t bv_chunk_terms = (size_t)1 << 21;   // the same for the slabs of zkp_batch_verify_proofs (one stream)
   // the digit sort (histogram, scan, scatter: L2-atomic bound) runs on a second, higher-priority stream
   // concurrently with decompression (integer-multiply bound); joined before bucket accumulation
   int overlap = 0;   // measured: no gain on B200 (159.2 vs 159.9 ms per step), kept as an option
@@ -70,7 +75,7 @@ struct zkp_ctx {
   int ramp_chunks = 0;
   // host-input pipeline: the chunk kernels alternate between two streams, so the last partial wave of one chunk's kernel
   // overlaps the first blocks of the next (the digit work is order-independent); joined at the scan and at the end
-  int dual_stream = 0;
+  int dual_stream = 1;
   cudaStream_t aux_stream = nullptr;
   cudaStream_t sort_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -229,6 +234,9 @@ extern "C" int32_t zkp_ctx_set_option(zkp_ctx* ctx, const char* key, int64_t val
   } else if (!strcmp(key, "chunk_terms")) {
     if (value < 1024) return ZKP_ERR_SIZE;
     ctx->chunk_terms = (size_t)value;
+  } else if (!strcmp(key, "bv_chunk_terms")) {
+    if (value < 1024) return ZKP_ERR_SIZE;
+    ctx->bv_chunk_terms = (size_t)value;
   } else if (!strcmp(key, "profile")) {
     ctx->profile = value ? 1 : 0;
     if (ctx->profile && !ctx->ev[0])
@@ -1166,7 +1174,7 @@ static int32_t batch_verify_proofs_impl(zkp_ctx* ctx, const zkp_statement_desc* 
   }
   const size_t rows = (size_t)ni + k, n = (size_t)nc + rows * N;
   if (n >= 0x7fffffffull) return ZKP_ERR_SIZE;
-  const size_t chunk = ctx->chunk_terms / (rows ? rows : 1) > 1024 ? (ctx->chunk_terms * 4 / (rows ? rows : 1)) & ~(size_t)127
+  const size_t chunk = ctx->bv_chunk_terms / (rows ? rows : 1) > 1024 ? (ctx->bv_chunk_terms * 4 / (rows ? rows : 1)) & ~(size_t)127
                                                                     : 1024;   // proofs per chunk (multiple of 128)
   const size_t nchunks = N ? (N + chunk - 1) / chunk : 0;
   ENSURE(ctx, ctx->bv_misc, blob_sz);
