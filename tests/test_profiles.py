@@ -10,7 +10,7 @@ def _load(name):
 
 
 def test_bench_records_carry_the_contract_keys():
-    for name, gpus in (("bench_r01_s3.json", 1), ("bench_r01_s2.json", 1), ("bench_r01_s2_2gpu.json", 2),
+    for name, gpus in (("bench_r01_s4.json", 1), ("bench_r01_s3.json", 1), ("bench_r01_s2.json", 1), ("bench_r01_s2_2gpu.json", 2),
                        ("bench_r01_s2_8gpu.json", 8)):
         d = _load(name)
         for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
@@ -38,6 +38,11 @@ def test_roofline_traffic_record_matches_the_bench_size():
 
 
 def test_cpu_baseline_of_the_latest_record_names_its_backend():
-    c = _load("bench_r01_s3.json")["cpu_baseline"]
+    c = _load("bench_r01_s4.json")["cpu_baseline"]
     assert c["kind"] == "port" and c["cores"] >= 1 and "backend" in c
     assert c["value"] >= c["u64_serial_backend_value"] > c["single_thread_value"] > 0
+
+
+def test_end_to_end_step_is_within_two_percent_of_the_device_resident_one():
+    d = _load("bench_r01_s4.json")
+    assert d["e2e"]["ms_per_step"] <= 1.02 * d["ms_per_step"]
