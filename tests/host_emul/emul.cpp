@@ -8,6 +8,8 @@
 #include "../../zkp_b200/csrc/sc.cuh"
 #include "../../zkp_b200/csrc/hash.cuh"
 #include "../../zkp_b200/csrc/scl.cuh"
+#include "../../zkp_b200/csrc/comb.cuh"
+#include <vector>
 using namespace zkp;
 
 static fe ld(const uint8_t* p) { fe r; memcpy(r.v, p, 32); return r; }
@@ -157,4 +159,39 @@ void emul_scl_mul_128(uint8_t* r, const uint8_t* a, const uint8_t* b) { scl x, y
 void emul_scl_add(uint8_t* r, const uint8_t* a, const uint8_t* b) { scl x, y, z; memcpy(x.v, a, 32); memcpy(y.v, b, 32); scl_add(z, x, y); memcpy(r, z.v, 32); }
 void emul_scl_sub(uint8_t* r, const uint8_t* a, const uint8_t* b) { scl x, y, z; memcpy(x.v, a, 32); memcpy(y.v, b, 32); scl_sub(z, x, y); memcpy(r, z.v, 32); }
 void emul_scl_wide(uint8_t* r, const uint8_t* a64) { scl z; scl_from_wide(z, a64); memcpy(r, z.v, 32); }
+
+// ---- signed four-tooth combs (comb.cuh): the constant-time MSM of batch proving ----
+void emul_comb_recode(uint8_t* m32, const uint8_t* s32) {
+  uint32_t s[8], m[8]; memcpy(s, s32, 32); comb_recode(m, s); memcpy(m32, m, 32);
+}
+// the eight entries of the comb of P as extended points would be redundant: return them as projective Niels (8 x 128 B)
+void emul_comb_build(uint8_t* out1024, const uint8_t* pt128) {
+  ge_pniels E[8]; comb_build(E, ldp(pt128)); memcpy(out1024, E, 1024);
+}
+// sum_t scalars[t] * points[t] the way k_small_msm_comb does it: recode, one comb per base, 64 columns of
+// (double; per term: column digits -> constant-time select -> add).  scalars [n][32] canonical, points [n][128] extended.
+void emul_comb_msm(uint8_t* out128, const uint8_t* scalars, const uint8_t* points, int n) {
+  std::vector<ge_pniels> tabs((size_t)8 * n);
+  std::vector<uint32_t> m((size_t)8 * n);
+  for (int t = 0; t < n; t++) {
+    comb_build(&tabs[(size_t)8 * t], ldp(points + 128 * (size_t)t));
+    uint32_t s[8]; memcpy(s, scalars + 32 * (size_t)t, 32);
+    comb_recode(&m[(size_t)8 * t], s);
+  }
+  ge_ext acc; ge_identity(acc);
+  for (int col = 63; col >= 0; col--) {
+    ge_double(acc, acc);
+    for (int t = 0; t < n; t++) {
+      uint32_t idx, neg;
+      comb_column(idx, neg, &m[(size_t)8 * t], col);
+      ge_pniels sel;
+      const uint32_t* tab = (const uint32_t*)&tabs[(size_t)8 * t];
+      comb_select(sel, [&](uint32_t e, int q, uint32_t& x, uint32_t& y, uint32_t& z, uint32_t& w) {
+        const uint32_t* p = tab + 32 * e + 4 * q; x = p[0]; y = p[1]; z = p[2]; w = p[3];
+      }, idx, neg);
+      ge_add_pniels(acc, acc, sel);
+    }
+  }
+  memcpy(out128, &acc, 128);
+}
 }

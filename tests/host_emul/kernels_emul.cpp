@@ -1,0 +1,67 @@
+// The batch prover's MSM kernels compiled for the HOST (cuda_shim.h + -DZKP_HOST_EMUL) and run thread by thread:
+// k_pv_gather -> (k_build_tables + k_small_msm_ct | k_build_combs + k_comb_recode + k_small_msm_comb) with the plan of
+// pv_plan.hpp, exactly the launch sequence of zkp_prove_batch (api.cu).  Checks the CSR / schedule / interleaved-table
+// indexing and the kernels' logic against the oracle without a GPU.  TEST INFRASTRUCTURE ONLY.
+#include "cuda_shim.h"
+#include <vector>
+#include "../../zkp_b200/csrc/pv_kernels.cuh"
+#include "../../zkp_b200/csrc/pv_plan.hpp"
+using namespace zkp;
+
+extern "C" {
+// limbs [N][p][20] (FieldElement51 X,Y,Z,T), blind [N][m][32] canonical -> com [N][k][32]; returns the not-uniform flag
+// (1 if a common point differed between proofs while share was requested: the caller reruns without sharing, as api.cu does)
+int emul_prove_msms(int m, int ni, int nc, int k, const int32_t* lhs, const int32_t* cons_off, const int32_t* term_scalar,
+                    const int32_t* term_point, size_t N, const uint64_t* limbs, const uint8_t* blind, int share, int comb,
+                    uint8_t* com) {
+  const int p = ni + nc, T = k ? cons_off[k] : 0;
+  pv_plan plan;
+  pv_make_plan(ni, p, k, cons_off, term_point, share != 0, comb != 0, &plan);
+  pv_desc d;
+  memset(&d, 0, sizeof d);
+  d.m = m; d.p = p; d.k = k; d.n_terms = T; d.ni = ni;
+  d.term_shared = plan.term_shared.data();
+  d.lhs = lhs; d.cons_off = cons_off; d.term_scalar = term_scalar; d.term_point = term_point;
+  d.cons_slot = plan.cons_slot.data();
+  const size_t total = N * (size_t)T, M = N * (size_t)k, Npad = (N + 31) / 32 * 32;
+  std::vector<uint4> scalars_flat(2 * total + 2), ext_flat(8 * total + 8), out(2 * M + 2);
+  std::vector<unsigned long long> offsets(M + 1);
+  std::vector<uint32_t> order(M + 1);
+  int flags[4] = {0x7fffffff, 0x7fffffff, 0, 0};
+  const size_t gthreads = std::max(total, M) ? std::max(total, M) : 1;
+  emul_launch((unsigned)((gthreads + 255) / 256), 256, k_pv_gather, d, N, (const unsigned long long*)limbs, blind,
+              scalars_flat.data(), ext_flat.data(), offsets.data(), order.data(), share ? &flags[2] : (int*)nullptr);
+  std::vector<uint4> biased(2 * total + 2);
+  if (comb) {
+    const size_t U = plan.comb_slot_point.size(), Us = plan.comb_shared_point.size();
+    std::vector<uint4> combs(Npad * U * 64 + 64), shared(Us * 64 + 64);
+    if (U)
+      emul_launch((unsigned)((N * U + 63) / 64), 64, k_build_combs<true>, (const unsigned long long*)limbs, N * U, (uint32_t)U,
+                  (uint32_t)p, plan.comb_slot_point.data(), combs.data());
+    if (Us)
+      emul_launch((unsigned)((Us + 63) / 64), 64, k_build_combs<false>, (const unsigned long long*)limbs, Us, (uint32_t)Us,
+                  (uint32_t)p, plan.comb_shared_point.data(), shared.data());
+    emul_launch((unsigned)((total + 255) / 256), 256, k_comb_recode, (const uint4*)scalars_flat.data(), total, biased.data());
+    emul_launch((unsigned)((M + 63) / 64), 64, k_small_msm_comb, (const uint32_t*)biased.data(), (const uint4*)combs.data(),
+                (const uint4*)shared.data(), plan.term_slot.data(), (const unsigned long long*)offsets.data(),
+                (const uint32_t*)order.data(), M, (uint32_t)T, (uint32_t)U, out.data());
+  } else {
+    std::vector<uint4> tables(Npad * (size_t)T * 64 + 64), s_ext(8 * (size_t)nc + 8), s_tab(64 * (size_t)nc + 64),
+        s_zero(2 * (size_t)nc + 2, make_uint4(0, 0, 0, 0)), s_bias(2 * (size_t)nc + 2);
+    const int32_t* shared_of = share ? plan.term_shared.data() : nullptr;
+    if (share) {
+      emul_launch((unsigned)((nc + 255) / 256), 256, k_limbs_to_ext, (const unsigned long long*)limbs + (size_t)ni * 20,
+                  (size_t)nc, s_ext.data());
+      emul_launch((unsigned)((nc + 127) / 128), 128, k_build_tables<false>, (const uint4*)s_ext.data(), (const uint4*)s_zero.data(),
+                  (size_t)nc, 1u, s_tab.data(), s_bias.data(), &flags[2], (const int32_t*)nullptr);
+    }
+    emul_launch((unsigned)((total + 127) / 128), 128, k_build_tables<true>, (const uint4*)ext_flat.data(),
+                (const uint4*)scalars_flat.data(), total, (uint32_t)T, tables.data(), biased.data(), &flags[2], shared_of);
+    emul_launch((unsigned)((M + 63) / 64), 64, k_small_msm_ct<true, false>, (const uint32_t*)biased.data(),
+                (const uint4*)tables.data(), (const unsigned long long*)offsets.data(), (const uint32_t*)order.data(), M,
+                (uint32_t)T, out.data(), shared_of, share ? (const uint4*)s_tab.data() : (const uint4*)nullptr);
+  }
+  memcpy(com, out.data(), M * 32);
+  return flags[2];
+}
+}

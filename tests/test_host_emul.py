@@ -18,7 +18,7 @@ P = R.P
 def lib():
     src = os.path.join(HERE, "host_emul", "emul.cpp")
     out = os.path.join(HERE, "host_emul", "libemul.so")
-    deps = [src] + [os.path.join(HERE, "..", "zkp_b200", "csrc", f) for f in ("fe.cuh", "fe64.cuh", "ge.cuh", "sc.cuh", "hash.cuh", "scl.cuh")]
+    deps = [src] + [os.path.join(HERE, "..", "zkp_b200", "csrc", f) for f in ("fe.cuh", "fe64.cuh", "ge.cuh", "sc.cuh", "hash.cuh", "scl.cuh", "comb.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         subprocess.check_call(["g++", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-DZKP_HOST_EMUL", "-x", "c++", src, "-o", out])
     return ctypes.CDLL(out)
@@ -295,3 +295,130 @@ def test_field_ops_property_based(lib):
         lib.emul_fe64_sq(r, a.to_bytes(32, "little"), 3)
         assert int.from_bytes(r.raw, "little") % P == pow(a, 8, P)
     check()
+
+
+def test_signed_comb_of_the_batch_prover(lib):
+    """comb.cuh (the four-tooth signed comb behind k_small_msm_comb): the recoding reproduces the scalar (or scalar + l
+    for even scalars) as +-1 digits, the eight table entries are T_3 +- T_2 +- T_1 +- T_0, and a comb MSM -- built,
+    recoded, selected and accumulated with the functions the kernel uses -- encodes to what the oracle's MSM encodes
+    to, for edge scalars (0, 1, 2, l-1, l-2, 2^252, powers of two) and random ones, one to twelve terms."""
+    from oracle import msm as M, scalar as S
+    L = S.L
+    rnd = random.Random(21)
+    edge = [0, 1, 2, 3, L - 1, L - 2, 2**252, 2**251, 2**64, 2**64 - 1, 2**128 + 1, 2**192, (L - 1) // 2]
+    for s in edge + [rnd.randrange(L) for _ in range(200)]:
+        m = ctypes.create_string_buffer(32)
+        lib.emul_comb_recode(m, s.to_bytes(32, "little"))
+        mi = int.from_bytes(m.raw, "little")
+        k = sum((2 * ((mi >> i) & 1) - 1) << i for i in range(256))
+        assert k == (s if s & 1 else s + L) and (mi >> 255) == 1
+    # table entries
+    pts = [R.from_uniform_bytes(rnd.randbytes(64)) for _ in range(6)] + [R.BASEPOINT, R.IDENTITY]
+    def mulp(p, k):
+        return R.pt_mul(k, p)
+    for p in pts[:3] + [R.IDENTITY]:
+        out = ctypes.create_string_buffer(1024)
+        lib.emul_comb_build(out, _pb(p))
+        teeth = [mulp(p, 1 << (64 * x)) for x in range(4)]
+        for idx in range(8):
+            e = out.raw[128 * idx:128 * (idx + 1)]
+            ypx, ymx, z, t2d = (int.from_bytes(e[32 * i:32 * (i + 1)], "little") % P for i in range(4))
+            inv2 = pow(2, P - 2, P)
+            x, y = (ypx - ymx) * inv2 % P, (ypx + ymx) * inv2 % P
+            t = x * y % P * pow(z, P - 2, P) % P
+            assert t2d == 2 * R.D * t % P
+            exp = teeth[3]
+            for b in range(3):
+                exp = R.pt_add(exp, teeth[b]) if (idx >> b) & 1 else R.pt_sub(exp, teeth[b])
+            assert R.compress((x, y, z, t)) == R.compress(exp), idx
+    # whole MSMs
+    for n in (1, 2, 3, 11, 12):
+        for trial in range(4):
+            sc = [rnd.choice(edge) if rnd.random() < 0.3 else rnd.randrange(L) for _ in range(n)]
+            ps = [rnd.choice(pts) for _ in range(n)]
+            out = ctypes.create_string_buffer(128)
+            lib.emul_comb_msm(out, b"".join(s.to_bytes(32, "little") for s in sc), b"".join(_pb(p) for p in ps), n)
+            enc = ctypes.create_string_buffer(32)
+            lib.emul_encode(enc, out.raw)
+            exp = M.msm_bytes([s.to_bytes(32, "little") for s in sc], [R.compress(p) for p in ps])
+            assert enc.raw == exp, (n, trial)
+
+
+@pytest.fixture(scope="module")
+def klib():
+    """The batch prover's kernels compiled for the host (tests/host_emul/cuda_shim.h) and run thread by thread."""
+    src = os.path.join(HERE, "host_emul", "kernels_emul.cpp")
+    out = os.path.join(HERE, "host_emul", "libkemul.so")
+    csrc = os.path.join(HERE, "..", "zkp_b200", "csrc")
+    deps = [src, os.path.join(HERE, "host_emul", "cuda_shim.h")] + [os.path.join(csrc, f) for f in os.listdir(csrc)
+                                                                    if f.endswith((".cuh", ".hpp"))]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-DZKP_HOST_EMUL",
+                               "-I/usr/local/cuda/include", src, "-o", out])
+    return ctypes.CDLL(out)
+
+
+def test_batch_prover_msm_kernels_run_on_the_host(klib):
+    """k_pv_gather, the Straus tables / MSMs (k_build_tables, k_small_msm_ct) and the comb path (k_build_combs,
+    k_comb_recode, k_small_msm_comb) executed thread by thread on the CPU with the launch sequence and the plan of
+    zkp_prove_batch: for 40 proofs (one full interleave group of 32 and a partial one) of a statement whose bases are
+    shared between constraints, used once, instance and common, every commitment equals the oracle's -- with and without
+    shared tables for the batch-static points, and a batch whose "common" points differ raises the not-uniform flag."""
+    import numpy as np
+    from oracle import scalar as S
+    rnd = random.Random(33)
+    m, ni, nc = 5, 3, 3
+    lhs = np.array([0, 2, 0, 2], dtype=np.int32)
+    terms = [[(0, 1), (1, 3)], [(2, 1), (3, 4), (4, 5), (0, 3)], [(1, 1)], [(2, 3), (3, 2)]]
+    k = len(terms)
+    off = np.cumsum([0] + [len(t) for t in terms]).astype(np.int32)
+    ts = np.array([s for t in terms for s, _ in t], dtype=np.int32)
+    tp = np.array([q for t in terms for _, q in t], dtype=np.int32)
+    N = 40
+    common = [R.from_uniform_bytes(rnd.randbytes(64)) for _ in range(nc)]
+    pts = [[R.from_uniform_bytes(rnd.randbytes(64)) for _ in range(ni)] + common for _ in range(N)]
+    edge = [0, 1, 2, S.L - 1, S.L - 2, 2**252]
+    blind = [[rnd.choice(edge) if rnd.random() < 0.15 else rnd.randrange(S.L) for _ in range(m)] for _ in range(N)]
+
+    def limbs_of(pt):
+        z = rnd.randrange(1, P)                        # any projective representative
+        x, y, zz = pt[0] * z % P, pt[1] * z % P, pt[2] * z % P
+        t = x * y % P * pow(zz, P - 2, P) % P
+        return [(c >> (51 * i)) & ((1 << 51) - 1) for c in (x, y, zz, t) for i in range(5)]
+
+    klib.emul_prove_msms.argtypes = [ctypes.c_int] * 4 + [ctypes.c_void_p] * 4 + [ctypes.c_size_t, ctypes.c_void_p,
+                                                                                ctypes.c_char_p, ctypes.c_int, ctypes.c_int,
+                                                                                ctypes.c_void_p]
+
+    def run(points, share, comb, same_representative):
+        if same_representative:     # the uniformity check compares limbs, so every copy of a common point is the same bytes
+            fixed = {id(q): limbs_of(q) for q in common}
+            rows = [[fixed.get(id(q)) or limbs_of(q) for q in row] for row in points]
+        else:
+            rows = [[limbs_of(q) for q in row] for row in points]
+        limbs = np.array(rows, dtype=np.uint64)
+        bl = b"".join(s.to_bytes(32, "little") for row in blind for s in row)
+        com = ctypes.create_string_buffer(N * k * 32)
+        flag = klib.emul_prove_msms(m, ni, nc, k, lhs.ctypes.data, off.ctypes.data, ts.ctypes.data, tp.ctypes.data, N,
+                                    limbs.ctypes.data, bl, share, comb, ctypes.cast(com, ctypes.c_void_p))
+        return flag, com.raw
+
+    expected = b""
+    for j in range(N):
+        for t in terms:
+            acc = R.IDENTITY
+            for s, q in t:
+                acc = R.pt_add(acc, R.pt_mul(blind[j][s], pts[j][q]))
+            expected += R.compress(acc)
+    for share in (1, 0):
+        for comb in (0, 1):
+            flag, com = run(pts, share, comb, same_representative=bool(share))
+            assert flag == 0, (share, comb)
+            bad = [i for i in range(N * k) if com[32 * i:32 * i + 32] != expected[32 * i:32 * i + 32]]
+            assert not bad, (share, comb, bad[:8])
+    # a "common" point that differs in one proof: the kernels say so (api.cu then redoes the call without sharing)
+    odd = [list(row) for row in pts]
+    odd[17][ni + 1] = R.from_uniform_bytes(rnd.randbytes(64))
+    for comb in (0, 1):
+        flag, _ = run(odd, 1, comb, same_representative=True)
+        assert flag != 0

@@ -17,6 +17,7 @@
 #include "bench_fe.cuh"
 #include "bv_kernels.cuh"
 #include "pv_kernels.cuh"
+#include "pv_plan.hpp"
 
 using namespace zkp;
 
@@ -66,6 +67,9 @@ struct zkp_ctx {
   int coop_max_msms = 8192;  // batched small vartime MSMs: up to this many run with four lanes per MSM (latency)
   int phase1_percent = 50;   // share of the host-path point chunks decompressed under the histogram (first phase)
   int share_static_tables = 1;   // batch proving: one constant-time table per batch-static point
+  // batch proving: signed four-tooth combs, one per base (comb.cuh): 64 doublings per constraint MSM instead of 256.
+  // Logic checked on the host against the oracle (tests/test_host_emul.py); not yet run on a GPU, hence off.
+  int prove_comb = 0;
   int bv_compiled = 1;      // batch-verification front end: host-compiled transcript script (k_bv_prepare2)
   int ingest_variant = 2;   // occupancy point of k_ingest2 (kernels.cuh ZKP_INGEST_*)
   int fused_sort = 1;  // histogram and scatter ride under the two halves of the decompression (k_ingest2)
@@ -220,6 +224,8 @@ extern "C" int32_t zkp_ctx_set_option(zkp_ctx* ctx, const char* key, int64_t val
     ctx->prove_chunk = (size_t)value;
   } else if (!strcmp(key, "share_static_tables")) {
     ctx->share_static_tables = value ? 1 : 0;
+  } else if (!strcmp(key, "prove_comb")) {
+    ctx->prove_comb = value ? 1 : 0;
   } else if (!strcmp(key, "bv_compiled")) {
     ctx->bv_compiled = value ? 1 : 0;
   } else if (!strcmp(key, "ingest_variant")) {
@@ -1359,29 +1365,33 @@ static int32_t prove_batch_impl(zkp_ctx* ctx, const zkp_statement_desc* sd, cons
     pool.insert(pool.end(), lp, lp + len);
     lp += len + 1;
   }
-  // MSM schedule: constraints ordered by (public) size, largest first, so that the lanes of a warp do equal work
-  std::vector<int32_t> by_size(k), slot(k);
-  for (int c = 0; c < k; c++) by_size[c] = c;
-  std::stable_sort(by_size.begin(), by_size.end(), [&](int a, int b) {
-    return sd->cons_off[a + 1] - sd->cons_off[a] > sd->cons_off[b + 1] - sd->cons_off[b];
-  });
-  for (int r0 = 0; r0 < k; r0++) slot[by_size[r0]] = r0;
   auto pad16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
   const size_t o_prefix = 0, o_pool = pad16(53 * 4), o_lo = pad16(o_pool + pool.size()), o_ll = pad16(o_lo + (size_t)p * 4),
                o_lhs = pad16(o_ll + (size_t)p * 4), o_co = pad16(o_lhs + (size_t)k * 4), o_ts = pad16(o_co + (size_t)(k + 1) * 4),
                o_tp = pad16(o_ts + (size_t)n_terms * 4), o_sl = pad16(o_tp + (size_t)n_terms * 4),
-               o_sh = pad16(o_sl + (size_t)k * 4), blob_sz = pad16(o_sh + (size_t)n_terms * 4) + 16;
+               o_sh = pad16(o_sl + (size_t)k * 4), o_cs = pad16(o_sh + (size_t)n_terms * 4),
+               o_cp = pad16(o_cs + (size_t)n_terms * 4), o_cq = pad16(o_cp + (size_t)p * 4),
+               blob_sz = pad16(o_cq + (size_t)p * 4) + 16;
   // batch-static bases: the statement's common points are the same for every proof when the caller says so
   // (points_are_uniform): their constant-time tables are built once and shared
   // (the caller passes a copy per proof, as the reference's per-proof assignments do: k_pv_gather compares every copy
   // with proof 0's on the device and the call is redone without sharing if one differs)
-  std::vector<int32_t> term_shared(n_terms, -1);
   const bool share = ctx->share_static_tables && nc > 0 && N > 1;
-  if (share)
-    for (int q = 0; q < n_terms; q++)
-      if (sd->term_point[q] >= ni) term_shared[q] = sd->term_point[q] - ni;
+  // comb path: every point that serves as a base gets a comb slot -- shared (one comb per batch) for the batch-static
+  // points when sharing is on, per proof otherwise (pv_plan.hpp)
+  const bool comb = ctx->prove_comb && n_terms > 0;
+  pv_plan plan;
+  pv_make_plan(ni, p, k, sd->cons_off, sd->term_point, share, comb, &plan);
+  const std::vector<int32_t>&slot = plan.cons_slot, &term_shared = plan.term_shared, &term_slot = plan.term_slot,
+                            &comb_slot_point = plan.comb_slot_point, &comb_shared_point = plan.comb_shared_point;
+  const size_t U = comb_slot_point.size(), Us = comb_shared_point.size();
   std::vector<uint8_t> blob(blob_sz, 0);
   memcpy(&blob[o_prefix], prefix_state, 53 * 4);
+  if (comb) {
+    memcpy(&blob[o_cs], term_slot.data(), (size_t)n_terms * 4);
+    if (U) memcpy(&blob[o_cp], comb_slot_point.data(), U * 4);
+    if (Us) memcpy(&blob[o_cq], comb_shared_point.data(), Us * 4);
+  }
   if (!pool.empty()) memcpy(&blob[o_pool], pool.data(), pool.size());
   if (p) { memcpy(&blob[o_lo], loff.data(), (size_t)p * 4); memcpy(&blob[o_ll], llen.data(), (size_t)p * 4); }
   if (k) { memcpy(&blob[o_lhs], sd->lhs, (size_t)k * 4); memcpy(&blob[o_sl], slot.data(), (size_t)k * 4); }
@@ -1402,7 +1412,8 @@ static int32_t prove_batch_impl(zkp_ctx* ctx, const zkp_statement_desc* sd, cons
   ENSURE(ctx, ctx->pv_resp, N * (size_t)m * 32 + 32);
   ENSURE(ctx, ctx->in_scalars, total * 32 + 32);
   ENSURE(ctx, ctx->niels, total * 128 + 128);
-  ENSURE(ctx, ctx->tables, ((N + 31) / 32 * 32) * (size_t)n_terms * 1024 + 1024);   // interleaved in groups of 32 proofs
+  // Straus tables: one KB per term; combs: one KB per per-proof base; both interleaved in groups of 32 proofs
+  ENSURE(ctx, ctx->tables, ((N + 31) / 32 * 32) * (comb ? U : (size_t)n_terms) * 1024 + 1024);
   ENSURE(ctx, ctx->sk0, total * 32 + 32);
   ENSURE(ctx, ctx->aux0, (M + 1) * 8);
   ENSURE(ctx, ctx->aux1, M * 32 + 32);
@@ -1450,6 +1461,30 @@ static int32_t prove_batch_impl(zkp_ctx* ctx, const zkp_statement_desc* sd, cons
     LAUNCH_CHECK(ctx);
     const int32_t* shared_of = share ? d.term_shared : nullptr;
     uint4* shared_tables = nullptr;
+    if (comb) {
+      // one comb per base, sign-bit recoding of every blinding, then 64 columns per constraint MSM
+      ENSURE(ctx, ctx->pv_static, Us * 1024 + 256);
+      if (U) {
+        k_build_combs<true><<<(unsigned)((N * U + 63) / 64), 64, 0, st>>>((const unsigned long long*)ctx->pv_limbs.p, N * U,
+                                                                        (uint32_t)U, (uint32_t)p,
+                                                                        (const int32_t*)(dm + o_cp), (uint4*)ctx->tables.p);
+        LAUNCH_CHECK(ctx);
+      }
+      if (Us) {   // from proof 0's copy (k_pv_gather compared every other copy with it)
+        k_build_combs<false><<<(unsigned)((Us + 63) / 64), 64, 0, st>>>((const unsigned long long*)ctx->pv_limbs.p, Us,
+                                                                      (uint32_t)Us, (uint32_t)p,
+                                                                      (const int32_t*)(dm + o_cq), (uint4*)ctx->pv_static.p);
+        LAUNCH_CHECK(ctx);
+      }
+      k_comb_recode<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const uint4*)ctx->in_scalars.p, total, (uint4*)ctx->sk0.p);
+      LAUNCH_CHECK(ctx);
+      k_small_msm_comb<<<(unsigned)((M + 63) / 64), 64, 0, st>>>((const uint32_t*)ctx->sk0.p, (const uint4*)ctx->tables.p,
+                                                              (const uint4*)ctx->pv_static.p, (const int32_t*)(dm + o_cs),
+                                                              (const unsigned long long*)ctx->aux0.p,
+                                                              (const uint32_t*)ctx->multi.p, M, (uint32_t)n_terms,
+                                                              (uint32_t)U, (uint4*)ctx->aux1.p);
+      LAUNCH_CHECK(ctx);
+    } else {
     if (share) {
       // tables of the nc batch-static points, built once from proof 0's copy (all copies were compared above)
       ENSURE(ctx, ctx->pv_static, (size_t)nc * (128 + 1024 + 32 + 32) + 256);
@@ -1477,6 +1512,7 @@ static int32_t prove_batch_impl(zkp_ctx* ctx, const zkp_statement_desc* sd, cons
                                                                    (const uint32_t*)ctx->multi.p, M, (uint32_t)n_terms,
                                                                    (uint4*)ctx->aux1.p, shared_of, shared_tables);
     LAUNCH_CHECK(ctx);
+    }
   }
   // (4) commitments into the transcript, challenge, responses (prover.rs:98-109)
   k_pv_finish<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(d, N, (const uint32_t*)ctx->pv_state.p, (const uint8_t*)ctx->aux1.p,

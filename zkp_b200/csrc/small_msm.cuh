@@ -12,6 +12,7 @@
 //                    digit and the selection is arithmetic masking; checked in SASS.
 // Outputs are ristretto encodings, so they are byte-identical to the reference's whatever the digit set.
 #pragma once
+#include "comb.cuh"
 #include "kernels.cuh"
 
 namespace zkp {
@@ -283,6 +284,96 @@ __global__ void __launch_bounds__(64) k_small_msm_ct(const uint32_t* __restrict_
     }
   }
   if (sub != 0) return;
+  uint32_t enc[8];
+  ristretto_encode(enc, acc);
+  out[2 * j] = make_uint4(enc[0], enc[1], enc[2], enc[3]);
+  out[2 * j + 1] = make_uint4(enc[4], enc[5], enc[6], enc[7]);
+}
+
+// ---- comb path of batch proving (comb.cuh; SURVEY 8f row f4, second half) ------------------------------------------
+// Every base a statement's constraints use gets ONE signed four-tooth comb -- per proof for instance points, per batch
+// for the batch-static points -- and every constraint MSM then runs 64 doublings instead of 256.
+// Layouts (uint4 units, entry e = 0..7 of 8 uint4): per-proof combs interleaved like the Straus tables,
+// combs[ct_table_index<true>(j * U + u, U) + (8 e + q) * 32] for slot u of proof j; shared combs[u * 64 + 8 e + q].
+
+// one thread per (proof j, slot u), i = j * U + u: the comb of the proof's copy of point slot_point[u]
+// (IL = false: the shared combs, built from proof 0's copy: n = U threads)
+template <bool IL>
+__global__ void __launch_bounds__(64) k_build_combs(const unsigned long long* __restrict__ limbs, size_t n, uint32_t U,
+                                                    uint32_t points_per_proof, const int32_t* __restrict__ slot_point,
+                                                    uint4* __restrict__ combs) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const size_t j = i / U;
+  const uint32_t u = (uint32_t)(i % U);
+  ge_ext P;
+  load_ext_limbs51(P, limbs + (j * points_per_proof + (size_t)slot_point[u]) * 20);
+  ge_pniels E[8];
+  comb_build(E, P);
+  const size_t stride = IL ? 32 : 1;
+  uint4* tab = combs + (IL ? ct_table_index<true>(i, U) : i * 64);
+#pragma unroll 1
+  for (int e = 0; e < 8; e++) {
+    const uint32_t* w = (const uint32_t*)&E[e];
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+      tab[(size_t)(8 * e + q) * stride] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+  }
+}
+
+// one thread per term: the sign bits of the signed-digit form of its (canonical) scalar
+__global__ void __launch_bounds__(256) k_comb_recode(const uint4* __restrict__ scalars, size_t n, uint4* __restrict__ recoded) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t s[8], m[8];
+  load_words8(s, scalars + 2 * i);
+  comb_recode(m, s);
+  recoded[2 * i] = make_uint4(m[0], m[1], m[2], m[3]);
+  recoded[2 * i + 1] = make_uint4(m[4], m[5], m[6], m[7]);
+}
+
+// one thread per MSM (a constraint of a proof; CSR over the batch's term list, T terms per proof).  term_slot[r] for
+// term r of a proof: u >= 0 = per-proof comb slot u, -(s + 1) = shared comb s.  Public: order, offsets, term_slot.
+__global__ void __launch_bounds__(64) k_small_msm_comb(const uint32_t* __restrict__ recoded, const uint4* __restrict__ combs,
+                                                       const uint4* __restrict__ shared_combs,
+                                                       const int32_t* __restrict__ term_slot,
+                                                       const unsigned long long* __restrict__ offsets,
+                                                       const uint32_t* __restrict__ order, size_t M, uint32_t T, uint32_t U,
+                                                       uint4* __restrict__ out) {
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= M) return;
+  const size_t j = order[tid];
+  const size_t lo = offsets[j], hi = offsets[j + 1];
+  const size_t proof = lo / T;
+  const uint32_t r0 = (uint32_t)(lo % T);
+  ge_ext acc;
+  ge_identity(acc);
+#pragma unroll 1
+  for (int col = 63; col >= 0; col--) {
+    ge_double(acc, acc);
+#pragma unroll 1
+    for (size_t t = lo; t < hi; t++) {
+      const int32_t slot = term_slot[r0 + (uint32_t)(t - lo)];
+      const uint4* tab;
+      size_t stride;
+      if (slot >= 0) {   // public: depends on the statement only
+        tab = combs + (((proof >> 5) * U + (uint32_t)slot) * 64 * 32 + (proof & 31));   // = ct_table_index<true>(proof * U + slot, U)
+        stride = 32;
+      } else {
+        tab = shared_combs + (size_t)(-slot - 1) * 64;
+        stride = 1;
+      }
+      const uint32_t* mw = recoded + 8 * t + (col >> 5);
+      uint32_t idx, neg;
+      comb_column_words(idx, neg, __ldg(mw), __ldg(mw + 2), __ldg(mw + 4), __ldg(mw + 6), col & 31);
+      ge_pniels sel;
+      comb_select(sel, [&](uint32_t e, int q, uint32_t& x, uint32_t& y, uint32_t& z, uint32_t& ww) {
+        const uint4 v = __ldg(tab + (size_t)(8 * e + q) * stride);
+        x = v.x; y = v.y; z = v.z; ww = v.w;
+      }, idx, neg);
+      ge_add_pniels(acc, acc, sel);
+    }
+  }
   uint32_t enc[8];
   ristretto_encode(enc, acc);
   out[2 * j] = make_uint4(enc[0], enc[1], enc[2], enc[3]);
