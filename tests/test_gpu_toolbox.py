@@ -1,5 +1,7 @@
 """GPU parity of the host mirror (C++ toolbox over the CUDA engine) against the oracle's restatement of the
 reference's Prover / Verifier / BatchVerifier: identical injected randomness => identical bytes."""
+import os
+
 import numpy as np
 import pytest
 
@@ -322,6 +324,57 @@ def test_prove_many_device_front_end_matches_host_and_oracle(engine):
     a = pk.prove_many(engine, b"PK", np.stack([sbytes([123456789])] * 4), pts, ent, threads=1)
     b = pk.prove_many_device(engine, b"PK", np.stack([sbytes([123456789])] * 4), pts, ent)
     assert all((x == y).all() for x, y in zip(a, b))
+
+
+@pytest.mark.skipif(os.environ.get("ZKP_TEST_PROVE_COMB") != "1",
+                    reason="the comb path of the batch prover (option prove_comb, off by default) has been checked in host "
+                           "emulation only; set ZKP_TEST_PROVE_COMB=1 to run its device parity test")
+def test_prove_many_device_comb_path_matches_straus_path(engine):
+    """Option prove_comb (signed four-tooth combs, comb.cuh) gives the bytes of the default Straus path of
+    zkp_prove_batch: CMZ with 70 proofs (three interleave groups, the last one partial), shared and per-proof combs for
+    the batch-static points, a batch whose common points differ (fallback), slices, N = 1, DLEQ and a static-lhs statement."""
+    st = PT.cmz10_statement()
+    N = 70
+    secs, ptss = _cmz_instances(N, b"cmz-comb")
+    sec_arr = np.stack([sbytes([s[n] for n in st.secrets]) for s in secs])
+    pts_arr = np.array([[limbs(p[n]) for n in st.points] for p in ptss], dtype=np.uint64)
+    entropy = np.frombuffer(OT.SeededRng(b"entropy-comb").bytes(32 * N), dtype=np.uint8).reshape(N, 32)
+    want = st.prove_many_device(engine, b"CMZ", sec_arr, pts_arr, entropy)
+    secs2, ptss2 = _cmz_instances(1, b"cmz-comb-other-common", fresh_common=True)
+    mixed_pts, mixed_sec = pts_arr.copy(), sec_arr.copy()
+    mixed_pts[N - 1] = np.array([limbs(ptss2[0][n]) for n in st.points], dtype=np.uint64)
+    mixed_sec[N - 1] = sbytes([secs2[0][n] for n in st.secrets])
+    want_mixed = st.prove_many_device(engine, b"CMZ", mixed_sec, mixed_pts, entropy)
+    dst = PT.dleq_statement()
+    G = R.BASEPOINT
+    H = R.hash_from_bytes_sha512(R.compress(G))
+    xs = [89327492234 + j for j in range(9)]
+    dl = np.array([[limbs(R.pt_mul(x, G)), limbs(R.pt_mul(x, H)), limbs(H), limbs(G)] for x in xs], dtype=np.uint64)
+    ent = np.frombuffer(OT.SeededRng(b"e-comb").bytes(32 * 9), dtype=np.uint8).reshape(9, 32)
+    dsec = np.stack([sbytes([x]) for x in xs])
+    want_dleq = dst.prove_many_device(engine, b"DLEQBatchTest", dsec, dl, ent)
+    pk = PT.Statement("pk", "PK proof", ["x"], ["A"], ["G", "Q"], [("A", [("x", "G")]), ("Q", [("x", "G")])])
+    Q = R.pt_mul(123456789, G)
+    pkp = np.array([[limbs(Q), limbs(G), limbs(Q)] for _ in range(4)], dtype=np.uint64)
+    pke = np.frombuffer(OT.SeededRng(b"pk-comb").bytes(32 * 4), dtype=np.uint8).reshape(4, 32)
+    want_pk = pk.prove_many_device(engine, b"PK", np.stack([sbytes([123456789])] * 4), pkp, pke)
+    same = lambda a, b: all((x == y).all() for x, y in zip(a, b))
+    engine.set_option("prove_comb", 1)
+    try:
+        for share in (1, 0):
+            engine.set_option("share_static_tables", share)
+            assert same(st.prove_many_device(engine, b"CMZ", sec_arr, pts_arr, entropy), want), share
+            assert same(st.prove_many_device(engine, b"CMZ", mixed_sec, mixed_pts, entropy), want_mixed), share
+            assert same(st.prove_many_device(engine, b"CMZ", sec_arr[:1], pts_arr[:1], entropy[:1]), [w[:1] for w in want])
+            assert same(dst.prove_many_device(engine, b"DLEQBatchTest", dsec, dl, ent), want_dleq), share
+            assert same(pk.prove_many_device(engine, b"PK", np.stack([sbytes([123456789])] * 4), pkp, pke), want_pk), share
+        engine.set_option("share_static_tables", 1)
+        engine.set_option("prove_chunk", 33)
+        assert same(st.prove_many_device(engine, b"CMZ", sec_arr, pts_arr, entropy), want)
+    finally:
+        engine.set_option("prove_comb", 0)
+        engine.set_option("share_static_tables", 1)
+        engine.set_option("prove_chunk", 1 << 17)
 
 
 def test_compiled_transcript_script_equals_bytewise_strobe(engine):

@@ -29,12 +29,16 @@ def main():
     ap.add_argument("--cpu-port", action="store_true",
                     help="also time the C port of the reference's CPU algorithms (oracle/_ref) beside the raw MSM sweep, as "
                          "bench.py's cpu_baseline leg does; it doubles as a byte-for-byte check of the GPU results")
+    ap.add_argument("--prove-comb", action="store_true",
+                    help="batch proving through the comb path (engine option prove_comb; off by default until measured)")
     ap.add_argument("--out", default="gpurun_out/configs.json")
     args = ap.parse_args()
     eng = Engine(0)
+    if args.prove_comb:
+        eng.set_option("prove_comb", 1)
     rng = np.random.default_rng(2026)
     threads = os.cpu_count() or 1
-    res = {"host_threads": threads, "gpu": torch.cuda.get_device_name(0)}
+    res = {"host_threads": threads, "gpu": torch.cuda.get_device_name(0), "prove_comb": bool(args.prove_comb)}
 
     # ---- configs[0]: DLEQ 1 prove + 1 verify (latency through the host mirror) -----------------------------
     st = PT.dleq_statement()
