@@ -8,21 +8,10 @@
 #include "../../zkp_b200/csrc/pv_plan.hpp"
 using namespace zkp;
 
-extern "C" {
-// limbs [N][p][20] (FieldElement51 X,Y,Z,T), blind [N][m][32] canonical -> com [N][k][32]; returns the not-uniform flag
-// (1 if a common point differed between proofs while share was requested: the caller reruns without sharing, as api.cu does)
-int emul_prove_msms(int m, int ni, int nc, int k, const int32_t* lhs, const int32_t* cons_off, const int32_t* term_scalar,
-                    const int32_t* term_point, size_t N, const uint64_t* limbs, const uint8_t* blind, int share, int comb,
-                    uint8_t* com) {
-  const int p = ni + nc, T = k ? cons_off[k] : 0;
-  pv_plan plan;
-  pv_make_plan(ni, p, k, cons_off, term_point, share != 0, comb != 0, &plan);
-  pv_desc d;
-  memset(&d, 0, sizeof d);
-  d.m = m; d.p = p; d.k = k; d.n_terms = T; d.ni = ni;
-  d.term_shared = plan.term_shared.data();
-  d.lhs = lhs; d.cons_off = cons_off; d.term_scalar = term_scalar; d.term_point = term_point;
-  d.cons_slot = plan.cons_slot.data();
+// step (3) of zkp_prove_batch: the N * k constant-time MSMs + compress; returns the not-uniform flag
+static int run_msms(const pv_desc& d, const pv_plan& plan, int nc, size_t N, const uint64_t* limbs, const uint8_t* blind,
+                    int share, int comb, uint8_t* com) {
+  const int p = d.p, k = d.k, T = d.n_terms, ni = d.ni;
   const size_t total = N * (size_t)T, M = N * (size_t)k, Npad = (N + 31) / 32 * 32;
   std::vector<uint4> scalars_flat(2 * total + 2), ext_flat(8 * total + 8), out(2 * M + 2);
   std::vector<unsigned long long> offsets(M + 1);
@@ -63,5 +52,70 @@ int emul_prove_msms(int m, int ni, int nc, int k, const int32_t* lhs, const int3
   }
   memcpy(com, out.data(), M * 32);
   return flags[2];
+}
+
+static void fill_desc(pv_desc* d, const pv_plan& plan, int m, int ni, int nc, int k, const int32_t* lhs,
+                      const int32_t* cons_off, const int32_t* term_scalar, const int32_t* term_point) {
+  memset(d, 0, sizeof *d);
+  d->m = m; d->p = ni + nc; d->k = k; d->n_terms = k ? cons_off[k] : 0; d->ni = ni;
+  d->term_shared = plan.term_shared.data();
+  d->lhs = lhs; d->cons_off = cons_off; d->term_scalar = term_scalar; d->term_point = term_point;
+  d->cons_slot = plan.cons_slot.data();
+}
+
+extern "C" {
+// limbs [N][p][20] (FieldElement51 X,Y,Z,T), blind [N][m][32] canonical -> com [N][k][32]; returns the not-uniform flag
+// (1 if a common point differed between proofs while share was requested: the caller reruns without sharing, as api.cu does)
+int emul_prove_msms(int m, int ni, int nc, int k, const int32_t* lhs, const int32_t* cons_off, const int32_t* term_scalar,
+                    const int32_t* term_point, size_t N, const uint64_t* limbs, const uint8_t* blind, int share, int comb,
+                    uint8_t* com) {
+  pv_plan plan;
+  pv_make_plan(ni, ni + nc, k, cons_off, term_point, share != 0, comb != 0, &plan);
+  pv_desc d;
+  fill_desc(&d, plan, m, ni, nc, k, lhs, cons_off, term_scalar, term_point);
+  return run_msms(d, plan, nc, N, limbs, blind, share, comb, com);
+}
+
+// All of zkp_prove_batch (api.cu) for N proofs: k_compress_limbs -> k_pv_blind -> MSMs -> k_pv_finish.
+// labels: p NUL-terminated point labels (instance ++ common); prefix53: the transcript state every proof starts from.
+// Returns 0, 3 for a non-canonical secret (ZKP_ERR_SCALAR), or -100 - flag when sharing was requested for points that differ.
+int emul_prove_batch(int m, int ni, int nc, int k, const char* labels, const int32_t* lhs, const int32_t* cons_off,
+                     const int32_t* term_scalar, const int32_t* term_point, const uint32_t* prefix53, size_t N,
+                     const uint8_t* secrets, const uint64_t* limbs, const uint8_t* entropy, int share, int comb,
+                     uint8_t* enc_out, uint8_t* com_out, uint8_t* resp_out) {
+  const int p = ni + nc;
+  pv_plan plan;
+  pv_make_plan(ni, p, k, cons_off, term_point, share != 0, comb != 0, &plan);
+  pv_desc d;
+  fill_desc(&d, plan, m, ni, nc, k, lhs, cons_off, term_scalar, term_point);
+  std::vector<uint32_t> loff, llen;
+  std::vector<uint8_t> pool;
+  const char* lp = labels;
+  for (int i = 0; i < p; i++) {
+    const size_t len = strlen(lp);
+    loff.push_back((uint32_t)pool.size());
+    llen.push_back((uint32_t)len);
+    pool.insert(pool.end(), lp, lp + len);
+    lp += len + 1;
+  }
+  pool.push_back(0);
+  d.label_off = loff.data(); d.label_len = llen.data(); d.labels = pool.data();
+  int flags[4] = {0x7fffffff, 0x7fffffff, 0, 0};
+  std::vector<uint4> enc(2 * N * p + 2);
+  if (p) emul_launch((unsigned)((N * p + 255) / 256), 256, k_compress_limbs, (const unsigned long long*)limbs, N * (size_t)p, enc.data());
+  std::vector<uint32_t> states(N * 56 + 56);
+  std::vector<uint8_t> blind(N * (size_t)m * 32 + 32), com(N * (size_t)k * 32 + 32), resp(N * (size_t)m * 32 + 32);
+  emul_launch((unsigned)((N + 127) / 128), 128, k_pv_blind, d, prefix53, N, (const uint8_t*)enc.data(), secrets, entropy,
+              states.data(), blind.data(), flags);
+  if (k) {
+    const int nu = run_msms(d, plan, nc, N, limbs, blind.data(), share, comb, com.data());
+    if (nu) return -100 - nu;
+  }
+  emul_launch((unsigned)((N + 127) / 128), 128, k_pv_finish, d, N, (const uint32_t*)states.data(), (const uint8_t*)com.data(),
+              secrets, (const uint8_t*)blind.data(), resp.data());
+  memcpy(enc_out, enc.data(), N * (size_t)p * 32);
+  memcpy(com_out, com.data(), N * (size_t)k * 32);
+  memcpy(resp_out, resp.data(), N * (size_t)m * 32);
+  return flags[1] != 0x7fffffff ? 3 : 0;
 }
 }

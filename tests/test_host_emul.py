@@ -422,3 +422,93 @@ def test_batch_prover_msm_kernels_run_on_the_host(klib):
     for comb in (0, 1):
         flag, _ = run(odd, 1, comb, same_representative=True)
         assert flag != 0
+
+
+def test_device_prover_pipeline_on_the_host_matches_the_oracle_prover(klib):
+    """All of zkp_prove_batch's kernels (k_compress_limbs, k_pv_blind, k_pv_gather, the Straus or the comb MSMs,
+    k_pv_finish) run thread by thread on the CPU from the same inputs as the oracle's Prover (/root/reference/src/toolbox/
+    prover.rs:76-112 restated): encodings, commitments and responses of CMZ'13 proofs (11 constraints, 31 terms) and of DLEQ
+    proofs are byte-identical, with shared and per-proof tables, Straus and comb; a non-canonical secret is reported."""
+    import numpy as np
+    from oracle import merlin as OM, msm as M, scalar as S, toolbox as OT
+
+    class OneShot:
+        def __init__(self, b): self.b = b
+        def bytes(self, n): return self.b
+
+    def limbs_of(pt):
+        return [((c % P) >> (51 * j)) & ((1 << 51) - 1) for c in pt for j in range(5)]
+
+    klib.emul_prove_batch.argtypes = ([ctypes.c_int] * 4 + [ctypes.c_char_p] + [ctypes.c_void_p] * 5 + [ctypes.c_size_t]
+                                      + [ctypes.c_void_p] * 3 + [ctypes.c_int] * 2 + [ctypes.c_void_p] * 3)
+
+    def device_prove(ost, tlabel, secs, ptss, entropy, share, comb):
+        names = ost.instance + ost.common
+        m, ni, nc, k, N = len(ost.secrets), len(ost.instance), len(ost.common), len(ost.constraints), len(secs)
+        lhs = np.array([names.index(l) for l, _ in ost.constraints], dtype=np.int32)
+        off = np.cumsum([0] + [len(r) for _, r in ost.constraints]).astype(np.int32)
+        ts = np.array([ost.secrets.index(s) for _, r in ost.constraints for s, _ in r], dtype=np.int32)
+        tp = np.array([names.index(q) for _, r in ost.constraints for _, q in r], dtype=np.int32)
+        # the transcript every proof starts from: Transcript::new(label), dom-sep, scalar labels (macros.rs:206-214)
+        t = OM.Transcript(tlabel)
+        OT.domain_sep(t, ost.label)
+        for s_ in ost.secrets:
+            OT.append_scalar_var(t, s_.encode())
+        st = t.strobe
+        state = bytes(st.state)
+        prefix = np.array([int.from_bytes(state[4 * i:4 * i + 4], "little") for i in range(50)]
+                          + [st.pos, st.pos_begin, st.cur_flags], dtype=np.uint32)
+        sec = np.frombuffer(b"".join(S.to_bytes(s[n]) if isinstance(s[n], int) else s[n] for s in secs for n in ost.secrets),
+                            dtype=np.uint8).copy()
+        lim = np.array([[limbs_of(pp[n]) for n in names] for pp in ptss], dtype=np.uint64)
+        ent = np.frombuffer(b"".join(entropy), dtype=np.uint8).copy()
+        enc, com, resp = (np.zeros((N, len(names), 32), np.uint8), np.zeros((N, k, 32), np.uint8), np.zeros((N, m, 32), np.uint8))
+        rc = klib.emul_prove_batch(m, ni, nc, k, b"".join(n.encode() + b"\0" for n in names), lhs.ctypes.data, off.ctypes.data,
+                                   ts.ctypes.data, tp.ctypes.data, prefix.ctypes.data, N, sec.ctypes.data, lim.ctypes.data,
+                                   ent.ctypes.data, share, comb, enc.ctypes.data, com.ctypes.data, resp.ctypes.data)
+        return rc, enc, com, resp
+
+    rng = OT.SeededRng(b"emul-prover")
+    ost = OT.CMZ10
+    common = {n: R.from_uniform_bytes(rng.bytes(64)) for n in ost.common}
+    secs, ptss = [], []
+    N = 3
+    for _ in range(N):
+        sec = {n: int.from_bytes(rng.bytes(64), "little") % S.L for n in ost.secrets}
+        Pp, Q = R.from_uniform_bytes(rng.bytes(64)), R.from_uniform_bytes(rng.bytes(64))
+        pts = dict(common)
+        pts["P"], pts["Q"] = Pp, Q
+        for i in range(1, 11):
+            pts["C_%d" % i] = M.naive_msm([sec["m_%d" % i], sec["z_%d" % i]], [Pp, pts["A"]])
+        pts["V"] = M.naive_msm([sec["m_%d" % i] for i in range(1, 11)] + [sec["minus_z_Q"]],
+                               [pts["X_%d" % i] for i in range(1, 11)] + [Q])
+        secs.append(sec)
+        ptss.append(pts)
+    entropy = [rng.bytes(32) for _ in range(N)]
+    want = [ost.prove_batchable(OM.Transcript(b"CMZ"), secs[j], ptss[j], OneShot(entropy[j])) for j in range(N)]
+    for share, comb in ((1, 0), (1, 1), (0, 1)):
+        rc, enc, com, resp = device_prove(ost, b"CMZ", secs, ptss, entropy, share, comb)
+        assert rc == 0, (share, comb)
+        for j in range(N):
+            proof, oenc = want[j]
+            assert [bytes(c) for c in com[j]] == proof.commitments, (share, comb, j)
+            assert [bytes(r) for r in resp[j]] == [S.to_bytes(r) for r in proof.responses], (share, comb, j)
+            assert [bytes(e) for e in enc[j]] == [oenc[n] for n in ost.instance + ost.common]
+    # DLEQ (tests/zkp.rs:28 form: H is an instance variable), comb path
+    G = R.BASEPOINT
+    H = R.hash_from_bytes_sha512(R.compress(G))
+    xs = [89327492234 + j for j in range(2)]
+    dsecs = [{"x": x} for x in xs]
+    dpts = [{"A": R.pt_mul(x, G), "B": R.pt_mul(x, H), "H": H, "G": G} for x in xs]
+    dent = [rng.bytes(32) for _ in xs]
+    for comb in (0, 1):
+        rc, enc, com, resp = device_prove(OT.DLEQ, b"DLEQTest", dsecs, dpts, dent, 1, comb)
+        assert rc == 0
+        for j in range(2):
+            proof, _ = OT.DLEQ.prove_batchable(OM.Transcript(b"DLEQTest"), dsecs[j], dpts[j], OneShot(dent[j]))
+            assert [bytes(c) for c in com[j]] == proof.commitments and [bytes(r) for r in resp[j]] == [S.to_bytes(r) for r in proof.responses]
+    # a non-canonical secret comes back as ZKP_ERR_SCALAR
+    bad = [dict(d) for d in dsecs]
+    bad[1]["x"] = b"\xff" * 32
+    rc, *_ = device_prove(OT.DLEQ, b"DLEQTest", bad, dpts, dent, 1, 0)
+    assert rc == 3
