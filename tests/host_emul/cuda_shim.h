@@ -38,8 +38,9 @@ static inline void __syncthreads() {}
 static inline void __syncwarp(unsigned = 0xffffffffu) {}
 static inline unsigned __ballot_sync(unsigned, int p) { return p ? 1u : 0u; }
 static inline int __any_sync(unsigned, int p) { return p; }
-static inline unsigned __activemask() { return 1u; }
-template <class T> static inline unsigned __match_any_sync(unsigned, T) { return 1u; }
+// a thread is alone in its warp here: it is its own (and only) peer
+static inline unsigned __activemask() { return 1u << (threadIdx.x & 31); }
+template <class T> static inline unsigned __match_any_sync(unsigned, T) { return 1u << (threadIdx.x & 31); }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
 static inline int __ffs(int x) { return __builtin_ffs(x); }
