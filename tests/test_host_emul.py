@@ -512,3 +512,40 @@ def test_device_prover_pipeline_on_the_host_matches_the_oracle_prover(klib):
     bad[1]["x"] = b"\xff" * 32
     rc, *_ = device_prove(OT.DLEQ, b"DLEQTest", bad, dpts, dent, 1, 0)
     assert rc == 3
+
+
+def test_small_msm_kernels_on_the_host_against_the_golden_kats(klib):
+    """The batched small-MSM kernels behind verify_compact and the single-proof prover -- k_decompress_valid,
+    k_prep_scalars_vt, k_small_msm_vt (variable time, signed binary digits of k and 3k) and k_decompress_ext,
+    k_build_tables, k_small_msm_ct (constant time, radix 16) -- run thread by thread on the CPU over the golden MSM KATs as
+    one CSR batch: every result equals the KAT (edge scalars, identity sums, sizes 1..36); an undecodable point and a
+    non-canonical scalar are reported per MSM."""
+    import numpy as np
+    from tests import util_data as U
+    kats = [k_ for k_ in U.golden("msm_kat.json")["kats"] if k_["n"] <= 36]
+    sc = b"".join(bytes.fromhex(x) for k_ in kats for x in k_["scalars"])
+    pt = b"".join(bytes.fromhex(x) for k_ in kats for x in k_["points"])
+    off = np.cumsum([0] + [k_["n"] for k_ in kats]).astype(np.uint64)
+    M = len(kats)
+    out = ctypes.create_string_buffer(M * 32)
+    status = np.zeros(M, dtype=np.int32)
+    klib.emul_msm_vartime_batched.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p,
+                                              ctypes.c_void_p]
+    klib.emul_msm_ct_batched.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+    klib.emul_msm_vartime_batched(sc, pt, off.ctypes.data, M, ctypes.cast(out, ctypes.c_void_p), status.ctypes.data)
+    assert (status == 0).all()
+    assert [out.raw[32 * j:32 * j + 32].hex() for j in range(M)] == [k_["expected"] for k_ in kats]
+    out2 = ctypes.create_string_buffer(M * 32)
+    assert klib.emul_msm_ct_batched(sc, pt, off.ctypes.data, M, ctypes.cast(out2, ctypes.c_void_p)) == 0
+    assert out2.raw == out.raw
+    # failures are local to their MSM (vartime) / reported with the entry point's codes (constant time)
+    victim = next(j for j, k_ in enumerate(kats) if k_["n"] >= 2)
+    t0 = int(off[victim])
+    bad_pt = bytearray(pt); bad_pt[32 * t0:32 * t0 + 32] = b"\xff" * 32
+    bad_sc = bytearray(sc); bad_sc[32 * (t0 + 1):32 * (t0 + 1) + 32] = b"\xff" * 32
+    klib.emul_msm_vartime_batched(sc, bytes(bad_pt), off.ctypes.data, M, ctypes.cast(out2, ctypes.c_void_p), status.ctypes.data)
+    assert status[victim] == 1 and (np.delete(status, victim) == 0).all() and out2.raw[32 * victim:32 * victim + 32] == bytes(32)
+    klib.emul_msm_vartime_batched(bytes(bad_sc), pt, off.ctypes.data, M, ctypes.cast(out2, ctypes.c_void_p), status.ctypes.data)
+    assert status[victim] == 3 and (np.delete(status, victim) == 0).all()
+    assert klib.emul_msm_ct_batched(sc, bytes(bad_pt), off.ctypes.data, M, ctypes.cast(out2, ctypes.c_void_p)) == 1
+    assert klib.emul_msm_ct_batched(bytes(bad_sc), pt, off.ctypes.data, M, ctypes.cast(out2, ctypes.c_void_p)) == 3
