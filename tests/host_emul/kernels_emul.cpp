@@ -165,4 +165,113 @@ int emul_msm_ct_batched(const uint8_t* scalars, const uint8_t* points, const uin
   if (flags[1] != 0x7fffffff) return 3;
   return 0;
 }
+
+// The variable-time MSM, device-resident path (api.cu msm_vartime_launch + msm_finish with the two-phase ingestion, the
+// size-ordered accumulation and the chunked bucket reduction), kernel by kernel: window width c, work-item length S
+// (0 = the heuristic of api.cu).  res64 receives the msm_result (enc[32] | status | is_identity | first_bad).
+// The launch sequence mirrors api.cu; grids of the grid-stride kernels are smaller (the result does not depend on them).
+// host_window_scan != 0: the per-window scan (W blocks of 1024 threads, by far the slowest thing to emulate) is replaced by a
+// host prefix sum with the same outputs; the single-block scans and every other kernel still run as kernels.
+void emul_msm_vartime(const uint8_t* scalars, const uint8_t* points, size_t n, int c, uint32_t S_forced, int balance,
+                      int host_window_scan, uint8_t* res64) {
+  msm_result res;
+  memset(&res, 0, sizeof res);
+  if (n == 0) {
+    emul_launch(1, 1, k_empty_result, &res);
+    memcpy(res64, &res, sizeof res);
+    return;
+  }
+  const int W = (253 + c - 1) / c;
+  const uint32_t B = 1u << (c - 1), total_buckets = (uint32_t)W * B;
+  std::vector<uint4> sc(2 * n), pt(2 * n), niels(6 * n), buckets((size_t)total_buckets * 8);
+  memcpy(sc.data(), scalars, n * 32);
+  memcpy(pt.data(), points, n * 32);
+  std::vector<uint32_t> hist((size_t)W * B, 0), offs((size_t)W * (B + 1)), cursor((size_t)W * B), sorted((size_t)W * n);
+  int flags[4];
+  emul_launch(1, 1, k_init_flags, flags);
+  auto ingest = [&](auto kernel, size_t p_lo, size_t p_cnt, size_t s_lo, size_t s_cnt, uint32_t* counters) {
+    const size_t half = (s_cnt + 1) / 2;
+    size_t threads = std::max(p_cnt, std::max(half, s_cnt - half));
+    if (!threads) return;
+    emul_launch((unsigned)((threads + 255) / 256), 256, kernel, (const uint4*)pt.data(), p_lo, p_cnt, niels.data(),
+                (const uint4*)sc.data(), s_lo, half, s_lo + half, s_cnt - half, n, c, W, B, counters, sorted.data(), flags);
+  };
+  const size_t half_p = (n + 1) / 2;
+  ingest(k_ingest2<0, 2>, 0, half_p, 0, n, hist.data());
+  if (host_window_scan) {
+    for (int w = 0; w < W; w++) {
+      uint32_t acc = 0;
+      for (uint32_t b = 0; b < B; b++) {
+        offs[(size_t)w * (B + 1) + b] = acc;
+        cursor[(size_t)w * B + b] = acc;
+        acc += hist[(size_t)w * B + b];
+      }
+      offs[(size_t)w * (B + 1) + B] = acc;
+    }
+  } else {
+    emul_launch_mt((unsigned)W, 1024, k_scan, (const uint32_t*)hist.data(), B, offs.data(), cursor.data());
+  }
+  ingest(k_ingest2<1, 2>, half_p, n - half_p, 0, n, cursor.data());
+  // ---- msm_finish ----
+  uint32_t S = S_forced;
+  if (!S) {
+    const double mean = (double)n / (double)B, want = 2.0 * mean, cap = (double)n * W / 200000.0;
+    double v = want < cap ? want : cap;
+    if (v < 16.0) v = 16.0;
+    if (v > 4096.0) v = 4096.0;
+    S = (uint32_t)v;
+  }
+  const size_t max_items = (size_t)total_buckets + ((size_t)W * n) / S + 1;
+  std::vector<uint32_t> aux0(total_buckets), aux1((size_t)total_buckets + 1), aux2(total_buckets), multi((size_t)total_buckets + 4, 0);
+  std::vector<work_item> items(max_items);
+  std::vector<uint4> partials(max_items * 8);
+  const unsigned tb = (total_buckets + 255) / 256;
+  emul_launch(tb, 256, k_plan, (const uint32_t*)offs.data(), B, total_buckets, S, aux0.data());
+  if (total_buckets <= 65536) {
+    emul_launch_mt(1, 1024, k_scan, (const uint32_t*)aux0.data(), total_buckets, aux1.data(), aux2.data());
+  } else {
+    const uint32_t tiles = (total_buckets + ZKP_SCAN_TILE - 1) / ZKP_SCAN_TILE;
+    std::vector<uint32_t> tt((size_t)tiles * 3 + 8);
+    emul_launch_mt(tiles, 1024, k_scan_tiles, (const uint32_t*)aux0.data(), total_buckets, aux1.data(), tt.data());
+    emul_launch_mt(1, 1024, k_scan, (const uint32_t*)tt.data(), tiles, tt.data() + tiles, tt.data() + 2 * tiles + 1);
+    emul_launch((total_buckets + 1023) / 1024, 1024, k_scan_add, aux1.data(), total_buckets, (const uint32_t*)(tt.data() + tiles));
+  }
+  emul_launch(tb, 256, k_items, (const uint32_t*)offs.data(), (const uint32_t*)aux1.data(), B, total_buckets, S, items.data(),
+              multi.data() + 4, multi.data());
+  const unsigned blocks = (unsigned)((max_items + 127) / 128);
+  const uint32_t* n_items = aux1.data() + total_buckets;
+  std::vector<uint32_t> lh(3 * (size_t)S + 8, 0), order(max_items);
+  const uint32_t* ord = nullptr;
+  if (balance && max_items >= 4096) {
+    const unsigned ib = (unsigned)((max_items + 255) / 256);
+    emul_launch(ib, 256, k_len_hist, (const work_item*)items.data(), n_items, S, lh.data());
+    emul_launch_mt(1, 1024, k_scan, (const uint32_t*)lh.data(), S + 1, lh.data() + S + 1, lh.data() + 2 * S + 3);
+    emul_launch(ib, 256, k_len_scatter, (const work_item*)items.data(), n_items, S, lh.data() + 2 * S + 3, order.data());
+    ord = order.data();
+  }
+  emul_launch(blocks, 128, k_accumulate, (const uint4*)niels.data(), (const uint32_t*)sorted.data(), (const work_item*)items.data(),
+              ord, n_items, n, buckets.data(), partials.data());
+  emul_launch_mt(2, 128, k_merge, (const uint32_t*)aux1.data(), (const uint32_t*)(multi.data() + 4), (const uint32_t*)multi.data(),
+                 (const uint4*)partials.data(), buckets.data());
+  const uint32_t chunks0 = B / ZKP_CHUNK_L;
+  std::vector<uint4> lvlT[2], lvlU, usum((size_t)8 * W * 8);
+  lvlT[0].resize((size_t)W * (chunks0 + 1) * 8);
+  lvlT[1].resize((size_t)W * (chunks0 / ZKP_CHUNK_L + 1) * 8);
+  lvlU.resize((size_t)W * (chunks0 + 1) * 8);
+  const uint4* cur = buckets.data();
+  uint32_t m = B;
+  int nl = 0;
+  while (m > ZKP_CHUNK_L) {
+    const uint32_t chunks = m / ZKP_CHUNK_L;
+    uint4* T = lvlT[nl & 1].data();
+    const unsigned threads = chunks * (unsigned)W;
+    emul_launch((threads + 127) / 128, 128, k_chunk_reduce, cur, m, W, T, lvlU.data());
+    emul_launch_mt((unsigned)W, 256, k_tree_sum, (const uint4*)lvlU.data(), chunks, usum.data() + (size_t)nl * W * 8);
+    cur = T;
+    m = chunks;
+    nl++;
+  }
+  emul_launch_mt(1, 64, k_finish, (const uint4*)usum.data(), nl, cur, m, W, c, n, (const int*)flags, &res, (uint4*)nullptr);
+  memcpy(res64, &res, sizeof res);
+}
 }

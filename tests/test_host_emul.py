@@ -353,8 +353,8 @@ def klib():
     deps = [src, os.path.join(HERE, "host_emul", "cuda_shim.h")] + [os.path.join(csrc, f) for f in os.listdir(csrc)
                                                                     if f.endswith((".cuh", ".hpp"))]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
-        subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-DZKP_HOST_EMUL",
-                               "-I/usr/local/cuda/include", src, "-o", out])
+        subprocess.check_call(["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-pthread",
+                               "-DZKP_HOST_EMUL", "-I/usr/local/cuda/include", src, "-o", out])
     return ctypes.CDLL(out)
 
 
@@ -549,3 +549,55 @@ def test_small_msm_kernels_on_the_host_against_the_golden_kats(klib):
     assert status[victim] == 3 and (np.delete(status, victim) == 0).all()
     assert klib.emul_msm_ct_batched(sc, bytes(bad_pt), off.ctypes.data, M, ctypes.cast(out2, ctypes.c_void_p)) == 1
     assert klib.emul_msm_ct_batched(bytes(bad_sc), pt, off.ctypes.data, M, ctypes.cast(out2, ctypes.c_void_p)) == 3
+
+
+def test_headline_msm_pipeline_kernel_by_kernel_on_the_host(klib):
+    """The variable-time MSM of the north-star path run kernel by kernel on the CPU (k_ingest2 histogram / scatter phases,
+    k_scan, k_plan, k_items, k_len_hist / k_len_scatter, k_accumulate, k_merge, k_chunk_reduce, k_tree_sum, k_finish -- the
+    cooperating ones with one OS thread per CUDA thread, tests/host_emul/cuda_shim.h) in the launch order of api.cu: the
+    encoding equals the C port's (oracle) for several window widths, work-item lengths that cut buckets into many
+    chunks, odd sizes, skewed scalars (one bucket takes everything), a cancelling instance (identity), and the first
+    undecodable point / non-canonical scalar is reported with its index."""
+    import struct
+    import numpy as np
+    from oracle import cref, scalar as S
+    from tests import util_data as U
+    klib.emul_msm_vartime.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint32, ctypes.c_int,
+                                      ctypes.c_int, ctypes.c_void_p]
+    base = U.base_points(64)
+
+    def run(sc, pts, c, S_forced=0, balance=1, host_window_scan=1):
+        # host_window_scan: the W-block scan is the slow part of the emulation (1024 OS threads per block); it runs as a
+        # kernel in ONE of the cases below and as a host prefix sum in the others
+        out = ctypes.create_string_buffer(64)
+        klib.emul_msm_vartime(bytes(sc), bytes(pts), len(sc) // 32, c, S_forced, balance, host_window_scan,
+                              ctypes.cast(out, ctypes.c_void_p))
+        status, ident, first_bad = struct.unpack_from("<iiq", out.raw, 32)
+        return out.raw[:32], status, ident, first_bad
+
+    n = 1500
+    sc = U.random_scalars(n, seed=5).tobytes()
+    pts = b"".join(base[(3 * i) % 64] for i in range(n))
+    want = cref.msm_vartime(np.frombuffer(sc, np.uint8).reshape(-1, 32), np.frombuffer(pts, np.uint8).reshape(-1, 32))
+    for c, s_forced, balance, hws in ((8, 0, 1, 1), (8, 12, 0, 1), (10, 0, 1, 0)):
+        enc, status, ident, first_bad = run(sc, pts, c, s_forced, balance, hws)
+        assert (enc, status, ident, first_bad) == (want, 0, 0, -1), (c, s_forced, balance)
+    # odd size, one term, empty
+    for m in (1, 333):
+        w2 = cref.msm_vartime(np.frombuffer(sc[:32 * m], np.uint8).reshape(-1, 32), np.frombuffer(pts[:32 * m], np.uint8).reshape(-1, 32))
+        assert run(sc[:32 * m], pts[:32 * m], 6, 64)[0] == w2, m
+    assert run(b"", b"", 8) == (bytes(32), 0, 1, -1)
+    # all scalars equal: one bucket per window takes every term (its work items are cut and merged)
+    same = (12345678901234567890123456789 % S.L).to_bytes(32, "little") * 600
+    w3 = cref.msm_vartime(np.frombuffer(same, np.uint8).reshape(-1, 32), np.frombuffer(pts[:32 * 600], np.uint8).reshape(-1, 32))
+    assert run(same, pts[:32 * 600], 6, 8)[0] == w3
+    # a cancelling instance: s * P + (l - s) * P for every pair -> the identity
+    half = U.random_scalars(200, seed=9)
+    neg = b"".join(((S.L - int.from_bytes(bytes(x), "little")) % S.L).to_bytes(32, "little") for x in half)
+    enc, status, ident, _ = run(half.tobytes() + neg, pts[:32 * 200] * 2, 6, 64)
+    assert (enc, status, ident) == (bytes(32), 0, 1)
+    # failures carry the index of the first offender
+    bad_pts = bytearray(pts); bad_pts[32 * 777:32 * 778] = b"\xff" * 32; bad_pts[32 * 1400:32 * 1401] = b"\xff" * 32
+    assert run(sc, bad_pts, 6, 64)[1:] == (1, 0, 777)
+    bad_sc = bytearray(sc); bad_sc[32 * 41:32 * 42] = b"\xff" * 32
+    assert run(bad_sc, pts, 6, 64)[1:] == (3, 0, 41)
