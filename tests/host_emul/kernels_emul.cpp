@@ -6,6 +6,7 @@
 #include <vector>
 #include "../../zkp_b200/csrc/pv_kernels.cuh"
 #include "../../zkp_b200/csrc/pv_plan.hpp"
+#include "../../zkp_b200/csrc/bv_plan.hpp"
 using namespace zkp;
 
 // step (3) of zkp_prove_batch: the N * k constant-time MSMs + compress; returns the not-uniform flag
@@ -273,5 +274,61 @@ void emul_msm_vartime(const uint8_t* scalars, const uint8_t* points, size_t n, i
   }
   emul_launch_mt(1, 64, k_finish, (const uint4*)usum.data(), nl, cur, m, W, c, n, (const int*)flags, &res, (uint4*)nullptr);
   memcpy(res64, &res, sizeof res);
+}
+
+// The front end of zkp_batch_verify_proofs (api.cu): transcripts, challenges, weights and coefficient fold of N proofs ->
+// the MSM inputs coeff_out / points_out [nc + (ni + k) N][32].  compiled = 1: k_bv_prepare2 (host-compiled script),
+// 0: k_bv_prepare (byte-wise STROBE); `chunk` proofs per launch (a multiple of 128, as in api.cu), then k_bv_static_sum.
+// Returns 0, or 1 / 3 for the first identity encoding / non-canonical response (flags as k_finish reports them).
+int emul_bv_front_end(int m, int ni, int nc, int k, const char* labels, const int32_t* lhs, const int32_t* cons_off,
+                      const int32_t* term_scalar, const int32_t* term_point, const uint32_t* prefix53, size_t N,
+                      const uint8_t* instance_enc, const uint8_t* common_enc, const uint8_t* commitments,
+                      const uint8_t* responses, const uint8_t* rho_seed, int compiled, size_t chunk, uint8_t* coeff_out,
+                      uint8_t* points_out, long long* first_bad) {
+  zkp_statement_desc sd;
+  sd.m = m; sd.ni = ni; sd.nc = nc; sd.k = k; sd.labels = labels; sd.lhs = lhs; sd.cons_off = cons_off;
+  sd.term_scalar = term_scalar; sd.term_point = term_point;
+  bv_plan bp;
+  bv_make_plan(&sd, prefix53, rho_seed, common_enc, &bp);
+  // device-side copies keep the 16-byte alignment the kernels' uint4 loads rely on
+  std::vector<uint4> blob4((bp.blob.size() + 15) / 16 + 1);
+  memcpy(blob4.data(), bp.blob.data(), bp.blob.size());
+  const uint8_t* dm = (const uint8_t*)blob4.data();
+  bv_desc d;
+  bv_fill_desc(&d, &sd, bp, dm);
+  const size_t rows = (size_t)ni + k, n = (size_t)nc + rows * N;
+  std::vector<uint4> dsc4(2 * n + 2), dpts4(2 * n + 2), com4(2 * N * k + 2), resp4(2 * N * m + 2);
+  uint8_t *dsc = (uint8_t*)dsc4.data(), *dpts = (uint8_t*)dpts4.data();
+  if (nc) memcpy(dpts, common_enc, (size_t)nc * 32);
+  if (ni) memcpy(dpts + (size_t)nc * 32, instance_enc, (size_t)ni * N * 32);
+  if (k) memcpy(com4.data(), commitments, N * (size_t)k * 32);
+  if (m) memcpy(resp4.data(), responses, N * (size_t)m * 32);
+  const size_t nchunks = N ? (N + chunk - 1) / chunk : 0;
+  const unsigned nblocks_total = (unsigned)(nchunks * ((chunk + 127) / 128) + 1);
+  std::vector<uint4> part4((size_t)nblocks_total * (nc ? nc : 1) * 2 + 2);
+  int flags[4];
+  emul_launch(1, 1, k_init_flags, flags);
+  unsigned block_base = 0;
+  for (size_t cidx = 0; cidx < nchunks; cidx++) {
+    const size_t j0 = cidx * chunk, cnt = j0 + chunk < N ? chunk : N - j0;
+    const unsigned nb = (unsigned)((cnt + 127) / 128);
+    if (compiled)
+      emul_launch_mt(nb, 128, k_bv_prepare2, d, (const uint32_t*)(dm + bp.o_prefix), N, (const uint8_t*)(dpts + (size_t)nc * 32),
+                     (const uint8_t*)com4.data(), (const uint8_t*)resp4.data(), dm + bp.o_seed, bp.script_blocks,
+                     (const unsigned long long*)(dm + bp.o_tm), (const uint32_t*)(dm + bp.o_ss), (const bv_seg*)(dm + bp.o_sg),
+                     dsc, dpts, (uint8_t*)part4.data(), (uint8_t*)nullptr, flags, j0, cnt, block_base);
+    else
+      emul_launch_mt(nb, 128, k_bv_prepare, d, (const uint32_t*)(dm + bp.o_prefix), N, (const uint8_t*)(dpts + (size_t)nc * 32),
+                     (const uint8_t*)dpts, (const uint8_t*)com4.data(), (const uint8_t*)resp4.data(), dm + bp.o_seed, dsc, dpts,
+                     (uint8_t*)part4.data(), (uint8_t*)nullptr, flags, j0, cnt, block_base);
+    block_base += nb;
+  }
+  if (nc) emul_launch_mt(1, 256, k_bv_static_sum, (const uint8_t*)part4.data(), (int)block_base, nc, dsc);
+  memcpy(coeff_out, dsc, n * 32);
+  memcpy(points_out, dpts, n * 32);
+  *first_bad = -1;
+  if (flags[0] != 0x7fffffff) { *first_bad = flags[0]; return 1; }
+  if (flags[1] != 0x7fffffff) { *first_bad = flags[1]; return 3; }
+  return 0;
 }
 }

@@ -601,3 +601,109 @@ def test_headline_msm_pipeline_kernel_by_kernel_on_the_host(klib):
     assert run(sc, bad_pts, 6, 64)[1:] == (1, 0, 777)
     bad_sc = bytearray(sc); bad_sc[32 * 41:32 * 42] = b"\xff" * 32
     assert run(bad_sc, pts, 6, 64)[1:] == (3, 0, 41)
+
+
+def test_batch_verification_front_end_kernels_on_the_host(klib):
+    """k_bv_prepare2 (host-compiled transcript script), k_bv_prepare (byte-wise STROBE) and k_bv_static_sum run on the CPU
+    with the plan of zkp_batch_verify_proofs (bv_plan.hpp): for real CMZ'13 proofs and for 130 DLEQ proofs (two launches,
+    the second block of the first only partly filled) the MSM inputs -- per-proof challenges, weights, folded
+    coefficients, block-reduced static coefficients, point rows -- are byte-equal to the oracle's BatchVerifier
+    (/root/reference/src/toolbox/batch_verifier.rs:137-228 restated); a tampered commitment changes them, an identity
+    commitment and a non-canonical response are reported with the proof's index."""
+    import numpy as np
+    from oracle import merlin as OM, msm as M, scalar as S, toolbox as OT
+
+    class OneShot:
+        def __init__(self, b): self.b = b
+        def bytes(self, n): return self.b
+
+    klib.emul_bv_front_end.argtypes = ([ctypes.c_int] * 4 + [ctypes.c_char_p] + [ctypes.c_void_p] * 5 + [ctypes.c_size_t]
+                                       + [ctypes.c_char_p] * 5 + [ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p,
+                                                                  ctypes.POINTER(ctypes.c_longlong)])
+
+    def front_end(ost, tlabel, encs, proofs, seed, compiled, chunk=128):
+        names = ost.instance + ost.common
+        m, ni, nc, k, N = len(ost.secrets), len(ost.instance), len(ost.common), len(ost.constraints), len(proofs)
+        lhs = np.array([names.index(l) for l, _ in ost.constraints], dtype=np.int32)
+        off = np.cumsum([0] + [len(r) for _, r in ost.constraints]).astype(np.int32)
+        ts = np.array([ost.secrets.index(s) for _, r in ost.constraints for s, _ in r], dtype=np.int32)
+        tp = np.array([names.index(q) for _, r in ost.constraints for _, q in r], dtype=np.int32)
+        t = OM.Transcript(tlabel)
+        OT.domain_sep(t, ost.label)
+        for s_ in ost.secrets:
+            OT.append_scalar_var(t, s_.encode())
+        st = t.strobe
+        state = bytes(st.state)
+        prefix = np.array([int.from_bytes(state[4 * i:4 * i + 4], "little") for i in range(50)]
+                          + [st.pos, st.pos_begin, st.cur_flags], dtype=np.uint32)
+        inst = b"".join(encs[n][j] for n in ost.instance for j in range(N))
+        comm = b"".join(encs[n] for n in ost.common)
+        com = b"".join(c for p in proofs for c in p.commitments)
+        resp = b"".join(r if isinstance(r, bytes) else S.to_bytes(r) for p in proofs for r in p.responses)
+        n = nc + (ni + k) * N
+        co, po = ctypes.create_string_buffer(n * 32), ctypes.create_string_buffer(n * 32)
+        bad = ctypes.c_longlong(-2)
+        rc = klib.emul_bv_front_end(m, ni, nc, k, b"".join(x.encode() + b"\0" for x in names), lhs.ctypes.data, off.ctypes.data,
+                                    ts.ctypes.data, tp.ctypes.data, prefix.ctypes.data, N, inst or b"\0", comm or b"\0", com or b"\0",
+                                    resp or b"\0", seed, compiled, chunk, ctypes.cast(co, ctypes.c_void_p),
+                                    ctypes.cast(po, ctypes.c_void_p), ctypes.byref(bad))
+        return rc, bad.value, [co.raw[32 * i:32 * i + 32] for i in range(n)], [po.raw[32 * i:32 * i + 32] for i in range(n)]
+
+    def oracle_inputs(ost, tlabel, encs, proofs, seed):
+        N = len(proofs)
+        bv = ost.build_batch_verifier(N, [OM.Transcript(tlabel) for _ in range(N)], encs)
+        oscal, opts = bv.batch_coeffs(proofs, OT.PerProofRng(seed))
+        return [S.to_bytes(s) for s in oscal], opts
+
+    seed = bytes(range(32))
+    rng = OT.SeededRng(b"emul-bv")
+    # ---- CMZ'13, 3 real proofs ----
+    ost = OT.CMZ10
+    common = {n: R.from_uniform_bytes(rng.bytes(64)) for n in ost.common}
+    proofs, encs = [], {n: [] for n in ost.instance}
+    for _ in range(3):
+        sec = {n: int.from_bytes(rng.bytes(64), "little") % S.L for n in ost.secrets}
+        Pp, Q = R.from_uniform_bytes(rng.bytes(64)), R.from_uniform_bytes(rng.bytes(64))
+        pts = dict(common)
+        pts["P"], pts["Q"] = Pp, Q
+        for i in range(1, 11):
+            pts["C_%d" % i] = M.naive_msm([sec["m_%d" % i], sec["z_%d" % i]], [Pp, pts["A"]])
+        pts["V"] = M.naive_msm([sec["m_%d" % i] for i in range(1, 11)] + [sec["minus_z_Q"]],
+                               [pts["X_%d" % i] for i in range(1, 11)] + [Q])
+        proof, enc = ost.prove_batchable(OM.Transcript(b"CMZ"), sec, pts, OneShot(rng.bytes(32)))
+        proofs.append(proof)
+        for n in ost.instance:
+            encs[n].append(enc[n])
+        for n in ost.common:
+            encs[n] = enc[n]
+    want_c, want_p = oracle_inputs(ost, b"CMZ", encs, proofs, seed)
+    for compiled in (1, 0):
+        rc, bad, co, po = front_end(ost, b"CMZ", encs, proofs, seed, compiled)
+        assert (rc, bad) == (0, -1) and po == want_p and co == want_c, compiled
+    tampered = [OT.BatchableProof(list(p.commitments), list(p.responses)) for p in proofs]
+    tampered[1].commitments[4] = encs["P"][0]
+    rc, bad, co2, _ = front_end(ost, b"CMZ", encs, tampered, seed, 1)
+    assert rc == 0 and co2 != want_c
+    tampered[1].commitments[4] = bytes(32)                      # identity encoding (toolbox/mod.rs:215)
+    assert front_end(ost, b"CMZ", encs, tampered, seed, 1)[:2] == (1, 1)
+    noncanon = [OT.BatchableProof(list(p.commitments), list(p.responses)) for p in proofs]
+    noncanon[2].responses[7] = b"\xff" * 32
+    assert front_end(ost, b"CMZ", encs, noncanon, seed, 1)[:2] == (3, 2)
+    # ---- DLEQ, 130 proofs: two launches of 128 and 2 proofs ----
+    ost = OT.DLEQ
+    G = R.BASEPOINT
+    H = R.hash_from_bytes_sha512(R.compress(G))
+    N = 130
+    proofs, encs = [], {n: [] for n in ost.instance}
+    for j in range(N):
+        x = 89327492234 + j
+        pts = {"A": R.pt_mul(x, G), "B": R.pt_mul(x, H), "H": H, "G": G}
+        proof, enc = ost.prove_batchable(OM.Transcript(b"DLEQBatchTest"), {"x": x}, pts, OneShot(rng.bytes(32)))
+        proofs.append(proof)
+        for n in ost.instance:
+            encs[n].append(enc[n])
+        encs["G"] = enc["G"]
+    want_c, want_p = oracle_inputs(ost, b"DLEQBatchTest", encs, proofs, seed)
+    for compiled in (1, 0):
+        rc, bad, co, po = front_end(ost, b"DLEQBatchTest", encs, proofs, seed, compiled)
+        assert (rc, bad) == (0, -1) and po == want_p and co == want_c, compiled

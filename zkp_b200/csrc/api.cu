@@ -18,6 +18,7 @@
 #include "bv_kernels.cuh"
 #include "pv_kernels.cuh"
 #include "pv_plan.hpp"
+#include "bv_plan.hpp"
 
 using namespace zkp;
 
@@ -953,105 +954,6 @@ static bool statement_ok(const zkp_statement_desc* sd) {
   return true;
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// Symbolic STROBE-128 over the per-proof transcript script of a batch (bv_kernels.cuh k_bv_prepare2): records the
-// constant bytes of every rate block and where the per-proof 32-byte values land.  Mirrors merlin 2.0 strobe.rs [ext]
-// exactly as csrc/hash.cuh and host/merlin.cpp do (begin_op framing, run_f padding, forced run_f of C-flagged ops).
-// ---------------------------------------------------------------------------------------------------------
-struct bv_script {
-  static const uint32_t R = 166;
-  uint32_t pos, pos_begin;
-  std::vector<uint8_t> cur;                 // 168 bytes of the block under construction
-  std::vector<uint64_t> tmpl;               // [nblocks][21]
-  std::vector<uint32_t> seg_start;          // [nblocks + 1]
-  std::vector<bv_seg> segs;
-  bv_script(uint32_t p, uint32_t pb) : pos(p), pos_begin(pb), cur(168, 0), seg_start(1, 0) {}
-  void run_f() {
-    cur[pos] ^= (uint8_t)pos_begin;
-    cur[pos + 1] ^= 0x04;
-    cur[R + 1] ^= 0x80;
-    for (int l = 0; l < 21; l++) {
-      uint64_t v = 0;
-      for (int b = 7; b >= 0; b--) v = (v << 8) | cur[8 * l + b];
-      tmpl.push_back(v);
-    }
-    seg_start.push_back((uint32_t)segs.size());
-    std::fill(cur.begin(), cur.end(), 0);
-    pos = 0;
-    pos_begin = 0;
-  }
-  void absorb(const uint8_t* d, size_t n) {
-    for (size_t i = 0; i < n; i++) {
-      cur[pos] ^= d[i];
-      if (++pos == R) run_f();
-    }
-  }
-  void absorb_value(uint32_t kind, uint32_t idx) {   // 32 per-proof bytes, split at block boundaries
-    uint32_t done = 0;
-    while (done < 32) {
-      const uint32_t room = R - pos, take = 32 - done < room ? 32 - done : room;
-      bv_seg sg;
-      memset(&sg, 0, sizeof sg);
-      sg.kind = kind; sg.idx = idx; sg.src_off = done; sg.len = take; sg.shift = (int32_t)pos - (int32_t)done;
-      segs.push_back(sg);
-      pos += take;
-      done += take;
-      if (pos == R) run_f();
-    }
-  }
-  void begin_op(uint32_t flags, bool more) {
-    if (more) return;
-    uint8_t hdr[2] = {(uint8_t)pos_begin, (uint8_t)flags};
-    pos_begin = pos + 1;
-    absorb(hdr, 2);
-    if ((flags & (ZKP_FLAG_C | ZKP_FLAG_K)) && pos != 0) run_f();
-  }
-  void meta_ad(const uint8_t* d, size_t n, bool more) { begin_op(ZKP_FLAG_M | ZKP_FLAG_A, more); absorb(d, n); }
-  void append_header(const char* label, const uint8_t* l2, size_t l2len) {   // append_message(label, <l2len bytes>) minus the data
-    uint8_t l4[4] = {(uint8_t)l2len, (uint8_t)(l2len >> 8), (uint8_t)(l2len >> 16), (uint8_t)(l2len >> 24)};
-    (void)l2;
-    meta_ad((const uint8_t*)label, strlen(label), false);
-    meta_ad(l4, 4, true);
-    begin_op(ZKP_FLAG_A, false);
-  }
-  void append_const(const char* label, const uint8_t* msg, size_t n) { append_header(label, msg, n); absorb(msg, n); }
-  void append_value(const char* label, uint32_t kind, uint32_t idx) { append_header(label, nullptr, 32); absorb_value(kind, idx); }
-  void challenge(const char* label, uint32_t n) {   // up to the forced run_f of prf; the squeeze reads the fresh state
-    uint8_t l4[4] = {(uint8_t)n, (uint8_t)(n >> 8), (uint8_t)(n >> 16), (uint8_t)(n >> 24)};
-    meta_ad((const uint8_t*)label, strlen(label), false);
-    meta_ad(l4, 4, true);
-    // the two header bytes leave pos != 0 (forced run_f) or end exactly on the block boundary (run_f inside absorb):
-    // either way the block is closed here and the squeeze starts at byte 0 of the permuted state
-    begin_op(ZKP_FLAG_I | ZKP_FLAG_A | ZKP_FLAG_C, false);
-  }
-};
-
-// the per-proof script of BatchVerifier (batch_verifier.rs:100-134, :152-167): instance points, static points, commitments,
-// challenge -- in the allocation order of the define_proof! expansion (macros.rs:348-365)
-static void bv_compile_batch_verify(bv_script& script, const zkp_statement_desc* sd, const uint8_t* common_enc) {
-  const int ni = sd->ni, nc = sd->nc, k = sd->k;
-  const char* q = sd->labels;
-  std::vector<std::string> names;
-  for (int i = 0; i < ni + nc; i++) {
-    names.push_back(std::string(q));
-    q += names.back().size() + 1;
-  }
-  for (int i = 0; i < ni; i++) {
-    script.append_const("ptvar", (const uint8_t*)names[i].data(), names[i].size());
-    script.append_value("val", 0u, (uint32_t)i);
-  }
-  for (int i = 0; i < nc; i++) {
-    script.append_const("ptvar", (const uint8_t*)names[ni + i].data(), names[ni + i].size());
-    script.append_const("val", common_enc + 32 * (size_t)i, 32);
-  }
-  for (int c = 0; c < k; c++) {
-    const std::string& nm = names[sd->lhs[c]];
-    script.append_const("blindcom", (const uint8_t*)nm.data(), nm.size());
-    script.append_value("val", 2u, (uint32_t)c);
-  }
-  script.challenge("chal", 64);
-}
-
 // Host execution of a compiled script for ONE proof (what a thread of k_bv_prepare2 does): the 64 challenge bytes.
 // Test hook: lets the CPU suite check the script compiler against the byte-wise Merlin of host/merlin.cpp.
 extern "C" int32_t zkp_selftest_bv_script(const zkp_statement_desc* sd, const uint32_t* prefix_state,
@@ -1120,64 +1022,12 @@ static int32_t batch_verify_proofs_impl(zkp_ctx* ctx, const zkp_statement_desc* 
   }
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
-  // ---- flatten the statement: label offsets, transcript script, constraint arrays ----
-  std::vector<uint32_t> loff, llen;
-  const char* lp = sd->labels;
-  std::vector<uint8_t> pool;
-  for (int i = 0; i < ni + nc; i++) {
-    size_t len = strlen(lp);
-    loff.push_back((uint32_t)pool.size());
-    llen.push_back((uint32_t)len);
-    pool.insert(pool.end(), lp, lp + len);
-    lp += len + 1;
-  }
-  const int n_terms = k ? sd->cons_off[k] : 0;
-  std::vector<bv_op> ops;
-  for (int i = 0; i < ni; i++) ops.push_back(bv_op{0u, loff[i], llen[i], (uint32_t)i});
-  for (int i = 0; i < nc; i++) ops.push_back(bv_op{1u, loff[ni + i], llen[ni + i], (uint32_t)i});
-  std::vector<int32_t> lhs_kind(k), lhs_idx(k), tkind(n_terms), tidx(n_terms);
-  for (int c = 0; c < k; c++) {
-    const int l = sd->lhs[c];
-    if (l < 0 || l >= ni + nc) return ZKP_ERR_SIZE;
-    lhs_kind[c] = l >= ni;
-    lhs_idx[c] = l >= ni ? l - ni : l;
-    ops.push_back(bv_op{2u, loff[l], llen[l], (uint32_t)c});
-  }
-  for (int q = 0; q < n_terms; q++) {
-    const int pnt = sd->term_point[q];
-    if (pnt < 0 || pnt >= ni + nc || sd->term_scalar[q] < 0 || sd->term_scalar[q] >= m) return ZKP_ERR_SIZE;
-    tkind[q] = pnt >= ni;
-    tidx[q] = pnt >= ni ? pnt - ni : pnt;
-  }
-  // the compiled transcript script (k_bv_prepare2): allocation order instance, static, then the commitments
-  bv_script script(prefix_state[50], prefix_state[51]);
-  bv_compile_batch_verify(script, sd, common_enc);
-  const int script_blocks = (int)(script.tmpl.size() / 21);
-  // one small device blob: prefix(53 w) | rho_seed(32 B) | pool | ops | int arrays | block templates | segments
-  auto pad16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
-  const size_t o_prefix = 0, o_seed = pad16(53 * 4), o_pool = o_seed + 32, o_ops = pad16(o_pool + pool.size()),
-               o_lk = pad16(o_ops + ops.size() * sizeof(bv_op)), o_li = pad16(o_lk + k * 4), o_co = pad16(o_li + k * 4),
-               o_ts = pad16(o_co + (k + 1) * 4), o_tk = pad16(o_ts + n_terms * 4), o_ti = pad16(o_tk + n_terms * 4),
-               o_tm = pad16(o_ti + n_terms * 4), o_ss = pad16(o_tm + script.tmpl.size() * 8),
-               o_sg = pad16(o_ss + script.seg_start.size() * 4), blob_sz = pad16(o_sg + script.segs.size() * sizeof(bv_seg)) + 16;
-  std::vector<uint8_t> blob(blob_sz, 0);
-  if (!script.tmpl.empty()) memcpy(&blob[o_tm], script.tmpl.data(), script.tmpl.size() * 8);
-  memcpy(&blob[o_ss], script.seg_start.data(), script.seg_start.size() * 4);
-  if (!script.segs.empty()) memcpy(&blob[o_sg], script.segs.data(), script.segs.size() * sizeof(bv_seg));
-  memcpy(&blob[o_prefix], prefix_state, 53 * 4);
-  memcpy(&blob[o_seed], rho_seed, 32);
-  if (!pool.empty()) memcpy(&blob[o_pool], pool.data(), pool.size());
-  if (!ops.empty()) memcpy(&blob[o_ops], ops.data(), ops.size() * sizeof(bv_op));
-  if (k) {
-    memcpy(&blob[o_lk], lhs_kind.data(), k * 4);
-    memcpy(&blob[o_li], lhs_idx.data(), k * 4);
-    memcpy(&blob[o_co], sd->cons_off, (k + 1) * 4);
-  }
-  if (n_terms) {
-    memcpy(&blob[o_ts], sd->term_scalar, n_terms * 4);
-    memcpy(&blob[o_tk], tkind.data(), n_terms * 4);
-    memcpy(&blob[o_ti], tidx.data(), n_terms * 4);
-  }
+  // ---- flatten the statement: label offsets, transcript script, constraint arrays -> one small device blob ----
+  bv_plan bp;
+  bv_make_plan(sd, prefix_state, rho_seed, common_enc, &bp);
+  const std::vector<uint8_t>& blob = bp.blob;
+  const size_t blob_sz = blob.size(), o_prefix = bp.o_prefix, o_seed = bp.o_seed, o_tm = bp.o_tm, o_ss = bp.o_ss, o_sg = bp.o_sg;
+  const int script_blocks = bp.script_blocks;
   const size_t rows = (size_t)ni + k, n = (size_t)nc + rows * N;
   if (n >= 0x7fffffffull) return ZKP_ERR_SIZE;
   const size_t chunk = ctx->bv_chunk_terms / (rows ? rows : 1) > 1024 ? (ctx->bv_chunk_terms * 4 / (rows ? rows : 1)) & ~(size_t)127
@@ -1215,15 +1065,7 @@ static int32_t batch_verify_proofs_impl(zkp_ctx* ctx, const zkp_statement_desc* 
   int32_t r = msm_prepare(ctx, n, &pl);   // sizes the MSM workspace, resets flags and the digit histogram
   if (r != ZKP_OK) return r;
   bv_desc d;
-  d.m = m; d.ni = ni; d.nc = nc; d.k = k; d.n_ops = (int)ops.size(); d.n_terms = n_terms;
-  d.ops = (const bv_op*)(dm + o_ops);
-  d.labels = dm + o_pool;
-  d.lhs_kind = (const int32_t*)(dm + o_lk);
-  d.lhs_idx = (const int32_t*)(dm + o_li);
-  d.cons_off = (const int32_t*)(dm + o_co);
-  d.term_scalar = (const int32_t*)(dm + o_ts);
-  d.term_pkind = (const int32_t*)(dm + o_tk);
-  d.term_pidx = (const int32_t*)(dm + o_ti);
+  bv_fill_desc(&d, sd, bp, dm);
   // the copy stream must not run ahead of earlier work on `st` that still uses the staging buffers
   CUDA_TRY(ctx, cudaEventRecord(ctx->chunk_ev[nchunks], st));
   CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[nchunks], 0));
