@@ -122,8 +122,8 @@ int emul_prove_batch(int m, int ni, int nc, int k, const char* labels, const int
 
 // zkp_msm_vartime_batched (api.cu): k_decompress_valid + k_prep_scalars_vt + k_small_msm_vt<false> over a CSR batch of
 // M small MSMs given as encodings; out [M][32], status [M] (0 ok, 1 undecodable point, 3 non-canonical scalar)
-void emul_msm_vartime_batched(const uint8_t* scalars, const uint8_t* points, const uint64_t* offsets, size_t M, uint8_t* out,
-                              int32_t* status) {
+void emul_msm_vartime_batched(const uint8_t* scalars, const uint8_t* points, const uint64_t* offsets, size_t M, int coop,
+                              uint8_t* out, int32_t* status) {
   const size_t total = (size_t)offsets[M];
   std::vector<uint4> sc(2 * total + 2), pt(2 * total + 2), niels(6 * total + 6), kk(2 * total + 2), k3(2 * total + 2), o(2 * M + 2);
   if (total) { memcpy(sc.data(), scalars, total * 32); memcpy(pt.data(), points, total * 32); }
@@ -135,16 +135,21 @@ void emul_msm_vartime_batched(const uint8_t* scalars, const uint8_t* points, con
     emul_launch((unsigned)((total + 255) / 256), 256, k_decompress_valid, (const uint4*)pt.data(), total, niels.data());
     emul_launch((unsigned)((total + 255) / 256), 256, k_prep_scalars_vt, (const uint4*)sc.data(), total, kk.data(), k3.data());
   }
-  emul_launch((unsigned)((M + 63) / 64), 64, k_small_msm_vt<false>, (const uint32_t*)kk.data(), (const uint32_t*)k3.data(),
-              (const uint4*)niels.data(), (const unsigned long long*)off.data(), (const uint32_t*)order.data(), M, o.data(),
-              st.data());
+  if (coop)   // four lanes per MSM (the latency schedule of small batches): the lanes exchange through shuffles
+    emul_launch_mt((unsigned)((4 * M + 63) / 64), 64, k_small_msm_vt<true>, (const uint32_t*)kk.data(), (const uint32_t*)k3.data(),
+                   (const uint4*)niels.data(), (const unsigned long long*)off.data(), (const uint32_t*)order.data(), M, o.data(),
+                   st.data());
+  else
+    emul_launch((unsigned)((M + 63) / 64), 64, k_small_msm_vt<false>, (const uint32_t*)kk.data(), (const uint32_t*)k3.data(),
+                (const uint4*)niels.data(), (const unsigned long long*)off.data(), (const uint32_t*)order.data(), M, o.data(),
+                st.data());
   memcpy(out, o.data(), M * 32);
   for (size_t j = 0; j < M; j++) status[j] = st[j];
 }
 
 // zkp_msm_ct_batched (api.cu) with compressed points: k_decompress_ext + k_build_tables<false> + k_small_msm_ct<false>;
 // returns 0, 1 (undecodable point) or 3 (non-canonical scalar) like the entry point
-int emul_msm_ct_batched(const uint8_t* scalars, const uint8_t* points, const uint64_t* offsets, size_t M, uint8_t* out) {
+int emul_msm_ct_batched(const uint8_t* scalars, const uint8_t* points, const uint64_t* offsets, size_t M, int coop, uint8_t* out) {
   const size_t total = (size_t)offsets[M];
   std::vector<uint4> sc(2 * total + 2), pt(2 * total + 2), ext(8 * total + 8), tables(64 * total + 64), biased(2 * total + 2),
       o(2 * M + 2);
@@ -158,9 +163,14 @@ int emul_msm_ct_batched(const uint8_t* scalars, const uint8_t* points, const uin
     emul_launch((unsigned)((total + 127) / 128), 128, k_build_tables<false>, (const uint4*)ext.data(), (const uint4*)sc.data(),
                 total, 1u, tables.data(), biased.data(), flags, (const int32_t*)nullptr);
   }
-  emul_launch((unsigned)((M + 63) / 64), 64, k_small_msm_ct<false, false>, (const uint32_t*)biased.data(),
-              (const uint4*)tables.data(), (const unsigned long long*)off.data(), (const uint32_t*)order.data(), M, 1u, o.data(),
-              (const int32_t*)nullptr, (const uint4*)nullptr);
+  if (coop)
+    emul_launch_mt((unsigned)((4 * M + 63) / 64), 64, k_small_msm_ct<false, true>, (const uint32_t*)biased.data(),
+                   (const uint4*)tables.data(), (const unsigned long long*)off.data(), (const uint32_t*)order.data(), M, 1u,
+                   o.data(), (const int32_t*)nullptr, (const uint4*)nullptr);
+  else
+    emul_launch((unsigned)((M + 63) / 64), 64, k_small_msm_ct<false, false>, (const uint32_t*)biased.data(),
+                (const uint4*)tables.data(), (const unsigned long long*)off.data(), (const uint32_t*)order.data(), M, 1u, o.data(),
+                (const int32_t*)nullptr, (const uint4*)nullptr);
   memcpy(out, o.data(), M * 32);
   if (flags[0] != 0x7fffffff) return 1;
   if (flags[1] != 0x7fffffff) return 3;

@@ -529,26 +529,37 @@ def test_small_msm_kernels_on_the_host_against_the_golden_kats(klib):
     M = len(kats)
     out = ctypes.create_string_buffer(M * 32)
     status = np.zeros(M, dtype=np.int32)
-    klib.emul_msm_vartime_batched.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p,
-                                              ctypes.c_void_p]
-    klib.emul_msm_ct_batched.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
-    klib.emul_msm_vartime_batched(sc, pt, off.ctypes.data, M, ctypes.cast(out, ctypes.c_void_p), status.ctypes.data)
+    klib.emul_msm_vartime_batched.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
+                                              ctypes.c_void_p, ctypes.c_void_p]
+    klib.emul_msm_ct_batched.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
+                                         ctypes.c_void_p]
+    _vt, _ct = klib.emul_msm_vartime_batched, klib.emul_msm_ct_batched
+    klib_vt = lambda s_, p_, o_, m_, out_, st_: _vt(s_, p_, o_, m_, 0, out_, st_)
+    klib_ct = lambda s_, p_, o_, m_, out_: _ct(s_, p_, o_, m_, 0, out_)
+    klib_vt(sc, pt, off.ctypes.data, M, ctypes.cast(out, ctypes.c_void_p), status.ctypes.data)
     assert (status == 0).all()
     assert [out.raw[32 * j:32 * j + 32].hex() for j in range(M)] == [k_["expected"] for k_ in kats]
     out2 = ctypes.create_string_buffer(M * 32)
-    assert klib.emul_msm_ct_batched(sc, pt, off.ctypes.data, M, ctypes.cast(out2, ctypes.c_void_p)) == 0
+    assert klib_ct(sc, pt, off.ctypes.data, M, ctypes.cast(out2, ctypes.c_void_p)) == 0
     assert out2.raw == out.raw
+    # the four-lanes-per-MSM schedules (ge_double_coop4 / ge_madd_coop4 / ge_add_pniels_coop4: shuffles between the lanes
+    # of a group, several groups with different term counts per warp) on the first MSMs of the batch
+    Mc = min(M, 9)
+    oc, stc = ctypes.create_string_buffer(Mc * 32), np.zeros(Mc, dtype=np.int32)
+    _vt(sc, pt, off.ctypes.data, Mc, 1, ctypes.cast(oc, ctypes.c_void_p), stc.ctypes.data)
+    assert (stc == 0).all() and oc.raw == out.raw[:32 * Mc]
+    assert _ct(sc, pt, off.ctypes.data, Mc, 1, ctypes.cast(oc, ctypes.c_void_p)) == 0 and oc.raw == out.raw[:32 * Mc]
     # failures are local to their MSM (vartime) / reported with the entry point's codes (constant time)
     victim = next(j for j, k_ in enumerate(kats) if k_["n"] >= 2)
     t0 = int(off[victim])
     bad_pt = bytearray(pt); bad_pt[32 * t0:32 * t0 + 32] = b"\xff" * 32
     bad_sc = bytearray(sc); bad_sc[32 * (t0 + 1):32 * (t0 + 1) + 32] = b"\xff" * 32
-    klib.emul_msm_vartime_batched(sc, bytes(bad_pt), off.ctypes.data, M, ctypes.cast(out2, ctypes.c_void_p), status.ctypes.data)
+    klib_vt(sc, bytes(bad_pt), off.ctypes.data, M, ctypes.cast(out2, ctypes.c_void_p), status.ctypes.data)
     assert status[victim] == 1 and (np.delete(status, victim) == 0).all() and out2.raw[32 * victim:32 * victim + 32] == bytes(32)
-    klib.emul_msm_vartime_batched(bytes(bad_sc), pt, off.ctypes.data, M, ctypes.cast(out2, ctypes.c_void_p), status.ctypes.data)
+    klib_vt(bytes(bad_sc), pt, off.ctypes.data, M, ctypes.cast(out2, ctypes.c_void_p), status.ctypes.data)
     assert status[victim] == 3 and (np.delete(status, victim) == 0).all()
-    assert klib.emul_msm_ct_batched(sc, bytes(bad_pt), off.ctypes.data, M, ctypes.cast(out2, ctypes.c_void_p)) == 1
-    assert klib.emul_msm_ct_batched(bytes(bad_sc), pt, off.ctypes.data, M, ctypes.cast(out2, ctypes.c_void_p)) == 3
+    assert klib_ct(sc, bytes(bad_pt), off.ctypes.data, M, ctypes.cast(out2, ctypes.c_void_p)) == 1
+    assert klib_ct(bytes(bad_sc), pt, off.ctypes.data, M, ctypes.cast(out2, ctypes.c_void_p)) == 3
 
 
 def test_headline_msm_pipeline_kernel_by_kernel_on_the_host(klib):
