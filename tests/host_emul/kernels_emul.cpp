@@ -24,7 +24,7 @@ static int run_msms(const pv_desc& d, const pv_plan& plan, int nc, size_t N, con
   std::vector<uint4> biased(2 * total + 2);
   if (comb) {
     const size_t U = plan.comb_slot_point.size(), Us = plan.comb_shared_point.size();
-    std::vector<uint4> combs(Npad * U * 64 + 64), shared(Us * 64 + 64);
+    std::vector<uint4> combs(Npad * U * 64 + 64), shared(Us * 48 + 16);   // the sizes of api.cu: 1 KB / 768 B per comb
     if (U)
       emul_launch((unsigned)((N * U + 63) / 64), 64, k_build_combs<true>, (const unsigned long long*)limbs, N * U, (uint32_t)U,
                   (uint32_t)p, plan.comb_slot_point.data(), combs.data());

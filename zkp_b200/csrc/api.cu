@@ -1305,7 +1305,7 @@ static int32_t prove_batch_impl(zkp_ctx* ctx, const zkp_statement_desc* sd, cons
     uint4* shared_tables = nullptr;
     if (comb) {
       // one comb per base, sign-bit recoding of every blinding, then 64 columns per constraint MSM
-      ENSURE(ctx, ctx->pv_static, Us * 1024 + 256);
+      ENSURE(ctx, ctx->pv_static, Us * 768 + 256);   // eight affine Niels entries of 96 bytes per shared comb
       if (U) {
         k_build_combs<true><<<(unsigned)((N * U + 63) / 64), 64, 0, st>>>((const unsigned long long*)ctx->pv_limbs.p, N * U,
                                                                         (uint32_t)U, (uint32_t)p,

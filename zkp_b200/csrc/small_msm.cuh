@@ -293,8 +293,9 @@ __global__ void __launch_bounds__(64) k_small_msm_ct(const uint32_t* __restrict_
 // ---- comb path of batch proving (comb.cuh; SURVEY 8f row f4, second half) ------------------------------------------
 // Every base a statement's constraints use gets ONE signed four-tooth comb -- per proof for instance points, per batch
 // for the batch-static points -- and every constraint MSM then runs 64 doublings instead of 256.
-// Layouts (uint4 units, entry e = 0..7 of 8 uint4): per-proof combs interleaved like the Straus tables,
-// combs[ct_table_index<true>(j * U + u, U) + (8 e + q) * 32] for slot u of proof j; shared combs[u * 64 + 8 e + q].
+// Layouts (uint4 units): per-proof combs, projective Niels entries e = 0..7 of 8 uint4, interleaved like the Straus tables,
+// combs[ct_table_index<true>(j * U + u, U) + (8 e + q) * 32] for slot u of proof j; shared combs, affine Niels entries of
+// 6 uint4 (normalised once per batch: mixed additions, shorter scans), combs[u * 48 + 6 e + q].
 
 // one thread per (proof j, slot u), i = j * U + u: the comb of the proof's copy of point slot_point[u]
 // (IL = false: the shared combs, built from proof 0's copy: n = U threads)
@@ -310,14 +311,25 @@ __global__ void __launch_bounds__(64) k_build_combs(const unsigned long long* __
   load_ext_limbs51(P, limbs + (j * points_per_proof + (size_t)slot_point[u]) * 20);
   ge_pniels E[8];
   comb_build(E, P);
-  const size_t stride = IL ? 32 : 1;
-  uint4* tab = combs + (IL ? ct_table_index<true>(i, U) : i * 64);
+  if (IL) {
+    uint4* tab = combs + ct_table_index<true>(i, U);
 #pragma unroll 1
-  for (int e = 0; e < 8; e++) {
-    const uint32_t* w = (const uint32_t*)&E[e];
+    for (int e = 0; e < 8; e++) {
+      const uint32_t* w = (const uint32_t*)&E[e];
 #pragma unroll
-    for (int q = 0; q < 8; q++)
-      tab[(size_t)(8 * e + q) * stride] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+      for (int q = 0; q < 8; q++)
+        tab[(size_t)(8 * e + q) * 32] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+    }
+  } else {
+    uint4* tab = combs + i * 48;
+#pragma unroll 1
+    for (int e = 0; e < 8; e++) {
+      ge_aniels a;
+      comb_entry_to_affine(a, E[e]);
+      const uint32_t* w = (const uint32_t*)&a;
+#pragma unroll
+      for (int q = 0; q < 6; q++) tab[6 * e + q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+    }
   }
 }
 
@@ -354,24 +366,26 @@ __global__ void __launch_bounds__(64) k_small_msm_comb(const uint32_t* __restric
 #pragma unroll 1
     for (size_t t = lo; t < hi; t++) {
       const int32_t slot = term_slot[r0 + (uint32_t)(t - lo)];
-      const uint4* tab;
-      size_t stride;
-      if (slot >= 0) {   // public: depends on the statement only
-        tab = combs + (((proof >> 5) * U + (uint32_t)slot) * 64 * 32 + (proof & 31));   // = ct_table_index<true>(proof * U + slot, U)
-        stride = 32;
-      } else {
-        tab = shared_combs + (size_t)(-slot - 1) * 64;
-        stride = 1;
-      }
       const uint32_t* mw = recoded + 8 * t + (col >> 5);
       uint32_t idx, neg;
       comb_column_words(idx, neg, __ldg(mw), __ldg(mw + 2), __ldg(mw + 4), __ldg(mw + 6), col & 31);
-      ge_pniels sel;
-      comb_select(sel, [&](uint32_t e, int q, uint32_t& x, uint32_t& y, uint32_t& z, uint32_t& ww) {
-        const uint4 v = __ldg(tab + (size_t)(8 * e + q) * stride);
-        x = v.x; y = v.y; z = v.z; ww = v.w;
-      }, idx, neg);
-      ge_add_pniels(acc, acc, sel);
+      if (slot >= 0) {   // public: depends on the statement only (and is the same for every lane of the warp)
+        const uint4* tab = combs + (((proof >> 5) * U + (uint32_t)slot) * 64 * 32 + (proof & 31));   // ct_table_index<true>(proof * U + slot, U)
+        ge_pniels sel;
+        comb_select(sel, [&](uint32_t e, int q, uint32_t& x, uint32_t& y, uint32_t& z, uint32_t& ww) {
+          const uint4 v = __ldg(tab + (size_t)(8 * e + q) * 32);
+          x = v.x; y = v.y; z = v.z; ww = v.w;
+        }, idx, neg);
+        ge_add_pniels(acc, acc, sel);
+      } else {
+        const uint4* tab = shared_combs + (size_t)(-slot - 1) * 48;
+        ge_aniels sel;
+        comb_select_affine(sel, [&](uint32_t e, int q, uint32_t& x, uint32_t& y, uint32_t& z, uint32_t& ww) {
+          const uint4 v = __ldg(tab + 6 * e + q);
+          x = v.x; y = v.y; z = v.z; ww = v.w;
+        }, idx, neg);
+        ge_madd(acc, acc, sel);
+      }
     }
   }
   uint32_t enc[8];
