@@ -64,6 +64,12 @@ static inline int atomicExch(int* a, int v) { return __atomic_exchange_n(a, v, _
 static inline int atomicOr(int* a, int v) { return __atomic_fetch_or(a, v, __ATOMIC_RELAXED); }
 static inline unsigned atomicOr(unsigned* a, unsigned v) { return __atomic_fetch_or(a, v, __ATOMIC_RELAXED); }
 
+static inline int __double2loint(double d) { unsigned long long b; memcpy(&b, &d, 8); return (int)(unsigned)b; }
+static inline int __double2hiint(double d) { unsigned long long b; memcpy(&b, &d, 8); return (int)(unsigned)(b >> 32); }
+static inline double __hiloint2double(int hi, int lo) {
+  unsigned long long b = ((unsigned long long)(unsigned)hi << 32) | (unsigned)lo;
+  double d; memcpy(&d, &b, 8); return d;
+}
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
 static inline int __ffs(int x) { return __builtin_ffs(x); }
