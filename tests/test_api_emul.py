@@ -37,7 +37,9 @@ def api():
     deps += [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cu", ".cuh", ".hpp"))]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         subprocess.check_call(["python", os.path.join(EMUL, "make_api_emul.py")])
-        subprocess.check_call(["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-pthread", "-DZKP_HOST_EMUL",
+        # -Bsymbolic: the library's cuda* calls must reach ITS runtime stand-in even when a real libcudart is in the process
+        subprocess.check_call(["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-pthread", "-Wl,-Bsymbolic",
+                               "-DZKP_HOST_EMUL",
                                "-I/usr/local/cuda/include", "-I" + csrc, "-I" + EMUL,
                                os.path.join(EMUL, "api_emul_generated.cpp"), os.path.join(EMUL, "cudart_shim.cpp"),
                                os.path.join(csrc, "host", "merlin.cpp"), "-o", out])
