@@ -68,3 +68,25 @@ def tiled_expected(scalars_arr, base_encs):
         sums[k] = tot % R.L
     pts = [R.decompress(e) for e in base_encs]
     return R.compress(M.naive_msm(sums, pts))
+
+
+def can_spawn_threads(n=1100):
+    """The host emulation of cooperating kernels runs one OS thread per CUDA thread (1024 per block): check that this
+    environment lets a process have that many before a test relies on it."""
+    import threading
+    ev, started, ths = threading.Event(), [], []
+    def body():
+        started.append(1)
+        ev.wait()
+    try:
+        for _ in range(n):
+            t = threading.Thread(target=body)
+            t.start()
+            ths.append(t)
+        ok = True
+    except RuntimeError:
+        ok = False
+    ev.set()
+    for t in ths:
+        t.join()
+    return ok
