@@ -593,7 +593,10 @@ def test_headline_msm_pipeline_kernel_by_kernel_on_the_host(klib):
     sc = U.random_scalars(n, seed=5).tobytes()
     pts = b"".join(base[(3 * i) % 64] for i in range(n))
     want = cref.msm_vartime(np.frombuffer(sc, np.uint8).reshape(-1, 32), np.frombuffer(pts, np.uint8).reshape(-1, 32))
-    for c, s_forced, balance, hws in ((8, 0, 1, 1), (8, 12, 0, 1), (10, 0, 1, 0)):
+    cases = [(8, 0, 1, 1), (8, 12, 0, 1)]
+    if os.environ.get("ZKP_SLOW_TESTS") == "1":     # the W-block scan as a kernel: also covered by tests/test_api_emul.py
+        cases.append((10, 0, 1, 0))
+    for c, s_forced, balance, hws in cases:
         enc, status, ident, first_bad = run(sc, pts, c, s_forced, balance, hws)
         assert (enc, status, ident, first_bad) == (want, 0, 0, -1), (c, s_forced, balance)
     # odd size, one term, empty
