@@ -10,7 +10,11 @@ cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
 cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 cudaError_t cudaGetLastError(void) { return cudaSuccess; }
 const char* cudaGetErrorString(cudaError_t) { return "host emulation"; }
-cudaError_t cudaDeviceGetAttribute(int* v, enum cudaDeviceAttr, int) { *v = 2; return cudaSuccess; }
+cudaError_t cudaDeviceGetAttribute(int* v, enum cudaDeviceAttr a, int) {
+  *v = a == cudaDevAttrMaxSharedMemoryPerBlockOptin ? 232448 : 2;   // 2 SMs; the opt-in shared memory of an sm_100 block
+  return cudaSuccess;
+}
+cudaError_t cudaFuncSetAttribute(const void*, enum cudaFuncAttribute, int) { return cudaSuccess; }
 cudaError_t cudaDeviceGetStreamPriorityRange(int* lo, int* hi) { *lo = 0; *hi = 0; return cudaSuccess; }
 
 static int g_handles;   // streams and events are distinct non-null tokens

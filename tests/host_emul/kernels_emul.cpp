@@ -31,10 +31,22 @@ static int run_msms(const pv_desc& d, const pv_plan& plan, int nc, size_t N, con
     if (Us)
       emul_launch((unsigned)((Us + 63) / 64), 64, k_build_combs<false>, (const unsigned long long*)limbs, Us, (uint32_t)Us,
                   (uint32_t)p, plan.comb_shared_point.data(), shared.data());
+    if (comb >= 2) {   // CTA-staged: group-interleaved recoding, one block per 32 proofs, units from pv_make_units
+      std::vector<uint32_t> rec(Npad * (size_t)T * 8 + 8);
+      emul_launch((unsigned)((total + 255) / 256), 256, k_comb_recode_il, (const uint4*)scalars_flat.data(), N, (uint32_t)T,
+                  rec.data());
+      const unsigned n_units = (unsigned)plan.unit_term0.size(), nw = n_units < 16 ? n_units : 16;
+      if (comb_cta_smem_bytes(U, Us, n_units) > sizeof(emul_dynamic_smem)) return -1;
+      emul_launch_mt((unsigned)((N + 31) / 32), 32 * nw, k_comb_msm_cta, (const uint32_t*)rec.data(),
+                     (const uint4*)combs.data(), (const uint4*)shared.data(), plan.term_slot.data(), plan.unit_term0.data(),
+                     plan.unit_nterms.data(), plan.cons_unit0.data(), N, (uint32_t)T, (uint32_t)U, (uint32_t)Us, n_units,
+                     (uint32_t)k, out.data());
+    } else {
     emul_launch((unsigned)((total + 255) / 256), 256, k_comb_recode, (const uint4*)scalars_flat.data(), total, biased.data());
     emul_launch((unsigned)((M + 63) / 64), 64, k_small_msm_comb, (const uint32_t*)biased.data(), (const uint4*)combs.data(),
                 (const uint4*)shared.data(), plan.term_slot.data(), (const unsigned long long*)offsets.data(),
                 (const uint32_t*)order.data(), M, (uint32_t)T, (uint32_t)U, out.data());
+    }
   } else {
     std::vector<uint4> tables(Npad * (size_t)T * 64 + 64), s_ext(8 * (size_t)nc + 8), s_tab(64 * (size_t)nc + 64),
         s_zero(2 * (size_t)nc + 2, make_uint4(0, 0, 0, 0)), s_bias(2 * (size_t)nc + 2);
@@ -64,7 +76,9 @@ static void fill_desc(pv_desc* d, const pv_plan& plan, int m, int ni, int nc, in
   d->cons_slot = plan.cons_slot.data();
 }
 
+static int g_emul_piece = 2;   // terms per unit of the CTA-staged comb kernel (api.cu: option prove_piece)
 extern "C" {
+void emul_set_piece(int piece) { g_emul_piece = piece; }
 // limbs [N][p][20] (FieldElement51 X,Y,Z,T), blind [N][m][32] canonical -> com [N][k][32]; returns the not-uniform flag
 // (1 if a common point differed between proofs while share was requested: the caller reruns without sharing, as api.cu does)
 int emul_prove_msms(int m, int ni, int nc, int k, const int32_t* lhs, const int32_t* cons_off, const int32_t* term_scalar,
@@ -72,6 +86,7 @@ int emul_prove_msms(int m, int ni, int nc, int k, const int32_t* lhs, const int3
                     uint8_t* com) {
   pv_plan plan;
   pv_make_plan(ni, ni + nc, k, cons_off, term_point, share != 0, comb != 0, &plan);
+  if (comb) pv_make_units(k, cons_off, g_emul_piece, &plan);
   pv_desc d;
   fill_desc(&d, plan, m, ni, nc, k, lhs, cons_off, term_scalar, term_point);
   return run_msms(d, plan, nc, N, limbs, blind, share, comb, com);
@@ -87,6 +102,7 @@ int emul_prove_batch(int m, int ni, int nc, int k, const char* labels, const int
   const int p = ni + nc;
   pv_plan plan;
   pv_make_plan(ni, p, k, cons_off, term_point, share != 0, comb != 0, &plan);
+  if (comb) pv_make_units(k, cons_off, g_emul_piece, &plan);
   pv_desc d;
   fill_desc(&d, plan, m, ni, nc, k, lhs, cons_off, term_scalar, term_point);
   std::vector<uint32_t> loff, llen;

@@ -151,6 +151,60 @@ def test_msm_bench_scale_properties(engine):
     assert not ident1
 
 
+_HEADLINE = {}
+
+
+def _headline_case(n, K=256):
+    """n terms with the scalar mix of the bench (bench.make_cmz_batch: 13 of 24 rows full-size, 11 of 24 rows l - rho with
+    128-bit rho, i.e. what batch_verifier.rs:183 produces and the engine's sign fold turns back into 128-bit digits) over
+    K tiled base points, and the exact expected encoding from the K-term reduction."""
+    if n not in _HEADLINE:
+        import bench
+        rng = np.random.default_rng(20260 + n % 1000)
+        sc = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+        sc[:, 31] &= 0x0F                                         # < 2^252 < l
+        small = (np.arange(n) % 24) >= 13                        # the commitment rows of a CMZ batch
+        rho = sc[small].copy()
+        rho[:, 16:] = 0
+        sc[small] = bench._sub_from_l(rho.view(np.uint64).reshape(-1, 4)).view(np.uint8).reshape(-1, 32)
+        base = U.base_points(K)
+        reps = -(-n // K)
+        pts = np.frombuffer(b"".join(base) * reps, dtype=np.uint8).reshape(-1, 32)[:n]
+        _HEADLINE[n] = (sc, pts, U.tiled_expected(sc, base))
+    return _HEADLINE[n]
+
+
+@pytest.mark.parametrize("window", [17, 18, 19, 20, 22, 24])
+def test_msm_headline_windows_bit_exact(engine, window):
+    """The windows the bench runs at (c = 19 by the automatic choice at 5 * 10^7 terms; 17 / 18 at smaller sizes; 20..24 by
+    option) checked bit for bit at n = 2^22 + 12 terms against the tiling oracle: B up to 2^23 buckets per window, the
+    multi-block item scan with > 256 tiles, bucket-reduction depth 4, the sign-folded 128-bit coefficient mix of a CMZ
+    batch (/root/reference/src/toolbox/batch_verifier.rs:173-230)."""
+    sc, pts, exp = _headline_case((1 << 22) + 12)
+    engine.set_option("window", window)
+    try:
+        enc, ident, _ = engine.msm_vartime(sc, pts)
+        assert engine.stage_ms()["window"] == window
+    finally:
+        engine.set_option("window", 0)
+    assert enc == exp and not ident, window
+
+
+def test_msm_2_pow_24_terms_at_the_automatic_window(engine):
+    """One 2^24-term MSM (a third of the bench's per-GPU MSM) at the window the engine picks itself, bit for bit against
+    the tiling oracle; and through the batch entry point with 12 static terms in front (the bench's e2e call)."""
+    n = 1 << 24
+    sc, pts, exp = _headline_case(n)
+    enc, ident, _ = engine.msm_vartime(sc, pts)
+    assert engine.stage_ms()["window"] >= 17
+    assert enc == exp and not ident
+    # zkp_batch_verify: same terms as 12 static + 24 rows x batch (the result is not the identity: reject, status ok)
+    batch = (n - 12) // 24
+    m = 12 + 24 * batch
+    ok, rc = engine.batch_verify(sc[:12], pts[:12], sc[12:m], pts[12:m], 24, batch)
+    assert not ok and rc == 0
+
+
 def test_small_batched_vartime(engine):
     kats = [k for k in U.golden("msm_kat.json")["kats"] if k["n"] <= 36]
     scal = np.concatenate([_h(k["scalars"]) for k in kats])

@@ -326,9 +326,6 @@ def test_prove_many_device_front_end_matches_host_and_oracle(engine):
     assert all((x == y).all() for x, y in zip(a, b))
 
 
-@pytest.mark.skipif(os.environ.get("ZKP_TEST_PROVE_COMB") != "1",
-                    reason="the comb path of the batch prover (option prove_comb, off by default) has been checked in host "
-                           "emulation only; set ZKP_TEST_PROVE_COMB=1 to run its device parity test")
 def test_prove_many_device_comb_path_matches_straus_path(engine):
     """Option prove_comb (signed four-tooth combs, comb.cuh) gives the bytes of the default Straus path of
     zkp_prove_batch: CMZ with 70 proofs (three interleave groups, the last one partial), shared and per-proof combs for

@@ -414,15 +414,17 @@ def test_batch_prover_msm_kernels_run_on_the_host(klib):
                 acc = R.pt_add(acc, R.pt_mul(blind[j][s], pts[j][q]))
             expected += R.compress(acc)
     for share in (1, 0):
-        for comb in (0, 1):
+        for comb, piece in ((0, 2), (1, 2), (2, 2), (2, 1), (2, 3)):   # 2 = CTA-staged comb kernel, units of <= piece terms
+            klib.emul_set_piece(piece)
             flag, com = run(pts, share, comb, same_representative=bool(share))
-            assert flag == 0, (share, comb)
+            assert flag == 0, (share, comb, piece)
             bad = [i for i in range(N * k) if com[32 * i:32 * i + 32] != expected[32 * i:32 * i + 32]]
-            assert not bad, (share, comb, bad[:8])
+            assert not bad, (share, comb, piece, bad[:8])
+    klib.emul_set_piece(2)
     # a "common" point that differs in one proof: the kernels say so (api.cu then redoes the call without sharing)
     odd = [list(row) for row in pts]
     odd[17][ni + 1] = R.from_uniform_bytes(rnd.randbytes(64))
-    for comb in (0, 1):
+    for comb in (0, 1, 2):
         flag, _ = run(odd, 1, comb, same_representative=True)
         assert flag != 0
 

@@ -71,6 +71,9 @@ struct zkp_ctx {
   // batch proving: signed four-tooth combs, one per base (comb.cuh): 64 doublings per constraint MSM instead of 256.
   // Logic checked on the host against the oracle (tests/test_host_emul.py); not yet run on a GPU, hence off.
   int prove_comb = 0;
+  int prove_piece = 2;        // CTA-staged comb kernel (prove_comb = 2): terms per unit (pv_make_units)
+  int smem_optin = -1;        // cudaDevAttrMaxSharedMemoryPerBlockOptin, read once
+  size_t cta_smem_set = 0;    // dynamic shared memory k_comb_msm_cta has been allowed so far
   int bv_compiled = 1;      // batch-verification front end: host-compiled transcript script (k_bv_prepare2)
   int ingest_variant = 2;   // occupancy point of k_ingest2 (kernels.cuh ZKP_INGEST_*)
   int fused_sort = 1;  // histogram and scatter ride under the two halves of the decompression (k_ingest2)
@@ -226,7 +229,11 @@ extern "C" int32_t zkp_ctx_set_option(zkp_ctx* ctx, const char* key, int64_t val
   } else if (!strcmp(key, "share_static_tables")) {
     ctx->share_static_tables = value ? 1 : 0;
   } else if (!strcmp(key, "prove_comb")) {
-    ctx->prove_comb = value ? 1 : 0;
+    if (value < 0 || value > 2) return ZKP_ERR_SIZE;
+    ctx->prove_comb = (int)value;
+  } else if (!strcmp(key, "prove_piece")) {
+    if (value < 1 || value > 64) return ZKP_ERR_SIZE;
+    ctx->prove_piece = (int)value;
   } else if (!strcmp(key, "bv_compiled")) {
     ctx->bv_compiled = value ? 1 : 0;
   } else if (!strcmp(key, "ingest_variant")) {
@@ -1213,7 +1220,8 @@ static int32_t prove_batch_impl(zkp_ctx* ctx, const zkp_statement_desc* sd, cons
                o_tp = pad16(o_ts + (size_t)n_terms * 4), o_sl = pad16(o_tp + (size_t)n_terms * 4),
                o_sh = pad16(o_sl + (size_t)k * 4), o_cs = pad16(o_sh + (size_t)n_terms * 4),
                o_cp = pad16(o_cs + (size_t)n_terms * 4), o_cq = pad16(o_cp + (size_t)p * 4),
-               blob_sz = pad16(o_cq + (size_t)p * 4) + 16;
+               o_ut = pad16(o_cq + (size_t)p * 4), o_un = pad16(o_ut + ((size_t)n_terms + k) * 4),
+               o_cu = pad16(o_un + ((size_t)n_terms + k) * 4), blob_sz = pad16(o_cu + (size_t)(k + 1) * 4) + 16;
   // batch-static bases: the statement's common points are the same for every proof when the caller says so
   // (points_are_uniform): their constant-time tables are built once and shared
   // (the caller passes a copy per proof, as the reference's per-proof assignments do: k_pv_gather compares every copy
@@ -1224,6 +1232,7 @@ static int32_t prove_batch_impl(zkp_ctx* ctx, const zkp_statement_desc* sd, cons
   const bool comb = ctx->prove_comb && n_terms > 0;
   pv_plan plan;
   pv_make_plan(ni, p, k, sd->cons_off, sd->term_point, share, comb, &plan);
+  if (comb) pv_make_units(k, sd->cons_off, ctx->prove_piece, &plan);   // at most n_terms + k units
   const std::vector<int32_t>&slot = plan.cons_slot, &term_shared = plan.term_shared, &term_slot = plan.term_slot,
                             &comb_slot_point = plan.comb_slot_point, &comb_shared_point = plan.comb_shared_point;
   const size_t U = comb_slot_point.size(), Us = comb_shared_point.size();
@@ -1233,6 +1242,9 @@ static int32_t prove_batch_impl(zkp_ctx* ctx, const zkp_statement_desc* sd, cons
     memcpy(&blob[o_cs], term_slot.data(), (size_t)n_terms * 4);
     if (U) memcpy(&blob[o_cp], comb_slot_point.data(), U * 4);
     if (Us) memcpy(&blob[o_cq], comb_shared_point.data(), Us * 4);
+    memcpy(&blob[o_ut], plan.unit_term0.data(), plan.unit_term0.size() * 4);
+    memcpy(&blob[o_un], plan.unit_nterms.data(), plan.unit_nterms.size() * 4);
+    memcpy(&blob[o_cu], plan.cons_unit0.data(), plan.cons_unit0.size() * 4);
   }
   if (!pool.empty()) memcpy(&blob[o_pool], pool.data(), pool.size());
   if (p) { memcpy(&blob[o_lo], loff.data(), (size_t)p * 4); memcpy(&blob[o_ll], llen.data(), (size_t)p * 4); }
@@ -1256,11 +1268,17 @@ static int32_t prove_batch_impl(zkp_ctx* ctx, const zkp_statement_desc* sd, cons
   ENSURE(ctx, ctx->niels, total * 128 + 128);
   // Straus tables: one KB per term; combs: one KB per per-proof base; both interleaved in groups of 32 proofs
   ENSURE(ctx, ctx->tables, ((N + 31) / 32 * 32) * (comb ? U : (size_t)n_terms) * 1024 + 1024);
-  ENSURE(ctx, ctx->sk0, total * 32 + 32);
+  ENSURE(ctx, ctx->sk0, ((N + 31) / 32 * 32) * (size_t)n_terms * 32 + 32);   // group-interleaved when CTA-staged
   ENSURE(ctx, ctx->aux0, (M + 1) * 8);
   ENSURE(ctx, ctx->aux1, M * 32 + 32);
   ENSURE(ctx, ctx->multi, M * 4 + 16);
   ENSURE(ctx, ctx->flags, 16);
+  // comb path, CTA-staged (k_comb_msm_cta): needs its tables and unit sums to fit the shared memory of one SM
+  const size_t n_units = plan.unit_term0.size();
+  const size_t cta_smem = comb ? comb_cta_smem_bytes(U, Us, n_units) : 0;
+  if (comb && ctx->prove_comb >= 2 && ctx->smem_optin < 0)
+    CUDA_TRY(ctx, cudaDeviceGetAttribute(&ctx->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+  const bool cta = comb && ctx->prove_comb >= 2 && cta_smem <= (size_t)(ctx->smem_optin > 0 ? ctx->smem_optin : 0);
   uint8_t* dm = (uint8_t*)ctx->pv_misc.p;
   CUDA_TRY(ctx, cudaMemcpyAsync(dm, blob.data(), blob_sz, cudaMemcpyHostToDevice, st));
   if (p) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->pv_limbs.p, points, N * (size_t)p * 160, cudaMemcpyHostToDevice, st));
@@ -1318,6 +1336,22 @@ static int32_t prove_batch_impl(zkp_ctx* ctx, const zkp_statement_desc* sd, cons
                                                                       (const int32_t*)(dm + o_cq), (uint4*)ctx->pv_static.p);
         LAUNCH_CHECK(ctx);
       }
+      if (cta) {
+        k_comb_recode_il<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const uint4*)ctx->in_scalars.p, N, (uint32_t)n_terms,
+                                                                         (uint32_t*)ctx->sk0.p);
+        LAUNCH_CHECK(ctx);
+        if (cta_smem > ctx->cta_smem_set) {
+          CUDA_TRY(ctx, cudaFuncSetAttribute(k_comb_msm_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cta_smem));
+          ctx->cta_smem_set = cta_smem;
+        }
+        const unsigned nw = n_units < 16 ? (unsigned)n_units : 16u;
+        k_comb_msm_cta<<<(unsigned)((N + 31) / 32), 32 * nw, cta_smem, st>>>(
+            (const uint32_t*)ctx->sk0.p, (const uint4*)ctx->tables.p, (const uint4*)ctx->pv_static.p,
+            (const int32_t*)(dm + o_cs), (const int32_t*)(dm + o_ut), (const int32_t*)(dm + o_un),
+            (const int32_t*)(dm + o_cu), N, (uint32_t)n_terms, (uint32_t)U, (uint32_t)Us, (uint32_t)n_units, (uint32_t)k,
+            (uint4*)ctx->aux1.p);
+        LAUNCH_CHECK(ctx);
+      } else {
       k_comb_recode<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const uint4*)ctx->in_scalars.p, total, (uint4*)ctx->sk0.p);
       LAUNCH_CHECK(ctx);
       k_small_msm_comb<<<(unsigned)((M + 63) / 64), 64, 0, st>>>((const uint32_t*)ctx->sk0.p, (const uint4*)ctx->tables.p,
@@ -1326,6 +1360,7 @@ static int32_t prove_batch_impl(zkp_ctx* ctx, const zkp_statement_desc* sd, cons
                                                               (const uint32_t*)ctx->multi.p, M, (uint32_t)n_terms,
                                                               (uint32_t)U, (uint4*)ctx->aux1.p);
       LAUNCH_CHECK(ctx);
+      }
     } else {
     if (share) {
       // tables of the nc batch-static points, built once from proof 0's copy (all copies were compared above)

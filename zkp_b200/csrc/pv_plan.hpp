@@ -15,7 +15,33 @@ struct pv_plan {
   std::vector<int32_t> term_slot;          // [n_terms] u >= 0: per-proof comb slot u; -(s + 1): shared comb s
   std::vector<int32_t> comb_slot_point;    // [U]  point index (instance ++ common) of per-proof slot u
   std::vector<int32_t> comb_shared_point;  // [Us] point index of shared slot s
+  // CTA-staged comb kernel (k_comb_msm_cta): every constraint is cut into units of at most `piece` consecutive terms, so
+  // that the warps of a CTA (one unit each per round) do equal work whatever the constraint sizes are
+  std::vector<int32_t> unit_term0;         // [n_units] first term (index within the proof's term list) of the unit
+  std::vector<int32_t> unit_nterms;        // [n_units] 1 .. piece
+  std::vector<int32_t> cons_unit0;         // [k + 1] the units of constraint c are cons_unit0[c] .. cons_unit0[c + 1] - 1
 };
+
+// units of at most `piece` terms per constraint (a constraint without terms keeps one empty unit: it commits to the identity)
+static inline void pv_make_units(int k, const int32_t* cons_off, int piece, pv_plan* pl) {
+  pl->unit_term0.clear();
+  pl->unit_nterms.clear();
+  pl->cons_unit0.assign(k + 1, 0);
+  if (piece < 1) piece = 1;
+  for (int c = 0; c < k; c++) {
+    pl->cons_unit0[c] = (int32_t)pl->unit_term0.size();
+    const int lo = cons_off[c], hi = cons_off[c + 1];
+    if (lo == hi) {
+      pl->unit_term0.push_back(lo);
+      pl->unit_nterms.push_back(0);
+    }
+    for (int q = lo; q < hi; q += piece) {
+      pl->unit_term0.push_back(q);
+      pl->unit_nterms.push_back(hi - q < piece ? hi - q : piece);
+    }
+  }
+  pl->cons_unit0[k] = (int32_t)pl->unit_term0.size();
+}
 
 // k constraints with term ranges cons_off[k + 1], term_point[n_terms] over instance (ni) ++ common points.
 // share: the batch-static (common) points get one table / comb per batch; comb: fill the comb slots as well.

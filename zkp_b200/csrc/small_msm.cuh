@@ -394,4 +394,164 @@ __global__ void __launch_bounds__(64) k_small_msm_comb(const uint32_t* __restric
   out[2 * j + 1] = make_uint4(enc[4], enc[5], enc[6], enc[7]);
 }
 
+
+// ---- comb path staged in shared memory: one CTA per group of 32 proofs --------------------------------------------------
+// The constant-time scans are the memory side of the prover: eight entries per term and column, ~117 GB per 2^16 CMZ
+// proofs when they come from global memory (k_small_msm_ct / k_small_msm_comb).  Here a CTA owns 32 consecutive proofs:
+// it stages their per-proof combs (U x 32 KB, contiguous in the group-interleaved layout of k_build_combs<true>) and the
+// batch's shared combs (Us x 768 B) in shared memory with 1-D bulk copies (cp.async.bulk, completion on an mbarrier) and
+// scans from there: lane l of every warp works for proof 32 g + l, so a per-proof entry word is one conflict-free
+// 512-byte LDS.128 and a shared entry word is one broadcast.  Warps take UNITS -- a constraint cut into pieces of at
+// most `piece` terms by pv_make_units -- round robin, so the warps of a CTA do equal work whatever the constraint sizes
+// are (CMZ: ten 2-term constraints and one 11-term constraint = 16 units of <= 2 terms); the pieces of a constraint are
+// added and encoded at the end.  Scalars arrive recoded and group-interleaved (k_comb_recode_il).  Public: everything
+// but `recoded`; the digits only ever feed arithmetic masks.
+//   shared memory (uint4 units): [0, Us*48) shared combs | [.., + U*2048) per-proof combs | [.., + n_units*256) unit sums
+//   | one mbarrier
+__global__ void __launch_bounds__(256) k_comb_recode_il(const uint4* __restrict__ scalars, size_t N, uint32_t T,
+                                                        uint32_t* __restrict__ recoded_il) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // term r of proof j: i = j * T + r
+  if (i >= N * (size_t)T) return;
+  const size_t j = i / T, r = i % T;
+  uint32_t s[8], m[8];
+  load_words8(s, scalars + 2 * i);
+  comb_recode(m, s);
+  uint32_t* o = recoded_il + (((j >> 5) * T + r) * 8) * 32 + (j & 31);
+#pragma unroll
+  for (int w = 0; w < 8; w++) o[w * 32] = m[w];
+}
+
+#ifdef ZKP_HOST_EMUL
+static uint4 emul_dynamic_smem[14528];   // 227 KB: blocks run one at a time under emul_launch_mt
+#endif
+
+static inline size_t comb_cta_smem_bytes(size_t U, size_t Us, size_t n_units) {
+  return 16 * (Us * 48 + U * 2048 + n_units * 256) + 16;
+}
+
+__global__ void __launch_bounds__(512, 1)
+    k_comb_msm_cta(const uint32_t* __restrict__ recoded_il, const uint4* __restrict__ combs,
+                   const uint4* __restrict__ shared_combs, const int32_t* __restrict__ term_slot,
+                   const int32_t* __restrict__ unit_term0, const int32_t* __restrict__ unit_nterms,
+                   const int32_t* __restrict__ cons_unit0, size_t N, uint32_t T, uint32_t U, uint32_t Us,
+                   uint32_t n_units, uint32_t k, uint4* __restrict__ out) {
+#ifdef ZKP_HOST_EMUL
+  uint4* smem = emul_dynamic_smem;
+#else
+  extern __shared__ uint4 comb_cta_smem[];
+  uint4* smem = comb_cta_smem;
+#endif
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const size_t g = blockIdx.x, proof = g * 32 + lane;
+  uint4* s_shared = smem;
+  uint4* s_combs = smem + (size_t)Us * 48;
+  uint4* s_res = s_combs + (size_t)U * 2048;
+  const uint4* g_combs = combs + g * (size_t)U * 2048;
+#if ZKP_DEVICE_ASM
+  {
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(s_res + (size_t)n_units * 256);
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const uint32_t bytes = (Us * 48 + U * 2048) * 16;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+      if (Us)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         (uint32_t)__cvta_generic_to_shared(s_shared)),
+                     "l"(shared_combs), "r"(Us * 768u), "r"(bar)
+                     : "memory");
+      for (uint32_t u = 0; u < U; u++)   // 32 KB per slot
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         (uint32_t)__cvta_generic_to_shared(s_combs + (size_t)u * 2048)),
+                     "l"(g_combs + (size_t)u * 2048), "r"(32768u), "r"(bar)
+                     : "memory");
+    }
+    uint32_t done;
+    do {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(done)
+                   : "r"(bar), "r"(0u)
+                   : "memory");
+    } while (!done);
+  }
+#else
+  if (threadIdx.x == 0) {
+    for (size_t i = 0; i < (size_t)Us * 48; i++) s_shared[i] = shared_combs[i];
+    for (size_t i = 0; i < (size_t)U * 2048; i++) s_combs[i] = g_combs[i];
+  }
+  __syncthreads();
+#endif
+  // ---- the units of this warp -------------------------------------------------------------------------------------
+#pragma unroll 1
+  for (uint32_t u = warp; u < n_units; u += nw) {
+    const uint32_t r0 = (uint32_t)unit_term0[u], nt = (uint32_t)unit_nterms[u];
+    ge_ext acc;
+    ge_identity(acc);
+#pragma unroll 1
+    for (int col = 63; col >= 0; col--) {
+      ge_double(acc, acc);
+#pragma unroll 1
+      for (uint32_t t = 0; t < nt; t++) {
+        const uint32_t r = r0 + t;
+        const int32_t slot = term_slot[r];
+        const uint32_t* mw = recoded_il + ((g * T + r) * 8 + (uint32_t)(col >> 5)) * 32 + lane;
+        uint32_t idx, neg;
+        comb_column_words(idx, neg, __ldg(mw), __ldg(mw + 64), __ldg(mw + 128), __ldg(mw + 192), col & 31);
+        if (slot >= 0) {   // public: the statement's, the same for every lane
+          const uint4* tab = s_combs + (size_t)slot * 2048 + lane;
+          ge_pniels sel;
+          comb_select(sel, [&](uint32_t e, int q, uint32_t& x, uint32_t& y, uint32_t& z, uint32_t& ww) {
+            const uint4 v = tab[(8 * e + q) * 32];
+            x = v.x; y = v.y; z = v.z; ww = v.w;
+          }, idx, neg);
+          ge_add_pniels(acc, acc, sel);
+        } else {
+          const uint4* tab = s_shared + (size_t)(-slot - 1) * 48;
+          ge_aniels sel;
+          comb_select_affine(sel, [&](uint32_t e, int q, uint32_t& x, uint32_t& y, uint32_t& z, uint32_t& ww) {
+            const uint4 v = tab[6 * e + q];
+            x = v.x; y = v.y; z = v.z; ww = v.w;
+          }, idx, neg);
+          ge_madd(acc, acc, sel);
+        }
+      }
+    }
+    uint4* o = s_res + (size_t)u * 256 + lane;
+    const uint32_t* w = (const uint32_t*)&acc;
+#pragma unroll
+    for (int q = 0; q < 8; q++) o[q * 32] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+  }
+  __syncthreads();
+  // ---- constraints: add the pieces, encode ------------------------------------------------------------------------
+#pragma unroll 1
+  for (uint32_t c = warp; c < k; c += nw) {
+    const uint32_t u0 = (uint32_t)cons_unit0[c], u1 = (uint32_t)cons_unit0[c + 1];
+    ge_ext acc, p;
+    auto load_unit = [&](ge_ext& dst, uint32_t u) {
+      const uint4* o = s_res + (size_t)u * 256 + lane;
+      uint32_t* w = (uint32_t*)&dst;
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        const uint4 v = o[q * 32];
+        w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+      }
+    };
+    load_unit(acc, u0);
+#pragma unroll 1
+    for (uint32_t u = u0 + 1; u < u1; u++) {
+      load_unit(p, u);
+      ge_add(acc, acc, p);
+    }
+    uint32_t enc[8];
+    ristretto_encode(enc, acc);
+    if (proof < N) {
+      out[2 * (proof * k + c)] = make_uint4(enc[0], enc[1], enc[2], enc[3]);
+      out[2 * (proof * k + c) + 1] = make_uint4(enc[4], enc[5], enc[6], enc[7]);
+    }
+  }
+}
+
 }  // namespace zkp
