@@ -211,6 +211,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log2-proofs", type=int, default=21, help="proofs per GPU (default 2^21)")
     ap.add_argument("--cpu-sample-log2", type=int, default=16, help="proofs in the CPU baseline sample")
+    ap.add_argument("--ref-sample-log2", type=int, default=17, help="proofs per step of the --impl reference arm")
     ap.add_argument("--window", type=int, default=0, help="tuning: force the Pippenger window width")
     ap.add_argument("--chunk", type=int, default=0, help="tuning: force the accumulate work-item length")
     ap.add_argument("--no-proofs-leg", action="store_true", help="skip the e2e_from_proofs leg (real proofs, device front end)")
@@ -224,6 +225,10 @@ def main():
     ap.add_argument("--dual-stream", type=int, default=-1, help="tuning: chunk kernels of the e2e leg on two alternating streams (0/1)")
     ap.add_argument("--no-fused-sort", action="store_true", help="tuning: separate scatter pass instead of the two-phase ingestion")
     ap.add_argument("--sweep", default="", help="tuning: comma list of windows; prints stage times per window and exits")
+    ap.add_argument("--no-configs", action="store_true", help="skip the legs of the other BASELINE configs (`configs` block)")
+    ap.add_argument("--dleq-log2", type=int, default=20, help="DLEQ proofs per GPU of the dleq_batch_verify leg")
+    ap.add_argument("--prove-log2", type=int, default=16, help="CMZ proofs per GPU of the cmz_prove leg")
+    ap.add_argument("--sweep-max-log2", type=int, default=22, help="largest size of the raw MSM sweep")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -242,15 +247,17 @@ def main():
         if rank != 0:
             return
         # the reference itself is Rust (no toolchain here): its CPU algorithms are timed through the C port
-        sample = 1 << args.cpu_sample_log2
+        # a bounded sample of the workload per step (the same 24-row coefficient mix, DISTINCT points, one MSM of
+        # 24 * sample terms): 2^21 proofs per step would take ~20 s on these cores, i.e. minutes per run
+        sample = 1 << args.ref_sample_log2
         sc, K, half = make_cmz_batch(sample, seed=1234, n_points=2 * sample)
         sc = finish_cancellation(sc, sample, half)
-        pts = _host_points(2 * sample)   # valid encodings made on the CPU (no GPU on this arm)
+        pts = _host_points(2 * sample, distinct=2 * sample, threads=host_threads)   # valid encodings made on the CPU
         pidx = (np.arange(sample) % half)[None, :] + (np.arange(ROWS) & 1)[:, None] * half
         pt_rows = pts[pidx]
         sc_rows = sc.view(np.uint8).reshape(ROWS, sample, 32)
         for _ in range(args.warmup):
-            cpu_baseline(sc_rows, pt_rows, min(sample, 1 << 10), host_threads)
+            cpu_baseline(sc_rows, pt_rows, min(sample, 1 << 12), host_threads)
         t0 = time.perf_counter()
         rates = [cpu_baseline(sc_rows, pt_rows, sample, host_threads)[0] for _ in range(args.steps)]
         dt = (time.perf_counter() - t0) / args.steps
@@ -261,11 +268,17 @@ def main():
                 "unit": "proofs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u64", "data": "synthetic", "config": config,
+                "same_workload_size": False, "sample_proofs_per_step": sample,
+                "what": "the reference is Rust (no toolchain in this image): this arm times a C port of its CPU algorithms "
+                        "(kind: port), on a %d-proof sample per step of the 2^%d-proof workload the GPU arm runs in full; "
+                        "the rate is per proof, so the two are comparable, the sizes are not equal"
+                        % (sample, args.log2_proofs),
                 "cpu_baseline": {"value": v, "unit": "proofs/s", "cores": host_threads, "kind": "port",
                                  "backend": backend, "u64_serial_backend_value": u64_v,
-                                 "sample": "%d proofs (%d-term MSM) per step, C port of dalek's CPU algorithms (%s), %d threads"
-                                           % (sample, ROWS * sample, "vector backend" if simd else "u64 serial backend",
-                                              host_threads)},
+                                 "sample": "%d proofs (%d-term MSM over %d distinct points) per step, C port of dalek's CPU "
+                                           "algorithms (%s), %d threads"
+                                           % (sample, ROWS * sample, 2 * sample,
+                                              "vector backend" if simd else "u64 serial backend", host_threads)},
                 "e2e": {"value": v, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -406,17 +419,34 @@ def main():
     clocks = sampler.stop()
     assert accepts == args.steps
 
-    # ---- e2e from PROOFS: 2^16 real CMZ proofs (made here with the engine) tiled to 2^21 batch entries; transcripts,
-    # challenges, weights, coefficient fold and MSM all on the GPU (zkp_batch_verify_proofs, SURVEY 8f f1+f2) ----------
+    # register-resident field-op rates of this GPU (the calibration every integer-pipe fraction refers to)
+    fe_sq_rate = eng.bench_field(9, 2048)                     # variable-time tails: what the verifier's kernels run
+    fe_mul_rate = eng.bench_field(8, 2048)
+    madd_rate = eng.bench_field(11, 512)
+    fe_sq_ct, fe_mul_ct = eng.bench_field(1, 2048), eng.bench_field(0, 2048)   # branch-free tails: the prover's kernels
+    configs = {}
+    from tools import bench_legs as BL
+    if not args.no_configs:
+        # the H2D copies of one e2e step alone, all ranks at once: the ceiling of the e2e leg at N GPUs
+        configs["h2d_ceiling"] = BL.h2d_ceiling([(d_scal, h_scal), (d_pts, h_pts)], args.steps, barrier, world)
+        # ONE batch, ONE verdict over all ranks (partial sums over NCCL)
+        configs["single_verdict"] = BL.single_verdict(eng, stream, d_scal, d_pts, n_terms, NUM_S, rank, world,
+                                                      max(2, min(args.steps, 5)))
+
+    # ---- e2e from PROOFS: 2^16 real CMZ proofs (made here by zkp_prove_batch = the cmz_prove leg, BASELINE configs[1])
+    # tiled to 2^21 batch entries; transcripts, challenges, weights, coefficient fold and MSM all on the GPU
+    # (zkp_batch_verify_proofs, SURVEY 8f f1+f2) ---------------------------------------------------------------------
     proofs_leg = None
     if not args.no_proofs_leg:
         from tools.workloads import cmz_instances
         from zkp_b200 import toolbox as PT
         eng.set_stream(None)
-        n_real = min(N, 1 << 16)
+        n_real = min(N, 1 << args.prove_log2)
         st_cmz, sec, limbs, enc_pts = cmz_instances(eng, n_real, np.random.default_rng(500 + rank))
         entropy = np.random.default_rng(600 + rank).integers(0, 256, size=(n_real, 32), dtype=np.uint8)
-        enc_p, com, resp = st_cmz.prove_many(eng, b"CMZ", sec, limbs, entropy, threads=host_threads)
+        configs["cmz_prove"], (enc_p, com, resp) = BL.cmz_prove(eng, st_cmz, sec, limbs, entropy, (fe_sq_ct, fe_mul_ct), 3,
+                                                               barrier, world)
+        assert (enc_p == enc_pts).all()
         del limbs
         reps = N // n_real
         pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
@@ -443,6 +473,21 @@ def main():
                       "h2d_bytes_per_step": int(inst_h.nbytes + com_h.nbytes + resp_h.nbytes + common_h.nbytes),
                       "distinct_real_proofs": int(n_real)}
         del inst_h, com_h, resp_h
+    # the CPU baseline's sample (rank 0 at N = 1): the first proofs' columns of every row of THIS workload
+    cpu_sample = min(1 << args.cpu_sample_log2, N)
+    cpu_sc_rows = cpu_pt_rows = None
+    if rank == 0 and world == 1:
+        cpu_sc_rows = np.ascontiguousarray(sc.view(np.uint8).reshape(ROWS, N, 32)[:, :cpu_sample])
+        cpu_pt_rows = np.ascontiguousarray(inst_points.numpy().reshape(ROWS, N, 32)[:, :cpu_sample])
+    if not args.no_configs:
+        h_sc_np = h_pt_np = None
+        del d_scal, d_pts, h_scal, h_pts, inst_points, inst_coeffs, sc
+        torch.cuda.empty_cache()
+        eng.set_stream(None)
+        configs["dleq_batch_verify"] = BL.dleq_batch_verify(eng, stream, args.dleq_log2, max(2, min(args.steps, 5)), rank,
+                                                            barrier, world)
+        configs["raw_msm_sweep"] = BL.raw_msm_sweep(eng, stream, list(range(8, args.sweep_max_log2 + 1, 2)), rank, world, 18,
+                                                    host_threads)
 
     # ---- gather: max time over ranks, accept bits over NCCL ---------------------------------------------------
     from zkp_b200 import parallel
@@ -467,48 +512,52 @@ def main():
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
         dom = max((k for k in stages if k not in ("window", "lanes")), key=lambda k: stages[k])
-        # The dominant kernel of a step is k_ingest2: two launches, each decompresses half of the points (32 B in, 96 B
-        # out per point) and reads all the scalars (32 B per term) for the digit histogram (phase 1) / scatter (phase 2).
+        # The dominant kernel of a step is k_ingest2: two launches, each decompresses half of the points and reads all the
+        # scalars (digit histogram in phase 1, counting-sort scatter in phase 2).  ALGORITHMIC bytes of one launch by
+        # SURVEY 8(d) (64 B read per MSM term = 32 B scalar + 32 B encoding): n/2 encodings + n scalars.
         ing = [live.get("ingest_phase1", -1.0), live.get("ingest_phase2", -1.0)]
         ing_ms = float(np.mean(ing)) if min(ing) > 0 else 0.0
-        ing_bytes = n_terms * (0.5 * 128.0 + 32.0)               # algorithmic bytes of ONE launch
+        ing_bytes = n_terms * (0.5 * 32.0 + 32.0)                # algorithmic bytes of ONE launch
         achieved = ing_bytes / (ing_ms * 1e-3) / 1e9 if ing_ms else 0.0
-        # integer-pipe view: field mults (254 S + 30 M per point) against the calibrated register-resident rates
-        fe_sq_rate = eng.bench_field(9, 2048)                     # variable-time tails: what the kernel runs
-        fe_mul_rate = eng.bench_field(8, 2048)
-        madd_rate = eng.bench_field(11, 512)
-        dec_time_at_peak = 0.5 * n_terms * (254.0 / fe_sq_rate + 30.0 / fe_mul_rate)
+        # integer-pipe view: field mults (257 S + 26 M per point) against the calibrated register-resident rates
+        dec_time_at_peak = 0.5 * n_terms * (257.0 / fe_sq_rate + 26.0 / fe_mul_rate)
         acc_ms = live.get("accumulate", -1.0)
-        traffic, traffic_src = None, None
+        traffic, traffic_each, traffic_src, pipe = None, None, None, None
         try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
-            prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ingest_ncu.json")))
-            traffic = prof["traffic_bytes_per_launch"] * (n_terms / prof["n_terms"])
-            traffic_src = ("profiles/r01_ingest_ncu.json (ncu --set full at n=%d, mean of the two launches, scaled by n)"
-                           % prof["n_terms"])
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r02_ingest_ncu.json")))
+            scale = n_terms / prof["n_terms"]
+            ing_l = [l for l in prof["launches"] if l["kernel"].startswith("k_ingest2")]
+            traffic_each = [l["traffic_bytes"] * scale for l in ing_l]
+            traffic = traffic_each[0]
+            traffic_src = ("profiles/r02_ingest_ncu.json (ncu --set full at n=%d; `traffic` = the phase-1 launch, "
+                           "`traffic_each` = both launches: the phase-2 launch carries the counting-sort scatter)" % prof["n_terms"])
+            pipe = {l["kernel"]: {"fmaheavy_busy_pct": l["fmaheavy_pct"], "issue_active_pct": l["issue_active_pct"]}
+                    for l in prof["launches"]}
         except Exception:
             pass
         roofline = {"bound": "hbm", "kernel": "k_ingest2 (2 launches per step: decompress half of the points + digit "
                                               "histogram / scatter of all scalars)",
                     "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                    "frac": achieved / hbm_peak, "traffic": traffic, "traffic_each": traffic_each,
+                    "traffic_source": traffic_src, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": ing_bytes, "kernel_ms": ing_ms, "kernel_ms_each": ing,
                     "share_of_step": (sum(ing) / ms_step) if ing_ms else None,
                     "whole_path_hbm": {"bytes_per_proof": BYTES_PER_PROOF,
                                        "achieved_GBs": N * BYTES_PER_PROOF / (ms_step * 1e-3) / 1e9,
                                        "frac": N * BYTES_PER_PROOF / (ms_step * 1e-3) / 1e9 / hbm_peak},
-                    "integer_pipe": {"what": "the path is bound by IMAD.WIDE issue (profiles/r01_issue_model.md), not by "
-                                             "HBM: kernel time against the register-resident field-op rates of this run",
+                    "integer_pipe": {"what": "the path is bound by the FMA-heavy pipe (32x32->64 IMAD.WIDE: 86-87 % busy in "
+                                             "k_ingest2 and k_accumulate, profiles/r02_pipe_counters.md), not by HBM: kernel "
+                                             "time against the register-resident field-op rates of this run",
                                      "fe_sq_per_s_calibrated": fe_sq_rate, "fe_mul_per_s_calibrated": fe_mul_rate,
                                      "madd_per_s_calibrated": madd_rate,
                                      "k_ingest2_frac_of_calibrated": (dec_time_at_peak / (ing_ms * 1e-3)) if ing_ms else None,
                                      "k_accumulate_ms": acc_ms if acc_ms > 0 else None,
                                      "k_accumulate_frac_of_calibrated":
                                          (bucket_adds_per_proof(int(stages.get("window", 19))) * N / madd_rate / (acc_ms * 1e-3))
-                                         if acc_ms > 0 else None},
+                                         if acc_ms > 0 else None,
+                                     "ncu_pipe_counters": pipe},
                     "stage_ms_unfused_profile_mode": stages, "dominant_stage_unfused": dom}
-        sample = min(1 << args.cpu_sample_log2, N)
-        sc_rows = sc.view(np.uint8).reshape(ROWS, N, 32)
-        pt_rows = inst_points.numpy().reshape(ROWS, N, 32)
+        sample, sc_rows, pt_rows = cpu_sample, cpu_sc_rows, cpu_pt_rows
         # the CPU baseline is taken at N = 1 only (the other ranks would compete for the same host cores)
         cpu_v, cpu_t = cpu_baseline(sc_rows, pt_rows, sample, host_threads) if world == 1 else (None, 0.0)
         cpu_1 = cpu_baseline(sc_rows, pt_rows, max(256, sample // 8), 1)[0] if world == 1 else None   # what `cargo bench` would see
@@ -531,7 +580,7 @@ def main():
                                                host_threads, cpu_t)} if world == 1 else
                                  {"value": None, "unit": "proofs/s", "cores": 0, "kind": "port",
                                   "sample": "taken at N = 1 only (bench.py --gpus 1)"}),
-                "accept_bits": accept_bitmap, "setup_s": setup_s, "numa_binding_rank0": numa}
+                "accept_bits": accept_bitmap, "setup_s": setup_s, "numa_binding_rank0": numa, "configs": configs}
         if proofs_leg:
             line["e2e_from_proofs"] = {
                 "value": world * N / (proofs_ms * 1e-3), "unit": "proofs/s", "ms_per_step": proofs_ms,
@@ -561,7 +610,7 @@ def gpu_points(eng, K, seed):
     return out
 
 
-def _host_points(K, distinct=4096):
+def _host_points(K, distinct=4096, threads=1):
     """K valid encodings without a GPU (reference arm): r*B for `distinct` random r via the C port, tiled."""
     from oracle import cref
     rng = np.random.default_rng(4242)
@@ -569,8 +618,22 @@ def _host_points(K, distinct=4096):
     r = rng.integers(0, 256, size=(d, 32), dtype=np.uint8)
     r[:, 31] &= 0x0F
     B = np.frombuffer(bytes.fromhex("e2f2ae0a6abc4e71a884a961c500515f58e30b6aa582dd8db6a65945e08d2d76"), dtype=np.uint8)
-    out, valid = cref.msm_vartime_batched(r, np.broadcast_to(B, (d, 32)).copy(), np.arange(d + 1, dtype=np.uint64))
-    assert valid.all()
+    out = np.empty((d, 32), dtype=np.uint8)
+    threads = max(1, min(int(threads), 64))
+    bounds = [d * i // threads for i in range(threads + 1)]
+
+    def work(i):
+        lo, hi = bounds[i], bounds[i + 1]
+        if hi > lo:
+            o, valid = cref.msm_vartime_batched(r[lo:hi], np.broadcast_to(B, (hi - lo, 32)).copy(),
+                                                np.arange(hi - lo + 1, dtype=np.uint64))
+            assert valid.all()
+            out[lo:hi] = o
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(threads)]   # ctypes releases the GIL in the C call
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
     return out[np.arange(K) % d]
 
 

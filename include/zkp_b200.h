@@ -162,6 +162,15 @@ int32_t zkp_batch_verify_partial(zkp_ctx* ctx, const uint8_t* static_coeffs, con
 int32_t zkp_partials_verdict(zkp_ctx* ctx, const uint64_t* partial_limbs, size_t count, int32_t* accept,
                              uint8_t* enc_out32);
 
+/* The same with device-resident data, asynchronous on the context's stream (what a rank of a sharded batch runs between
+ * its MSM and the verdict): zkp_msm_vartime_partial_dev = zkp_msm_vartime_dev that also leaves the sum as 160 bytes of
+ * FieldElement51 limbs at d_partial_limbs; after an all-gather of those 160-byte records (NCCL, same stream),
+ * zkp_partials_verdict_dev writes the 48-byte result record of zkp_msm_vartime_dev for their sum to d_result
+ * (is_identity = the verdict of batch_verifier.rs:230).  All pointers 16-byte aligned device memory.                  */
+int32_t zkp_msm_vartime_partial_dev(zkp_ctx* ctx, const void* d_scalars, const void* d_points, size_t n, void* d_result,
+                                    void* d_partial_limbs);
+int32_t zkp_partials_verdict_dev(zkp_ctx* ctx, const void* d_partial_limbs, size_t count, void* d_result);
+
 /* Batch proving with the per-proof work of Prover::prove_impl (/root/reference/src/toolbox/prover.rs:76-112) on the
  * device: allocate_point compressions (toolbox/mod.rs:180), transcript replay, the synthetic-nonce blindings of
  * prover.rs:78-89 (TranscriptRng rekeyed with every secret and finalized with entropy[j], the stand-in for thread_rng),

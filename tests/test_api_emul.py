@@ -112,6 +112,7 @@ def test_batch_verify_and_partial_sums_through_the_emulated_abi(api):
     base = U.base_points(64)
     num_s, rows, batch = 3, 4, 50
     n = num_s + rows * batch
+    assert api.zkp_ctx_set_option(api.ctx, b"small_max", 0) == 0      # this test is about the pipeline's launch sequence
     sc = U.random_scalars(n, seed=12)
     pts = np.frombuffer(b"".join(base[(3 * i + 1) % 64] for i in range(n)), np.uint8).reshape(-1, 32).copy()
     # make the last term cancel the others:  sum_{i<n-1} s_i P_i + (l - 1) * R = 0  with R the sum so far
@@ -121,12 +122,16 @@ def test_batch_verify_and_partial_sums_through_the_emulated_abi(api):
     acc, bad = i32(-1), i64(0)
     call = lambda s_: api.zkp_batch_verify(api.ctx, _p(s_[:num_s]), _p(pts[:num_s]), num_s, _p(s_[num_s:]), _p(pts[num_s:]), rows,
                                            batch, ctypes.byref(acc), ctypes.byref(bad))
-    assert call(sc) == 0 and acc.value == 1
-    flipped = sc.copy()
-    flipped[17, 0] ^= 1
-    assert call(flipped) == 0 and acc.value == 0
+    try:
+        assert call(sc) == 0 and acc.value == 1
+        flipped = sc.copy()
+        flipped[17, 0] ^= 1
+        assert call(flipped) == 0 and acc.value == 0
+    finally:
+        api.zkp_ctx_set_option(api.ctx, b"small_max", 1024)
     if not SLOW:
         return
+    api.zkp_ctx_set_option(api.ctx, b"small_max", 0)
     # two shards: columns [0, 20) and [20, 50) of every row; the static terms go to the first shard
     inst_s = sc[num_s:].reshape(rows, batch, 32)
     inst_p = pts[num_s:].reshape(rows, batch, 32)
@@ -138,6 +143,7 @@ def test_batch_verify_and_partial_sums_through_the_emulated_abi(api):
         assert api.zkp_batch_verify_partial(api.ctx, _p(sc[:num_s]), _p(pts[:num_s]), ns, _p(s_), _p(p_), rows, hi - lo,
                                             _p(partials[g]), ctypes.byref(bad)) == 0
     enc = np.zeros(32, np.uint8)
+    api.zkp_ctx_set_option(api.ctx, b"small_max", 1024)
     assert api.zkp_partials_verdict(api.ctx, _p(partials), 2, ctypes.byref(acc), _p(enc)) == 0
     assert acc.value == 1 and enc.tobytes() == bytes(32)
 
@@ -213,7 +219,9 @@ def test_prove_batch_and_verify_from_proof_bytes_through_the_emulated_abi(api):
         return rc, enc, com, resp
 
     try:
-        for comb, share, chunk in ((0, 1, 1 << 17), (1, 1, 1 << 17), (1, 0, 1 << 17), (1, 1, 2), (0, 0, 2)):
+        # prove_comb: 0 = Straus tables, 1 = combs scanned from global memory, 2 = combs staged in shared memory (default)
+        for comb, share, chunk in ((0, 1, 1 << 17), (1, 1, 1 << 17), (1, 0, 1 << 17), (1, 1, 2), (0, 0, 2), (2, 1, 1 << 17),
+                                   (2, 0, 2)):
             for key, v in ((b"prove_comb", comb), (b"share_static_tables", share), (b"prove_chunk", chunk)):
                 assert api.zkp_ctx_set_option(api.ctx, key, v) == 0
             rc, enc, com, resp = prove()
@@ -224,7 +232,7 @@ def test_prove_batch_and_verify_from_proof_bytes_through_the_emulated_abi(api):
                 assert [bytes(r) for r in resp[j]] == [S.to_bytes(r) for r in proof.responses]
                 assert [bytes(e) for e in enc[j]] == [oenc[n] for n in names]
     finally:
-        for key, v in ((b"prove_comb", 0), (b"share_static_tables", 1), (b"prove_chunk", 1 << 17)):
+        for key, v in ((b"prove_comb", 2), (b"share_static_tables", 1), (b"prove_chunk", 1 << 17)):
             api.zkp_ctx_set_option(api.ctx, key, v)
     # ---- verification of those proofs from their bytes ----
     seed = bytes(range(32))
@@ -281,6 +289,22 @@ def test_small_msms_codec_and_selftests_through_the_emulated_abi(api):
             assert out2.tobytes() == expected, coop_max
     finally:
         api.zkp_ctx_set_option(api.ctx, b"coop_max_msms", 8192)
+    # one small MSM through zkp_msm_vartime: the four-lane Straus path (k_single_msm_vt / k_single_finish) instead of the
+    # sort pipeline -- one term per group, and several terms per group; the index of a bad point
+    try:
+        for groups in (1024, 3):
+            assert api.zkp_ctx_set_option(api.ctx, b"small_groups", groups) == 0
+            for k_ in kats[:4] + kats[-1:]:
+                s_ = np.frombuffer(b"".join(bytes.fromhex(x) for x in k_["scalars"]), np.uint8).reshape(-1, 32)
+                p_ = np.frombuffer(b"".join(bytes.fromhex(x) for x in k_["points"]), np.uint8).reshape(-1, 32)
+                rc, enc, ident, bad = _msm(api, s_, p_)
+                assert (rc, enc.hex(), bad) == (0, k_["expected"], -1), (groups, k_["n"])
+                assert ident == (k_["expected"] == "00" * 32)
+        p_bad = p_.copy()
+        p_bad[len(p_bad) // 2] = 0xFF
+        assert _msm(api, s_, p_bad)[0::3] == (native.ZKP_ERR_POINT, len(p_bad) // 2)
+    finally:
+        api.zkp_ctx_set_option(api.ctx, b"small_groups", 1024)
     encs = np.frombuffer(b"".join(U.base_points(8)) + b"\xff" * 32, np.uint8).reshape(-1, 32)
     limbs, valid = np.zeros((9, 20), np.uint64), np.zeros(9, np.uint8)
     assert api.zkp_decompress_batch(api.ctx, _p(encs), 9, _p(limbs), _p(valid)) == 0

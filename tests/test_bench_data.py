@@ -33,8 +33,10 @@ def test_reference_arm_line(capsys, monkeypatch):
     import json
     import sys
     monkeypatch.setattr(sys, "argv", ["bench.py", "--impl", "reference", "--steps", "1", "--warmup", "1",
-                                      "--cpu-sample-log2", "8"])
+                                      "--ref-sample-log2", "8"])
     bench.main()
     line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port" and line["value"] > 0
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["unit"] == "proofs/s"
+    # the arm says that a step is a bounded sample of the workload, and how large
+    assert line["same_workload_size"] is False and line["sample_proofs_per_step"] == 256

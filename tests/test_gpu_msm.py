@@ -43,6 +43,49 @@ def test_msm_kats(engine):
         assert ident == (kat["expected"] == "00" * 32)
 
 
+def test_small_n_dispatch_matches_the_pipeline(engine):
+    """Few terms take the four-lane Straus path (k_single_msm_vt: the reference's n < 190 dispatch,
+    /root/reference/src/toolbox/verifier.rs:162-166), many take the Pippenger pipeline; every KAT gives the same bytes
+    through both (small_max = 0 forces the pipeline, a large small_max forces the small path, small_groups cuts the terms
+    over fewer groups), and the status / first-bad-index reporting is the same."""
+    kats = U.golden("msm_kat.json")["kats"]
+    g = U.golden("rfc9496.json")
+    bad_pt = np.frombuffer(bytes.fromhex(g["bad_encodings"][5]), dtype=np.uint8)
+    from zkp_b200 import EngineError
+    try:
+        for small_max, groups in ((0, 1024), (1 << 20, 1024), (1 << 20, 7), (1 << 20, 1)):
+            engine.set_option("small_max", small_max)
+            engine.set_option("small_groups", groups)
+            for kat in kats:
+                enc, ident, _ = engine.msm_vartime(_h(kat["scalars"]), _h(kat["points"]))
+                assert enc.hex() == kat["expected"], (small_max, groups, kat["n"])
+                assert ident == (kat["expected"] == "00" * 32)
+            kat = [k for k in kats if k["n"] >= 36][0]
+            sc, pts = _h(kat["scalars"]).copy(), _h(kat["points"]).copy()
+            for idx in (0, 17, kat["n"] - 1):
+                p2 = pts.copy()
+                p2[idx] = bad_pt
+                enc, _, first_bad = engine.msm_vartime(sc, p2)
+                assert enc is None and first_bad == idx, (small_max, groups, idx)
+                s2 = sc.copy()
+                s2[idx] = 0xFF
+                with pytest.raises(EngineError) as ei:
+                    engine.msm_vartime(s2, pts)
+                assert ei.value.code == 3
+            # the batch entry point and the partial-sum entry point (single-verdict mode) over a small batch
+            kb = U.golden("toolbox_kat.json")["dleq_batch"]
+            scal, bpts = _h(kb["msm_scalars"]), _h(kb["msm_points"])
+            rows = (scal.shape[0] - 1) // 4
+            ok, rc = engine.batch_verify(scal[:1], bpts[:1], scal[1:], bpts[1:], rows, 4)
+            assert ok and rc == 0, (small_max, groups)
+            part = engine.batch_verify_partial(scal[:1], bpts[:1], scal[1:], bpts[1:], rows, 4)
+            acc, enc = engine.partials_verdict(part.reshape(1, 20))
+            assert acc and enc == bytes(32)
+    finally:
+        engine.set_option("small_max", 1024)
+        engine.set_option("small_groups", 1024)
+
+
 @pytest.mark.parametrize("window", [4, 5, 7, 8, 11, 13, 16])
 def test_msm_all_windows(engine, window):
     kat = [k for k in U.golden("msm_kat.json")["kats"] if k["n"] == 300][0]
@@ -328,7 +371,7 @@ def test_two_phase_ingestion_and_item_balance_options(engine):
                 d_sc = torch.from_numpy(sc).cuda()
                 d_pt = torch.from_numpy(pts.copy()).cuda()
                 d_res = torch.zeros(64, dtype=torch.uint8, device="cuda")
-                for cnt, exp in ((n, bytes.fromhex(case["expected"])), (odd, exp_odd), (1, None)):
+                for cnt, exp in ((1, None), (odd, exp_odd), (n, bytes.fromhex(case["expected"]))):
                     engine.msm_vartime_dev(d_sc.data_ptr(), d_pt.data_ptr(), cnt, d_res.data_ptr())
                     engine.synchronize()
                     r = d_res.cpu().numpy()

@@ -336,6 +336,7 @@ def test_prove_many_device_comb_path_matches_straus_path(engine):
     sec_arr = np.stack([sbytes([s[n] for n in st.secrets]) for s in secs])
     pts_arr = np.array([[limbs(p[n]) for n in st.points] for p in ptss], dtype=np.uint64)
     entropy = np.frombuffer(OT.SeededRng(b"entropy-comb").bytes(32 * N), dtype=np.uint8).reshape(N, 32)
+    engine.set_option("prove_comb", 0)       # the reference bytes come from the Straus path (k_small_msm_ct)
     want = st.prove_many_device(engine, b"CMZ", sec_arr, pts_arr, entropy)
     secs2, ptss2 = _cmz_instances(1, b"cmz-comb-other-common", fresh_common=True)
     mixed_pts, mixed_sec = pts_arr.copy(), sec_arr.copy()
@@ -356,20 +357,27 @@ def test_prove_many_device_comb_path_matches_straus_path(engine):
     pke = np.frombuffer(OT.SeededRng(b"pk-comb").bytes(32 * 4), dtype=np.uint8).reshape(4, 32)
     want_pk = pk.prove_many_device(engine, b"PK", np.stack([sbytes([123456789])] * 4), pkp, pke)
     same = lambda a, b: all((x == y).all() for x, y in zip(a, b))
-    engine.set_option("prove_comb", 1)
     try:
-        for share in (1, 0):
-            engine.set_option("share_static_tables", share)
-            assert same(st.prove_many_device(engine, b"CMZ", sec_arr, pts_arr, entropy), want), share
-            assert same(st.prove_many_device(engine, b"CMZ", mixed_sec, mixed_pts, entropy), want_mixed), share
-            assert same(st.prove_many_device(engine, b"CMZ", sec_arr[:1], pts_arr[:1], entropy[:1]), [w[:1] for w in want])
-            assert same(dst.prove_many_device(engine, b"DLEQBatchTest", dsec, dl, ent), want_dleq), share
-            assert same(pk.prove_many_device(engine, b"PK", np.stack([sbytes([123456789])] * 4), pkp, pke), want_pk), share
-        engine.set_option("share_static_tables", 1)
-        engine.set_option("prove_chunk", 33)
-        assert same(st.prove_many_device(engine, b"CMZ", sec_arr, pts_arr, entropy), want)
+        # 1 = combs scanned from global memory (k_small_msm_comb); 2 = combs staged in shared memory, one CTA per 32 proofs,
+        # constraints cut into units of <= prove_piece terms (k_comb_msm_cta: the default)
+        for comb, piece in ((1, 2), (2, 2), (2, 1), (2, 3), (2, 11)):
+            engine.set_option("prove_comb", comb)
+            engine.set_option("prove_piece", piece)
+            for share in (1, 0):
+                engine.set_option("share_static_tables", share)
+                tag = (comb, piece, share)
+                assert same(st.prove_many_device(engine, b"CMZ", sec_arr, pts_arr, entropy), want), tag
+                assert same(st.prove_many_device(engine, b"CMZ", mixed_sec, mixed_pts, entropy), want_mixed), tag
+                assert same(st.prove_many_device(engine, b"CMZ", sec_arr[:1], pts_arr[:1], entropy[:1]), [w[:1] for w in want]), tag
+                assert same(dst.prove_many_device(engine, b"DLEQBatchTest", dsec, dl, ent), want_dleq), tag
+                assert same(pk.prove_many_device(engine, b"PK", np.stack([sbytes([123456789])] * 4), pkp, pke), want_pk), tag
+            engine.set_option("share_static_tables", 1)
+            engine.set_option("prove_chunk", 33)
+            assert same(st.prove_many_device(engine, b"CMZ", sec_arr, pts_arr, entropy), want), (comb, piece)
+            engine.set_option("prove_chunk", 1 << 17)
     finally:
-        engine.set_option("prove_comb", 0)
+        engine.set_option("prove_comb", 2)
+        engine.set_option("prove_piece", 2)
         engine.set_option("share_static_tables", 1)
         engine.set_option("prove_chunk", 1 << 17)
 

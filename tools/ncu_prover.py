@@ -16,11 +16,14 @@ rng = np.random.default_rng(11)
 st, sec, limbs, enc = cmz_instances(eng, N, rng)
 entropy = rng.integers(0, 256, size=(N, 32), dtype=np.uint8)
 outs = {}
-for comb in (0, 1):
+for comb in (0, 1, 2):        # Straus tables; combs from global memory; combs staged in shared memory (the default)
     if (comb and "--straus-only" in sys.argv) or (not comb and "--comb-only" in sys.argv):
+        continue
+    if comb == 1 and "--cta-only" in sys.argv:
         continue
     eng.set_option("prove_comb", comb)
     outs[comb] = st.prove_many_device(eng, b"CMZ", sec, limbs, entropy)
-if len(outs) == 2:
-    assert all((a == b).all() for a, b in zip(outs[0], outs[1])), "comb and Straus provers disagree"
+ref = next(iter(outs.values()))
+for comb, o in outs.items():
+    assert all((a == b).all() for a, b in zip(ref, o)), "prover paths disagree (prove_comb = %d)" % comb
 print("done", N, sorted(outs))

@@ -69,8 +69,15 @@ struct zkp_ctx {
   int phase1_percent = 50;   // share of the host-path point chunks decompressed under the histogram (first phase)
   int share_static_tables = 1;   // batch proving: one constant-time table per batch-static point
   // batch proving: signed four-tooth combs, one per base (comb.cuh): 64 doublings per constraint MSM instead of 256.
-  // Logic checked on the host against the oracle (tests/test_host_emul.py); not yet run on a GPU, hence off.
-  int prove_comb = 0;
+  // 0 = Straus tables (k_small_msm_ct), 1 = combs scanned from global memory (k_small_msm_comb), 2 = combs staged in
+  // shared memory by one CTA per 32 proofs (k_comb_msm_cta; falls back to 1 when a group's combs do not fit one SM).
+  // Measured, 2^16 CMZ proofs from pinned buffers: 47.2 ms (0), 35.0 ms (1) -- profiles/configs_r02_s1_*.json
+  int prove_comb = 2;
+  // one small MSM (zkp_msm_vartime / zkp_batch_verify / zkp_msm_vartime_dev with few terms): up to this many terms skip the
+  // sort pipeline and run as groups of four lanes over the terms (k_single_msm_vt) -- the reference's own size dispatch
+  // (n < 190 -> Straus, /root/reference/src/toolbox/verifier.rs:162-166 -> dalek edwards.rs [ext]); 0 = always Pippenger
+  int small_max = 1024;
+  int small_groups = 1024;    // at most this many four-lane groups share the terms
   int prove_piece = 2;        // CTA-staged comb kernel (prove_comb = 2): terms per unit (pv_make_units)
   int smem_optin = -1;        // cudaDevAttrMaxSharedMemoryPerBlockOptin, read once
   size_t cta_smem_set = 0;    // dynamic shared memory k_comb_msm_cta has been allowed so far
@@ -231,6 +238,12 @@ extern "C" int32_t zkp_ctx_set_option(zkp_ctx* ctx, const char* key, int64_t val
   } else if (!strcmp(key, "prove_comb")) {
     if (value < 0 || value > 2) return ZKP_ERR_SIZE;
     ctx->prove_comb = (int)value;
+  } else if (!strcmp(key, "small_max")) {
+    if (value < 0 || value > (1 << 20)) return ZKP_ERR_SIZE;
+    ctx->small_max = (int)value;
+  } else if (!strcmp(key, "small_groups")) {
+    if (value < 1 || value > (1 << 16)) return ZKP_ERR_SIZE;
+    ctx->small_groups = (int)value;
   } else if (!strcmp(key, "prove_piece")) {
     if (value < 1 || value > 64) return ZKP_ERR_SIZE;
     ctx->prove_piece = (int)value;
@@ -437,6 +450,38 @@ static bool use_fused_sort(const zkp_ctx* ctx, const msm_plan& pl) {
   return !ctx->profile && pl.sort == ctx->stream && ctx->fused_sort;
 }
 
+// few terms: decompress, fold the scalars, groups of four lanes over the terms, one block adds and encodes (4 launches)
+static bool use_small_path(const zkp_ctx* ctx, size_t n) {
+  return n > 0 && n <= (size_t)ctx->small_max && !ctx->profile && !ctx->window;   // a forced window asks for the pipeline
+}
+static int32_t msm_small_launch(zkp_ctx* ctx, const void* d_scalars, const void* d_points, size_t n, msm_result* d_result) {
+  cudaStream_t st = ctx->stream;
+  const uint32_t G = (uint32_t)(n < (size_t)ctx->small_groups ? n : (size_t)ctx->small_groups);
+  ENSURE(ctx, ctx->niels, n * 96 + 96);
+  ENSURE(ctx, ctx->sk0, n * 32 + 32);
+  ENSURE(ctx, ctx->sk1, n * 32 + 32);
+  ENSURE(ctx, ctx->partials, (size_t)G * 128);
+  ENSURE(ctx, ctx->flags, 16);
+  ctx->live_valid = false;
+  ctx->last_window = 0;
+  ctx->last_lanes = 0;
+  k_init_flags<<<1, 1, 0, st>>>((int*)ctx->flags.p);
+  LAUNCH_CHECK(ctx);
+  const unsigned nb = (unsigned)((n + 255) / 256);
+  k_decompress_valid<<<nb, 256, 0, st>>>((const uint4*)d_points, n, (uint4*)ctx->niels.p);
+  LAUNCH_CHECK(ctx);
+  k_prep_scalars_vt<<<nb, 256, 0, st>>>((const uint4*)d_scalars, n, (uint4*)ctx->sk0.p, (uint4*)ctx->sk1.p);
+  LAUNCH_CHECK(ctx);
+  k_single_msm_vt<<<(4 * G + 63) / 64, 64, 0, st>>>((const uint32_t*)ctx->sk0.p, (const uint32_t*)ctx->sk1.p,
+                                                    (const uint4*)ctx->niels.p, n, G, (uint4*)ctx->partials.p,
+                                                    (int*)ctx->flags.p);
+  LAUNCH_CHECK(ctx);
+  k_single_finish<<<1, 128, 0, st>>>((const uint4*)ctx->partials.p, G, (const int*)ctx->flags.p, d_result,
+                                     (uint4*)ctx->partial_out);
+  LAUNCH_CHECK(ctx);
+  return ZKP_OK;
+}
+
 static int32_t msm_vartime_launch(zkp_ctx* ctx, const void* d_scalars, const void* d_points, size_t n,
                                   msm_result* d_result) {
   cudaStream_t st = ctx->stream;
@@ -445,6 +490,7 @@ static int32_t msm_vartime_launch(zkp_ctx* ctx, const void* d_scalars, const voi
     LAUNCH_CHECK(ctx);
     return ZKP_OK;
   }
+  if (use_small_path(ctx, n)) return msm_small_launch(ctx, d_scalars, d_points, n, d_result);
   msm_plan pl;
   int32_t r = msm_prepare(ctx, n, &pl);
   if (r != ZKP_OK) return r;
@@ -703,6 +749,19 @@ static int32_t msm_from_host(zkp_ctx* ctx, const hseg* sc_segs, const hseg* pt_s
   }
   ENSURE(ctx, ctx->in_scalars, n * 32);
   ENSURE(ctx, ctx->in_points, n * 32);
+  if (use_small_path(ctx, n)) {   // few terms: copies and kernels on the one stream
+    size_t off = 0;
+    for (int k = 0; k < nseg; k++) {
+      if (sc_segs[k].cnt) {
+        CUDA_TRY(ctx, cudaMemcpyAsync((uint8_t*)ctx->in_scalars.p + off * 32, sc_segs[k].p, sc_segs[k].cnt * 32,
+                                      cudaMemcpyHostToDevice, st));
+        CUDA_TRY(ctx, cudaMemcpyAsync((uint8_t*)ctx->in_points.p + off * 32, pt_segs[k].p, pt_segs[k].cnt * 32,
+                                      cudaMemcpyHostToDevice, st));
+      }
+      off += sc_segs[k].cnt;
+    }
+    return msm_small_launch(ctx, ctx->in_scalars.p, ctx->in_points.p, n, d_result);
+  }
   if (!ctx->copy_stream) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   if (ctx->profile) {   // per-stage timing wants the stages back to back: copy everything first, then one pass
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
@@ -921,6 +980,49 @@ extern "C" int32_t zkp_partials_verdict(zkp_ctx* ctx, const uint64_t* partial_li
   int32_t r = fetch_result(ctx, enc_out32, &ident, nullptr);
   if (r != ZKP_OK) return r;
   *accept = ident;
+  return ZKP_OK;
+}
+
+// device-resident forms: the partial sum stays on the device (160 bytes of limbs), so the all-gather of the shards' sums
+// (NCCL, on the same stream) and the verdict follow without a host round trip
+extern "C" int32_t zkp_msm_vartime_partial_dev(zkp_ctx* ctx, const void* d_scalars, const void* d_points, size_t n,
+                                               void* d_result, void* d_partial_limbs) {
+  if (!ctx || !d_result || !d_partial_limbs || (n && (!d_scalars || !d_points))) return ZKP_ERR_SIZE;
+  if (!aligned16(d_scalars) || !aligned16(d_points) || !aligned16(d_result) || !aligned16(d_partial_limbs)) {
+    ctx->err = "device pointers must be 16-byte aligned";
+    return ZKP_ERR_SIZE;
+  }
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  ENSURE(ctx, ctx->partial_buf, 128 + 160);
+  cudaStream_t st = ctx->stream;
+  if (n == 0) {   // the empty sum: the identity (0 : 1 : 1 : 0)
+    uint64_t ident[20] = {0};
+    ident[5] = 1;
+    ident[10] = 1;
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_partial_limbs, ident, 160, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));   // `ident` is on this stack frame
+    k_empty_result<<<1, 1, 0, st>>>((msm_result*)d_result);
+    LAUNCH_CHECK(ctx);
+    return ZKP_OK;
+  }
+  ctx->partial_out = ctx->partial_buf.p;
+  int32_t r = msm_vartime_launch(ctx, d_scalars, d_points, n, (msm_result*)d_result);
+  ctx->partial_out = nullptr;
+  if (r != ZKP_OK) return r;
+  k_ext_to_limbs<<<1, 1, 0, st>>>((const uint4*)ctx->partial_buf.p, (unsigned long long*)d_partial_limbs);
+  LAUNCH_CHECK(ctx);
+  return ZKP_OK;
+}
+
+extern "C" int32_t zkp_partials_verdict_dev(zkp_ctx* ctx, const void* d_partial_limbs, size_t count, void* d_result) {
+  if (!ctx || !d_result || (count && !d_partial_limbs)) return ZKP_ERR_SIZE;
+  if (!aligned16(d_partial_limbs) || !aligned16(d_result)) {
+    ctx->err = "device pointers must be 16-byte aligned";
+    return ZKP_ERR_SIZE;
+  }
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  k_sum_partials<<<1, 1, 0, ctx->stream>>>((const unsigned long long*)d_partial_limbs, count, (msm_result*)d_result);
+  LAUNCH_CHECK(ctx);
   return ZKP_OK;
 }
 
@@ -1341,7 +1443,7 @@ static int32_t prove_batch_impl(zkp_ctx* ctx, const zkp_statement_desc* sd, cons
                                                                          (uint32_t*)ctx->sk0.p);
         LAUNCH_CHECK(ctx);
         if (cta_smem > ctx->cta_smem_set) {
-          CUDA_TRY(ctx, cudaFuncSetAttribute(k_comb_msm_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cta_smem));
+          CUDA_TRY(ctx, cudaFuncSetAttribute((const void*)k_comb_msm_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cta_smem));
           ctx->cta_smem_set = cta_smem;
         }
         const unsigned nw = n_units < 16 ? (unsigned)n_units : 16u;

@@ -121,6 +121,96 @@ __global__ void __launch_bounds__(64) k_small_msm_vt(const uint32_t* __restrict_
   status[j] = 0;
 }
 
+// ---- one small MSM (the reference's n < 190 Straus dispatch: verifier.rs:162-166 -> dalek edwards.rs [ext]) ----------
+// zkp_msm_vartime / zkp_batch_verify with few terms must not pay for the sort pipeline (21 launches, bucket reduction
+// levels): G groups of four lanes take the terms g, g + G, ... each (doublings shared by the four lanes as in
+// k_small_msm_vt<true>), write their partial sums, and k_single_finish adds them, encodes and fills the msm_result.
+// Inputs as prepared by k_decompress_valid / k_prep_scalars_vt (invalid point: zero first element; bad scalar: word 7 = ~0).
+__global__ void __launch_bounds__(64) k_single_msm_vt(const uint32_t* __restrict__ kk, const uint32_t* __restrict__ k3,
+                                                      const uint4* __restrict__ niels, size_t n, uint32_t G,
+                                                      uint4* __restrict__ partials, int* __restrict__ flags) {
+  const size_t thread = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t g = thread >> 2;
+  const int sub = (int)(threadIdx.x & 3);
+  const int gbase = (int)(threadIdx.x & 31 & ~3);
+  const unsigned gmask = 0xfu << gbase;
+  if (g >= G) return;          // the four lanes of a group leave together
+  bool ok = true;
+  for (size_t t = g; t < n; t += G) {
+    uint4 first = __ldg(niels + 6 * t), second = __ldg(niels + 6 * t + 1);
+    if ((first.x | first.y | first.z | first.w | second.x | second.y | second.z | second.w) == 0) {
+      if (sub == 0) atomicMin(&flags[0], (int)t);
+      ok = false;
+    }
+    if (__ldg(kk + 8 * t + 7) == 0xffffffffu) {
+      if (sub == 0) atomicMin(&flags[1], (int)t);
+      ok = false;
+    }
+  }
+  ge_ext acc;
+  ge_identity(acc);
+  bool started = false;
+  if (ok) {
+    for (int i = 253; i >= 0; i--) {
+      if (started) ge_double_coop4(acc, sub, gmask, gbase);
+      const int b = i + 1, wi = b >> 5, sh = b & 31;
+      for (size_t t = g; t < n; t += G) {
+        uint32_t w3 = __ldg(k3 + 8 * t + wi), w1 = __ldg(kk + 8 * t + wi);
+        if (wi == 7) w1 &= 0x7fffffffu;
+        int d = (int)((w3 >> sh) & 1u) - (int)((w1 >> sh) & 1u);
+        if (d != 0) {
+          uint32_t neg = (__ldg(kk + 8 * t + 7) >> 31) ^ (d < 0 ? 1u : 0u);
+          ge_aniels q;
+          load_aniels(q, niels, (uint32_t)t);
+          ge_aniels_cneg(q, neg);
+          ge_madd_coop4(acc, q, sub, gmask, gbase);
+          started = true;
+        }
+      }
+    }
+  }
+  if (sub == 0) store_ext(partials + 8 * g, acc);
+}
+
+// one block of 128 threads: sum of the G partial sums, ristretto encode, status (the layout k_finish writes)
+__global__ void __launch_bounds__(128) k_single_finish(const uint4* __restrict__ partials, uint32_t G,
+                                                       const int* __restrict__ flags, msm_result* __restrict__ res,
+                                                       uint4* __restrict__ partial_out) {
+  __shared__ uint4 sm[4 * 8];
+  ge_ext acc, p;
+  ge_identity(acc);
+  for (uint32_t i = threadIdx.x; i < G; i += blockDim.x) {
+    load_ext(p, partials + (size_t)i * 8);
+    ge_add(acc, acc, p);
+  }
+#pragma unroll 1
+  for (int off = 16; off >= 1; off >>= 1) {
+    shfl_down_ext(p, acc, off, 32);
+    ge_add(acc, acc, p);
+  }
+  if ((threadIdx.x & 31) == 0) store_ext(sm + (threadIdx.x >> 5) * 8, acc);
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  for (int k = 1; k < 4; k++) {
+    load_ext(p, sm + k * 8);
+    ge_add(acc, acc, p);
+  }
+  if (partial_out) store_ext(partial_out, acc);
+  uint32_t enc[8];
+  ristretto_encode(enc, acc);
+  uint32_t z = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) { res->enc[i] = enc[i]; z |= enc[i]; }
+  const int bad_pt = flags[0], bad_sc = flags[1];
+  int status = 0;
+  long long first_bad = -1;
+  if (bad_pt != 0x7fffffff) { status = 1; first_bad = bad_pt; }
+  else if (bad_sc != 0x7fffffff) { status = 3; first_bad = bad_sc; }
+  res->status = status;
+  res->is_identity = (z == 0) ? 1 : 0;
+  res->first_bad = first_bad;
+}
+
 // ---- constant-time path ----------------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(256) k_decompress_ext(const uint4* __restrict__ enc, size_t n, uint4* __restrict__ ext,

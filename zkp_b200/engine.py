@@ -113,6 +113,17 @@ class Engine:
                                                   ctypes.c_void_p(d_points_ptr), int(n),
                                                   ctypes.c_void_p(d_result_ptr)))
 
+    def msm_vartime_partial_dev(self, d_scalars_ptr, d_points_ptr, n, d_result_ptr, d_partial_ptr):
+        """msm_vartime_dev that also leaves the sum as a 160-byte limb-form point at d_partial_ptr (single-verdict mode)."""
+        self._check(self._lib.zkp_msm_vartime_partial_dev(self._ctx, ctypes.c_void_p(d_scalars_ptr),
+                                                          ctypes.c_void_p(d_points_ptr), int(n),
+                                                          ctypes.c_void_p(d_result_ptr), ctypes.c_void_p(d_partial_ptr)))
+
+    def partials_verdict_dev(self, d_partials_ptr, count, d_result_ptr):
+        """Sum of `count` 160-byte limb-form points on the device -> the 48-byte result record (asynchronous)."""
+        self._check(self._lib.zkp_partials_verdict_dev(self._ctx, ctypes.c_void_p(d_partials_ptr), int(count),
+                                                       ctypes.c_void_p(d_result_ptr)))
+
     def batch_verify(self, static_coeffs, static_points, instance_coeffs, instance_points, rows, batch):
         """Returns (accept: bool, status).  status ZKP_ERR_POINT == VerificationFailure from a bad encoding."""
         sc, sp = _u8(static_coeffs, 32), _u8(static_points, 32)

@@ -16,6 +16,7 @@ SYMBOLS = [
     "zkp_ctx_synchronize", "zkp_last_error", "zkp_ctx_launch_count", "zkp_decompress_batch", "zkp_compress_batch",
     "zkp_msm_vartime", "zkp_msm_vartime_dev", "zkp_msm_vartime_batched", "zkp_msm_ct_batched", "zkp_batch_verify",
     "zkp_bench_field", "zkp_ctx_stage_ms", "zkp_bench_dual", "zkp_batch_verify_proofs", "zkp_selftest_hash", "zkp_prove_batch", "zkp_batch_verify_partial", "zkp_partials_verdict", "zkp_selftest_bv_script", "zkp_selftest_chunk_schedule",
+    "zkp_msm_vartime_partial_dev", "zkp_partials_verdict_dev",
 ]
 
 _lib = None
@@ -73,6 +74,10 @@ def load():
     lib.zkp_batch_verify_partial.restype = c_int32
     lib.zkp_partials_verdict.argtypes = [c_void_p, c_void_p, c_size_t, P(c_int32), c_void_p]
     lib.zkp_partials_verdict.restype = c_int32
+    lib.zkp_msm_vartime_partial_dev.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]
+    lib.zkp_msm_vartime_partial_dev.restype = c_int32
+    lib.zkp_partials_verdict_dev.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.zkp_partials_verdict_dev.restype = c_int32
     lib.zkp_bench_field.argtypes = [c_void_p, c_int32, c_int32, P(ctypes.c_double)]
     lib.zkp_bench_field.restype = c_int32
     lib.zkp_bench_dual.argtypes = [c_void_p, c_int32, c_int32, P(ctypes.c_double)]
