@@ -142,6 +142,10 @@ typedef struct {
  * transcript every proof starts from (user transcript + dom-sep + scalar labels; zkp_b200_host.h produces it).
  * instance_enc[ni][N][32], common_enc[nc][32], commitments[N][k][32], responses[N][m][32], rho_seed[32]: the
  * weights are rho_(i,j) = bytes [16i,16i+16) of SHAKE256(rho_seed || le64(j)) (stand-in for thread_rng).
+ * rho_seed may be NULL: the library then draws it from the OS CSPRNG for this call (the deployment default).  A seed
+ * that is passed must itself be fresh, secret CSPRNG output per call and per shard of a sharded batch -- with weights
+ * a prover can predict (constant, reused or public seed) responses can be chosen so that the weighted errors cancel,
+ * and the batch check is void.
  * coeff_out / points_out (optional, n = nc + (ni+k)*N rows of 32 bytes) receive the MSM inputs for parity tests.
  * Returns ZKP_ERR_POINT for an identity or undecodable encoding (VerificationFailure), ZKP_ERR_SCALAR for a
  * non-canonical response, ZKP_ERR_SIZE if the statement exceeds 40 point variables per kind or 64 constraints.  */
@@ -179,7 +183,10 @@ int32_t zkp_partials_verdict_dev(zkp_ctx* ctx, const void* d_partial_limbs, size
  * allocation order instance ++ common), entropy[N][32] -> encodings_out[N][p][32], commitments_out[N][k][32],
  * responses_out[N][m][32]; blindings_out[N][m][32] optional (parity tests).  prefix_state as for
  * zkp_batch_verify_proofs.  Proof j equals what the reference's prover produces from the same transcript, secrets and
- * entropy.  Batches larger than the "prove_chunk" option (default 2^17 proofs) run as slices over one workspace.
+ * entropy.  entropy may be NULL: 32 fresh bytes per proof then come from the OS CSPRNG (the deployment default); entropy
+ * that is passed must be fresh and secret (a repeated value repeats nonces and reveals the witnesses).  Batches of at
+ * least 2^15 proofs run as slices of 2^14 ("prove_pipe_chunk") alternating between two workspaces and streams, so the
+ * copies of one slice overlap the kernels of the next; outputs are written only after the slice's checks have passed.
  * Returns ZKP_ERR_SCALAR for a non-canonical secret.                                                               */
 int32_t zkp_prove_batch(zkp_ctx* ctx, const zkp_statement_desc* st, const uint32_t* prefix_state, size_t N,
                         const uint8_t* secrets, const uint64_t* points, const uint8_t* entropy, uint8_t* encodings_out,

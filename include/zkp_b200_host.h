@@ -8,6 +8,14 @@
  * A statement is described by flat arrays (what define_proof!{name, label, (secrets), (instance), (common) : ...}
  * expands to): NUL-separated label strings and constraints in CSR form; point indices run over instance ++ common.
  * Return values are the reference's ProofError: 0 Ok, 1 VerificationFailure, 2 BatchSizeMismatch, 3 engine failure.
+ *
+ * RANDOMNESS.  The reference draws from rand::thread_rng(): 32 bytes of prover entropy per proof (prover.rs:82) and the
+ * 128-bit weights of verify_batchable / batch_verify (verifier.rs:153, batch_verifier.rs:179).  Every `rng_seed`,
+ * `rho_seed32` and `entropy` argument below may be NULL: the library then draws fresh bytes from the OS CSPRNG
+ * (getrandom) for that call -- the default a deployment wants.  A seed that IS passed is used as is, for reproducible
+ * tests and benches; it must then itself be fresh, secret CSPRNG output, per call and per shard of a sharded batch:
+ * weights the prover can predict (a constant, reused or public seed) let a forger pick responses whose weighted errors
+ * cancel, which voids batch soundness, and a repeated prover seed repeats nonces, which reveals witnesses.
  */
 #ifndef ZKP_B200_HOST_H
 #define ZKP_B200_HOST_H
@@ -52,6 +60,15 @@ int32_t zkph_batch_verify(zkp_ctx* ctx, const zkph_statement* st, const uint8_t*
                           const uint8_t* responses, const uint8_t* rng_seed, size_t seed_len, int32_t threads,
                           uint8_t* coeff_out, uint8_t* points_out, double* host_seconds /* hashing+fold, may be NULL */);
 
+/* module::batch_verify with the reference's own signature: one transcript handle per proof (each with its own prior
+ * state; every handle is left advanced, like the reference's `&mut Transcript`s).  n_transcripts != n_proofs is
+ * BatchSizeMismatch (batch_verifier.rs:72-74).                                                                         */
+typedef struct zkph_transcript zkph_transcript;
+int32_t zkph_batch_verify_t(zkp_ctx* ctx, const zkph_statement* st, zkph_transcript* const* transcripts,
+                            size_t n_transcripts, size_t n_proofs, const uint8_t* instance_enc, const uint8_t* common_enc,
+                            const uint8_t* commitments, const uint8_t* responses, const uint8_t* rng_seed, size_t seed_len,
+                            int32_t threads);
+
 /* module::batch_verify with the per-proof work on the DEVICE (SURVEY.md 8f rows f1 + f2): the host hashes only the
  * batch-wide transcript prefix (user transcript + dom-sep + scalar labels) and hands everything else to
  * zkp_batch_verify_proofs.  Same inputs as zkph_batch_verify; the weights are derived per proof from rho_seed[32]
@@ -94,7 +111,6 @@ int32_t zkph_batchable_proofs_parse(const uint8_t* buf, size_t len, size_t N, si
 /* merlin::Transcript handles, for callers that drive the transcript themselves the way the reference's API takes
  * `&mut Transcript` (e.g. /root/reference/tests/sig_and_vrf_example.rs:86-125: messages are appended before proving).
  * The *_t entry points below mutate the handle exactly like the reference mutates its transcript.               */
-typedef struct zkph_transcript zkph_transcript;
 zkph_transcript* zkph_transcript_new(const uint8_t* label, size_t len);
 zkph_transcript* zkph_transcript_clone(const zkph_transcript* t);
 void zkph_transcript_free(zkph_transcript* t);

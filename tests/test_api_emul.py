@@ -220,9 +220,11 @@ def test_prove_batch_and_verify_from_proof_bytes_through_the_emulated_abi(api):
 
     try:
         # prove_comb: 0 = Straus tables, 1 = combs scanned from global memory, 2 = combs staged in shared memory (default)
-        for comb, share, chunk in ((0, 1, 1 << 17), (1, 1, 1 << 17), (1, 0, 1 << 17), (1, 1, 2), (0, 0, 2), (2, 1, 1 << 17),
-                                   (2, 0, 2)):
-            for key, v in ((b"prove_comb", comb), (b"share_static_tables", share), (b"prove_chunk", chunk)):
+        # pipe = 1: slices of one proof alternating between the two workspaces / streams of the pipelined prover
+        for comb, share, chunk, pipe in ((0, 1, 1 << 17, 0), (1, 1, 1 << 17, 0), (1, 0, 1 << 17, 0), (1, 1, 2, 0), (0, 0, 2, 0),
+                                         (2, 1, 1 << 17, 0), (2, 0, 2, 0), (2, 1, 1 << 17, 1)):
+            for key, v in ((b"prove_comb", comb), (b"share_static_tables", share), (b"prove_chunk", chunk),
+                           (b"prove_pipe_chunk", pipe)):
                 assert api.zkp_ctx_set_option(api.ctx, key, v) == 0
             rc, enc, com, resp = prove()
             assert rc == 0, (comb, share, chunk)
@@ -232,7 +234,7 @@ def test_prove_batch_and_verify_from_proof_bytes_through_the_emulated_abi(api):
                 assert [bytes(r) for r in resp[j]] == [S.to_bytes(r) for r in proof.responses]
                 assert [bytes(e) for e in enc[j]] == [oenc[n] for n in names]
     finally:
-        for key, v in ((b"prove_comb", 2), (b"share_static_tables", 1), (b"prove_chunk", 1 << 17)):
+        for key, v in ((b"prove_comb", 2), (b"share_static_tables", 1), (b"prove_chunk", 1 << 17), (b"prove_pipe_chunk", 1 << 14)):
             api.zkp_ctx_set_option(api.ctx, key, v)
     # ---- verification of those proofs from their bytes ----
     seed = bytes(range(32))

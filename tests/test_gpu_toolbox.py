@@ -375,11 +375,22 @@ def test_prove_many_device_comb_path_matches_straus_path(engine):
             engine.set_option("prove_chunk", 33)
             assert same(st.prove_many_device(engine, b"CMZ", sec_arr, pts_arr, entropy), want), (comb, piece)
             engine.set_option("prove_chunk", 1 << 17)
+            # the pipelined prover: slices of 16 proofs (the last one ragged) alternating between two workspaces and
+            # streams; a batch whose common points differ in the LAST slice is redone without sharing
+            engine.set_option("prove_pipe_chunk", 16)
+            for stagger in (0, 3000):
+                engine.set_option("prove_stagger_ns", stagger)
+                assert same(st.prove_many_device(engine, b"CMZ", sec_arr, pts_arr, entropy), want), (comb, piece, stagger)
+            assert same(st.prove_many_device(engine, b"CMZ", mixed_sec, mixed_pts, entropy), want_mixed), (comb, piece)
+            engine.set_option("prove_stagger_ns", 0)
+            engine.set_option("prove_pipe_chunk", 1 << 14)
     finally:
         engine.set_option("prove_comb", 2)
         engine.set_option("prove_piece", 2)
         engine.set_option("share_static_tables", 1)
         engine.set_option("prove_chunk", 1 << 17)
+        engine.set_option("prove_pipe_chunk", 1 << 14)
+        engine.set_option("prove_stagger_ns", 0)
 
 
 def test_compiled_transcript_script_equals_bytewise_strobe(engine):

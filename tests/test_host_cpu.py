@@ -55,7 +55,7 @@ def test_statement_descriptor_matches_oracle():
 def test_wire_format_matches_oracle_and_rejects_what_bincode_rejects():
     """bincode layout of src/proofs.rs (tests/zkp.rs:53-54, :96-97): serialize / parse round trips against the oracle's
     restatement, sizes 32 + 8 + 32m and 8 + 32k + 8 + 32m, and the refusals: truncated input, trailing bytes,
-    non-canonical scalars (MalformedProof), wrong counts (VerificationFailure / BatchSizeMismatch like the verifiers)."""
+    non-canonical scalars (MalformedProof), wrong counts (VerificationFailure like the verifiers)."""
     import numpy as np
     import pytest
     rnd = random.Random(12)
@@ -89,14 +89,14 @@ def test_wire_format_matches_oracle_and_rejects_what_bincode_rejects():
         PT.parse_batchable_many(bytes(bad), N, k, m, threads=2)
     with pytest.raises(ValueError):
         OT.parse_batchable(bytes(bad), 5 * (8 + 32 * k + 8 + 32 * m))
-    # a proof with another shape inside the batch: BatchSizeMismatch (batch_verifier.rs:138-148), also when the total
-    # length happens to fit
+    # a proof with another shape inside the batch: VerificationFailure (batch_verifier.rs:142-148; BatchSizeMismatch is
+    # only proofs.len() != batch_size), also when the total length happens to fit
     odd = OT.BatchableProof(proofs[0].commitments[:-1], proofs[0].responses + [5])
     mixed = OT.serialize_batchable(odd) + b"".join(OT.serialize_batchable(p) for p in proofs[1:])
     assert len(mixed) == len(blob)
-    with pytest.raises(PT.BatchSizeMismatch):
+    with pytest.raises(PT.VerificationFailure):
         PT.parse_batchable_many(mixed, N, k, m, threads=2)
-    with pytest.raises(PT.BatchSizeMismatch):
+    with pytest.raises(PT.VerificationFailure):
         PT.parse_batchable_many(blob, N, k - 1, m + 1)
     # length prefixes that exceed the input
     with pytest.raises(PT.MalformedProof):

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <sys/random.h>
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
@@ -26,6 +27,26 @@ struct devbuf {
   void* p = nullptr;
   size_t cap = 0;
 };
+
+// workspace + stream of one slice of the batch prover (two of them alternate: zkp_prove_batch)
+struct pv_set {
+  devbuf pv_misc, pv_limbs, pv_enc, pv_sec, pv_ent, pv_state, pv_blind, pv_resp, in_scalars, niels, tables, sk0, aux0, aux1,
+      multi, flags, pv_static;
+  cudaStream_t stream = nullptr;       // set 0: the context's stream; set 1: own_stream
+  cudaStream_t own_stream = nullptr;
+  int* h_flags = nullptr;              // pinned, 64 bytes
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+};
+
+static bool os_random_bytes(uint8_t* out, size_t n) {
+  while (n) {
+    ssize_t got = getrandom(out, n > 256 ? 256 : n, 0);
+    if (got <= 0) return false;
+    out += got;
+    n -= (size_t)got;
+  }
+  return true;
+}
 
 struct zkp_ctx {
   int device = 0;
@@ -64,7 +85,11 @@ struct zkp_ctx {
   int overlap = 0;   // measured: no gain on B200 (159.2 vs 159.9 ms per step), kept as an option
   int balance = 1;     // size-ordered work items in the bucket accumulation (equal-length items share a warp)
   void* partial_out = nullptr;   // when set, k_finish also stores the MSM result as an extended point (single-verdict mode)
-  size_t prove_chunk = (size_t)1 << 17;   // proofs per slice of zkp_prove_batch (4 GB of tables for CMZ)
+  size_t prove_chunk = (size_t)1 << 17;   // proofs per slice of zkp_prove_batch at most (workspace bound)
+  // batches of at least two such slices are pipelined: slices alternate between two buffer sets / streams, so the copies
+  // of one slice run under the kernels of the other (0 = off)
+  size_t prove_pipe_chunk = (size_t)1 << 14;
+  pv_set pvs[2];
   int coop_max_msms = 8192;  // batched small vartime MSMs: up to this many run with four lanes per MSM (latency)
   int phase1_percent = 50;   // share of the host-path point chunks decompressed under the histogram (first phase)
   int share_static_tables = 1;   // batch proving: one constant-time table per batch-static point
@@ -78,6 +103,7 @@ struct zkp_ctx {
   // (n < 190 -> Straus, /root/reference/src/toolbox/verifier.rs:162-166 -> dalek edwards.rs [ext]); 0 = always Pippenger
   int small_max = 1024;
   int small_groups = 1024;    // at most this many four-lane groups share the terms
+  int prove_stagger_ns = 0;   // CTA-staged comb kernel: start offset between the warps of one scheduler (0 = none)
   int prove_piece = 2;        // CTA-staged comb kernel (prove_comb = 2): terms per unit (pv_make_units)
   int smem_optin = -1;        // cudaDevAttrMaxSharedMemoryPerBlockOptin, read once
   size_t cta_smem_set = 0;    // dynamic shared memory k_comb_msm_cta has been allowed so far
@@ -191,6 +217,16 @@ extern "C" void zkp_ctx_destroy(zkp_ctx* ctx) {
                     &ctx->pv_state, &ctx->pv_blind, &ctx->pv_resp, &ctx->pv_misc, &ctx->scan_tmp, &ctx->partial_buf, &ctx->pv_static};
   for (devbuf* b : bufs)
     if (b->p) cudaFree(b->p);
+  for (pv_set& S : ctx->pvs) {
+    devbuf* sb[] = {&S.pv_misc, &S.pv_limbs, &S.pv_enc, &S.pv_sec, &S.pv_ent, &S.pv_state, &S.pv_blind, &S.pv_resp,
+                    &S.in_scalars, &S.niels, &S.tables, &S.sk0, &S.aux0, &S.aux1, &S.multi, &S.flags, &S.pv_static};
+    for (devbuf* b : sb)
+      if (b->p) cudaFree(b->p);
+    if (S.h_flags) cudaFreeHost(S.h_flags);
+    if (S.ev_fork) cudaEventDestroy(S.ev_fork);
+    if (S.ev_join) cudaEventDestroy(S.ev_join);
+    if (S.own_stream) cudaStreamDestroy(S.own_stream);
+  }
   if (ctx->h_result) cudaFreeHost(ctx->h_result);
   for (cudaEvent_t e : ctx->chunk_ev) cudaEventDestroy(e);
   for (int i = 0; i < 10; i++)
@@ -233,6 +269,9 @@ extern "C" int32_t zkp_ctx_set_option(zkp_ctx* ctx, const char* key, int64_t val
   } else if (!strcmp(key, "prove_chunk")) {
     if (value < 1) return ZKP_ERR_SIZE;
     ctx->prove_chunk = (size_t)value;
+  } else if (!strcmp(key, "prove_pipe_chunk")) {
+    if (value < 0) return ZKP_ERR_SIZE;
+    ctx->prove_pipe_chunk = (size_t)value;
   } else if (!strcmp(key, "share_static_tables")) {
     ctx->share_static_tables = value ? 1 : 0;
   } else if (!strcmp(key, "prove_comb")) {
@@ -244,6 +283,9 @@ extern "C" int32_t zkp_ctx_set_option(zkp_ctx* ctx, const char* key, int64_t val
   } else if (!strcmp(key, "small_groups")) {
     if (value < 1 || value > (1 << 16)) return ZKP_ERR_SIZE;
     ctx->small_groups = (int)value;
+  } else if (!strcmp(key, "prove_stagger_ns")) {
+    if (value < 0 || value > 200000) return ZKP_ERR_SIZE;
+    ctx->prove_stagger_ns = (int)value;
   } else if (!strcmp(key, "prove_piece")) {
     if (value < 1 || value > 64) return ZKP_ERR_SIZE;
     ctx->prove_piece = (int)value;
@@ -1110,8 +1152,16 @@ static int32_t batch_verify_proofs_impl(zkp_ctx* ctx, const zkp_statement_desc* 
                                         const uint8_t* commitments, const uint8_t* responses,
                                         const uint8_t* rho_seed, int32_t* accept, int64_t* first_bad,
                                         uint8_t* coeff_out, uint8_t* points_out) {
-  if (!ctx || !sd || !prefix_state || !accept || !rho_seed) return ZKP_ERR_SIZE;
+  if (!ctx || !sd || !prefix_state || !accept) return ZKP_ERR_SIZE;
   *accept = 0;
+  uint8_t own_seed[32];
+  if (!rho_seed) {   // no seed: the weights' seed comes from the OS CSPRNG, fresh for this call (batch_verifier.rs:179 thread_rng)
+    if (!os_random_bytes(own_seed, 32)) {
+      ctx->err = "getrandom failed";
+      return ZKP_ERR_CUDA;
+    }
+    rho_seed = own_seed;
+  }
   if (first_bad) *first_bad = -1;
   const int m = sd->m, ni = sd->ni, nc = sd->nc, k = sd->k;
   if (!statement_ok(sd)) {
@@ -1274,37 +1324,29 @@ extern "C" int32_t zkp_batch_verify_proofs(zkp_ctx* ctx, const zkp_statement_des
 // ---------------------------------------------------------------------------------------------------------
 // batch proving: N proofs of one statement, per-proof transcript / nonce / response work on the device
 // ---------------------------------------------------------------------------------------------------------
-static int32_t prove_batch_impl(zkp_ctx* ctx, const zkp_statement_desc* sd, const uint32_t* prefix_state, size_t N,
-                                const uint8_t* secrets, const uint64_t* points, const uint8_t* entropy,
-                                uint8_t* encodings_out, uint8_t* commitments_out, uint8_t* responses_out,
-                                uint8_t* blindings_out) {
-  if (!ctx || !sd || !prefix_state) return ZKP_ERR_SIZE;
-  if (!statement_ok(sd) || sd->ni + sd->nc > 2 * ZKP_BV_MAX_VARS) {
-    ctx->err = "inconsistent or oversized statement description";
-    return ZKP_ERR_SIZE;
-  }
+// One slice of a batch on one buffer set: everything up to the flags' way back is enqueued on the set's stream by
+// prove_slice_enqueue; prove_slice_complete waits for it, reads the flags and only then lets the outputs leave the device.
+// Two sets alternate, so the H2D copies of slice i + 1 and the D2H copies of slice i - 1 overlap the kernels of slice i.
+struct pv_slice {
+  size_t N = 0;
+  const uint8_t* secrets = nullptr;
+  const uint64_t* points = nullptr;
+  const uint8_t* entropy = nullptr;
+  uint8_t *encodings_out = nullptr, *commitments_out = nullptr, *responses_out = nullptr, *blindings_out = nullptr;
+  bool share = false;
+};
+#define ZKP_PV_NOT_UNIFORM 1000   // internal: a "common" point differed between proofs while its table was shared
+
+static int32_t prove_slice_enqueue(zkp_ctx* ctx, pv_set& S, const zkp_statement_desc* sd, const uint32_t* prefix_state,
+                                   pv_slice& sl, bool share_allowed) {
+  const size_t N = sl.N;
+  const uint8_t* secrets = sl.secrets;
+  const uint64_t* points = sl.points;
+  const uint8_t* entropy = sl.entropy;
   const int m = sd->m, ni = sd->ni, nc = sd->nc, k = sd->k, p = ni + nc;
-  if (!N) return ZKP_OK;
-  if ((m && (!secrets || !responses_out)) || (p && (!points || !encodings_out)) || (k && !commitments_out) || !entropy)
-    return ZKP_ERR_SIZE;
   const int n_terms = k ? sd->cons_off[k] : 0;
-  // large batches run as slices of at most `prove_chunk` proofs: the constant-time tables take 1 KB per term
-  // (31 KB per CMZ proof), and the slices reuse one workspace
-  if (N > ctx->prove_chunk) {
-    for (size_t lo = 0; lo < N; lo += ctx->prove_chunk) {
-      const size_t cnt = N - lo < ctx->prove_chunk ? N - lo : ctx->prove_chunk;
-      int32_t rc = zkp_prove_batch(ctx, sd, prefix_state, cnt, secrets ? secrets + lo * (size_t)m * 32 : nullptr,
-                                   points ? points + lo * (size_t)p * 20 : nullptr, entropy + lo * 32,
-                                   encodings_out ? encodings_out + lo * (size_t)p * 32 : nullptr,
-                                   commitments_out ? commitments_out + lo * (size_t)k * 32 : nullptr,
-                                   responses_out ? responses_out + lo * (size_t)m * 32 : nullptr,
-                                   blindings_out ? blindings_out + lo * (size_t)m * 32 : nullptr);
-      if (rc != ZKP_OK) return rc;
-    }
-    return ZKP_OK;
-  }
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  cudaStream_t st = ctx->stream;
+  cudaStream_t st = S.stream;
   // ---- statement blob: prefix | label pool | label offsets/lengths | lhs | cons_off | term arrays | schedule slots ----
   std::vector<uint32_t> loff, llen;
   std::vector<uint8_t> pool;
@@ -1328,7 +1370,7 @@ static int32_t prove_batch_impl(zkp_ctx* ctx, const zkp_statement_desc* sd, cons
   // (points_are_uniform): their constant-time tables are built once and shared
   // (the caller passes a copy per proof, as the reference's per-proof assignments do: k_pv_gather compares every copy
   // with proof 0's on the device and the call is redone without sharing if one differs)
-  const bool share = ctx->share_static_tables && nc > 0 && N > 1;
+  const bool share = share_allowed && ctx->share_static_tables && nc > 0 && N > 1;
   // comb path: every point that serves as a base gets a comb slot -- shared (one comb per batch) for the batch-static
   // points when sharing is on, per proof otherwise (pv_plan.hpp)
   const bool comb = ctx->prove_comb && n_terms > 0;
@@ -1358,37 +1400,37 @@ static int32_t prove_batch_impl(zkp_ctx* ctx, const zkp_statement_desc* sd, cons
     memcpy(&blob[o_sh], term_shared.data(), (size_t)n_terms * 4);
   }
   const size_t total = N * (size_t)n_terms, M = N * (size_t)k;
-  ENSURE(ctx, ctx->pv_misc, blob_sz);
-  ENSURE(ctx, ctx->pv_limbs, N * (size_t)p * 160 + 160);
-  ENSURE(ctx, ctx->pv_enc, N * (size_t)p * 32 + 32);
-  ENSURE(ctx, ctx->pv_sec, N * (size_t)m * 32 + 32);
-  ENSURE(ctx, ctx->pv_ent, N * 32);
-  ENSURE(ctx, ctx->pv_state, N * 56 * 4);
-  ENSURE(ctx, ctx->pv_blind, N * (size_t)m * 32 + 32);
-  ENSURE(ctx, ctx->pv_resp, N * (size_t)m * 32 + 32);
-  ENSURE(ctx, ctx->in_scalars, total * 32 + 32);
-  ENSURE(ctx, ctx->niels, total * 128 + 128);
+  ENSURE(ctx, S.pv_misc, blob_sz);
+  ENSURE(ctx, S.pv_limbs, N * (size_t)p * 160 + 160);
+  ENSURE(ctx, S.pv_enc, N * (size_t)p * 32 + 32);
+  ENSURE(ctx, S.pv_sec, N * (size_t)m * 32 + 32);
+  ENSURE(ctx, S.pv_ent, N * 32);
+  ENSURE(ctx, S.pv_state, N * 56 * 4);
+  ENSURE(ctx, S.pv_blind, N * (size_t)m * 32 + 32);
+  ENSURE(ctx, S.pv_resp, N * (size_t)m * 32 + 32);
+  ENSURE(ctx, S.in_scalars, total * 32 + 32);
+  ENSURE(ctx, S.niels, total * 128 + 128);
   // Straus tables: one KB per term; combs: one KB per per-proof base; both interleaved in groups of 32 proofs
-  ENSURE(ctx, ctx->tables, ((N + 31) / 32 * 32) * (comb ? U : (size_t)n_terms) * 1024 + 1024);
-  ENSURE(ctx, ctx->sk0, ((N + 31) / 32 * 32) * (size_t)n_terms * 32 + 32);   // group-interleaved when CTA-staged
-  ENSURE(ctx, ctx->aux0, (M + 1) * 8);
-  ENSURE(ctx, ctx->aux1, M * 32 + 32);
-  ENSURE(ctx, ctx->multi, M * 4 + 16);
-  ENSURE(ctx, ctx->flags, 16);
+  ENSURE(ctx, S.tables, ((N + 31) / 32 * 32) * (comb ? U : (size_t)n_terms) * 1024 + 1024);
+  ENSURE(ctx, S.sk0, ((N + 31) / 32 * 32) * (size_t)n_terms * 32 + 32);   // group-interleaved when CTA-staged
+  ENSURE(ctx, S.aux0, (M + 1) * 8);
+  ENSURE(ctx, S.aux1, M * 32 + 32);
+  ENSURE(ctx, S.multi, M * 4 + 16);
+  ENSURE(ctx, S.flags, 16);
   // comb path, CTA-staged (k_comb_msm_cta): needs its tables and unit sums to fit the shared memory of one SM
   const size_t n_units = plan.unit_term0.size();
   const size_t cta_smem = comb ? comb_cta_smem_bytes(U, Us, n_units) : 0;
   if (comb && ctx->prove_comb >= 2 && ctx->smem_optin < 0)
     CUDA_TRY(ctx, cudaDeviceGetAttribute(&ctx->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
   const bool cta = comb && ctx->prove_comb >= 2 && cta_smem <= (size_t)(ctx->smem_optin > 0 ? ctx->smem_optin : 0);
-  uint8_t* dm = (uint8_t*)ctx->pv_misc.p;
+  uint8_t* dm = (uint8_t*)S.pv_misc.p;
   CUDA_TRY(ctx, cudaMemcpyAsync(dm, blob.data(), blob_sz, cudaMemcpyHostToDevice, st));
-  if (p) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->pv_limbs.p, points, N * (size_t)p * 160, cudaMemcpyHostToDevice, st));
-  if (m) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->pv_sec.p, secrets, N * (size_t)m * 32, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->pv_ent.p, entropy, N * 32, cudaMemcpyHostToDevice, st));
-  k_init_flags<<<1, 1, 0, st>>>((int*)ctx->flags.p);
+  if (p) CUDA_TRY(ctx, cudaMemcpyAsync(S.pv_limbs.p, points, N * (size_t)p * 160, cudaMemcpyHostToDevice, st));
+  if (m) CUDA_TRY(ctx, cudaMemcpyAsync(S.pv_sec.p, secrets, N * (size_t)m * 32, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(S.pv_ent.p, entropy, N * 32, cudaMemcpyHostToDevice, st));
+  k_init_flags<<<1, 1, 0, st>>>((int*)S.flags.p);
   LAUNCH_CHECK(ctx);
-  CUDA_TRY(ctx, cudaMemsetAsync((int*)ctx->flags.p + 2, 0, 8, st));   // flags[2]: a common point differs between proofs
+  CUDA_TRY(ctx, cudaMemsetAsync((int*)S.flags.p + 2, 0, 8, st));   // flags[2]: a common point differs between proofs
   pv_desc d;
   d.m = m; d.p = p; d.k = k; d.n_terms = n_terms; d.ni = ni;
   d.term_shared = (const int32_t*)(dm + o_sh);
@@ -1400,47 +1442,65 @@ static int32_t prove_batch_impl(zkp_ctx* ctx, const zkp_statement_desc* sd, cons
   d.term_scalar = (const int32_t*)(dm + o_ts);
   d.term_point = (const int32_t*)(dm + o_tp);
   d.cons_slot = (const int32_t*)(dm + o_sl);
-  // (1) every allocate_point compression (toolbox/mod.rs:180)
-  if (p) {
-    k_compress_limbs<<<(unsigned)((N * p + 255) / 256), 256, 0, st>>>((const unsigned long long*)ctx->pv_limbs.p, N * p,
-                                                                      (uint4*)ctx->pv_enc.p);
+  // the shared combs depend on the points only: built on the auxiliary stream (one thread per base, ~0.7 ms of serial
+  // doublings and inversions) under the compressions and the transcript kernel of this slice
+  const bool shared_combs_aux = comb && Us > 0;
+  if (shared_combs_aux) {
+    ENSURE(ctx, S.pv_static, Us * 768 + 256);   // eight affine Niels entries of 96 bytes per shared comb
+    CUDA_TRY(ctx, cudaEventRecord(S.ev_fork, st));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->aux_stream, S.ev_fork, 0));
+    // from proof 0's copy (k_pv_gather compares every other copy with it)
+    k_build_combs<false><<<(unsigned)((Us + 63) / 64), 64, 0, ctx->aux_stream>>>(
+        (const unsigned long long*)S.pv_limbs.p, Us, (uint32_t)Us, (uint32_t)p, (const int32_t*)(dm + o_cq),
+        (uint4*)S.pv_static.p);
     LAUNCH_CHECK(ctx);
+    CUDA_TRY(ctx, cudaEventRecord(S.ev_join, ctx->aux_stream));
+  }
+  // (1) every allocate_point compression (toolbox/mod.rs:180); with shared tables the batch-static points are the same
+  // in every proof (checked by k_pv_gather), so proof 0's are compressed and the others get copies
+  if (p) {
+    if (share) {
+      k_compress_limbs_shared<<<(unsigned)((N * p + 255) / 256), 256, 0, st>>>((const unsigned long long*)S.pv_limbs.p, N,
+                                                                               (uint32_t)p, (uint32_t)ni, (uint4*)S.pv_enc.p);
+      LAUNCH_CHECK(ctx);
+      k_replicate_common_enc<<<(unsigned)((N * (size_t)nc + 255) / 256), 256, 0, st>>>((uint4*)S.pv_enc.p, N, (uint32_t)p,
+                                                                                       (uint32_t)ni);
+      LAUNCH_CHECK(ctx);
+    } else {
+      k_compress_limbs<<<(unsigned)((N * p + 255) / 256), 256, 0, st>>>((const unsigned long long*)S.pv_limbs.p, N * p,
+                                                                        (uint4*)S.pv_enc.p);
+      LAUNCH_CHECK(ctx);
+    }
   }
   // (2) transcripts up to the commitments + synthetic-nonce blindings (prover.rs:78-89)
-  k_pv_blind<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(d, (const uint32_t*)(dm + o_prefix), N, (const uint8_t*)ctx->pv_enc.p,
-                                                          (const uint8_t*)ctx->pv_sec.p, (const uint8_t*)ctx->pv_ent.p,
-                                                          (uint32_t*)ctx->pv_state.p, (uint8_t*)ctx->pv_blind.p,
-                                                          (int*)ctx->flags.p);
+  k_pv_blind<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(d, (const uint32_t*)(dm + o_prefix), N, (const uint8_t*)S.pv_enc.p,
+                                                          (const uint8_t*)S.pv_sec.p, (const uint8_t*)S.pv_ent.p,
+                                                          (uint32_t*)S.pv_state.p, (uint8_t*)S.pv_blind.p,
+                                                          (int*)S.flags.p);
   LAUNCH_CHECK(ctx);
   // (3) the N*k constant-time MSMs + compress (prover.rs:93-103)
   if (M) {
     size_t gthreads = total > M ? total : M;
     if (!gthreads) gthreads = 1;
-    k_pv_gather<<<(unsigned)((gthreads + 255) / 256), 256, 0, st>>>(d, N, (const unsigned long long*)ctx->pv_limbs.p,
-                                                                    (const uint8_t*)ctx->pv_blind.p, (uint4*)ctx->in_scalars.p,
-                                                                    (uint4*)ctx->niels.p, (unsigned long long*)ctx->aux0.p,
-                                                                    (uint32_t*)ctx->multi.p, share ? (int*)ctx->flags.p + 2 : nullptr);
+    k_pv_gather<<<(unsigned)((gthreads + 255) / 256), 256, 0, st>>>(d, N, (const unsigned long long*)S.pv_limbs.p,
+                                                                    (const uint8_t*)S.pv_blind.p, (uint4*)S.in_scalars.p,
+                                                                    (uint4*)S.niels.p, (unsigned long long*)S.aux0.p,
+                                                                    (uint32_t*)S.multi.p, share ? (int*)S.flags.p + 2 : nullptr);
     LAUNCH_CHECK(ctx);
     const int32_t* shared_of = share ? d.term_shared : nullptr;
     uint4* shared_tables = nullptr;
     if (comb) {
       // one comb per base, sign-bit recoding of every blinding, then 64 columns per constraint MSM
-      ENSURE(ctx, ctx->pv_static, Us * 768 + 256);   // eight affine Niels entries of 96 bytes per shared comb
       if (U) {
-        k_build_combs<true><<<(unsigned)((N * U + 63) / 64), 64, 0, st>>>((const unsigned long long*)ctx->pv_limbs.p, N * U,
+        k_build_combs<true><<<(unsigned)((N * U + 63) / 64), 64, 0, st>>>((const unsigned long long*)S.pv_limbs.p, N * U,
                                                                         (uint32_t)U, (uint32_t)p,
-                                                                        (const int32_t*)(dm + o_cp), (uint4*)ctx->tables.p);
+                                                                        (const int32_t*)(dm + o_cp), (uint4*)S.tables.p);
         LAUNCH_CHECK(ctx);
       }
-      if (Us) {   // from proof 0's copy (k_pv_gather compared every other copy with it)
-        k_build_combs<false><<<(unsigned)((Us + 63) / 64), 64, 0, st>>>((const unsigned long long*)ctx->pv_limbs.p, Us,
-                                                                      (uint32_t)Us, (uint32_t)p,
-                                                                      (const int32_t*)(dm + o_cq), (uint4*)ctx->pv_static.p);
-        LAUNCH_CHECK(ctx);
-      }
+      if (shared_combs_aux) CUDA_TRY(ctx, cudaStreamWaitEvent(st, S.ev_join, 0));   // the shared combs are ready
       if (cta) {
-        k_comb_recode_il<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const uint4*)ctx->in_scalars.p, N, (uint32_t)n_terms,
-                                                                         (uint32_t*)ctx->sk0.p);
+        k_comb_recode_il<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const uint4*)S.in_scalars.p, N, (uint32_t)n_terms,
+                                                                         (uint32_t*)S.sk0.p);
         LAUNCH_CHECK(ctx);
         if (cta_smem > ctx->cta_smem_set) {
           CUDA_TRY(ctx, cudaFuncSetAttribute((const void*)k_comb_msm_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cta_smem));
@@ -1448,73 +1508,178 @@ static int32_t prove_batch_impl(zkp_ctx* ctx, const zkp_statement_desc* sd, cons
         }
         const unsigned nw = n_units < 16 ? (unsigned)n_units : 16u;
         k_comb_msm_cta<<<(unsigned)((N + 31) / 32), 32 * nw, cta_smem, st>>>(
-            (const uint32_t*)ctx->sk0.p, (const uint4*)ctx->tables.p, (const uint4*)ctx->pv_static.p,
+            (const uint32_t*)S.sk0.p, (const uint4*)S.tables.p, (const uint4*)S.pv_static.p,
             (const int32_t*)(dm + o_cs), (const int32_t*)(dm + o_ut), (const int32_t*)(dm + o_un),
             (const int32_t*)(dm + o_cu), N, (uint32_t)n_terms, (uint32_t)U, (uint32_t)Us, (uint32_t)n_units, (uint32_t)k,
-            (uint4*)ctx->aux1.p);
+            (uint4*)S.aux1.p, (uint32_t)ctx->prove_stagger_ns);
         LAUNCH_CHECK(ctx);
       } else {
-      k_comb_recode<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const uint4*)ctx->in_scalars.p, total, (uint4*)ctx->sk0.p);
+      k_comb_recode<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const uint4*)S.in_scalars.p, total, (uint4*)S.sk0.p);
       LAUNCH_CHECK(ctx);
-      k_small_msm_comb<<<(unsigned)((M + 63) / 64), 64, 0, st>>>((const uint32_t*)ctx->sk0.p, (const uint4*)ctx->tables.p,
-                                                              (const uint4*)ctx->pv_static.p, (const int32_t*)(dm + o_cs),
-                                                              (const unsigned long long*)ctx->aux0.p,
-                                                              (const uint32_t*)ctx->multi.p, M, (uint32_t)n_terms,
-                                                              (uint32_t)U, (uint4*)ctx->aux1.p);
+      k_small_msm_comb<<<(unsigned)((M + 63) / 64), 64, 0, st>>>((const uint32_t*)S.sk0.p, (const uint4*)S.tables.p,
+                                                              (const uint4*)S.pv_static.p, (const int32_t*)(dm + o_cs),
+                                                              (const unsigned long long*)S.aux0.p,
+                                                              (const uint32_t*)S.multi.p, M, (uint32_t)n_terms,
+                                                              (uint32_t)U, (uint4*)S.aux1.p);
       LAUNCH_CHECK(ctx);
       }
     } else {
     if (share) {
       // tables of the nc batch-static points, built once from proof 0's copy (all copies were compared above)
-      ENSURE(ctx, ctx->pv_static, (size_t)nc * (128 + 1024 + 32 + 32) + 256);
-      uint8_t* ps = (uint8_t*)ctx->pv_static.p;
+      ENSURE(ctx, S.pv_static, (size_t)nc * (128 + 1024 + 32 + 32) + 256);
+      uint8_t* ps = (uint8_t*)S.pv_static.p;
       uint4* s_ext = (uint4*)ps;
       shared_tables = (uint4*)(ps + (size_t)nc * 128);
       uint4* s_zero = (uint4*)(ps + (size_t)nc * (128 + 1024));            // dummy scalars (zero: canonical)
       uint4* s_bias = (uint4*)(ps + (size_t)nc * (128 + 1024 + 32));
       CUDA_TRY(ctx, cudaMemsetAsync(s_zero, 0, (size_t)nc * 32, st));
-      k_limbs_to_ext<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>((const unsigned long long*)ctx->pv_limbs.p + (size_t)ni * 20,
+      k_limbs_to_ext<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>((const unsigned long long*)S.pv_limbs.p + (size_t)ni * 20,
                                                                    (size_t)nc, s_ext);
       LAUNCH_CHECK(ctx);
       k_build_tables<false><<<(unsigned)((nc + 127) / 128), 128, 0, st>>>(s_ext, s_zero, (size_t)nc, 1u, shared_tables, s_bias,
-                                                                          (int*)ctx->flags.p + 2);
+                                                                          (int*)S.flags.p + 2);
       LAUNCH_CHECK(ctx);
     }
     if (total) {
       k_build_tables<true><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(
-          (const uint4*)ctx->niels.p, (const uint4*)ctx->in_scalars.p, total, (uint32_t)n_terms, (uint4*)ctx->tables.p,
-          (uint4*)ctx->sk0.p, (int*)ctx->flags.p + 2, shared_of);   // blindings are canonical
+          (const uint4*)S.niels.p, (const uint4*)S.in_scalars.p, total, (uint32_t)n_terms, (uint4*)S.tables.p,
+          (uint4*)S.sk0.p, (int*)S.flags.p + 2, shared_of);   // blindings are canonical
       LAUNCH_CHECK(ctx);
     }
-    k_small_msm_ct<true><<<(unsigned)((M + 63) / 64), 64, 0, st>>>((const uint32_t*)ctx->sk0.p, (const uint4*)ctx->tables.p,
-                                                                   (const unsigned long long*)ctx->aux0.p,
-                                                                   (const uint32_t*)ctx->multi.p, M, (uint32_t)n_terms,
-                                                                   (uint4*)ctx->aux1.p, shared_of, shared_tables);
+    k_small_msm_ct<true><<<(unsigned)((M + 63) / 64), 64, 0, st>>>((const uint32_t*)S.sk0.p, (const uint4*)S.tables.p,
+                                                                   (const unsigned long long*)S.aux0.p,
+                                                                   (const uint32_t*)S.multi.p, M, (uint32_t)n_terms,
+                                                                   (uint4*)S.aux1.p, shared_of, shared_tables);
     LAUNCH_CHECK(ctx);
     }
   }
   // (4) commitments into the transcript, challenge, responses (prover.rs:98-109)
-  k_pv_finish<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(d, N, (const uint32_t*)ctx->pv_state.p, (const uint8_t*)ctx->aux1.p,
-                                                           (const uint8_t*)ctx->pv_sec.p, (const uint8_t*)ctx->pv_blind.p,
-                                                           (uint8_t*)ctx->pv_resp.p);
+  k_pv_finish<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(d, N, (const uint32_t*)S.pv_state.p, (const uint8_t*)S.aux1.p,
+                                                           (const uint8_t*)S.pv_sec.p, (const uint8_t*)S.pv_blind.p,
+                                                           (uint8_t*)S.pv_resp.p);
   LAUNCH_CHECK(ctx);
-  int hflags[4];
-  if (p) CUDA_TRY(ctx, cudaMemcpyAsync(encodings_out, ctx->pv_enc.p, N * (size_t)p * 32, cudaMemcpyDeviceToHost, st));
-  if (k) CUDA_TRY(ctx, cudaMemcpyAsync(commitments_out, ctx->aux1.p, M * 32, cudaMemcpyDeviceToHost, st));
-  if (m) CUDA_TRY(ctx, cudaMemcpyAsync(responses_out, ctx->pv_resp.p, N * (size_t)m * 32, cudaMemcpyDeviceToHost, st));
-  if (m && blindings_out)
-    CUDA_TRY(ctx, cudaMemcpyAsync(blindings_out, ctx->pv_blind.p, N * (size_t)m * 32, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(ctx, cudaMemcpyAsync(hflags, ctx->flags.p, 16, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(ctx, cudaStreamSynchronize(st));
-  if (hflags[1] != 0x7fffffff) return ZKP_ERR_SCALAR;   // a non-canonical secret
-  if (share && hflags[2] != 0) {   // the "common" points were not common after all: per-proof tables for every term
-    ctx->share_static_tables = 0;
-    int32_t rc = zkp_prove_batch(ctx, sd, prefix_state, N, secrets, points, entropy, encodings_out, commitments_out,
-                                 responses_out, blindings_out);
-    ctx->share_static_tables = 1;
-    return rc;
-  }
+  sl.share = share;
+  CUDA_TRY(ctx, cudaMemcpyAsync(S.h_flags, S.flags.p, 16, cudaMemcpyDeviceToHost, st));
   return ZKP_OK;
+}
+
+// Outputs leave the device only on the success path: the flags are read first.  (With shared tables a batch whose
+// "common" points differ computes commitments from the wrong tables, and its responses s*c + b would share the
+// blinding b with the redone call's s*c' + b: two challenges for one nonce reveal s.  Those bytes never reach the caller.)
+static int32_t prove_slice_complete(zkp_ctx* ctx, pv_set& S, const zkp_statement_desc* sd, const pv_slice& sl) {
+  const int m = sd->m, k = sd->k, p = sd->ni + sd->nc;
+  const size_t N = sl.N, M = N * (size_t)k;
+  cudaStream_t st = S.stream;
+  CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  if (S.h_flags[1] != 0x7fffffff) return ZKP_ERR_SCALAR;   // a non-canonical secret
+  if (sl.share && S.h_flags[2] != 0) return ZKP_PV_NOT_UNIFORM;
+  if (p) CUDA_TRY(ctx, cudaMemcpyAsync(sl.encodings_out, S.pv_enc.p, N * (size_t)p * 32, cudaMemcpyDeviceToHost, st));
+  if (k) CUDA_TRY(ctx, cudaMemcpyAsync(sl.commitments_out, S.aux1.p, M * 32, cudaMemcpyDeviceToHost, st));
+  if (m) CUDA_TRY(ctx, cudaMemcpyAsync(sl.responses_out, S.pv_resp.p, N * (size_t)m * 32, cudaMemcpyDeviceToHost, st));
+  if (m && sl.blindings_out)
+    CUDA_TRY(ctx, cudaMemcpyAsync(sl.blindings_out, S.pv_blind.p, N * (size_t)m * 32, cudaMemcpyDeviceToHost, st));
+  return ZKP_OK;
+}
+
+static int32_t prove_sets_ready(zkp_ctx* ctx) {
+  for (int i = 0; i < 2; i++) {
+    pv_set& S = ctx->pvs[i];
+    if (i == 1 && !S.own_stream) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&S.own_stream, cudaStreamNonBlocking));
+    S.stream = i == 0 ? ctx->stream : S.own_stream;
+    if (!S.h_flags) CUDA_TRY(ctx, cudaMallocHost((void**)&S.h_flags, 64));
+    if (!S.ev_fork) {
+      CUDA_TRY(ctx, cudaEventCreateWithFlags(&S.ev_fork, cudaEventDisableTiming));
+      CUDA_TRY(ctx, cudaEventCreateWithFlags(&S.ev_join, cudaEventDisableTiming));
+    }
+  }
+  if (!ctx->aux_stream) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+  return ZKP_OK;
+}
+
+static int32_t prove_batch_run(zkp_ctx* ctx, const zkp_statement_desc* sd, const uint32_t* prefix_state, size_t N,
+                               const uint8_t* secrets, const uint64_t* points, const uint8_t* entropy,
+                               uint8_t* encodings_out, uint8_t* commitments_out, uint8_t* responses_out,
+                               uint8_t* blindings_out, bool share_allowed) {
+  const int m = sd->m, k = sd->k, p = sd->ni + sd->nc;
+  int32_t rc = prove_sets_ready(ctx);
+  if (rc != ZKP_OK) return rc;
+  // slices: at most prove_chunk proofs (workspace bound: tables), and at most prove_pipe_chunk when the batch is large
+  // enough to be worth pipelining (copies of one slice under the kernels of another)
+  size_t chunk = ctx->prove_chunk;
+  if (ctx->prove_pipe_chunk && N >= 2 * ctx->prove_pipe_chunk && ctx->prove_pipe_chunk < chunk) chunk = ctx->prove_pipe_chunk;
+  pv_slice cur[2];
+  bool pending[2] = {false, false};
+  auto drain = [&]() {
+    for (int i = 0; i < 2; i++)
+      if (ctx->pvs[i].stream) cudaStreamSynchronize(ctx->pvs[i].stream);
+    if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
+  };
+  size_t idx = 0;
+  for (size_t lo = 0; lo < N; lo += chunk, idx++) {
+    const int w = (int)(idx & 1);
+    pv_set& S = ctx->pvs[w];
+    if (pending[w]) {   // the set is still busy with slice idx - 2: finish it (outputs after the flags)
+      rc = prove_slice_complete(ctx, S, sd, cur[w]);
+      pending[w] = false;
+      if (rc != ZKP_OK) break;
+      CUDA_TRY(ctx, cudaStreamSynchronize(S.stream));   // its outputs have left before the buffers are overwritten
+    }
+    pv_slice& sl = cur[w];
+    sl.N = N - lo < chunk ? N - lo : chunk;
+    sl.secrets = secrets ? secrets + lo * (size_t)m * 32 : nullptr;
+    sl.points = points ? points + lo * (size_t)p * 20 : nullptr;
+    sl.entropy = entropy + lo * 32;
+    sl.encodings_out = encodings_out ? encodings_out + lo * (size_t)p * 32 : nullptr;
+    sl.commitments_out = commitments_out ? commitments_out + lo * (size_t)k * 32 : nullptr;
+    sl.responses_out = responses_out ? responses_out + lo * (size_t)m * 32 : nullptr;
+    sl.blindings_out = blindings_out ? blindings_out + lo * (size_t)m * 32 : nullptr;
+    rc = prove_slice_enqueue(ctx, S, sd, prefix_state, sl, share_allowed);
+    if (rc != ZKP_OK) break;
+    pending[w] = true;
+    if (pending[w ^ 1]) {   // while this slice runs, the previous one's flags are checked and its outputs leave
+      rc = prove_slice_complete(ctx, ctx->pvs[w ^ 1], sd, cur[w ^ 1]);
+      pending[w ^ 1] = false;
+      if (rc != ZKP_OK) break;
+    }
+  }
+  for (int w = 0; w < 2 && rc == ZKP_OK; w++)
+    if (pending[w]) {
+      rc = prove_slice_complete(ctx, ctx->pvs[w], sd, cur[w]);
+      pending[w] = false;
+    }
+  drain();
+  return rc;
+}
+
+static int32_t prove_batch_impl(zkp_ctx* ctx, const zkp_statement_desc* sd, const uint32_t* prefix_state, size_t N,
+                                const uint8_t* secrets, const uint64_t* points, const uint8_t* entropy,
+                                uint8_t* encodings_out, uint8_t* commitments_out, uint8_t* responses_out,
+                                uint8_t* blindings_out) {
+  if (!ctx || !sd || !prefix_state) return ZKP_ERR_SIZE;
+  if (!statement_ok(sd) || sd->ni + sd->nc > 2 * ZKP_BV_MAX_VARS) {
+    ctx->err = "inconsistent or oversized statement description";
+    return ZKP_ERR_SIZE;
+  }
+  const int m = sd->m, k = sd->k, p = sd->ni + sd->nc;
+  if (!N) return ZKP_OK;
+  if ((m && (!secrets || !responses_out)) || (p && (!points || !encodings_out)) || (k && !commitments_out))
+    return ZKP_ERR_SIZE;
+  std::vector<uint8_t> own_entropy;
+  if (!entropy) {   // the caller leaves the 32 bytes per proof of prover.rs:82 (thread_rng) to the OS CSPRNG
+    own_entropy.resize(N * 32);
+    if (!os_random_bytes(own_entropy.data(), own_entropy.size())) {
+      ctx->err = "getrandom failed";
+      return ZKP_ERR_CUDA;
+    }
+    entropy = own_entropy.data();
+  }
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  int32_t rc = prove_batch_run(ctx, sd, prefix_state, N, secrets, points, entropy, encodings_out, commitments_out,
+                               responses_out, blindings_out, /*share_allowed=*/true);
+  if (rc == ZKP_PV_NOT_UNIFORM)   // the "common" points were not common after all: per-proof tables for every term
+    rc = prove_batch_run(ctx, sd, prefix_state, N, secrets, points, entropy, encodings_out, commitments_out, responses_out,
+                         blindings_out, /*share_allowed=*/false);
+  return rc;
 }
 extern "C" int32_t zkp_prove_batch(zkp_ctx* ctx, const zkp_statement_desc* sd, const uint32_t* prefix_state, size_t N,
                                    const uint8_t* secrets, const uint64_t* points, const uint8_t* entropy,

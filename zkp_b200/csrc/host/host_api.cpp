@@ -1,4 +1,6 @@
 // extern "C" face of the host mirror (include/zkp_b200_host.h).
+#include <sys/random.h>
+
 #include <atomic>
 #include <chrono>
 #include <new>
@@ -20,6 +22,33 @@ static int32_t guarded(F&& body) {
     return EngineFailure;
   }
 }
+
+// Randomness the reference draws from rand::thread_rng() (prover.rs:82, verifier.rs:153, batch_verifier.rs:179): a caller
+// that passes no seed gets fresh bytes from the OS CSPRNG, per call.  A seed that is given is used as is (reproducible
+// tests and benches) and must then be fresh, secret CSPRNG output itself: batch soundness rests on weights the prover
+// cannot predict, and a repeated prover seed repeats nonces.
+static bool os_random(uint8_t* out, size_t n) {
+  while (n) {
+    ssize_t got = getrandom(out, n > 256 ? 256 : n, 0);
+    if (got <= 0) return false;
+    out += got;
+    n -= (size_t)got;
+  }
+  return true;
+}
+struct seed_arg {
+  uint8_t own[32];
+  const uint8_t* p;
+  size_t len;
+  bool ok;
+  seed_arg(const uint8_t* seed, size_t seed_len) : p(seed), len(seed_len), ok(true) {
+    if (!seed) {
+      ok = os_random(own, 32);
+      p = own;
+      len = 32;
+    }
+  }
+};
 
 extern "C" zkph_statement* zkph_statement_new(const char* name, const char* label, const char* labels, int32_t n_secrets,
                                               int32_t n_instance, int32_t n_common, int32_t n_constraints,
@@ -111,7 +140,9 @@ extern "C" int32_t zkph_prove_t(zkp_ctx* ctx, const zkph_statement* h, zkph_tran
   for (size_t i = 0; i < m; i++) sec[i] = load_scalar(secrets + 32 * i);
   std::vector<Limbs> pts(p);
   for (size_t i = 0; i < p; i++) memcpy(pts[i].data(), points + 20 * i, 160);
-  Rng rng(seed, seed_len);
+  seed_arg sa(seed, seed_len);
+  if (!sa.ok) return EngineFailure;
+  Rng rng(sa.p, sa.len);
   // re-implemented inline (instead of stmt_prove) to hand the blindings back for parity tests
   Prover pr(ctx, st.label, &t);
   for (size_t i = 0; i < m; i++) pr.allocate_scalar(st.secrets[i], sec[i]);
@@ -195,17 +226,19 @@ extern "C" int32_t zkph_verify_batchable_t(zkp_ctx* ctx, const zkph_statement* h
   bp.responses.resize(n_responses);
   for (size_t i = 0; i < n_responses; i++)
     if (!Scalar::from_canonical_bytes(&bp.responses[i], responses + 32 * i)) return VerificationFailure;
-  Rng rng(seed, seed_len);
+  seed_arg sa(seed, seed_len);
+  if (!sa.ok) return EngineFailure;
+  Rng rng(sa.p, sa.len);
   return stmt_verify_batchable(ctx, st, &tr->t, load_encs(points_enc, st.num_points()), bp, rng);
   });
 }
 
-extern "C" int32_t zkph_batch_verify(zkp_ctx* ctx, const zkph_statement* h, const uint8_t* tl, size_t tl_len, size_t N,
-                                     const uint8_t* instance_enc, const uint8_t* common_enc, const uint8_t* commitments,
-                                     const uint8_t* responses, const uint8_t* seed, size_t seed_len, int32_t threads,
-                                     uint8_t* coeff_out, uint8_t* points_out, double* host_seconds) {
-  return guarded([&]() -> int32_t {
-  const Statement& st = h->st;
+// module::batch_verify over N transcripts (macros.rs:336-370); identical = every transcript holds the same state
+static int32_t batch_verify_impl(zkp_ctx* ctx, const Statement& st, std::vector<Transcript>* transcripts, bool identical,
+                                 size_t n_proofs, const uint8_t* instance_enc, const uint8_t* common_enc,
+                                 const uint8_t* commitments, const uint8_t* responses, const uint8_t* seed, size_t seed_len,
+                                 int32_t threads, uint8_t* coeff_out, uint8_t* points_out, double* host_seconds) {
+  const size_t N = n_proofs;
   const size_t m = st.secrets.size(), k = st.constraints.size(), ni = st.instance.size(), nc = st.common.size();
   auto t0 = std::chrono::steady_clock::now();
   std::vector<BatchableProof> proofs(N);
@@ -219,10 +252,11 @@ extern "C" int32_t zkph_batch_verify(zkp_ctx* ctx, const zkph_statement* h, cons
     }
   });
   if (noncanon.load()) return VerificationFailure;
-  std::vector<Transcript> transcripts(N, Transcript(tl, tl_len));
-  Rng rng(seed, seed_len);
+  seed_arg sa(seed, seed_len);
+  if (!sa.ok) return EngineFailure;
+  Rng rng(sa.p, sa.len);
   ProofError err;
-  BatchVerifier bv(ctx, st.label, N, &transcripts, &err, threads, /*identical_transcripts=*/true);
+  BatchVerifier bv(ctx, st.label, N, transcripts, &err, threads, identical);
   if (err != PROOF_OK) return err;
   for (auto& s : st.secrets) bv.allocate_scalar(s);
   std::vector<BatchPointVar> pv;
@@ -261,6 +295,35 @@ extern "C" int32_t zkph_batch_verify(zkp_ctx* ctx, const zkph_statement* h, cons
   if (rc == ZKP_ERR_POINT) return VerificationFailure;
   if (rc != ZKP_OK) return EngineFailure;
   return accept ? PROOF_OK : VerificationFailure;
+}
+
+extern "C" int32_t zkph_batch_verify(zkp_ctx* ctx, const zkph_statement* h, const uint8_t* tl, size_t tl_len, size_t N,
+                                     const uint8_t* instance_enc, const uint8_t* common_enc, const uint8_t* commitments,
+                                     const uint8_t* responses, const uint8_t* seed, size_t seed_len, int32_t threads,
+                                     uint8_t* coeff_out, uint8_t* points_out, double* host_seconds) {
+  return guarded([&]() -> int32_t {
+  std::vector<Transcript> transcripts(N, Transcript(tl, tl_len));
+  return batch_verify_impl(ctx, h->st, &transcripts, /*identical=*/true, N, instance_enc, common_enc, commitments, responses,
+                           seed, seed_len, threads, coeff_out, points_out, host_seconds);
+  });
+}
+
+// The reference's signature: one `&mut Transcript` per proof, each with its own prior state, each left advanced
+// (batch_verifier.rs:67-88; macros.rs:336-346).  n_transcripts != n_proofs is BatchSizeMismatch (batch_verifier.rs:72-74).
+extern "C" int32_t zkph_batch_verify_t(zkp_ctx* ctx, const zkph_statement* h, zkph_transcript* const* transcripts,
+                                       size_t n_transcripts, size_t n_proofs, const uint8_t* instance_enc,
+                                       const uint8_t* common_enc, const uint8_t* commitments, const uint8_t* responses,
+                                       const uint8_t* seed, size_t seed_len, int32_t threads) {
+  return guarded([&]() -> int32_t {
+  if (n_transcripts != n_proofs) return BatchSizeMismatch;
+  for (size_t j = 0; j < n_transcripts; j++)
+    if (!transcripts || !transcripts[j]) return EngineFailure;
+  std::vector<Transcript> ts(n_transcripts);
+  for (size_t j = 0; j < n_transcripts; j++) ts[j] = transcripts[j]->t;
+  int32_t rc = batch_verify_impl(ctx, h->st, &ts, /*identical=*/false, n_proofs, instance_enc, common_enc, commitments,
+                                 responses, seed, seed_len, threads, nullptr, nullptr, nullptr);
+  for (size_t j = 0; j < n_transcripts; j++) transcripts[j]->t = ts[j];   // advanced, like the reference's &mut borrows
+  return rc;
   });
 }
 
@@ -307,7 +370,9 @@ extern "C" int32_t zkph_batch_verify_device(zkp_ctx* ctx, const zkph_statement* 
   flat_stmt f(st);
   int32_t accept = 0;
   int64_t bad = -1;
-  int32_t rc = zkp_batch_verify_proofs(ctx, &f.d, prefix, N, instance_enc, common_enc, commitments, responses, rho_seed32,
+  seed_arg sa(rho_seed32, 32);     // no seed: 32 fresh bytes from the OS CSPRNG
+  if (!sa.ok) return EngineFailure;
+  int32_t rc = zkp_batch_verify_proofs(ctx, &f.d, prefix, N, instance_enc, common_enc, commitments, responses, sa.p,
                                        &accept, &bad, coeff_out, points_out);
   if (rc == ZKP_ERR_POINT || rc == ZKP_ERR_SCALAR) return VerificationFailure;
   if (rc == ZKP_ERR_SIZE) return BatchSizeMismatch;
@@ -328,6 +393,12 @@ extern "C" int32_t zkph_prove_many_device(zkp_ctx* ctx, const zkph_statement* h,
   uint32_t prefix[53];
   t.export_state(prefix);
   flat_stmt f(st);
+  std::vector<uint8_t> own_entropy;
+  if (!entropy && N) {             // no entropy: 32 fresh bytes per proof from the OS CSPRNG (prover.rs:82 thread_rng)
+    own_entropy.resize(N * 32);
+    if (!os_random(own_entropy.data(), own_entropy.size())) return EngineFailure;
+    entropy = own_entropy.data();
+  }
   int32_t rc = zkp_prove_batch(ctx, &f.d, prefix, N, secrets, points, entropy, encodings, commitments, responses, nullptr);
   if (rc == ZKP_ERR_SIZE) return BatchSizeMismatch;
   if (rc != ZKP_OK) return EngineFailure;
@@ -345,6 +416,12 @@ extern "C" int32_t zkph_prove_many(zkp_ctx* ctx, const zkph_statement* h, const 
   parallel_for(N * m, threads, [&](size_t lo, size_t hi, int) {
     for (size_t i = lo; i < hi; i++) sec[i] = load_scalar(secrets + 32 * i);
   });
+  std::vector<uint8_t> own_entropy;
+  if (!entropy && N) {
+    own_entropy.resize(N * 32);
+    if (!os_random(own_entropy.data(), own_entropy.size())) return EngineFailure;
+    entropy = own_entropy.data();
+  }
   std::vector<BatchableProof> proofs;
   std::vector<Enc> encs;
   ProofError e = stmt_prove_many(ctx, st, std::string((const char*)tl, tl_len), N, sec.data(), (const Limbs*)points,

@@ -24,9 +24,22 @@ static uint64_t add_n(uint64_t* r, const uint64_t* a, const uint64_t* b, int n) 
   }
   return c;
 }
-static bool ge_l(const uint64_t* a) {  // a (4 words) >= l ?
+static bool ge_l(const uint64_t* a) {  // a (4 words) >= l ?   (used on public data only: canonicity of wire scalars)
   uint64_t t[4];
   return sub_n(t, a, L, 4) == 0;
+}
+// Branch-free selects: the arithmetic below runs on witnesses and blindings (Prover::prove_impl, prover.rs:85-109), and
+// the reference's curve25519-dalek Scalar arithmetic is constant time, so nothing here may branch on a value.
+// r = a + (b & mask) over 4 words; mask is 0 or ~0
+static void add_masked(uint64_t* r, const uint64_t* a, const uint64_t* b, uint64_t mask) {
+  uint64_t m[4] = {b[0] & mask, b[1] & mask, b[2] & mask, b[3] & mask};
+  add_n(r, a, m, 4);
+}
+// r = a - l if a >= l else a   (one conditional subtraction, selected by mask)
+static void cond_sub_l(uint64_t* r, const uint64_t* a) {
+  uint64_t t[4];
+  const uint64_t keep = 0 - sub_n(t, a, L, 4);   // borrow -> a < l -> keep a
+  for (int i = 0; i < 4; i++) r[i] = (a[i] & keep) | (t[i] & ~keep);
 }
 
 // Reduce an n-word (n <= 9) little-endian value mod l by binary long division on 64-bit words:
@@ -49,20 +62,21 @@ static void reduce_words(uint64_t out[4], const uint64_t* in, int n) {
     p = (u128)hi0 * C[1] + carry;
     prod[1] = (uint64_t)p;
     prod[2] = (uint64_t)(p >> 64);
-    if (hi1) {  // + c * 2^64
-      u128 s = (u128)prod[1] + C[0];
+    {  // + (hi1 ? c : 0) * 2^64, selected by mask
+      const uint64_t m1 = 0 - hi1;
+      u128 s = (u128)prod[1] + (C[0] & m1);
       prod[1] = (uint64_t)s;
-      s = (u128)prod[2] + C[1] + (uint64_t)(s >> 64);
+      s = (u128)prod[2] + (C[1] & m1) + (uint64_t)(s >> 64);
       prod[2] = (uint64_t)s;
       prod[3] = (uint64_t)(s >> 64);
     }
-    // r = lo - prod (mod l): lo < 2^252 < l, prod < 2^191 < l
+    // r = lo - prod (mod l): lo < 2^252 < l, prod < 2^191 < l, so lo - prod + (borrow ? l : 0) is in [0, l)
     uint64_t d[4];
-    if (sub_n(d, lo, prod, 4)) add_n(d, d, L, 4);
+    const uint64_t borrow = sub_n(d, lo, prod, 4);
+    add_masked(d, d, L, 0 - borrow);
     memcpy(r, d, 32);
   }
-  while (ge_l(r)) sub_n(r, r, L, 4);
-  memcpy(out, r, 32);
+  cond_sub_l(out, r);   // r < l already (see above); one fixed conditional subtraction keeps the bound explicit
 }
 
 Scalar Scalar::from_bytes_mod_order(const uint8_t b[32]) {
@@ -88,13 +102,15 @@ bool Scalar::from_canonical_bytes(Scalar* out, const uint8_t b[32]) {
 }
 Scalar sc_add(const Scalar& a, const Scalar& b) {
   Scalar r;
-  add_n(r.w, a.w, b.w, 4);  // < 2^254: no carry out
-  if (ge_l(r.w)) sub_n(r.w, r.w, L, 4);
+  uint64_t t[4];
+  add_n(t, a.w, b.w, 4);  // < 2^254: no carry out
+  cond_sub_l(r.w, t);
   return r;
 }
 Scalar sc_sub(const Scalar& a, const Scalar& b) {
   Scalar r;
-  if (sub_n(r.w, a.w, b.w, 4)) add_n(r.w, r.w, L, 4);
+  const uint64_t borrow = sub_n(r.w, a.w, b.w, 4);
+  add_masked(r.w, r.w, L, 0 - borrow);
   return r;
 }
 Scalar sc_neg(const Scalar& a) { return sc_sub(Scalar::zero(), a); }

@@ -68,8 +68,9 @@ extern "C" int32_t zkph_compact_proof_parse(const uint8_t* buf, size_t len, size
 }
 
 // N serialized BatchableProofs of ONE statement (k commitments, m responses each), concatenated: -> SoA.
-// A proof whose counts differ from (k, m) makes the batch BatchSizeMismatch (batch_verifier.rs:138-148); truncated input,
-// trailing bytes or a non-canonical scalar make it ZKPH_MALFORMED (the reference's bincode::deserialize fails).
+// A proof whose counts differ from (k, m) makes the batch VerificationFailure (batch_verifier.rs:142-148; BatchSizeMismatch
+// there is only proofs.len() != batch_size, :138-140); truncated input, trailing bytes or a non-canonical scalar make it
+// ZKPH_MALFORMED (the reference's bincode::deserialize fails).
 extern "C" int32_t zkph_batchable_proofs_parse(const uint8_t* buf, size_t len, size_t N, size_t k, size_t m,
                                                uint8_t* commitments, uint8_t* responses, int32_t threads,
                                                int64_t* first_bad) {
@@ -120,7 +121,7 @@ extern "C" int32_t zkph_batchable_proofs_parse(const uint8_t* buf, size_t len, s
     if (mm > (len - q - 8) / 32) return ZKPH_MALFORMED;
     for (uint64_t i = 0; i < mm; i++)
       if (!canonical(buf + q + 8 + 32 * i)) return ZKPH_MALFORMED;
-    if (kk != k || mm != m) return BatchSizeMismatch;
+    if (kk != k || mm != m) return VerificationFailure;   // batch_verifier.rs:142-148
     if (k) memcpy(commitments + j * k * 32, buf + off + 8, 32 * k);
     if (m) memcpy(responses + j * m * 32, buf + q + 8, 32 * m);
     off = q + 8 + 32 * (size_t)mm;

@@ -77,6 +77,34 @@ __global__ void __launch_bounds__(128) k_pv_blind(pv_desc d, const uint32_t* __r
   }
 }
 
+// allocate_point compressions of a batch whose common points (indices ni .. p-1) are the same in every proof: thread
+// (j, i) compresses point i of proof j unless it is a common point of a proof other than proof 0 ...
+__global__ void __launch_bounds__(256) k_compress_limbs_shared(const unsigned long long* __restrict__ limbs, size_t N,
+                                                               uint32_t p, uint32_t ni, uint4* __restrict__ enc) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= N * p) return;
+  const size_t j = t / p;
+  const uint32_t i = (uint32_t)(t % p);
+  if (i >= ni && j != 0) return;
+  ge_ext pt;
+  load_ext_limbs51(pt, limbs + 20 * t);
+  uint32_t w[8];
+  ristretto_encode(w, pt);
+  enc[2 * t] = make_uint4(w[0], w[1], w[2], w[3]);
+  enc[2 * t + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+// ... and those get proof 0's encodings
+__global__ void __launch_bounds__(256) k_replicate_common_enc(uint4* __restrict__ enc, size_t N, uint32_t p, uint32_t ni) {
+  const uint32_t nc = p - ni;
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= N * nc) return;
+  const size_t j = t / nc;
+  const uint32_t i = ni + (uint32_t)(t % nc);
+  if (j == 0) return;
+  enc[2 * (j * p + i)] = enc[2 * (size_t)i];
+  enc[2 * (j * p + i) + 1] = enc[2 * (size_t)i + 1];
+}
+
 // one thread per term (j, q): flat scalar and extended point of the constraint MSMs; one thread per (j, c): CSR + order
 __global__ void __launch_bounds__(256) k_pv_gather(pv_desc d, size_t N, const unsigned long long* __restrict__ limbs,
                                                    const uint8_t* __restrict__ blind, uint4* __restrict__ scalars_flat,

@@ -524,7 +524,7 @@ __global__ void __launch_bounds__(512, 1)
                    const uint4* __restrict__ shared_combs, const int32_t* __restrict__ term_slot,
                    const int32_t* __restrict__ unit_term0, const int32_t* __restrict__ unit_nterms,
                    const int32_t* __restrict__ cons_unit0, size_t N, uint32_t T, uint32_t U, uint32_t Us,
-                   uint32_t n_units, uint32_t k, uint4* __restrict__ out) {
+                   uint32_t n_units, uint32_t k, uint4* __restrict__ out, uint32_t stagger_ns) {
 #ifdef ZKP_HOST_EMUL
   uint4* smem = emul_dynamic_smem;
 #else
@@ -574,10 +574,36 @@ __global__ void __launch_bounds__(512, 1)
   }
   __syncthreads();
 #endif
+  // The warps of one scheduler (warp ids equal mod 4) would otherwise run in phase: all scanning (ALU + LSU, multiplier
+  // idle), then all adding (multiplier saturated).  A start offset per warp keeps their phases apart (public: warp id).
+#if ZKP_DEVICE_ASM
+  if (stagger_ns) __nanosleep(stagger_ns * (warp >> 2));
+#endif
   // ---- the units of this warp -------------------------------------------------------------------------------------
 #pragma unroll 1
   for (uint32_t u = warp; u < n_units; u += nw) {
     const uint32_t r0 = (uint32_t)unit_term0[u], nt = (uint32_t)unit_nterms[u];
+    // Shared combs (the same table for all 32 lanes = proofs, each lane wanting its own entry): with at most two terms
+    // per unit the table lives in REGISTERS, spread over the warp -- word q of entry e in slot q / 4 of lane
+    // 8 (q % 4) + e -- and a lane fetches its entry with 24 shuffles whose source lane is 8 (q % 4) + idx: no memory is
+    // indexed by a digit, and the 48 shared-memory loads + 192 masked selects of the scan go away.
+    const bool in_regs = nt <= 2;
+    uint32_t stab0[6] = {0, 0, 0, 0, 0, 0}, stab1[6] = {0, 0, 0, 0, 0, 0};
+    if (in_regs) {
+#pragma unroll 1
+      for (uint32_t t = 0; t < nt; t++) {
+        const int32_t slot = term_slot[r0 + t];
+        if (slot < 0) {
+          const uint32_t* tab32 = (const uint32_t*)(s_shared + (size_t)(-slot - 1) * 48) + 24 * (lane & 7) + (lane >> 3);
+#pragma unroll
+          for (int r = 0; r < 6; r++) {
+            const uint32_t w = tab32[4 * r];
+            if (t == 0) stab0[r] = w;
+            else stab1[r] = w;
+          }
+        }
+      }
+    }
     ge_ext acc;
     ge_identity(acc);
 #pragma unroll 1
@@ -598,6 +624,16 @@ __global__ void __launch_bounds__(512, 1)
             x = v.x; y = v.y; z = v.z; ww = v.w;
           }, idx, neg);
           ge_add_pniels(acc, acc, sel);
+        } else if (in_regs) {
+          ge_aniels sel;
+          uint32_t* d = (uint32_t*)&sel;
+#pragma unroll
+          for (int q = 0; q < 24; q++) {
+            const uint32_t mine = t == 0 ? stab0[q >> 2] : stab1[q >> 2];
+            d[q] = __shfl_sync(0xffffffffu, mine, (int)(((q & 3) << 3) + idx));
+          }
+          ge_aniels_cneg(sel, neg);
+          ge_madd(acc, acc, sel);
         } else {
           const uint4* tab = s_shared + (size_t)(-slot - 1) * 48;
           ge_aniels sel;

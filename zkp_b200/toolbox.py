@@ -56,6 +56,7 @@ def _lib():
         lib.zkph_verify_compact.argtypes = [vp, vp, vp, sz, vp, vp, vp, sz]
         lib.zkph_verify_batchable.argtypes = [vp, vp, vp, sz, vp, vp, sz, vp, sz, vp, sz]
         lib.zkph_batch_verify.argtypes = [vp, vp, vp, sz, sz, vp, vp, vp, vp, vp, sz, i32, vp, vp, vp]
+        lib.zkph_batch_verify_t.argtypes = [vp, vp, vp, sz, sz, vp, vp, vp, vp, vp, sz, i32]
         lib.zkph_prove_many.argtypes = [vp, vp, vp, sz, sz, vp, vp, vp, i32, vp, vp, vp]
         lib.zkph_batch_verify_device.argtypes = [vp, vp, vp, sz, sz, vp, vp, vp, vp, vp, vp, vp]
         lib.zkph_prove_many_device.argtypes = [vp, vp, vp, sz, sz, vp, vp, vp, vp, vp, vp]
@@ -89,6 +90,15 @@ def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
 
 
+def _seed(seed):
+    """(pointer argument, length) of an optional seed: None lets the library draw from the OS CSPRNG (the default a
+    deployment wants; see RANDOMNESS in include/zkp_b200_host.h).  A seed that is given must be fresh and secret."""
+    if seed is None:
+        return None, 0
+    seed = bytes(seed)
+    return seed, len(seed)
+
+
 class Transcript:
     """merlin::Transcript (re-exported by the reference as zkp::Transcript, /root/reference/src/lib.rs:35), hashed
     by the C++ host library.  Pass an instance wherever a transcript label (bytes) is accepted to drive the
@@ -96,9 +106,14 @@ class Transcript:
 
     def __init__(self, label=None, _handle=None):
         self._h = _handle if _handle is not None else _lib().zkph_transcript_new(bytes(label), len(label))
+        if not self._h:
+            raise MemoryError("zkph_transcript_new / zkph_transcript_clone returned NULL")
 
     def clone(self):
-        return Transcript(_handle=_lib().zkph_transcript_clone(self._h))
+        h = _lib().zkph_transcript_clone(self._h)
+        if not h:
+            raise MemoryError("zkph_transcript_clone returned NULL")
+        return Transcript(_handle=h)
 
     def append_message(self, label, message):
         _lib().zkph_transcript_append_message(self._h, bytes(label), len(label), bytes(message), len(message))
@@ -153,20 +168,21 @@ class Statement:
         com = np.zeros((self.k, 32), np.uint8)
         resp = np.zeros((self.m, 32), np.uint8)
         blind = np.zeros((self.m, 32), np.uint8)
+        seed, seed_len = _seed(rng_seed)
         if isinstance(transcript_label, Transcript):
-            _raise(lib.zkph_prove_t(eng._ctx, self._h, transcript_label._h, _p(sec), _p(pts), rng_seed, len(rng_seed),
+            _raise(lib.zkph_prove_t(eng._ctx, self._h, transcript_label._h, _p(sec), _p(pts), seed, seed_len,
                                     1 if batchable else 0, _p(enc), _p(chal), _p(com), _p(resp), _p(blind)))
         else:
-            _raise(lib.zkph_prove(eng._ctx, self._h, transcript_label, len(transcript_label), _p(sec), _p(pts), rng_seed,
-                                  len(rng_seed), 1 if batchable else 0, _p(enc), _p(chal), _p(com), _p(resp), _p(blind)))
+            _raise(lib.zkph_prove(eng._ctx, self._h, transcript_label, len(transcript_label), _p(sec), _p(pts), seed,
+                                  seed_len, 1 if batchable else 0, _p(enc), _p(chal), _p(com), _p(resp), _p(blind)))
         return enc, chal, com, resp, blind
 
-    def prove_compact(self, eng, transcript_label, secrets, points_limbs, rng_seed):
+    def prove_compact(self, eng, transcript_label, secrets, points_limbs, rng_seed=None):
         """-> ((challenge, responses), encodings)   (macros.rs:261-268)"""
         enc, chal, _, resp, _ = self._prove(eng, transcript_label, secrets, points_limbs, rng_seed, False)
         return (chal.tobytes(), resp), enc
 
-    def prove_batchable(self, eng, transcript_label, secrets, points_limbs, rng_seed):
+    def prove_batchable(self, eng, transcript_label, secrets, points_limbs, rng_seed=None):
         """-> ((commitments, responses), encodings)   (macros.rs:271-278)"""
         enc, _, com, resp, _ = self._prove(eng, transcript_label, secrets, points_limbs, rng_seed, True)
         return (com, resp), enc
@@ -184,23 +200,27 @@ class Statement:
             _raise(_lib().zkph_verify_compact(eng._ctx, self._h, transcript_label, len(transcript_label), _p(enc),
                                               bytes(chal), _p(resp), resp.shape[0]))
 
-    def verify_batchable(self, eng, proof, transcript_label, encodings, rng_seed):
+    def verify_batchable(self, eng, proof, transcript_label, encodings, rng_seed=None):
         com, resp = proof
         com, resp, enc = _u8(com, 32), _u8(resp, 32), _u8(encodings, 32)
         assert enc.shape[0] == self.p
+        seed, seed_len = _seed(rng_seed)
         if isinstance(transcript_label, Transcript):
             _raise(_lib().zkph_verify_batchable_t(eng._ctx, self._h, transcript_label._h, _p(enc), _p(com), com.shape[0],
-                                                  _p(resp), resp.shape[0], rng_seed, len(rng_seed)))
+                                                  _p(resp), resp.shape[0], seed, seed_len))
         else:
             _raise(_lib().zkph_verify_batchable(eng._ctx, self._h, transcript_label, len(transcript_label), _p(enc), _p(com),
-                                                com.shape[0], _p(resp), resp.shape[0], rng_seed, len(rng_seed)))
+                                                com.shape[0], _p(resp), resp.shape[0], seed, seed_len))
 
     # ---- module::batch_verify ---------------------------------------------------------------------------------
     def batch_verify(self, eng, proofs_commitments, proofs_responses, transcript_label, instance_enc, common_enc,
-                     rng_seed, threads=0, want_msm_inputs=False):
+                     rng_seed=None, threads=0, want_msm_inputs=False):
         """proofs_commitments (N,k,32), proofs_responses (N,m,32), instance_enc (n_instance,N,32), common_enc
         (n_common,32).  Raises VerificationFailure / BatchSizeMismatch like the reference.  With
-        want_msm_inputs returns (scalars, points, host_seconds) exactly as fed to the MSM."""
+        want_msm_inputs returns (scalars, points, host_seconds) exactly as fed to the MSM.
+        transcript_label: one label (bytes) shared by all proofs, or -- the reference's own signature, macros.rs:336-346 --
+        a list of Transcript objects, one per proof, each with its own prior state; they are left advanced, and a list
+        whose length differs from the number of proofs is BatchSizeMismatch (batch_verifier.rs:72-74)."""
         com = np.ascontiguousarray(proofs_commitments, dtype=np.uint8)
         resp = np.ascontiguousarray(proofs_responses, dtype=np.uint8)
         inst = np.ascontiguousarray(instance_enc, dtype=np.uint8)
@@ -213,8 +233,16 @@ class Statement:
         co = np.zeros((n, 32), np.uint8) if want_msm_inputs else None
         po = np.zeros((n, 32), np.uint8) if want_msm_inputs else None
         hs = ctypes.c_double(0)
+        seed, seed_len = _seed(rng_seed)
+        if isinstance(transcript_label, (list, tuple)):
+            if want_msm_inputs:
+                raise ValueError("want_msm_inputs needs the shared-label form")
+            handles = (ctypes.c_void_p * len(transcript_label))(*[t._h for t in transcript_label])
+            _raise(_lib().zkph_batch_verify_t(eng._ctx, self._h, handles, len(transcript_label), N, _p(inst), _p(comm),
+                                              _p(com), _p(resp), seed, seed_len, int(threads)))
+            return 0.0
         rc = _lib().zkph_batch_verify(eng._ctx, self._h, transcript_label, len(transcript_label), N, _p(inst), _p(comm),
-                                      _p(com), _p(resp), rng_seed, len(rng_seed), int(threads), _p(co), _p(po),
+                                      _p(com), _p(resp), seed, seed_len, int(threads), _p(co), _p(po),
                                       ctypes.byref(hs))
         _raise(rc)
         if want_msm_inputs:
@@ -222,7 +250,7 @@ class Statement:
         return hs.value
 
     def batch_verify_device(self, eng, proofs_commitments, proofs_responses, transcript_label, instance_enc, common_enc,
-                            rho_seed32, want_msm_inputs=False):
+                            rho_seed32=None, want_msm_inputs=False):
         """module::batch_verify with transcripts, challenges, weights and the coefficient fold on the GPU
         (zkp_batch_verify_proofs).  Same arguments as batch_verify; rho_seed32 seeds the per-proof weights."""
         com = np.ascontiguousarray(proofs_commitments, dtype=np.uint8)
@@ -233,23 +261,24 @@ class Statement:
         if resp.shape[0] != N or inst.shape[1] != N:
             raise BatchSizeMismatch()
         assert com.shape[1:] == (self.k, 32) and resp.shape[1:] == (self.m, 32) and inst.shape[0] == len(self.instance)
-        assert len(rho_seed32) == 32
+        assert rho_seed32 is None or len(rho_seed32) == 32       # None: 32 fresh bytes from the OS CSPRNG
         n = len(self.common) + (len(self.instance) + self.k) * N
         co = np.zeros((n, 32), np.uint8) if want_msm_inputs else None
         po = np.zeros((n, 32), np.uint8) if want_msm_inputs else None
         rc = _lib().zkph_batch_verify_device(eng._ctx, self._h, transcript_label, len(transcript_label), N, _p(inst),
-                                             _p(comm), _p(com), _p(resp), bytes(rho_seed32), _p(co), _p(po))
+                                             _p(comm), _p(com), _p(resp), _seed(rho_seed32)[0], _p(co), _p(po))
         if want_msm_inputs and rc in (0, 1):
             self._last_msm_inputs = (co, po)
         _raise(rc)
         return (co, po) if want_msm_inputs else None
 
     # ---- N proofs at once (no counterpart in the reference; = N x prove_batchable) ----------------------------
-    def prove_many(self, eng, transcript_label, secrets, points_limbs, entropy, threads=0):
+    def prove_many(self, eng, transcript_label, secrets, points_limbs, entropy=None, threads=0):
+        """entropy (N, 32): the 32 bytes per proof the reference takes from thread_rng (prover.rs:82); None = OS CSPRNG."""
         sec = np.ascontiguousarray(secrets, dtype=np.uint8).reshape(-1, self.m, 32)
         N = sec.shape[0]
         pts = np.ascontiguousarray(points_limbs, dtype=np.uint64).reshape(N, self.p, 20)
-        ent = np.ascontiguousarray(entropy, dtype=np.uint8).reshape(N, 32)
+        ent = None if entropy is None else np.ascontiguousarray(entropy, dtype=np.uint8).reshape(N, 32)
         enc = np.zeros((N, self.p, 32), np.uint8)
         com = np.zeros((N, self.k, 32), np.uint8)
         resp = np.zeros((N, self.m, 32), np.uint8)
@@ -258,7 +287,7 @@ class Statement:
         return enc, com, resp
 
 
-    def prove_many_device(self, eng, transcript_label, secrets, points_limbs, entropy, out=None):
+    def prove_many_device(self, eng, transcript_label, secrets, points_limbs, entropy=None, out=None):
         """prove_many with the per-proof transcript, nonce and response work on the GPU (zkp_prove_batch): the host hashes
         only the batch-wide transcript prefix.  Byte-identical to prove_many.  `out` = preallocated (encodings[N][p][32],
         commitments[N][k][32], responses[N][m][32]) uint8 arrays; inputs and outputs in pinned host memory avoid the
@@ -266,7 +295,7 @@ class Statement:
         sec = np.ascontiguousarray(secrets, dtype=np.uint8).reshape(-1, self.m, 32)
         N = sec.shape[0]
         pts = np.ascontiguousarray(points_limbs, dtype=np.uint64).reshape(N, self.p, 20)
-        ent = np.ascontiguousarray(entropy, dtype=np.uint8).reshape(N, 32)
+        ent = None if entropy is None else np.ascontiguousarray(entropy, dtype=np.uint8).reshape(N, 32)
         if out is not None:
             enc, com, resp = out
             for a, shp in ((enc, (N, self.p, 32)), (com, (N, self.k, 32)), (resp, (N, self.m, 32))):
