@@ -215,13 +215,11 @@ def main():
     ap.add_argument("--window", type=int, default=0, help="tuning: force the Pippenger window width")
     ap.add_argument("--chunk", type=int, default=0, help="tuning: force the accumulate work-item length")
     ap.add_argument("--no-proofs-leg", action="store_true", help="skip the e2e_from_proofs leg (real proofs, device front end)")
-    ap.add_argument("--no-overlap", action="store_true", help="tuning: run the digit sort on the compute stream")
     ap.add_argument("--chunk-terms-log2", type=int, default=0, help="tuning: H2D pipeline chunk (terms) for the e2e leg")
     ap.add_argument("--ingest-variant", type=int, default=-1, help="tuning: occupancy point of k_ingest2 (0..3)")
     ap.add_argument("--phase1-percent", type=int, default=0, help="tuning: share of point chunks in the first ingestion phase (e2e)")
     ap.add_argument("--no-numa-bind", action="store_true", help="tuning: do not pin ranks to their GPU's NUMA node")
     ap.add_argument("--bv-chunk-terms-log2", type=int, default=0, help="tuning: slab size (terms) of the from-proofs leg")
-    ap.add_argument("--ramp", action="store_true", help="tuning: ramped H2D chunk schedule instead of uniform chunks (e2e)")
     ap.add_argument("--dual-stream", type=int, default=-1, help="tuning: chunk kernels of the e2e leg on two alternating streams (0/1)")
     ap.add_argument("--no-fused-sort", action="store_true", help="tuning: separate scatter pass instead of the two-phase ingestion")
     ap.add_argument("--sweep", default="", help="tuning: comma list of windows; prints stage times per window and exits")
@@ -332,12 +330,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    if args.no_overlap:
-        eng.set_option("overlap", 0)
     if args.no_fused_sort:
         eng.set_option("fused_sort", 0)
-    if args.ramp:
-        eng.set_option("ramp_chunks", 1)
     if args.bv_chunk_terms_log2:
         eng.set_option("bv_chunk_terms", 1 << args.bv_chunk_terms_log2)
     if args.dual_stream >= 0:

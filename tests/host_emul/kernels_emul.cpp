@@ -40,7 +40,7 @@ static int run_msms(const pv_desc& d, const pv_plan& plan, int nc, size_t N, con
       emul_launch_mt((unsigned)((N + 31) / 32), 32 * nw, k_comb_msm_cta, (const uint32_t*)rec.data(),
                      (const uint4*)combs.data(), (const uint4*)shared.data(), plan.term_slot.data(), plan.unit_term0.data(),
                      plan.unit_nterms.data(), plan.cons_unit0.data(), N, (uint32_t)T, (uint32_t)U, (uint32_t)Us, n_units,
-                     (uint32_t)k, out.data(), 0u);
+                     (uint32_t)k, out.data());
     } else {
     emul_launch((unsigned)((total + 255) / 256), 256, k_comb_recode, (const uint4*)scalars_flat.data(), total, biased.data());
     emul_launch((unsigned)((M + 63) / 64), 64, k_small_msm_comb, (const uint32_t*)biased.data(), (const uint4*)combs.data(),

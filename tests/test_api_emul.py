@@ -40,7 +40,7 @@ def api():
         subprocess.check_call(["python", os.path.join(EMUL, "make_api_emul.py")])
         # -Bsymbolic: the library's cuda* calls must reach ITS runtime stand-in even when a real libcudart is in the process
         subprocess.check_call(["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-pthread", "-Wl,-Bsymbolic",
-                               "-DZKP_HOST_EMUL",
+                               "-DZKP_HOST_EMUL", "-DZKP_ABLATIONS",
                                "-I/usr/local/cuda/include", "-I" + csrc, "-I" + EMUL,
                                os.path.join(EMUL, "api_emul_generated.cpp"), os.path.join(EMUL, "cudart_shim.cpp"),
                                os.path.join(csrc, "host", "merlin.cpp"), "-o", out])

@@ -8,6 +8,18 @@ from tests import util_data as U
 pytestmark = pytest.mark.gpu
 
 
+def _ablations(engine):
+    """True if the library was built with -DZKP_ABLATIONS (python -m zkp_b200.build --ablations): the measured-negative
+    paths (second-stream sort, ramped chunk schedule, byte-wise STROBE front end) are not in the product library."""
+    from zkp_b200 import EngineError
+    try:
+        engine.set_option("overlap", 1)
+    except EngineError:
+        return False
+    engine.set_option("overlap", 0)
+    return True
+
+
 def _h(xs):
     return np.frombuffer(b"".join(bytes.fromhex(x) for x in xs), dtype=np.uint8).reshape(-1, 32)
 
@@ -315,7 +327,10 @@ def test_host_pipeline_chunking_overlap_and_profile_options(engine):
     sc = U.random_scalars(case["n"], seed=case["seed"])
     pts = np.frombuffer(b"".join(base[i % case["K"]] for i in range(case["n"])), dtype=np.uint8).reshape(-1, 32)
     try:
-        for opts in ({"chunk_terms": 4096}, {"chunk_terms": 4096, "overlap": 1}, {"profile": 1}, {"overlap": 1}):
+        cases = [{"chunk_terms": 4096}, {"profile": 1}, {"chunk_terms": 1 << 16}]
+        if _ablations(engine):
+            cases += [{"chunk_terms": 4096, "overlap": 1}, {"overlap": 1}]
+        for opts in cases:
             for k, v in opts.items():
                 engine.set_option(k, v)
             enc, _, _ = engine.msm_vartime(sc, pts)
@@ -352,7 +367,8 @@ def test_two_phase_ingestion_and_item_balance_options(engine):
                 engine.set_option("balance", balance)
                 for chunk in (1 << 21, 4096, 5000, n // 3 + 1, n):       # 1 chunk, many, ragged, 3 chunks (odd), exactly 1
                     engine.set_option("chunk_terms", max(chunk, 1024))
-                    for ramp, dual in ((1, 0), (0, 0), (0, 1), (1, 1)):   # ramped / uniform chunks, one / two streams
+                    # uniform chunks on one / two streams (and the ramped schedule where the ablations are built in)
+                    for ramp, dual in (((1, 0), (0, 0), (0, 1), (1, 1)) if _ablations(engine) else ((0, 0), (0, 1))):
                         engine.set_option("ramp_chunks", ramp)
                         engine.set_option("dual_stream", dual)
                         enc, _, _ = engine.msm_vartime(sc, pts)

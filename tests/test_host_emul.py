@@ -20,7 +20,7 @@ def lib():
     out = os.path.join(HERE, "host_emul", "libemul.so")
     deps = [src] + [os.path.join(HERE, "..", "zkp_b200", "csrc", f) for f in ("fe.cuh", "fe64.cuh", "ge.cuh", "sc.cuh", "hash.cuh", "scl.cuh", "comb.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
-        subprocess.check_call(["g++", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-DZKP_HOST_EMUL", "-x", "c++", src, "-o", out])
+        subprocess.check_call(["g++", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-DZKP_HOST_EMUL", "-DZKP_ABLATIONS", "-x", "c++", src, "-o", out])
     return ctypes.CDLL(out)
 
 
@@ -357,7 +357,7 @@ def klib():
                                                                     if f.endswith((".cuh", ".hpp"))]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         subprocess.check_call(["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-pthread",
-                               "-DZKP_HOST_EMUL", "-I/usr/local/cuda/include", src, "-o", out])
+                               "-DZKP_HOST_EMUL", "-DZKP_ABLATIONS", "-I/usr/local/cuda/include", src, "-o", out])
     return ctypes.CDLL(out)
 
 

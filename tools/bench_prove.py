@@ -1,5 +1,4 @@
-"""Tuning sweep of zkp_prove_batch (2^LOG2 CMZ cred_show_10 proofs, pinned host buffers): the prover paths, the warp
-stagger of the CTA-staged kernel, the slice size of the copy/compute pipeline.  Usage: python tools/bench_prove.py
+"""Tuning sweep of zkp_prove_batch (2^LOG2 CMZ cred_show_10 proofs, pinned host buffers): the prover paths and the slice size of the copy/compute pipeline.  Usage: python tools/bench_prove.py
 [--log2 16] [--out gpurun_out/prove.json] [--quick]"""
 import json
 import os
@@ -24,16 +23,13 @@ sec_p, limbs_p, ent_p = pin(sec), pin(limbs), pin(entropy)
 outs = tuple(torch.zeros(shp, dtype=torch.uint8).pin_memory().numpy() for shp in ((N, 25, 32), (N, 11, 32), (N, 21, 32)))
 ref = None
 rows = []
-DEFAULTS = {"prove_comb": 2, "prove_stagger_ns": 0, "prove_pipe_chunk": 1 << 14, "prove_piece": 2}
+DEFAULTS = {"prove_comb": 2, "prove_pipe_chunk": 1 << 14, "prove_piece": 2}
 cases = [{"prove_comb": 0, "prove_pipe_chunk": 0}, {"prove_comb": 1, "prove_pipe_chunk": 0}, {"prove_comb": 2, "prove_pipe_chunk": 0}]
-for stg in (1000, 2000, 4000, 6000, 8000, 12000):
-    cases.append({"prove_pipe_chunk": 0, "prove_stagger_ns": stg})
 for pc in (1 << 12, 1 << 13, 1 << 14, 1 << 15):
     cases.append({"prove_pipe_chunk": pc})
-cases += [{"prove_pipe_chunk": 1 << 14, "prove_stagger_ns": 4000}, {"prove_piece": 3, "prove_pipe_chunk": 0},
-          {"prove_piece": 1, "prove_pipe_chunk": 0}]
+cases += [{"prove_piece": 3, "prove_pipe_chunk": 0}, {"prove_piece": 1, "prove_pipe_chunk": 0}]
 if "--quick" in sys.argv:
-    cases = cases[:3] + cases[9:13]
+    cases = [{"prove_comb": 1, "prove_pipe_chunk": 0}, {"prove_pipe_chunk": 0}, {}, {"prove_pipe_chunk": 1 << 15}]
 for case in cases:
     opts = dict(DEFAULTS)
     opts.update(case)

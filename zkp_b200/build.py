@@ -35,13 +35,17 @@ def _stale():
     return any(os.path.getmtime(f) > t for f in [os.path.join(CSRC, s) for s in SOURCES] + _headers())
 
 
-def build(force=False, verbose=False):
-    """Compile zkp_b200/csrc/*.cu -> zkp_b200/lib/libzkp_b200.so (sm_100a, -lineinfo)."""
+def build(force=False, verbose=False, ablations=False):
+    """Compile zkp_b200/csrc/*.cu -> zkp_b200/lib/libzkp_b200.so (sm_100a, -lineinfo).  ablations=True also compiles the
+    measured-negative paths (-DZKP_ABLATIONS: second-stream sort, ramped chunk schedule, byte-wise STROBE front end, FP64
+    field arithmetic): for re-measuring them, not for the product."""
     if not force and not _stale():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
            "-Xcompiler", "-fPIC,-pthread", "-shared", "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    if ablations:
+        cmd.insert(1, "-DZKP_ABLATIONS")
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
@@ -51,4 +55,5 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv or "--ablations" in sys.argv, verbose="-v" in sys.argv,
+                ablations="--ablations" in sys.argv))

@@ -23,6 +23,19 @@
 
 using namespace zkp;
 
+// Paths that were measured and lost stay in the source as ablations but out of the product
+// library: built only with -DZKP_ABLATIONS (the host-emulation tests do; `python -m zkp_b200.build --ablations`).
+//   overlap        digit sort on a second stream beside the decompression      (159.2 vs 159.9 ms per step: neutral)
+//   ramp_chunks    ramped H2D chunk schedule                                   (138.6 vs 135.8 ms per step: slower)
+//   bv_compiled=0  byte-wise STROBE front end k_bv_prepare                     (~40 vs 18 ms per 2^21 proofs)
+//   k_ingest       single-phase fused ingestion (histogram only)               (superseded by k_ingest2)
+//   fe64 / bench   FP64-pipe field arithmetic and the mixed-pipe micro-benchmarks (no gain: section 3)
+#ifdef ZKP_ABLATIONS
+#define ZKP_ABL(x) (x)
+#else
+#define ZKP_ABL(x) (0)
+#endif
+
 struct devbuf {
   void* p = nullptr;
   size_t cap = 0;
@@ -101,11 +114,11 @@ struct zkp_ctx {
   // one small MSM (zkp_msm_vartime / zkp_batch_verify / zkp_msm_vartime_dev with few terms): up to this many terms skip the
   // sort pipeline and run as groups of four lanes over the terms (k_single_msm_vt) -- the reference's own size dispatch
   // (n < 190 -> Straus, /root/reference/src/toolbox/verifier.rs:162-166 -> dalek edwards.rs [ext]); 0 = always Pippenger
-  int small_max = 1024;
-  int small_groups = 1024;    // at most this many four-lane groups share the terms
-  int prove_stagger_ns = 0;   // CTA-staged comb kernel: start offset between the warps of one scheduler (0 = none)
+  int small_max = 4096;
+  int small_groups = 4096;    // at most this many four-lane groups share the terms (measured: profiles/r02_small_msm.json)
   int prove_piece = 2;        // CTA-staged comb kernel (prove_comb = 2): terms per unit (pv_make_units)
   int smem_optin = -1;        // cudaDevAttrMaxSharedMemoryPerBlockOptin, read once
+  int sm_count = -1;          // cudaDevAttrMultiProcessorCount, read once
   size_t cta_smem_set = 0;    // dynamic shared memory k_comb_msm_cta has been allowed so far
   int bv_compiled = 1;      // batch-verification front end: host-compiled transcript script (k_bv_prepare2)
   int ingest_variant = 2;   // occupancy point of k_ingest2 (kernels.cuh ZKP_INGEST_*)
@@ -257,6 +270,7 @@ extern "C" int32_t zkp_ctx_set_option(zkp_ctx* ctx, const char* key, int64_t val
     if (value < 4 || value > 24) return ZKP_ERR_SIZE;
     ctx->window_cap = (int)value;
   } else if (!strcmp(key, "overlap")) {
+    if (value && !ZKP_ABL(1)) return ZKP_ERR_SIZE;   // ablation: not in the product build
     ctx->overlap = value ? 1 : 0;
   } else if (!strcmp(key, "balance")) {
     ctx->balance = value ? 1 : 0;
@@ -283,13 +297,11 @@ extern "C" int32_t zkp_ctx_set_option(zkp_ctx* ctx, const char* key, int64_t val
   } else if (!strcmp(key, "small_groups")) {
     if (value < 1 || value > (1 << 16)) return ZKP_ERR_SIZE;
     ctx->small_groups = (int)value;
-  } else if (!strcmp(key, "prove_stagger_ns")) {
-    if (value < 0 || value > 200000) return ZKP_ERR_SIZE;
-    ctx->prove_stagger_ns = (int)value;
   } else if (!strcmp(key, "prove_piece")) {
     if (value < 1 || value > 64) return ZKP_ERR_SIZE;
     ctx->prove_piece = (int)value;
   } else if (!strcmp(key, "bv_compiled")) {
+    if (!value && !ZKP_ABL(1)) return ZKP_ERR_SIZE;   // ablation: not in the product build
     ctx->bv_compiled = value ? 1 : 0;
   } else if (!strcmp(key, "ingest_variant")) {
     if (value < 0 || value > 3) return ZKP_ERR_SIZE;
@@ -297,6 +309,7 @@ extern "C" int32_t zkp_ctx_set_option(zkp_ctx* ctx, const char* key, int64_t val
   } else if (!strcmp(key, "fused_sort")) {
     ctx->fused_sort = value ? 1 : 0;
   } else if (!strcmp(key, "ramp_chunks")) {
+    if (value && !ZKP_ABL(1)) return ZKP_ERR_SIZE;   // ablation: not in the product build
     ctx->ramp_chunks = value ? 1 : 0;
   } else if (!strcmp(key, "dual_stream")) {
     ctx->dual_stream = value ? 1 : 0;
@@ -410,7 +423,7 @@ static int32_t msm_prepare(zkp_ctx* ctx, size_t n, msm_plan* pl) {
   LAUNCH_CHECK(ctx);
   CUDA_TRY(ctx, cudaMemsetAsync(ctx->hist.p, 0, (size_t)W * B * 4, st));
   pl->sort = st;
-  if (ctx->overlap && !ctx->profile) {
+  if (ZKP_ABL(ctx->overlap) && !ctx->profile) {
     if (!ctx->sort_stream) {
       int lo = 0, hi = 0;
       CUDA_TRY(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -435,12 +448,14 @@ static int32_t msm_ingest(zkp_ctx* ctx, const msm_plan& pl, const void* d_scalar
   cudaStream_t st = ctx->stream;
   int* flags = (int*)ctx->flags.p;
   const unsigned nb = (unsigned)((cnt + 255) / 256);
+#ifdef ZKP_ABLATIONS
   if (!ctx->profile && pl.sort == st) {   // fused: histogram reductions ride along with the decompression
     k_ingest<<<nb, 256, 0, st>>>((const uint4*)d_points + 2 * base, (const uint4*)d_scalars + 2 * base, cnt,
                                  (uint4*)ctx->niels.p + 6 * base, pl.c, pl.W, pl.B, (uint32_t*)ctx->hist.p, flags, base);
     LAUNCH_CHECK(ctx);
     return ZKP_OK;
   }
+#endif
   if (whole) STAGE(0);
   k_decompress<<<nb, 256, 0, st>>>((const uint4*)d_points + 2 * base, cnt, (uint4*)ctx->niels.p + 6 * base, flags, base);
   LAUNCH_CHECK(ctx);
@@ -823,7 +838,7 @@ static int32_t msm_from_host(zkp_ctx* ctx, const hseg* sc_segs, const hseg* pt_s
   std::vector<size_t> bnd;
   size_t K1 = 0;
   try {
-    chunk_schedule(n, chunk, ctx->phase1_percent, fused && ctx->ramp_chunks, &bnd, &K1);
+    chunk_schedule(n, chunk, ctx->phase1_percent, fused && ZKP_ABL(ctx->ramp_chunks), &bnd, &K1);
   } catch (...) {
     ctx->err = "host allocation failed";
     return ZKP_ERR_NOMEM;
@@ -1247,16 +1262,18 @@ static int32_t batch_verify_proofs_impl(zkp_ctx* ctx, const zkp_statement_desc* 
     CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->chunk_ev[cidx], 0));
     if (pl.sort != st) CUDA_TRY(ctx, cudaStreamWaitEvent(pl.sort, ctx->chunk_ev[cidx], 0));
     const unsigned nb = (unsigned)((cnt + 127) / 128);
-    if (ctx->bv_compiled)
+#ifdef ZKP_ABLATIONS
+    if (!ctx->bv_compiled)
+      k_bv_prepare<<<nb, 128, 0, st>>>(d, (const uint32_t*)(dm + o_prefix), N, dpts + (size_t)nc * 32, dpts,
+                                       (const uint8_t*)ctx->bv_com.p, (const uint8_t*)ctx->bv_resp.p, dm + o_seed, dsc, dpts,
+                                       (uint8_t*)ctx->bv_part.p, nullptr, (int*)ctx->flags.p, j0, cnt, block_base);
+    else
+#endif
       k_bv_prepare2<<<nb, 128, 0, st>>>(d, (const uint32_t*)(dm + o_prefix), N, dpts + (size_t)nc * 32,
                                         (const uint8_t*)ctx->bv_com.p, (const uint8_t*)ctx->bv_resp.p, dm + o_seed,
                                         script_blocks, (const unsigned long long*)(dm + o_tm),
                                         (const uint32_t*)(dm + o_ss), (const bv_seg*)(dm + o_sg), dsc, dpts,
                                         (uint8_t*)ctx->bv_part.p, nullptr, (int*)ctx->flags.p, j0, cnt, block_base);
-    else
-      k_bv_prepare<<<nb, 128, 0, st>>>(d, (const uint32_t*)(dm + o_prefix), N, dpts + (size_t)nc * 32, dpts,
-                                       (const uint8_t*)ctx->bv_com.p, (const uint8_t*)ctx->bv_resp.p, dm + o_seed, dsc, dpts,
-                                       (uint8_t*)ctx->bv_part.p, nullptr, (int*)ctx->flags.p, j0, cnt, block_base);
     LAUNCH_CHECK(ctx);
     block_base += nb;
     // the slabs of this chunk are complete (points and coefficients)
@@ -1511,7 +1528,7 @@ static int32_t prove_slice_enqueue(zkp_ctx* ctx, pv_set& S, const zkp_statement_
             (const uint32_t*)S.sk0.p, (const uint4*)S.tables.p, (const uint4*)S.pv_static.p,
             (const int32_t*)(dm + o_cs), (const int32_t*)(dm + o_ut), (const int32_t*)(dm + o_un),
             (const int32_t*)(dm + o_cu), N, (uint32_t)n_terms, (uint32_t)U, (uint32_t)Us, (uint32_t)n_units, (uint32_t)k,
-            (uint4*)S.aux1.p, (uint32_t)ctx->prove_stagger_ns);
+            (uint4*)S.aux1.p);
         LAUNCH_CHECK(ctx);
       } else {
       k_comb_recode<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const uint4*)S.in_scalars.p, total, (uint4*)S.sk0.p);
@@ -1606,7 +1623,21 @@ static int32_t prove_batch_run(zkp_ctx* ctx, const zkp_statement_desc* sd, const
   // slices: at most prove_chunk proofs (workspace bound: tables), and at most prove_pipe_chunk when the batch is large
   // enough to be worth pipelining (copies of one slice under the kernels of another)
   size_t chunk = ctx->prove_chunk;
-  if (ctx->prove_pipe_chunk && N >= 2 * ctx->prove_pipe_chunk && ctx->prove_pipe_chunk < chunk) chunk = ctx->prove_pipe_chunk;
+  if (ctx->prove_pipe_chunk && N >= 2 * ctx->prove_pipe_chunk && ctx->prove_pipe_chunk < chunk) {
+    // about prove_pipe_chunk proofs per slice, rounded so that a slice is a whole number of waves of the CTA-staged MSM
+    // kernel (one CTA = 32 proofs, one CTA per SM): 2^14-proof slices on 148 SMs would run 3.46 waves, 13 % of them idle
+    if (ctx->sm_count < 0) CUDA_TRY(ctx, cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, ctx->device));
+    const size_t wave = (size_t)32 * (size_t)(ctx->sm_count > 0 ? ctx->sm_count : 1);
+    if (ctx->prove_pipe_chunk >= wave) {
+      const size_t slices = (N + ctx->prove_pipe_chunk / 2) / ctx->prove_pipe_chunk;          // >= 2
+      const size_t waves_total = (N + wave - 1) / wave;
+      const size_t waves_per_slice = (waves_total + slices - 1) / slices;
+      chunk = waves_per_slice * wave;
+    } else {
+      chunk = ctx->prove_pipe_chunk;   // slices smaller than a wave: taken as given (tests)
+    }
+    if (chunk > ctx->prove_chunk) chunk = ctx->prove_chunk;
+  }
   pv_slice cur[2];
   bool pending[2] = {false, false};
   auto drain = [&]() {
@@ -1923,6 +1954,7 @@ extern "C" int32_t zkp_selftest_hash(zkp_ctx* ctx, uint8_t* out32) {
   return ZKP_OK;
 }
 
+#ifdef ZKP_ABLATIONS
 // diagnostic: integer squaring warps and FP64 warps side by side; returns milliseconds
 extern "C" int32_t zkp_bench_dual(zkp_ctx* ctx, int32_t mode, int32_t iters, double* ms_out) {
   if (!ctx || !ms_out || iters <= 0 || mode < 0 || mode > 2) return ZKP_ERR_SIZE;
@@ -1950,8 +1982,12 @@ extern "C" int32_t zkp_bench_dual(zkp_ctx* ctx, int32_t mode, int32_t iters, dou
   return ZKP_OK;
 }
 
+#else
+extern "C" int32_t zkp_bench_dual(zkp_ctx*, int32_t, int32_t, double*) { return ZKP_ERR_SIZE; }   // ablation build only
+#endif
+
 extern "C" int32_t zkp_bench_field(zkp_ctx* ctx, int32_t kind, int32_t iters, double* ops_per_sec) {
-  if (!ctx || !ops_per_sec || iters <= 0 || kind < 0 || kind > 16) return ZKP_ERR_SIZE;
+  if (!ctx || !ops_per_sec || iters <= 0 || kind < 0 || kind > (ZKP_ABL(1) ? 16 : 11)) return ZKP_ERR_SIZE;
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   int sms = 0;
   CUDA_TRY(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
@@ -1977,11 +2013,13 @@ extern "C" int32_t zkp_bench_field(zkp_ctx* ctx, int32_t kind, int32_t iters, do
       case 9: k_bench_sq32<0, true><<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, iters); break;
       case 10: k_bench_madd<false><<<blocks * 2, threads / 2, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, iters); break;
       case 11: k_bench_madd<true><<<blocks * 2, threads / 2, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, iters); break;
+#ifdef ZKP_ABLATIONS
       case 12: k_bench_sq_mixed<0><<<sms * 2, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, pool_units, (unsigned int*)ctx->aux1.p); break;
       case 13: k_bench_sq_mixed<2><<<sms * 2, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, pool_units, (unsigned int*)ctx->aux1.p); break;
       case 14: k_bench_sq_mixed<3><<<sms * 2, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, pool_units, (unsigned int*)ctx->aux1.p); break;
       case 15: k_bench_sq_mixed<4><<<sms * 2, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, pool_units, (unsigned int*)ctx->aux1.p); break;
       case 16: k_bench_sq_mixed<8><<<sms * 2, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, pool_units, (unsigned int*)ctx->aux1.p); break;
+#endif
       case 2: k_bench_mul51<<<blocks, threads, 0, ctx->stream>>>((unsigned long long*)ctx->aux0.p, iters); break;
       case 3: k_bench_mul25<<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, iters); break;
       case 4: k_bench_wide_plain<<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, iters); break;

@@ -5,7 +5,9 @@
 #pragma once
 #include "fe.cuh"
 #include "ge.cuh"
-#include "fe64.cuh"
+#ifdef ZKP_ABLATIONS
+#include "fe64.cuh"   // FP64-pipe field arithmetic: a measured ablation, not in the product library
+#endif
 
 namespace zkp {
 
@@ -64,6 +66,7 @@ __global__ void __launch_bounds__(128, 4) k_bench_madd(uint32_t* out, int iters)
   for (int i = 0; i < 8; i++) out[(size_t)gid * 16 + i] = acc.X.v[i] ^ acc.Y.v[i] ^ acc.Z.v[i] ^ acc.T.v[i];
 }
 
+#ifdef ZKP_ABLATIONS
 // ---- integer and FP64 squaring chains side by side: warps [0, NFP) of every 8-warp block square on the FP64 pipe
 // (fe64_sq), the others on the integer pipes (fe_sq, variable-time tail).  Work is handed out dynamically: a warp
 // takes the next unit (a chain of 256 squarings per lane) from a global counter until `units` are done, so slower
@@ -101,6 +104,8 @@ __global__ void __launch_bounds__(256, 2) k_bench_sq_mixed(uint32_t* out, int un
   }
   out[gid] = x;
 }
+
+#endif  // ZKP_ABLATIONS
 
 // ---- 5 x 51-bit limbs, 64x64->128 products (the layout of dalek's u64 backend, FieldElement51::mul [ext]) --
 struct fe51 { unsigned long long v[5]; };
@@ -254,6 +259,7 @@ __global__ void __launch_bounds__(256) k_bench_wide_carry(uint32_t* out, int ite
 }
 
 
+#ifdef ZKP_ABLATIONS
 // ---- can the FP64 pipe run beside the integer pipe?  Odd warps run the fe_sq chain, even warps run a chain of
 // DFMAs (16 independent accumulators, `fp64_per_iter` DFMAs per loop trip).  mode 0: both, 1: only integer warps
 // (the others exit), 2: only FP64 warps.  Reported through zkp_bench_dual.
@@ -290,5 +296,7 @@ __global__ void __launch_bounds__(256) k_bench_dual(uint32_t* out, int iters, in
     out[(size_t)gid * 16] = (uint32_t)__double2loint(s);
   }
 }
+
+#endif  // ZKP_ABLATIONS
 
 }  // namespace zkp

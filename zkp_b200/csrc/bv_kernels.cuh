@@ -109,6 +109,7 @@ __device__ __forceinline__ void bv_static_block_sums(const bv_desc& d, const scl
   }
 }
 
+#ifdef ZKP_ABLATIONS   // byte-wise STROBE on the device: the cross-check of k_bv_prepare2 (api.cu: bv_compiled = 0)
 // Per proof j: replay the transcript, derive the challenge, draw the weights, fold the coefficients.
 //   prefix        strobe state shared by all proofs (user transcript + dom-sep + scalar labels), 53 words
 //   instance_enc  [ni][N][32]   commitments [N][k][32]   responses [N][m][32]   common_enc [nc][32]
@@ -177,6 +178,8 @@ __global__ void __launch_bounds__(128) k_bv_prepare(bv_desc d, const uint32_t* _
   }
   bv_static_block_sums(d, stat, red, static_part, block_base + blockIdx.x);
 }
+
+#endif  // ZKP_ABLATIONS
 
 // -----------------------------------------------------------------------------------------------------------------
 // The same front end with the transcript COMPILED on the host.  Every proof of a batch follows the same script (same

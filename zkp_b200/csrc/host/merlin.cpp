@@ -1,4 +1,6 @@
 #include "merlin.hpp"
+#include <stdio.h>
+#include <stdlib.h>
 
 namespace zkp_host {
 
@@ -105,10 +107,29 @@ static inline void u32le(uint8_t out[4], size_t n) {
   out[0] = (uint8_t)n; out[1] = (uint8_t)(n >> 8); out[2] = (uint8_t)(n >> 16); out[3] = (uint8_t)(n >> 24);
 }
 
+// ZKP_DEBUG_TRANSCRIPT=1 in the environment: everything fed to (and drawn from) a host transcript goes to stderr, like
+// the reference's `debug-transcript` feature (Cargo.toml:35 -> merlin/debug-transcript, README.md:76-79).  For comparing
+// transcripts with another implementation byte by byte; it prints challenges, so never in production.
+static bool debug_transcript() {
+  static const bool on = [] {
+    const char* e = getenv("ZKP_DEBUG_TRANSCRIPT");
+    return e && *e && *e != '0';
+  }();
+  return on;
+}
+static void debug_line(const char* op, const uint8_t* label, size_t llen, const uint8_t* data, size_t dlen) {
+  fprintf(stderr, "[zkp transcript] %s label=\"", op);
+  for (size_t i = 0; i < llen; i++) fputc(label[i] >= 32 && label[i] < 127 ? label[i] : '.', stderr);
+  fprintf(stderr, "\" len=%zu data=", dlen);
+  for (size_t i = 0; i < dlen; i++) fprintf(stderr, "%02x", data[i]);
+  fputc('\n', stderr);
+}
+
 Transcript::Transcript(const uint8_t* label, size_t len) : strobe_((const uint8_t*)"Merlin v1.0", 11) {
   append_message((const uint8_t*)"dom-sep", 7, label, len);
 }
 void Transcript::append_message(const uint8_t* label, size_t llen, const uint8_t* msg, size_t mlen) {
+  if (debug_transcript()) debug_line("append_message", label, llen, msg, mlen);
   uint8_t l4[4];
   u32le(l4, mlen);
   strobe_.meta_ad(label, llen, false);
@@ -121,6 +142,7 @@ void Transcript::challenge_bytes(const uint8_t* label, size_t llen, uint8_t* des
   strobe_.meta_ad(label, llen, false);
   strobe_.meta_ad(l4, 4, true);
   strobe_.prf(dest, dlen, false);
+  if (debug_transcript()) debug_line("challenge_bytes", label, llen, dest, dlen);
 }
 void TranscriptRngBuilder::rekey_with_witness_bytes(const uint8_t* label, size_t llen, const uint8_t* w, size_t wlen) {
   uint8_t l4[4];

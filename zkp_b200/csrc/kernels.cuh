@@ -161,6 +161,7 @@ __global__ void __launch_bounds__(256) k_recode(const uint4* __restrict__ scalar
   }
 }
 
+#ifdef ZKP_ABLATIONS   // single-phase predecessor of k_ingest2 (api.cu: fused_sort = 0 outside profiling mode)
 // K1+K2 fused: the digit histogram of term i is issued (fire-and-forget L2 reductions) before the ~31k-instruction
 // decompression of point i, whose LSU pipe is otherwise idle.  Used outside profiling mode.
 __global__ void __launch_bounds__(256) k_ingest(const uint4* __restrict__ enc, const uint4* __restrict__ scalars, size_t n,
@@ -200,6 +201,8 @@ __global__ void __launch_bounds__(256) k_ingest(const uint4* __restrict__ enc, c
   store_fe(o + 2, q.yminusx);
   store_fe(o + 4, q.xy2d);
 }
+
+#endif  // ZKP_ABLATIONS
 
 // Two-phase ingestion: every thread first issues the digit work of up to two terms -- MODE 0: histogram reductions,
 // MODE 1: counting-sort scatter (atomic cursor + 4-byte store) -- and then decompresses one point.  The L2 atomics and

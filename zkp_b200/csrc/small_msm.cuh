@@ -524,7 +524,7 @@ __global__ void __launch_bounds__(512, 1)
                    const uint4* __restrict__ shared_combs, const int32_t* __restrict__ term_slot,
                    const int32_t* __restrict__ unit_term0, const int32_t* __restrict__ unit_nterms,
                    const int32_t* __restrict__ cons_unit0, size_t N, uint32_t T, uint32_t U, uint32_t Us,
-                   uint32_t n_units, uint32_t k, uint4* __restrict__ out, uint32_t stagger_ns) {
+                   uint32_t n_units, uint32_t k, uint4* __restrict__ out) {
 #ifdef ZKP_HOST_EMUL
   uint4* smem = emul_dynamic_smem;
 #else
@@ -573,11 +573,6 @@ __global__ void __launch_bounds__(512, 1)
     for (size_t i = 0; i < (size_t)U * 2048; i++) s_combs[i] = g_combs[i];
   }
   __syncthreads();
-#endif
-  // The warps of one scheduler (warp ids equal mod 4) would otherwise run in phase: all scanning (ALU + LSU, multiplier
-  // idle), then all adding (multiplier saturated).  A start offset per warp keeps their phases apart (public: warp id).
-#if ZKP_DEVICE_ASM
-  if (stagger_ns) __nanosleep(stagger_ns * (warp >> 2));
 #endif
   // ---- the units of this warp -------------------------------------------------------------------------------------
 #pragma unroll 1
