@@ -1987,7 +1987,8 @@ extern "C" int32_t zkp_bench_dual(zkp_ctx*, int32_t, int32_t, double*) { return 
 #endif
 
 extern "C" int32_t zkp_bench_field(zkp_ctx* ctx, int32_t kind, int32_t iters, double* ops_per_sec) {
-  if (!ctx || !ops_per_sec || iters <= 0 || kind < 0 || kind > (ZKP_ABL(1) ? 16 : 11)) return ZKP_ERR_SIZE;
+  // kinds 17 / 18: squaring / multiplication with the round-1 carry schedule (fe_sq_v1 / fe_mul_v1), variable-time tails
+  if (!ctx || !ops_per_sec || iters <= 0 || kind < 0 || kind > 18 || (kind > 11 && kind < 17 && !ZKP_ABL(1))) return ZKP_ERR_SIZE;
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   int sms = 0;
   CUDA_TRY(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
@@ -2002,7 +2003,7 @@ extern "C" int32_t zkp_bench_field(zkp_ctx* ctx, int32_t kind, int32_t iters, do
   const int pool_units = (int)(((long long)threads * blocks / 32) * iters / 256);
   ENSURE(ctx, ctx->aux1, 256);
   for (int rep = 0; rep < 4; rep++) {
-    if (kind >= 12) CUDA_TRY(ctx, cudaMemsetAsync(ctx->aux1.p, 0, 4, ctx->stream));
+    if (kind >= 12 && kind <= 16) CUDA_TRY(ctx, cudaMemsetAsync(ctx->aux1.p, 0, 4, ctx->stream));
     CUDA_TRY(ctx, cudaEventRecord(e0, ctx->stream));
     switch (kind) {
       case 0: k_bench_mul32<0, false><<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, iters); break;
@@ -2020,6 +2021,8 @@ extern "C" int32_t zkp_bench_field(zkp_ctx* ctx, int32_t kind, int32_t iters, do
       case 15: k_bench_sq_mixed<4><<<sms * 2, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, pool_units, (unsigned int*)ctx->aux1.p); break;
       case 16: k_bench_sq_mixed<8><<<sms * 2, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, pool_units, (unsigned int*)ctx->aux1.p); break;
 #endif
+      case 17: k_bench_sq32<0, true, 1><<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, iters); break;
+      case 18: k_bench_mul32<0, true, 1><<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, iters); break;
       case 2: k_bench_mul51<<<blocks, threads, 0, ctx->stream>>>((unsigned long long*)ctx->aux0.p, iters); break;
       case 3: k_bench_mul25<<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, iters); break;
       case 4: k_bench_wide_plain<<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->aux0.p, iters); break;
@@ -2033,7 +2036,7 @@ extern "C" int32_t zkp_bench_field(zkp_ctx* ctx, int32_t kind, int32_t iters, do
     CUDA_TRY(ctx, cudaEventElapsedTime(&ms, e0, e1));
     if (rep > 0 && ms < best) best = ms;
   }
-  if (kind >= 12) *ops_per_sec = (double)pool_units * 32.0 * 256.0 / (best * 1e-3);
+  if (kind >= 12 && kind <= 16) *ops_per_sec = (double)pool_units * 32.0 * 256.0 / (best * 1e-3);
   else *ops_per_sec = (double)threads * blocks * (double)iters / (best * 1e-3);
   return ZKP_OK;
 }

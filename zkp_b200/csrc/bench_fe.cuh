@@ -11,7 +11,7 @@
 
 namespace zkp {
 
-template <int RED, bool VT>
+template <int RED, bool VT, int VER = 2>   // VER 1 = the round-1 schedule (carries captured into fresh limbs)
 __global__ void __launch_bounds__(256) k_bench_mul32(uint32_t* out, int iters) {
   uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
   fe a, b;
@@ -22,14 +22,14 @@ __global__ void __launch_bounds__(256) k_bench_mul32(uint32_t* out, int iters) {
   }
 #pragma unroll 1
   for (int k = 0; k < iters; k += 2) {
-    fe_mul_t<RED, VT>(a, a, b);
-    fe_mul_t<RED, VT>(b, b, a);
+    if (VER == 1) { fe_mul_v1<RED, VT>(a, a, b); fe_mul_v1<RED, VT>(b, b, a); }
+    else { fe_mul_t<RED, VT>(a, a, b); fe_mul_t<RED, VT>(b, b, a); }
   }
 #pragma unroll
   for (int i = 0; i < 8; i++) out[(size_t)gid * 16 + i] = a.v[i] ^ b.v[i];
 }
 
-template <int RED, bool VT>
+template <int RED, bool VT, int VER = 2>
 __global__ void __launch_bounds__(256) k_bench_sq32(uint32_t* out, int iters) {
   uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
   fe a;
@@ -37,8 +37,8 @@ __global__ void __launch_bounds__(256) k_bench_sq32(uint32_t* out, int iters) {
   for (int i = 0; i < 8; i++) a.v[i] = gid * 2654435761u + i * 40503u + 1;
 #pragma unroll 1
   for (int k = 0; k < iters; k += 2) {
-    fe_sq_t<RED, VT>(a, a);
-    fe_sq_t<RED, VT>(a, a);
+    if (VER == 1) { fe_sq_v1<RED, VT>(a, a); fe_sq_v1<RED, VT>(a, a); }
+    else { fe_sq_t<RED, VT>(a, a); fe_sq_t<RED, VT>(a, a); }
   }
 #pragma unroll
   for (int i = 0; i < 8; i++) out[(size_t)gid * 16 + i] = a.v[i];

@@ -142,6 +142,113 @@ ZKP_DEV uint32_t mad1(uint32_t* acc, uint32_t a0, uint32_t b) {
 #endif
 }
 
+// ---- chains whose carry never leaves the chain (round 2) ----------------------------------------------------------------
+// A carry captured into a fresh limb (`c = addc 0, 0`) becomes, one row later, the low word of a 64-bit addend whose high
+// word must be zeroed: ptxas emits SEL + `IMAD.MOV.U32 Rx, RZ, RZ, RZ`, and the zeroing lands on the FMA-heavy pipe that
+// the wide multiplies saturate (profiles/r02_pipe_counters.md: 6 % of its cycles in a squaring).  The chains below end
+// either in a FRESH pair computed in the chain itself -- (x * y) + carry, which cannot overflow 64 bits -- or in a two-limb
+// ripple of the carry into the pair above, which already holds one product plus at most one earlier carry.
+#if ZKP_DEVICE_ASM
+#define ZKP_MADPAIR(lo, hi, a, b) "madc.lo.cc.u32 " lo ", " a ", " b ", " lo ";\n\tmadc.hi.cc.u32 " hi ", " a ", " b ", " hi ";\n\t"
+#endif
+// acc[0..2N-1] += (a0..a_{N-1}) * b as pairs; then acc[2N], acc[2N+1] = x * y + carry   (fresh pair, written not read)
+ZKP_DEV void mad1x1(uint32_t* acc, uint32_t a0, uint32_t b, uint32_t x, uint32_t y) {
+#if ZKP_DEVICE_ASM
+  asm("mad.lo.cc.u32 %0, %4, %5, %0;\n\tmadc.hi.cc.u32 %1, %4, %5, %1;\n\t"
+      "madc.lo.cc.u32 %2, %6, %7, 0;\n\tmadc.hi.u32 %3, %6, %7, 0;"
+      : "+r"(acc[0]), "+r"(acc[1]), "=r"(acc[2]), "=r"(acc[3])
+      : "r"(a0), "r"(b), "r"(x), "r"(y));
+#else
+  acc[2] = 0; acc[3] = 0;
+  uint32_t c = mad1(acc, a0, b);
+  uint64_t p = (uint64_t)x * y + c;
+  acc[2] = (uint32_t)p; acc[3] = (uint32_t)(p >> 32);
+#endif
+}
+ZKP_DEV void mad2x1(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t b, uint32_t x, uint32_t y) {
+#if ZKP_DEVICE_ASM
+  asm("mad.lo.cc.u32 %0, %6, %8, %0;\n\tmadc.hi.cc.u32 %1, %6, %8, %1;\n\t"
+      "madc.lo.cc.u32 %2, %7, %8, %2;\n\tmadc.hi.cc.u32 %3, %7, %8, %3;\n\t"
+      "madc.lo.cc.u32 %4, %9, %10, 0;\n\tmadc.hi.u32 %5, %9, %10, 0;"
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "=r"(acc[4]), "=r"(acc[5])
+      : "r"(a0), "r"(a1), "r"(b), "r"(x), "r"(y));
+#else
+  uint32_t c = mad2(acc, a0, a1, b);
+  uint64_t p = (uint64_t)x * y + c;
+  acc[4] = (uint32_t)p; acc[5] = (uint32_t)(p >> 32);
+#endif
+}
+ZKP_DEV void mad3x1(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t b, uint32_t x, uint32_t y) {
+#if ZKP_DEVICE_ASM
+  asm("mad.lo.cc.u32 %0, %8, %11, %0;\n\tmadc.hi.cc.u32 %1, %8, %11, %1;\n\t"
+      "madc.lo.cc.u32 %2, %9, %11, %2;\n\tmadc.hi.cc.u32 %3, %9, %11, %3;\n\t"
+      "madc.lo.cc.u32 %4, %10, %11, %4;\n\tmadc.hi.cc.u32 %5, %10, %11, %5;\n\t"
+      "madc.lo.cc.u32 %6, %12, %13, 0;\n\tmadc.hi.u32 %7, %12, %13, 0;"
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "=r"(acc[6]), "=r"(acc[7])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(b), "r"(x), "r"(y));
+#else
+  uint32_t c = mad3(acc, a0, a1, a2, b);
+  uint64_t p = (uint64_t)x * y + c;
+  acc[6] = (uint32_t)p; acc[7] = (uint32_t)(p >> 32);
+#endif
+}
+ZKP_DEV void mad4x1(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b, uint32_t x, uint32_t y) {
+#if ZKP_DEVICE_ASM
+  asm("mad.lo.cc.u32 %0, %10, %14, %0;\n\tmadc.hi.cc.u32 %1, %10, %14, %1;\n\t"
+      "madc.lo.cc.u32 %2, %11, %14, %2;\n\tmadc.hi.cc.u32 %3, %11, %14, %3;\n\t"
+      "madc.lo.cc.u32 %4, %12, %14, %4;\n\tmadc.hi.cc.u32 %5, %12, %14, %5;\n\t"
+      "madc.lo.cc.u32 %6, %13, %14, %6;\n\tmadc.hi.cc.u32 %7, %13, %14, %7;\n\t"
+      "madc.lo.cc.u32 %8, %15, %16, 0;\n\tmadc.hi.u32 %9, %15, %16, 0;"
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]),
+        "=r"(acc[8]), "=r"(acc[9])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b), "r"(x), "r"(y));
+#else
+  uint32_t c = mad4(acc, a0, a1, a2, a3, b);
+  uint64_t p = (uint64_t)x * y + c;
+  acc[8] = (uint32_t)p; acc[9] = (uint32_t)(p >> 32);
+#endif
+}
+// acc[0..2N-1] += (a0..a_{N-1}) * b as pairs; then the carry ripples into acc[2N], acc[2N+1] (no carry out: see above)
+ZKP_DEV void mad1r(uint32_t* acc, uint32_t a0, uint32_t b) {
+#if ZKP_DEVICE_ASM
+  asm("mad.lo.cc.u32 %0, %4, %5, %0;\n\tmadc.hi.cc.u32 %1, %4, %5, %1;\n\t"
+      "addc.cc.u32 %2, %2, 0;\n\taddc.u32 %3, %3, 0;"
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3])
+      : "r"(a0), "r"(b));
+#else
+  uint32_t c = mad1(acc, a0, b);
+  uint64_t s = (uint64_t)acc[2] + c;
+  acc[2] = (uint32_t)s; acc[3] += (uint32_t)(s >> 32);
+#endif
+}
+ZKP_DEV void mad2r(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t b) {
+#if ZKP_DEVICE_ASM
+  asm("mad.lo.cc.u32 %0, %6, %8, %0;\n\tmadc.hi.cc.u32 %1, %6, %8, %1;\n\t"
+      "madc.lo.cc.u32 %2, %7, %8, %2;\n\tmadc.hi.cc.u32 %3, %7, %8, %3;\n\t"
+      "addc.cc.u32 %4, %4, 0;\n\taddc.u32 %5, %5, 0;"
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5])
+      : "r"(a0), "r"(a1), "r"(b));
+#else
+  uint32_t c = mad2(acc, a0, a1, b);
+  uint64_t s = (uint64_t)acc[4] + c;
+  acc[4] = (uint32_t)s; acc[5] += (uint32_t)(s >> 32);
+#endif
+}
+ZKP_DEV void mad3r(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t b) {
+#if ZKP_DEVICE_ASM
+  asm("mad.lo.cc.u32 %0, %8, %11, %0;\n\tmadc.hi.cc.u32 %1, %8, %11, %1;\n\t"
+      "madc.lo.cc.u32 %2, %9, %11, %2;\n\tmadc.hi.cc.u32 %3, %9, %11, %3;\n\t"
+      "madc.lo.cc.u32 %4, %10, %11, %4;\n\tmadc.hi.cc.u32 %5, %10, %11, %5;\n\t"
+      "addc.cc.u32 %6, %6, 0;\n\taddc.u32 %7, %7, 0;"
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(b));
+#else
+  uint32_t c = mad3(acc, a0, a1, a2, b);
+  uint64_t s = (uint64_t)acc[6] + c;
+  acc[6] = (uint32_t)s; acc[7] += (uint32_t)(s >> 32);
+#endif
+}
+
 // (lo,hi) = a*b  -- a single IMAD.WIDE.U32
 ZKP_DEV void mulw(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
   uint64_t p = (uint64_t)a * b;
@@ -534,9 +641,10 @@ ZKP_DEV void fe_reduce512_sel(fe& r, const uint32_t* t) {
   else fe_reduce512_t<VT>(r, t);
 }
 
-// r = a*b mod p (weak: r < 2^256)
+// r = a*b mod p (weak: r < 2^256) -- round-1 schedule: every row's carry is captured into a fresh limb (kept for the
+// micro-benchmark that measures the difference: zkp_bench_field kinds 17, 18)
 template <int RED, bool VT = false>
-ZKP_DEV void fe_mul_t(fe& r, const fe& a, const fe& b) {
+ZKP_DEV void fe_mul_v1(fe& r, const fe& a, const fe& b) {
   const uint32_t* A = a.v;
   const uint32_t* B = b.v;
   uint32_t E[17], O[17];
@@ -564,12 +672,48 @@ ZKP_DEV void fe_mul_t(fe& r, const fe& a, const fe& b) {
   add15(t + 1, E + 1, O);
   fe_reduce512_sel<RED, VT>(r, t);
 }
+// r = a*b mod p (weak: r < 2^256): the same 64 + 8 wide products, scheduled so that no carry is ever materialised
+// between chains (see "chains whose carry never leaves the chain" above): the even-a part of an odd row also computes the
+// top product of the following row into a fresh pair, and that row ripples its carry into the pair.
+template <int RED, bool VT = false>
+ZKP_DEV void fe_mul_t(fe& r, const fe& a, const fe& b) {
+  const uint32_t* A = a.v;
+  const uint32_t* B = b.v;
+  uint32_t E[17], O[17];
+#pragma unroll
+  for (int i = 0; i < 17; i++) { E[i] = 0; O[i] = 0; }
+  // row 0 (fresh accumulators: plain wide multiplies)
+  mulw(E[0], E[1], A[0], B[0]); mulw(E[2], E[3], A[2], B[0]);
+  mulw(E[4], E[5], A[4], B[0]); mulw(E[6], E[7], A[6], B[0]);
+  mulw(O[0], O[1], A[1], B[0]); mulw(O[2], O[3], A[3], B[0]);
+  mulw(O[4], O[5], A[5], B[0]); mulw(O[6], O[7], A[7], B[0]);
+#pragma unroll
+  for (int i = 1; i < 8; i += 2) {
+    // odd row i, even a -> O[i-1 .. i+6]; with it the top product a7 * b[i+1] of the next row into the fresh pair O[i+7, i+8]
+    if (i + 1 < 8) mad4x1(O + i - 1, A[0], A[2], A[4], A[6], B[i], A[7], B[i + 1]);
+    else O[i + 7] = mad4(O + i - 1, A[0], A[2], A[4], A[6], B[i]);   // last row: the carry is the top limb
+    // odd row i, odd a -> E[i+1 .. i+8]: the top pair is fresh for i = 1 and was made by the previous even row afterwards
+    if (i == 1) mad3x1(E + 2, A[1], A[3], A[5], B[1], A[7], B[1]);
+    else mad3r(E + i + 1, A[1], A[3], A[5], B[i]);
+    if (i + 1 < 8) {
+      // even row i+1, even a -> E[i+1 .. i+8]; with it the top product a7 * b[i+2] of the next odd row into E[i+9, i+10]
+      mad4x1(E + i + 1, A[0], A[2], A[4], A[6], B[i + 1], A[7], B[i + 2]);
+      // even row i+1, odd a -> O[i+1 .. i+6], carry into the pair made above
+      mad3r(O + i + 1, A[1], A[3], A[5], B[i + 1]);
+    }
+  }
+  // t = E + (O << 32): one 15-limb chain (E[16] = O[15] = 0 and the product fits in 512 bits)
+  uint32_t t[16];
+  t[0] = E[0];
+  add15(t + 1, E + 1, O);
+  fe_reduce512_sel<RED, VT>(r, t);
+}
 ZKP_DEV void fe_mul(fe& r, const fe& a, const fe& b) { fe_mul_t<ZKP_REDUCE_DEFAULT, false>(r, a, b); }
 ZKP_DEV void fe_mul_vt(fe& r, const fe& a, const fe& b) { fe_mul_t<ZKP_REDUCE_DEFAULT, true>(r, a, b); }
 
-// r = a^2 mod p
+// r = a^2 mod p -- round-1 schedule (see fe_mul_v1)
 template <int RED, bool VT = false>
-ZKP_DEV void fe_sq_t(fe& r, const fe& a) {
+ZKP_DEV void fe_sq_v1(fe& r, const fe& a) {
   const uint32_t* A = a.v;
   uint32_t E[17], O[17];
 #pragma unroll
@@ -596,6 +740,42 @@ ZKP_DEV void fe_sq_t(fe& r, const fe& a) {
   O[12] = mad1(O + 10, A[6], A[5]);
   // row 6: j=7 -> O[12,13]
   mad1(O + 12, A[7], A[6]);
+  // cross = E + (O << 32): limbs 1..15
+  uint32_t x[16];
+  x[0] = 0;
+  add15(x + 1, E + 1, O);          // one chain; x[15] picks up the last carry
+  // double it (funnel shifts: independent, no carry chain)
+  uint32_t t[16];
+  t[0] = 0;
+#pragma unroll
+  for (int i = 1; i < 16; i++) t[i] = (x[i] << 1) | (x[i - 1] >> 31);
+  // add the squares a_i^2 at limb 2i: one chain of eight fused lo/hi pairs
+  sqr8(t, A);
+  fe_reduce512_sel<RED, VT>(r, t);
+}
+// r = a^2 mod p: 28 cross products + 8 squares + 8 for the reduction, no carry materialised between chains
+template <int RED, bool VT = false>
+ZKP_DEV void fe_sq_t(fe& r, const fe& a) {
+  const uint32_t* A = a.v;
+  uint32_t E[17], O[17];
+#pragma unroll
+  for (int i = 0; i < 17; i++) { E[i] = 0; O[i] = 0; }
+  // cross products a_i*a_j, i<j; (i+j) even -> pair E[i+j, i+j+1], odd -> pair O[i+j-1, i+j]
+  // row 0: fresh pairs
+  mulw(E[2], E[3], A[2], A[0]); mulw(E[4], E[5], A[4], A[0]); mulw(E[6], E[7], A[6], A[0]);
+  mulw(O[0], O[1], A[1], A[0]); mulw(O[2], O[3], A[3], A[0]);
+  mulw(O[4], O[5], A[5], A[0]); mulw(O[6], O[7], A[7], A[0]);
+  // odd sums: (1,2)(1,4)(1,6) + fresh (2,7) | (2,3)(2,5) ripple | (3,4)(3,6) + fresh (4,7) | (4,5) ripple | (5,6) + fresh (6,7)
+  mad3x1(O + 2, A[2], A[4], A[6], A[1], A[7], A[2]);
+  mad2r(O + 4, A[3], A[5], A[2]);
+  mad2x1(O + 6, A[4], A[6], A[3], A[7], A[4]);
+  mad1r(O + 8, A[5], A[4]);
+  mad1x1(O + 10, A[6], A[5], A[7], A[6]);
+  // even sums: (1,3)(1,5) + fresh (1,7) | (2,4)(2,6) + fresh (3,7) | (3,5) ripple | (4,6) + fresh (5,7)
+  mad2x1(E + 4, A[3], A[5], A[1], A[7], A[1]);
+  mad2x1(E + 6, A[4], A[6], A[2], A[7], A[3]);
+  mad1r(E + 8, A[5], A[3]);
+  mad1x1(E + 10, A[6], A[4], A[7], A[5]);
   // cross = E + (O << 32): limbs 1..15
   uint32_t x[16];
   x[0] = 0;
