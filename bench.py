@@ -221,6 +221,7 @@ def main():
     ap.add_argument("--no-numa-bind", action="store_true", help="tuning: do not pin ranks to their GPU's NUMA node")
     ap.add_argument("--bv-chunk-terms-log2", type=int, default=0, help="tuning: slab size (terms) of the from-proofs leg")
     ap.add_argument("--dual-stream", type=int, default=-1, help="tuning: chunk kernels of the e2e leg on two alternating streams (0/1)")
+    ap.add_argument("--bv-merge-rows", type=int, default=-1, help="tuning: row launches of a from-proofs slab merged into one 2-D grid (0/1)")
     ap.add_argument("--no-fused-sort", action="store_true", help="tuning: separate scatter pass instead of the two-phase ingestion")
     ap.add_argument("--sweep", default="", help="tuning: comma list of windows; prints stage times per window and exits")
     ap.add_argument("--no-configs", action="store_true", help="skip the legs of the other BASELINE configs (`configs` block)")
@@ -338,6 +339,8 @@ def main():
         eng.set_option("dual_stream", args.dual_stream)
     if args.phase1_percent:
         eng.set_option("phase1_percent", args.phase1_percent)
+    if args.bv_merge_rows >= 0:
+        eng.set_option("bv_merge_rows", args.bv_merge_rows)
     if args.ingest_variant >= 0:
         eng.set_option("ingest_variant", args.ingest_variant)
     if args.chunk_terms_log2:
@@ -513,8 +516,9 @@ def main():
         ing_ms = float(np.mean(ing)) if min(ing) > 0 else 0.0
         ing_bytes = n_terms * (0.5 * 32.0 + 32.0)                # algorithmic bytes of ONE launch
         achieved = ing_bytes / (ing_ms * 1e-3) / 1e9 if ing_ms else 0.0
-        # integer-pipe view: field mults (257 S + 26 M per point) against the calibrated register-resident rates
-        dec_time_at_peak = 0.5 * n_terms * (257.0 / fe_sq_rate + 26.0 / fe_mul_rate)
+        # integer-pipe view: field mults per point (decode 3 S + 2 M, inverse square root 252 S + 13 M, coordinates 6 M, Niels
+        # form 1 M = 255 S + 22 M; ge.cuh ristretto_decode) against the calibrated register-resident rates
+        dec_time_at_peak = 0.5 * n_terms * (255.0 / fe_sq_rate + 22.0 / fe_mul_rate)
         acc_ms = live.get("accumulate", -1.0)
         traffic, traffic_each, traffic_src, pipe = None, None, None, None
         try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture

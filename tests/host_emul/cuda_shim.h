@@ -120,15 +120,16 @@ static inline int __any_sync(unsigned, int p) { return p; }
 
 // run a communication-free kernel: every thread of every block in turn
 template <class K, class... A>
-static void emul_launch(unsigned grid, unsigned block, K kernel, A... args) {
-  gridDim = dim3(grid, 1, 1);
+static void emul_launch(dim3 grid, unsigned block, K kernel, A... args) {
+  gridDim = grid;
   blockDim = dim3(block, 1, 1);
-  for (unsigned b = 0; b < grid; b++)
-    for (unsigned t = 0; t < block; t++) {
-      blockIdx.x = b; blockIdx.y = 0; blockIdx.z = 0;
-      threadIdx.x = t; threadIdx.y = 0; threadIdx.z = 0;
-      kernel(args...);
-    }
+  for (unsigned by = 0; by < grid.y; by++)
+    for (unsigned b = 0; b < grid.x; b++)
+      for (unsigned t = 0; t < block; t++) {
+        blockIdx.x = b; blockIdx.y = by; blockIdx.z = 0;
+        threadIdx.x = t; threadIdx.y = 0; threadIdx.z = 0;
+        kernel(args...);
+      }
 }
 
 // run a kernel whose threads cooperate: block after block, one OS thread per CUDA thread

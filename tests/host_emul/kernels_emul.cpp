@@ -221,7 +221,8 @@ void emul_msm_vartime(const uint8_t* scalars, const uint8_t* points, size_t n, i
     size_t threads = std::max(p_cnt, std::max(half, s_cnt - half));
     if (!threads) return;
     emul_launch((unsigned)((threads + 255) / 256), 256, kernel, (const uint4*)pt.data(), p_lo, p_cnt, niels.data(),
-                (const uint4*)sc.data(), s_lo, half, s_lo + half, s_cnt - half, n, c, W, B, counters, sorted.data(), flags);
+                (const uint4*)sc.data(), s_lo, half, s_lo + half, s_cnt - half, n, c, W, B, counters, sorted.data(), flags, (size_t)0, (size_t)0,
+                (size_t)0);
   };
   const size_t half_p = (n + 1) / 2;
   ingest(k_ingest2<0, 2>, 0, half_p, 0, n, hist.data());

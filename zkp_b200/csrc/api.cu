@@ -120,6 +120,7 @@ struct zkp_ctx {
   int smem_optin = -1;        // cudaDevAttrMaxSharedMemoryPerBlockOptin, read once
   int sm_count = -1;          // cudaDevAttrMultiProcessorCount, read once
   size_t cta_smem_set = 0;    // dynamic shared memory k_comb_msm_cta has been allowed so far
+  int bv_merge_rows = 1;    // batch verification from proofs: the row launches of a slab / of phase 2 merged into one 2-D grid
   int bv_compiled = 1;      // batch-verification front end: host-compiled transcript script (k_bv_prepare2)
   int ingest_variant = 2;   // occupancy point of k_ingest2 (kernels.cuh ZKP_INGEST_*)
   int fused_sort = 1;  // histogram and scatter ride under the two halves of the decompression (k_ingest2)
@@ -300,6 +301,8 @@ extern "C" int32_t zkp_ctx_set_option(zkp_ctx* ctx, const char* key, int64_t val
   } else if (!strcmp(key, "prove_piece")) {
     if (value < 1 || value > 64) return ZKP_ERR_SIZE;
     ctx->prove_piece = (int)value;
+  } else if (!strcmp(key, "bv_merge_rows")) {
+    ctx->bv_merge_rows = value ? 1 : 0;
   } else if (!strcmp(key, "bv_compiled")) {
     if (!value && !ZKP_ABL(1)) return ZKP_ERR_SIZE;   // ablation: not in the product build
     ctx->bv_compiled = value ? 1 : 0;
@@ -475,17 +478,18 @@ static int32_t msm_finish(zkp_ctx* ctx, const msm_plan& pl, const void* d_scalar
 template <int MODE>
 static int32_t launch_ingest2(zkp_ctx* ctx, const msm_plan& pl, const void* d_scalars, const void* d_points, size_t n,
                               size_t p_lo, size_t p_cnt, size_t sA_lo, size_t sA_cnt, size_t sB_lo, size_t sB_cnt,
-                              cudaStream_t on = nullptr) {
+                              cudaStream_t on = nullptr, unsigned ny = 1, size_t y_p = 0, size_t y_a = 0, size_t y_b = 0) {
   const cudaStream_t launch_stream = on ? on : ctx->stream;
   size_t threads = p_cnt > sA_cnt ? p_cnt : sA_cnt;
   if (sB_cnt > threads) threads = sB_cnt;
-  if (!threads) return ZKP_OK;
+  if (!threads || !ny) return ZKP_OK;
+  // ny > 1: ny equally shaped triples, their starts y_p / y_a / y_b apart, as the y dimension of one grid
 #define ZKP_LAUNCH_INGEST(VAR)                                                                                              \
-  k_ingest2<MODE, VAR><<<(unsigned)((threads + ZKP_INGEST_THREADS(VAR) - 1) / ZKP_INGEST_THREADS(VAR)),                     \
+  k_ingest2<MODE, VAR><<<dim3((unsigned)((threads + ZKP_INGEST_THREADS(VAR) - 1) / ZKP_INGEST_THREADS(VAR)), ny),           \
                          ZKP_INGEST_THREADS(VAR), 0, launch_stream>>>(                                                      \
       (const uint4*)d_points, p_lo, p_cnt, (uint4*)ctx->niels.p, (const uint4*)d_scalars, sA_lo, sA_cnt, sB_lo, sB_cnt, n,  \
       pl.c, pl.W, pl.B, MODE == 0 ? (uint32_t*)ctx->hist.p : (uint32_t*)ctx->cursor.p, (uint32_t*)ctx->sorted.p,            \
-      (int*)ctx->flags.p)
+      (int*)ctx->flags.p, y_p, y_a, y_b)
   switch (ctx->ingest_variant) {
     case 1: ZKP_LAUNCH_INGEST(1); break;
     case 2: ZKP_LAUNCH_INGEST(2); break;
@@ -1279,10 +1283,17 @@ static int32_t batch_verify_proofs_impl(zkp_ctx* ctx, const zkp_statement_desc* 
     // the slabs of this chunk are complete (points and coefficients)
     if (fused) {
       // phase 1 of the two-phase ingestion: histogram every slab, decompress the slabs of the first R1 rows
-      for (size_t row = 0; row < R1; row++) {
-        const size_t a = (size_t)nc + row * N + j0, b = (size_t)nc + (row + R1) * N + j0;
-        r = launch_ingest2<0>(ctx, pl, dsc, dpts, n, a, cnt, a, cnt, b, cnt);
+      // (rows 0 .. R1-1 as the y dimension of ONE launch: row r decompresses its slab and histograms rows r and r + R1)
+      if (ctx->bv_merge_rows) {
+        const size_t a = (size_t)nc + j0, b = (size_t)nc + R1 * N + j0;
+        r = launch_ingest2<0>(ctx, pl, dsc, dpts, n, a, cnt, a, cnt, b, cnt, nullptr, (unsigned)R1, N, N, N);
         if (r != ZKP_OK) return r;
+      } else {
+        for (size_t row = 0; row < R1; row++) {
+          const size_t a = (size_t)nc + row * N + j0, b = (size_t)nc + (row + R1) * N + j0;
+          r = launch_ingest2<0>(ctx, pl, dsc, dpts, n, a, cnt, a, cnt, b, cnt);
+          if (r != ZKP_OK) return r;
+        }
       }
       for (size_t row = 2 * R1; row < rows; row++) {   // odd row count: the last row's histogram on its own
         r = launch_ingest2<0>(ctx, pl, dsc, dpts, n, 0, 0, (size_t)nc + row * N + j0, cnt, 0, 0);
@@ -1306,7 +1317,15 @@ static int32_t batch_verify_proofs_impl(zkp_ctx* ctx, const zkp_statement_desc* 
     // phase 2: the remaining rows are decompressed while the digits of all rows are scattered (two rows per launch)
     k_scan<<<pl.W, 1024, 0, st>>>((const uint32_t*)ctx->hist.p, pl.B, (uint32_t*)ctx->offs.p, (uint32_t*)ctx->cursor.p);
     LAUNCH_CHECK(ctx);
-    for (size_t q = 0; q < rows - R1; q++) {
+    // launches q < rows / 2 have the same shape (N points, N + N terms): one grid with q as its y dimension
+    size_t q0 = 0;
+    if (ctx->bv_merge_rows && rows / 2 > 1 && rows / 2 <= rows - R1) {
+      q0 = rows / 2;
+      r = launch_ingest2<1>(ctx, pl, dsc, dpts, n, (size_t)nc + R1 * N, N, (size_t)nc, N, (size_t)nc + N, N, nullptr,
+                            (unsigned)q0, N, 2 * N, 2 * N);
+      if (r != ZKP_OK) return r;
+    }
+    for (size_t q = q0; q < rows - R1; q++) {
       const size_t ra = 2 * q, rb = 2 * q + 1;
       r = launch_ingest2<1>(ctx, pl, dsc, dpts, n, (size_t)nc + (R1 + q) * N, N, (size_t)nc + ra * N, ra < rows ? N : 0,
                             (size_t)nc + rb * N, rb < rows ? N : 0);

@@ -180,6 +180,28 @@ ZKP_DEV uint32_t fe_invsqrt(fe& r, const fe& v) {
   return correct | flipped;
 }
 
+// (was_square, r) with r = |1/sqrt(v)| for a nonzero square v -- the decoder's use of sqrt_ratio_i(1, v).
+// RFC 9496 4.2 evaluates r0 = v^3 (v^7)^((p-5)/8) = v^((p-5)/8) * zeta with zeta = (v^((p-1)/4))^3; for a square v,
+// zeta = +-1, so v r0^2 = v (v^((p-5)/8))^2 and the two candidates agree up to the sign that the final |.| removes: the
+// exponentiation can start from v itself (2 squarings and 3 multiplications fewer per point).  For v = 0 or a non-square
+// both forms report was_square = 0 and the decoder rejects; r is then unspecified, so this form is NOT sqrt_ratio_i and
+// is used by ristretto_decode only.
+template <bool VT = false>
+ZKP_DEV uint32_t fe_invsqrt_decode(fe& r, const fe& v) {
+  fe t, check, one, m1, ti;
+  fe_pow22523<VT>(t, v);
+  fe_sqx<VT>(check, t);
+  fe_mulx<VT>(check, check, v);   // v * t^2 = v^((p-1)/4): +1 or -1 for a nonzero square
+  fe_one(one);
+  fe_neg(m1, one);
+  uint32_t correct = fe_eq(check, one);
+  uint32_t flipped = fe_eq(check, m1);
+  fe_mulx<VT>(ti, t, fe_SQRT_M1());
+  fe_select(t, t, ti, flipped);
+  fe_abs(r, t);
+  return correct | flipped;
+}
+
 // RFC 9496 4.3.1.  w = the 32 encoding bytes as 8 little-endian words.  Returns 1 if valid.
 // Output: affine extended coordinates (x, y, 1, t) delivered as x, y, t.
 template <bool VT = false>
@@ -194,24 +216,24 @@ ZKP_DEV uint32_t ristretto_decode(fe& x, fe& y, fe& t, const uint32_t* w) {
   for (int i = 0; i < 8; i++) diff |= cw[i] ^ w[i];
   uint32_t ok = (diff == 0) & ((w[0] & 1u) == 0);
   fe_one(one);
-  fe_sq(ss, s);
-  fe_sub(u1, one, ss);
-  fe_add(u2, one, ss);
-  fe_sq(u2sq, u2);
-  fe_sq(tmp, u1);
-  fe_mul(tmp, tmp, fe_D());
+  fe_sqx<VT>(ss, s);
+  fe_sub_t<VT>(u1, one, ss);
+  fe_add_t<VT>(u2, one, ss);
+  fe_sqx<VT>(u2sq, u2);
+  fe_sqx<VT>(tmp, u1);
+  fe_mulx<VT>(tmp, tmp, fe_D());
   fe_neg(tmp, tmp);
-  fe_sub(v, tmp, u2sq);       // v = -(D*u1^2) - u2^2
-  fe_mul(tmp, v, u2sq);
-  uint32_t sq = fe_invsqrt<VT>(inv, tmp);
-  fe_mul(dx, inv, u2);
-  fe_mul(dy, inv, dx);
-  fe_mul(dy, dy, v);
-  fe_mul(tmp, s, dx);
-  fe_add(tmp, tmp, tmp);
+  fe_sub_t<VT>(v, tmp, u2sq);       // v = -(D*u1^2) - u2^2
+  fe_mulx<VT>(tmp, v, u2sq);
+  uint32_t sq = fe_invsqrt_decode<VT>(inv, tmp);
+  fe_mulx<VT>(dx, inv, u2);
+  fe_mulx<VT>(dy, inv, dx);
+  fe_mulx<VT>(dy, dy, v);
+  fe_mulx<VT>(tmp, s, dx);
+  fe_add_t<VT>(tmp, tmp, tmp);
   fe_abs(x, tmp);
-  fe_mul(y, u1, dy);
-  fe_mul(t, x, y);
+  fe_mulx<VT>(y, u1, dy);
+  fe_mulx<VT>(t, x, y);
   ok &= sq & (fe_is_negative(t) ^ 1u) & (fe_is_zero(y) ^ 1u);
   return ok;
 }

@@ -248,7 +248,13 @@ __global__ void __launch_bounds__(ZKP_INGEST_THREADS(VAR), ZKP_INGEST_MINBLK(VAR
                                                  uint4* __restrict__ niels, const uint4* __restrict__ scalars, size_t sA_lo,
                                                  size_t sA_cnt, size_t sB_lo, size_t sB_cnt, size_t n, int c, int W,
                                                  uint32_t B, uint32_t* __restrict__ counters,
-                                                 uint32_t* __restrict__ sorted, int* __restrict__ flags) {
+                                                 uint32_t* __restrict__ sorted, int* __restrict__ flags, size_t y_p,
+                                                 size_t y_a, size_t y_b) {
+  // blockIdx.y = one of several equally shaped (points, terms A, terms B) triples whose starts are y_p / y_a / y_b apart:
+  // the rows of a batch-verification slab go out as ONE launch (one partial last wave instead of one per row)
+  p_lo += (size_t)blockIdx.y * y_p;
+  sA_lo += (size_t)blockIdx.y * y_a;
+  sB_lo += (size_t)blockIdx.y * y_b;
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t < sA_cnt) ingest_digits<MODE>(scalars, sA_lo + t, n, c, W, B, counters, sorted, flags);
   if (t < sB_cnt) ingest_digits<MODE>(scalars, sB_lo + t, n, c, W, B, counters, sorted, flags);
