@@ -221,7 +221,9 @@ def main():
     ap.add_argument("--no-numa-bind", action="store_true", help="tuning: do not pin ranks to their GPU's NUMA node")
     ap.add_argument("--bv-chunk-terms-log2", type=int, default=0, help="tuning: slab size (terms) of the from-proofs leg")
     ap.add_argument("--dual-stream", type=int, default=-1, help="tuning: chunk kernels of the e2e leg on two alternating streams (0/1)")
-    ap.add_argument("--bv-merge-rows", type=int, default=-1, help="tuning: row launches of a from-proofs slab merged into one 2-D grid (0/1)")
+    ap.add_argument("--bv-phase1-rows", type=int, default=0, help="tuning: rows decompressed in phase 1 of the from-proofs leg")
+    ap.add_argument("--bv-prep-stream", type=int, default=-1, help="tuning: front-end kernel of the from-proofs leg on its own stream (0/1)")
+    ap.add_argument("--bv-prep-smem-kb", type=int, default=-1, help="tuning: residency cap of that kernel (unused dynamic shared memory, KB)")
     ap.add_argument("--no-fused-sort", action="store_true", help="tuning: separate scatter pass instead of the two-phase ingestion")
     ap.add_argument("--sweep", default="", help="tuning: comma list of windows; prints stage times per window and exits")
     ap.add_argument("--no-configs", action="store_true", help="skip the legs of the other BASELINE configs (`configs` block)")
@@ -339,8 +341,12 @@ def main():
         eng.set_option("dual_stream", args.dual_stream)
     if args.phase1_percent:
         eng.set_option("phase1_percent", args.phase1_percent)
-    if args.bv_merge_rows >= 0:
-        eng.set_option("bv_merge_rows", args.bv_merge_rows)
+    if args.bv_phase1_rows:
+        eng.set_option("bv_phase1_rows", args.bv_phase1_rows)
+    if args.bv_prep_stream >= 0:
+        eng.set_option("bv_prep_stream", args.bv_prep_stream)
+    if args.bv_prep_smem_kb >= 0:
+        eng.set_option("bv_prep_smem_kb", args.bv_prep_smem_kb)
     if args.ingest_variant >= 0:
         eng.set_option("ingest_variant", args.ingest_variant)
     if args.chunk_terms_log2:

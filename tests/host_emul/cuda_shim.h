@@ -10,6 +10,7 @@
 #define __launch_bounds__(...)
 #undef __global__
 #define __global__
+#define __grid_constant__
 #undef __device__
 #define __device__
 #undef __shared__

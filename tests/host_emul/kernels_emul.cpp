@@ -220,9 +220,12 @@ void emul_msm_vartime(const uint8_t* scalars, const uint8_t* points, size_t n, i
     const size_t half = (s_cnt + 1) / 2;
     size_t threads = std::max(p_cnt, std::max(half, s_cnt - half));
     if (!threads) return;
-    emul_launch((unsigned)((threads + 255) / 256), 256, kernel, (const uint4*)pt.data(), p_lo, p_cnt, niels.data(),
-                (const uint4*)sc.data(), s_lo, half, s_lo + half, s_cnt - half, n, c, W, B, counters, sorted.data(), flags, (size_t)0, (size_t)0,
-                (size_t)0);
+    ingest_args a = {};
+    a.p_lo = p_lo; a.p_cnt = p_cnt;
+    a.s_lo[0] = s_lo; a.s_cnt[0] = half;
+    a.s_lo[1] = s_lo + half; a.s_cnt[1] = s_cnt - half;
+    emul_launch((unsigned)((threads + 255) / 256), 256, kernel, (const uint4*)pt.data(), niels.data(), (const uint4*)sc.data(), a,
+                n, c, W, B, counters, sorted.data(), flags);
   };
   const size_t half_p = (n + 1) / 2;
   ingest(k_ingest2<0, 2>, 0, half_p, 0, n, hist.data());
@@ -338,7 +341,8 @@ int emul_bv_front_end(int m, int ni, int nc, int k, const char* labels, const in
   unsigned block_base = 0;
   for (size_t cidx = 0; cidx < nchunks; cidx++) {
     const size_t j0 = cidx * chunk, cnt = j0 + chunk < N ? chunk : N - j0;
-    const unsigned nb = (unsigned)((cnt + 127) / 128);
+    unsigned nb = (unsigned)((cnt + 127) / 128);
+    if (compiled && chunk > 128) nb = 1;   // a resident grid smaller than the slab: the block loops over the 128-proof groups
     if (compiled)
       emul_launch_mt(nb, 128, k_bv_prepare2, d, (const uint32_t*)(dm + bp.o_prefix), N, (const uint8_t*)(dpts + (size_t)nc * 32),
                      (const uint8_t*)com4.data(), (const uint8_t*)resp4.data(), dm + bp.o_seed, bp.script_blocks,

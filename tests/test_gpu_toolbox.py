@@ -243,6 +243,43 @@ def test_batch_verify_device_front_end_matches_oracle(engine):
     assert [bytes(p) for p in po] == opts and [bytes(c) for c in co] == [S.to_bytes(s) for s in oscal]
 
 
+def test_batch_verify_device_slab_pipeline_and_phase_splits(engine):
+    """zkp_batch_verify_proofs over several slabs: whatever the split of the rows between the two ingestion phases (three
+    term ranges per thread, digit-only launches for rows nothing is left to hide under) and wherever the front-end kernel
+    runs (its own high-priority stream next to the previous slab's decompression, or the compute stream), the MSM inputs are
+    those of the single-slab call, the batch is accepted, and a tampered proof in the LAST slab is caught."""
+    from tools import workloads as WL
+    rng = np.random.default_rng(20261017)
+    N = 2500
+    st, sec, lim, enc = WL.cmz_instances(engine, N, rng)
+    ent = rng.integers(0, 256, (N, 32), dtype=np.uint8)
+    _, com, resp = st.prove_many_device(engine, b"CMZ", sec, lim, ent)
+    ni = len(st.instance)
+    inst = np.ascontiguousarray(enc[:, :ni].transpose(1, 0, 2))
+    comm = np.ascontiguousarray(enc[0, ni:])
+    seed = bytes(range(7, 39))
+    bad = resp.copy()
+    bad[N - 3, 20, 2] ^= 0x10
+    try:
+        engine.set_option("bv_chunk_terms", 1 << 30)              # one slab
+        co0, po0 = st.batch_verify_device(engine, com, resp, b"CMZ", inst, comm, seed, want_msm_inputs=True)
+        co0, po0 = co0.copy(), po0.copy()
+        engine.set_option("bv_chunk_terms", 1024)                 # 1024-proof slabs: 1024 + 1024 + 452
+        # rows1: 0 = the split chosen per slab from the arrival of the copies, -1 = alternating half / all, else fixed
+        for rows1, prep, cap in ((0, 1, 64), (0, 0, 64), (-1, 1, 64), (-1, 0, 64), (1, 1, 0), (7, 1, 64), (8, 0, 64), (12, 1, 32),
+                                 (16, 1, 64), (20, 1, 64), (24, 1, 64)):
+            engine.set_option("bv_phase1_rows", rows1)
+            engine.set_option("bv_prep_stream", prep)
+            engine.set_option("bv_prep_smem_kb", cap)
+            co, po = st.batch_verify_device(engine, com, resp, b"CMZ", inst, comm, seed, want_msm_inputs=True)
+            assert (co == co0).all() and (po == po0).all(), (rows1, prep)
+            with pytest.raises(PT.VerificationFailure):
+                st.batch_verify_device(engine, com, bad, b"CMZ", inst, comm, seed)
+    finally:
+        for key, v in (("bv_chunk_terms", 1 << 21), ("bv_phase1_rows", 0), ("bv_prep_stream", 1), ("bv_prep_smem_kb", 64)):
+            engine.set_option(key, v)
+
+
 def test_prove_many_device_front_end_matches_host_and_oracle(engine):
     """zkp_prove_batch (allocate_point compressions, transcript replay, TranscriptRng blindings, constant-time MSMs,
     challenge and responses on the GPU) is byte-identical to the host mirror and to the oracle prover given the same

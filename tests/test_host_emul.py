@@ -726,3 +726,6 @@ def test_batch_verification_front_end_kernels_on_the_host(klib):
     for compiled in (1, 0):
         rc, bad, co, po = front_end(ost, b"DLEQBatchTest", encs, proofs, seed, compiled)
         assert (rc, bad) == (0, -1) and po == want_p and co == want_c, compiled
+    # one slab of 130 proofs on a grid of ONE block (the resident grid of the slab pipeline): the block takes both groups
+    rc, bad, co, po = front_end(ost, b"DLEQBatchTest", encs, proofs, seed, 1, chunk=256)
+    assert (rc, bad) == (0, -1) and po == want_p and co == want_c

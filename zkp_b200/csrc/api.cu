@@ -92,7 +92,7 @@ struct zkp_ctx {
   // per-launch partial waves overlap.  Measured at the bench size (e2e per step): 2^21 on one stream 135.8 ms,
   // 2^20 on two 132.3 ms, 2^19 on two 130.6 ms (device-resident inputs: 129.5 ms)
   size_t chunk_terms = (size_t)1 << 19;
-  size_t bv_chunk_terms = (size_t)1 << 21;   // the same for the slabs of zkp_batch_verify_proofs (one stream)
+  size_t bv_chunk_terms = (size_t)1 << 19;   // the same for the slabs of zkp_batch_verify_proofs (x 4 / rows proofs per slab)
   // the digit sort (histogram, scan, scatter: L2-atomic bound) runs on a second, higher-priority stream
   // concurrently with decompression (integer-multiply bound); joined before bucket accumulation
   int overlap = 0;   // measured: no gain on B200 (159.2 vs 159.9 ms per step), kept as an option
@@ -120,7 +120,16 @@ struct zkp_ctx {
   int smem_optin = -1;        // cudaDevAttrMaxSharedMemoryPerBlockOptin, read once
   int sm_count = -1;          // cudaDevAttrMultiProcessorCount, read once
   size_t cta_smem_set = 0;    // dynamic shared memory k_comb_msm_cta has been allowed so far
-  int bv_merge_rows = 1;    // batch verification from proofs: the row launches of a slab / of phase 2 merged into one 2-D grid
+  // batch verification from proofs (zkp_batch_verify_proofs)
+  int bv_phase1_rows = 0;   // rows of a slab decompressed in phase 1: 0 = chosen per slab (half, or all while the host link is the limit)
+  int bv_prep_stream = 1;   // front-end kernel of slab i + 1 on its own high-priority stream next to the decompression of slab i
+  int bv_prep_smem_kb = 64; // ... its residency cap: unused dynamic shared memory per 128-thread block (64 KB = 2 blocks per SM)
+  size_t bv_prep_smem_set = 0;
+  int bv_prep_blocks = 2;   // ... and the resident grid it runs as: blocks per SM (0 = one block per 128 proofs)
+  int bv_carveout = 100;    // ... shared-memory carve-out (percent) preferred by BOTH that kernel and k_ingest2 (-1 = leave)
+  int bv_carveout_set = -2;
+  cudaStream_t prep_stream = nullptr;
+  std::vector<cudaEvent_t> prep_ev, ing_ev;
   int bv_compiled = 1;      // batch-verification front end: host-compiled transcript script (k_bv_prepare2)
   int ingest_variant = 2;   // occupancy point of k_ingest2 (kernels.cuh ZKP_INGEST_*)
   int fused_sort = 1;  // histogram and scatter ride under the two halves of the decompression (k_ingest2)
@@ -250,6 +259,9 @@ extern "C" void zkp_ctx_destroy(zkp_ctx* ctx) {
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->sort_stream) cudaStreamDestroy(ctx->sort_stream);
   if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+  if (ctx->prep_stream) cudaStreamDestroy(ctx->prep_stream);
+  for (cudaEvent_t e : ctx->prep_ev) cudaEventDestroy(e);
+  for (cudaEvent_t e : ctx->ing_ev) cudaEventDestroy(e);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -301,8 +313,20 @@ extern "C" int32_t zkp_ctx_set_option(zkp_ctx* ctx, const char* key, int64_t val
   } else if (!strcmp(key, "prove_piece")) {
     if (value < 1 || value > 64) return ZKP_ERR_SIZE;
     ctx->prove_piece = (int)value;
-  } else if (!strcmp(key, "bv_merge_rows")) {
-    ctx->bv_merge_rows = value ? 1 : 0;
+  } else if (!strcmp(key, "bv_phase1_rows")) {
+    if (value < -1 || value > 4096) return ZKP_ERR_SIZE;
+    ctx->bv_phase1_rows = (int)value;
+  } else if (!strcmp(key, "bv_prep_stream")) {
+    ctx->bv_prep_stream = value ? 1 : 0;
+  } else if (!strcmp(key, "bv_prep_blocks")) {
+    if (value < 0 || value > 16) return ZKP_ERR_SIZE;
+    ctx->bv_prep_blocks = (int)value;
+  } else if (!strcmp(key, "bv_carveout")) {
+    if (value < -1 || value > 100) return ZKP_ERR_SIZE;
+    ctx->bv_carveout = (int)value;
+  } else if (!strcmp(key, "bv_prep_smem_kb")) {
+    if (value < 0 || value > 160) return ZKP_ERR_SIZE;
+    ctx->bv_prep_smem_kb = (int)value;
   } else if (!strcmp(key, "bv_compiled")) {
     if (!value && !ZKP_ABL(1)) return ZKP_ERR_SIZE;   // ablation: not in the product build
     ctx->bv_compiled = value ? 1 : 0;
@@ -473,23 +497,21 @@ static int32_t msm_ingest(zkp_ctx* ctx, const msm_plan& pl, const void* d_scalar
 static int32_t msm_finish(zkp_ctx* ctx, const msm_plan& pl, const void* d_scalars, size_t n, msm_result* d_result,
                           bool whole, bool sorted_done = false);
 
-// one launch of the two-phase ingestion (kernels.cuh k_ingest2): points [p_lo, p_lo + p_cnt), terms [sA_lo, +sA_cnt) and
-// [sB_lo, +sB_cnt) of the scalar array; MODE 0 histograms their digits, MODE 1 scatters them
+// one launch of the two-phase ingestion (kernels.cuh k_ingest2): the points and the (up to three) term ranges of `a`,
+// ny equally shaped launches as the y dimension of one grid; MODE 0 histograms the terms' digits, MODE 1 scatters them
 template <int MODE>
 static int32_t launch_ingest2(zkp_ctx* ctx, const msm_plan& pl, const void* d_scalars, const void* d_points, size_t n,
-                              size_t p_lo, size_t p_cnt, size_t sA_lo, size_t sA_cnt, size_t sB_lo, size_t sB_cnt,
-                              cudaStream_t on = nullptr, unsigned ny = 1, size_t y_p = 0, size_t y_a = 0, size_t y_b = 0) {
+                              const ingest_args& a, unsigned ny = 1, cudaStream_t on = nullptr) {
   const cudaStream_t launch_stream = on ? on : ctx->stream;
-  size_t threads = p_cnt > sA_cnt ? p_cnt : sA_cnt;
-  if (sB_cnt > threads) threads = sB_cnt;
+  size_t threads = a.p_cnt;
+  for (int j = 0; j < 3; j++)
+    if (a.s_cnt[j] > threads) threads = a.s_cnt[j];
   if (!threads || !ny) return ZKP_OK;
-  // ny > 1: ny equally shaped triples, their starts y_p / y_a / y_b apart, as the y dimension of one grid
 #define ZKP_LAUNCH_INGEST(VAR)                                                                                              \
   k_ingest2<MODE, VAR><<<dim3((unsigned)((threads + ZKP_INGEST_THREADS(VAR) - 1) / ZKP_INGEST_THREADS(VAR)), ny),           \
                          ZKP_INGEST_THREADS(VAR), 0, launch_stream>>>(                                                      \
-      (const uint4*)d_points, p_lo, p_cnt, (uint4*)ctx->niels.p, (const uint4*)d_scalars, sA_lo, sA_cnt, sB_lo, sB_cnt, n,  \
-      pl.c, pl.W, pl.B, MODE == 0 ? (uint32_t*)ctx->hist.p : (uint32_t*)ctx->cursor.p, (uint32_t*)ctx->sorted.p,            \
-      (int*)ctx->flags.p, y_p, y_a, y_b)
+      (const uint4*)d_points, (uint4*)ctx->niels.p, (const uint4*)d_scalars, a, n, pl.c, pl.W, pl.B,                        \
+      MODE == 0 ? (uint32_t*)ctx->hist.p : (uint32_t*)ctx->cursor.p, (uint32_t*)ctx->sorted.p, (int*)ctx->flags.p)
   switch (ctx->ingest_variant) {
     case 1: ZKP_LAUNCH_INGEST(1); break;
     case 2: ZKP_LAUNCH_INGEST(2); break;
@@ -500,12 +522,16 @@ static int32_t launch_ingest2(zkp_ctx* ctx, const msm_plan& pl, const void* d_sc
   LAUNCH_CHECK(ctx);
   return ZKP_OK;
 }
-// the same with one contiguous scalar range [s_lo, s_lo + s_cnt) cut into two halves
+// points [p_lo, p_lo + p_cnt) and ONE contiguous term range [s_lo, s_lo + s_cnt) cut into two halves
 template <int MODE>
 static int32_t launch_ingest2_range(zkp_ctx* ctx, const msm_plan& pl, const void* d_scalars, const void* d_points, size_t n,
                                     size_t p_lo, size_t p_cnt, size_t s_lo, size_t s_cnt, cudaStream_t on = nullptr) {
   const size_t half = (s_cnt + 1) / 2;
-  return launch_ingest2<MODE>(ctx, pl, d_scalars, d_points, n, p_lo, p_cnt, s_lo, half, s_lo + half, s_cnt - half, on);
+  ingest_args a = {};
+  a.p_lo = p_lo; a.p_cnt = p_cnt;
+  a.s_lo[0] = s_lo; a.s_cnt[0] = half;
+  a.s_lo[1] = s_lo + half; a.s_cnt[1] = s_cnt - half;
+  return launch_ingest2<MODE>(ctx, pl, d_scalars, d_points, n, a, 1, on);
 }
 static bool use_fused_sort(const zkp_ctx* ctx, const msm_plan& pl) {
   return !ctx->profile && pl.sort == ctx->stream && ctx->fused_sort;
@@ -1166,6 +1192,64 @@ extern "C" int32_t zkp_selftest_bv_script(const zkp_statement_desc* sd, const ui
 // ---------------------------------------------------------------------------------------------------------
 // batch verification from proofs: transcripts, challenges, weights and coefficient fold on the device
 // ---------------------------------------------------------------------------------------------------------
+// ZKP_BV_TIMELINE=1 in the environment: zkp_batch_verify_proofs records a timed event after every copy, front-end kernel and
+// ingestion launch and prints, after the call, when each of them ENDED (ms after the call's first event) -- a development
+// aid for the slab pipeline (no profiler needed); the call runs as usual otherwise.
+struct bv_timeline {
+  bool on = false;
+  std::vector<std::pair<std::string, cudaEvent_t>> marks;
+  bv_timeline() { const char* e = getenv("ZKP_BV_TIMELINE"); on = e && *e && *e != '0'; }
+  void mark(const char* what, size_t idx, cudaStream_t s) {
+    if (!on) return;
+    cudaEvent_t ev;
+    if (cudaEventCreate(&ev) != cudaSuccess) return;
+    cudaEventRecord(ev, s);
+    marks.emplace_back(std::string(what) + "[" + std::to_string(idx) + "]", ev);
+  }
+  void report() {
+    if (!on || marks.empty()) return;
+    cudaDeviceSynchronize();
+    for (auto& m : marks) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, marks[0].second, m.second);
+      fprintf(stderr, "bv_timeline %-18s %9.3f ms\n", m.first.c_str(), ms);
+    }
+    for (auto& m : marks) cudaEventDestroy(m.second);
+    marks.clear();
+  }
+};
+// The MSM terms of a batch are a (rows x N) matrix behind the nc static terms (term (row, j) = nc + row * N + j).  One
+// ingestion step over the columns [j0, j0 + cnt): the points of the P rows from p_row0 on are decompressed, and the thread
+// that takes point (p_row0 + q, j) also takes the digits of the terms (q, j), (q + P, j), (q + 2 P, j) -- as many of the
+// `rows` rows as exist -- so the digit work of ALL rows rides under the decompression of P of them (rows <= 3 P; rows beyond
+// that get digit-only launches).  Rows with the same number of term ranges go out as ONE grid (blockIdx.y = row).
+template <int MODE>
+static int32_t bv_rows_launch(zkp_ctx* ctx, const msm_plan& pl, const void* dsc, const void* dpts, size_t n, size_t nc,
+                              size_t N, size_t rows, size_t p_row0, size_t P, size_t j0, size_t cnt) {
+  auto clampP = [&](size_t x) { return x > P ? P : x; };
+  const size_t g3 = rows > 2 * P ? clampP(rows - 2 * P) : 0, g2 = rows > P ? clampP(rows - P) : 0;
+  const size_t lo[4] = {0, g3, g2, P};   // q in [lo[i], lo[i+1]) carries 3 - i term ranges
+  for (int i = 0; i < 3; i++) {
+    const size_t q0 = lo[i], q1 = lo[i + 1];
+    if (q1 <= q0) continue;
+    ingest_args a = {};
+    a.p_lo = nc + (p_row0 + q0) * N + j0; a.p_cnt = cnt; a.y_p = N;
+    for (int j = 0; j < 3 - i; j++) {
+      a.s_lo[j] = nc + (q0 + (size_t)j * P) * N + j0; a.s_cnt[j] = cnt; a.y_s[j] = N;
+    }
+    int32_t r = launch_ingest2<MODE>(ctx, pl, dsc, dpts, n, a, (unsigned)(q1 - q0));
+    if (r != ZKP_OK) return r;
+  }
+  for (size_t row = 3 * P; row < rows; row += 3) {   // digit-only: no decompression left to hide them under
+    ingest_args a = {};
+    for (int j = 0; j < 3 && row + j < rows; j++) {
+      a.s_lo[j] = nc + (row + j) * N + j0; a.s_cnt[j] = cnt;
+    }
+    int32_t r = launch_ingest2<MODE>(ctx, pl, dsc, dpts, n, a);
+    if (r != ZKP_OK) return r;
+  }
+  return ZKP_OK;
+}
 static int32_t batch_verify_proofs_impl(zkp_ctx* ctx, const zkp_statement_desc* sd, const uint32_t* prefix_state,
                                         size_t N, const uint8_t* instance_enc, const uint8_t* common_enc,
                                         const uint8_t* commitments, const uint8_t* responses,
@@ -1249,56 +1333,129 @@ static int32_t batch_verify_proofs_impl(zkp_ctx* ctx, const zkp_statement_desc* 
   CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[nchunks], 0));
   unsigned block_base = 0;
   const bool fused = use_fused_sort(ctx, pl);
-  const size_t R1 = rows / 2;   // rows decompressed during phase 1 (the others during phase 2)
+  bv_timeline tl;
+  tl.mark("start", 0, st);
+  // Rows of a slab decompressed during phase 1 (under the histogram of all its rows, as the proofs arrive); the others follow
+  // in phase 2 under the scatter.  The split is chosen PER SLAB: when a slab arrives and the GPU has already finished the
+  // previous one, the pipeline is waiting for the host link (several GPUs sharing one host's memory bandwidth), and the slab
+  // is decompressed whole, there and then -- time that would otherwise be idle; its digits are scattered on their own in
+  // phase 2.  Otherwise (the GPU is the bottleneck, every order costs the same) half of the rows go to each phase, the split
+  // under which neither the histogram nor the scatter costs a pass.  bv_phase1_rows > 0 fixes the split for every slab;
+  // -1 alternates between the two choices (tests).
+  const size_t R_half = rows / 2, R_all = rows;
+  const bool adaptive = fused && ctx->bv_phase1_rows == 0 && nchunks > 1;
+  std::vector<size_t> r1_of(nchunks, R_half);
+  if (ctx->bv_phase1_rows > 0)
+    for (size_t c = 0; c < nchunks; c++) r1_of[c] = (size_t)ctx->bv_phase1_rows > rows ? rows : (size_t)ctx->bv_phase1_rows;
+  if (ctx->bv_phase1_rows < 0)
+    for (size_t c = 0; c < nchunks; c++) r1_of[c] = (c & 1) ? R_all : R_half;
+  while (adaptive && ctx->ing_ev.size() < nchunks) {
+    cudaEvent_t e;
+    CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->ing_ev.push_back(e);
+  }
+  // the front end (k_bv_prepare2: Keccak and scalar arithmetic, ALU pipe) of slab i + 1 runs on its own stream, at a higher
+  // priority and with its residency capped (dynamic shared memory it does not use), NEXT TO the decompression of slab i
+  // (integer multiplier) instead of in front of it
+  cudaStream_t ps = st;
+  size_t prep_smem = 0;
+  if (ctx->bv_prep_stream && fused && nchunks > 1) {
+    if (ctx->sm_count < 0) CUDA_TRY(ctx, cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, ctx->device));
+    if (!ctx->prep_stream) {
+      int plo = 0, phi = 0;
+      CUDA_TRY(ctx, cudaDeviceGetStreamPriorityRange(&plo, &phi));
+      CUDA_TRY(ctx, cudaStreamCreateWithPriority(&ctx->prep_stream, cudaStreamNonBlocking, phi));
+    }
+    ps = ctx->prep_stream;
+    prep_smem = (size_t)ctx->bv_prep_smem_kb << 10;
+    if (ctx->bv_carveout >= 0 && ctx->bv_carveout_set != ctx->bv_carveout) {
+      // blocks of two kernels share an SM only under ONE L1 / shared-memory split: give the front end and the ingestion
+      // kernels the same preference, or every SM drains one kernel's blocks before it takes the other's
+      CUDA_TRY(ctx, cudaFuncSetAttribute((const void*)k_bv_prepare2, cudaFuncAttributePreferredSharedMemoryCarveout, ctx->bv_carveout));
+#define ZKP_CARVE(M, V) \
+  CUDA_TRY(ctx, cudaFuncSetAttribute((const void*)k_ingest2<M, V>, cudaFuncAttributePreferredSharedMemoryCarveout, ctx->bv_carveout))
+      ZKP_CARVE(0, 0); ZKP_CARVE(0, 1); ZKP_CARVE(0, 2); ZKP_CARVE(0, 3);
+      ZKP_CARVE(1, 0); ZKP_CARVE(1, 1); ZKP_CARVE(1, 2); ZKP_CARVE(1, 3);
+#undef ZKP_CARVE
+      ctx->bv_carveout_set = ctx->bv_carveout;
+    }
+    if (prep_smem > ctx->bv_prep_smem_set) {
+      CUDA_TRY(ctx, cudaFuncSetAttribute((const void*)k_bv_prepare2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
+      ctx->bv_prep_smem_set = prep_smem;
+    }
+    while (ctx->prep_ev.size() < nchunks) {
+      cudaEvent_t e;
+      CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      ctx->prep_ev.push_back(e);
+    }
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ps, ctx->chunk_ev[nchunks], 0));   // the blob, the reset flags and histogram
+  }
+  // H2D of a slab on the copy stream: instance slab (ni rows of cnt encodings), commitments and responses.  The copies run
+  // two slabs ahead of the kernels (from pageable memory cudaMemcpyAsync returns only when the slab is staged)
+  size_t copies_enqueued = 0;
+  auto enqueue_copies_upto = [&](size_t upto) -> int32_t {
+    for (; copies_enqueued < nchunks && copies_enqueued <= upto; copies_enqueued++) {
+      const size_t cc = copies_enqueued, j0 = cc * chunk, cnt = j0 + chunk < N ? chunk : N - j0;
+      if (ni)
+        CUDA_TRY(ctx, cudaMemcpy2DAsync(dpts + ((size_t)nc + j0) * 32, N * 32, instance_enc + j0 * 32, N * 32, cnt * 32,
+                                        (size_t)ni, cudaMemcpyHostToDevice, ctx->copy_stream));
+      if (k)
+        CUDA_TRY(ctx, cudaMemcpyAsync((uint8_t*)ctx->bv_com.p + j0 * k * 32, commitments + j0 * k * 32, cnt * k * 32,
+                                      cudaMemcpyHostToDevice, ctx->copy_stream));
+      if (m)
+        CUDA_TRY(ctx, cudaMemcpyAsync((uint8_t*)ctx->bv_resp.p + j0 * m * 32, responses + j0 * m * 32, cnt * m * 32,
+                                      cudaMemcpyHostToDevice, ctx->copy_stream));
+      CUDA_TRY(ctx, cudaEventRecord(ctx->chunk_ev[cc], ctx->copy_stream));
+      tl.mark("copy", cc, ctx->copy_stream);
+    }
+    return ZKP_OK;
+  };
   for (size_t cidx = 0; cidx < nchunks; cidx++) {
     const size_t j0 = cidx * chunk, cnt = j0 + chunk < N ? chunk : N - j0;
-    // H2D of this chunk: instance slab (ni rows of cnt encodings), commitments and responses of cnt proofs
-    if (ni)
-      CUDA_TRY(ctx, cudaMemcpy2DAsync(dpts + ((size_t)nc + j0) * 32, N * 32, instance_enc + j0 * 32, N * 32, cnt * 32,
-                                      (size_t)ni, cudaMemcpyHostToDevice, ctx->copy_stream));
-    if (k)
-      CUDA_TRY(ctx, cudaMemcpyAsync((uint8_t*)ctx->bv_com.p + j0 * k * 32, commitments + j0 * k * 32, cnt * k * 32,
-                                    cudaMemcpyHostToDevice, ctx->copy_stream));
-    if (m)
-      CUDA_TRY(ctx, cudaMemcpyAsync((uint8_t*)ctx->bv_resp.p + j0 * m * 32, responses + j0 * m * 32, cnt * m * 32,
-                                    cudaMemcpyHostToDevice, ctx->copy_stream));
-    CUDA_TRY(ctx, cudaEventRecord(ctx->chunk_ev[cidx], ctx->copy_stream));
-    CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->chunk_ev[cidx], 0));
+    r = enqueue_copies_upto(cidx + 2);
+    if (r != ZKP_OK) return r;
+    if (adaptive) {
+      // the host follows the arrival of the slabs: was the GPU already done with the previous slab when this one landed?
+      CUDA_TRY(ctx, cudaEventSynchronize(ctx->chunk_ev[cidx]));
+      if (cidx > 0 && cudaEventQuery(ctx->ing_ev[cidx - 1]) == cudaSuccess) r1_of[cidx] = R_all;
+    }
+    const size_t R1 = r1_of[cidx];
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ps, ctx->chunk_ev[cidx], 0));
     if (pl.sort != st) CUDA_TRY(ctx, cudaStreamWaitEvent(pl.sort, ctx->chunk_ev[cidx], 0));
-    const unsigned nb = (unsigned)((cnt + 127) / 128);
+    unsigned nb = (unsigned)((cnt + 127) / 128);
 #ifdef ZKP_ABLATIONS
     if (!ctx->bv_compiled)
-      k_bv_prepare<<<nb, 128, 0, st>>>(d, (const uint32_t*)(dm + o_prefix), N, dpts + (size_t)nc * 32, dpts,
+      k_bv_prepare<<<nb, 128, 0, ps>>>(d, (const uint32_t*)(dm + o_prefix), N, dpts + (size_t)nc * 32, dpts,
                                        (const uint8_t*)ctx->bv_com.p, (const uint8_t*)ctx->bv_resp.p, dm + o_seed, dsc, dpts,
                                        (uint8_t*)ctx->bv_part.p, nullptr, (int*)ctx->flags.p, j0, cnt, block_base);
     else
 #endif
-      k_bv_prepare2<<<nb, 128, 0, st>>>(d, (const uint32_t*)(dm + o_prefix), N, dpts + (size_t)nc * 32,
-                                        (const uint8_t*)ctx->bv_com.p, (const uint8_t*)ctx->bv_resp.p, dm + o_seed,
-                                        script_blocks, (const unsigned long long*)(dm + o_tm),
-                                        (const uint32_t*)(dm + o_ss), (const bv_seg*)(dm + o_sg), dsc, dpts,
-                                        (uint8_t*)ctx->bv_part.p, nullptr, (int*)ctx->flags.p, j0, cnt, block_base);
+    {
+      // next to the decompression: a RESIDENT grid (every block placed at once, looping over the slab's 128-proof groups).
+      // The block scheduler serves the higher-priority grid first and waits while it has blocks it cannot place, so a
+      // grid larger than its residency cap would keep the ingestion kernel's blocks out for its whole duration.
+      if (ps != st && ctx->bv_prep_blocks > 0 && nb > (unsigned)(ctx->bv_prep_blocks * ctx->sm_count))
+        nb = (unsigned)(ctx->bv_prep_blocks * ctx->sm_count);
+      k_bv_prepare2<<<nb, 128, prep_smem, ps>>>(d, (const uint32_t*)(dm + o_prefix), N, dpts + (size_t)nc * 32,
+                                                (const uint8_t*)ctx->bv_com.p, (const uint8_t*)ctx->bv_resp.p, dm + o_seed,
+                                                script_blocks, (const unsigned long long*)(dm + o_tm),
+                                                (const uint32_t*)(dm + o_ss), (const bv_seg*)(dm + o_sg), dsc, dpts,
+                                                (uint8_t*)ctx->bv_part.p, nullptr, (int*)ctx->flags.p, j0, cnt, block_base);
+    }
     LAUNCH_CHECK(ctx);
     block_base += nb;
+    tl.mark("prepare", cidx, ps);
+    if (ps != st) {
+      CUDA_TRY(ctx, cudaEventRecord(ctx->prep_ev[cidx], ps));
+      CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->prep_ev[cidx], 0));
+    }
     // the slabs of this chunk are complete (points and coefficients)
     if (fused) {
       // phase 1 of the two-phase ingestion: histogram every slab, decompress the slabs of the first R1 rows
-      // (rows 0 .. R1-1 as the y dimension of ONE launch: row r decompresses its slab and histograms rows r and r + R1)
-      if (ctx->bv_merge_rows) {
-        const size_t a = (size_t)nc + j0, b = (size_t)nc + R1 * N + j0;
-        r = launch_ingest2<0>(ctx, pl, dsc, dpts, n, a, cnt, a, cnt, b, cnt, nullptr, (unsigned)R1, N, N, N);
-        if (r != ZKP_OK) return r;
-      } else {
-        for (size_t row = 0; row < R1; row++) {
-          const size_t a = (size_t)nc + row * N + j0, b = (size_t)nc + (row + R1) * N + j0;
-          r = launch_ingest2<0>(ctx, pl, dsc, dpts, n, a, cnt, a, cnt, b, cnt);
-          if (r != ZKP_OK) return r;
-        }
-      }
-      for (size_t row = 2 * R1; row < rows; row++) {   // odd row count: the last row's histogram on its own
-        r = launch_ingest2<0>(ctx, pl, dsc, dpts, n, 0, 0, (size_t)nc + row * N + j0, cnt, 0, 0);
-        if (r != ZKP_OK) return r;
-      }
+      r = bv_rows_launch<0>(ctx, pl, dsc, dpts, n, (size_t)nc, N, rows, 0, R1, j0, cnt);
+      if (r != ZKP_OK) return r;
+      if (adaptive) CUDA_TRY(ctx, cudaEventRecord(ctx->ing_ev[cidx], st));
+      tl.mark(R1 == R_half ? "ingest1" : "ingest1*", cidx, st);
     } else {
       for (size_t row = 0; row < rows; row++) {
         r = msm_ingest(ctx, pl, dsc, dpts, (size_t)nc + row * N + j0, cnt, false);
@@ -1309,39 +1466,37 @@ static int32_t batch_verify_proofs_impl(zkp_ctx* ctx, const zkp_statement_desc* 
   if (nc) {
     k_bv_static_sum<<<1, 256, 0, st>>>((const uint8_t*)ctx->bv_part.p, (int)block_base, nc, dsc);
     LAUNCH_CHECK(ctx);
-    if (fused) r = launch_ingest2<0>(ctx, pl, dsc, dpts, n, 0, (size_t)nc, 0, (size_t)nc, 0, 0);
+    if (fused) r = launch_ingest2_range<0>(ctx, pl, dsc, dpts, n, 0, (size_t)nc, 0, (size_t)nc);
     else r = msm_ingest(ctx, pl, dsc, dpts, 0, (size_t)nc, false);
     if (r != ZKP_OK) return r;
   }
   if (fused) {
-    // phase 2: the remaining rows are decompressed while the digits of all rows are scattered (two rows per launch)
+    // phase 2: the remaining rows are decompressed while the digits of all rows are scattered
     k_scan<<<pl.W, 1024, 0, st>>>((const uint32_t*)ctx->hist.p, pl.B, (uint32_t*)ctx->offs.p, (uint32_t*)ctx->cursor.p);
     LAUNCH_CHECK(ctx);
-    // launches q < rows / 2 have the same shape (N points, N + N terms): one grid with q as its y dimension
-    size_t q0 = 0;
-    if (ctx->bv_merge_rows && rows / 2 > 1 && rows / 2 <= rows - R1) {
-      q0 = rows / 2;
-      r = launch_ingest2<1>(ctx, pl, dsc, dpts, n, (size_t)nc + R1 * N, N, (size_t)nc, N, (size_t)nc + N, N, nullptr,
-                            (unsigned)q0, N, 2 * N, 2 * N);
+    tl.mark("scan", 0, st);
+    for (size_t c0 = 0; c0 < nchunks;) {   // one step per run of slabs with the same split
+      size_t c1 = c0 + 1;
+      while (c1 < nchunks && r1_of[c1] == r1_of[c0]) c1++;
+      const size_t j0 = c0 * chunk, j1 = c1 * chunk < N ? c1 * chunk : N;
+      r = bv_rows_launch<1>(ctx, pl, dsc, dpts, n, (size_t)nc, N, rows, r1_of[c0], rows - r1_of[c0], j0, j1 - j0);
       if (r != ZKP_OK) return r;
+      c0 = c1;
     }
-    for (size_t q = q0; q < rows - R1; q++) {
-      const size_t ra = 2 * q, rb = 2 * q + 1;
-      r = launch_ingest2<1>(ctx, pl, dsc, dpts, n, (size_t)nc + (R1 + q) * N, N, (size_t)nc + ra * N, ra < rows ? N : 0,
-                            (size_t)nc + rb * N, rb < rows ? N : 0);
-      if (r != ZKP_OK) return r;
-    }
+    tl.mark("ingest2", 0, st);
     if (nc) {
-      r = launch_ingest2<1>(ctx, pl, dsc, dpts, n, 0, 0, 0, (size_t)nc, 0, 0);
+      r = launch_ingest2_range<1>(ctx, pl, dsc, dpts, n, 0, 0, 0, (size_t)nc);
       if (r != ZKP_OK) return r;
     }
   }
   r = msm_finish(ctx, pl, dsc, n, (msm_result*)ctx->result.p, false, fused);
   if (r != ZKP_OK) return r;
+  tl.mark("finish", 0, st);
   if (coeff_out) CUDA_TRY(ctx, cudaMemcpyAsync(coeff_out, dsc, n * 32, cudaMemcpyDeviceToHost, st));
   if (points_out) CUDA_TRY(ctx, cudaMemcpyAsync(points_out, dpts, n * 32, cudaMemcpyDeviceToHost, st));
   int32_t ident = 0;
   r = fetch_result(ctx, nullptr, &ident, first_bad);   // identity encodings / bad points -> 1, bad responses -> 3
+  tl.report();
   if (r != ZKP_OK) return r;
   *accept = ident;
   return ZKP_OK;

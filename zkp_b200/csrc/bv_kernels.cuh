@@ -215,13 +215,16 @@ __global__ void __launch_bounds__(128) k_bv_prepare2(bv_desc d, const uint32_t* 
                                                      size_t cnt, unsigned block_base) {
   __shared__ unsigned long long buf[21][128];   // the rate block under construction, one column per thread
   __shared__ scl red[128];
-  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t j = j0 + tid;
-  const bool live = tid < cnt;
   const int tx = threadIdx.x;
   scl inst[ZKP_BV_MAX_VARS], stat[ZKP_BV_MAX_VARS];
-  for (int i = 0; i < d.ni; i++) scl_zero(inst[i]);
   for (int i = 0; i < d.nc; i++) scl_zero(stat[i]);
+  // a block takes the 128-proof groups blockIdx.x, blockIdx.x + gridDim.x, ...: the grid may be smaller than the slab (a
+  // resident set next to the previous slab's decompression, api.cu); the static coefficients accumulate over the groups
+  for (size_t vb = blockIdx.x; vb * 128 < cnt; vb += gridDim.x) {
+  const size_t tid = vb * 128 + threadIdx.x;
+  const size_t j = j0 + tid;
+  const bool live = tid < cnt;
+  for (int i = 0; i < d.ni; i++) scl_zero(inst[i]);
   if (live) {
     uint64_t st[25];
 #pragma unroll
@@ -276,6 +279,7 @@ __global__ void __launch_bounds__(128) k_bv_prepare2(bv_desc d, const uint32_t* 
     scl_neg(minus_c, c);
     if (minus_c_out) store_scl(minus_c_out + j * 32, minus_c);
     bv_weights_and_fold(d, j, N, minus_c, rho_seed, responses, msm_scalars, inst, stat, flags);
+  }
   }
   bv_static_block_sums(d, stat, red, static_part, block_base + blockIdx.x);
 }

@@ -242,22 +242,24 @@ __device__ __forceinline__ void ingest_digits(const uint4* __restrict__ scalars,
 // 1 = (128, 5): <= 96 registers, 20 warps/SM; 2 = (256, 3) and 3 = (128, 6): <= 80 registers, 24 warps/SM.
 #define ZKP_INGEST_THREADS(VAR) ((VAR) == 0 || (VAR) == 2 ? 256 : 128)
 #define ZKP_INGEST_MINBLK(VAR) ((VAR) == 0 ? 1 : (VAR) == 1 ? 5 : (VAR) == 2 ? 3 : 6)
+// One launch = up to three term ranges (A, B, C) and one point range; thread t takes the terms s_lo[j] + t (t < s_cnt[j])
+// and the point p_lo + t (t < p_cnt).  blockIdx.y = one of several equally shaped launches whose starts are y_p / y_s[j]
+// apart: the rows of a batch-verification slab go out as ONE grid (one partial last wave instead of one per row).
+struct ingest_args {
+  size_t p_lo, p_cnt, y_p;
+  size_t s_lo[3], s_cnt[3], y_s[3];
+};
 template <int MODE, int VAR>
 __global__ void __launch_bounds__(ZKP_INGEST_THREADS(VAR), ZKP_INGEST_MINBLK(VAR))
-    k_ingest2(const uint4* __restrict__ enc, size_t p_lo, size_t p_cnt,
-                                                 uint4* __restrict__ niels, const uint4* __restrict__ scalars, size_t sA_lo,
-                                                 size_t sA_cnt, size_t sB_lo, size_t sB_cnt, size_t n, int c, int W,
-                                                 uint32_t B, uint32_t* __restrict__ counters,
-                                                 uint32_t* __restrict__ sorted, int* __restrict__ flags, size_t y_p,
-                                                 size_t y_a, size_t y_b) {
-  // blockIdx.y = one of several equally shaped (points, terms A, terms B) triples whose starts are y_p / y_a / y_b apart:
-  // the rows of a batch-verification slab go out as ONE launch (one partial last wave instead of one per row)
-  p_lo += (size_t)blockIdx.y * y_p;
-  sA_lo += (size_t)blockIdx.y * y_a;
-  sB_lo += (size_t)blockIdx.y * y_b;
+    k_ingest2(const uint4* __restrict__ enc, uint4* __restrict__ niels, const uint4* __restrict__ scalars,
+              const __grid_constant__ ingest_args a, size_t n, int c, int W, uint32_t B, uint32_t* __restrict__ counters,
+              uint32_t* __restrict__ sorted, int* __restrict__ flags) {
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < sA_cnt) ingest_digits<MODE>(scalars, sA_lo + t, n, c, W, B, counters, sorted, flags);
-  if (t < sB_cnt) ingest_digits<MODE>(scalars, sB_lo + t, n, c, W, B, counters, sorted, flags);
+#pragma unroll 1
+  for (int j = 0; j < 3; j++)
+    if (t < a.s_cnt[j])
+      ingest_digits<MODE>(scalars, a.s_lo[j] + (size_t)blockIdx.y * a.y_s[j] + t, n, c, W, B, counters, sorted, flags);
+  const size_t p_cnt = a.p_cnt, p_lo = a.p_lo + (size_t)blockIdx.y * a.y_p;
   if (t >= p_cnt) return;
   const size_t i = p_lo + t;
   uint32_t w8[8];
