@@ -116,7 +116,7 @@ int emul_recode(int32_t* digits, uint8_t* k32, int* neg, const uint8_t* s32, int
   uint32_t ng; uint32_t can = sc_fold_sign(k, ng, s);
   memcpy(k32, k, 32); *neg = (int)ng;
   uint32_t carry = 0;
-  for (int w = 0; w < W; w++) { uint32_t mag, dn; sc_digit(mag, dn, carry, k, w, c); digits[w] = dn ? -(int32_t)mag : (int32_t)mag; }
+  for (int w = 0; w < W; w++) { uint32_t mag, dn; sc_next_digit(mag, dn, carry, k, c); digits[w] = dn ? -(int32_t)mag : (int32_t)mag; }
   return (int)can | ((int)carry << 1);
 }
 

@@ -141,7 +141,7 @@ int emul_prove_batch(int m, int ni, int nc, int k, const char* labels, const int
 void emul_msm_vartime_batched(const uint8_t* scalars, const uint8_t* points, const uint64_t* offsets, size_t M, int coop,
                               uint8_t* out, int32_t* status) {
   const size_t total = (size_t)offsets[M];
-  std::vector<uint4> sc(2 * total + 2), pt(2 * total + 2), niels(6 * total + 6), kk(2 * total + 2), k3(2 * total + 2), o(2 * M + 2);
+  std::vector<uint4> sc(2 * total + 2), pt(2 * total + 2), niels(ZKP_NIELS_U4 * total + ZKP_NIELS_U4), kk(2 * total + 2), k3(2 * total + 2), o(2 * M + 2);
   if (total) { memcpy(sc.data(), scalars, total * 32); memcpy(pt.data(), points, total * 32); }
   std::vector<unsigned long long> off(offsets, offsets + M + 1);
   std::vector<uint32_t> order(M + 1);
@@ -210,7 +210,7 @@ void emul_msm_vartime(const uint8_t* scalars, const uint8_t* points, size_t n, i
   }
   const int W = (253 + c - 1) / c;
   const uint32_t B = 1u << (c - 1), total_buckets = (uint32_t)W * B;
-  std::vector<uint4> sc(2 * n), pt(2 * n), niels(6 * n), buckets((size_t)total_buckets * 8);
+  std::vector<uint4> sc(2 * n), pt(2 * n), niels(ZKP_NIELS_U4 * n), buckets((size_t)total_buckets * 8);
   memcpy(sc.data(), scalars, n * 32);
   memcpy(pt.data(), points, n * 32);
   std::vector<uint32_t> hist((size_t)W * B, 0), offs((size_t)W * (B + 1)), cursor((size_t)W * B), sorted((size_t)W * n);

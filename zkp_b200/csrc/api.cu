@@ -132,6 +132,7 @@ struct zkp_ctx {
   std::vector<cudaEvent_t> prep_ev, ing_ev;
   int bv_compiled = 1;      // batch-verification front end: host-compiled transcript script (k_bv_prepare2)
   int ingest_variant = 2;   // occupancy point of k_ingest2 (kernels.cuh ZKP_INGEST_*)
+  int scatter_batch = 1;    // k_ingest2, scatter phase: cursor atomics of four windows in flight together
   int fused_sort = 1;  // histogram and scatter ride under the two halves of the decompression (k_ingest2)
   // host-input pipeline: ramped chunk sizes (from chunk_terms / 8 up to 2 * chunk_terms, down again at the end of phase 1).
   // Measured at the bench size: 138.6 ms per step against 135.8 ms with uniform chunks -- phase 1 is copy-bound, so every
@@ -346,6 +347,15 @@ extern "C" int32_t zkp_ctx_set_option(zkp_ctx* ctx, const char* key, int64_t val
   } else if (!strcmp(key, "bv_chunk_terms")) {
     if (value < 1024) return ZKP_ERR_SIZE;
     ctx->bv_chunk_terms = (size_t)value;
+  } else if (!strcmp(key, "scatter_batch")) {
+    ctx->scatter_batch = value ? 1 : 0;
+  } else if (!strcmp(key, "l2_fetch_granularity")) {
+    // device-wide limit of the calling context (cudaLimitMaxL2FetchGranularity: 32, 64 or 128 bytes): the bucket accumulation
+    // gathers 96-byte points at 32-byte alignment, and every L2 miss fetches this much from HBM
+    if (value != 32 && value != 64 && value != 128) return ZKP_ERR_SIZE;
+    if (cudaSetDevice(ctx->device) != cudaSuccess ||
+        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value) != cudaSuccess)
+      return ZKP_ERR_CUDA;
   } else if (!strcmp(key, "profile")) {
     ctx->profile = value ? 1 : 0;
     if (ctx->profile && !ctx->ev[0])
@@ -431,7 +441,7 @@ static int32_t msm_prepare(zkp_ctx* ctx, size_t n, msm_plan* pl) {
   const uint32_t B = 1u << (c - 1);
   const uint32_t total_buckets = (uint32_t)W * B;
   pl->c = c; pl->W = W; pl->B = B; pl->total_buckets = total_buckets;
-  ENSURE(ctx, ctx->niels, n * 96);
+  ENSURE(ctx, ctx->niels, n * (16 * ZKP_NIELS_U4));
   ENSURE(ctx, ctx->hist, (size_t)W * B * 4);
   ENSURE(ctx, ctx->offs, (size_t)W * (B + 1) * 4);
   ENSURE(ctx, ctx->cursor, (size_t)W * B * 4);
@@ -478,13 +488,13 @@ static int32_t msm_ingest(zkp_ctx* ctx, const msm_plan& pl, const void* d_scalar
 #ifdef ZKP_ABLATIONS
   if (!ctx->profile && pl.sort == st) {   // fused: histogram reductions ride along with the decompression
     k_ingest<<<nb, 256, 0, st>>>((const uint4*)d_points + 2 * base, (const uint4*)d_scalars + 2 * base, cnt,
-                                 (uint4*)ctx->niels.p + 6 * base, pl.c, pl.W, pl.B, (uint32_t*)ctx->hist.p, flags, base);
+                                 (uint4*)ctx->niels.p + ZKP_NIELS_U4 * base, pl.c, pl.W, pl.B, (uint32_t*)ctx->hist.p, flags, base);
     LAUNCH_CHECK(ctx);
     return ZKP_OK;
   }
 #endif
   if (whole) STAGE(0);
-  k_decompress<<<nb, 256, 0, st>>>((const uint4*)d_points + 2 * base, cnt, (uint4*)ctx->niels.p + 6 * base, flags, base);
+  k_decompress<<<nb, 256, 0, st>>>((const uint4*)d_points + 2 * base, cnt, (uint4*)ctx->niels.p + ZKP_NIELS_U4 * base, flags, base);
   LAUNCH_CHECK(ctx);
   if (whole) STAGE(1);
   k_recode<false><<<nb, 256, 0, pl.sort>>>((const uint4*)d_scalars + 2 * base, cnt, pl.c, pl.W, pl.B,
@@ -501,8 +511,10 @@ static int32_t msm_finish(zkp_ctx* ctx, const msm_plan& pl, const void* d_scalar
 // ny equally shaped launches as the y dimension of one grid; MODE 0 histograms the terms' digits, MODE 1 scatters them
 template <int MODE>
 static int32_t launch_ingest2(zkp_ctx* ctx, const msm_plan& pl, const void* d_scalars, const void* d_points, size_t n,
-                              const ingest_args& a, unsigned ny = 1, cudaStream_t on = nullptr) {
+                              const ingest_args& a_in, unsigned ny = 1, cudaStream_t on = nullptr) {
   const cudaStream_t launch_stream = on ? on : ctx->stream;
+  ingest_args a = a_in;
+  a.batched = ctx->scatter_batch;
   size_t threads = a.p_cnt;
   for (int j = 0; j < 3; j++)
     if (a.s_cnt[j] > threads) threads = a.s_cnt[j];
@@ -544,7 +556,7 @@ static bool use_small_path(const zkp_ctx* ctx, size_t n) {
 static int32_t msm_small_launch(zkp_ctx* ctx, const void* d_scalars, const void* d_points, size_t n, msm_result* d_result) {
   cudaStream_t st = ctx->stream;
   const uint32_t G = (uint32_t)(n < (size_t)ctx->small_groups ? n : (size_t)ctx->small_groups);
-  ENSURE(ctx, ctx->niels, n * 96 + 96);
+  ENSURE(ctx, ctx->niels, (n + 1) * (16 * ZKP_NIELS_U4));
   ENSURE(ctx, ctx->sk0, n * 32 + 32);
   ENSURE(ctx, ctx->sk1, n * 32 + 32);
   ENSURE(ctx, ctx->partials, (size_t)G * 128);
@@ -1976,7 +1988,7 @@ extern "C" int32_t zkp_msm_vartime_batched(zkp_ctx* ctx, const uint8_t* scalars,
   ENSURE(ctx, ctx->aux0, (M + 1) * 8);
   ENSURE(ctx, ctx->aux1, M * 32);
   ENSURE(ctx, ctx->aux2, M * 4);
-  ENSURE(ctx, ctx->niels, total * 96 + 96);
+  ENSURE(ctx, ctx->niels, (total + 1) * (16 * ZKP_NIELS_U4));
   ENSURE(ctx, ctx->sk0, total * 32 + 32);
   ENSURE(ctx, ctx->sk1, total * 32 + 32);
   cudaStream_t st = ctx->stream;

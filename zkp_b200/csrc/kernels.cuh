@@ -23,6 +23,13 @@
 #include "ge.cuh"
 #include "sc.cuh"
 
+// An affine Niels point (y+x, y-x, 2dxy: 96 bytes) occupies ZKP_NIELS_U4 uint4 slots of the workspace.  With 8 (128 bytes,
+// 128-byte aligned) the gather of the bucket accumulation touches exactly ONE line per point; with 6 (packed) a point
+// straddles two lines half of the time and HBM delivers whole lines (measured: 196 B per 96-byte point).
+#ifndef ZKP_NIELS_U4
+#define ZKP_NIELS_U4 8
+#endif
+
 namespace zkp {
 
 #define ZKP_CHUNK_L 32      // chunk length of the bucket running-sum reduction
@@ -81,7 +88,7 @@ __global__ void __launch_bounds__(256) k_decompress(const uint4* __restrict__ en
     ge_aniels_identity(q);
     atomicMin(&flags[0], (int)(base + i));
   }
-  uint4* o = niels + 6 * i;
+  uint4* o = niels + ZKP_NIELS_U4 * i;
   store_fe(o, q.yplusx);
   store_fe(o + 2, q.yminusx);
   store_fe(o + 4, q.xy2d);
@@ -148,7 +155,7 @@ __global__ void __launch_bounds__(256) k_recode(const uint4* __restrict__ scalar
   uint32_t carry = 0;
   for (int w = 0; w < W; w++) {
     uint32_t mag, dneg;
-    sc_digit(mag, dneg, carry, k, w, c);
+    sc_next_digit(mag, dneg, carry, k, c);
     if (mag != 0) {
       uint32_t* ctr = counters + (size_t)w * B + (mag - 1);
       if (SCATTER) {
@@ -180,7 +187,7 @@ __global__ void __launch_bounds__(256) k_ingest(const uint4* __restrict__ enc, c
       uint32_t carry = 0;
       for (int w = 0; w < W; w++) {
         uint32_t mag, dneg;
-        sc_digit(mag, dneg, carry, k, w, c);
+        sc_next_digit(mag, dneg, carry, k, c);
         if (mag != 0) atomicAdd(hist + (size_t)w * B + (mag - 1), 1u);
       }
     }
@@ -196,7 +203,7 @@ __global__ void __launch_bounds__(256) k_ingest(const uint4* __restrict__ enc, c
     ge_aniels_identity(q);
     atomicMin(&flags[0], (int)(base + i));
   }
-  uint4* o = niels + 6 * i;
+  uint4* o = niels + ZKP_NIELS_U4 * i;
   store_fe(o, q.yplusx);
   store_fe(o + 2, q.yminusx);
   store_fe(o + 4, q.xy2d);
@@ -213,7 +220,7 @@ __global__ void __launch_bounds__(256) k_ingest(const uint4* __restrict__ enc, c
 template <int MODE>
 __device__ __forceinline__ void ingest_digits(const uint4* __restrict__ scalars, size_t i, size_t n, int c, int W, uint32_t B,
                                               uint32_t* __restrict__ counters, uint32_t* __restrict__ sorted,
-                                              int* __restrict__ flags) {
+                                              int* __restrict__ flags, bool batched) {
   uint32_t s[8], k[8];
   load_words8(s, scalars + 2 * i);
   uint32_t neg;
@@ -223,9 +230,35 @@ __device__ __forceinline__ void ingest_digits(const uint4* __restrict__ scalars,
     return;   // contributes nothing; the call fails with ZKP_ERR_SCALAR
   }
   uint32_t carry = 0;
-  for (int w = 0; w < W; w++) {
+  if (MODE == 1 && batched) {
+    // scatter, four windows at a time: the four cursor atomics are in flight together and the four stores wait for
+    // them afterwards (one round trip to L2 per group instead of one per window)
+    for (int w0 = 0; w0 < W && !sc_digits_done(k, carry); w0 += 4) {   // (the higher windows of a 128-bit weight are empty)
+      uint32_t pos[4], val[4];
+      bool has[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int w = w0 + u;
+        has[u] = false;
+        if (w < W) {
+          uint32_t mag, dneg;
+          sc_next_digit(mag, dneg, carry, k, c);
+          if (mag != 0) {
+            has[u] = true;
+            val[u] = (uint32_t)i | ((neg ^ dneg) << 31);
+            pos[u] = atomicAdd(counters + (size_t)w * B + (mag - 1), 1u);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (has[u]) sorted[(size_t)(w0 + u) * n + pos[u]] = val[u];
+    }
+    return;
+  }
+  for (int w = 0; w < W && !sc_digits_done(k, carry); w++) {
     uint32_t mag, dneg;
-    sc_digit(mag, dneg, carry, k, w, c);
+    sc_next_digit(mag, dneg, carry, k, c);
     if (mag != 0) {
       uint32_t* ctr = counters + (size_t)w * B + (mag - 1);
       if (MODE == 0) {
@@ -248,6 +281,7 @@ __device__ __forceinline__ void ingest_digits(const uint4* __restrict__ scalars,
 struct ingest_args {
   size_t p_lo, p_cnt, y_p;
   size_t s_lo[3], s_cnt[3], y_s[3];
+  int batched;   // scatter: the cursor atomics of four windows in flight together
 };
 template <int MODE, int VAR>
 __global__ void __launch_bounds__(ZKP_INGEST_THREADS(VAR), ZKP_INGEST_MINBLK(VAR))
@@ -258,7 +292,8 @@ __global__ void __launch_bounds__(ZKP_INGEST_THREADS(VAR), ZKP_INGEST_MINBLK(VAR
 #pragma unroll 1
   for (int j = 0; j < 3; j++)
     if (t < a.s_cnt[j])
-      ingest_digits<MODE>(scalars, a.s_lo[j] + (size_t)blockIdx.y * a.y_s[j] + t, n, c, W, B, counters, sorted, flags);
+      ingest_digits<MODE>(scalars, a.s_lo[j] + (size_t)blockIdx.y * a.y_s[j] + t, n, c, W, B, counters, sorted, flags,
+                          a.batched != 0);
   const size_t p_cnt = a.p_cnt, p_lo = a.p_lo + (size_t)blockIdx.y * a.y_p;
   if (t >= p_cnt) return;
   const size_t i = p_lo + t;
@@ -273,7 +308,7 @@ __global__ void __launch_bounds__(ZKP_INGEST_THREADS(VAR), ZKP_INGEST_MINBLK(VAR
     ge_aniels_identity(q);
     atomicMin(&flags[0], (int)i);
   }
-  uint4* o = niels + 6 * i;
+  uint4* o = niels + ZKP_NIELS_U4 * i;
   store_fe(o, q.yplusx);
   store_fe(o + 2, q.yminusx);
   store_fe(o + 4, q.xy2d);
@@ -374,7 +409,7 @@ __global__ void __launch_bounds__(1024) k_scan_add(uint32_t* __restrict__ out, u
 // K5: bucket accumulation.  G lanes cooperate on one bucket.
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void load_aniels(ge_aniels& q, const uint4* __restrict__ niels, uint32_t e) {
-  const uint4* p = niels + (size_t)(e & 0x7fffffffu) * 6;
+  const uint4* p = niels + (size_t)(e & 0x7fffffffu) * ZKP_NIELS_U4;
   load_fe_ldg(q.yplusx, p);
   load_fe_ldg(q.yminusx, p + 2);
   load_fe_ldg(q.xy2d, p + 4);

@@ -41,20 +41,22 @@ ZKP_DEV uint32_t sc_fold_sign(uint32_t* k, uint32_t& neg, const uint32_t* s) {
   return canonical;
 }
 
-// c-bit field of k starting at bit position pos (pos + c may run past 256: zero-extended).  c <= 24.
-ZKP_DEV uint32_t sc_bits(const uint32_t* k, int pos, int c) {
-  int wi = pos >> 5, sh = pos & 31;
-  uint32_t lo = wi < 8 ? k[wi] : 0u;
-  uint32_t hi = (wi + 1) < 8 ? k[wi + 1] : 0u;
-  uint64_t v = ((uint64_t)hi << 32) | lo;
-  return (uint32_t)(v >> sh) & ((1u << c) - 1u);
+// Signed window digits, lowest window first: every call returns the digit of the lowest c bits of k (plus the incoming
+// carry) in (-2^(c-1), 2^(c-1)] -- |digit| in `mag` (0..2^(c-1)), its sign in `dneg` -- and shifts k right by c bits
+// (eight funnel shifts: no limb of k is ever indexed by a run-time value).  1 <= c <= 24.
+ZKP_DEV uint32_t sc_shr_limb(uint32_t lo, uint32_t hi, int s) {
+#if ZKP_DEVICE_ASM
+  return __funnelshift_r(lo, hi, s);
+#else
+  return (lo >> s) | (hi << (32 - s));
+#endif
 }
-
-// Signed digit of window w (width c) with incoming carry; digits in (-2^(c-1), 2^(c-1)].
-// Returns |digit| in `mag` (0..2^(c-1)), its sign in `dneg`, and updates carry.
-ZKP_DEV void sc_digit(uint32_t& mag, uint32_t& dneg, uint32_t& carry, const uint32_t* k, int w, int c) {
-  uint32_t raw = sc_bits(k, w * c, c) + carry;
-  uint32_t half = 1u << (c - 1);
+ZKP_DEV void sc_next_digit(uint32_t& mag, uint32_t& dneg, uint32_t& carry, uint32_t* k, int c) {
+  const uint32_t raw = (k[0] & ((1u << c) - 1u)) + carry;
+#pragma unroll
+  for (int i = 0; i < 7; i++) k[i] = sc_shr_limb(k[i], k[i + 1], c);
+  k[7] >>= c;
+  const uint32_t half = 1u << (c - 1);
   if (raw > half) {
     mag = (1u << c) - raw;
     dneg = 1;
@@ -64,6 +66,10 @@ ZKP_DEV void sc_digit(uint32_t& mag, uint32_t& dneg, uint32_t& carry, const uint
     dneg = 0;
     carry = 0;
   }
+}
+// nothing left: every further digit is zero
+ZKP_DEV bool sc_digits_done(const uint32_t* k, uint32_t carry) {
+  return (k[0] | k[1] | k[2] | k[3] | k[4] | k[5] | k[6] | k[7] | carry) == 0;
 }
 
 }  // namespace zkp

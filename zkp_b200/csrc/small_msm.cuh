@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(256) k_decompress_valid(const uint4* __restric
   ge_aniels q;
   ge_aniels_from_affine(q, x, y, t);
   if (!ok) fe_zero(q.yplusx);
-  uint4* o = niels + 6 * i;
+  uint4* o = niels + ZKP_NIELS_U4 * i;
   store_fe(o, q.yplusx);
   store_fe(o + 2, q.yminusx);
   store_fe(o + 4, q.xy2d);
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(64) k_small_msm_vt(const uint32_t* __restrict_
   const size_t lo = offsets[j], hi = offsets[j + 1];
   int st = 0;
   for (size_t t = lo; t < hi; t++) {
-    uint4 first = __ldg(niels + 6 * t), second = __ldg(niels + 6 * t + 1);
+    uint4 first = __ldg(niels + ZKP_NIELS_U4 * t), second = __ldg(niels + ZKP_NIELS_U4 * t + 1);
     if ((first.x | first.y | first.z | first.w | second.x | second.y | second.z | second.w) == 0) st = 1;
     if (__ldg(kk + 8 * t + 7) == 0xffffffffu && st == 0) st = 3;
   }
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(64) k_single_msm_vt(const uint32_t* __restrict
   if (g >= G) return;          // the four lanes of a group leave together
   bool ok = true;
   for (size_t t = g; t < n; t += G) {
-    uint4 first = __ldg(niels + 6 * t), second = __ldg(niels + 6 * t + 1);
+    uint4 first = __ldg(niels + ZKP_NIELS_U4 * t), second = __ldg(niels + ZKP_NIELS_U4 * t + 1);
     if ((first.x | first.y | first.z | first.w | second.x | second.y | second.z | second.w) == 0) {
       if (sub == 0) atomicMin(&flags[0], (int)t);
       ok = false;
