@@ -222,7 +222,6 @@ def main():
     ap.add_argument("--bv-chunk-terms-log2", type=int, default=0, help="tuning: slab size (terms) of the from-proofs leg")
     ap.add_argument("--dual-stream", type=int, default=-1, help="tuning: chunk kernels of the e2e leg on two alternating streams (0/1)")
     ap.add_argument("--scatter-batch", type=int, default=-1, help="tuning: scatter phase with four cursor atomics in flight (0/1)")
-    ap.add_argument("--l2-fetch", type=int, default=0, help="tuning: cudaLimitMaxL2FetchGranularity (32/64/128)")
     ap.add_argument("--bv-phase1-rows", type=int, default=0, help="tuning: rows decompressed in phase 1 of the from-proofs leg")
     ap.add_argument("--bv-prep-stream", type=int, default=-1, help="tuning: front-end kernel of the from-proofs leg on its own stream (0/1)")
     ap.add_argument("--bv-prep-smem-kb", type=int, default=-1, help="tuning: residency cap of that kernel (unused dynamic shared memory, KB)")
@@ -345,8 +344,6 @@ def main():
         eng.set_option("phase1_percent", args.phase1_percent)
     if args.scatter_batch >= 0:
         eng.set_option("scatter_batch", args.scatter_batch)
-    if args.l2_fetch:
-        eng.set_option("l2_fetch_granularity", args.l2_fetch)
     if args.bv_phase1_rows:
         eng.set_option("bv_phase1_rows", args.bv_phase1_rows)
     if args.bv_prep_stream >= 0:

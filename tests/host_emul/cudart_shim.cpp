@@ -24,7 +24,6 @@ cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
 cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
 cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
-cudaError_t cudaDeviceSetLimit(enum cudaLimit, size_t) { return cudaSuccess; }
 cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = (cudaEvent_t)(++g_handles + (char*)nullptr); return cudaSuccess; }
 cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = (cudaEvent_t)(++g_handles + (char*)nullptr); return cudaSuccess; }
 cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }

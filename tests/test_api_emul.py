@@ -317,3 +317,60 @@ def test_small_msms_codec_and_selftests_through_the_emulated_abi(api):
     buf = ctypes.create_string_buffer(32)
     assert api.zkp_selftest_hash(api.ctx, buf) == 0
     assert buf.raw.hex() == U.golden("merlin.json")["complex"]
+
+
+def test_verify_from_proof_bytes_over_several_slabs_through_the_emulated_abi(api):
+    """zkp_batch_verify_proofs with more proofs than one slab holds (1030 DLEQ proofs, 1024-proof slabs): the copies run
+    ahead, the front-end kernel runs slab by slab on its own stream as a resident grid (2 emulated SMs x 2 blocks: every block
+    loops over two 128-proof groups), the split of the rows between the two ingestion phases is chosen per slab -- here the
+    stand-in runtime reports every earlier slab as finished, so slab 1 is decompressed whole in phase 1 -- or alternates
+    (-1) or is fixed, phase 2 runs once per run of equally split slabs.  Every variant builds the MSM inputs of the
+    single-slab call, accepts, and rejects a tampered proof of the LAST slab."""
+    ost = OT.DLEQ
+    G = R.BASEPOINT
+    H = R.hash_from_bytes_sha512(R.compress(G))
+    rng = OT.SeededRng(b"slabs")
+    D, N = 5, 1030
+    proofs, encs = [], []
+    for j in range(D):
+        x = 7700000001 + 13 * j
+        pts = {"A": R.pt_mul(x, G), "B": R.pt_mul(x, H), "H": H, "G": G}
+        proof, enc = ost.prove_batchable(OM.Transcript(b"DLEQSlabs"), {"x": x}, pts, OneShot(rng.bytes(32)))
+        proofs.append(proof)
+        encs.append(enc)
+    names = ost.instance + ost.common
+    ni, nc, k, m = len(ost.instance), len(ost.common), len(ost.constraints), len(ost.secrets)
+    d, keep = _flat(ost)
+    prefix = _prefix(ost, b"DLEQSlabs")
+    inst = np.frombuffer(b"".join(encs[j % D][n] for n in ost.instance for j in range(N)), np.uint8).reshape(ni, N, 32).copy()
+    comm = np.frombuffer(b"".join(encs[0][n] for n in ost.common), np.uint8).reshape(nc, 32).copy()
+    com = np.frombuffer(b"".join(c for j in range(N) for c in proofs[j % D].commitments), np.uint8).reshape(N, k, 32).copy()
+    resp = np.frombuffer(b"".join(S.to_bytes(r) for j in range(N) for r in proofs[j % D].responses), np.uint8).reshape(N, m, 32).copy()
+    n = nc + (ni + k) * N
+    sd = (ctypes.c_uint8 * 32)(*bytes(range(3, 35)))
+    acc, bad = i32(-1), i64(0)
+
+    def verify(resp_, want=True):
+        co, po = np.zeros((n, 32), np.uint8), np.zeros((n, 32), np.uint8)
+        rc = api.zkp_batch_verify_proofs(api.ctx, ctypes.byref(d), _p(prefix), N, _p(inst), _p(comm), _p(com), _p(resp_), sd,
+                                         ctypes.byref(acc), ctypes.byref(bad), _p(co) if want else None, _p(po) if want else None)
+        return rc, acc.value, co, po
+
+    tampered = resp.copy()
+    tampered[N - 2, 0, 5] ^= 0x40
+    try:
+        assert api.zkp_ctx_set_option(api.ctx, b"bv_chunk_terms", 1 << 30) == 0     # one slab
+        rc, a, co0, po0 = verify(resp)
+        assert (rc, a) == (0, 1)
+        assert api.zkp_ctx_set_option(api.ctx, b"bv_chunk_terms", 1024) == 0        # slabs of 1024 + 6 proofs
+        cases = (0, -1, 1, 3, 4) if SLOW else (0, -1, 3)
+        for rows1 in cases:
+            assert api.zkp_ctx_set_option(api.ctx, b"bv_phase1_rows", rows1) == 0
+            rc, a, co, po = verify(resp)
+            assert (rc, a) == (0, 1), rows1
+            assert (co == co0).all() and (po == po0).all(), rows1
+            rc, a, _, _ = verify(tampered, want=False)
+            assert (rc, a) == (0, 0), rows1
+    finally:
+        for key, v in ((b"bv_chunk_terms", 1 << 19), (b"bv_phase1_rows", 0)):
+            api.zkp_ctx_set_option(api.ctx, key, v)

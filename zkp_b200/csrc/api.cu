@@ -126,8 +126,6 @@ struct zkp_ctx {
   int bv_prep_smem_kb = 64; // ... its residency cap: unused dynamic shared memory per 128-thread block (64 KB = 2 blocks per SM)
   size_t bv_prep_smem_set = 0;
   int bv_prep_blocks = 2;   // ... and the resident grid it runs as: blocks per SM (0 = one block per 128 proofs)
-  int bv_carveout = 100;    // ... shared-memory carve-out (percent) preferred by BOTH that kernel and k_ingest2 (-1 = leave)
-  int bv_carveout_set = -2;
   cudaStream_t prep_stream = nullptr;
   std::vector<cudaEvent_t> prep_ev, ing_ev;
   int bv_compiled = 1;      // batch-verification front end: host-compiled transcript script (k_bv_prepare2)
@@ -322,9 +320,6 @@ extern "C" int32_t zkp_ctx_set_option(zkp_ctx* ctx, const char* key, int64_t val
   } else if (!strcmp(key, "bv_prep_blocks")) {
     if (value < 0 || value > 16) return ZKP_ERR_SIZE;
     ctx->bv_prep_blocks = (int)value;
-  } else if (!strcmp(key, "bv_carveout")) {
-    if (value < -1 || value > 100) return ZKP_ERR_SIZE;
-    ctx->bv_carveout = (int)value;
   } else if (!strcmp(key, "bv_prep_smem_kb")) {
     if (value < 0 || value > 160) return ZKP_ERR_SIZE;
     ctx->bv_prep_smem_kb = (int)value;
@@ -349,13 +344,6 @@ extern "C" int32_t zkp_ctx_set_option(zkp_ctx* ctx, const char* key, int64_t val
     ctx->bv_chunk_terms = (size_t)value;
   } else if (!strcmp(key, "scatter_batch")) {
     ctx->scatter_batch = value ? 1 : 0;
-  } else if (!strcmp(key, "l2_fetch_granularity")) {
-    // device-wide limit of the calling context (cudaLimitMaxL2FetchGranularity: 32, 64 or 128 bytes): the bucket accumulation
-    // gathers 96-byte points at 32-byte alignment, and every L2 miss fetches this much from HBM
-    if (value != 32 && value != 64 && value != 128) return ZKP_ERR_SIZE;
-    if (cudaSetDevice(ctx->device) != cudaSuccess ||
-        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value) != cudaSuccess)
-      return ZKP_ERR_CUDA;
   } else if (!strcmp(key, "profile")) {
     ctx->profile = value ? 1 : 0;
     if (ctx->profile && !ctx->ev[0])
@@ -1380,17 +1368,6 @@ static int32_t batch_verify_proofs_impl(zkp_ctx* ctx, const zkp_statement_desc* 
     }
     ps = ctx->prep_stream;
     prep_smem = (size_t)ctx->bv_prep_smem_kb << 10;
-    if (ctx->bv_carveout >= 0 && ctx->bv_carveout_set != ctx->bv_carveout) {
-      // blocks of two kernels share an SM only under ONE L1 / shared-memory split: give the front end and the ingestion
-      // kernels the same preference, or every SM drains one kernel's blocks before it takes the other's
-      CUDA_TRY(ctx, cudaFuncSetAttribute((const void*)k_bv_prepare2, cudaFuncAttributePreferredSharedMemoryCarveout, ctx->bv_carveout));
-#define ZKP_CARVE(M, V) \
-  CUDA_TRY(ctx, cudaFuncSetAttribute((const void*)k_ingest2<M, V>, cudaFuncAttributePreferredSharedMemoryCarveout, ctx->bv_carveout))
-      ZKP_CARVE(0, 0); ZKP_CARVE(0, 1); ZKP_CARVE(0, 2); ZKP_CARVE(0, 3);
-      ZKP_CARVE(1, 0); ZKP_CARVE(1, 1); ZKP_CARVE(1, 2); ZKP_CARVE(1, 3);
-#undef ZKP_CARVE
-      ctx->bv_carveout_set = ctx->bv_carveout;
-    }
     if (prep_smem > ctx->bv_prep_smem_set) {
       CUDA_TRY(ctx, cudaFuncSetAttribute((const void*)k_bv_prepare2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
       ctx->bv_prep_smem_set = prep_smem;
