@@ -552,8 +552,8 @@ def main():
                     "whole_path_hbm": {"bytes_per_proof": BYTES_PER_PROOF,
                                        "achieved_GBs": N * BYTES_PER_PROOF / (ms_step * 1e-3) / 1e9,
                                        "frac": N * BYTES_PER_PROOF / (ms_step * 1e-3) / 1e9 / hbm_peak},
-                    "integer_pipe": {"what": "the path is bound by the FMA-heavy pipe (32x32->64 IMAD.WIDE: 86-87 % busy in "
-                                             "k_ingest2 and k_accumulate, profiles/r02_pipe_counters.md), not by HBM: kernel "
+                    "integer_pipe": {"what": "the path is bound by the FMA-heavy pipe (32x32->64 IMAD.WIDE: 85-86 % busy in "
+                                             "k_ingest2 and k_accumulate, profiles/r02_ingest_ncu.json), not by HBM: kernel "
                                              "time against the register-resident field-op rates of this run",
                                      "fe_sq_per_s_calibrated": fe_sq_rate, "fe_mul_per_s_calibrated": fe_mul_rate,
                                      "madd_per_s_calibrated": madd_rate,
