@@ -13,7 +13,28 @@
 
 namespace zkp {
 
-ZKP_DEV uint64_t rol64(uint64_t x, int n) { return (x << n) | (x >> (64 - n)); }
+
+// Three-input logic on 32-bit halves, spelled out: the front-end kernels are bound by the ALU pipe (profiles/
+// r02_front_end_ncu.md) and a Keccak round written on 64-bit lanes compiled to 156 LOP3 + 27 register moves where
+// 122 LOP3 do -- theta's D = C[x-1] ^ rol(C[x+1], 1) is never formed: every lane takes A ^ C[x-1] ^ rol(C[x+1], 1) in ONE
+// LOP3 per half (the compiler, left alone, factors D out again), and halves that are not register pairs need no moves.
+#if ZKP_DEVICE_ASM
+ZKP_DEV uint32_t kx3(uint32_t a, uint32_t b, uint32_t c) {      // a ^ b ^ c
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+ZKP_DEV uint32_t kchi(uint32_t a, uint32_t b, uint32_t c) {     // a ^ (~b & c)
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0xD2;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+ZKP_DEV uint32_t kfsl(uint32_t lo, uint32_t hi, int s) { return __funnelshift_l(lo, hi, s); }   // high word of (hi:lo) << s
+#else
+ZKP_DEV uint32_t kx3(uint32_t a, uint32_t b, uint32_t c) { return a ^ b ^ c; }
+ZKP_DEV uint32_t kchi(uint32_t a, uint32_t b, uint32_t c) { return a ^ (~b & c); }
+ZKP_DEV uint32_t kfsl(uint32_t lo, uint32_t hi, int s) { return (hi << s) | (lo >> (32 - s)); }
+#endif
 
 ZKP_DEV void keccak_f1600_dev(uint64_t* a) {
   const uint64_t RC[24] = {
@@ -22,41 +43,56 @@ ZKP_DEV void keccak_f1600_dev(uint64_t* a) {
       0x0000000080008009ULL, 0x000000008000000AULL, 0x000000008000808BULL, 0x800000000000008BULL, 0x8000000000008089ULL,
       0x8000000000008003ULL, 0x8000000000008002ULL, 0x8000000000000080ULL, 0x000000000000800AULL, 0x800000008000000AULL,
       0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
-  uint64_t a00 = a[0], a10 = a[1], a20 = a[2], a30 = a[3], a40 = a[4];
-  uint64_t a01 = a[5], a11 = a[6], a21 = a[7], a31 = a[8], a41 = a[9];
-  uint64_t a02 = a[10], a12 = a[11], a22 = a[12], a32 = a[13], a42 = a[14];
-  uint64_t a03 = a[15], a13 = a[16], a23 = a[17], a33 = a[18], a43 = a[19];
-  uint64_t a04 = a[20], a14 = a[21], a24 = a[22], a34 = a[23], a44 = a[24];
+  // rho offsets of lane (x, y) at index x + 5 y; pi sends lane (x, y) to (y, 2x + 3y)
+  const int RHO[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};
+  uint32_t l[25], h[25];
+#pragma unroll
+  for (int i = 0; i < 25; i++) { l[i] = (uint32_t)a[i]; h[i] = (uint32_t)(a[i] >> 32); }
 #if ZKP_DEVICE_ASM
 #pragma unroll 1
 #endif
   for (int rnd = 0; rnd < 24; rnd++) {
-    uint64_t c0 = a00 ^ a01 ^ a02 ^ a03 ^ a04, c1 = a10 ^ a11 ^ a12 ^ a13 ^ a14, c2 = a20 ^ a21 ^ a22 ^ a23 ^ a24;
-    uint64_t c3 = a30 ^ a31 ^ a32 ^ a33 ^ a34, c4 = a40 ^ a41 ^ a42 ^ a43 ^ a44;
-    uint64_t d0 = c4 ^ rol64(c1, 1), d1 = c0 ^ rol64(c2, 1), d2 = c1 ^ rol64(c3, 1), d3 = c2 ^ rol64(c4, 1),
-             d4 = c3 ^ rol64(c0, 1);
-    uint64_t b00 = a00 ^ d0, b13 = rol64(a01 ^ d0, 36), b21 = rol64(a02 ^ d0, 3), b34 = rol64(a03 ^ d0, 41),
-             b42 = rol64(a04 ^ d0, 18);
-    uint64_t b02 = rol64(a10 ^ d1, 1), b10 = rol64(a11 ^ d1, 44), b23 = rol64(a12 ^ d1, 10), b31 = rol64(a13 ^ d1, 45),
-             b44 = rol64(a14 ^ d1, 2);
-    uint64_t b04 = rol64(a20 ^ d2, 62), b12 = rol64(a21 ^ d2, 6), b20 = rol64(a22 ^ d2, 43), b33 = rol64(a23 ^ d2, 15),
-             b41 = rol64(a24 ^ d2, 61);
-    uint64_t b01 = rol64(a30 ^ d3, 28), b14 = rol64(a31 ^ d3, 55), b22 = rol64(a32 ^ d3, 25), b30 = rol64(a33 ^ d3, 21),
-             b43 = rol64(a34 ^ d3, 56);
-    uint64_t b03 = rol64(a40 ^ d4, 27), b11 = rol64(a41 ^ d4, 20), b24 = rol64(a42 ^ d4, 39), b32 = rol64(a43 ^ d4, 8),
-             b40 = rol64(a44 ^ d4, 14);
-    a00 = b00 ^ (~b10 & b20); a10 = b10 ^ (~b20 & b30); a20 = b20 ^ (~b30 & b40); a30 = b30 ^ (~b40 & b00); a40 = b40 ^ (~b00 & b10);
-    a01 = b01 ^ (~b11 & b21); a11 = b11 ^ (~b21 & b31); a21 = b21 ^ (~b31 & b41); a31 = b31 ^ (~b41 & b01); a41 = b41 ^ (~b01 & b11);
-    a02 = b02 ^ (~b12 & b22); a12 = b12 ^ (~b22 & b32); a22 = b22 ^ (~b32 & b42); a32 = b32 ^ (~b42 & b02); a42 = b42 ^ (~b02 & b12);
-    a03 = b03 ^ (~b13 & b23); a13 = b13 ^ (~b23 & b33); a23 = b23 ^ (~b33 & b43); a33 = b33 ^ (~b43 & b03); a43 = b43 ^ (~b03 & b13);
-    a04 = b04 ^ (~b14 & b24); a14 = b14 ^ (~b24 & b34); a24 = b24 ^ (~b34 & b44); a34 = b34 ^ (~b44 & b04); a44 = b44 ^ (~b04 & b14);
-    a00 ^= RC[rnd];
+    uint32_t cl[5], ch[5], rl[5], rh[5], bl[25], bh[25];
+#pragma unroll
+    for (int x = 0; x < 5; x++) {
+      cl[x] = kx3(kx3(l[x], l[x + 5], l[x + 10]), l[x + 15], l[x + 20]);
+      ch[x] = kx3(kx3(h[x], h[x + 5], h[x + 10]), h[x + 15], h[x + 20]);
+    }
+#pragma unroll
+    for (int x = 0; x < 5; x++) {   // rol64(C[x], 1)
+      rl[x] = kfsl(ch[x], cl[x], 1);
+      rh[x] = kfsl(cl[x], ch[x], 1);
+    }
+#pragma unroll
+    for (int y = 0; y < 5; y++) {
+#pragma unroll
+      for (int x = 0; x < 5; x++) {
+        const int i = x + 5 * y, dst = y + 5 * ((2 * x + 3 * y) % 5), r = RHO[i];
+        const uint32_t tl = kx3(l[i], cl[(x + 4) % 5], rl[(x + 1) % 5]);
+        const uint32_t th = kx3(h[i], ch[(x + 4) % 5], rh[(x + 1) % 5]);
+        if (r == 0) {
+          bl[dst] = tl; bh[dst] = th;
+        } else if (r < 32) {
+          bl[dst] = kfsl(th, tl, r); bh[dst] = kfsl(tl, th, r);
+        } else {   // rotation by 32 + (r - 32): the halves trade places first (no lane rotates by exactly 32)
+          bl[dst] = kfsl(tl, th, r - 32); bh[dst] = kfsl(th, tl, r - 32);
+        }
+      }
+    }
+#pragma unroll
+    for (int y = 0; y < 5; y++) {
+#pragma unroll
+      for (int x = 0; x < 5; x++) {
+        const int i = x + 5 * y, i1 = (x + 1) % 5 + 5 * y, i2 = (x + 2) % 5 + 5 * y;
+        l[i] = kchi(bl[i], bl[i1], bl[i2]);
+        h[i] = kchi(bh[i], bh[i1], bh[i2]);
+      }
+    }
+    l[0] ^= (uint32_t)RC[rnd];
+    h[0] ^= (uint32_t)(RC[rnd] >> 32);
   }
-  a[0] = a00; a[1] = a10; a[2] = a20; a[3] = a30; a[4] = a40;
-  a[5] = a01; a[6] = a11; a[7] = a21; a[8] = a31; a[9] = a41;
-  a[10] = a02; a[11] = a12; a[12] = a22; a[13] = a32; a[14] = a42;
-  a[15] = a03; a[16] = a13; a[17] = a23; a[18] = a33; a[19] = a43;
-  a[20] = a04; a[21] = a14; a[22] = a24; a[23] = a34; a[24] = a44;
+#pragma unroll
+  for (int i = 0; i < 25; i++) a[i] = (uint64_t)l[i] | ((uint64_t)h[i] << 32);
 }
 
 // STROBE-128 state of one transcript: 200 state bytes as 25 lanes + (pos, pos_begin, cur_flags)
