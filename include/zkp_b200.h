@@ -60,9 +60,14 @@ int32_t zkp_ctx_set_stream(zkp_ctx* ctx, void* cuda_stream);
  * second stream concurrently with decompression; measured neutral), "chunk_terms" (terms per H2D chunk of the host-input MSM,
  * default 2^19), "dual_stream" (0/1, default 1: the chunk kernels alternate between two streams), "ramp_chunks" (0/1,
  * default 0: growing chunk sizes; measured slower), "phase1_percent" (share of the points decompressed under the digit
- * histogram, default 50), "bv_chunk_terms" (slab size of zkp_batch_verify_proofs, default 2^21), "fused_sort",
+ * histogram, default 50), "bv_chunk_terms" (slab size of zkp_batch_verify_proofs: 4 x this / rows proofs, default 2^19),
+ * "bv_phase1_rows" (rows of a slab decompressed under the histogram: 0 = chosen per slab from the arrival of the copies,
+ * default; n > 0 = fixed; -1 = alternating, for tests), "bv_prep_stream" (0/1, default 1: the front-end kernel of a slab as a
+ * resident grid on its own high-priority stream), "bv_prep_blocks" / "bv_prep_smem_kb" (that grid: blocks per SM, default 2,
+ * and the unused dynamic shared memory that caps its residency, default 64), "scatter_batch" (0/1, default 1), "fused_sort",
  * "balance", "ingest_variant", "bv_compiled", "share_static_tables", "prove_chunk", "coop_max_msms" (ablation
- * switches documented in DESIGN.md). */
+ * switches documented in DESIGN.md).  Environment: ZKP_BV_TIMELINE=1 makes zkp_batch_verify_proofs print, on stderr, when
+ * every copy, front-end kernel and ingestion launch of the call ended (timed CUDA events; a development aid). */
 int32_t zkp_ctx_set_option(zkp_ctx* ctx, const char* key, int64_t value);
 int32_t zkp_ctx_synchronize(zkp_ctx* ctx);
 const char* zkp_last_error(zkp_ctx* ctx);
