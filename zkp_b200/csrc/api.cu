@@ -1640,7 +1640,7 @@ static int32_t prove_slice_enqueue(zkp_ctx* ctx, pv_set& S, const zkp_statement_
   // in every proof (checked by k_pv_gather), so proof 0's are compressed and the others get copies
   if (p) {
     if (share) {
-      k_compress_limbs_shared<<<(unsigned)((N * p + 255) / 256), 256, 0, st>>>((const unsigned long long*)S.pv_limbs.p, N,
+      k_compress_limbs_shared<<<(unsigned)((N * ni + (size_t)nc + 255) / 256), 256, 0, st>>>((const unsigned long long*)S.pv_limbs.p, N,
                                                                                (uint32_t)p, (uint32_t)ni, (uint4*)S.pv_enc.p);
       LAUNCH_CHECK(ctx);
       k_replicate_common_enc<<<(unsigned)((N * (size_t)nc + 255) / 256), 256, 0, st>>>((uint4*)S.pv_enc.p, N, (uint32_t)p,
