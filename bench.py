@@ -221,6 +221,7 @@ def main():
     ap.add_argument("--no-numa-bind", action="store_true", help="tuning: do not pin ranks to their GPU's NUMA node")
     ap.add_argument("--bv-chunk-terms-log2", type=int, default=0, help="tuning: slab size (terms) of the from-proofs leg")
     ap.add_argument("--dual-stream", type=int, default=-1, help="tuning: chunk kernels of the e2e leg on two alternating streams (0/1)")
+    ap.add_argument("--accumulate-variant", type=int, default=0, help="tuning: occupancy point of k_accumulate (4, 5, 6 resident blocks)")
     ap.add_argument("--scatter-batch", type=int, default=-1, help="tuning: scatter phase with four cursor atomics in flight (0/1)")
     ap.add_argument("--bv-phase1-rows", type=int, default=0, help="tuning: rows decompressed in phase 1 of the from-proofs leg")
     ap.add_argument("--bv-prep-stream", type=int, default=-1, help="tuning: front-end kernel of the from-proofs leg on its own stream (0/1)")
@@ -342,6 +343,8 @@ def main():
         eng.set_option("dual_stream", args.dual_stream)
     if args.phase1_percent:
         eng.set_option("phase1_percent", args.phase1_percent)
+    if args.accumulate_variant:
+        eng.set_option("accumulate_variant", args.accumulate_variant)
     if args.scatter_batch >= 0:
         eng.set_option("scatter_batch", args.scatter_batch)
     if args.bv_phase1_rows:

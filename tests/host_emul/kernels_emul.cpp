@@ -280,7 +280,7 @@ void emul_msm_vartime(const uint8_t* scalars, const uint8_t* points, size_t n, i
     emul_launch(ib, 256, k_len_scatter, (const work_item*)items.data(), n_items, S, lh.data() + 2 * S + 3, order.data());
     ord = order.data();
   }
-  emul_launch(blocks, 128, k_accumulate, (const uint4*)niels.data(), (const uint32_t*)sorted.data(), (const work_item*)items.data(),
+  emul_launch(blocks, 128, k_accumulate<4>, (const uint4*)niels.data(), (const uint32_t*)sorted.data(), (const work_item*)items.data(),
               ord, n_items, n, buckets.data(), partials.data());
   emul_launch_mt(2, 128, k_merge, (const uint32_t*)aux1.data(), (const uint32_t*)(multi.data() + 4), (const uint32_t*)multi.data(),
                  (const uint4*)partials.data(), buckets.data());

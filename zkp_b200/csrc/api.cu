@@ -129,7 +129,8 @@ struct zkp_ctx {
   cudaStream_t prep_stream = nullptr;
   std::vector<cudaEvent_t> prep_ev, ing_ev;
   int bv_compiled = 1;      // batch-verification front end: host-compiled transcript script (k_bv_prepare2)
-  int ingest_variant = 2;   // occupancy point of k_ingest2 (kernels.cuh ZKP_INGEST_*)
+  int ingest_variant = 4;   // occupancy point of k_ingest2 (kernels.cuh ZKP_INGEST_*): 4 = 72 registers, 28 warps/SM; 2 = 80, 24
+  int accumulate_variant = 5;   // occupancy point of k_accumulate: 5 = 96 registers, 20 warps/SM, no prefetch; 4 = 122, 16, prefetch
   int scatter_batch = 1;    // k_ingest2, scatter phase: cursor atomics of four windows in flight together
   int fused_sort = 1;  // histogram and scatter ride under the two halves of the decompression (k_ingest2)
   // host-input pipeline: ramped chunk sizes (from chunk_terms / 8 up to 2 * chunk_terms, down again at the end of phase 1).
@@ -327,7 +328,7 @@ extern "C" int32_t zkp_ctx_set_option(zkp_ctx* ctx, const char* key, int64_t val
     if (!value && !ZKP_ABL(1)) return ZKP_ERR_SIZE;   // ablation: not in the product build
     ctx->bv_compiled = value ? 1 : 0;
   } else if (!strcmp(key, "ingest_variant")) {
-    if (value < 0 || value > 3) return ZKP_ERR_SIZE;
+    if (value < 0 || value > 5 || (!ZKP_ABL(1) && value != 2 && value != 4)) return ZKP_ERR_SIZE;
     ctx->ingest_variant = (int)value;
   } else if (!strcmp(key, "fused_sort")) {
     ctx->fused_sort = value ? 1 : 0;
@@ -342,6 +343,9 @@ extern "C" int32_t zkp_ctx_set_option(zkp_ctx* ctx, const char* key, int64_t val
   } else if (!strcmp(key, "bv_chunk_terms")) {
     if (value < 1024) return ZKP_ERR_SIZE;
     ctx->bv_chunk_terms = (size_t)value;
+  } else if (!strcmp(key, "accumulate_variant")) {
+    if (value < 4 || value > 5) return ZKP_ERR_SIZE;
+    ctx->accumulate_variant = (int)value;
   } else if (!strcmp(key, "scatter_batch")) {
     ctx->scatter_batch = value ? 1 : 0;
   } else if (!strcmp(key, "profile")) {
@@ -513,10 +517,14 @@ static int32_t launch_ingest2(zkp_ctx* ctx, const msm_plan& pl, const void* d_sc
       (const uint4*)d_points, (uint4*)ctx->niels.p, (const uint4*)d_scalars, a, n, pl.c, pl.W, pl.B,                        \
       MODE == 0 ? (uint32_t*)ctx->hist.p : (uint32_t*)ctx->cursor.p, (uint32_t*)ctx->sorted.p, (int*)ctx->flags.p)
   switch (ctx->ingest_variant) {
-    case 1: ZKP_LAUNCH_INGEST(1); break;
     case 2: ZKP_LAUNCH_INGEST(2); break;
+#ifdef ZKP_ABLATIONS   // the other occupancy points (measured: DESIGN.md section 4)
+    case 0: ZKP_LAUNCH_INGEST(0); break;
+    case 1: ZKP_LAUNCH_INGEST(1); break;
     case 3: ZKP_LAUNCH_INGEST(3); break;
-    default: ZKP_LAUNCH_INGEST(0); break;
+    case 5: ZKP_LAUNCH_INGEST(5); break;
+#endif
+    default: ZKP_LAUNCH_INGEST(4); break;
   }
 #undef ZKP_LAUNCH_INGEST
   LAUNCH_CHECK(ctx);
@@ -689,9 +697,15 @@ static int32_t msm_finish(zkp_ctx* ctx, const msm_plan& pl, const void* d_scalar
       order = (const uint32_t*)ctx->order.p;
     }
     if (ctx->live_valid) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_live[4], st));
-    k_accumulate<<<blocks, 128, 0, st>>>((const uint4*)ctx->niels.p, (const uint32_t*)ctx->sorted.p,
-                                         (const work_item*)ctx->items.p, order, n_items, n, (uint4*)ctx->buckets.p,
-                                         (uint4*)ctx->partials.p);
+#define ZKP_LAUNCH_ACC(MB)                                                                                       \
+  k_accumulate<MB><<<blocks, 128, 0, st>>>((const uint4*)ctx->niels.p, (const uint32_t*)ctx->sorted.p,           \
+                                           (const work_item*)ctx->items.p, order, n_items, n, (uint4*)ctx->buckets.p, \
+                                           (uint4*)ctx->partials.p)
+    switch (ctx->accumulate_variant) {
+      case 4: ZKP_LAUNCH_ACC(4); break;
+      default: ZKP_LAUNCH_ACC(5); break;
+    }
+#undef ZKP_LAUNCH_ACC
     LAUNCH_CHECK(ctx);
     if (ctx->live_valid) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_live[5], st));
     k_merge<<<148 * 8, 128, 0, st>>>((const uint32_t*)ctx->aux1.p, n_multi + 4, n_multi,

@@ -272,9 +272,12 @@ __device__ __forceinline__ void ingest_digits(const uint4* __restrict__ scalars,
 }
 
 // VAR picks the occupancy point (block size, minimum resident blocks): 0 = 256 threads, 106 registers, 16 warps/SM;
-// 1 = (128, 5): <= 96 registers, 20 warps/SM; 2 = (256, 3) and 3 = (128, 6): <= 80 registers, 24 warps/SM.
+// 1 = (128, 5): <= 96 registers, 20 warps/SM; 2 = (256, 3) and 3 = (128, 6): <= 80 registers, 24 warps/SM;
+// 4 = (128, 7): 72 registers, 28 warps/SM (default: the spills it adds, 180 bytes per thread, lie outside the squaring loops);
+// 5 = (128, 8): 64 registers, 32 warps/SM.  Measured, both ingestion launches of a step: 0: 91.0 ms (round 1 arithmetic),
+// 2: 85.8, 3: 85.7, 4: 84.2, 5: 84.2 ms.
 #define ZKP_INGEST_THREADS(VAR) ((VAR) == 0 || (VAR) == 2 ? 256 : 128)
-#define ZKP_INGEST_MINBLK(VAR) ((VAR) == 0 ? 1 : (VAR) == 1 ? 5 : (VAR) == 2 ? 3 : 6)
+#define ZKP_INGEST_MINBLK(VAR) ((VAR) == 0 ? 1 : (VAR) == 1 ? 5 : (VAR) == 2 ? 3 : (VAR) == 3 ? 6 : (VAR) == 4 ? 7 : 8)
 // One launch = up to three term ranges (A, B, C) and one point range; thread t takes the terms s_lo[j] + t (t < s_cnt[j])
 // and the point p_lo + t (t < p_cnt).  blockIdx.y = one of several equally shaped launches whose starts are y_p / y_s[j]
 // apart: the rows of a batch-verification slab go out as ONE grid (one partial last wave instead of one per row).
@@ -496,7 +499,11 @@ __global__ void __launch_bounds__(256) k_len_scatter(const work_item* __restrict
   order[base + __popc(peers & ((1u << lane) - 1u))] = id;
 }
 
-__global__ void __launch_bounds__(128, 4) k_accumulate(const uint4* __restrict__ niels, const uint32_t* __restrict__ sorted,
+// MB = minimum resident blocks per SM (the occupancy point).  4: 122 registers, 16 warps/SM, the next point's gather prefetched
+// in software (24 registers); 5 (default): 96 registers, 20 warps/SM, no prefetch -- the fifth warp per scheduler hides the gather
+// better than the prefetch did: 35.9 -> 35.3 ms at the bench size (6 = 80 registers needs spills inside the loop: 35.9 ms).
+template <int MB>
+__global__ void __launch_bounds__(128, MB) k_accumulate(const uint4* __restrict__ niels, const uint32_t* __restrict__ sorted,
                                                        const work_item* __restrict__ items,
                                                        const uint32_t* __restrict__ order,
                                                        const uint32_t* __restrict__ n_items, size_t n,
@@ -510,6 +517,15 @@ __global__ void __launch_bounds__(128, 4) k_accumulate(const uint4* __restrict__
   ge_ext acc;
   ge_identity(acc);
   uint32_t i = start;
+  if (MB >= 5) {   // more resident warps instead of the software prefetch (its 24 registers)
+    while (i < end) {
+      const uint32_t e = __ldg(base + i);
+      ge_aniels q;
+      load_aniels(q, niels, e);
+      ge_madd_signed<true>(acc, acc, q, e >> 31);
+      i++;
+    }
+  } else {
   ge_aniels cur;
   uint32_t e_cur = 0;
   if (i < end) {
@@ -528,6 +544,7 @@ __global__ void __launch_bounds__(128, 4) k_accumulate(const uint4* __restrict__
     cur = nxt;
     e_cur = e_nxt;
     i = inext;
+  }
   }
   uint4* dst = (wflag >> 31) ? partials + (size_t)out * 8 : buckets + (size_t)out * 8;
   store_ext(dst, acc);
