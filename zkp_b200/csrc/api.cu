@@ -104,7 +104,10 @@ struct zkp_ctx {
   size_t prove_pipe_chunk = (size_t)1 << 14;
   pv_set pvs[2];
   int coop_max_msms = 8192;  // batched small vartime MSMs: up to this many run with four lanes per MSM (latency)
-  int phase1_percent = 50;   // share of the host-path point chunks decompressed under the histogram (first phase)
+  // share of the host-path point chunks decompressed under the histogram (first phase).  Phase 1 also moves all the scalars, so
+  // at 55 GB/s it is copy-bound: a point more in it costs 0.58 ns of copy and saves 1.67 ns of phase 2, until the kernels of
+  // phase 1 catch up with its copies.  Measured e2e at the bench size: 50 % 125.9 ms, 52 % 125.5, 54 % 125.1, 56 % 125.9, 58 % 126.6
+  int phase1_percent = 54;
   int share_static_tables = 1;   // batch proving: one constant-time table per batch-static point
   // batch proving: signed four-tooth combs, one per base (comb.cuh): 64 doublings per constraint MSM instead of 256.
   // 0 = Straus tables (k_small_msm_ct), 1 = combs scanned from global memory (k_small_msm_comb), 2 = combs staged in
@@ -1350,14 +1353,16 @@ static int32_t batch_verify_proofs_impl(zkp_ctx* ctx, const zkp_statement_desc* 
   bv_timeline tl;
   tl.mark("start", 0, st);
   // Rows of a slab decompressed during phase 1 (under the histogram of all its rows, as the proofs arrive); the others follow
-  // in phase 2 under the scatter.  The split is chosen PER SLAB: when a slab arrives and the GPU has already finished the
-  // previous one, the pipeline is waiting for the host link (several GPUs sharing one host's memory bandwidth), and the slab
-  // is decompressed whole, there and then -- time that would otherwise be idle; its digits are scattered on their own in
-  // phase 2.  Otherwise (the GPU is the bottleneck, every order costs the same) half of the rows go to each phase, the split
-  // under which neither the histogram nor the scatter costs a pass.  bv_phase1_rows > 0 fixes the split for every slab;
-  // -1 alternates between the two choices (tests).
-  const size_t R_half = rows / 2, R_all = rows;
+  // in phase 2 under the scatter.  The split is chosen PER SLAB.  Half of the rows per phase is the split under which neither
+  // the histogram nor the scatter costs a pass, and it is right while the GPU is the bottleneck (every order costs the same).
+  // When a slab lands and the GPU has already finished the previous one, the pipeline is waiting for the host link (several
+  // GPUs sharing one host's memory bandwidth): the split moves one step towards phase 1 -- two thirds of the rows (the scatter
+  // of all rows still hides under the last third: three term ranges per thread), then all of them (the slab's digits are then
+  // scattered on their own in phase 2) -- and one step back whenever a slab finds the GPU still busy.  bv_phase1_rows > 0
+  // fixes the split for every slab; -1 alternates between half and all (tests).
+  const size_t R_half = rows / 2, R_23 = rows - (rows + 2) / 3, R_all = rows;
   const bool adaptive = fused && ctx->bv_phase1_rows == 0 && nchunks > 1;
+  int level = 0;   // 0: half of the rows in phase 1; 1: two thirds (the scatter still hides under the last third); 2: all
   std::vector<size_t> r1_of(nchunks, R_half);
   if (ctx->bv_phase1_rows > 0)
     for (size_t c = 0; c < nchunks; c++) r1_of[c] = (size_t)ctx->bv_phase1_rows > rows ? rows : (size_t)ctx->bv_phase1_rows;
@@ -1420,7 +1425,9 @@ static int32_t batch_verify_proofs_impl(zkp_ctx* ctx, const zkp_statement_desc* 
     if (adaptive) {
       // the host follows the arrival of the slabs: was the GPU already done with the previous slab when this one landed?
       CUDA_TRY(ctx, cudaEventSynchronize(ctx->chunk_ev[cidx]));
-      if (cidx > 0 && cudaEventQuery(ctx->ing_ev[cidx - 1]) == cudaSuccess) r1_of[cidx] = R_all;
+      const bool idle = cidx > 0 && cudaEventQuery(ctx->ing_ev[cidx - 1]) == cudaSuccess;
+      level = idle ? (level < 2 ? level + 1 : 2) : (level > 0 ? level - 1 : 0);
+      r1_of[cidx] = level == 2 ? R_all : level == 1 ? R_23 : R_half;
     }
     const size_t R1 = r1_of[cidx];
     CUDA_TRY(ctx, cudaStreamWaitEvent(ps, ctx->chunk_ev[cidx], 0));
