@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(256) k_decompress(const uint4* __restrict__ en
 }
 
 // decompress to FieldElement51 limb form (zkp_decompress_batch)
-__global__ void __launch_bounds__(256) k_decompress_limbs(const uint4* __restrict__ enc, size_t n,
+__global__ void __launch_bounds__(256, 3) k_decompress_limbs(const uint4* __restrict__ enc, size_t n,
                                                           unsigned long long* __restrict__ limbs,
                                                           uint8_t* __restrict__ valid) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

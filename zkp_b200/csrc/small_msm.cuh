@@ -21,7 +21,7 @@ namespace zkp {
 
 // decompress to affine Niels; an invalid encoding is marked by an all-zero first element (y+x is never 0 on
 // the curve)
-__global__ void __launch_bounds__(256) k_decompress_valid(const uint4* __restrict__ enc, size_t n,
+__global__ void __launch_bounds__(256, 3) k_decompress_valid(const uint4* __restrict__ enc, size_t n,
                                                           uint4* __restrict__ niels) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
