@@ -501,7 +501,8 @@ __global__ void __launch_bounds__(256) k_len_scatter(const work_item* __restrict
 
 // MB = minimum resident blocks per SM (the occupancy point).  4: 122 registers, 16 warps/SM, the next point's gather prefetched
 // in software (24 registers); 5 (default): 96 registers, 20 warps/SM, no prefetch -- the fifth warp per scheduler hides the gather
-// better than the prefetch did: 35.9 -> 35.3 ms at the bench size (6 = 80 registers needs spills inside the loop: 35.9 ms).
+// better than the prefetch did: 35.9 -> 35.3 ms at the bench size (6 = 80 registers needs spills inside the loop: 35.9 ms;
+// asking for the next point's line with prefetch.global.L2 / .L1, no register held: 39.5 ms -- session 29).
 template <int MB>
 __global__ void __launch_bounds__(128, MB) k_accumulate(const uint4* __restrict__ niels, const uint32_t* __restrict__ sorted,
                                                        const work_item* __restrict__ items,
