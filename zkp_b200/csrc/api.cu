@@ -91,7 +91,9 @@ struct zkp_ctx {
   // plus one chunk's kernel after the ideal: small chunks, with their kernels alternating between two streams so that the
   // per-launch partial waves overlap.  Measured at the bench size (e2e per step): 2^21 on one stream 135.8 ms,
   // 2^20 on two 132.3 ms, 2^19 on two 130.6 ms (device-resident inputs: 129.5 ms)
-  size_t chunk_terms = (size_t)1 << 19;
+  // (round 2, with the faster ingestion kernel and 54 % of the points in phase 1: 2^19 125.5 ms, 2^18 124.2 ms, 2^17 125.3-125.8,
+  // 2^16 137.8 ms)
+  size_t chunk_terms = (size_t)1 << 18;
   size_t bv_chunk_terms = (size_t)1 << 19;   // the same for the slabs of zkp_batch_verify_proofs (x 4 / rows proofs per slab)
   // the digit sort (histogram, scan, scatter: L2-atomic bound) runs on a second, higher-priority stream
   // concurrently with decompression (integer-multiply bound); joined before bucket accumulation
