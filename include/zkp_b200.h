@@ -60,7 +60,7 @@ int32_t zkp_ctx_set_stream(zkp_ctx* ctx, void* cuda_stream);
  * second stream concurrently with decompression; measured neutral), "chunk_terms" (terms per H2D chunk of the host-input MSM,
  * default 2^18), "dual_stream" (0/1, default 1: the chunk kernels alternate between two streams), "ramp_chunks" (0/1,
  * default 0: growing chunk sizes; measured slower), "phase1_percent" (share of the points decompressed under the digit
- * histogram, default 54), "bv_chunk_terms" (slab size of zkp_batch_verify_proofs: 4 x this / rows proofs, default 2^19),
+ * histogram, default 54), "bv_chunk_terms" (slab size of zkp_batch_verify_proofs: 4 x this / rows proofs, default 3 * 2^17),
  * "bv_phase1_rows" (rows of a slab decompressed under the histogram: 0 = chosen per slab from the arrival of the copies,
  * default; n > 0 = fixed; -1 = alternating, for tests), "bv_prep_stream" (0/1, default 1: the front-end kernel of a slab as a
  * resident grid on its own high-priority stream), "bv_prep_blocks" / "bv_prep_smem_kb" (that grid: blocks per SM, default 2,

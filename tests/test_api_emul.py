@@ -372,5 +372,5 @@ def test_verify_from_proof_bytes_over_several_slabs_through_the_emulated_abi(api
             rc, a, _, _ = verify(tampered, want=False)
             assert (rc, a) == (0, 0), rows1
     finally:
-        for key, v in ((b"bv_chunk_terms", 1 << 19), (b"bv_phase1_rows", 0)):
+        for key, v in ((b"bv_chunk_terms", 3 << 17), (b"bv_phase1_rows", 0)):
             api.zkp_ctx_set_option(api.ctx, key, v)

@@ -276,7 +276,7 @@ def test_batch_verify_device_slab_pipeline_and_phase_splits(engine):
             with pytest.raises(PT.VerificationFailure):
                 st.batch_verify_device(engine, com, bad, b"CMZ", inst, comm, seed)
     finally:
-        for key, v in (("bv_chunk_terms", 1 << 21), ("bv_phase1_rows", 0), ("bv_prep_stream", 1), ("bv_prep_smem_kb", 64)):
+        for key, v in (("bv_chunk_terms", 3 << 17), ("bv_phase1_rows", 0), ("bv_prep_stream", 1), ("bv_prep_smem_kb", 64)):
             engine.set_option(key, v)
 
 

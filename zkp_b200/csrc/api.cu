@@ -94,7 +94,9 @@ struct zkp_ctx {
   // (round 2, with the faster ingestion kernel and 54 % of the points in phase 1: 2^19 125.5 ms, 2^18 124.2 ms, 2^17 125.3-125.8,
   // 2^16 137.8 ms)
   size_t chunk_terms = (size_t)1 << 18;
-  size_t bv_chunk_terms = (size_t)1 << 19;   // the same for the slabs of zkp_batch_verify_proofs (x 4 / rows proofs per slab)
+  // the same for the slabs of zkp_batch_verify_proofs (x 4 / rows proofs per slab: 65 536 CMZ proofs); measured at HEAD: 2^18
+  // 140.9 ms, 3 * 2^17 139.5, 2^19 140.3, 3 * 2^18 142.2 ms per 2^21 CMZ proofs
+  size_t bv_chunk_terms = (size_t)3 << 17;
   // the digit sort (histogram, scan, scatter: L2-atomic bound) runs on a second, higher-priority stream
   // concurrently with decompression (integer-multiply bound); joined before bucket accumulation
   int overlap = 0;   // measured: no gain on B200 (159.2 vs 159.9 ms per step), kept as an option
