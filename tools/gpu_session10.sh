@@ -1,5 +1,7 @@
 #!/bin/bash
 # round 2, GPU session 10: from-proofs path -- front-end kernel on its own high-priority stream next to the decompression,
+# (record of a measurement: options of this script that measured neutral or negative -- bv_merge_rows, l2_fetch, plan_overlap,
+# bv_carveout, accumulate variants 51 / 52 -- were removed from the library afterwards; DESIGN.md sections 4, 5b and 9 quote the results)
 # uneven split of the rows between the two ingestion phases (three term ranges per thread)
 set -u
 O=gpurun_out

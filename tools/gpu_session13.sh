@@ -1,5 +1,7 @@
 #!/bin/bash
 # round 2, GPU session 13: shifting digit extractor + batched scatter atomics in k_ingest2; L2 fetch granularity
+# (record of a measurement: options of this script that measured neutral or negative -- bv_merge_rows, l2_fetch, plan_overlap,
+# bv_carveout, accumulate variants 51 / 52 -- were removed from the library afterwards; DESIGN.md sections 4, 5b and 9 quote the results)
 set -u
 O=gpurun_out
 mkdir -p $O

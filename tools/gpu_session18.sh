@@ -1,5 +1,7 @@
 #!/bin/bash
 # round 2, GPU session 18: Keccak on 32-bit halves (122 LOP3 + 58 SHF per round), bucket work items planned under phase 2;
+# (record of a measurement: options of this script that measured neutral or negative -- bv_merge_rows, l2_fetch, plan_overlap,
+# bv_carveout, accumulate variants 51 / 52 -- were removed from the library afterwards; DESIGN.md sections 4, 5b and 9 quote the results)
 # compute-sanitizer memcheck over the kernels this round touched
 set -u
 O=gpurun_out

@@ -1,5 +1,7 @@
 #!/bin/bash
 # round 2, GPU session 29: k_accumulate<5> with the next point's line prefetched into L2 / L1 (no register held)
+# (record of a measurement: options of this script that measured neutral or negative -- bv_merge_rows, l2_fetch, plan_overlap,
+# bv_carveout, accumulate variants 51 / 52 -- were removed from the library afterwards; DESIGN.md sections 4, 5b and 9 quote the results)
 set -u
 O=gpurun_out
 for a in 5 51 52 5 51; do

@@ -1,5 +1,7 @@
 #!/bin/bash
 # round 2, GPU session 9: decoder's inverse square root started from v itself (2 S + 3 M fewer per point), slab rows of the
+# (record of a measurement: options of this script that measured neutral or negative -- bv_merge_rows, l2_fetch, plan_overlap,
+# bv_carveout, accumulate variants 51 / 52 -- were removed from the library afterwards; DESIGN.md sections 4, 5b and 9 quote the results)
 # from-proofs path as one 2-D launch (bv_merge_rows): whole GPU suite, field rates, full bench line, merge on/off
 set -u
 O=gpurun_out
