@@ -206,7 +206,7 @@ def test_group_and_codec(lib):
 def test_scalar_recode(lib):
     rnd = random.Random(3)
     L = R.L
-    for c in (4, 7, 8, 13, 16, 20, 23):
+    for c in (4, 7, 8, 13, 16, 19, 20, 23, 24):   # 19 = the bench's window; 24 = the widest the digit extractor takes
         W = -(-253 // c)
         cases = [0, 1, 2, L - 1, L - 2, L // 2, L // 2 + 1, L // 2 - 1, 2**128, 2**252 - 1, 2**252, L, L + 1, 2**256 - 1]
         cases += [rnd.randrange(L) for _ in range(100)] + [L - rnd.getrandbits(128) for _ in range(30)]
@@ -294,6 +294,35 @@ def test_field_ops_property_based(lib):
         assert int.from_bytes(r.raw, "little") % P == a * b % P
         lib.emul_fe64_sq(r, a.to_bytes(32, "little"), 3)
         assert int.from_bytes(r.raw, "little") % P == pow(a, 8, P)
+    check()
+
+
+def test_scalar_chains_property_based(lib):
+    """hypothesis over the operand space of the device scalar arithmetic (scl.cuh on the multiply-add chains of fe.cuh), biased
+    towards limb boundaries: the 128-bit-weight product and its short reduction, the full product, the wide reduction of
+    the challenge, addition and subtraction agree with big integers mod l."""
+    from hypothesis import given, settings, strategies as st_
+    L = R.L
+    limb = st_.one_of(st_.sampled_from([0, 1, 2, 2**28 - 1, 2**28, 2**31 - 1, 2**31, 2**32 - 2, 2**32 - 1, 0x5cf5d3ed, 0x14def9de]),
+                      st_.integers(0, 2**32 - 1))
+    w128 = st_.lists(limb, min_size=4, max_size=4).map(lambda ws: sum(w << (32 * i) for i, w in enumerate(ws)))
+    red = st_.lists(limb, min_size=8, max_size=8).map(lambda ws: sum(w << (32 * i) for i, w in enumerate(ws)) % L)
+    wide = st_.lists(limb, min_size=16, max_size=16).map(lambda ws: sum(w << (32 * i) for i, w in enumerate(ws)))
+    o = ctypes.create_string_buffer(32)
+
+    @settings(max_examples=400, deadline=None)
+    @given(w128, red, red, wide)
+    def check(a, b, c, w):
+        lib.emul_scl_mul_128(o, a.to_bytes(32, "little"), b.to_bytes(32, "little"))
+        assert int.from_bytes(o.raw, "little") == a * b % L
+        lib.emul_scl_mul(o, b.to_bytes(32, "little"), c.to_bytes(32, "little"))
+        assert int.from_bytes(o.raw, "little") == b * c % L
+        lib.emul_scl_add(o, b.to_bytes(32, "little"), c.to_bytes(32, "little"))
+        assert int.from_bytes(o.raw, "little") == (b + c) % L
+        lib.emul_scl_sub(o, b.to_bytes(32, "little"), c.to_bytes(32, "little"))
+        assert int.from_bytes(o.raw, "little") == (b - c) % L
+        lib.emul_scl_wide(o, w.to_bytes(64, "little"))
+        assert int.from_bytes(o.raw, "little") == w % L
     check()
 
 
